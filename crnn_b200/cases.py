@@ -1,0 +1,234 @@
+"""The reference scripts' `p2vec` maps (flat trainable vector p -> physical weights)
+and their Jacobians dW/dp (the seed matrix `crnn_loss_grad_batch` takes).
+
+In the Julia front end this part STAYS in Julia: `W = p2vec(p)` and
+`S = ForwardDiff.jacobian(p2vec_flat, p)`.  Here the same maps are written once
+over a tiny forward-mode dual array (`_D`) whose derivative conventions are
+ForwardDiff's: clamp passes derivative 1 on the closed interval, abs uses
+signbit (derivative +1 at +0).
+
+  case1      case1/case1.jl:72-78      (b0 = -10, :70)
+  case2      case2/case2.jl:91-99
+  case3      case3/case3.jl:42-53
+  robertson  robertson/rober_crnn.jl:85-96
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .model import CRNNModel, SolveOpts
+
+
+class _D:
+    """value [..] + jacobian [.., np] w.r.t. the flat parameter vector."""
+
+    def __init__(self, v, j):
+        self.v = np.asarray(v, dtype=np.float64)
+        self.j = np.asarray(j, dtype=np.float64)
+
+    @staticmethod
+    def seed(p):
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        return _D(p, np.eye(p.size))
+
+    def __getitem__(self, idx):
+        return _D(self.v[idx], self.j[idx])
+
+    def reshape_f(self, *shape):  # Julia reshape = column-major
+        n_p = self.j.shape[-1]
+        return _D(self.v.reshape(shape, order="F"), self.j.reshape(shape + (n_p,), order="F"))
+
+    def __mul__(self, o):
+        if isinstance(o, _D):
+            return _D(self.v * o.v, self.j * o.v[..., None] + o.j * self.v[..., None])
+        return _D(self.v * o, self.j * o)
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        if isinstance(o, _D):
+            return _D(self.v + o.v, self.j + o.j)
+        return _D(self.v + o, self.j)
+
+    def __neg__(self):
+        return _D(-self.v, -self.j)
+
+    def abs(self):
+        s = np.where(np.signbit(self.v), -1.0, 1.0)
+        return _D(self.v * s, self.j * s[..., None])
+
+    def clamp(self, lo, hi):
+        inside = (self.v >= lo) & (self.v <= hi)
+        return _D(np.clip(self.v, lo, hi), self.j * inside[..., None])
+
+    def pow10(self):
+        v = 10.0 ** self.v
+        return _D(v, self.j * (v * np.log(10.0))[..., None])
+
+    def broadcast_scalar(self, shape):
+        return _D(np.broadcast_to(self.v, shape), np.broadcast_to(self.j, shape + self.j.shape[-1:]))
+
+
+def _pack(w_in: _D, w_b: _D, w_out: _D):
+    """-> (w_in, w_b, w_out, dW_dp[n_w, np]) with rows [vec(w_in); w_b; vec(w_out)] col-major."""
+    n_p = w_b.j.shape[-1]
+    seed = np.concatenate([
+        w_in.j.reshape(-1, n_p, order="F"), w_b.j.reshape(-1, n_p), w_out.j.reshape(-1, n_p, order="F")], axis=0)
+    return w_in.v.copy(), w_b.v.copy(), w_out.v.copy(), np.asfortranarray(seed)
+
+
+def p2vec_case1(p, ns=5, nr=4, b0=-10.0):
+    """case1/case1.jl:70-78."""
+    d = _D.seed(p)
+    w_b = d[0:nr] + b0
+    w_out = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_in = (-w_out).clamp(0.0, 2.5)
+    return _pack(w_in, w_b, w_out)
+
+
+def p2vec_case2(p, ns=6, nr=3):
+    """case2/case2.jl:91-99; last row of w_in is the Arrhenius Ea row."""
+    d = _D.seed(p)
+    slope = d[nr * (ns + 2)] * 100.0
+    slope_v = slope.broadcast_scalar((nr,))
+    w_b = d[0:nr] * slope_v
+    w_out = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_in_Ea = (d[nr * (ns + 1):nr * (ns + 2)] * slope_v).abs()
+    w_in = (-w_out).clamp(0.0, 4.0)
+    w_in = _D(np.vstack([w_in.v, w_in_Ea.v[None, :]]), np.concatenate([w_in.j, w_in_Ea.j[None, :, :]], axis=0))
+    return _pack(w_in, w_b, w_out)
+
+
+def p2vec_case3(p, ns=9, nr=8):
+    """case3/case3.jl:42-53 (p[end] is unused by the weights)."""
+    d = _D.seed(p)
+    w_b = d[0:nr]
+    w_in_raw = d[nr * (ns + 1):nr * (2 * ns + 1)].reshape_f(ns, nr)
+    w_out_raw = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_out = (-w_in_raw) * w_out_raw.abs()
+    w_in = w_in_raw.clamp(0.0, 4.0)
+    return _pack(w_in, w_b, w_out)
+
+
+def p2vec_robertson(p, ns=3, nr=6):
+    """robertson/rober_crnn.jl:85-96."""
+    d = _D.seed(p)
+    slope = d[nr * (2 * ns + 1)].abs()
+    w_b = d[0:nr] * (slope * 10.0).broadcast_scalar((nr,))
+    w_in_raw = d[nr * (ns + 1):nr * (2 * ns + 1)].reshape_f(ns, nr)
+    w_out_raw = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_out = (-w_in_raw) * w_out_raw.pow10()
+    w_in = w_in_raw.clamp(0.0, 2.5)
+    return _pack(w_in, w_b, w_out)
+
+
+@dataclass
+class Case:
+    """Constants of one reference script."""
+    name: str
+    ns: int
+    nr: int
+    n_p: int
+    rhs_kind: int
+    lb: float
+    ub: float
+    alg: int
+    abstol: object
+    reltol: object
+    tspan: tuple
+    n_save: int
+    p2vec: object
+    pred_clamp: tuple
+    loss_kind: int
+    maxiters: int = 100000
+    log_saveat: bool = False
+
+    def saveat(self) -> np.ndarray:
+        if self.log_saveat:  # tsteps = 10 .^ range(0, 5, length=datasize), rober_crnn.jl:48
+            return 10.0 ** np.linspace(0.0, 5.0, self.n_save)
+        return np.linspace(self.tspan[0], self.tspan[1], self.n_save)
+
+    def model(self, p, out_scale=None):
+        w_in, w_b, w_out, seed = self.p2vec(p)
+        m = CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=self.rhs_kind, lb=self.lb, ub=self.ub,
+                      out_scale=out_scale)
+        return m, seed
+
+    def opts(self, **kw) -> SolveOpts:
+        base = dict(saveat=self.saveat(), t0=self.tspan[0], t1=self.tspan[1], alg=self.alg,
+                    abstol=self.abstol, reltol=self.reltol, maxiters=self.maxiters,
+                    pred_clamp=self.pred_clamp)
+        base.update(kw)
+        return SolveOpts(**base)
+
+
+INF = float("inf")
+
+# Tolerances: the scripts pass `atol=`/`rtol=`, which Julia-1.6-era OrdinaryDiffEq
+# silently ignored, so the effective tolerances are the defaults
+# abstol=1e-6 / reltol=1e-3.  `as_written` keeps the values in the scripts.
+CASES = {
+    "case1": Case("case1", 5, 4, 20, _abi.RHS_F0, 1e-5, 10.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
+                  (0.0, 40.0), 100, p2vec_case1, (-10.0, 10.0), _abi.LOSS_MAE_SCALED, maxiters=10000),
+    "case2": Case("case2", 6, 3, 25, _abi.RHS_F1, 1e-6, 10.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
+                  (0.0, 50.0), 50, p2vec_case2, (-10.0, 10.0), _abi.LOSS_MAE_SCALED),
+    "case3": Case("case3", 9, 8, 153, _abi.RHS_F0, 1e-5, 100.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
+                  (0.0, 10.0), 100, p2vec_case3, (1e-5, 100.0), _abi.LOSS_MAE_LOG),
+    "robertson": Case("robertson", 3, 6, 43, _abi.RHS_F0, 1e-8, INF, _abi.ALG_ROSENBROCK23,
+                      np.array([1e-6, 1e-8, 1e-6]), np.array([1e-3, 1e-3, 1e-3]),
+                      (0.0, 1e5), 40, p2vec_robertson, (-INF, INF), _abi.LOSS_MAE_SCALED,
+                      maxiters=10000, log_saveat=True),
+}
+AS_WRITTEN_TOL = {"case1": (1e-5, 1e-2), "case2": (1e-6, 1e-3), "case3": (1e-5, 1e-2)}
+
+
+# ---- generating ("true") mechanisms written as CRNNs, used to make synthetic targets ----
+
+def true_model_case2(lb=1e-30) -> CRNNModel:
+    """trueODEfunc + Arrhenius of case2/case2.jl:38-59 as an F1 CRNN."""
+    ns, nr = 6, 3
+    logA = np.array([18.60, 19.13, 7.93]); Ea = np.array([14.54, 14.42, 6.47])
+    w_in = np.zeros((ns + 1, nr)); w_out = np.zeros((ns, nr))
+    # r1 = k1*TG*ROH ; r2 = k2*DG*ROH ; r3 = k3*MG*ROH
+    w_in[[0, 1], 0] = 1; w_in[[2, 1], 1] = 1; w_in[[3, 1], 2] = 1
+    w_in[ns, :] = Ea
+    w_out[:, 0] = [-1, -1, 1, 0, 0, 1]
+    w_out[:, 1] = [0, -1, -1, 1, 0, 1]
+    w_out[:, 2] = [0, -1, 0, -1, 1, 1]
+    return CRNNModel(w_in=w_in, w_b=logA, w_out=w_out, rhs_kind=_abi.RHS_F1, lb=lb, ub=INF)
+
+
+def true_model_robertson(lb=1e-300) -> CRNNModel:
+    """trueODEfunc of robertson/rober_crnn.jl:52,56-63 as an F0 CRNN (no scaling)."""
+    k = np.array([4e-2, 3e7, 1e4])
+    w_in = np.zeros((3, 3)); w_out = np.zeros((3, 3))
+    w_in[0, 0] = 1; w_in[1, 1] = 2; w_in[[1, 2], 2] = 1
+    w_out[:, 0] = [-1, 1, 0]; w_out[:, 1] = [0, -1, 1]; w_out[:, 2] = [1, -1, 0]
+    return CRNNModel(w_in=w_in, w_b=np.log(k), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)
+
+
+def true_model_case1(lb=1e-30) -> CRNNModel:
+    """trueODEfunc of case1/case1.jl:27,38-44 as an F0 CRNN."""
+    k = np.array([0.1, 0.2, 0.13, 0.3])
+    w_in = np.zeros((5, 4)); w_out = np.zeros((5, 4))
+    w_in[0, 0] = 2; w_in[0, 1] = 1; w_in[2, 2] = 1; w_in[[1, 3], 3] = 1
+    w_out[:, 0] = [-2, 1, 0, 0, 0]; w_out[:, 1] = [-1, 0, 1, 0, 0]
+    w_out[:, 2] = [0, 0, -1, 1, 0]; w_out[:, 3] = [0, -1, 0, -1, 1]
+    return CRNNModel(w_in=w_in, w_b=np.log(k), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)
+
+
+def true_model_case3(lb=1e-30) -> CRNNModel:
+    """trueODEfunc of case3/case3.jl:83-103 (MAPK cascade, k = ones(8)) as an F0 CRNN."""
+    ns, nr = 9, 8
+    w_in = np.zeros((ns, nr)); w_out = np.zeros((ns, nr))
+    pairs = [(0, 1), (2, 3), (4, 5), (6, 7)]
+    for j, (a, b) in enumerate(pairs):          # r_{j+1} = y_a * y_b ; b -> b*
+        w_in[[a, b], j] = 1
+        w_out[b, j] = -1; w_out[b + 1, j] = 1
+    for j, a in enumerate([2, 4, 6, 8]):        # r_{5..8} = y_a ; a* -> a
+        w_in[a, 4 + j] = 1
+        w_out[a, 4 + j] = -1; w_out[a - 1, 4 + j] = 1
+    return CRNNModel(w_in=w_in, w_b=np.zeros(nr), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)

@@ -1,0 +1,138 @@
+"""Host-side descriptions of a CRNN model and of one `solve` call.
+
+`CRNNModel` is what the reference scripts' `p2vec` returns (w_in, w_b, w_out —
+column-major, e.g. case2/case2.jl:91-99) plus the constants their RHS closes
+over (lb, ub, dydt_scale / dy_std_, the gas constant).  `SolveOpts` is the
+keyword set of `ODEProblem(...)`/`solve(...)` (case2/case2.jl:121,126).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import CModel, COpts, _f64, dptr, iptr
+
+GAS_R = 1.98720425864083e-3  # case2/case2.jl:113
+
+
+@dataclass
+class CRNNModel:
+    w_in: np.ndarray          # [n_in, n_reac]
+    w_b: np.ndarray           # [n_reac]
+    w_out: np.ndarray         # [n_species, n_reac]
+    rhs_kind: int = _abi.RHS_F0
+    lb: float = 1e-5
+    ub: float = 10.0
+    out_scale: np.ndarray | None = None
+    gas_R: float = GAS_R
+
+    def __post_init__(self):
+        self.w_in = np.asarray(self.w_in, dtype=np.float64)
+        self.w_b = np.asarray(self.w_b, dtype=np.float64).reshape(-1)
+        self.w_out = np.asarray(self.w_out, dtype=np.float64)
+        if self.out_scale is not None:
+            self.out_scale = np.asarray(self.out_scale, dtype=np.float64).reshape(-1)
+        n_in, nr = self.w_in.shape
+        ns, nr2 = self.w_out.shape
+        if nr != nr2 or self.w_b.shape[0] != nr:
+            raise ValueError("w_in, w_b, w_out disagree on n_reac")
+        if self.rhs_kind == _abi.RHS_F0 and n_in != ns:
+            raise ValueError("F0 needs n_in == n_species")
+        if self.rhs_kind == _abi.RHS_F1 and n_in != ns + 1:
+            raise ValueError("F1 needs n_in == n_species + 1 (Arrhenius row)")
+        if self.out_scale is not None and self.out_scale.shape[0] != ns:
+            raise ValueError("out_scale must have n_species entries")
+
+    @property
+    def n_species(self) -> int:
+        return self.w_out.shape[0]
+
+    @property
+    def n_reac(self) -> int:
+        return self.w_out.shape[1]
+
+    @property
+    def n_in(self) -> int:
+        return self.w_in.shape[0]
+
+    @property
+    def n_state(self) -> int:
+        return self.n_species + (1 if self.rhs_kind == _abi.RHS_F1 else 0)
+
+    @property
+    def n_w(self) -> int:
+        return self.n_reac * (self.n_in + 1 + self.n_species)
+
+    def flat_weights(self) -> np.ndarray:
+        """[vec(w_in); w_b; vec(w_out)] column-major: the row order of dW_dp."""
+        return np.concatenate([self.w_in.reshape(-1, order="F"), self.w_b, self.w_out.reshape(-1, order="F")])
+
+    def to_c(self):
+        """Returns (CModel, keepalive)."""
+        keep = [
+            np.asfortranarray(self.w_in).reshape(-1, order="F").copy(),
+            _f64(self.w_b),
+            np.asfortranarray(self.w_out).reshape(-1, order="F").copy(),
+            None if self.out_scale is None else _f64(self.out_scale),
+        ]
+        m = CModel()
+        m.n_state, m.n_species, m.n_in, m.n_reac = self.n_state, self.n_species, self.n_in, self.n_reac
+        m.rhs_kind = self.rhs_kind
+        m.lb, m.ub, m.gas_R = float(self.lb), float(self.ub), float(self.gas_R)
+        m.w_in, m.w_b, m.w_out = dptr(keep[0]), dptr(keep[1]), dptr(keep[2])
+        m.out_scale = dptr(keep[3])
+        return m, keep
+
+
+@dataclass
+class SolveOpts:
+    saveat: np.ndarray
+    t0: float
+    t1: float
+    alg: int = _abi.ALG_TSIT5
+    abstol: float | np.ndarray = 1e-6   # OrdinaryDiffEq defaults (what `atol=`/`rtol=` silently fell back to)
+    reltol: float | np.ndarray = 1e-3
+    maxiters: int = 100000
+    obs_idx: np.ndarray | None = None   # default: every row of u
+    pred_clamp: tuple[float, float] = (-np.inf, np.inf)
+    sens_mode: int = _abi.SENS_FORWARD
+    err_norm_includes_sens: bool = True
+    controller: dict = field(default_factory=dict)  # qmin,qmax,gamma,beta1,beta2 overrides
+
+    def to_c(self, n_state: int, buffers_on_device: bool = False, stream: int = 0):
+        saveat = _f64(self.saveat).reshape(-1)
+        if saveat.size and (np.any(np.diff(saveat) < 0) or saveat[0] < self.t0 or saveat[-1] > self.t1):
+            raise ValueError("saveat must be ascending and inside [t0, t1]")
+        abstol = _f64(np.atleast_1d(self.abstol))
+        reltol = _f64(np.atleast_1d(self.reltol))
+        for name, a in (("abstol", abstol), ("reltol", reltol)):
+            if a.size not in (1, n_state):
+                raise ValueError(f"{name} must have 1 or n_state entries")
+        obs = np.arange(n_state, dtype=np.int32) if self.obs_idx is None else \
+            np.ascontiguousarray(np.asarray(self.obs_idx, dtype=np.int32))
+        if obs.size and (obs.min() < 0 or obs.max() >= n_state):
+            raise ValueError("obs_idx out of range")
+        o = COpts()
+        o.alg, o.sens_mode = int(self.alg), int(self.sens_mode)
+        o.err_norm_includes_sens = int(bool(self.err_norm_includes_sens))
+        o.n_save, o.n_obs = saveat.size, obs.size
+        o.n_abstol, o.n_reltol = abstol.size, reltol.size
+        o.buffers_on_device = int(buffers_on_device)
+        o.maxiters = int(self.maxiters)
+        o.t0, o.t1 = float(self.t0), float(self.t1)
+        o.pred_clamp_lo, o.pred_clamp_hi = float(self.pred_clamp[0]), float(self.pred_clamp[1])
+        o.abstol, o.reltol, o.saveat, o.obs_idx = dptr(abstol), dptr(reltol), dptr(saveat), iptr(obs)
+        for k in ("qmin", "qmax", "gamma", "beta1", "beta2"):
+            setattr(o, k, float(self.controller.get(k, 0.0)))
+        o.stream = C.c_void_p(stream)
+        return o, [saveat, abstol, reltol, obs]
+
+    @property
+    def n_save(self) -> int:
+        return int(np.asarray(self.saveat).size)
+
+    def n_obs(self, n_state: int) -> int:
+        return n_state if self.obs_idx is None else int(np.asarray(self.obs_idx).size)

@@ -1,0 +1,173 @@
+/* crnn_b200.h — C-ABI of the B200-native batched CRNN neural-ODE engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of DENG-MIT/CRNN: the
+ * `solve(...)` call inside `predict_neuralode` and the
+ * `ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` call in the training
+ * loop.  The reference has no FFI of its own (it is 22 Julia scripts over
+ * un-vendored SciML packages), so every entry point below cites the reference
+ * call site it replaces (paths relative to the reference tree):
+ *
+ *   crnn_solve_batch       <- predict_neuralode: case1/case1.jl:92-97,
+ *                             case2/case2.jl:124-128, case3/case3.jl:172-176,
+ *                             robertson/rober_crnn.jl:123-136
+ *   crnn_loss_grad_batch   <- ForwardDiff.gradient(loss_neuralode):
+ *                             case2/case2.jl:132-137,195;
+ *                             robertson/rober_crnn.jl:139-144,219;
+ *                             Zygote.forwarddiff: case1/case1.jl:195-199,
+ *                             case3/case3.jl:265-270
+ *
+ * Plain C: pointers and sizes only.  All matrices are COLUMN-MAJOR (Julia
+ * layout), exactly what the scripts' `p2vec` returns.  Batched buffers are
+ * laid out trajectory-slowest:  u0[n_state, N], data[n_obs, n_save, N],
+ * pred[n_obs, n_save, N].
+ *
+ * Ownership: the caller owns every buffer.  With opts.buffers_on_device == 0
+ * the batched buffers are host memory and the library does the H2D/D2H copies
+ * itself (synchronous call).  With buffers_on_device == 1 they are device
+ * pointers on the handle's device and the call only enqueues work on
+ * opts.stream (a cudaStream_t; NULL = legacy default stream); the small
+ * model/option arrays (weights, tolerances, saveat, obs_idx, seed) are always
+ * host memory.
+ *
+ * Errors: 0 on success, a negative crnn_status otherwise (message through
+ * crnn_last_error).  Solver outcomes are PER TRAJECTORY in retcode[] (values
+ * mirror SciMLBase.ReturnCode, which robertson/rober_crnn.jl:130 tests), and
+ * n_saved[i] says how many save columns of trajectory i are valid (the
+ * reference tolerates truncated solutions: robertson/rober_crnn.jl:141).
+ * A batch never aborts because one trajectory failed.
+ */
+#ifndef CRNN_B200_H
+#define CRNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRNN_B200_VERSION 100 /* 0.1.0 */
+
+typedef struct crnn_handle crnn_handle;
+
+enum crnn_status {
+  CRNN_OK = 0,
+  CRNN_ERR_BAD_ARG = -1,
+  CRNN_ERR_CUDA = -2,
+  CRNN_ERR_UNSUPPORTED = -3,
+  CRNN_ERR_NO_DEVICE = -4
+};
+
+/* RHS flavours. */
+enum crnn_rhs_kind {
+  CRNN_RHS_F0 = 0, /* du = s .* W_out*exp(W_in'*log(clamp(u,lb,ub)) + b): case1.jl:80-83, case3.jl:162-166, rober_crnn.jl:113-116 */
+  CRNN_RHS_F1_ARRH_TSTATE = 1 /* state [X;T], x=[log clamp X; -1/(R T)], dT/dt=0: case2.jl:113-118 */
+};
+
+enum crnn_alg {
+  CRNN_ALG_TSIT5 = 0,        /* case1.jl:28, case3.jl:29, non-stiff half of case2.jl:26 */
+  CRNN_ALG_ROSENBROCK23 = 1, /* rober_crnn.jl:33 */
+  CRNN_ALG_KENCARP4 = 2      /* BASELINE config 5 (not in the reference) */
+};
+
+enum crnn_sens_mode {
+  CRNN_SENS_NONE = 0,
+  CRNN_SENS_FORWARD = 1,       /* duals-through-the-solver semantics: case2.jl:195 */
+  CRNN_SENS_INTERP_ADJOINT = 2 /* BASELINE config 4 (not in the reference) */
+};
+
+enum crnn_loss_kind {
+  CRNN_LOSS_MAE_SCALED = 0, /* mean|d/ys - clamp(pred)/ys|: case2.jl:132-137, rober_crnn.jl:139-144 */
+  CRNN_LOSS_MAE_LOG = 1     /* mean|log clamp d - log clamp pred|: case3.jl:183-190 */
+};
+
+/* Per-trajectory return codes (SciMLBase.ReturnCode values). */
+enum crnn_retcode {
+  CRNN_RET_DEFAULT = 0,
+  CRNN_RET_SUCCESS = 1,
+  CRNN_RET_DTNAN = 3,
+  CRNN_RET_MAXITERS = 4,
+  CRNN_RET_DTLESSTHANMIN = 5,
+  CRNN_RET_UNSTABLE = 6
+};
+
+/* Physical CRNN weights, exactly what the scripts' p2vec returns. */
+typedef struct crnn_model {
+  int32_t n_state;   /* length of u (F1: n_species + 1) */
+  int32_t n_species; /* rows of w_out */
+  int32_t n_in;      /* rows of w_in (== n_state for F0 and F1) */
+  int32_t n_reac;    /* columns of w_in / w_out */
+  int32_t rhs_kind;  /* crnn_rhs_kind */
+  int32_t reserved0;
+  double lb, ub;     /* clamp bounds inside the RHS; ub may be +Inf (rober_crnn.jl:114) */
+  double gas_R;      /* F1 only: 1.98720425864083e-3 (case2.jl:113) */
+  const double* out_scale; /* [n_species] or NULL: dy_std_ (case3.jl:165), dydt_scale (rober_crnn.jl:115) */
+  const double* w_in;      /* [n_in x n_reac] col-major */
+  const double* w_b;       /* [n_reac] */
+  const double* w_out;     /* [n_species x n_reac] col-major */
+} crnn_model;
+
+typedef struct crnn_opts {
+  int32_t alg;                    /* crnn_alg */
+  int32_t sens_mode;              /* crnn_sens_mode (loss_grad only) */
+  int32_t err_norm_includes_sens; /* 1: dual partials take part in step-size control (DiffEqBase norm over Duals) */
+  int32_t n_save;                 /* length of saveat */
+  int32_t n_obs;                  /* length of obs_idx */
+  int32_t n_abstol;               /* 1 or n_state (rober_crnn.jl:34 writes a vector) */
+  int32_t n_reltol;               /* 1 or n_state */
+  int32_t buffers_on_device;      /* 0: batched buffers are host memory; 1: device pointers */
+  int64_t maxiters;               /* accepted+rejected step cap (case1.jl:32, rober_crnn.jl:30) */
+  double t0, t1;                  /* tspan */
+  double pred_clamp_lo, pred_clamp_hi; /* clamp applied to saved states: (-ub,ub) case2.jl:126, (lb,ub) case3.jl:174, (-Inf,Inf) robertson */
+  const double* abstol;
+  const double* reltol;
+  const double* saveat;           /* [n_save], ascending, inside [t0,t1] */
+  const int32_t* obs_idx;         /* [n_obs] 0-based rows of u that are observed (case2.jl:131) */
+  double qmin, qmax, gamma, beta1, beta2; /* step controller; <= 0 selects the OrdinaryDiffEq defaults */
+  void* stream;                   /* cudaStream_t, used when buffers_on_device == 1 */
+} crnn_opts;
+
+typedef struct crnn_stats {
+  int32_t n_accept, n_reject, n_rhs, n_jac;
+  double t_reached, dt_last;
+} crnn_stats;
+
+/* device_id < 0 selects the current CUDA device.  Fails with
+ * CRNN_ERR_NO_DEVICE when no CUDA device is usable: there is NO CPU fallback. */
+int crnn_create(crnn_handle** h, int device_id);
+void crnn_destroy(crnn_handle* h);
+const char* crnn_last_error(const crnn_handle* h);
+int crnn_version(void);
+/* Number of CUDA kernels this handle has launched since creation. */
+int64_t crnn_launch_count(const crnn_handle* h);
+
+/* predict_neuralode for a batch of N initial conditions.
+ *   u0      [n_state, N]
+ *   n_save_used [N] or NULL: trajectory i integrates only to
+ *           saveat[n_save_used[i]-1] (random time truncation, rober_crnn.jl:218)
+ *   pred    [n_obs, n_save, N]  clamped saved states (columns >= n_saved[i] are left zero)
+ *   n_saved [N], retcode [N], stats [N] or NULL                              */
+int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
+                     const double* u0, int64_t N, const int32_t* n_save_used,
+                     double* pred, int32_t* n_saved, int32_t* retcode,
+                     crnn_stats* stats);
+
+/* loss_neuralode + its gradient for a batch.
+ *   dW_dp   [n_w, np] col-major HOST seed matrix = Jacobian of p2vec, with the
+ *           n_w = n_reac*(n_in + 1 + n_species) rows ordered
+ *           [vec(w_in); w_b; vec(w_out)]
+ *   data    [n_obs, n_save, N], yscale [n_obs] (host; ignored for MAE_LOG)
+ *   loss    [N] per-trajectory loss (NaN when a trajectory saved nothing)
+ *   grad_sum[np] (HOST, always) sum over trajectories of d loss_i / d p,
+ *           accumulated in a fixed order (deterministic)
+ *   pred    may be NULL                                                     */
+int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
+                         const double* dW_dp, int32_t np,
+                         const double* u0, int64_t N, const int32_t* n_save_used,
+                         const double* data, const double* yscale, int32_t loss_kind,
+                         double* loss, double* grad_sum, double* pred,
+                         int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRNN_B200_H */

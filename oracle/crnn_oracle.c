@@ -1,0 +1,624 @@
+/* crnn_oracle.c — CPU restatement of the CRNN solve + sensitivity + loss path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (crnn_b200/, the C-ABI
+ * library) may import, link or execute this file; only tests/, the smoke check
+ * and bench.py's cpu_baseline / --impl reference legs use it, as the checker
+ * and as the timed CPU baseline.
+ *
+ * PARITY UNPINNED for the solver semantics: the reference (DENG-MIT/CRNN) is a
+ * set of Julia scripts whose arithmetic lives in un-vendored packages
+ * (OrdinaryDiffEq / ForwardDiff / Flux; versions pinned only for the Cathode
+ * sub-projects: OrdinaryDiffEq 6.102.1, OrdinaryDiffEqTsit5 1.5.0,
+ * OrdinaryDiffEqRosenbrock 1.18.0, ForwardDiff 1.2.1 — Cathode/Manifest.toml),
+ * Julia is not installed here, and the reference ships no tests or golden
+ * trajectories.  What IS in the reference tree is restated literally and
+ * pinned against the committed checkpoints (tests/golden): the RHS, p2vec and
+ * the loss.  The stepper/controller/interpolant follow the published
+ * algorithms (Tsitouras 2011; Shampine & Reichelt ode23s; Hairer-Wanner
+ * initial step; OrdinaryDiffEq's PI controller defaults) and are validated
+ * against scipy Radau at 1e-12 and finite differences in tests/.
+ *
+ * Each function cites the reference file:line it follows (paths relative to
+ * the reference tree) or the SURVEY.md appendix that specifies it.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/crnn_b200.h"
+
+#define MAXN 64 /* max n_state */
+#define MAXR 64 /* max n_reac  */
+
+typedef struct {
+  const crnn_model* m;
+  const crnn_opts* o;
+  int n, ns, nin, nr;
+  int ncol; /* 1 + np when forward sensitivities are carried */
+  int nw;
+  const double* seed; /* [nw, np] col-major */
+  double qmin, qmax, gamma, beta1, beta2;
+  int order;
+} ctx_t;
+
+typedef struct {
+  double x[MAXN], dx[MAXN], d2x[MAXN], r[MAXR];
+} rhs_cache;
+
+static inline double clampd(double v, double lo, double hi) {
+  /* Julia Base.clamp: ifelse(x > hi, hi, ifelse(x < lo, lo, x)) */
+  return v > hi ? hi : (v < lo ? lo : v);
+}
+
+/* RHS value.  F0: case1/case1.jl:80-83, case3/case3.jl:162-166,
+ * robertson/rober_crnn.jl:113-116.  F1: case2/case2.jl:113-118.
+ * Also returns x = W_in-side inputs, dx = dx_i/du_i, d2x, r = exp(z). */
+static void rhs_value(const ctx_t* c, const double* u, double* du, rhs_cache* k) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  for (int i = 0; i < ns; ++i) {
+    double uc = clampd(u[i], m->lb, m->ub);
+    int inside = (u[i] >= m->lb) && (u[i] <= m->ub); /* dual clamp passes derivative 1 on the closed interval */
+    k->x[i] = log(uc);
+    k->dx[i] = inside ? 1.0 / uc : 0.0;
+    k->d2x[i] = inside ? -1.0 / (uc * uc) : 0.0;
+  }
+  if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE) {
+    double T = u[ns];
+    k->x[ns] = -1.0 / (m->gas_R * T); /* inv_R / u[end], case2.jl:113,116 */
+    k->dx[ns] = 1.0 / (m->gas_R * T * T);
+    k->d2x[ns] = -2.0 / (m->gas_R * T * T * T);
+  }
+  for (int j = 0; j < nr; ++j) {
+    double z = m->w_b[j];
+    for (int i = 0; i < nin; ++i) z += m->w_in[i + nin * j] * k->x[i];
+    k->r[j] = exp(z);
+  }
+  for (int i = 0; i < ns; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * k->r[j];
+    du[i] = m->out_scale ? s * m->out_scale[i] : s;
+  }
+  for (int i = ns; i < c->n; ++i) du[i] = 0.0; /* vcat(..., 0.f0), case2.jl:117 */
+}
+
+/* Directional derivative of f along (S for u, seed column for the weights):
+ * what ForwardDiff duals compute when pushed through crnn. */
+static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
+                         const double* sd /* seed column or NULL */, double* dS) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  double zq[MAXR];
+  for (int j = 0; j < nr; ++j) {
+    double zd = 0.0;
+    for (int i = 0; i < nin; ++i) zd += m->w_in[i + nin * j] * (S[i] * k->dx[i]);
+    if (sd) {
+      for (int i = 0; i < nin; ++i) zd += sd[i + nin * j] * k->x[i];
+      zd += sd[nin * nr + j];
+    }
+    zq[j] = k->r[j] * zd;
+  }
+  for (int i = 0; i < ns; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * zq[j];
+    if (sd)
+      for (int j = 0; j < nr; ++j) s += sd[nin * nr + nr + i + ns * j] * k->r[j];
+    dS[i] = m->out_scale ? s * m->out_scale[i] : s;
+  }
+  for (int i = ns; i < c->n; ++i) dS[i] = 0.0;
+}
+
+/* f on all columns: Y[col][n] -> dY[col][n]; col 0 is the value. */
+static void eval_cols(const ctx_t* c, const double* Y, double* dY, rhs_cache* k) {
+  int n = c->n;
+  rhs_value(c, Y, dY, k);
+  for (int col = 1; col < c->ncol; ++col)
+    rhs_sens_col(c, k, Y + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, dY + col * n);
+}
+
+/* Analytic Jacobian, row-major J[i*n+l] = d f_i / d u_l. */
+static void jac_value(const ctx_t* c, const rhs_cache* k, double* J) {
+  const crnn_model* m = c->m;
+  int n = c->n, ns = c->ns, nin = c->nin, nr = c->nr;
+  memset(J, 0, sizeof(double) * n * n);
+  for (int i = 0; i < ns; ++i)
+    for (int l = 0; l < nin; ++l) {
+      double s = 0.0;
+      for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * k->r[j] * m->w_in[l + nin * j];
+      s *= k->dx[l];
+      J[i * n + l] = m->out_scale ? s * m->out_scale[i] : s;
+    }
+}
+
+/* J*v at cached point. */
+static void jac_vec(const ctx_t* c, const rhs_cache* k, const double* v, double* out) {
+  rhs_sens_col(c, k, v, NULL, out);
+}
+
+/* d/d eps [ J(u + eps S, W + eps dW) v ] with v fixed: the partials a nested
+ * dual Jacobian carries (Rosenbrock23(autodiff=true) under ForwardDiff.gradient,
+ * robertson/rober_crnn.jl:33,219).  SURVEY §7.3 "Rosenbrock sensitivities". */
+static void djac_vec(const ctx_t* c, const rhs_cache* k, const double* S, const double* sd,
+                     const double* v, double* out) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  double q1[MAXR], q2[MAXR]; /* q1 = r.*a ; q2 = r.*(zd.*a + ad) */
+  for (int j = 0; j < nr; ++j) {
+    double a = 0.0, zd = 0.0, ad = 0.0;
+    for (int i = 0; i < nin; ++i) {
+      double w = m->w_in[i + nin * j];
+      a += w * (v[i] * k->dx[i]);
+      zd += w * (S[i] * k->dx[i]);
+      ad += w * (v[i] * k->d2x[i] * S[i]);
+    }
+    if (sd) {
+      for (int i = 0; i < nin; ++i) {
+        zd += sd[i + nin * j] * k->x[i];
+        ad += sd[i + nin * j] * (v[i] * k->dx[i]);
+      }
+      zd += sd[nin * nr + j];
+    }
+    q1[j] = k->r[j] * a;
+    q2[j] = k->r[j] * (zd * a + ad);
+  }
+  for (int i = 0; i < ns; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * q2[j];
+    if (sd)
+      for (int j = 0; j < nr; ++j) s += sd[nin * nr + nr + i + ns * j] * q1[j];
+    out[i] = m->out_scale ? s * m->out_scale[i] : s;
+  }
+  for (int i = ns; i < c->n; ++i) out[i] = 0.0;
+}
+
+/* DiffEqBase norm over (dual) arrays: sse(dual) = value^2 + sum(partials^2),
+ * calculate_residuals scale uses the dual magnitude. */
+static double err_norm(const ctx_t* c, const double* E, const double* U0, const double* U1) {
+  int n = c->n;
+  int nc = c->o->err_norm_includes_sens ? c->ncol : 1;
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double e2 = 0.0, a2 = 0.0, b2 = 0.0;
+    for (int col = 0; col < nc; ++col) {
+      double e = E[col * n + i], a = U0[col * n + i], b = U1[col * n + i];
+      e2 += e * e; a2 += a * a; b2 += b * b;
+    }
+    double mag = fmax(sqrt(a2), sqrt(b2));
+    double at = c->o->abstol[c->o->n_abstol > 1 ? i : 0];
+    double rt = c->o->reltol[c->o->n_reltol > 1 ? i : 0];
+    double sc = at + mag * rt;
+    acc += e2 / (sc * sc);
+  }
+  return sqrt(acc / n);
+}
+
+/* rms( V ./ sk ) with sk = abstol + |u0| * reltol, dual-aware. */
+static double initdt_norm(const ctx_t* c, const double* V, const double* U0, double divisor) {
+  int n = c->n;
+  int nc = c->o->err_norm_includes_sens ? c->ncol : 1;
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double v2 = 0.0, a2 = 0.0;
+    for (int col = 0; col < nc; ++col) {
+      double v = V[col * n + i] / divisor, a = U0[col * n + i];
+      v2 += v * v; a2 += a * a;
+    }
+    double at = c->o->abstol[c->o->n_abstol > 1 ? i : 0];
+    double rt = c->o->reltol[c->o->n_reltol > 1 ? i : 0];
+    double sk = at + sqrt(a2) * rt;
+    acc += v2 / (sk * sk);
+  }
+  return sqrt(acc / n);
+}
+
+/* Hairer-Wanner initial step as OrdinaryDiffEq's ode_determine_initdt
+ * (SURVEY App. C.3).  F0 = f(U0) on all columns (in), two RHS evaluations
+ * are charged to the trajectory (f0 is shared with the first stage). */
+static double initial_dt(const ctx_t* c, const double* U0, const double* F0, double tspan_len,
+                         double* work /* 2*ncol*n */, rhs_cache* k) {
+  int n = c->n, tot = c->ncol * n;
+  double d0 = initdt_norm(c, U0, U0, 1.0);
+  double d1 = initdt_norm(c, F0, U0, 1.0);
+  double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+  dt0 = fmin(dt0, tspan_len);
+  double* U1 = work; double* F1 = work + tot;
+  for (int q = 0; q < tot; ++q) U1[q] = U0[q] + dt0 * F0[q];
+  eval_cols(c, U1, F1, k);
+  for (int q = 0; q < tot; ++q) F1[q] -= F0[q];
+  double d2 = initdt_norm(c, F1, U0, 1.0) / dt0;
+  double dm = fmax(d1, d2);
+  double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / c->order);
+  return fmin(fmin(100.0 * dt0, dt1), tspan_len);
+}
+
+/* ---- Tsit5 tableau (Tsitouras 2011) ---- */
+static const double TS_A[7][6] = {
+  {0},
+  {0.161},
+  {-0.008480655492356989, 0.335480655492357},
+  {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+  {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+  {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
+  {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+static const double TS_BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                -0.1447110071732629, 0.5823571654525552, -0.45808210592918697,
+                                0.015151515151515152};
+static const double TS_R[7][4] = {
+  {1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+  {0.0, 0.13169999999999998, -0.2234, 0.1017},
+  {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+  {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+  {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+  {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+  {0.0, 1.5, -4.0, 2.5}};
+
+void crnn_oracle_tsit5_tableau(double* a /*7x6*/, double* btilde /*7*/, double* r /*7x4*/) {
+  memcpy(a, TS_A, sizeof(TS_A)); memcpy(btilde, TS_BT, sizeof(TS_BT)); memcpy(r, TS_R, sizeof(TS_R));
+}
+
+/* Per-save-point loss accumulation.
+ * kind 0: case2/case2.jl:132-137 (pred clamped at :126), rober_crnn.jl:139-144.
+ * kind 1: case3/case3.jl:183-190 (pred clamped at :174, data at :185).
+ * abs(dual) uses signbit(value), so d|v|/dv = +1 at v == +0. */
+typedef struct {
+  int loss_kind;
+  const double* data;   /* [n_obs, n_save] of this trajectory or NULL */
+  const double* yscale; /* [n_obs] */
+  double loss;          /* running sum */
+  double* grad;         /* [np] running sum or NULL */
+  double* pred;         /* [n_obs, n_save] or NULL */
+} save_sink;
+
+static void emit_save(const ctx_t* c, save_sink* sk, int ksave, const double* Ys /* ncol x n */) {
+  const crnn_opts* o = c->o;
+  int n = c->n;
+  for (int q = 0; q < o->n_obs; ++q) {
+    int i = o->obs_idx[q];
+    double y = Ys[i];
+    double yc = clampd(y, o->pred_clamp_lo, o->pred_clamp_hi);
+    int inside = (y >= o->pred_clamp_lo) && (y <= o->pred_clamp_hi);
+    if (sk->pred) sk->pred[q + o->n_obs * ksave] = yc;
+    if (!sk->data) continue;
+    double d = sk->data[q + o->n_obs * ksave];
+    double diff, g;
+    if (sk->loss_kind == CRNN_LOSS_MAE_SCALED) {
+      diff = d / sk->yscale[q] - yc / sk->yscale[q];
+      g = (signbit(diff) ? 1.0 : -1.0) / sk->yscale[q];
+    } else {
+      double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi);
+      diff = log(dc) - log(yc);
+      g = (signbit(diff) ? 1.0 : -1.0) / yc;
+    }
+    sk->loss += fabs(diff);
+    if (sk->grad && inside)
+      for (int col = 1; col < c->ncol; ++col) sk->grad[col - 1] += g * Ys[col * n + i];
+  }
+}
+
+static int has_nan(const double* v, int len) {
+  for (int q = 0; q < len; ++q) if (isnan(v[q])) return 1;
+  return 0;
+}
+
+/* PI controller of OrdinaryDiffEq: returns q; *q11 out. */
+static double pi_q(const ctx_t* c, double EEst, double qold, double* q11) {
+  if (EEst == 0.0) { *q11 = 0.0; return 1.0 / c->qmax; }
+  *q11 = pow(EEst, c->beta1);
+  double q = *q11 / pow(qold, c->beta2);
+  return fmax(1.0 / c->qmax, fmin(1.0 / c->qmin, q / c->gamma));
+}
+
+static double snap_t(double tnew, double tend) {
+  /* OrdinaryDiffEq fixed_t_for_floatingpoint_error!: land exactly on the tstop */
+  if (fabs(tnew - tend) < 100.0 * 2.220446049250313e-16 * fmax(fabs(tnew), fabs(tend))) return tend;
+  return tnew;
+}
+
+/* LU with partial pivoting, row-major A[n*n] in place; piv[n]. */
+static void lu_factor(double* A, int* piv, int n) {
+  for (int k = 0; k < n; ++k) {
+    int p = k; double best = fabs(A[k * n + k]);
+    for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + k]) > best) { best = fabs(A[i * n + k]); p = i; }
+    piv[k] = p;
+    if (p != k) for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
+    double d = 1.0 / A[k * n + k];
+    for (int i = k + 1; i < n; ++i) {
+      double l = A[i * n + k] * d; A[i * n + k] = l;
+      for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
+    }
+  }
+}
+static void lu_solve(const double* A, const int* piv, int n, double* b) {
+  for (int k = 0; k < n; ++k) { int p = piv[k]; if (p != k) { double t = b[k]; b[k] = b[p]; b[p] = t; } }
+  for (int i = 1; i < n; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= A[i * n + j] * b[j]; b[i] = s; }
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * b[j]; b[i] = s / A[i * n + i]; }
+}
+
+typedef struct {
+  int retcode, n_saved;
+  crnn_stats st;
+} traj_result;
+
+/* One trajectory, Tsit5 or Rosenbrock23, value + optional forward-sensitivity
+ * columns.  Mirrors OrdinaryDiffEq's solve! loop (loopheader!/perform_step!/
+ * loopfooter!), saveat by dense interpolation without stopping at save points
+ * (SURVEY App. C.2 "saveat semantics"). */
+static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sink* sk, traj_result* res) {
+  const crnn_opts* o = c->o;
+  const int n = c->n, ncol = c->ncol, tot = n * ncol;
+  const int rosen = (o->alg == CRNN_ALG_ROSENBROCK23);
+  double* buf = (double*)calloc((size_t)tot * 14 + (size_t)n * n * 2 + 8 * n, sizeof(double));
+  double* U = buf;              /* current state, all columns */
+  double* Un = U + tot;         /* proposed state */
+  double* K[7];
+  for (int s = 0; s < 7; ++s) K[s] = Un + tot * (s + 1);
+  double* TMP = K[6] + tot;
+  double* E = TMP + tot;
+  double* W2 = E + tot;         /* 2*tot work */
+  double* Jm = W2 + 2 * tot;    /* n*n */
+  double* LU = Jm + n * n;      /* n*n */
+  double* vtmp = LU + n * n;    /* 8n */
+  int piv[MAXN];
+  rhs_cache kc, kc0;
+
+  memcpy(U, u0, sizeof(double) * n); /* sensitivities of u0 are zero: u0 does not depend on p in any script */
+  const double t0 = o->t0;
+  const double tend = (n_save_use > 0 && n_save_use <= o->n_save) ? o->saveat[n_save_use - 1] : o->t1;
+  const int nsave = (n_save_use > 0 && n_save_use <= o->n_save) ? n_save_use : o->n_save;
+  const double dtmax = tend - t0;
+  const double dtmin = fmax(nextafter(fabs(t0), INFINITY) - fabs(t0), nextafter(fabs(tend), INFINITY) - fabs(tend));
+  double t = t0, dt, qold = 1e-4;
+  int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
+  memset(&res->st, 0, sizeof(res->st));
+
+  eval_cols(c, U, K[0], &kc); res->st.n_rhs++;
+  kc0 = kc;
+  dt = initial_dt(c, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
+  /* save_start: t0 is saved iff it is in saveat */
+  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
+
+  while (t < tend) {
+    ++iter;
+    /* check_error! order: DtNaN, MaxIters, DtLessThanMin, Unstable */
+    if (isnan(dt)) { ret = CRNN_RET_DTNAN; break; }
+    if (iter > o->maxiters) { ret = CRNN_RET_MAXITERS; break; }
+    dt = fmin(dt, dtmax);
+    dt = fmin(dt, tend - t); /* modify_dt_for_tstops! */
+    if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+    if (has_nan(U, tot)) { ret = CRNN_RET_UNSTABLE; break; }
+
+    if (!rosen) {
+      for (int s = 1; s < 7; ++s) {
+        double* Y = (s == 6) ? Un : TMP;
+        for (int q = 0; q < tot; ++q) {
+          double acc = TS_A[s][0] * K[0][q];
+          for (int j = 1; j < s; ++j) acc += TS_A[s][j] * K[j][q];
+          Y[q] = U[q] + dt * acc;
+        }
+        eval_cols(c, Y, K[s], &kc); res->st.n_rhs++;
+      }
+      for (int q = 0; q < tot; ++q) {
+        double acc = TS_BT[0] * K[0][q];
+        for (int j = 1; j < 7; ++j) acc += TS_BT[j] * K[j][q];
+        E[q] = dt * acc;
+      }
+    } else {
+      /* Rosenbrock23 = Shampine-Reichelt ode23s.  K[0]=f0
+       * (FSAL), K[1]=k1, K[2]=k2, K[3]=k3, K[4]=f1, K[5]=f2. */
+      const double d = 1.0 / (2.0 + sqrt(2.0)), e32 = 6.0 + sqrt(2.0);
+      const double g = d * dt;
+      /* kc0 holds the cache at U (value); J = df/du(U) */
+      jac_value(c, &kc0, Jm); res->st.n_jac++;
+      for (int i = 0; i < n; ++i)
+        for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - g * Jm[i * n + l];
+      lu_factor(LU, piv, n);
+      /* k1 */
+      for (int col = 0; col < ncol; ++col) {
+        double* k1 = K[1] + col * n;
+        for (int i = 0; i < n; ++i) k1[i] = K[0][col * n + i];
+        if (col > 0) { /* + gamma * dJ * k1(value) */
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[1], vtmp);
+          for (int i = 0; i < n; ++i) k1[i] += g * vtmp[i];
+        }
+        lu_solve(LU, piv, n, k1);
+      }
+      for (int q = 0; q < tot; ++q) TMP[q] = U[q] + 0.5 * dt * K[1][q];
+      eval_cols(c, TMP, K[4], &kc); res->st.n_rhs++;
+      /* k2 = W\(f1 - k1) + k1 */
+      for (int i = 0; i < n; ++i) vtmp[n + i] = 0.0;
+      for (int col = 0; col < ncol; ++col) {
+        double* k2 = K[2] + col * n;
+        for (int i = 0; i < n; ++i) k2[i] = K[4][col * n + i] - K[1][col * n + i];
+        if (col == 0) {
+          lu_solve(LU, piv, n, k2);
+          for (int i = 0; i < n; ++i) { vtmp[n + i] = k2[i]; /* k2 - k1 (value) */ k2[i] += K[1][i]; }
+        } else {
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, vtmp + n, vtmp);
+          for (int i = 0; i < n; ++i) k2[i] += g * vtmp[i];
+          lu_solve(LU, piv, n, k2);
+          for (int i = 0; i < n; ++i) k2[i] += K[1][col * n + i];
+        }
+      }
+      for (int q = 0; q < tot; ++q) Un[q] = U[q] + dt * K[2][q];
+      eval_cols(c, Un, K[5], &kc); res->st.n_rhs++;
+      for (int col = 0; col < ncol; ++col) {
+        double* k3 = K[3] + col * n;
+        for (int i = 0; i < n; ++i) {
+          int q = col * n + i;
+          k3[i] = K[5][q] - e32 * (K[2][q] - K[4][q]) - 2.0 * (K[1][q] - K[0][q]);
+        }
+        if (col == 0) {
+          lu_solve(LU, piv, n, k3);
+        } else {
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[3], vtmp);
+          for (int i = 0; i < n; ++i) k3[i] += g * vtmp[i];
+          lu_solve(LU, piv, n, k3);
+        }
+      }
+      for (int q = 0; q < tot; ++q) E[q] = dt / 6.0 * (K[1][q] - 2.0 * K[2][q] + K[3][q]);
+    }
+
+    double EEst = err_norm(c, E, U, Un);
+    double q11, q = pi_q(c, EEst, qold, &q11);
+    res->st.dt_last = dt;
+    if (EEst <= 1.0) {
+      res->st.n_accept++;
+      qold = fmax(EEst, 1e-4);
+      double dtnew = dt / q;
+      double tprev = t;
+      t = snap_t(t + dt, tend);
+      /* savevalues!: every save time in (tprev, t] via the dense interpolant */
+      while (isave < nsave && o->saveat[isave] <= t) {
+        double ts = o->saveat[isave];
+        if (ts == t) {
+          emit_save(c, sk, isave, Un);
+        } else {
+          double th = (ts - tprev) / dt;
+          if (!rosen) {
+            double b[7];
+            for (int s = 0; s < 7; ++s)
+              b[s] = th * (TS_R[s][0] + th * (TS_R[s][1] + th * (TS_R[s][2] + th * TS_R[s][3])));
+            for (int qq = 0; qq < tot; ++qq) {
+              double acc = b[0] * K[0][qq];
+              for (int s = 1; s < 7; ++s) acc += b[s] * K[s][qq];
+              TMP[qq] = U[qq] + dt * acc;
+            }
+          } else {
+            const double d = 1.0 / (2.0 + sqrt(2.0));
+            double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
+            for (int qq = 0; qq < tot; ++qq) TMP[qq] = U[qq] + dt * (c1 * K[1][qq] + c2 * K[2][qq]);
+          }
+          emit_save(c, sk, isave, TMP);
+        }
+        ++isave;
+      }
+      memcpy(U, Un, sizeof(double) * tot);
+      if (!rosen) memcpy(K[0], K[6], sizeof(double) * tot);
+      else { memcpy(K[0], K[5], sizeof(double) * tot); kc0 = kc; }
+      dt = fmin(dtnew, dtmax);
+    } else {
+      res->st.n_reject++;
+      dt = dt / fmin(1.0 / c->qmin, q11 / c->gamma);
+    }
+  }
+  if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+  res->retcode = ret;
+  res->n_saved = isave;
+  res->st.t_reached = t;
+  free(buf);
+}
+
+static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const double* seed, int np) {
+  c->m = m; c->o = o;
+  c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
+  c->nw = m->n_reac * (m->n_in + 1 + m->n_species);
+  c->seed = seed; c->ncol = 1 + np;
+  c->order = (o->alg == CRNN_ALG_TSIT5) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
+  c->qmin = o->qmin > 0 ? o->qmin : 0.2;
+  c->qmax = o->qmax > 0 ? o->qmax : 10.0;
+  c->gamma = o->gamma > 0 ? o->gamma : 0.9;
+  c->beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * c->order);
+  c->beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * c->order);
+}
+
+static int check_dims(const crnn_model* m, const crnn_opts* o) {
+  if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state) return CRNN_ERR_BAD_ARG;
+  if (m->rhs_kind == CRNN_RHS_F0 && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
+  if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE && m->n_species + 1 != m->n_state) return CRNN_ERR_BAD_ARG;
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23) return CRNN_ERR_UNSUPPORTED;
+  return CRNN_OK;
+}
+
+/* predict_neuralode over a batch (case2/case2.jl:124-128 etc.). */
+int crnn_oracle_solve_batch(const crnn_model* m, const crnn_opts* o, const double* u0, int64_t N,
+                            const int32_t* n_save_used, double* pred, int32_t* n_saved,
+                            int32_t* retcode, crnn_stats* stats, int n_threads) {
+  int rc = check_dims(m, o);
+  if (rc) return rc;
+  ctx_t c; make_ctx(&c, m, o, NULL, 0);
+  size_t pstride = (size_t)o->n_obs * o->n_save;
+  (void)n_threads;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int64_t i = 0; i < N; ++i) {
+    save_sink sk; memset(&sk, 0, sizeof(sk));
+    sk.pred = pred ? pred + pstride * i : NULL;
+    if (sk.pred) memset(sk.pred, 0, sizeof(double) * pstride);
+    traj_result r;
+    solve_one(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
+    if (n_saved) n_saved[i] = r.n_saved;
+    if (retcode) retcode[i] = r.retcode;
+    if (stats) stats[i] = r.st;
+  }
+  return CRNN_OK;
+}
+
+/* ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p) over a batch
+ * (case2/case2.jl:132-137,195).  All np seed columns ride one solve. */
+int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,
+                                const double* u0, int64_t N, const int32_t* n_save_used,
+                                const double* data, const double* yscale, int32_t loss_kind,
+                                double* loss, double* grad_sum, double* grad_each /* [np,N] or NULL */,
+                                double* pred, int32_t* n_saved, int32_t* retcode, crnn_stats* stats,
+                                int n_threads) {
+  int rc = check_dims(m, o);
+  if (rc) return rc;
+  ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
+  size_t pstride = (size_t)o->n_obs * o->n_save;
+  double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));
+  (void)n_threads;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int64_t i = 0; i < N; ++i) {
+    save_sink sk; memset(&sk, 0, sizeof(sk));
+    sk.loss_kind = loss_kind;
+    sk.data = data + pstride * i; sk.yscale = yscale;
+    sk.grad = (c.ncol > 1) ? gall + (size_t)np * i : NULL;
+    sk.pred = pred ? pred + pstride * i : NULL;
+    if (sk.pred) memset(sk.pred, 0, sizeof(double) * pstride);
+    traj_result r;
+    solve_one(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
+    double cnt = (double)o->n_obs * (double)r.n_saved;
+    if (r.n_saved > 0) {
+      loss[i] = sk.loss / cnt;
+      for (int q = 0; q < np; ++q) gall[(size_t)np * i + q] /= cnt;
+    } else {
+      loss[i] = NAN;
+      for (int q = 0; q < np; ++q) gall[(size_t)np * i + q] = 0.0;
+    }
+    if (n_saved) n_saved[i] = r.n_saved;
+    if (retcode) retcode[i] = r.retcode;
+    if (stats) stats[i] = r.st;
+  }
+  if (grad_sum) {
+    /* fixed-order sum (trajectory index ascending): deterministic */
+    for (int q = 0; q < np; ++q) {
+      double s = 0.0;
+      for (int64_t i = 0; i < N; ++i) s += gall[(size_t)np * i + q];
+      grad_sum[q] = s;
+    }
+  }
+  if (grad_each) memcpy(grad_each, gall, sizeof(double) * (size_t)np * (size_t)N);
+  free(gall);
+  return CRNN_OK;
+}
+
+/* Exposed pieces for unit tests (RHS / Jacobian / J*v / dJ*v). */
+int crnn_oracle_rhs(const crnn_model* m, const double* u, double* du, double* J /* n*n row-major or NULL */) {
+  crnn_opts o; memset(&o, 0, sizeof(o));
+  ctx_t c; make_ctx(&c, m, &o, NULL, 0);
+  rhs_cache k;
+  rhs_value(&c, u, du, &k);
+  if (J) jac_value(&c, &k, J);
+  return CRNN_OK;
+}
+
+int crnn_oracle_rhs_sens(const crnn_model* m, const double* u, const double* S, const double* seedcol,
+                         const double* v, double* dS, double* dJv) {
+  crnn_opts o; memset(&o, 0, sizeof(o));
+  ctx_t c; make_ctx(&c, m, &o, NULL, 0);
+  rhs_cache k; double du[MAXN];
+  rhs_value(&c, u, du, &k);
+  rhs_sens_col(&c, &k, S, seedcol, dS);
+  if (v && dJv) djac_vec(&c, &k, S, seedcol, v, dJv);
+  (void)jac_vec;
+  return CRNN_OK;
+}
