@@ -1,0 +1,175 @@
+"""Python face of the C-ABI (libcrnn_b200.so): `Engine.solve_batch` / `Engine.loss_grad_batch`.
+
+Host-side mirror of the two reference call sites the engine replaces:
+`predict_neuralode(u0, p)` (case2/case2.jl:124-128) and
+`ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` (case2/case2.jl:195), batched.
+
+Inputs are either numpy arrays (host buffers: the library runs the chunked
+H2D -> kernel -> D2H pipeline itself) or torch CUDA tensors (device buffers: the
+call only enqueues kernels on the current torch stream).  Layout is
+trajectory-major: u0 [N, n_state], data/pred [N, n_save, n_obs] (C order), which
+is the C-ABI's column-major u0[n_state, N], data[n_obs, n_save, N].
+There is no CPU fallback: constructing an Engine without the CUDA library or a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import STATS_DTYPE
+from .model import CRNNModel, SolveOpts
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Engine:
+    def __init__(self, device: int = -1):
+        self._lib = _abi.load_library()
+        h = C.c_void_p()
+        rc = self._lib.crnn_create(C.byref(h), int(device))
+        if rc != 0:
+            raise EngineError(f"crnn_create failed ({rc}): no usable CUDA device; crnn_b200 has no CPU path")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.crnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.crnn_launch_count(self._h))
+
+    def profile_begin(self):
+        self._check(self._lib.crnn_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> (summed solver-kernel milliseconds, number of solver-kernel launches)"""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self._lib.crnn_profile_end(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(f"crnn_b200 error {rc}: {self._lib.crnn_last_error(self._h).decode()}")
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _host(a, dtype, shape=None, name="array"):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {shape}, got {a.shape}")
+        return a
+
+    @staticmethod
+    def _dev(t, dtype, shape, name):
+        import torch
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+            raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {dtype}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+        return t
+
+    def solve_batch(self, model: CRNNModel, opts: SolveOpts, u0, n_save_used=None, want_stats=True, out=None):
+        """predict_neuralode for N initial conditions -> dict(pred, n_saved, retcode, stats)."""
+        n_obs, n_save, n = opts.n_obs(model.n_state), opts.n_save, model.n_state
+        cm, k1 = model.to_c()
+        if _is_torch(u0):
+            import torch
+            N = u0.shape[0]
+            self._dev(u0, torch.float64, (N, n), "u0")
+            dev = u0.device
+            co, k2 = opts.to_c(n, True, torch.cuda.current_stream(dev).cuda_stream)
+            pred = torch.empty((N, n_save, n_obs), dtype=torch.float64, device=dev) if out is None else out
+            n_saved = torch.empty(N, dtype=torch.int32, device=dev)
+            ret = torch.empty(N, dtype=torch.int32, device=dev)
+            stats = torch.empty((N, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev) if want_stats else None
+            nsu = None if n_save_used is None else self._dev(n_save_used, torch.int32, (N,), "n_save_used")
+            ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+            self._check(self._lib.crnn_solve_batch(self._h, C.byref(cm), C.byref(co), ptr(u0), N, ptr(nsu),
+                                                   ptr(pred), ptr(n_saved), ptr(ret), ptr(stats)))
+            return dict(pred=pred, n_saved=n_saved, retcode=ret, stats=stats)
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        if u0.ndim == 1:
+            u0 = u0[None, :]
+        N = u0.shape[0]
+        self._host(u0, np.float64, (N, n), "u0")
+        co, k2 = opts.to_c(n, False)
+        pred = np.empty((N, n_save, n_obs)) if out is None else out
+        n_saved = np.empty(N, dtype=np.int32); ret = np.empty(N, dtype=np.int32)
+        stats = np.empty(N, dtype=STATS_DTYPE) if want_stats else None
+        nsu = None if n_save_used is None else self._host(n_save_used, np.int32, (N,), "n_save_used")
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.crnn_solve_batch(self._h, C.byref(cm), C.byref(co), ptr(u0), N, ptr(nsu),
+                                               ptr(pred), ptr(n_saved), ptr(ret), ptr(stats)))
+        return dict(pred=pred, n_saved=n_saved, retcode=ret, stats=stats)
+
+    def loss_grad_batch(self, model: CRNNModel, opts: SolveOpts, seed, u0, data, yscale,
+                        loss_kind=_abi.LOSS_MAE_SCALED, n_save_used=None, want_pred=False, want_stats=True):
+        """Batched loss_neuralode and its gradient -> dict(loss [N], grad_sum [np], ...).
+
+        seed = dW/dp [n_w, np] (Jacobian of p2vec; rows [vec(w_in); w_b; vec(w_out)])."""
+        n_obs, n_save, n = opts.n_obs(model.n_state), opts.n_save, model.n_state
+        cm, k1 = model.to_c()
+        seed = np.asarray(seed, dtype=np.float64)
+        if seed.ndim != 2 or seed.shape[0] != model.n_w:
+            raise ValueError(f"seed must be [n_w={model.n_w}, np]")
+        n_p = seed.shape[1]
+        seed_flat = np.ascontiguousarray(seed.reshape(-1, order="F"))
+        ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (n_obs,), "yscale")
+        hp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        if _is_torch(u0):
+            import torch
+            N = u0.shape[0]
+            dev = u0.device
+            self._dev(u0, torch.float64, (N, n), "u0")
+            self._dev(data, torch.float64, (N, n_save, n_obs), "data")
+            co, k2 = opts.to_c(n, True, torch.cuda.current_stream(dev).cuda_stream)
+            loss = torch.empty(N, dtype=torch.float64, device=dev)
+            grad = torch.empty(n_p, dtype=torch.float64, device=dev)
+            pred = torch.empty((N, n_save, n_obs), dtype=torch.float64, device=dev) if want_pred else None
+            n_saved = torch.empty(N, dtype=torch.int32, device=dev)
+            ret = torch.empty(N, dtype=torch.int32, device=dev)
+            stats = torch.empty((N, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev) if want_stats else None
+            nsu = None if n_save_used is None else self._dev(n_save_used, torch.int32, (N,), "n_save_used")
+            ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+            self._check(self._lib.crnn_loss_grad_batch(
+                self._h, C.byref(cm), C.byref(co), hp(seed_flat), n_p, ptr(u0), N, ptr(nsu), ptr(data), hp(ys),
+                int(loss_kind), ptr(loss), ptr(grad), ptr(pred), ptr(n_saved), ptr(ret), ptr(stats)))
+            return dict(loss=loss, grad_sum=grad, pred=pred, n_saved=n_saved, retcode=ret, stats=stats)
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        if u0.ndim == 1:
+            u0 = u0[None, :]
+        N = u0.shape[0]
+        self._host(u0, np.float64, (N, n), "u0")
+        data = self._host(data, np.float64, (N, n_save, n_obs), "data")
+        co, k2 = opts.to_c(n, False)
+        loss = np.empty(N); grad = np.zeros(n_p)
+        pred = np.empty((N, n_save, n_obs)) if want_pred else None
+        n_saved = np.empty(N, dtype=np.int32); ret = np.empty(N, dtype=np.int32)
+        stats = np.empty(N, dtype=STATS_DTYPE) if want_stats else None
+        nsu = None if n_save_used is None else self._host(n_save_used, np.int32, (N,), "n_save_used")
+        self._check(self._lib.crnn_loss_grad_batch(
+            self._h, C.byref(cm), C.byref(co), hp(seed_flat), n_p, hp(u0), N, hp(nsu), hp(data), hp(ys),
+            int(loss_kind), hp(loss), hp(grad), hp(pred), hp(n_saved), hp(ret), hp(stats)))
+        return dict(loss=loss, grad_sum=grad, pred=pred, n_saved=n_saved, retcode=ret, stats=stats)
+
+
+def stats_from_torch(stats_u8) -> np.ndarray:
+    """uint8 [N, 32] CUDA tensor of crnn_stats -> numpy structured array."""
+    return stats_u8.cpu().numpy().view(STATS_DTYPE).reshape(-1)

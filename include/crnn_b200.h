@@ -140,6 +140,13 @@ int crnn_version(void);
 /* Number of CUDA kernels this handle has launched since creation. */
 int64_t crnn_launch_count(const crnn_handle* h);
 
+/* Optional device-side timing of the solver kernels (the dominant launches): between
+ * crnn_profile_begin and crnn_profile_end every solver-kernel launch is bracketed by CUDA
+ * events on its own stream; _end synchronises and returns their summed duration and count.
+ * Used by bench.py for the roofline line; off by default (no events recorded). */
+int crnn_profile_begin(crnn_handle* h);
+int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches);
+
 /* predict_neuralode for a batch of N initial conditions.
  *   u0      [n_state, N]
  *   n_save_used [N] or NULL: trajectory i integrates only to
@@ -157,8 +164,9 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
  *           [vec(w_in); w_b; vec(w_out)]
  *   data    [n_obs, n_save, N], yscale [n_obs] (host; ignored for MAE_LOG)
  *   loss    [N] per-trajectory loss (NaN when a trajectory saved nothing)
- *   grad_sum[np] (HOST, always) sum over trajectories of d loss_i / d p,
- *           accumulated in a fixed order (deterministic)
+ *   grad_sum[np] sum over trajectories of d loss_i / d p, accumulated in a fixed
+ *           order (deterministic); host or device memory like the other
+ *           batched buffers (opts.buffers_on_device)
  *   pred    may be NULL                                                     */
 int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
                          const double* dW_dp, int32_t np,

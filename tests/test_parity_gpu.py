@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.  Bar: accepted/rejected step counts and retcodes identical; saved states,
+losses and gradients within the fp64 tolerances written below."""
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases, synth
+from oracle import oracle
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL_STATE = 1e-9     # saved states vs oracle (north star asks <= 1e-6)
+RTOL_LOSS = 1e-10
+RTOL_GRAD = 1e-8
+
+
+def _counts_equal(got, ref):
+    for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+        bad = np.nonzero(got["stats"][k] != ref["stats"][k])[0]
+        assert bad.size == 0, f"{k} differs from the oracle for trajectories {bad[:8]}"
+    assert np.array_equal(got["retcode"], ref["retcode"])
+    assert np.array_equal(got["n_saved"], ref["n_saved"])
+
+
+@pytest.mark.parametrize("name,N", [("case1", 64), ("case2", 512), ("case3", 128)])
+def test_tsit5_value_matches_oracle(engine, golden, name, N):
+    pb = make_problem(name, golden, N)
+    got = engine.solve_batch(pb["model"], pb["opts"], pb["u0"])
+    ref = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["pred"], ref["pred"], rtol=RTOL_STATE, atol=1e-13)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+
+
+@pytest.mark.parametrize("name", ["case1", "case2", "case3", "robertson"])
+def test_true_mechanism_value(engine, golden, name):
+    """generating mechanisms written as CRNNs (the synthetic-target path of bench.py)"""
+    pb = make_problem(name, golden, 96)
+    c = pb["case"]
+    o = c.opts(obs_idx=np.arange(c.ns), pred_clamp=(-np.inf, np.inf))
+    got = engine.solve_batch(pb["true_model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["true_model"], o, pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    assert (np.abs(got["pred"] - ref["pred"]) / scale).max() < 1e-9
+
+
+def test_rosenbrock23_value_matches_oracle(engine, golden):
+    pb = make_problem("robertson", golden, 256)
+    got = engine.solve_batch(pb["model"], pb["opts"], pb["u0"])
+    ref = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    assert (np.abs(got["pred"] - ref["pred"]) / scale).max() < 1e-8
+
+
+@pytest.mark.parametrize("name,N", [("case1", 64), ("case2", 384)])
+def test_tsit5_forward_sens_loss_grad(engine, golden, name, N):
+    pb = make_problem(name, golden, N)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["pred"], ref["pred"], rtol=RTOL_STATE, atol=1e-13)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
+    gmax = np.abs(ref["grad_sum"]).max()
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=RTOL_GRAD, atol=1e-10 * gmax)
+
+
+def test_sens_value_only_norm_switch(engine, golden):
+    """err_norm_includes_sens = 0: the step sequence must equal the value-only solve's."""
+    pb = make_problem("case2", golden, 128)
+    o = pb["case"].opts(obs_idx=np.arange(6), err_norm_includes_sens=False)
+    got = engine.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    val = engine.solve_batch(pb["model"], o, pb["u0"])
+    assert np.array_equal(got["stats"]["n_accept"], val["stats"]["n_accept"])
+    ref = oracle.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"], n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=RTOL_GRAD, atol=1e-10 * np.abs(ref["grad_sum"]).max())
+
+
+def test_mae_log_loss_kind(engine, golden):
+    """case3's loss (log-MAE with (lb,ub) clamps) on a case1-sized model (np=20 fits forward mode)."""
+    pb = make_problem("case1", golden, 64)
+    o = pb["case"].opts(obs_idx=np.arange(5), pred_clamp=(1e-5, 10.0))
+    args = (pb["model"], o, pb["seed"], pb["u0"], np.abs(pb["data"]) + 1e-7, pb["yscale"], _abi.LOSS_MAE_LOG)
+    got = engine.loss_grad_batch(*args)
+    ref = oracle.loss_grad_batch(*args, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=RTOL_GRAD, atol=1e-10 * np.abs(ref["grad_sum"]).max())
+
+
+def test_missing_species_obs_idx(engine, golden):
+    """case2_missing.jl:165: i_obs = [1,2,4,5,6] (species 3 unobserved)."""
+    obs = np.array([0, 1, 3, 4, 5])
+    pb = make_problem("case2", golden, 96, obs=obs)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["pred"], ref["pred"], rtol=RTOL_STATE, atol=1e-13)
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=RTOL_GRAD, atol=1e-10 * np.abs(ref["grad_sum"]).max())
+
+
+def test_device_buffers_equal_host_buffers(engine, golden):
+    import torch
+    pb = make_problem("case2", golden, 300)
+    host = engine.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"],
+                                  pb["loss_kind"], want_pred=True)
+    u0 = torch.from_numpy(pb["u0"]).cuda(); data = torch.from_numpy(pb["data"]).cuda()
+    dev = engine.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], u0, data, pb["yscale"], pb["loss_kind"],
+                                 want_pred=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["pred"].cpu().numpy(), host["pred"])
+    assert np.array_equal(dev["loss"].cpu().numpy(), host["loss"])
+    assert np.array_equal(dev["retcode"].cpu().numpy(), host["retcode"])
+    # the reduction order differs between the chunked host path and the single-launch device path
+    np.testing.assert_allclose(dev["grad_sum"].cpu().numpy(), host["grad_sum"], rtol=1e-12)
+
+
+def test_edge_empty_single_and_ragged(engine, golden):
+    pb = make_problem("case2", golden, 33)
+    # N = 0
+    r0 = engine.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], pb["u0"][:0], pb["data"][:0], pb["yscale"])
+    assert r0["loss"].shape == (0,) and np.all(r0["grad_sum"] == 0)
+    # N = 1
+    r1 = engine.solve_batch(pb["model"], pb["opts"], pb["u0"][:1])
+    ref1 = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"][:1])
+    np.testing.assert_allclose(r1["pred"], ref1["pred"], rtol=RTOL_STATE, atol=1e-13)
+    # ragged time truncation (rober_crnn.jl:218: sample = rand(batchsize:datasize))
+    nsu = np.random.default_rng(3).integers(5, 51, size=33).astype(np.int32)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, n_save_used=nsu, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, n_save_used=nsu, want_pred=True, n_threads=4)
+    _counts_equal(got, ref)
+    assert np.array_equal(got["n_saved"], nsu)
+    np.testing.assert_allclose(got["pred"], ref["pred"], rtol=RTOL_STATE, atol=1e-13)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
+
+
+def test_retcode_paths(engine, golden):
+    pb = make_problem("case2", golden, 40)
+    c = pb["case"]
+    # maxiters truncation: n_saved < n_save, MaxIters, batch does not abort
+    o = c.opts(obs_idx=np.arange(6), maxiters=5)
+    got = engine.solve_batch(pb["model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["model"], o, pb["u0"])
+    _counts_equal(got, ref)
+    assert (got["retcode"] == _abi.RET_MAXITERS).all() and (got["n_saved"] < 50).all()
+    for i in range(40):
+        k = got["n_saved"][i]
+        np.testing.assert_allclose(got["pred"][i, :k], ref["pred"][i, :k], rtol=RTOL_STATE, atol=1e-13)
+        assert np.all(got["pred"][i, k:] == 0)
+    # NaN weights: flagged per trajectory, never an engine error
+    m = cases.CRNNModel(w_in=pb["model"].w_in, w_b=pb["model"].w_b * np.nan, w_out=pb["model"].w_out,
+                        rhs_kind=pb["model"].rhs_kind, lb=pb["model"].lb, ub=pb["model"].ub)
+    bad = engine.solve_batch(m, pb["opts"], pb["u0"])
+    refb = oracle.solve_batch(m, pb["opts"], pb["u0"])
+    assert np.array_equal(bad["retcode"], refb["retcode"])
+    assert np.isin(bad["retcode"], [_abi.RET_DTNAN, _abi.RET_UNSTABLE]).all()
+
+
+def test_bad_arguments_are_engine_errors(engine, golden):
+    from crnn_b200.engine import EngineError
+    pb = make_problem("case2", golden, 4)
+    with pytest.raises(EngineError):
+        engine.solve_batch(pb["model"], pb["case"].opts(obs_idx=np.array([0, 0])), pb["u0"])
+    with pytest.raises(EngineError):   # Rosenbrock23 forward sensitivities / unsupported dims
+        m = cases.CRNNModel(w_in=np.ones((4, 2)), w_b=np.zeros(2), w_out=np.ones((4, 2)))
+        engine.solve_batch(m, pb["case"].opts(obs_idx=np.arange(4)), np.ones((2, 4)))
+
+
+def test_full_size_properties_case2(engine, golden):
+    """BASELINE configs[1] size (65 536 ICs): size-independent properties instead of the oracle."""
+    import torch
+    c = cases.CASES["case2"]
+    N = 65536
+    u0 = synth.make_u0("case2", N)
+    tm = cases.true_model_case2()
+    o = c.opts(obs_idx=np.arange(6), pred_clamp=(-np.inf, np.inf))
+    tr = engine.solve_batch(tm, o, u0)
+    assert (tr["retcode"] == 1).all() and (tr["n_saved"] == 50).all()
+    y = tr["pred"]
+    # element balances of the transesterification mechanism (case2.jl:40-48):
+    # glycerol backbone TG+DG+MG+GL and acyl groups 3TG+2DG+MG+ester are conserved, ROH+ester too
+    for w in ([1, 0, 1, 1, 1, 0], [3, 0, 2, 1, 0, 1], [0, 1, 0, 0, 0, 1]):
+        inv = y @ np.array(w, dtype=float)
+        assert np.abs(inv - inv[:, :1]).max() < 2e-3
+    assert np.array_equal(y[:, 0, :], u0[:, :6])          # t0 is in saveat: saved exactly
+    # CRNN loss/gradient at full size: sharded sum == whole-batch sum (linearity of grad_sum)
+    data = synth.noisy_targets(y, 0.05)
+    ys = synth.yscale_from(data, c.lb)
+    model, seed = c.model(np.array(golden["case2"]["p"]))
+    opts = c.opts(obs_idx=np.arange(6))
+    whole = engine.loss_grad_batch(model, opts, seed, u0, data, ys)
+    assert (whole["retcode"] == 1).all()
+    parts = [engine.loss_grad_batch(model, opts, seed, u0[a:b], data[a:b], ys)
+             for a, b in ((0, 20000), (20000, 65536))]
+    np.testing.assert_allclose(sum(p["grad_sum"] for p in parts), whole["grad_sum"], rtol=1e-11)
+    assert np.array_equal(np.concatenate([p["loss"] for p in parts]), whole["loss"])
+    # trained checkpoint reproduces the generating mechanism: normalised MAE of the order the
+    # reference's own loss history ends at (1.4e-2..1.7e-2 incl. 5 % noise)
+    assert 0.01 < whole["loss"].mean() < 0.06
+    # a random sample against the oracle
+    idx = np.random.default_rng(0).choice(N, 64, replace=False)
+    ref = oracle.loss_grad_batch(model, opts, seed, u0[idx], data[idx], ys, n_threads=8)
+    np.testing.assert_allclose(whole["loss"][idx], ref["loss"], rtol=RTOL_LOSS)
+    assert np.array_equal(whole["stats"]["n_accept"][idx], ref["stats"]["n_accept"])
