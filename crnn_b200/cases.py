@@ -171,7 +171,7 @@ INF = float("inf")
 # silently ignored, so the effective tolerances are the defaults
 # abstol=1e-6 / reltol=1e-3.  `as_written` keeps the values in the scripts.
 CASES = {
-    "case1": Case("case1", 5, 4, 20, _abi.RHS_F0, 1e-5, 10.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
+    "case1": Case("case1", 5, 4, 24, _abi.RHS_F0, 1e-5, 10.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
                   (0.0, 40.0), 100, p2vec_case1, (-10.0, 10.0), _abi.LOSS_MAE_SCALED, maxiters=10000),
     "case2": Case("case2", 6, 3, 25, _abi.RHS_F1, 1e-6, 10.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
                   (0.0, 50.0), 50, p2vec_case2, (-10.0, 10.0), _abi.LOSS_MAE_SCALED),

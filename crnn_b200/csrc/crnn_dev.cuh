@@ -78,6 +78,10 @@ __device__ __forceinline__ void dense_b(double th, double (&b)[7]) {
 }
 }  // namespace ts
 
+// Julia's min/max propagate NaN (fmin/fmax drop it): a NaN RHS must surface as a NaN dt.
+__device__ __forceinline__ double jmin(double a, double b) { return a < b ? a : (b <= a ? b : a + b); }
+__device__ __forceinline__ double jmax(double a, double b) { return a > b ? a : (b >= a ? b : a + b); }
+
 // Julia Base.clamp semantics (NaN propagates).
 __device__ __forceinline__ double clampd(double v, double lo, double hi) {
   return v > hi ? hi : (v < lo ? lo : v);
@@ -89,7 +93,7 @@ __device__ __forceinline__ double pi_controller(const SolveP<C>& sp, double EEst
   if (EEst == 0.0) { q11 = 0.0; return sp.inv_qmax; }
   q11 = pow(EEst, sp.beta1);
   double q = q11 / pow(qold, sp.beta2);
-  return fmax(sp.inv_qmax, fmin(sp.inv_qmin, q / sp.gamma));
+  return jmax(sp.inv_qmax, jmin(sp.inv_qmin, q / sp.gamma));
 }
 
 __device__ __forceinline__ double snap_t(double tnew, double tend) {

@@ -1,0 +1,392 @@
+#pragma once
+// crnn_host.cuh — host side of the engine shared by crnn_api.cu and the per-configuration
+// instantiation units (inst.cu): argument validation, packing of the model/solver
+// options into by-value kernel parameters, dispatch to the dimension-specialised
+// kernels, and (for host buffers) a chunked H2D -> kernel -> D2H pipeline on two
+// streams so that PCIe copies overlap the solve.  No CPU compute path exists here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/crnn_b200.h"
+#include "crnn_dev.cuh"
+#include "kernel_tsit5_value.cuh"
+#include "kernel_tsit5_sens.cuh"
+#include "kernel_rosenbrock23.cuh"
+
+using namespace crnn;
+
+// ------------------------------------------------------------------------------------------
+// Dimension dispatch.  (n_species, n_reac, rhs_kind) of every model the reference scripts and
+// their generating mechanisms use:
+//   case1 5/4/F0, case2 6/3/F1, case3 9/8/F0, robertson CRNN 3/6/F0, robertson truth 3/3/F0,
+//   gene-regulatory 9/15/F0.
+// ------------------------------------------------------------------------------------------
+#define CRNN_FOR_EACH_CFG(X) \
+  X(5, 4, 0) X(6, 3, 1) X(9, 8, 0) X(3, 6, 0) X(3, 3, 0) X(9, 15, 0)
+
+
+namespace crnn_host {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kPipe = 2;  // pipeline depth of the host-buffer path
+
+}  // namespace crnn_host
+using crnn_host::DevBuf;
+using crnn_host::kPipe;
+
+struct crnn_handle {
+  int device = 0;
+  int num_sms = 0;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {}, ev_out[kPipe] = {};
+  // small per-call device state
+  DevBuf cfg, seed, ctr, partial;
+  // staging for the host-buffer path (per pipeline slot) and full-batch gradients
+  DevBuf d_u0[kPipe], d_nsu[kPipe], d_data[kPipe], d_pred[kPipe], d_loss[kPipe], d_nsaved[kPipe], d_ret[kPipe],
+      d_stats[kPipe];
+  DevBuf d_grad_each, d_grad_sum;
+  // optional kernel timing (crnn_profile_begin/_end)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+};
+
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+      return CRNN_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+namespace crnn_host {
+
+inline int fail(crnn_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+// brackets one solver-kernel launch with events when profiling is on
+struct ProfScope {
+  crnn_handle* h; cudaStream_t st; cudaEvent_t e1 = nullptr;
+  ProfScope(crnn_handle* h_, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->profiling) return;
+    if (h->prof_used == h->prof_events.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      h->prof_events.emplace_back(a, b);
+    }
+    auto& pr = h->prof_events[h->prof_used++];
+    cudaEventRecord(pr.first, st);
+    e1 = pr.second;
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
+};
+
+struct Packed {
+  std::vector<double> w_out_scaled, seed_pad;
+  std::vector<int> row2obs;
+  std::vector<double> inv_ys;
+};
+
+inline int validate(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int64_t N) {
+  if (!m || !o) return fail(h, CRNN_ERR_BAD_ARG, "null model/opts");
+  if (N < 0) return fail(h, CRNN_ERR_BAD_ARG, "negative N");
+  if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "rhs_kind not supported");
+  if (m->n_in != m->n_state || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
+    return fail(h, CRNN_ERR_BAD_ARG, "inconsistent n_state / n_species / n_in for rhs_kind");
+  if (!m->w_in || !m->w_b || !m->w_out) return fail(h, CRNN_ERR_BAD_ARG, "null weights");
+  if (!(m->lb > 0.0) || !(m->ub > m->lb)) return fail(h, CRNN_ERR_BAD_ARG, "need 0 < lb < ub");
+  if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(h, CRNN_ERR_BAD_ARG, "bad saveat");
+  for (int k = 0; k < o->n_save; ++k) {
+    if (k > 0 && o->saveat[k] < o->saveat[k - 1]) return fail(h, CRNN_ERR_BAD_ARG, "saveat must be ascending");
+    if (o->saveat[k] < o->t0 || o->saveat[k] > o->t1) return fail(h, CRNN_ERR_BAD_ARG, "saveat outside [t0,t1]");
+  }
+  if (!(o->t1 > o->t0)) return fail(h, CRNN_ERR_BAD_ARG, "need t1 > t0");
+  if ((o->n_abstol != 1 && o->n_abstol != m->n_state) || (o->n_reltol != 1 && o->n_reltol != m->n_state) ||
+      !o->abstol || !o->reltol)
+    return fail(h, CRNN_ERR_BAD_ARG, "abstol/reltol must have 1 or n_state entries");
+  if (o->n_obs < 0 || o->n_obs > m->n_state || (o->n_obs > 0 && !o->obs_idx))
+    return fail(h, CRNN_ERR_BAD_ARG, "bad obs_idx");
+  if (o->maxiters <= 0) return fail(h, CRNN_ERR_BAD_ARG, "maxiters must be positive");
+  return CRNN_OK;
+}
+
+template <class C>
+int pack(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* yscale, int loss_kind,
+         ModelP<C>& mp, SolveP<C>& sp, Packed& pk) {
+  for (int q = 0; q < C::NIN * C::NR; ++q) mp.w_in[q] = m->w_in[q];
+  for (int q = 0; q < C::NR; ++q) mp.w_b[q] = m->w_b[q];
+  for (int j = 0; j < C::NR; ++j)
+    for (int i = 0; i < C::NS; ++i)
+      mp.w_out[i + C::NS * j] = m->w_out[i + C::NS * j] * (m->out_scale ? m->out_scale[i] : 1.0);
+  mp.lb = m->lb; mp.ub = m->ub; mp.gas_R = m->gas_R;
+  const int order = (o->alg == CRNN_ALG_TSIT5) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
+  for (int i = 0; i < C::N; ++i) {
+    sp.abstol[i] = o->abstol[o->n_abstol > 1 ? i : 0];
+    sp.reltol[i] = o->reltol[o->n_reltol > 1 ? i : 0];
+    sp.inv_yscale[i] = 1.0;
+  }
+  pk.row2obs.assign(C::N, -1);
+  for (int q = 0; q < o->n_obs; ++q) {
+    int r = o->obs_idx[q];
+    if (r < 0 || r >= C::N) return fail(h, CRNN_ERR_BAD_ARG, "obs_idx out of range");
+    if (pk.row2obs[r] >= 0) return fail(h, CRNN_ERR_BAD_ARG, "obs_idx has duplicates");
+    pk.row2obs[r] = q;
+    if (yscale && loss_kind == CRNN_LOSS_MAE_SCALED) sp.inv_yscale[r] = 1.0 / yscale[q];
+  }
+  sp.t0 = o->t0; sp.t1 = o->t1;
+  sp.pred_lo = o->pred_clamp_lo; sp.pred_hi = o->pred_clamp_hi;
+  const double qmin = o->qmin > 0 ? o->qmin : 0.2, qmax = o->qmax > 0 ? o->qmax : 10.0;
+  sp.inv_qmin = 1.0 / qmin; sp.inv_qmax = 1.0 / qmax;
+  sp.gamma = o->gamma > 0 ? o->gamma : 0.9;
+  sp.beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * order);
+  sp.beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * order);
+  sp.inv_order = 1.0 / order;
+  sp.maxiters = o->maxiters;
+  sp.n_save = o->n_save; sp.n_obs = o->n_obs;
+  sp.incl_sens = o->err_norm_includes_sens;
+  sp.loss_kind = loss_kind;
+  return CRNN_OK;
+}
+
+// uploads saveat + row2obs into the handle's config blob; fills the device pointers of sp
+template <class C>
+int upload_cfg(crnn_handle* h, const crnn_opts* o, const Packed& pk, SolveP<C>& sp, cudaStream_t st) {
+  const size_t off_r2o = ((size_t)o->n_save * sizeof(double) + 15) & ~size_t(15);
+  const size_t bytes = off_r2o + C::N * sizeof(int);
+  CK(h->cfg.reserve(std::max<size_t>(bytes, 4096)));
+  if (o->n_save) CK(cudaMemcpyAsync(h->cfg.p, o->saveat, o->n_save * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((char*)h->cfg.p + off_r2o, pk.row2obs.data(), C::N * sizeof(int), cudaMemcpyHostToDevice, st));
+  sp.saveat = h->cfg.as<double>();
+  sp.row2obs = reinterpret_cast<const int*>((char*)h->cfg.p + off_r2o);
+  return CRNN_OK;
+}
+
+struct BatchPtrs {  // device pointers of one (sub)batch
+  const double* u0; const int* nsu; const double* data;
+  double* pred; double* loss; int* n_saved; int* retcode; crnn_stats* stats;
+  double* grad_each;
+  long long n;
+};
+
+// ---------------- value path launchers ----------------
+template <class C>
+int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& sp, const BatchPtrs& b,
+                 cudaStream_t st) {
+  if (b.n == 0) return CRNN_OK;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((b.n + threads - 1) / threads);
+  ProfScope prof(h, st);
+  if (alg == CRNN_ALG_TSIT5)
+    k_tsit5_value<C><<<blocks, threads, 0, st>>>(mp, sp, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode, b.stats);
+  else
+    k_rosenbrock23_value<C><<<blocks, threads, 0, st>>>(mp, sp, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode,
+                                                       b.stats);
+  CK(cudaGetLastError());
+  h->launches++;
+  return CRNN_OK;
+}
+
+// ---------------- sensitivity path launchers ----------------
+template <class C, int CT>
+int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
+                cudaStream_t st) {
+  if (b.n == 0) return CRNN_OK;
+  constexpr int WARPS = (CT == 1 ? 8 : 4), MINB = 2;
+  auto kern = k_tsit5_sens<C, CT, WARPS, MINB>;
+  const size_t smem = sizeof(SensSmem<C, CT>) + WARPS * sizeof(WarpBuf<C, CT>);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+  if (bps < 1) bps = 1;
+  long long want = (b.n + WARPS - 1) / WARPS;
+  unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
+  CK(cudaMemsetAsync(h->ctr.p, 0, sizeof(unsigned long long), st));
+  ProfScope prof(h, st);
+  kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), ncol, b.u0, b.nsu, b.n, b.data, b.loss,
+                                      b.grad_each, b.pred, b.n_saved, b.retcode, b.stats,
+                                      h->ctr.as<unsigned long long>());
+  CK(cudaGetLastError());
+  h->launches++;
+  return CRNN_OK;
+}
+
+inline int launch_grad_reduce(crnn_handle* h, const double* grad_each, long long n, int np, double* grad_sum_dev,
+                       cudaStream_t st) {
+  const int nb = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (n + 63) / 64));
+  CK(h->partial.reserve((size_t)nb * np * sizeof(double)));
+  k_grad_reduce<<<nb, 256, 0, st>>>(grad_each, n, np, h->partial.as<double>(), grad_sum_dev,
+                                    reinterpret_cast<unsigned int*>(h->ctr.as<unsigned long long>() + 1));
+  CK(cudaGetLastError());
+  h->launches++;
+  return CRNN_OK;
+}
+
+// Pads dW/dp to [NW][32*CT] (column 0 = value lane = 0), folding out_scale into the w_out rows.
+template <class C>
+int upload_seed(crnn_handle* h, const crnn_model* m, const double* dW_dp, int np, int ct, Packed& pk,
+                cudaStream_t st) {
+  const int width = 32 * ct;
+  pk.seed_pad.assign((size_t)C::NW * width, 0.0);
+  const int off_out = C::NIN * C::NR + C::NR;
+  for (int c = 0; c < np; ++c)
+    for (int w = 0; w < C::NW; ++w) {
+      double v = dW_dp[w + (size_t)C::NW * c];
+      if (w >= off_out && m->out_scale) v *= m->out_scale[(w - off_out) % C::NS];
+      pk.seed_pad[(size_t)w * width + (c + 1)] = v;
+    }
+  CK(h->seed.reserve(pk.seed_pad.size() * sizeof(double)));
+  CK(cudaMemcpyAsync(h->seed.p, pk.seed_pad.data(), pk.seed_pad.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  return CRNN_OK;
+}
+
+// The generic driver: runs `launch(b, stream)` over the batch, either directly on device
+// buffers or through the chunked host pipeline.
+struct HostIO {
+  const double* u0; const int32_t* nsu; const double* data;
+  double* pred; double* loss; int32_t* n_saved; int32_t* retcode; crnn_stats* stats;
+};
+
+template <class F>
+int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N, bool want_loss,
+              int np, double* grad_sum, F&& launch) {
+  const size_t ns = m->n_state, ps = (size_t)o->n_obs * o->n_save;
+  if (o->buffers_on_device) {
+    cudaStream_t st = (cudaStream_t)o->stream;
+    BatchPtrs b{io.u0, io.nsu, io.data, io.pred, io.loss, io.n_saved, io.retcode, io.stats, nullptr, N};
+    if (want_loss && np > 0) {
+      CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
+      b.grad_each = h->d_grad_each.as<double>();
+    }
+    int rc = launch(b, st);
+    if (rc) return rc;
+    if (want_loss && np > 0 && grad_sum) {
+      if (N == 0) { CK(cudaMemsetAsync(grad_sum, 0, np * sizeof(double), st)); }
+      else { rc = launch_grad_reduce(h, b.grad_each, N, np, grad_sum, st); if (rc) return rc; }
+    }
+    return CRNN_OK;
+  }
+
+  // ---- host buffers: chunked, double-buffered pipeline (H2D stream || compute stream || D2H stream) ----
+  if (want_loss && np > 0) CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
+  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(16384, (N + 7) / 8));
+  const int64_t nchunk = (N + chunk - 1) / chunk;
+  for (int s = 0; s < kPipe; ++s) {
+    CK(h->d_u0[s].reserve(chunk * ns * sizeof(double)));
+    if (io.nsu) CK(h->d_nsu[s].reserve(chunk * sizeof(int)));
+    if (want_loss) { CK(h->d_data[s].reserve(std::max<size_t>(8, chunk * ps * sizeof(double)))); CK(h->d_loss[s].reserve(chunk * sizeof(double))); }
+    if (io.pred) CK(h->d_pred[s].reserve(std::max<size_t>(8, chunk * ps * sizeof(double))));
+    CK(h->d_nsaved[s].reserve(chunk * sizeof(int)));
+    CK(h->d_ret[s].reserve(chunk * sizeof(int)));
+    if (io.stats) CK(h->d_stats[s].reserve(chunk * sizeof(crnn_stats)));
+  }
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int s = (int)(c % kPipe);
+    const int64_t lo = c * chunk, n = std::min<int64_t>(chunk, N - lo);
+    // slot reuse: inputs may be overwritten once the kernel of chunk c-kPipe is done,
+    // outputs once their D2H copies are done
+    if (c >= kPipe) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[s], 0));
+    CK(cudaMemcpyAsync(h->d_u0[s].p, io.u0 + lo * ns, n * ns * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
+    if (io.nsu) CK(cudaMemcpyAsync(h->d_nsu[s].p, io.nsu + lo, n * sizeof(int), cudaMemcpyHostToDevice, h->s_h2d));
+    if (want_loss && ps) CK(cudaMemcpyAsync(h->d_data[s].p, io.data + lo * ps, n * ps * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
+    CK(cudaEventRecord(h->ev_in[s], h->s_h2d));
+    CK(cudaStreamWaitEvent(h->s_compute, h->ev_in[s], 0));
+    if (c >= kPipe) CK(cudaStreamWaitEvent(h->s_compute, h->ev_out[s], 0));
+    BatchPtrs b{h->d_u0[s].as<double>(), io.nsu ? h->d_nsu[s].as<int>() : nullptr,
+                want_loss ? h->d_data[s].as<double>() : nullptr, io.pred ? h->d_pred[s].as<double>() : nullptr,
+                want_loss ? h->d_loss[s].as<double>() : nullptr, h->d_nsaved[s].as<int>(), h->d_ret[s].as<int>(),
+                io.stats ? h->d_stats[s].as<crnn_stats>() : nullptr,
+                (want_loss && np > 0) ? h->d_grad_each.as<double>() + (size_t)lo * np : nullptr, n};
+    int rc = launch(b, h->s_compute);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_done[s], h->s_compute));
+    // D2H of this chunk's results on its own stream (a second copy engine)
+    CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[s], 0));
+    if (io.pred && ps) CK(cudaMemcpyAsync(io.pred + lo * ps, h->d_pred[s].p, n * ps * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (want_loss && io.loss) CK(cudaMemcpyAsync(io.loss + lo, h->d_loss[s].p, n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io.n_saved) CK(cudaMemcpyAsync(io.n_saved + lo, h->d_nsaved[s].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io.retcode) CK(cudaMemcpyAsync(io.retcode + lo, h->d_ret[s].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io.stats) CK(cudaMemcpyAsync(io.stats + lo, h->d_stats[s].p, n * sizeof(crnn_stats), cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(cudaEventRecord(h->ev_out[s], h->s_d2h));
+  }
+  if (want_loss && np > 0 && grad_sum) {
+    if (N == 0) {
+      std::memset(grad_sum, 0, np * sizeof(double));
+    } else {
+      CK(h->d_grad_sum.reserve(np * sizeof(double)));
+      int rc = launch_grad_reduce(h, h->d_grad_each.as<double>(), N, np, h->d_grad_sum.as<double>(), h->s_compute);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(grad_sum, h->d_grad_sum.p, np * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
+    }
+  }
+  CK(cudaStreamSynchronize(h->s_h2d));
+  CK(cudaStreamSynchronize(h->s_d2h));
+  CK(cudaStreamSynchronize(h->s_compute));
+  return CRNN_OK;
+}
+
+}  // namespace
+
+
+namespace crnn_host {
+
+template <class C>
+int solve_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  ModelP<C> mp; SolveP<C> sp; Packed pk;
+  int rc = pack<C>(h, m, o, nullptr, 0, mp, sp, pk);
+  if (rc) return rc;
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  rc = upload_cfg<C>(h, o, pk, sp, st);
+  if (rc) return rc;
+  const int alg = o->alg;
+  return run_batch(h, m, o, io, N, false, 0, nullptr,
+                   [&](const BatchPtrs& b, cudaStream_t s) { return launch_value<C>(h, alg, mp, sp, b, s); });
+}
+
+template <class C>
+int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                   const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  if (o->alg != CRNN_ALG_TSIT5)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5 only (so far)");
+  const int ncol = np + 1;
+  const int ct = (ncol + 31) / 32;
+  if (ct > 2) return fail(h, CRNN_ERR_UNSUPPORTED, "forward mode supports np <= 63; use the adjoint for larger np");
+  ModelP<C> mp; SolveP<C> sp; Packed pk;
+  int rc = pack<C>(h, m, o, yscale, loss_kind, mp, sp, pk);
+  if (rc) return rc;
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  rc = upload_cfg<C>(h, o, pk, sp, st);
+  if (rc) return rc;
+  rc = upload_seed<C>(h, m, dW_dp, np, ct, pk, st);
+  if (rc) return rc;
+  return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) {
+    return ct == 1 ? launch_sens<C, 1>(h, mp, sp, ncol, b, s) : launch_sens<C, 2>(h, mp, sp, ncol, b, s);
+  });
+}
+
+}  // namespace crnn_host

@@ -65,7 +65,7 @@ k_tsit5_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solv
     if (C::KIND == 1) { double a = Tval / (sp.abstol[NS] + fabs(Tval) * sp.reltol[NS]); s0 = fma(a, a, s0); }
     double d0 = sqrt(s0 / N), d1 = sqrt(s1 / N);
     double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-    dt0 = fmin(dt0, dtmax);
+    dt0 = jmin(dt0, dtmax);
 #pragma unroll
     for (int i = 0; i < NS; ++i) tmp[i] = fma(dt0, k1[i], u[i]);
     rhs_value<C>(mp, bT, tmp, k2); ++n_rhs;
@@ -73,9 +73,9 @@ k_tsit5_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solv
 #pragma unroll
     for (int i = 0; i < NS; ++i) { double b = (k2[i] - k1[i]) / sk[i]; s2 = fma(b, b, s2); }
     double d2 = sqrt(s2 / N) / dt0;
-    double dm = fmax(d1, d2);
+    double dm = jmax(d1, d2);
     double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
-    dt = fmin(fmin(100.0 * dt0, dt1), dtmax);
+    dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
   }
 
   double t = t0, qold = 1e-4, dt_last = 0.0;
@@ -87,8 +87,8 @@ k_tsit5_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solv
     ++iter;
     if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
     if (iter > sp.maxiters) { ret = CRNN_RET_MAXITERS; break; }
-    dt = fmin(dt, dtmax);
-    dt = fmin(dt, tend - t);
+    dt = jmin(dt, dtmax);
+    dt = jmin(dt, tend - t);
     if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
     bool bad = false;
 #pragma unroll
@@ -134,7 +134,7 @@ k_tsit5_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solv
     dt_last = dt;
     if (EEst <= 1.0) {
       ++n_acc;
-      qold = fmax(EEst, 1e-4);
+      qold = jmax(EEst, 1e-4);
       const double dtnew = dt / q;
       const double tprev = t;
       t = snap_t(t + dt, tend);
@@ -156,10 +156,10 @@ k_tsit5_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solv
       }
 #pragma unroll
       for (int i = 0; i < NS; ++i) { u[i] = un[i]; k1[i] = k7[i]; }
-      dt = fmin(dtnew, dtmax);
+      dt = jmin(dtnew, dtmax);
     } else {
       ++n_rej;
-      dt = dt / fmin(sp.inv_qmin, q11 / sp.gamma);
+      dt = dt / jmin(sp.inv_qmin, q11 / sp.gamma);
     }
   }
   if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;

@@ -45,6 +45,10 @@ typedef struct {
   double x[MAXN], dx[MAXN], d2x[MAXN], r[MAXR];
 } rhs_cache;
 
+/* Julia's min/max propagate NaN (C fmin/fmax drop it): a NaN RHS must surface as a NaN dt. */
+static inline double jmin(double a, double b) { return a < b ? a : (b <= a ? b : a + b); }
+static inline double jmax(double a, double b) { return a > b ? a : (b >= a ? b : a + b); }
+
 static inline double clampd(double v, double lo, double hi) {
   /* Julia Base.clamp: ifelse(x > hi, hi, ifelse(x < lo, lo, x)) */
   return v > hi ? hi : (v < lo ? lo : v);
@@ -220,15 +224,15 @@ static double initial_dt(const ctx_t* c, const double* U0, const double* F0, dou
   double d0 = initdt_norm(c, U0, U0, 1.0);
   double d1 = initdt_norm(c, F0, U0, 1.0);
   double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-  dt0 = fmin(dt0, tspan_len);
+  dt0 = jmin(dt0, tspan_len);
   double* U1 = work; double* F1 = work + tot;
   for (int q = 0; q < tot; ++q) U1[q] = U0[q] + dt0 * F0[q];
   eval_cols(c, U1, F1, k);
   for (int q = 0; q < tot; ++q) F1[q] -= F0[q];
   double d2 = initdt_norm(c, F1, U0, 1.0) / dt0;
-  double dm = fmax(d1, d2);
+  double dm = jmax(d1, d2);
   double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / c->order);
-  return fmin(fmin(100.0 * dt0, dt1), tspan_len);
+  return jmin(jmin(100.0 * dt0, dt1), tspan_len);
 }
 
 /* ---- Tsit5 tableau (Tsitouras 2011) ---- */
@@ -305,7 +309,7 @@ static double pi_q(const ctx_t* c, double EEst, double qold, double* q11) {
   if (EEst == 0.0) { *q11 = 0.0; return 1.0 / c->qmax; }
   *q11 = pow(EEst, c->beta1);
   double q = *q11 / pow(qold, c->beta2);
-  return fmax(1.0 / c->qmax, fmin(1.0 / c->qmin, q / c->gamma));
+  return jmax(1.0 / c->qmax, jmin(1.0 / c->qmin, q / c->gamma));
 }
 
 static double snap_t(double tnew, double tend) {
@@ -382,8 +386,8 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
     /* check_error! order: DtNaN, MaxIters, DtLessThanMin, Unstable */
     if (isnan(dt)) { ret = CRNN_RET_DTNAN; break; }
     if (iter > o->maxiters) { ret = CRNN_RET_MAXITERS; break; }
-    dt = fmin(dt, dtmax);
-    dt = fmin(dt, tend - t); /* modify_dt_for_tstops! */
+    dt = jmin(dt, dtmax);
+    dt = jmin(dt, tend - t); /* modify_dt_for_tstops! */
     if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
     if (has_nan(U, tot)) { ret = CRNN_RET_UNSTABLE; break; }
 
@@ -463,7 +467,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
     res->st.dt_last = dt;
     if (EEst <= 1.0) {
       res->st.n_accept++;
-      qold = fmax(EEst, 1e-4);
+      qold = jmax(EEst, 1e-4);
       double dtnew = dt / q;
       double tprev = t;
       t = snap_t(t + dt, tend);
@@ -495,10 +499,10 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       memcpy(U, Un, sizeof(double) * tot);
       if (!rosen) memcpy(K[0], K[6], sizeof(double) * tot);
       else { memcpy(K[0], K[5], sizeof(double) * tot); kc0 = kc; }
-      dt = fmin(dtnew, dtmax);
+      dt = jmin(dtnew, dtmax);
     } else {
       res->st.n_reject++;
-      dt = dt / fmin(1.0 / c->qmin, q11 / c->gamma);
+      dt = dt / jmin(1.0 / c->qmin, q11 / c->gamma);
     }
   }
   if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
