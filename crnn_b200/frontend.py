@@ -1,0 +1,101 @@
+"""Python mirror of the reference scripts' front end, batched.
+
+The Julia scripts keep `p2vec`, `predict_neuralode`, `loss_neuralode` and the ADAM epoch loop
+(case2/case2.jl:91-99,124-128,132-137,192-207); only `solve` and `ForwardDiff.gradient` are
+replaced by the C-ABI.  Julia is not available in this image, so this module restates that
+front end in Python with the same names and argument meaning; `julia/CRNNB200.jl` is the shim a
+maintainer would drop into the scripts.
+
+Semantics that change by batching: the scripts take one optimiser step per experiment
+(batch size 1, `for i_exp in randperm(n_exp_train)`); `train` here takes one step per
+mini-batch with the mean gradient, `batch=1` reproduces the per-experiment loop.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi, optim as _optim
+from .cases import CASES, Case
+from .engine import Engine
+
+
+class CRNNProblem:
+    """One script's globals: u0_list, ode_data_list, tsteps, yscale (+ dydt_scale), i_obs."""
+
+    def __init__(self, case: str | Case, u0_list, ode_data_list, yscale, i_obs=None, out_scale=None,
+                 engine: Engine | None = None, **opt_overrides):
+        self.case = CASES[case] if isinstance(case, str) else case
+        self.u0_list = np.ascontiguousarray(u0_list, dtype=np.float64)            # [n_exp, n_state]
+        self.i_obs = np.arange(self.case.ns) if i_obs is None else np.asarray(i_obs)
+        self.ode_data_list = np.ascontiguousarray(ode_data_list, dtype=np.float64)  # [n_exp, n_save, n_obs]
+        self.yscale = np.asarray(yscale, dtype=np.float64).reshape(-1)
+        self.out_scale = out_scale
+        self.engine = engine or Engine()
+        self.opts = self.case.opts(obs_idx=self.i_obs, **opt_overrides)
+
+    # -- the scripts' functions ------------------------------------------------------------
+    def p2vec(self, p):
+        w_in, w_b, w_out, _ = self.case.p2vec(p)
+        return w_in, w_b, w_out
+
+    def predict_neuralode(self, u0, p, sample=None):
+        """`predict_neuralode(u0, p)`: clamped saved states [n_obs, n_saved] (Julia orientation)
+        for one IC, or [N, n_save, n_obs] for a batch of ICs."""
+        model, _ = self.case.model(p, self.out_scale)
+        u0 = np.asarray(u0, dtype=np.float64)
+        single = u0.ndim == 1
+        nsu = None if sample is None else np.full(1 if single else u0.shape[0], sample, dtype=np.int32)
+        r = self.engine.solve_batch(model, self.opts, u0, n_save_used=nsu)
+        if single:
+            if r["retcode"][0] != _abi.RET_SUCCESS:
+                print("ode solver failed")   # robertson/rober_crnn.jl:130-134
+            return r["pred"][0, :r["n_saved"][0]].T
+        return r["pred"]
+
+    def loss_neuralode(self, p, i_exp, sample=None):
+        """`loss_neuralode(p, i_exp)` (0-based i_exp); an index array gives the per-experiment losses."""
+        return self.loss_grad(p, i_exp, sample=sample)[0]
+
+    def loss_grad(self, p, idx, sample=None):
+        """(loss, grad) for experiments `idx`: `ForwardDiff.gradient(x -> loss_neuralode(x, i), p)`
+        batched; the loss / gradient are means over the batch."""
+        idx = np.atleast_1d(np.asarray(idx))
+        model, seed = self.case.model(p, self.out_scale)
+        nsu = None if sample is None else np.broadcast_to(np.asarray(sample, dtype=np.int32), idx.shape).copy()
+        r = self.engine.loss_grad_batch(model, self.opts, seed, self.u0_list[idx], self.ode_data_list[idx],
+                                        self.yscale, self.case.loss_kind, n_save_used=nsu)
+        ok = r["n_saved"] > 0
+        n = max(int(ok.sum()), 1)
+        return float(np.nansum(r["loss"]) / n), r["grad_sum"] / n
+
+    # -- the epoch loop ---------------------------------------------------------------------
+    def train(self, p, opt: _optim.Optimiser, n_epoch, n_exp_train, batch=None, grad_max=None, rng=None,
+              sample_range=None, callback=None):
+        """The scripts' training loop (case2/case2.jl:192-207, robertson/rober_crnn.jl:215-234)."""
+        rng = rng or np.random.default_rng(0)
+        p = np.array(p, dtype=np.float64)
+        batch = batch or n_exp_train
+        history = []
+        for epoch in range(n_epoch):
+            perm = rng.permutation(n_exp_train)
+            gnorms = []
+            for lo in range(0, n_exp_train, batch):
+                idx = perm[lo:lo + batch]
+                sample = None if sample_range is None else rng.integers(sample_range[0], sample_range[1] + 1, size=idx.size)
+                _, grad = self.loss_grad(p, idx, sample=sample)
+                if grad_max is not None:
+                    grad, gn = _optim.clip_by_norm(grad, grad_max)
+                else:
+                    gn = float(np.linalg.norm(grad))
+                gnorms.append(gn)
+                opt.update(p, grad)
+            n_exp = self.u0_list.shape[0]
+            model, seed = self.case.model(p, self.out_scale)
+            losses = self.engine.loss_grad_batch(model, self.opts, seed, self.u0_list, self.ode_data_list,
+                                                 self.yscale, self.case.loss_kind)["loss"]
+            loss_train = float(np.mean(losses[:n_exp_train]))
+            loss_val = float(np.mean(losses[n_exp_train:])) if n_exp > n_exp_train else float("nan")
+            history.append((loss_train, loss_val, float(np.mean(gnorms))))
+            if callback is not None:
+                callback(p, loss_train, loss_val)
+        return p, history

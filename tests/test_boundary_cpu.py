@@ -1,0 +1,185 @@
+"""CPU tests of the drop-in boundary and the host logic: the C-ABI library loads and exports
+every symbol include/crnn_b200.h declares (no compute calls: there is no GPU here), the ctypes
+mirror matches the header, the product path fails loudly without CUDA, and the host-side
+pieces (optimisers, sharding, synthetic inputs, the world_size-2 exchange over gloo) work."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases, dist as cdist, optim, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "crnn_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crnn_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load_library()
+    declared = _declared_functions()
+    assert set(declared) == set(_abi.EXPORTS), (declared, _abi.EXPORTS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.crnn_version() == 100
+
+
+def test_ctypes_mirror_matches_header_layout():
+    """Compile a probe against the real header and compare sizeof/offsetof with the ctypes structs."""
+    probe = textwrap.dedent("""
+        #include <stdio.h>
+        #include <stddef.h>
+        #include "crnn_b200.h"
+        int main(void) {
+          printf("%zu %zu %zu ", sizeof(crnn_model), sizeof(crnn_opts), sizeof(crnn_stats));
+          printf("%zu %zu %zu %zu ", offsetof(crnn_model, lb), offsetof(crnn_model, out_scale), offsetof(crnn_model, w_out),
+                 offsetof(crnn_opts, maxiters));
+          printf("%zu %zu %zu %zu\\n", offsetof(crnn_opts, pred_clamp_lo), offsetof(crnn_opts, obs_idx), offsetof(crnn_opts, qmin),
+                 offsetof(crnn_opts, stream));
+          return 0;
+        }""")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c"); exe = os.path.join(d, "p")
+        open(c, "w").write(probe)
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([cc, "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    M, O, S = _abi.CModel, _abi.COpts, _abi.CStats
+    want = [ctypes.sizeof(M), ctypes.sizeof(O), ctypes.sizeof(S), M.lb.offset, M.out_scale.offset, M.w_out.offset,
+            O.maxiters.offset, O.pred_clamp_lo.offset, O.obs_idx.offset, O.qmin.offset, O.stream.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine refuses to exist; without the .so it refuses to load."""
+    import torch
+    from crnn_b200.engine import Engine, EngineError
+    if not torch.cuda.is_available():
+        with pytest.raises(EngineError):
+            Engine(0)
+        lib = _abi.load_library()
+        h = ctypes.c_void_p()
+        assert lib.crnn_create(ctypes.byref(h), 0) == _abi.ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        _abi.load_library(os.path.join(ROOT, "does_not_exist.so"))
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under crnn_b200/ or include/ may reference it."""
+    for base, _, files in os.walk(os.path.join(ROOT, "crnn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                txt = open(os.path.join(base, f)).read()
+                assert "oracle" not in txt.lower().replace("cpu oracle", "").replace("the oracle", ""), f"{f} mentions oracle"
+
+
+def test_model_and_opts_validation():
+    with pytest.raises(ValueError):
+        cases.CRNNModel(w_in=np.ones((3, 2)), w_b=np.zeros(3), w_out=np.ones((3, 2)))
+    with pytest.raises(ValueError):
+        cases.CRNNModel(w_in=np.ones((3, 2)), w_b=np.zeros(2), w_out=np.ones((3, 2)), rhs_kind=_abi.RHS_F1)
+    m = cases.true_model_case2()
+    assert (m.n_state, m.n_species, m.n_in, m.n_reac, m.n_w) == (7, 6, 7, 3, 42)
+    with pytest.raises(ValueError):
+        cases.SolveOpts(saveat=np.array([0.0, 60.0]), t0=0.0, t1=50.0).to_c(7)
+    with pytest.raises(ValueError):
+        cases.SolveOpts(saveat=np.array([0.0, 5.0]), t0=0.0, t1=50.0, obs_idx=np.array([9])).to_c(7)
+    o, keep = cases.CASES["robertson"].opts().to_c(3)
+    assert (o.n_abstol, o.n_reltol, o.n_save, o.alg) == (3, 3, 40, _abi.ALG_ROSENBROCK23)
+    assert abs(o.saveat[39] - 1e5) < 1e-6 and o.saveat[0] == 1.0
+
+
+def test_synth_inputs_follow_the_scripts_and_shard():
+    u = synth.make_u0("case2", 5000)
+    assert u[:, 0:2].min() >= 0.2 and u[:, 0:2].max() <= 2.2 and np.all(u[:, 2:6] == 0)
+    assert u[:, 6].min() >= 323 and u[:, 6].max() <= 343                  # case2.jl:62-65
+    r = synth.make_u0("robertson", 3000)
+    assert np.all(r[:, 1] == 1e-8) and r[:, [0, 2]].min() >= 0.5 and r[:, [0, 2]].max() <= 1.5
+    c3 = synth.make_u0("case3", 2000)
+    assert c3.min() >= 1e-3 and c3.max() <= 1.0                           # 10^(-3 U)
+    assert np.array_equal(synth.make_u0("case2", 700, start=900), u[900:1600])   # shard == slice of the whole
+    x = np.ones((1500, 4, 3))
+    assert np.array_equal(synth.noisy_targets(x[:200], 0.05, start=1100), synth.noisy_targets(x, 0.05)[1100:1300])
+    assert np.allclose(synth.yscale_from(np.arange(24.0).reshape(2, 4, 3), 1.0), [10, 10, 10])
+
+
+def test_shard_bounds_cover_exactly():
+    for N in (0, 1, 7, 65536, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [cdist.shard_bounds(N, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == N
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_optimisers_match_flux_formulas():
+    """ADAMW = ADAM then decoupled weight decay."""
+    p = np.array([1.0, -2.0]); g = np.array([0.5, 0.25])
+    opt = optim.ADAMW(5e-3, (0.9, 0.999), 1e-6)
+    p1 = opt.update(p.copy(), g)
+    m = 0.1 * g; v = 0.001 * g * g
+    d = m / (1 - 0.9) / (np.sqrt(v / (1 - 0.999)) + 1e-8) * 5e-3 + 1e-6 * p
+    np.testing.assert_allclose(p1, p - d, rtol=1e-14)
+    # second step uses beta powers ^2
+    p2 = opt.update(p1.copy(), g)
+    m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+    d = m / (1 - 0.81) / (np.sqrt(v / (1 - 0.999**2)) + 1e-8) * 5e-3 + 1e-6 * p1
+    np.testing.assert_allclose(p2, p1 - d, rtol=1e-13)
+    e = optim.ExpDecay(5e-3, 0.5, 2, 1e-4)
+    assert np.allclose(e.apply(p, g), 5e-3 * g) and np.allclose(e.apply(p, g), 2.5e-3 * g)   # decays on the 2nd call
+    gc, n = optim.clip_by_norm(np.array([30.0, 40.0]), 10.0)
+    assert n == 50.0 and np.allclose(gc, [6.0, 8.0])
+    n1 = optim.Optimiser(optim.NADAM(1e-3)).update(p.copy(), g)
+    assert np.all(np.abs(n1 - p) < 2e-3) and np.all(np.sign(p - n1) == np.sign(g))
+
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch, torch.distributed as dist
+from crnn_b200 import dist as cdist, synth
+from oracle import oracle
+from problems import make_problem
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+golden = json.load(open(os.path.join({root!r}, "tests", "golden", "checkpoints.json")))
+N = 37                                  # uneven split on purpose
+pb = make_problem("case2", golden, N)
+lo, hi = cdist.shard_bounds(N, world, rank)
+# each rank regenerates ITS shard of the inputs from the counter-based stream (no scatter)
+u0 = synth.make_u0("case2", hi - lo, start=lo)
+assert np.array_equal(u0, pb["u0"][lo:hi])
+r = oracle.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], u0, pb["data"][lo:hi], pb["yscale"])
+loss, grad = cdist.allreduce_loss_grad(r["loss"].sum(), hi - lo, r["grad_sum"])
+if rank == 0:
+    whole = oracle.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+    np.testing.assert_allclose(loss, whole["loss"].mean(), rtol=1e-13)
+    np.testing.assert_allclose(grad, whole["grad_sum"] / N, rtol=1e-11, atol=1e-15)
+    print("DIST_OK", world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_shard_and_allreduce_over_gloo(tmp_path):
+    """world_size 2 on CPU: shards + the one exchange ([loss, n, grad_sum] all-reduce) reproduce the
+    whole-batch result (the oracle stands in for the per-rank engine: there is no GPU here)."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK 2" in r.stdout
