@@ -153,7 +153,7 @@ def main():
     config = {"workload": "case2 (ns=6+T, nr=3, np=25) Tsit5 + forward sensitivities + fused MAE loss, "
                           f"{N_PER_GPU} ICs per GPU, abstol 1e-6 reltol 1e-3, t in [0,50], 50 saves",
               "n_traj_per_gpu": N_PER_GPU, "parallelism": f"dp{a.gpus} (trajectory shards, all-reduce of [loss, grad])",
-              "l2": "inputs larger than L2 (157 MB targets + 13 MB per-trajectory gradients per step)"}
+              "l2": "inputs larger than L2 (157 MB targets read + 157 MB saved states written per step)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -186,7 +186,7 @@ def main():
     red = torch.zeros(seed.shape[1] + 1, dtype=torch.float64, device=dev)
 
     def step_device():
-        r = eng.loss_grad_batch(model, opts, seed, u0_d, data_d, yscale, c.loss_kind, want_stats=False)
+        r = eng.loss_grad_batch(model, opts, seed, u0_d, data_d, yscale, c.loss_kind, want_stats=False, want_pred=True)
         if world > 1:   # the one exchange of the path: [sum loss, grad_sum] over NVLink
             red[0] = r["loss"].sum(); red[1:] = r["grad_sum"]
             dist.all_reduce(red)

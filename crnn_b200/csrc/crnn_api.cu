@@ -37,7 +37,9 @@ int crnn_create(crnn_handle** out, int device_id) {
   h->num_sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+            cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_cfg, cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; s < kPipe && ok; ++s) ok = cudaStreamCreateWithFlags(&h->s_slot[s], cudaStreamNonBlocking) == cudaSuccess;
   for (int s = 0; s < kPipe && ok; ++s)
     ok = cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
@@ -52,7 +54,7 @@ void crnn_destroy(crnn_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum};
+  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
     DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s], &h->d_loss[s], &h->d_nsaved[s],
@@ -61,8 +63,10 @@ void crnn_destroy(crnn_handle* h) {
     if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
     if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
     if (h->ev_out[s]) cudaEventDestroy(h->ev_out[s]);
+    if (h->s_slot[s]) cudaStreamDestroy(h->s_slot[s]);
   }
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (h->ev_cfg) cudaEventDestroy(h->ev_cfg);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);

@@ -60,9 +60,10 @@ struct crnn_handle {
   std::string err;
   int64_t launches = 0;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {}, ev_out[kPipe] = {};
-  // small per-call device state
-  DevBuf cfg, seed, ctr, partial;
+  cudaStream_t s_slot[kPipe] = {};  // one compute stream per pipeline slot: chunk c+1 fills the SMs chunk c's tail leaves idle
+  cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {}, ev_out[kPipe] = {}, ev_cfg = nullptr;
+  // small per-call device state.  ctr: [0] work queue (device mode), [1] reduce ticket, [2+s] queue of slot s
+  DevBuf cfg, seed, desc, ctr, partial;
   // staging for the host-buffer path (per pipeline slot) and full-batch gradients
   DevBuf d_u0[kPipe], d_nsu[kPipe], d_data[kPipe], d_pred[kPipe], d_loss[kPipe], d_nsaved[kPipe], d_ret[kPipe],
       d_stats[kPipe];
@@ -192,6 +193,7 @@ struct BatchPtrs {  // device pointers of one (sub)batch
   double* pred; double* loss; int* n_saved; int* retcode; crnn_stats* stats;
   double* grad_each;
   long long n;
+  int qslot;  // which work-queue counter of the handle this launch uses
 };
 
 // ---------------- value path launchers ----------------
@@ -213,31 +215,31 @@ int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& 
 }
 
 // ---------------- sensitivity path launchers ----------------
-template <class C, int CT>
+template <class C, int CT, bool R1>
 int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
                 cudaStream_t st) {
   if (b.n == 0) return CRNN_OK;
   constexpr int WARPS = (CT == 1 ? 8 : 4), MINB = 2;
-  auto kern = k_tsit5_sens<C, CT, WARPS, MINB>;
-  const size_t smem = sizeof(SensSmem<C, CT>) + WARPS * sizeof(WarpBuf<C, CT>);
+  auto kern = k_tsit5_sens<C, CT, WARPS, MINB, R1>;
+  const size_t smem = sizeof(SensSmem<C, CT, R1>) + WARPS * sizeof(WarpBuf<C, CT>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
   if (bps < 1) bps = 1;
   long long want = (b.n + WARPS - 1) / WARPS;
   unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
-  CK(cudaMemsetAsync(h->ctr.p, 0, sizeof(unsigned long long), st));
+  unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+  CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
   ProfScope prof(h, st);
-  kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), ncol, b.u0, b.nsu, b.n, b.data, b.loss,
-                                      b.grad_each, b.pred, b.n_saved, b.retcode, b.stats,
-                                      h->ctr.as<unsigned long long>());
+  kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
+                                      b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue);
   CK(cudaGetLastError());
   h->launches++;
   return CRNN_OK;
 }
 
 inline int launch_grad_reduce(crnn_handle* h, const double* grad_each, long long n, int np, double* grad_sum_dev,
-                       cudaStream_t st) {
+                              cudaStream_t st) {
   const int nb = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (n + 63) / 64));
   CK(h->partial.reserve((size_t)nb * np * sizeof(double)));
   k_grad_reduce<<<nb, 256, 0, st>>>(grad_each, n, np, h->partial.as<double>(), grad_sum_dev,
@@ -245,6 +247,50 @@ inline int launch_grad_reduce(crnn_handle* h, const double* grad_each, long long
   CK(cudaGetLastError());
   h->launches++;
   return CRNN_OK;
+}
+
+// Structured ("R1") form of the seed matrix (kernel_tsit5_sens.cuh): usable when every column of
+// dW/dp touches w_in in at most ONE row and w_out in at most ONE entry — true for every p2vec of
+// the reference scripts.  Otherwise ok = false and the caller uses the dense layout.
+struct R1Plan {
+  std::vector<R1Desc> desc;   // [32*ct], lane 0 of tile 0 = value column
+  std::vector<double> rows;   // [2*NR][32*ct]: a_j = dW_in[i_in, j], then b_j = db_j
+  bool ok = false;
+};
+
+template <class C>
+R1Plan plan_r1(const crnn_model* m, const double* dW_dp, int np) {
+  R1Plan pl;
+  const int ct = (np + 1 + 31) / 32, width = 32 * ct;
+  const int off_b = C::NIN * C::NR, off_out = off_b + C::NR;
+  pl.desc.assign(width, R1Desc{});
+  pl.rows.assign((size_t)2 * C::NR * width, 0.0);
+  for (int c = 0; c < np; ++c) {
+    const double* s = dW_dp + (size_t)C::NW * c;
+    R1Desc d{};
+    int i_in = -1, n_out = 0;
+    for (int j = 0; j < C::NR; ++j) {
+      for (int i = 0; i < C::NIN; ++i)
+        if (s[i + C::NIN * j] != 0.0) {
+          if (i_in >= 0 && i_in != i) return pl;
+          i_in = i;
+        }
+      for (int i = 0; i < C::NS; ++i)
+        if (s[off_out + i + C::NS * j] != 0.0) {
+          if (++n_out > 1) return pl;
+          d.i_out = i; d.j_out = j;
+          d.o = s[off_out + i + C::NS * j] * (m->out_scale ? m->out_scale[i] : 1.0);
+        }
+    }
+    d.i_in = i_in < 0 ? 0 : i_in;
+    pl.desc[c + 1] = d;
+    for (int j = 0; j < C::NR; ++j) {
+      pl.rows[(size_t)j * width + c + 1] = i_in < 0 ? 0.0 : s[i_in + C::NIN * j];
+      pl.rows[(size_t)(C::NR + j) * width + c + 1] = s[off_b + j];
+    }
+  }
+  pl.ok = true;
+  return pl;
 }
 
 // Pads dW/dp to [NW][32*CT] (column 0 = value lane = 0), folding out_scale into the w_out rows.
@@ -278,7 +324,7 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   const size_t ns = m->n_state, ps = (size_t)o->n_obs * o->n_save;
   if (o->buffers_on_device) {
     cudaStream_t st = (cudaStream_t)o->stream;
-    BatchPtrs b{io.u0, io.nsu, io.data, io.pred, io.loss, io.n_saved, io.retcode, io.stats, nullptr, N};
+    BatchPtrs b{io.u0, io.nsu, io.data, io.pred, io.loss, io.n_saved, io.retcode, io.stats, nullptr, N, 0};
     if (want_loss && np > 0) {
       CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
       b.grad_each = h->d_grad_each.as<double>();
@@ -294,7 +340,9 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
 
   // ---- host buffers: chunked, double-buffered pipeline (H2D stream || compute stream || D2H stream) ----
   if (want_loss && np > 0) CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
-  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(16384, (N + 7) / 8));
+  CK(cudaEventRecord(h->ev_cfg, h->s_compute));  // model/option uploads were enqueued on s_compute
+  for (int s = 0; s < kPipe; ++s) CK(cudaStreamWaitEvent(h->s_slot[s], h->ev_cfg, 0));
+  const int64_t chunk = std::max<int64_t>(2048, std::min<int64_t>(16384, (N + 7) / 8));
   const int64_t nchunk = (N + chunk - 1) / chunk;
   for (int s = 0; s < kPipe; ++s) {
     CK(h->d_u0[s].reserve(chunk * ns * sizeof(double)));
@@ -315,16 +363,17 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
     if (io.nsu) CK(cudaMemcpyAsync(h->d_nsu[s].p, io.nsu + lo, n * sizeof(int), cudaMemcpyHostToDevice, h->s_h2d));
     if (want_loss && ps) CK(cudaMemcpyAsync(h->d_data[s].p, io.data + lo * ps, n * ps * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
     CK(cudaEventRecord(h->ev_in[s], h->s_h2d));
-    CK(cudaStreamWaitEvent(h->s_compute, h->ev_in[s], 0));
-    if (c >= kPipe) CK(cudaStreamWaitEvent(h->s_compute, h->ev_out[s], 0));
+    cudaStream_t sc = h->s_slot[s];
+    CK(cudaStreamWaitEvent(sc, h->ev_in[s], 0));
+    if (c >= kPipe) CK(cudaStreamWaitEvent(sc, h->ev_out[s], 0));
     BatchPtrs b{h->d_u0[s].as<double>(), io.nsu ? h->d_nsu[s].as<int>() : nullptr,
                 want_loss ? h->d_data[s].as<double>() : nullptr, io.pred ? h->d_pred[s].as<double>() : nullptr,
                 want_loss ? h->d_loss[s].as<double>() : nullptr, h->d_nsaved[s].as<int>(), h->d_ret[s].as<int>(),
                 io.stats ? h->d_stats[s].as<crnn_stats>() : nullptr,
-                (want_loss && np > 0) ? h->d_grad_each.as<double>() + (size_t)lo * np : nullptr, n};
-    int rc = launch(b, h->s_compute);
+                (want_loss && np > 0) ? h->d_grad_each.as<double>() + (size_t)lo * np : nullptr, n, 2 + s};
+    int rc = launch(b, sc);
     if (rc) return rc;
-    CK(cudaEventRecord(h->ev_done[s], h->s_compute));
+    CK(cudaEventRecord(h->ev_done[s], sc));
     // D2H of this chunk's results on its own stream (a second copy engine)
     CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[s], 0));
     if (io.pred && ps) CK(cudaMemcpyAsync(io.pred + lo * ps, h->d_pred[s].p, n * ps * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
@@ -334,6 +383,7 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
     if (io.stats) CK(cudaMemcpyAsync(io.stats + lo, h->d_stats[s].p, n * sizeof(crnn_stats), cudaMemcpyDeviceToHost, h->s_d2h));
     CK(cudaEventRecord(h->ev_out[s], h->s_d2h));
   }
+  for (int s = 0; s < kPipe && s < nchunk; ++s) CK(cudaStreamWaitEvent(h->s_compute, h->ev_done[s], 0));
   if (want_loss && np > 0 && grad_sum) {
     if (N == 0) {
       std::memset(grad_sum, 0, np * sizeof(double));
@@ -346,6 +396,7 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   }
   CK(cudaStreamSynchronize(h->s_h2d));
   CK(cudaStreamSynchronize(h->s_d2h));
+  for (int s = 0; s < kPipe; ++s) CK(cudaStreamSynchronize(h->s_slot[s]));
   CK(cudaStreamSynchronize(h->s_compute));
   return CRNN_OK;
 }
@@ -382,10 +433,21 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   rc = upload_cfg<C>(h, o, pk, sp, st);
   if (rc) return rc;
-  rc = upload_seed<C>(h, m, dW_dp, np, ct, pk, st);
-  if (rc) return rc;
+  R1Plan pl = plan_r1<C>(m, dW_dp, np);
+  const bool r1 = pl.ok;
+  if (r1) {
+    CK(h->desc.reserve(pl.desc.size() * sizeof(R1Desc)));
+    CK(cudaMemcpyAsync(h->desc.p, pl.desc.data(), pl.desc.size() * sizeof(R1Desc), cudaMemcpyHostToDevice, st));
+    CK(h->seed.reserve(pl.rows.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(h->seed.p, pl.rows.data(), pl.rows.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    rc = upload_seed<C>(h, m, dW_dp, np, ct, pk, st);
+    if (rc) return rc;
+    CK(h->desc.reserve(sizeof(R1Desc)));
+  }
   return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) {
-    return ct == 1 ? launch_sens<C, 1>(h, mp, sp, ncol, b, s) : launch_sens<C, 2>(h, mp, sp, ncol, b, s);
+    if (r1) return ct == 1 ? launch_sens<C, 1, true>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, true>(h, mp, sp, ncol, b, s);
+    return ct == 1 ? launch_sens<C, 1, false>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, false>(h, mp, sp, ncol, b, s);
   });
 }
 

@@ -3,15 +3,29 @@
 // Replaces `ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` (case2/case2.jl:132-137,195;
 // Zygote.forwarddiff in case1/case1.jl:195-199): duals pushed through the adaptive solver.
 // Lane l of the warp owns dual column l (+32 per column tile): column 0 is the value, column
-// c >= 1 the partial d/dp_c.  All columns share one step sequence; the partials take part in
-// the error norm exactly like DiffEqBase's norm over Dual arrays.
+// c >= 1 the partial d/dp_c.  All columns share one step sequence; the partials take part in the
+// error norm exactly like DiffEqBase's norm over Dual arrays.
 //
 // Per stage the value path (NS logs, NR exps) is spread over lanes — lane i takes log(u_i),
 // lane j takes exp(z_j) — and broadcast through a few bytes of per-warp shared memory, so the
 // warp issues ONE log and ONE exp per stage instead of NS+NR; every lane then applies
 // J(u)*S + (df/dW)*dW/dp_c matrix-free to its own column.
+//
+// Two seed layouts (template flag R1):
+//   R1 = false  dense dW/dp column per lane, NW shared-memory loads per stage (any p2vec);
+//   R1 = true   structured columns: dW_in non-zero in ONE row i (any reactions), db arbitrary,
+//               dW_out non-zero in at most ONE entry (i', j') — the shape of every p2vec in the
+//               reference (a weight and its mirrored w_in entry, a bias, an activation energy, or
+//               a slope that rescales all biases / activation energies).  The forcing term is
+//               W_out*(r .* (a_j*x_i + b_j)) + o*r_j'*e_i': 2*NR seed loads instead of NW.
+//
+// Code-size discipline (profiles/r1_*): the whole integration is a phase machine around ONE
+// inlined instance of the RHS, ONE of the norm reduction and ONE of the loss/gradient block,
+// with the stage vectors in shared memory and the tableau in the constant bank.  The first,
+// fully unrolled version was 160 KB of SASS and spent 11 of 15 stall cycles per instruction
+// waiting for instruction fetch.
 // The loss (MAE-scaled or MAE-log) and its gradient are fused at each save point, so the
-// n_state x n_save x np sensitivity tensor never leaves registers.
+// n_state x n_save x np sensitivity tensor never leaves the SM.
 // A persistent grid pulls trajectory indices from a global atomic queue (step counts vary ~3x).
 #pragma once
 #include "crnn_dev.cuh"
@@ -31,14 +45,21 @@ __constant__ double c_tsA[8][6] = {
     {1.0, 0, 0, 0, 0, 0}};
 __constant__ double c_tsBT[7] = {ts::bt1, ts::bt2, ts::bt3, ts::bt4, ts::bt5, ts::bt6, ts::bt7};
 
-template <class C, int CT>
+// One structured seed column (R1 layout), one entry per lane and tile; its per-reaction parts
+// a_j = dW_in[i_in, j] and b_j = db_j sit in SensSmem::seed rows [0,NR) and [NR,2NR).
+struct R1Desc {
+  double o;  // dW_out[i_out, j_out] (out_scale folded in)
+  int i_in, i_out, j_out, pad;
+};
+
+template <class C, int CT, bool R1>
 struct alignas(16) SensSmem {
-  double seed[C::NW][32 * CT];  // dW/dp, zero padded; column 0 (value lane) is zero
+  double seed[R1 ? 2 * C::NR : C::NW][32 * CT];  // dW/dp (dense, or the a_j / b_j rows); column 0 = value = 0
   double w_in[C::NIN * C::NR];
   double w_b[C::NR];
-  double yscale[C::N];
+  double inv_ys[C::N];
   double abstol[C::N], reltol[C::N];
-  double dense_r[7][4];         // Tsit5 dense-output polynomial coefficients (lane j takes b_j)
+  double dense_r[7][4];  // Tsit5 dense-output polynomial coefficients (lane j takes b_j)
   int row2obs[C::N];
 };
 
@@ -47,36 +68,36 @@ struct alignas(16) SensSmem {
 template <class C, int CT>
 struct alignas(16) WarpBuf {
   double K[7][CT][C::NS][32];
-  double red[C::NS][32];  // column-sum scratch for the dual-aware norms
+  double red[C::NS][32];      // column-sum scratch of the dual-aware norms
   double y[C::N];
-  double x[C::N];
+  double x[C::N];             // x[NS] = -1/(R T) for F1
   double dx[C::N];
   double r[C::NR];
   double g[C::N];
-  double b[8];            // dense-output weights b_j(theta)
-  double term[C::N];
+  double b[8];                // dense-output weights b_j(theta)
+  double term[2][C::N];
 };
 
-template <class C, int CT, int WARPS, int MINB>
+template <class C, int CT, int WARPS, int MINB, bool R1>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ SolveP<C> sp,
-             const double* __restrict__ seed_dev, int ncol,
+             const double* __restrict__ seed_dev, const R1Desc* __restrict__ desc_dev, int ncol,
              const double* __restrict__ u0, const int* __restrict__ n_save_used, long long ntraj,
              const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
              double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
              crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SensSmem<C, CT>& sm = *reinterpret_cast<SensSmem<C, CT>*>(smem_raw);
-  WarpBuf<C, CT>* wbs = reinterpret_cast<WarpBuf<C, CT>*>(smem_raw + sizeof(SensSmem<C, CT>));
+  SensSmem<C, CT, R1>& sm = *reinterpret_cast<SensSmem<C, CT, R1>*>(smem_raw);
+  WarpBuf<C, CT>* wbs = reinterpret_cast<WarpBuf<C, CT>*>(smem_raw + sizeof(SensSmem<C, CT, R1>));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpBuf<C, CT>& wb = wbs[warp];
 
-  for (int q = threadIdx.x; q < NW * 32 * CT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
+  for (int q = threadIdx.x; q < (R1 ? 2 * NR : NW) * 32 * CT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
   for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = mp.w_in[q];
   for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = mp.w_b[q];
   for (int q = threadIdx.x; q < N; q += blockDim.x) {
-    sm.yscale[q] = 1.0 / sp.inv_yscale[q];
+    sm.inv_ys[q] = sp.inv_yscale[q];
     sm.row2obs[q] = sp.row2obs[q];
     sm.abstol[q] = sp.abstol[q];
     sm.reltol[q] = sp.reltol[q];
@@ -94,20 +115,23 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
 
   // columns owned by this lane; live = takes part in norms
   bool isval[CT], live[CT];
+  double d_o[CT];
+  int d_iin[CT], d_iout[CT], d_jout[CT];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
     isval[t] = (t == 0 && lane == 0);
+    d_o[t] = 0.0; d_iin[t] = d_iout[t] = d_jout[t] = 0;
+    if (R1) {
+      const R1Desc d = desc_dev[lane + 32 * t];
+      d_o[t] = d.o; d_iin[t] = d.i_in; d_iout[t] = d.i_out; d_jout[t] = d.j_out;
+    }
     live[t] = (lane + 32 * t) < ncol && (sp.incl_sens || isval[t]);
   }
+  // lane i < NS keeps the per-row controller state (tolerances, |u| magnitudes)
   double my_at = 0.0, my_rt = 0.0;
   if (lane < NS) { my_at = sm.abstol[lane]; my_rt = sm.reltol[lane]; }
 
-  // Phase machine (one warp-uniform `phase` per trajectory).  Every RHS evaluation — the two
-  // of the initial-step heuristic and the six Tsit5 stages — goes through ONE instance of the
-  // warp-cooperative RHS inside a runtime stage loop, the stage vectors live in shared memory
-  // and the tableau in the constant bank, so the hot loop is a few KB of code (the fully
-  // unrolled first version was 160 KB of SASS and stalled on instruction fetch: profiles/).
-  constexpr int PH_F0 = 0, PH_F1 = 7, PH_SAVE = 8;   // phases 1..6 are the Tsit5 stages
+  constexpr int PH_F0 = 0, PH_F1 = 7, PH_SAVE = 8;  // phases 1..6 are the Tsit5 stages
 
   while (true) {
     unsigned long long tq = 0;
@@ -124,6 +148,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
     }
+    if (C::KIND == 1 && lane == 0) wb.x[NS] = xT;
 #pragma unroll
     for (int t = 0; t < CT; ++t)
 #pragma unroll
@@ -143,40 +168,11 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
     const size_t pbase = (size_t)traj * sp.n_obs * sp.n_save;
 
-    // lane i < NS returns sum over participating columns of V[.][i]^2 (others: garbage-free 0)
-    auto colsq = [&](const double (&V)[CT][NS]) -> double {
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int t = 0; t < CT; ++t) s = live[t] ? fma(V[t][i], V[t][i], s) : s;
-        wb.red[i][lane] = s;
-      }
-      __syncwarp();
-      double tot = 0.0;
-      if (lane < NS) {
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) tot += wb.red[lane][(k + lane) & 31];  // skewed: conflict-free
-      }
-      return tot;
-    };
-    // all lanes: sum_i term_i, term held by lane i < NS
-    auto sum_terms = [&](double term) -> double {
-      __syncwarp();
-      if (lane < NS) wb.term[lane] = term;
-      __syncwarp();
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < NS; ++i) s += wb.term[i];
-      return s;
-    };
-
     int n_rhs = 0, n_acc = 0, n_rej = 0;
     double G[CT], loss_acc = 0.0;
 #pragma unroll
     for (int t = 0; t < CT; ++t) G[t] = 0.0;
-    double asum = my_u0 * my_u0, bsum = 0.0;  // lane i: dual magnitude^2 of u_i at t_n / t_{n+1}
+    double asum = my_u0 * my_u0, bsum = 0.0;  // lane i < NS: dual magnitude^2 of u_i at t_n / t_{n+1}
     double t = t0, tprev = t0, dt = 0.0, dt0 = 0.0, d1 = 0.0, dtnew = 0.0, qold = 1e-4, dt_last = 0.0;
     int isave = 0, ret = CRNN_RET_DEFAULT, phase = PH_F0, k1s = 0;  // k1s: slot of K1 (0 or 6), K7 in 6-k1s
     long long iter = 0;
@@ -191,6 +187,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
             for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
+#pragma unroll 1
           for (int j = 0; j < nj; ++j) {
             const double a = c_tsA[phase][j];
             const int slot = (j == 0) ? k1s : j;
@@ -216,7 +213,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           const double uc = clampd(yi, mp.lb, mp.ub);
           const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
           wb.x[lane] = log(uc);
-          wb.dx[lane] = inside ? 1.0 / uc : 0.0;
+          wb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
         __syncwarp();
         if (lane < NR) {
@@ -227,10 +224,9 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         }
         __syncwarp();
         {
-          double x[NIN], dx[NS], r[NR];
+          double dx[NS], r[NR];
 #pragma unroll
-          for (int i = 0; i < NS; ++i) { x[i] = wb.x[i]; dx[i] = wb.dx[i]; }
-          if (C::KIND == 1) x[NS] = xT;
+          for (int i = 0; i < NS; ++i) dx[i] = wb.dx[i];
 #pragma unroll
           for (int j = 0; j < NR; ++j) r[j] = wb.r[j];
 #pragma unroll
@@ -239,23 +235,32 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             double sd[NS], q[NR];
 #pragma unroll
             for (int i = 0; i < NS; ++i) sd[i] = Y[tt][i] * dx[i];
+            const double xin = R1 ? wb.x[d_iin[tt]] : 0.0;
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-              double zd = sm.seed[NIN * NR + j][lc];
+              double zd = R1 ? fma(sm.seed[j][lc], xin, sm.seed[NR + j][lc]) : sm.seed[NIN * NR + j][lc];
 #pragma unroll
               for (int i = 0; i < NS; ++i) zd = fma(mp.w_in[i + NIN * j], sd[i], zd);
+              if (!R1) {
 #pragma unroll
-              for (int i = 0; i < NIN; ++i) zd = fma(sm.seed[i + NIN * j][lc], x[i], zd);
+                for (int i = 0; i < NS; ++i) zd = fma(sm.seed[i + NIN * j][lc], wb.x[i], zd);
+                if (C::KIND == 1) zd = fma(sm.seed[NS + NIN * j][lc], xT, zd);
+              }
               if (isval[tt]) zd = 1.0;
               q[j] = r[j] * zd;
             }
+            const double ro = R1 ? d_o[tt] * wb.r[d_jout[tt]] : 0.0;
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
               double s = 0.0;
 #pragma unroll
               for (int j = 0; j < NR; ++j) s = fma(mp.w_out[i + NS * j], q[j], s);
+              if (!R1) {
 #pragma unroll
-              for (int j = 0; j < NR; ++j) s = fma(sm.seed[NIN * NR + NR + i + NS * j][lc], r[j], s);
+                for (int j = 0; j < NR; ++j) s = fma(sm.seed[NIN * NR + NR + i + NS * j][lc], r[j], s);
+              } else if (d_iout[tt] == i) {
+                s += ro;
+              }
               KO[tt][i] = s;
             }
           }
@@ -272,97 +277,122 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             for (int i = 0; i < NS; ++i) wb.K[dst][tt][i][lane] = KO[tt][i];
         }
 
-        if (phase == PH_F0) {
-          // initial step size, part 1 (ode_determine_initdt)
-          const double f2 = colsq(KO);
-          double t0s = 0.0, t1s = 0.0;
-          if (lane < NS) {
-            const double a = my_u0 / my_sk;
-            t0s = a * a;
-            t1s = f2 / (my_sk * my_sk);
-          }
-          if (C::KIND == 1 && lane == NS) {
-            const double a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]);
-            t0s = a * a;
-          }
-          // two sums through the same scratch
-          __syncwarp();
-          if (lane < N) { wb.term[lane] = t0s; wb.g[lane] = t1s; }
-          __syncwarp();
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < N; ++i) { s0 += wb.term[i]; s1 += wb.g[i]; }
-          const double d0 = sqrt(s0 / N);
-          d1 = sqrt(s1 / N);
-          dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-          dt0 = jmin(dt0, dtmax);
-          phase = PH_F1;
-        } else if (phase == PH_F1) {
-          // initial step size, part 2; then the pseudo-step that saves t0
-#pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-            for (int i = 0; i < NS; ++i) KO[tt][i] -= wb.K[k1s][tt][i][lane];
-          const double f2 = colsq(KO);
-          const double s2 = sum_terms(lane < NS ? f2 / (my_sk * my_sk) : 0.0);
-          const double d2 = sqrt(s2 / N) / dt0;
-          const double dm = jmax(d1, d2);
-          const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
-          dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
-          dtnew = dt;
-          // pseudo-step: proposed state = U, K7 = K1, so the commit below is a no-op
-#pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              Y[tt][i] = U[tt][i];
-              wb.K[6 - k1s][tt][i][lane] = wb.K[k1s][tt][i][lane];
-            }
-          bsum = asum;
-          phase = PH_SAVE;
-        } else if (phase < 6) {
+        if (phase >= 1 && phase < 6) {
           ++phase;
         } else {
-          // all seven stages done: error estimate, PI controller, accept / reject
-#pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-            for (int i = 0; i < NS; ++i) KO[tt][i] *= c_tsBT[6];
-          for (int j = 0; j < 6; ++j) {
-            const double a = c_tsBT[j];
-            const int slot = (j == 0) ? k1s : j;
+          // ---- phases that need a norm: F0 (|f0|), F1 (|f1 - f0|), stage 6 (error estimate) ----
+          if (phase == PH_F1) {
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
-              for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, wb.K[slot][tt][i][lane], KO[tt][i]);
+              for (int i = 0; i < NS; ++i) KO[tt][i] -= wb.K[k1s][tt][i][lane];
+          } else if (phase == 6) {
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt)
+#pragma unroll
+              for (int i = 0; i < NS; ++i) KO[tt][i] *= c_tsBT[6];
+#pragma unroll 1
+            for (int j = 0; j < 6; ++j) {
+              const double a = c_tsBT[j];
+              const int slot = (j == 0) ? k1s : j;
+#pragma unroll
+              for (int tt = 0; tt < CT; ++tt)
+#pragma unroll
+                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, wb.K[slot][tt][i][lane], KO[tt][i]);
+            }
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt)
+#pragma unroll
+              for (int i = 0; i < NS; ++i) KO[tt][i] *= dt;
           }
+          // (a) lane i < NS <- sum over participating columns of KO[.][i]^2 (pass 0) and, for the
+          //     error estimate, of Y[.][i]^2 (pass 1: dual magnitude of u_{n+1}).  One code instance.
+          double rsum = 0.0;
+          const int npass = (phase == 6) ? 2 : 1;
+#pragma unroll 1
+          for (int pass = 0; pass < npass; ++pass) {
+            __syncwarp();
 #pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
+            for (int i = 0; i < NS; ++i) {
+              double sa = 0.0;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) KO[tt][i] *= dt;
-          const double e2 = colsq(KO);
-          bsum = colsq(Y);
-          double term = 0.0;
+              for (int tt = 0; tt < CT; ++tt) {
+                const double v = pass == 0 ? KO[tt][i] : Y[tt][i];
+                sa = live[tt] ? fma(v, v, sa) : sa;
+              }
+              wb.red[i][lane] = sa;
+            }
+            __syncwarp();
+            if (lane < NS) {
+              double tot = 0.0;
+#pragma unroll 8
+              for (int k = 0; k < 32; ++k) tot += wb.red[lane][(k + lane) & 31];  // skewed: conflict-free
+              if (pass == 0) rsum = tot; else bsum = tot;
+            }
+          }
+          // (b) per-row terms (lane i < NS), then their sums in every lane
+          double term0 = 0.0, term1 = 0.0;
           if (lane < NS) {
-            // max(|u0|,|u1|) with dual magnitudes; sqrt is monotone, so one sqrt serves both
-            const double sc = fma(sqrt(fmax(asum, bsum)), my_rt, my_at);
-            term = e2 / (sc * sc);
+            if (phase == 6) {
+              // max(|u0|,|u1|) with dual magnitudes; sqrt is monotone, so one sqrt serves both
+              const double sc = fma(sqrt(fmax(asum, bsum)), my_rt, my_at);
+              term0 = rsum / (sc * sc);
+            } else {
+              const double a = my_u0 / my_sk;
+              term0 = rsum / (my_sk * my_sk);
+              term1 = a * a;
+            }
+            wb.term[0][lane] = term0;
+            wb.term[1][lane] = term1;
           }
-          const double EEst = sqrt(sum_terms(term) / N);
-          double q11;
-          const double q = pi_controller<C>(sp, EEst, qold, q11);
-          dt_last = dt;
-          if (EEst <= 1.0) {
-            ++n_acc;
-            qold = jmax(EEst, 1e-4);
-            dtnew = dt / q;
-            tprev = t;
-            t = snap_t(t + dt, tend);
+          __syncwarp();
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) { s0 += wb.term[0][i]; s1 += wb.term[1][i]; }
+
+          if (phase == PH_F0) {
+            // initial step size, part 1 (ode_determine_initdt)
+            if (C::KIND == 1) { const double a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]); s1 = fma(a, a, s1); }
+            const double d0 = sqrt(s1 / N);
+            d1 = sqrt(s0 / N);
+            dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            dt0 = jmin(dt0, dtmax);
+            phase = PH_F1;
+          } else if (phase == PH_F1) {
+            // initial step size, part 2; then the pseudo-step that saves t0
+            const double d2 = sqrt(s0 / N) / dt0;
+            const double dm = jmax(d1, d2);
+            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
+            dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
+            dtnew = dt;
+            // pseudo-step: proposed state = U, K7 = K1, so the commit below is a no-op
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt)
+#pragma unroll
+              for (int i = 0; i < NS; ++i) {
+                Y[tt][i] = U[tt][i];
+                wb.K[6 - k1s][tt][i][lane] = wb.K[k1s][tt][i][lane];
+              }
+            bsum = asum;
             phase = PH_SAVE;
           } else {
-            ++n_rej;
-            dt = dt / jmin(sp.inv_qmin, q11 / sp.gamma);
-            phase = 1;
+            // all seven stages done: PI controller, accept / reject
+            const double EEst = sqrt(s0 / N);
+            double q11;
+            const double q = pi_controller<C>(sp, EEst, qold, q11);
+            dt_last = dt;
+            if (EEst <= 1.0) {
+              ++n_acc;
+              qold = jmax(EEst, 1e-4);
+              dtnew = dt / q;
+              tprev = t;
+              t = snap_t(t + dt, tend);
+              phase = PH_SAVE;
+            } else {
+              ++n_rej;
+              dt = dt / jmin(sp.inv_qmin, q11 / sp.gamma);
+              phase = 1;
+            }
           }
         }
       } else {
@@ -387,6 +417,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
               for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
+#pragma unroll 1
             for (int j = 0; j < 7; ++j) {
               const double bj = wb.b[j];
               const int slot = (j == 0) ? k1s : (j == 6 ? 6 - k1s : j);
@@ -417,9 +448,9 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const double d = __ldg(data + off);
               double diff;
               if (sp.loss_kind == CRNN_LOSS_MAE_SCALED) {
-                const double ys = sm.yscale[lane];
-                diff = d / ys - yc / ys;
-                g = (signbit(diff) ? 1.0 : -1.0) / ys;
+                const double iy = sm.inv_ys[lane];
+                diff = d * iy - yc * iy;
+                g = signbit(diff) ? iy : -iy;
               } else {
                 diff = log(clampd(d, sp.pred_lo, sp.pred_hi)) - log(yc);
                 g = (signbit(diff) ? 1.0 : -1.0) / yc;
