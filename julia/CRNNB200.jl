@@ -1,0 +1,114 @@
+# CRNNB200.jl — thin Julia shim over libcrnn_b200.so for the DENG-MIT/CRNN scripts.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  It is kept
+# deliberately thin (one `ccall` per C entry point, column-major arrays passed straight
+# through) so that it can be checked by reading it against include/crnn_b200.h.
+#
+# What stays in the script:  p2vec, the optimiser (`update!`), the epoch loop, checkpoints.
+# What this replaces:        `solve(prob, alg, u0=u0, p=p, ...)` inside predict_neuralode
+#                            (case2/case2.jl:126) and `ForwardDiff.gradient(x -> loss_neuralode(x, i), p)`
+#                            (case2/case2.jl:195).
+module CRNNB200
+
+using ForwardDiff
+
+const LIB = get(ENV, "CRNN_B200_LIB", "libcrnn_b200.so")
+
+# mirrors of the C structs (include/crnn_b200.h)
+struct CModel
+    n_state::Int32; n_species::Int32; n_in::Int32; n_reac::Int32; rhs_kind::Int32; reserved0::Int32
+    lb::Float64; ub::Float64; gas_R::Float64
+    out_scale::Ptr{Float64}; w_in::Ptr{Float64}; w_b::Ptr{Float64}; w_out::Ptr{Float64}
+end
+struct COpts
+    alg::Int32; sens_mode::Int32; err_norm_includes_sens::Int32; n_save::Int32; n_obs::Int32
+    n_abstol::Int32; n_reltol::Int32; buffers_on_device::Int32
+    maxiters::Int64
+    t0::Float64; t1::Float64; pred_clamp_lo::Float64; pred_clamp_hi::Float64
+    abstol::Ptr{Float64}; reltol::Ptr{Float64}; saveat::Ptr{Float64}; obs_idx::Ptr{Int32}
+    qmin::Float64; qmax::Float64; gamma::Float64; beta1::Float64; beta2::Float64
+    stream::Ptr{Cvoid}
+end
+
+mutable struct Engine
+    h::Ptr{Cvoid}
+    function Engine(device::Integer=-1)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:crnn_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, device)
+        rc == 0 || error("crnn_create failed ($rc): no CUDA device (there is no CPU fallback)")
+        e = new(ref[]); finalizer(x -> ccall((:crnn_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), e); e
+    end
+end
+check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:crnn_last_error, LIB), Cstring, (Ptr{Cvoid},), e.h)))
+
+"Problem constants a script defines once (tsteps, tolerances, lb/ub, i_obs, dydt_scale ...)."
+Base.@kwdef struct Setup
+    rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state)
+    alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23
+    lb::Float64; ub::Float64
+    abstol::Vector{Float64} = [1e-6]; reltol::Vector{Float64} = [1e-3]
+    tspan::Tuple{Float64,Float64}; saveat::Vector{Float64}
+    obs_idx::Vector{Int32}         # 0-based rows of u (i_obs .- 1)
+    pred_clamp::Tuple{Float64,Float64} = (-Inf, Inf)
+    out_scale::Union{Nothing,Vector{Float64}} = nothing
+    maxiters::Int64 = 100_000
+    loss_kind::Int32 = 0           # 0 MAE-scaled, 1 MAE-log (case3)
+end
+
+function with_structs(f, s::Setup, w_in, w_b, w_out)
+    w_in = Matrix{Float64}(w_in); w_b = Vector{Float64}(w_b); w_out = Matrix{Float64}(w_out)
+    ns, nr = size(w_out); n_in = size(w_in, 1)
+    osc = s.out_scale === nothing ? Float64[] : s.out_scale
+    GC.@preserve w_in w_b w_out osc s begin
+        m = CModel(n_in, ns, n_in, nr, s.rhs_kind, 0, s.lb, s.ub, 1.98720425864083e-3,
+                   isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out))
+        o = COpts(s.alg, 1, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
+                  s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
+                  pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
+                  0.0, 0.0, 0.0, 0.0, 0.0, C_NULL)
+        f(Ref(m), Ref(o))
+    end
+end
+
+"""
+    predict_neuralode(e, s, p2vec, u0s, p) -> pred[n_obs, n_save, N], n_saved, retcode
+
+Drop-in for the scripts' `predict_neuralode(u0, p)`, batched: `u0s` is n_state × N.
+"""
+function predict_neuralode(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, p)
+    w_in, w_b, w_out = p2vec(p)
+    N = size(u0s, 2)
+    pred = zeros(length(s.obs_idx), length(s.saveat), N)
+    n_saved = zeros(Int32, N); ret = zeros(Int32, N)
+    with_structs(s, w_in, w_b, w_out) do m, o
+        check(e, ccall((:crnn_solve_batch, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+              e.h, m, o, u0s, N, C_NULL, pred, n_saved, ret, C_NULL))
+    end
+    pred, n_saved, ret
+end
+
+"""
+    loss_grad(e, s, p2vec, u0s, data, yscale, p) -> (mean loss, mean gradient)
+
+Replaces `ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` for a batch of experiments:
+`data` is n_obs × n_save × N (a `permutedims` of the scripts' `ode_data_list[i, :, :]`).
+The result feeds the unchanged `update!(opt, p, grad)` line.
+"""
+function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array{Float64,3}, yscale::Vector{Float64}, p)
+    flat(q) = (w = p2vec(q); vcat(vec(w[1]), vec(w[2]), vec(w[3])))
+    w_in, w_b, w_out = p2vec(p)
+    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat, p))      # n_w × np seed matrix
+    N = size(u0s, 2); np_ = length(p)
+    loss = zeros(N); grad = zeros(np_); n_saved = zeros(Int32, N); ret = zeros(Int32, N)
+    with_structs(s, w_in, w_b, w_out) do m, o
+        check(e, ccall((:crnn_loss_grad_batch, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int32},
+               Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+              e.h, m, o, dWdp, np_, u0s, N, C_NULL, data, yscale, s.loss_kind, loss, grad, C_NULL, n_saved, ret, C_NULL))
+    end
+    ok = n_saved .> 0
+    sum(loss[ok]) / max(count(ok), 1), grad ./ max(count(ok), 1)
+end
+
+end # module
