@@ -215,18 +215,23 @@ int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& 
 }
 
 // ---------------- sensitivity path launchers ----------------
-template <class C, int CT, bool R1>
+template <class C, int CT, bool R1, int WPT = 1>
 int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
                 cudaStream_t st) {
   if (b.n == 0) return CRNN_OK;
-  constexpr int WARPS = (CT == 1 ? 8 : 4), MINB = 2;
-  auto kern = k_tsit5_sens<C, CT, WARPS, MINB, R1>;
-  const size_t smem = sizeof(SensSmem<C, CT, R1>) + WARPS * sizeof(WarpBuf<C, CT>);
+  // warps per block: 16 warps/SM in two blocks for the single-warp layouts; one or two warp
+  // groups per block when WPT warps share a trajectory
+  constexpr int WARPS = WPT == 1 ? (CT == 1 ? 8 : 4) : (WPT <= 4 ? 2 * WPT : WPT);
+  constexpr int MINB = WPT == 1 ? 2 : 1;
+  auto kern = k_tsit5_sens<C, CT, WARPS, MINB, R1, WPT>;
+  const size_t smem = sizeof(SensSmem<C, CT, R1, WPT>) + WARPS * sizeof(WarpBuf<C, CT>);
+  if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
   if (bps < 1) bps = 1;
-  long long want = (b.n + WARPS - 1) / WARPS;
+  constexpr int GROUPS = WARPS / WPT;
+  long long want = (b.n + GROUPS - 1) / GROUPS;
   unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
   unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
   CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
@@ -261,7 +266,8 @@ struct R1Plan {
 template <class C>
 R1Plan plan_r1(const crnn_model* m, const double* dW_dp, int np) {
   R1Plan pl;
-  const int ct = (np + 1 + 31) / 32, width = 32 * ct;
+  const int tiles = (np + 1 + 31) / 32;
+  const int width = 32 * (tiles <= 2 ? tiles : (tiles <= 3 ? 3 : (tiles <= 5 ? 5 : 8)));  // matches the WPT dispatch
   const int off_b = C::NIN * C::NR, off_out = off_b + C::NR;
   pl.desc.assign(width, R1Desc{});
   pl.rows.assign((size_t)2 * C::NR * width, 0.0);
@@ -425,8 +431,8 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   if (o->alg != CRNN_ALG_TSIT5)
     return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5 only (so far)");
   const int ncol = np + 1;
-  const int ct = (ncol + 31) / 32;
-  if (ct > 2) return fail(h, CRNN_ERR_UNSUPPORTED, "forward mode supports np <= 63; use the adjoint for larger np");
+  const int ct = (ncol + 31) / 32;  // 32-lane tiles of dual columns
+  if (ct > 8) return fail(h, CRNN_ERR_UNSUPPORTED, "forward mode supports np <= 255");
   ModelP<C> mp; SolveP<C> sp; Packed pk;
   int rc = pack<C>(h, m, o, yscale, loss_kind, mp, sp, pk);
   if (rc) return rc;
@@ -435,6 +441,8 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   if (rc) return rc;
   R1Plan pl = plan_r1<C>(m, dW_dp, np);
   const bool r1 = pl.ok;
+  if (!r1 && ct > 2)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "np > 63 needs a structured seed (one w_in row and one w_out entry per column)");
   if (r1) {
     CK(h->desc.reserve(pl.desc.size() * sizeof(R1Desc)));
     CK(cudaMemcpyAsync(h->desc.p, pl.desc.data(), pl.desc.size() * sizeof(R1Desc), cudaMemcpyHostToDevice, st));
@@ -446,6 +454,11 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
     CK(h->desc.reserve(sizeof(R1Desc)));
   }
   return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) {
+    if (r1 && ct > 2) {  // several warps per trajectory
+      if (ct <= 3) return launch_sens<C, 1, true, 3>(h, mp, sp, ncol, b, s);
+      if (ct <= 5) return launch_sens<C, 1, true, 5>(h, mp, sp, ncol, b, s);
+      return launch_sens<C, 1, true, 8>(h, mp, sp, ncol, b, s);
+    }
     if (r1) return ct == 1 ? launch_sens<C, 1, true>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, true>(h, mp, sp, ncol, b, s);
     return ct == 1 ? launch_sens<C, 1, false>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, false>(h, mp, sp, ncol, b, s);
   });

@@ -52,9 +52,9 @@ struct R1Desc {
   int i_in, i_out, j_out, pad;
 };
 
-template <class C, int CT, bool R1>
+template <class C, int CT, bool R1, int WPT = 1>
 struct alignas(16) SensSmem {
-  double seed[R1 ? 2 * C::NR : C::NW][32 * CT];  // dW/dp (dense, or the a_j / b_j rows); column 0 = value = 0
+  double seed[R1 ? 2 * C::NR : C::NW][32 * CT * WPT];  // dW/dp (dense, or the a_j / b_j rows); column 0 = value = 0
   double w_in[C::NIN * C::NR];
   double w_b[C::NR];
   double inv_ys[C::N];
@@ -76,9 +76,14 @@ struct alignas(16) WarpBuf {
   double g[C::N];
   double b[8];                // dense-output weights b_j(theta)
   double term[2][C::N];
+  double part[8][C::N];       // WPT > 1: per-warp partial row sums of the trajectory's warp group
+  long long trajslot;         // WPT > 1: trajectory index broadcast
+  int flag, pad;              // WPT > 1: NaN flag of the group
 };
 
-template <class C, int CT, int WARPS, int MINB, bool R1>
+// WPT warps share one trajectory (32*CT*WPT dual columns): the group synchronises on a named
+// barrier instead of __syncwarp, the small broadcast arrays live in the group leader's WarpBuf.
+template <class C, int CT, int WARPS, int MINB, bool R1, int WPT = 1>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ SolveP<C> sp,
              const double* __restrict__ seed_dev, const R1Desc* __restrict__ desc_dev, int ncol,
@@ -88,12 +93,20 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
              crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SensSmem<C, CT, R1>& sm = *reinterpret_cast<SensSmem<C, CT, R1>*>(smem_raw);
-  WarpBuf<C, CT>* wbs = reinterpret_cast<WarpBuf<C, CT>*>(smem_raw + sizeof(SensSmem<C, CT, R1>));
+  static_assert(WPT >= 1 && WPT <= 8 && WARPS % WPT == 0 && (WPT == 1 || CT == 1), "bad warp grouping");
+  SensSmem<C, CT, R1, WPT>& sm = *reinterpret_cast<SensSmem<C, CT, R1, WPT>*>(smem_raw);
+  WarpBuf<C, CT>* wbs = reinterpret_cast<WarpBuf<C, CT>*>(smem_raw + sizeof(SensSmem<C, CT, R1, WPT>));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpBuf<C, CT>& wb = wbs[warp];
+  const int wig = warp % WPT, grp = warp / WPT;  // warp in group, group in block
+  WarpBuf<C, CT>& wb = wbs[warp];        // own: K, red
+  WarpBuf<C, CT>& gb = wbs[warp - wig];  // group leader's: broadcast arrays
+  auto gsync = [&]() {
+    if (WPT == 1) __syncwarp();
+    else if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPT * 32) : "memory");  // immediate ids: a register id
+    else asm volatile("bar.sync 2, %0;" ::"n"(WPT * 32) : "memory");                 // would reserve all 16 barriers
+  };
 
-  for (int q = threadIdx.x; q < (R1 ? 2 * NR : NW) * 32 * CT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
+  for (int q = threadIdx.x; q < (R1 ? 2 * NR : NW) * 32 * CT * WPT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
   for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = mp.w_in[q];
   for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = mp.w_b[q];
   for (int q = threadIdx.x; q < N; q += blockDim.x) {
@@ -119,13 +132,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
   int d_iin[CT], d_iout[CT], d_jout[CT];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
-    isval[t] = (t == 0 && lane == 0);
+    isval[t] = (wig == 0 && t == 0 && lane == 0);
     d_o[t] = 0.0; d_iin[t] = d_iout[t] = d_jout[t] = 0;
     if (R1) {
-      const R1Desc d = desc_dev[lane + 32 * t];
+      const R1Desc d = desc_dev[lane + 32 * (t + CT * wig)];
       d_o[t] = d.o; d_iin[t] = d.i_in; d_iout[t] = d.i_out; d_jout[t] = d.j_out;
     }
-    live[t] = (lane + 32 * t) < ncol && (sp.incl_sens || isval[t]);
+    live[t] = (lane + 32 * (t + CT * wig)) < ncol && (sp.incl_sens || isval[t]);
   }
   // lane i < NS keeps the per-row controller state (tolerances, |u| magnitudes)
   double my_at = 0.0, my_rt = 0.0;
@@ -134,9 +147,17 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
   constexpr int PH_F0 = 0, PH_F1 = 7, PH_SAVE = 8;  // phases 1..6 are the Tsit5 stages
 
   while (true) {
-    unsigned long long tq = 0;
-    if (lane == 0) tq = atomicAdd(queue, 1ull);
-    const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
+    long long traj;
+    if (WPT == 1) {
+      unsigned long long tq = 0;
+      if (lane == 0) tq = atomicAdd(queue, 1ull);
+      traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
+    } else {
+      if (isval[0]) { gb.trajslot = (long long)atomicAdd(queue, 1ull); gb.flag = 0; }
+      gsync();
+      traj = gb.trajslot;
+      gsync();
+    }
     if (traj >= ntraj) break;
 
     // U: state; Y: stage state (holds the proposed u_{n+1} from stage 6 through the save phase);
@@ -148,7 +169,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
     }
-    if (C::KIND == 1 && lane == 0) wb.x[NS] = xT;
+    if (C::KIND == 1 && isval[0]) gb.x[NS] = xT;
 #pragma unroll
     for (int t = 0; t < CT; ++t)
 #pragma unroll
@@ -203,39 +224,39 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         }
 
         // ---- KO = f(Y) on all columns: the single RHS instance (3 warp barriers) ----
-        if (lane == 0) {
+        if (isval[0]) {
 #pragma unroll
-          for (int i = 0; i < NS; ++i) wb.y[i] = Y[0][i];
+          for (int i = 0; i < NS; ++i) gb.y[i] = Y[0][i];
         }
-        __syncwarp();
-        if (lane < NS) {
-          const double yi = wb.y[lane];
+        gsync();
+        if (wig == 0 && lane < NS) {
+          const double yi = gb.y[lane];
           const double uc = clampd(yi, mp.lb, mp.ub);
           const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
-          wb.x[lane] = log(uc);
-          wb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
+          gb.x[lane] = log(uc);
+          gb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
-        __syncwarp();
-        if (lane < NR) {
+        gsync();
+        if (wig == 0 && lane < NR) {
           double z = mybT;
 #pragma unroll
-          for (int i = 0; i < NS; ++i) z = fma(sm.w_in[i + NIN * lane], wb.x[i], z);
-          wb.r[lane] = exp(z);
+          for (int i = 0; i < NS; ++i) z = fma(sm.w_in[i + NIN * lane], gb.x[i], z);
+          gb.r[lane] = exp(z);
         }
-        __syncwarp();
+        gsync();
         {
           double dx[NS], r[NR];
 #pragma unroll
-          for (int i = 0; i < NS; ++i) dx[i] = wb.dx[i];
+          for (int i = 0; i < NS; ++i) dx[i] = gb.dx[i];
 #pragma unroll
-          for (int j = 0; j < NR; ++j) r[j] = wb.r[j];
+          for (int j = 0; j < NR; ++j) r[j] = gb.r[j];
 #pragma unroll
           for (int tt = 0; tt < CT; ++tt) {
-            const int lc = lane + 32 * tt;
+            const int lc = lane + 32 * (tt + CT * wig);
             double sd[NS], q[NR];
 #pragma unroll
             for (int i = 0; i < NS; ++i) sd[i] = Y[tt][i] * dx[i];
-            const double xin = R1 ? wb.x[d_iin[tt]] : 0.0;
+            const double xin = R1 ? gb.x[d_iin[tt]] : 0.0;
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
               double zd = R1 ? fma(sm.seed[j][lc], xin, sm.seed[NR + j][lc]) : sm.seed[NIN * NR + j][lc];
@@ -243,13 +264,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               for (int i = 0; i < NS; ++i) zd = fma(mp.w_in[i + NIN * j], sd[i], zd);
               if (!R1) {
 #pragma unroll
-                for (int i = 0; i < NS; ++i) zd = fma(sm.seed[i + NIN * j][lc], wb.x[i], zd);
+                for (int i = 0; i < NS; ++i) zd = fma(sm.seed[i + NIN * j][lc], gb.x[i], zd);
                 if (C::KIND == 1) zd = fma(sm.seed[NS + NIN * j][lc], xT, zd);
               }
               if (isval[tt]) zd = 1.0;
               q[j] = r[j] * zd;
             }
-            const double ro = R1 ? d_o[tt] * wb.r[d_jout[tt]] : 0.0;
+            const double ro = R1 ? d_o[tt] * gb.r[d_jout[tt]] : 0.0;
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
               double s = 0.0;
@@ -311,7 +332,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           const int npass = (phase == 6) ? 2 : 1;
 #pragma unroll 1
           for (int pass = 0; pass < npass; ++pass) {
-            __syncwarp();
+            gsync();
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
               double sa = 0.0;
@@ -323,12 +344,21 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               wb.red[i][lane] = sa;
             }
             __syncwarp();
+            double tot = 0.0;
             if (lane < NS) {
-              double tot = 0.0;
 #pragma unroll 8
               for (int k = 0; k < 32; ++k) tot += wb.red[lane][(k + lane) & 31];  // skewed: conflict-free
-              if (pass == 0) rsum = tot; else bsum = tot;
+              if (WPT > 1) gb.part[wig][lane] = tot;
             }
+            if (WPT > 1) {  // combine the group's per-warp partial sums (same order in every warp)
+              gsync();
+              tot = 0.0;
+              if (lane < NS) {
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) tot += gb.part[w][lane];
+              }
+            }
+            if (lane < NS) { if (pass == 0) rsum = tot; else bsum = tot; }
           }
           // (b) per-row terms (lane i < NS), then their sums in every lane
           double term0 = 0.0, term1 = 0.0;
@@ -342,13 +372,12 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               term0 = rsum / (my_sk * my_sk);
               term1 = a * a;
             }
-            wb.term[0][lane] = term0;
-            wb.term[1][lane] = term1;
+            if (wig == 0) { gb.term[0][lane] = term0; gb.term[1][lane] = term1; }
           }
-          __syncwarp();
+          gsync();
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int i = 0; i < NS; ++i) { s0 += wb.term[0][i]; s1 += wb.term[1][i]; }
+          for (int i = 0; i < NS; ++i) { s0 += gb.term[0][i]; s1 += gb.term[1][i]; }
 
           if (phase == PH_F0) {
             // initial step size, part 1 (ode_determine_initdt)
@@ -408,18 +437,18 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               for (int i = 0; i < NS; ++i) KO[tt][i] = Y[tt][i];
           } else {
             const double th = (tsv - tprev) / dt;
-            __syncwarp();
-            if (lane < 7)
-              wb.b[lane] = th * (sm.dense_r[lane][0] + th * (sm.dense_r[lane][1] +
+            gsync();
+            if (wig == 0 && lane < 7)
+              gb.b[lane] = th * (sm.dense_r[lane][0] + th * (sm.dense_r[lane][1] +
                                  th * (sm.dense_r[lane][2] + th * sm.dense_r[lane][3])));
-            __syncwarp();
+            gsync();
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
               for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
 #pragma unroll 1
             for (int j = 0; j < 7; ++j) {
-              const double bj = wb.b[j];
+              const double bj = gb.b[j];
               const int slot = (j == 0) ? k1s : (j == 6 ? 6 - k1s : j);
 #pragma unroll
               for (int tt = 0; tt < CT; ++tt)
@@ -431,16 +460,16 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
 #pragma unroll
               for (int i = 0; i < NS; ++i) KO[tt][i] = fma(dt, KO[tt][i], U[tt][i]);
           }
-          if (lane == 0) {
+          if (isval[0]) {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) wb.y[i] = KO[0][i];
+            for (int i = 0; i < NS; ++i) gb.y[i] = KO[0][i];
           }
-          __syncwarp();
-          if (lane < N) {
+          gsync();
+          if (wig == 0 && lane < N) {
             const int q = sm.row2obs[lane];
             double g = 0.0;
             if (q >= 0) {
-              const double y = (lane < NS) ? wb.y[lane] : Tval;
+              const double y = (lane < NS) ? gb.y[lane] : Tval;
               const double yc = clampd(y, sp.pred_lo, sp.pred_hi);
               const bool inside = (y >= sp.pred_lo) && (y <= sp.pred_hi);
               const size_t off = pbase + q + (size_t)sp.n_obs * isave;
@@ -458,12 +487,12 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               loss_acc += fabs(diff);
               if (!inside) g = 0.0;
             }
-            wb.g[lane] = g;
+            gb.g[lane] = g;
           }
-          __syncwarp();
+          gsync();
 #pragma unroll
           for (int i = 0; i < NS; ++i) {
-            const double g = wb.g[i];
+            const double g = gb.g[i];
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt) G[tt] = fma(g, KO[tt][i], G[tt]);
           }
@@ -493,7 +522,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
           for (int i = 0; i < NS; ++i) bad |= (U[tt][i] != U[tt][i]);
-        if (__any_sync(0xffffffffu, bad)) { ret = CRNN_RET_UNSTABLE; break; }
+        bad = __any_sync(0xffffffffu, bad);
+        if (WPT > 1) {  // any warp of the group
+          if (bad && lane == 0) gb.flag = 1;
+          gsync();
+          bad = gb.flag != 0;
+        }
+        if (bad) { ret = CRNN_RET_UNSTABLE; break; }
       }
     }
     if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
@@ -501,7 +536,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // ---- per-trajectory outputs ----
     const double cnt = (double)sp.n_obs * (double)isave;
     const double ltot = warp_sum(loss_acc);
-    if (lane == 0) {
+    if (isval[0]) {
       loss[traj] = isave > 0 ? ltot / cnt : __longlong_as_double(0x7ff8000000000000LL);
       if (n_saved) n_saved[traj] = isave;
       if (retcode) retcode[traj] = ret;
@@ -514,13 +549,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     }
 #pragma unroll
     for (int tt = 0; tt < CT; ++tt) {
-      const int c = lane + 32 * tt;
+      const int c = lane + 32 * (tt + CT * wig);
       if (c >= 1 && c < ncol) grad_each[(size_t)traj * np + (c - 1)] = isave > 0 ? G[tt] / cnt : 0.0;
     }
-    if (pred && isave < sp.n_save) {
+    if (wig == 0 && pred && isave < sp.n_save) {
       for (int q = isave * sp.n_obs + lane; q < sp.n_save * sp.n_obs; q += 32) pred[pbase + q] = 0.0;
     }
-    __syncwarp();
+    gsync();
   }
 }
 

@@ -220,3 +220,63 @@ def test_full_size_properties_case2(engine, golden):
     ref = oracle.loss_grad_batch(model, opts, seed, u0[idx], data[idx], ys, n_threads=8)
     np.testing.assert_allclose(whole["loss"][idx], ref["loss"], rtol=RTOL_LOSS)
     assert np.array_equal(whole["stats"]["n_accept"][idx], ref["stats"]["n_accept"])
+
+
+# ---------------------------------------------------------------- wide gradients: several warps per trajectory
+def _grad_close(got, ref, rtol=RTOL_GRAD):
+    gmax = np.abs(ref["grad_sum"]).max()
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=rtol, atol=1e-9 * gmax)
+
+
+def test_case3_forward_sens_np153_five_warps_per_trajectory(engine, golden):
+    """case3/case3.jl:265-270: Zygote.forwarddiff over all 153 parameters, log-MAE loss (:183-190).
+    154 dual columns = 5 warps sharing one trajectory (named-barrier group)."""
+    pb = make_problem("case3", golden, 48)
+    # targets must be positive for the log loss; the script clamps them to [lb, ub] (case3.jl:185)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], np.abs(pb["data"]) + 1e-6, pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    _counts_equal(got, ref)
+    _states_close(got["pred"], ref["pred"], rtol=1e-5, scaled=1e-9)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-7)
+    _grad_close(got, ref, rtol=1e-5)       # rounding-amplifying random weights (see test_tsit5_value)
+
+
+def test_three_warps_per_trajectory_column_subset(engine, golden):
+    """80 of case3's seed columns (np = 80 -> 3 tiles): also how ForwardDiff-style chunking is expressed."""
+    pb = make_problem("case3", golden, 32)
+    seed = pb["seed"][:, :80]
+    args = (pb["model"], pb["opts"], seed, pb["u0"], np.abs(pb["data"]) + 1e-6, pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args)
+    ref = oracle.loss_grad_batch(*args, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-7)
+    _grad_close(got, ref, rtol=1e-5)
+
+
+def test_two_tiles_per_lane_np43(engine, golden):
+    """robertson's p2vec (np = 43 -> two column tiles per lane) integrated with Tsit5 on a short span."""
+    pb = make_problem("robertson", golden, 24)
+    c = pb["case"]
+    o = c.opts(alg=_abi.ALG_TSIT5, t1=2.0, saveat=np.linspace(0.1, 2.0, 12), abstol=1e-8, reltol=1e-4, maxiters=200000)
+    data = pb["data"][:, :12, :]
+    args = (pb["model"], o, pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args)
+    ref = oracle.loss_grad_batch(*args, n_threads=8)
+    _counts_equal(got, ref)
+    assert (got["retcode"] == 1).all()
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-8)
+    _grad_close(got, ref, rtol=1e-6)
+
+
+def test_dense_seed_fallback(engine, golden):
+    """A seed that is not 'one w_in row + one w_out entry per column' takes the dense layout."""
+    pb = make_problem("case2", golden, 64)
+    rng = np.random.default_rng(5)
+    seed = rng.standard_normal((pb["model"].n_w, 9)) * (rng.random((pb["model"].n_w, 9)) < 0.5)
+    args = (pb["model"], pb["opts"], seed, pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args)
+    ref = oracle.loss_grad_batch(*args, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
+    _grad_close(got, ref)
