@@ -18,6 +18,7 @@
 #include "kernel_tsit5_value.cuh"
 #include "kernel_tsit5_sens.cuh"
 #include "kernel_rosenbrock23.cuh"
+#include "kernel_rosenbrock23_sens.cuh"
 
 using namespace crnn;
 
@@ -243,6 +244,34 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
   return CRNN_OK;
 }
 
+// Rosenbrock23 + forward sensitivities (structured seeds, NS <= 6: per-lane register LU)
+template <class C, int CT>
+int launch_ros_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
+                    cudaStream_t st) {
+  if constexpr (C::NS > 6) {
+    return fail(h, CRNN_ERR_UNSUPPORTED, "Rosenbrock23 forward sensitivities need n_species <= 6");
+  } else {
+    if (b.n == 0) return CRNN_OK;
+    constexpr int WARPS = 4, MINB = 2;
+    auto kern = k_rosenbrock23_sens<C, CT, WARPS, MINB>;
+    const size_t smem = sizeof(SensSmem<C, CT, true>) + WARPS * sizeof(RosWarpBuf<C, CT>);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+    if (bps < 1) bps = 1;
+    long long want = (b.n + WARPS - 1) / WARPS;
+    unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
+    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+    ProfScope prof(h, st);
+    kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
+                                        b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue);
+    CK(cudaGetLastError());
+    h->launches++;
+    return CRNN_OK;
+  }
+}
+
 inline int launch_grad_reduce(crnn_handle* h, const double* grad_each, long long n, int np, double* grad_sum_dev,
                               cudaStream_t st) {
   const int nb = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (n + 63) / 64));
@@ -428,8 +457,9 @@ int solve_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
 template <class C>
 int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                    const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
-  if (o->alg != CRNN_ALG_TSIT5)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5 only (so far)");
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5 and Rosenbrock23");
+  const bool ros = (o->alg == CRNN_ALG_ROSENBROCK23);
   const int ncol = np + 1;
   const int ct = (ncol + 31) / 32;  // 32-lane tiles of dual columns
   if (ct > 8) return fail(h, CRNN_ERR_UNSUPPORTED, "forward mode supports np <= 255");
@@ -441,8 +471,9 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   if (rc) return rc;
   R1Plan pl = plan_r1<C>(m, dW_dp, np);
   const bool r1 = pl.ok;
-  if (!r1 && ct > 2)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "np > 63 needs a structured seed (one w_in row and one w_out entry per column)");
+  if (!r1 && (ct > 2 || ros))
+    return fail(h, CRNN_ERR_UNSUPPORTED, "np > 63 and Rosenbrock23 sensitivities need a structured seed (one w_in row and one w_out entry per column)");
+  if (ros && ct > 2) return fail(h, CRNN_ERR_UNSUPPORTED, "Rosenbrock23 forward sensitivities support np <= 63");
   if (r1) {
     CK(h->desc.reserve(pl.desc.size() * sizeof(R1Desc)));
     CK(cudaMemcpyAsync(h->desc.p, pl.desc.data(), pl.desc.size() * sizeof(R1Desc), cudaMemcpyHostToDevice, st));
@@ -454,6 +485,7 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
     CK(h->desc.reserve(sizeof(R1Desc)));
   }
   return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) {
+    if (ros) return ct == 1 ? launch_ros_sens<C, 1>(h, mp, sp, ncol, b, s) : launch_ros_sens<C, 2>(h, mp, sp, ncol, b, s);
     if (r1 && ct > 2) {  // several warps per trajectory
       if (ct <= 3) return launch_sens<C, 1, true, 3>(h, mp, sp, ncol, b, s);
       if (ct <= 5) return launch_sens<C, 1, true, 5>(h, mp, sp, ncol, b, s);

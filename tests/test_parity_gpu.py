@@ -280,3 +280,31 @@ def test_dense_seed_fallback(engine, golden):
     _counts_equal(got, ref)
     np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
     _grad_close(got, ref)
+
+
+def test_rosenbrock23_forward_sens_robertson(engine, golden):
+    """The reference's stiff training path: ForwardDiff.gradient through Rosenbrock23(autodiff=true)
+    (rober_crnn.jl:33,139-144,219), vector tolerances (:34-35), random time truncation (:218)."""
+    pb = make_problem("robertson", golden, 96)
+    nsu = np.random.default_rng(7).integers(32, 41, size=96).astype(np.int32)   # sample = rand(batchsize:datasize)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, n_save_used=nsu, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, n_save_used=nsu, want_pred=True, n_threads=8)
+    _counts_equal(got, ref)
+    assert (got["retcode"] == 1).all() and np.array_equal(got["n_saved"], nsu)
+    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    assert (np.abs(got["pred"] - ref["pred"]) / scale).max() < 1e-7
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-6)
+    _grad_close(got, ref, rtol=1e-5)
+
+
+def test_rosenbrock23_forward_sens_case2(engine, golden):
+    """stiff half of AutoTsit5(Rosenbrock23) on the case2 model (F1: Arrhenius row, T as state)."""
+    pb = make_problem("case2", golden, 64)
+    o = pb["case"].opts(obs_idx=np.arange(6), alg=_abi.ALG_ROSENBROCK23)
+    args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args)
+    ref = oracle.loss_grad_batch(*args, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-8)
+    _grad_close(got, ref, rtol=1e-6)
