@@ -232,3 +232,40 @@ def true_model_case3(lb=1e-30) -> CRNNModel:
         w_in[a, 4 + j] = 1
         w_out[a, 4 + j] = -1; w_out[a - 1, 4 + j] = 1
     return CRNNModel(w_in=w_in, w_b=np.zeros(nr), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)
+
+
+def synthetic_stiff_model(ns=29, nr=30, seed=0, lb=1e-12) -> CRNNModel:
+    """HyChem-sized synthetic CRNN (BASELINE config 5; the reference's HyChem data file is not in its
+    repository, HyChem/crnn_pyrolysis_mass.jl:32): `ns` species + temperature as the last state (F1),
+    `nr` mass-action reactions (1 or 2 reactants -> as many products, so sum(u) is conserved and the
+    state stays bounded), pre-exponentials spread over 9 decades and Arrhenius rows of 0-12 kcal/mol:
+    a stiff system."""
+    g = np.random.default_rng(seed)
+    w_in = np.zeros((ns + 1, nr)); w_out = np.zeros((ns, nr))
+    for j in range(nr):
+        k = 1 if g.random() < 0.4 else 2
+        reac = g.choice(ns, size=k, replace=False)
+        prod = g.choice(np.setdiff1d(np.arange(ns), reac), size=k, replace=False)
+        for a in reac:
+            w_in[a, j] += 1.0; w_out[a, j] -= 1.0
+        for c in prod:
+            w_out[c, j] += 1.0
+    w_in[ns, :] = g.uniform(0.0, 12.0, nr)           # Ea [kcal/mol]
+    w_b = g.uniform(-2.0, 19.0, nr)                  # ln A
+    return CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F1, lb=lb, ub=INF)
+
+
+def synthetic_stiff_u0(N, ns=29, seed=1234, start=0) -> np.ndarray:
+    """ICs for synthetic_stiff_model: six species at U(0.05,1), the rest at 1e-8, T ~ U(1000,1400) K."""
+    from . import synth
+    r = synth._blocked(seed, 7, start, N, (7,), lambda g, shp: g.random(shp))
+    u0 = np.full((N, ns + 1), 1e-8)
+    u0[:, :6] = 0.05 + 0.95 * r[:, :6]
+    u0[:, ns] = 1000.0 + 400.0 * r[:, 6]
+    return u0
+
+
+def synthetic_stiff_opts(alg=_abi.ALG_KENCARP4, ns=29, n_save=40, t1=1.0) -> SolveOpts:
+    """HyChem-like settings: abstol 1e-8 / reltol 1e-3 (crnn_pyrolysis_mass.jl:26-27), 40 log-spaced saves."""
+    return SolveOpts(saveat=t1 * 10.0 ** np.linspace(-6.0, 0.0, n_save), t0=0.0, t1=t1, alg=alg, abstol=1e-8,
+                     reltol=1e-3, maxiters=100000, obs_idx=np.arange(ns))

@@ -4,6 +4,7 @@
 // dimension-specialised engines, which are compiled one translation unit per configuration
 // (inst.cu with -DCRNN_NS/-DCRNN_NR/-DCRNN_KIND) so the build parallelises.
 #include "crnn_host.cuh"
+#include "kernel_kencarp4_wide.cuh"
 
 namespace crnn_host {
 #define X(NS_, NR_, K_)                                                                                     \
@@ -16,6 +17,81 @@ CRNN_FOR_EACH_CFG(X)
 #undef X
 }  // namespace crnn_host
 using namespace crnn_host;
+
+namespace {
+
+// KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
+int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 kernel supports n_state <= 32 and n_reac <= 32");
+  const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
+  WideP P{};
+  std::vector<int> row2obs(n, -1);
+  for (int q = 0; q < o->n_obs; ++q) {
+    const int r = o->obs_idx[q];
+    if (r < 0 || r >= n) return fail(h, CRNN_ERR_BAD_ARG, "obs_idx out of range");
+    if (row2obs[r] >= 0) return fail(h, CRNN_ERR_BAD_ARG, "obs_idx has duplicates");
+    row2obs[r] = q;
+  }
+  for (int i = 0; i < KW_MAXN; ++i) {
+    P.abstol[i] = i < n ? o->abstol[o->n_abstol > 1 ? i : 0] : 1.0;
+    P.reltol[i] = i < n ? o->reltol[o->n_reltol > 1 ? i : 0] : 0.0;
+  }
+  P.lb = m->lb; P.ub = m->ub; P.gas_R = m->gas_R;
+  P.t0 = o->t0; P.t1 = o->t1; P.pred_lo = o->pred_clamp_lo; P.pred_hi = o->pred_clamp_hi;
+  const int order = 4;
+  const double qmin = o->qmin > 0 ? o->qmin : 0.2, qmax = o->qmax > 0 ? o->qmax : 10.0;
+  P.inv_qmin = 1.0 / qmin; P.inv_qmax = 1.0 / qmax;
+  P.gamma = o->gamma > 0 ? o->gamma : 0.9;
+  P.beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * order);
+  P.beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * order);
+  P.inv_order = 1.0 / order;
+  P.maxiters = o->maxiters;
+  P.n = n; P.ns = ns; P.nin = nin; P.nr = nr; P.kind = m->rhs_kind;
+  P.n_save = o->n_save; P.n_obs = o->n_obs;
+  // device blob: w_inT [nin][32] | w_b [nr] | w_out [ns*nr] | saveat [n_save] | row2obs [n]
+  std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + (n + 1) / 2 + 2, 0.0);
+  double* p_winT = blob.data();
+  double* p_wb = p_winT + (size_t)nin * KW_MAXN;
+  double* p_wout = p_wb + nr;
+  double* p_save = p_wout + (size_t)ns * nr;
+  int* p_r2o = reinterpret_cast<int*>(p_save + o->n_save);
+  for (int j = 0; j < nr; ++j) {
+    for (int i = 0; i < nin; ++i) p_winT[(size_t)i * KW_MAXN + j] = m->w_in[i + nin * j];
+    p_wb[j] = m->w_b[j];
+    for (int i = 0; i < ns; ++i) p_wout[i + ns * j] = m->w_out[i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0);
+  }
+  for (int k = 0; k < o->n_save; ++k) p_save[k] = o->saveat[k];
+  for (int i = 0; i < n; ++i) p_r2o[i] = row2obs[i];
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  CK(h->cfg.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
+  CK(cudaMemcpyAsync(h->cfg.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  double* d = h->cfg.as<double>();
+  P.w_inT = d; P.w_b = d + (p_wb - blob.data()); P.w_out = d + (p_wout - blob.data());
+  P.saveat = d + (p_save - blob.data());
+  P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
+  constexpr int WARPS = 4;
+  auto kern = k_kencarp4_wide<WARPS>;
+  const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+  if (bps < 1) bps = 1;
+  return run_batch(h, m, o, io, N, false, 0, nullptr, [&](const BatchPtrs& b, cudaStream_t s) -> int {
+    if (b.n == 0) return (int)CRNN_OK;
+    const long long want = (b.n + WARPS - 1) / WARPS;
+    const unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
+    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    ProfScope prof(h, s);
+    kern<<<blocks, WARPS * 32, smem, s>>>(P, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode, b.stats, queue);
+    CK(cudaGetLastError());
+    h->launches++;
+    return (int)CRNN_OK;
+  });
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -107,10 +183,11 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
   int rc = validate(h, m, o, N);
   if (rc) return rc;
   if (N > 0 && !u0) return fail(h, CRNN_ERR_BAD_ARG, "null u0");
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23)
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4)
     return fail(h, CRNN_ERR_UNSUPPORTED, "alg not supported by solve_batch");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, nullptr, pred, nullptr, n_saved, retcode, stats};
+  if (o->alg == CRNN_ALG_KENCARP4) return solve_kencarp4(h, m, o, io, N);
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return solve_impl<Cfg<NS_, NR_, K_>>(h, m, o, io, N);

@@ -1,0 +1,336 @@
+// kernel_kencarp4_wide.cuh — stiff predict path for LARGE states (BASELINE config 5, "HyChem-sized"):
+// one WARP owns one trajectory and lane i owns state component i (n_state <= 32, n_reac <= 32,
+// dimensions are RUNTIME values, no template instantiation per model).
+//
+// KenCarp4 (ESDIRK4(3)6L[2]SA, Kennedy & Carpenter 2003) is not used anywhere in the
+// reference — BASELINE asks for it — so its policies are ours and documented in oracle/crnn_oracle.c
+// (solve_one_kencarp4), which this kernel mirrors operation by operation:
+//   * W = I - gamma*dt*J(u_n) with the ANALYTIC CRNN Jacobian, one LU per step attempt, factored
+//     cooperatively in shared memory (lane = row, partial pivoting by a warp arg-max, first strict maximum);
+//   * simplified Newton per implicit stage (predictor z_i = z_{i-1}, eta*|dz| < 1/100, <= 10 iterations,
+//     divergence => reject and halve dt), triangular solves with one shuffle broadcast per pivot;
+//   * smoothed embedded error estimate, PI controller (order 4), Hermite dense output at the save points.
+// The RHS is naturally lane-parallel here: lane i takes log(u_i), lane j takes exp(z_j) — one log and
+// one exp issued per evaluation for the whole state.
+#pragma once
+#include "crnn_dev.cuh"
+
+namespace crnn {
+
+constexpr int KW_MAXN = 32;
+
+struct WideP {
+  double abstol[KW_MAXN], reltol[KW_MAXN];
+  double lb, ub, gas_R;
+  double t0, t1, pred_lo, pred_hi;
+  double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
+  long long maxiters;
+  const double* w_inT;   // device [n_in][nrp]: w_in transposed (reaction fastest), nrp = 32
+  const double* w_b;     // device [n_reac]
+  const double* w_out;   // device [n_species x n_reac] col-major, out_scale folded in
+  const double* saveat;  // device [n_save]
+  const int* row2obs;    // device [n_state]
+  int n, ns, nin, nr, kind;
+  int n_save, n_obs;
+};
+
+namespace kc {
+constexpr double g = 0.25;
+__constant__ double A[6][5] = {
+    {0, 0, 0, 0, 0},
+    {0.25, 0, 0, 0, 0},
+    {8611.0 / 62500.0, -1743.0 / 31250.0, 0, 0, 0},
+    {5012029.0 / 34652500.0, -654441.0 / 2922500.0, 174375.0 / 388108.0, 0, 0},
+    {15267082809.0 / 155376265600.0, -71443401.0 / 120774400.0, 730878875.0 / 902184768.0, 2285395.0 / 8070912.0, 0},
+    {82889.0 / 524892.0, 0.0, 15625.0 / 83664.0, 69875.0 / 102672.0, -2260.0 / 8211.0}};
+__constant__ double BHAT[6] = {4586570599.0 / 29645900160.0, 0.0, 178811875.0 / 945068544.0,
+                               814220225.0 / 1159782912.0, -3700637.0 / 11593932.0, 61727.0 / 225920.0};
+}  // namespace kc
+
+struct alignas(16) WideWarp {
+  double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
+  double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
+  int perm[KW_MAXN];
+};
+
+struct alignas(16) WideBlock {
+  double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
+  double w_out[KW_MAXN][KW_MAXN];  // [j][i]: lane i reads consecutive addresses for fixed j
+  double w_b[KW_MAXN];
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 3)
+k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
+                const int* __restrict__ n_save_used, long long ntraj, double* __restrict__ pred,
+                int* __restrict__ n_saved, int* __restrict__ retcode, crnn_stats* __restrict__ stats,
+                unsigned long long* __restrict__ queue) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WideBlock& sb = *reinterpret_cast<WideBlock*>(smem_raw);
+  WideWarp* wws = reinterpret_cast<WideWarp*>(smem_raw + sizeof(WideBlock));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WideWarp& ww = wws[warp];
+  const int n = P.n, ns = P.ns, nin = P.nin, nr = P.nr;
+
+  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
+    const int i = q / KW_MAXN, j = q % KW_MAXN;
+    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
+    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
+  }
+  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
+  __syncthreads();
+
+  const bool isp = lane < ns;                      // lane owns a species
+  const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
+  const int my_obs = lane < n ? P.row2obs[lane] : -1;
+
+  // f(y): lane i holds y_i in, f_i out; leaves x in ww.x, r in ww.r; returns dx_i = d log(clamp y_i)/dy_i
+  auto rhs = [&](double y, double& dxi) -> double {
+    __syncwarp();
+    double xi = 0.0;
+    dxi = 0.0;
+    if (isp) {
+      const double uc = clampd(y, P.lb, P.ub);
+      xi = log(uc);
+      dxi = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
+    } else if (P.kind == 1 && lane == ns) {
+      xi = -1.0 / (P.gas_R * y);
+    }
+    ww.x[lane] = xi;
+    __syncwarp();
+    if (lane < nr) {
+      double z = sb.w_b[lane];
+      for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
+      ww.r[lane] = exp(z);
+    }
+    __syncwarp();
+    double f = 0.0;
+    if (isp)
+      for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+    return f;
+  };
+  // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)
+  auto wrms = [&](double v, double a, double b) -> double {
+    double q = 0.0;
+    if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
+    return sqrt(warp_sum(q) / n);
+  };
+  // b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
+  auto lusolve = [&](double b) -> double {
+    b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
+    for (int k = 0; k + 1 < ns; ++k) {
+      const double bk = __shfl_sync(0xffffffffu, b, k);
+      if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
+    }
+    for (int k = ns - 1; k >= 0; --k) {
+      if (lane == k) b = b / ww.A[k][k];
+      const double bk = __shfl_sync(0xffffffffu, b, k);
+      if (lane < k) b = fma(-ww.A[lane][k], bk, b);
+    }
+    return isp ? b : 0.0;
+  };
+
+  // W = I - gdt*J from the RHS intermediates (r in rsrc, this lane's dx), then the cooperative LU
+  auto build_lu = [&](const double* rsrc, double dxl, double gdt) {
+    __syncwarp();
+    ww.x[lane] = dxl;  // broadcast dx_l
+    __syncwarp();
+    if (isp) {
+      for (int l = 0; l < ns; ++l) {
+        double s = 0.0;
+        for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
+        ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * (s * ww.x[l]);
+      }
+    }
+    ww.perm[lane] = lane;
+    __syncwarp();
+    for (int k = 0; k < ns; ++k) {
+      // pivot: first strict maximum of |A[i][k]|, i >= k
+      double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
+      int bi = lane;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (bi != k) {
+        if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
+        if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
+      }
+      __syncwarp();
+      if (lane > k && isp) {
+        const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
+        ww.A[lane][k] = l;
+        for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
+      }
+      __syncwarp();
+    }
+  };
+
+  while (true) {
+    unsigned long long tq = 0;
+    if (lane == 0) tq = atomicAdd(queue, 1ull);
+    const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
+    if (traj >= ntraj) break;
+
+    double u = lane < n ? __ldg(u0 + traj * n + lane) : 0.0;
+    int nsave = P.n_save;
+    double tend = P.t1;
+    if (n_save_used) {
+      int q = __ldg(n_save_used + traj);
+      if (q > 0 && q <= P.n_save) { nsave = q; tend = __ldg(P.saveat + q - 1); }
+    }
+    const double t0 = P.t0, dtmax = tend - t0;
+    const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
+    double* mypred = pred ? pred + (size_t)traj * P.n_obs * P.n_save : nullptr;
+    auto save = [&](int ks, double y) {
+      if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
+    };
+
+    int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
+    double dx0, dxs;
+    double f0 = rhs(u, dx0); ++n_rhs;
+    ww.r0[lane] = ww.r[lane];
+    // ---- initial step (Hairer-Wanner, order 4) ----
+    double dt;
+    {
+      const double sk = my_at + fabs(u) * my_rt;
+      double a = 0.0, b = 0.0;
+      if (lane < n) { a = u / sk; a *= a; b = f0 / sk; b *= b; }
+      const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+      double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+      dt0 = jmin(dt0, dtmax);
+      const double f1p = rhs(fma(dt0, f0, u), dxs); ++n_rhs;
+      double c = 0.0;
+      if (lane < n) { c = (f1p - f0) / sk; c *= c; }
+      const double d2 = sqrt(warp_sum(c) / n) / dt0;
+      const double dm = jmax(d1, d2);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * P.inv_order);
+      dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
+    }
+    double t = t0, qold = 1e-4, eta_old = 1.0, dt_last = 0.0;
+    int isave = 0, ret = CRNN_RET_DEFAULT;
+    long long iter = 0;
+    while (isave < nsave && __ldg(P.saveat + isave) <= t0) { save(isave, u); ++isave; }
+
+    while (t < tend) {
+      ++iter;
+      if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
+      if (iter > P.maxiters) { ret = CRNN_RET_MAXITERS; break; }
+      dt = jmin(dt, dtmax);
+      dt = jmin(dt, tend - t);
+      if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+      if (__any_sync(0xffffffffu, lane < n && u != u)) { ret = CRNN_RET_UNSTABLE; break; }
+
+      // ---- W = I - g dt J(u_n), J[i][l] = sum_j w_out[i,j] r0_j w_in[l,j] dx0_l ; LU ----
+      const double gdt = kc::g * dt;
+      build_lu(ww.r0, dx0, gdt);
+      ++n_jac;
+
+      // ---- stages ----
+      double z[6], tmp = u, yk = u;
+      z[0] = dt * f0;
+      bool ok = true, refreshed = false;
+#pragma unroll 1
+      for (int s = 1; s < 6 && ok; ++s) {
+        tmp = u;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j < s) tmp = fma(kc::A[s][j], z[j], tmp);
+        double zs = z[s - 1];
+        bool conv = false;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
+          double ndz_prev = 0.0, eta = pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+#pragma unroll 1
+          for (int it = 1; it <= 10; ++it) {
+            yk = fma(kc::g, zs, tmp);
+            double dz = fma(dt, rhs(yk, dxs), -zs); ++n_rhs;
+            dz = lusolve(dz);
+            const double ndz = wrms(dz, u, yk);
+            zs += dz;
+            if (it > 1) {
+              const double theta = ndz / ndz_prev;
+              if (!(theta <= 2.0)) break;
+              eta = theta / (1.0 - theta);
+            }
+            if ((eta >= 0.0 && eta * ndz < 0.01) || ndz == 0.0) { conv = true; eta_old = eta; break; }
+            ndz_prev = ndz;
+          }
+          if (!conv) {
+            // a stage value that crossed the clamp sees a very different Jacobian: once per step
+            // attempt rebuild W at the last iterate and redo this stage (oracle: solve_one_kencarp4)
+            if (refreshed || __any_sync(0xffffffffu, lane < n && zs != zs)) break;
+            refreshed = true;
+            yk = fma(kc::g, zs, tmp);
+            (void)rhs(yk, dxs); ++n_rhs;
+            build_lu(ww.r, dxs, gdt);
+            ++n_jac;
+          }
+        }
+        // z[s] = zs with a compile-time index
+#pragma unroll
+        for (int j = 1; j < 6; ++j)
+          if (j == s) z[j] = zs;
+        if (!conv) ok = false;
+      }
+      dt_last = dt;
+      if (!ok) { ++n_rej; dt = dt / 2.0; continue; }
+      const double un = fma(kc::g, z[5], tmp);
+      double e = (kc::g - kc::BHAT[5]) * z[5];
+#pragma unroll
+      for (int j = 4; j >= 0; --j) e = fma(kc::A[5][j] - kc::BHAT[j], z[j], e);
+      e = lusolve(isp ? e : 0.0);
+      const double EEst = wrms(e, u, un);
+      double q11, q;
+      if (EEst == 0.0) { q11 = 0.0; q = P.inv_qmax; }
+      else {
+        q11 = pow(EEst, P.beta1);
+        q = jmax(P.inv_qmax, jmin(P.inv_qmin, q11 / pow(qold, P.beta2) / P.gamma));
+      }
+      if (EEst <= 1.0) {
+        ++n_acc;
+        qold = jmax(EEst, 1e-4);
+        const double dtnew = dt / q, tprev = t;
+        t = snap_t(t + dt, tend);
+        double dx1;
+        const double f1 = rhs(un, dx1); ++n_rhs;
+        while (isave < nsave) {
+          const double tsv = __ldg(P.saveat + isave);
+          if (!(tsv <= t)) break;
+          if (tsv == t) save(isave, un);
+          else {
+            const double th = (tsv - tprev) / dt;
+            save(isave, (1.0 - th) * u + th * un +
+                            th * (th - 1.0) * ((1.0 - 2.0 * th) * (un - u) + (th - 1.0) * dt * f0 + th * dt * f1));
+          }
+          ++isave;
+        }
+        u = un; f0 = f1; dx0 = dx1;
+        __syncwarp();
+        ww.r0[lane] = ww.r[lane];
+        dt = jmin(dtnew, dtmax);
+      } else {
+        ++n_rej;
+        dt = dt / jmin(P.inv_qmin, q11 / P.gamma);
+      }
+    }
+    if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+    if (mypred && my_obs >= 0)
+      for (int ks = isave; ks < P.n_save; ++ks) mypred[my_obs + P.n_obs * ks] = 0.0;
+    if (lane == 0) {
+      if (n_saved) n_saved[traj] = isave;
+      if (retcode) retcode[traj] = ret;
+      if (stats) {
+        crnn_stats s;
+        s.n_accept = n_acc; s.n_reject = n_rej; s.n_rhs = n_rhs; s.n_jac = n_jac;
+        s.t_reached = t; s.dt_last = dt_last;
+        stats[traj] = s;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace crnn

@@ -335,7 +335,8 @@ static void lu_factor(double* A, int* piv, int n) {
 static void lu_solve(const double* A, const int* piv, int n, double* b) {
   for (int k = 0; k < n; ++k) { int p = piv[k]; if (p != k) { double t = b[k]; b[k] = b[p]; b[p] = t; } }
   for (int i = 1; i < n; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= A[i * n + j] * b[j]; b[i] = s; }
-  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * b[j]; b[i] = s / A[i * n + i]; }
+  /* column-oriented order (j descending), the order a lane-per-row GPU solve produces */
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = n - 1; j > i; --j) s -= A[i * n + j] * b[j]; b[i] = s / A[i * n + i]; }
 }
 
 typedef struct {
@@ -512,6 +513,164 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
   free(buf);
 }
 
+/* ---- KenCarp4 = ESDIRK4(3)6L[2]SA (Kennedy & Carpenter 2003), implicit tableau.
+ * NOT in the reference (BASELINE config 5 asks for it): every policy below is OUR documented choice —
+ * parity unpinned.  Stage values z_i = dt f(Y_i), Y_i = u_n + sum_{j<i} a_ij z_j + gamma z_i, simplified
+ * Newton on W = I - gamma dt J(u_n) (one LU per step attempt, J analytic), predictor z_i^0 = z_{i-1},
+ * convergence test eta*|dz| < kappa = 1/100 with eta = theta/(1-theta) (first iteration: eta_old^0.8),
+ * at most 10 iterations, theta > 2 or exhaustion => reject and halve dt; error estimate
+ * W^{-1} sum (b_i - bhat_i) z_i (smoothed), PI controller of order 4, Hermite dense output. */
+static long long g_dbg_newton_fail = 0, g_dbg_err_rej = 0;
+void crnn_oracle_debug_counts(long long* out) { out[0] = g_dbg_newton_fail; out[1] = g_dbg_err_rej; g_dbg_newton_fail = g_dbg_err_rej = 0; }
+static const double KC_G = 0.25;
+static const double KC_A[6][5] = {
+  {0},
+  {0.25},
+  {8611.0 / 62500.0, -1743.0 / 31250.0},
+  {5012029.0 / 34652500.0, -654441.0 / 2922500.0, 174375.0 / 388108.0},
+  {15267082809.0 / 155376265600.0, -71443401.0 / 120774400.0, 730878875.0 / 902184768.0, 2285395.0 / 8070912.0},
+  {82889.0 / 524892.0, 0.0, 15625.0 / 83664.0, 69875.0 / 102672.0, -2260.0 / 8211.0}};
+static const double KC_BHAT[6] = {4586570599.0 / 29645900160.0, 0.0, 178811875.0 / 945068544.0,
+                                  814220225.0 / 1159782912.0, -3700637.0 / 11593932.0, 61727.0 / 225920.0};
+
+void crnn_oracle_kencarp4_tableau(double* a /*6x6 incl. diagonal*/, double* bhat /*6*/) {
+  memset(a, 0, sizeof(double) * 36);
+  for (int i = 1; i < 6; ++i) { for (int j = 0; j < i; ++j) a[i * 6 + j] = KC_A[i][j]; a[i * 6 + i] = KC_G; }
+  memcpy(bhat, KC_BHAT, sizeof(KC_BHAT));
+}
+
+static double wrms(const ctx_t* c, const double* v, const double* a, const double* b) {
+  double acc = 0.0;
+  for (int i = 0; i < c->n; ++i) {
+    double at = c->o->abstol[c->o->n_abstol > 1 ? i : 0], rt = c->o->reltol[c->o->n_reltol > 1 ? i : 0];
+    double sc = at + fmax(fabs(a[i]), fabs(b[i])) * rt;
+    acc += (v[i] / sc) * (v[i] / sc);
+  }
+  return sqrt(acc / c->n);
+}
+
+static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use, save_sink* sk, traj_result* res) {
+  const crnn_opts* o = c->o;
+  const int n = c->n;
+  double* buf = (double*)calloc((size_t)n * 16 + (size_t)n * n * 2, sizeof(double));
+  double* U = buf; double* Un = U + n; double* F0 = Un + n; double* F1 = F0 + n;
+  double* Z[6]; for (int s = 0; s < 6; ++s) Z[s] = F1 + n * (s + 1);
+  double* TMP = Z[5] + n; double* Yk = TMP + n; double* DZ = Yk + n; double* W2 = DZ + n; /* 2n */
+  double* Jm = W2 + 2 * n; double* LU = Jm + n * n;
+  int piv[MAXN];
+  rhs_cache kc, kc0;
+  memcpy(U, u0, sizeof(double) * n);
+  const double t0 = o->t0;
+  const double tend = (n_save_use > 0 && n_save_use <= o->n_save) ? o->saveat[n_save_use - 1] : o->t1;
+  const int nsave = (n_save_use > 0 && n_save_use <= o->n_save) ? n_save_use : o->n_save;
+  const double dtmax = tend - t0;
+  const double dtmin = fmax(nextafter(fabs(t0), INFINITY) - fabs(t0), nextafter(fabs(tend), INFINITY) - fabs(tend));
+  double t = t0, dt, qold = 1e-4, eta_old = 1.0;
+  int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
+  memset(&res->st, 0, sizeof(res->st));
+  rhs_value(c, U, F0, &kc); res->st.n_rhs++;
+  kc0 = kc;
+  dt = initial_dt(c, U, F0, dtmax, W2, &kc); res->st.n_rhs++;
+  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
+
+  while (t < tend) {
+    ++iter;
+    if (isnan(dt)) { ret = CRNN_RET_DTNAN; break; }
+    if (iter > o->maxiters) { ret = CRNN_RET_MAXITERS; break; }
+    dt = jmin(dt, dtmax);
+    dt = jmin(dt, tend - t);
+    if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+    if (has_nan(U, n)) { ret = CRNN_RET_UNSTABLE; break; }
+
+    jac_value(c, &kc0, Jm); res->st.n_jac++;
+    for (int i = 0; i < n; ++i)
+      for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - KC_G * dt * Jm[i * n + l];
+    lu_factor(LU, piv, n);
+    for (int i = 0; i < n; ++i) Z[0][i] = dt * F0[i];
+    int newton_ok = 1, refreshed = 0;
+    for (int s = 1; s < 6 && newton_ok; ++s) {
+      for (int i = 0; i < n; ++i) {
+        double acc = U[i];
+        for (int j = 0; j < s; ++j) acc += KC_A[s][j] * Z[j][i];
+        TMP[i] = acc;
+        Z[s][i] = Z[s - 1][i]; /* predictor */
+      }
+      int conv = 0;
+      for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
+        double ndz_prev = 0.0, eta = pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+        for (int it = 1; it <= 10; ++it) {
+          for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
+          rhs_value(c, Yk, DZ, &kc); res->st.n_rhs++;
+          for (int i = 0; i < n; ++i) DZ[i] = dt * DZ[i] - Z[s][i];
+          lu_solve(LU, piv, n, DZ);
+          double ndz = wrms(c, DZ, U, Yk);
+          for (int i = 0; i < n; ++i) Z[s][i] += DZ[i];
+          if (it > 1) {
+            double theta = ndz / ndz_prev;
+            if (!(theta <= 2.0)) break; /* diverging (also catches NaN): OrdinaryDiffEq's NLNewton threshold */
+            eta = theta / (1.0 - theta);
+          }
+          if ((eta >= 0.0 && eta * ndz < 0.01) || ndz == 0.0) { conv = 1; eta_old = eta; break; }
+          ndz_prev = ndz;
+        }
+        if (!conv) {
+          /* The clamp in log(clamp(u)) kinks f: a stage value that crossed lb sees a Jacobian very
+           * different from J(u_n) and the simplified Newton crawls.  Once per step attempt, rebuild
+           * W from the Jacobian at the last iterate and redo this stage. */
+          if (refreshed || has_nan(Z[s], n)) break;
+          refreshed = 1;
+          for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
+          rhs_value(c, Yk, DZ, &kc); res->st.n_rhs++;
+          jac_value(c, &kc, Jm); res->st.n_jac++;
+          for (int i = 0; i < n; ++i)
+            for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - KC_G * dt * Jm[i * n + l];
+          lu_factor(LU, piv, n);
+        }
+      }
+      if (!conv) newton_ok = 0;
+    }
+    res->st.dt_last = dt;
+    if (!newton_ok) { res->st.n_reject++; g_dbg_newton_fail++; dt = dt / 2.0; continue; }
+    for (int i = 0; i < n; ++i) {
+      Un[i] = TMP[i] + KC_G * Z[5][i]; /* stiffly accurate: b = a_6. */
+      double e = 0.0;
+      for (int j = 0; j < 5; ++j) e += (KC_A[5][j] - KC_BHAT[j]) * Z[j][i];
+      e += (KC_G - KC_BHAT[5]) * Z[5][i];
+      DZ[i] = e;
+    }
+    lu_solve(LU, piv, n, DZ); /* smoothed estimate */
+    double EEst = wrms(c, DZ, U, Un);
+    double q11, q = pi_q(c, EEst, qold, &q11);
+    if (EEst <= 1.0) {
+      res->st.n_accept++;
+      qold = jmax(EEst, 1e-4);
+      double dtnew = dt / q, tprev = t;
+      t = snap_t(t + dt, tend);
+      rhs_value(c, Un, F1, &kc); res->st.n_rhs++;
+      while (isave < nsave && o->saveat[isave] <= t) {
+        double ts = o->saveat[isave];
+        if (ts == t) emit_save(c, sk, isave, Un);
+        else {
+          double th = (ts - tprev) / dt;
+          for (int i = 0; i < n; ++i)
+            TMP[i] = (1.0 - th) * U[i] + th * Un[i] +
+                     th * (th - 1.0) * ((1.0 - 2.0 * th) * (Un[i] - U[i]) + (th - 1.0) * dt * F0[i] + th * dt * F1[i]);
+          emit_save(c, sk, isave, TMP);
+        }
+        ++isave;
+      }
+      memcpy(U, Un, sizeof(double) * n); memcpy(F0, F1, sizeof(double) * n); kc0 = kc;
+      dt = jmin(dtnew, dtmax);
+    } else {
+      res->st.n_reject++; g_dbg_err_rej++;
+      dt = dt / jmin(1.0 / c->qmin, q11 / c->gamma);
+    }
+  }
+  if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+  res->retcode = ret; res->n_saved = isave; res->st.t_reached = t;
+  free(buf);
+}
+
 static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const double* seed, int np) {
   c->m = m; c->o = o;
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
@@ -529,7 +688,7 @@ static int check_dims(const crnn_model* m, const crnn_opts* o) {
   if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F0 && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE && m->n_species + 1 != m->n_state) return CRNN_ERR_BAD_ARG;
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23) return CRNN_ERR_UNSUPPORTED;
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED;
   return CRNN_OK;
 }
 
@@ -548,7 +707,8 @@ int crnn_oracle_solve_batch(const crnn_model* m, const crnn_opts* o, const doubl
     sk.pred = pred ? pred + pstride * i : NULL;
     if (sk.pred) memset(sk.pred, 0, sizeof(double) * pstride);
     traj_result r;
-    solve_one(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
+    if (o->alg == CRNN_ALG_KENCARP4) solve_one_kencarp4(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
+    else solve_one(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
     if (n_saved) n_saved[i] = r.n_saved;
     if (retcode) retcode[i] = r.retcode;
     if (stats) stats[i] = r.st;
@@ -566,6 +726,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
                                 int n_threads) {
   int rc = check_dims(m, o);
   if (rc) return rc;
+  if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));

@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         _lib.crnn_oracle_rhs_sens.argtypes = [C.POINTER(CModel)] + [C.c_void_p] * 6
         _lib.crnn_oracle_tsit5_tableau.restype = None
         _lib.crnn_oracle_tsit5_tableau.argtypes = [C.c_void_p] * 3
+        _lib.crnn_oracle_kencarp4_tableau.restype = None
+        _lib.crnn_oracle_kencarp4_tableau.argtypes = [C.c_void_p] * 2
     return _lib
 
 
@@ -132,3 +134,9 @@ def tsit5_tableau():
     a = np.zeros((7, 6)); bt = np.zeros(7); r = np.zeros((7, 4))
     lib().crnn_oracle_tsit5_tableau(_p(a), _p(bt), _p(r))
     return a, bt, r
+
+
+def kencarp4_tableau():
+    a = np.zeros((6, 6)); bhat = np.zeros(6)
+    lib().crnn_oracle_kencarp4_tableau(_p(a), _p(bhat))
+    return a, bhat

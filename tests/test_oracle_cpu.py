@@ -320,3 +320,41 @@ def test_golden_oracle_vectors():
             r = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"])
         assert r["stats"]["n_accept"].tolist() == v["n_accept"] and r["stats"]["n_reject"].tolist() == v["n_reject"]
         np.testing.assert_allclose(r["pred"][:, ::7, :], np.array(v["pred_every7"]), rtol=1e-6, atol=1e-10)
+
+
+# ---------------------------------------------------------------- KenCarp4 (BASELINE config 5; not in the reference)
+def test_kencarp4_tableau_order_conditions():
+    """ESDIRK4(3)6L[2]SA: stiffly accurate, stage order 2, main method order 4, embedded order 3."""
+    A, bhat = oracle.kencarp4_tableau()
+    b = A[5].copy(); c = A.sum(axis=1); one = np.ones(6)
+    assert np.allclose(c, [0, 1 / 2, 83 / 250, 31 / 50, 17 / 20, 1], atol=1e-14)
+    assert np.allclose(np.diag(A)[1:], 0.25) and A[0, 0] == 0
+    Ac = A @ c
+    for got, want in [(b @ one, 1), (b @ c, 1 / 2), (b @ c**2, 1 / 3), (b @ Ac, 1 / 6), (b @ c**3, 1 / 4),
+                      (b @ (c * Ac), 1 / 8), (b @ (A @ c**2), 1 / 12), (b @ (A @ Ac), 1 / 24)]:
+        assert abs(got - want) < 1e-13
+    for got, want in [(bhat @ one, 1), (bhat @ c, 1 / 2), (bhat @ c**2, 1 / 3), (bhat @ Ac, 1 / 6)]:
+        assert abs(got - want) < 1e-13
+    assert np.allclose(A[1:] @ c, c[1:]**2 / 2, atol=1e-13)       # stage order 2
+
+
+def test_kencarp4_against_radau_and_conservation(golden):
+    c = cases.CASES["robertson"]
+    pb = make_problem("robertson", golden, 6)
+    o = c.opts(alg=_abi.ALG_KENCARP4)
+    r = oracle.solve_batch(pb["model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["model"], c.opts(abstol=np.array([1e-10, 1e-12, 1e-10]), reltol=np.full(3, 1e-7),
+                                                  maxiters=10**7), pb["u0"])          # tight Rosenbrock23
+    assert (r["retcode"] == 1).all() and (r["stats"]["n_accept"] < 60).all()
+    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    assert (np.abs(r["pred"][:, -1] - ref["pred"][:, -1]) / scale).max() < 2e-3       # step endpoints: the method itself
+    # HyChem-sized synthetic model (29 species + T, 30 reactions): sum(u) is conserved by construction
+    m = cases.synthetic_stiff_model(); u0 = cases.synthetic_stiff_u0(8); so = cases.synthetic_stiff_opts()
+    s = oracle.solve_batch(m, so, u0, n_threads=4)
+    assert (s["retcode"] == 1).all()
+    assert np.abs(s["pred"][:, -1].sum(axis=1) - u0[:, :29].sum(axis=1)).max() < 1e-6
+    sol = solve_ivp(lambda t, u: oracle.rhs(m, u), (0, 1.0), u0[0], method="Radau", rtol=1e-10, atol=1e-14)
+    assert np.abs(sol.y[:29, -1] - s["pred"][0, -1]).max() < 5e-4
+    from crnn_b200.engine import EngineError  # noqa: F401  (KenCarp4 has no sensitivity path: value only)
+    with pytest.raises(RuntimeError):
+        oracle.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"])
