@@ -237,21 +237,25 @@ def true_model_case3(lb=1e-30) -> CRNNModel:
 def synthetic_stiff_model(ns=29, nr=30, seed=0, lb=1e-12) -> CRNNModel:
     """HyChem-sized synthetic CRNN (BASELINE config 5; the reference's HyChem data file is not in its
     repository, HyChem/crnn_pyrolysis_mass.jl:32): `ns` species + temperature as the last state (F1),
-    `nr` mass-action reactions (1 or 2 reactants -> as many products, so sum(u) is conserved and the
-    state stays bounded), pre-exponentials spread over 9 decades and Arrhenius rows of 0-12 kcal/mol:
-    a stiff system."""
+    `nr`/2 REVERSIBLE mass-action reactions (1 or 2 reactants <-> as many products: sum(u) is conserved,
+    the state stays bounded and — being reversible — away from the lb clamp), pre-exponentials spread over
+    9 decades and Arrhenius rows of 0-12 kcal/mol: a stiff system."""
     g = np.random.default_rng(seed)
     w_in = np.zeros((ns + 1, nr)); w_out = np.zeros((ns, nr))
-    for j in range(nr):
+    w_b = np.zeros(nr)
+    for jf in range(0, nr - 1, 2):
         k = 1 if g.random() < 0.4 else 2
         reac = g.choice(ns, size=k, replace=False)
         prod = g.choice(np.setdiff1d(np.arange(ns), reac), size=k, replace=False)
-        for a in reac:
-            w_in[a, j] += 1.0; w_out[a, j] -= 1.0
-        for c in prod:
-            w_out[c, j] += 1.0
-    w_in[ns, :] = g.uniform(0.0, 12.0, nr)           # Ea [kcal/mol]
-    w_b = g.uniform(-2.0, 19.0, nr)                  # ln A
+        for j, (a_, b_) in ((jf, (reac, prod)), (jf + 1, (prod, reac))):
+            for a in a_:
+                w_in[a, j] += 1.0; w_out[a, j] -= 1.0
+            for c in b_:
+                w_out[c, j] += 1.0
+        w_b[jf] = g.uniform(2.0, 19.0)                  # ln A forward
+        w_b[jf + 1] = w_b[jf] - g.uniform(0.0, 5.0)     # ln A reverse
+        w_in[ns, jf] = g.uniform(0.0, 12.0)             # Ea [kcal/mol]
+        w_in[ns, jf + 1] = g.uniform(0.0, 12.0)
     return CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F1, lb=lb, ub=INF)
 
 

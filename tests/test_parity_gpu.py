@@ -341,13 +341,13 @@ def test_kencarp4_hychem_sized(engine):
     got = engine.solve_batch(m, o, u0)
     ref = oracle.solve_batch(m, o, u0, n_threads=8)
     assert (got["retcode"] == 1).all() and np.array_equal(got["n_saved"], ref["n_saved"])
-    # This model keeps crossing the lb clamp (exhausted species): its simplified-Newton decisions sit on
-    # a knife edge, and CUDA's exp/log differ from glibc's in the last ulp, so iteration counts differ for
-    # many trajectories.  Both solve the same ODE to tolerance: compare states and total work.
-    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    # Newton decisions can flip on last-ulp differences between CUDA's and glibc's exp/log; allow a few
+    # trajectories to differ in counts (they still solve the same ODE to tolerance).
+    # trace species sit at the abstol (1e-8) level: measure against max(species range, 1e-4)
+    scale = np.maximum(np.abs(ref["pred"]).max(axis=(0, 1)), 1e-4)
     assert (np.abs(got["pred"] - ref["pred"]) / scale).max() < 5e-3
     same = got["stats"]["n_rhs"] == ref["stats"]["n_rhs"]
-    assert (np.abs(got["pred"] - ref["pred"])[same] / scale).max() < 1e-7 if same.any() else True
+    assert same.mean() > 0.9 and (np.abs(got["pred"] - ref["pred"])[same] / scale).max() < 2e-6
     assert abs(got["stats"]["n_rhs"].sum() / ref["stats"]["n_rhs"].sum() - 1.0) < 0.1
     assert np.abs(got["pred"][:, -1].sum(axis=1) - u0[:, :29].sum(axis=1)).max() < 1e-6   # sum(u) conserved
     nsu = np.random.default_rng(1).integers(5, 41, size=256).astype(np.int32)
