@@ -5,6 +5,7 @@
 // (inst.cu with -DCRNN_NS/-DCRNN_NR/-DCRNN_KIND) so the build parallelises.
 #include "crnn_host.cuh"
 #include "kernel_kencarp4_wide.cuh"
+#include "kernel_tsit5_adjoint.cuh"
 
 namespace crnn_host {
 #define X(NS_, NR_, K_)                                                                                     \
@@ -20,12 +21,13 @@ using namespace crnn_host;
 
 namespace {
 
-// KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
-int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+// Fills the generic-dimension parameter block shared by the lane-per-component kernels and uploads
+// its device arrays: w_inT [nin][32] | w_b | w_out (scaled) | saveat | row2obs | extra doubles.
+int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int order, const std::vector<double>& extra,
+               cudaStream_t st, WideP& P, const double** extra_dev) {
   if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 kernel supports n_state <= 32 and n_reac <= 32");
+    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state <= 32 and n_reac <= 32");
   const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
-  WideP P{};
   std::vector<int> row2obs(n, -1);
   for (int q = 0; q < o->n_obs; ++q) {
     const int r = o->obs_idx[q];
@@ -39,7 +41,6 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   }
   P.lb = m->lb; P.ub = m->ub; P.gas_R = m->gas_R;
   P.t0 = o->t0; P.t1 = o->t1; P.pred_lo = o->pred_clamp_lo; P.pred_hi = o->pred_clamp_hi;
-  const int order = 4;
   const double qmin = o->qmin > 0 ? o->qmin : 0.2, qmax = o->qmax > 0 ? o->qmax : 10.0;
   P.inv_qmin = 1.0 / qmin; P.inv_qmax = 1.0 / qmax;
   P.gamma = o->gamma > 0 ? o->gamma : 0.9;
@@ -49,13 +50,14 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   P.maxiters = o->maxiters;
   P.n = n; P.ns = ns; P.nin = nin; P.nr = nr; P.kind = m->rhs_kind;
   P.n_save = o->n_save; P.n_obs = o->n_obs;
-  // device blob: w_inT [nin][32] | w_b [nr] | w_out [ns*nr] | saveat [n_save] | row2obs [n]
-  std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + (n + 1) / 2 + 2, 0.0);
+  const size_t n_r2o = (n + 1) / 2 + 1;
+  std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + n_r2o + extra.size() + 2, 0.0);
   double* p_winT = blob.data();
   double* p_wb = p_winT + (size_t)nin * KW_MAXN;
   double* p_wout = p_wb + nr;
   double* p_save = p_wout + (size_t)ns * nr;
   int* p_r2o = reinterpret_cast<int*>(p_save + o->n_save);
+  double* p_extra = p_save + o->n_save + n_r2o;
   for (int j = 0; j < nr; ++j) {
     for (int i = 0; i < nin; ++i) p_winT[(size_t)i * KW_MAXN + j] = m->w_in[i + nin * j];
     p_wb[j] = m->w_b[j];
@@ -63,13 +65,23 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   }
   for (int k = 0; k < o->n_save; ++k) p_save[k] = o->saveat[k];
   for (int i = 0; i < n; ++i) p_r2o[i] = row2obs[i];
-  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  for (size_t q = 0; q < extra.size(); ++q) p_extra[q] = extra[q];
   CK(h->cfg.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
   CK(cudaMemcpyAsync(h->cfg.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   double* d = h->cfg.as<double>();
   P.w_inT = d; P.w_b = d + (p_wb - blob.data()); P.w_out = d + (p_wout - blob.data());
   P.saveat = d + (p_save - blob.data());
   P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
+  if (extra_dev) *extra_dev = d + (p_extra - blob.data());
+  return CRNN_OK;
+}
+
+// KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
+int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  WideP P{};
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
+  if (rcw) return rcw;
   constexpr int WARPS = 4;
   auto kern = k_kencarp4_wide<WARPS>;
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
@@ -89,6 +101,68 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
     h->launches++;
     return (int)CRNN_OK;
   });
+}
+
+
+// Interpolating adjoint (BASELINE config 4): Tsit5, generic dimensions, any np (cost independent of np).
+int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                      const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  if (o->alg != CRNN_ALG_TSIT5) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for Tsit5");
+  const int n = m->n_state, ns = m->n_species, nr = m->n_reac;
+  const int nw = nr * (m->n_in + 1 + ns);
+  if (nw > 32 * ADJ_MAX_ENT) return fail(h, CRNN_ERR_UNSUPPORTED, "adjoint kernel supports n_w <= 512");
+  // extra device doubles: scale[ns] | inv_ys[n] | seed [nw*np]
+  std::vector<double> extra((size_t)ns + n + (size_t)nw * np, 1.0);
+  for (int i = 0; i < ns; ++i) extra[i] = m->out_scale ? m->out_scale[i] : 1.0;
+  for (int q = 0; q < o->n_obs; ++q) {
+    const int r = o->obs_idx[q];
+    if (r >= 0 && r < n && loss_kind == CRNN_LOSS_MAE_SCALED) extra[ns + r] = 1.0 / yscale[q];
+  }
+  for (size_t q = 0; q < (size_t)nw * np; ++q) extra[(size_t)ns + n + q] = dW_dp[q];
+  AdjP P{};
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  const double* extra_dev = nullptr;
+  int rcw = build_wide(h, m, o, 5, extra, st, P.w, &extra_dev);
+  if (rcw) return rcw;
+  P.scale = extra_dev; P.inv_ys = extra_dev + ns;
+  const double* seed_dev = extra_dev + ns + n;
+  P.nw = nw; P.loss_kind = loss_kind;
+  constexpr int WARPS = 4;
+  auto kern = k_tsit5_adjoint<WARPS>;
+  const int stride = 8 * n + 2;
+  // forward-record capacity in shared memory: two blocks of 4 warps per SM
+  const size_t budget = (size_t)(227 * 1024 / 2) - 2048 - sizeof(WideBlock);
+  const size_t fixed_pw = (128 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
+  if (fixed_pw * WARPS > budget) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
+  P.cap_s = (int)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
+  P.cap_g = 512;
+  const size_t smem = sizeof(WideBlock) + WARPS * (fixed_pw + (size_t)P.cap_s * stride * sizeof(double));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+  if (bps < 1) bps = 1;
+  const long long max_blocks = (long long)h->num_sms * bps;
+  CK(h->adj_scratch.reserve((size_t)max_blocks * WARPS * P.cap_g * stride * sizeof(double)));
+  P.scratch = h->adj_scratch.as<double>();
+  PostFn post = [=](const double* red, double* out, cudaStream_t s) -> int {
+    k_seed_contract<<<1, 256, 0, s>>>(seed_dev, red, nw, np, out);
+    CK(cudaGetLastError());
+    h->launches++;
+    return CRNN_OK;
+  };
+  return run_batch(h, m, o, io, N, true, nw, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) -> int {
+    if (b.n == 0) return (int)CRNN_OK;
+    const long long want = (b.n + WARPS - 1) / WARPS;
+    const unsigned blocks = (unsigned)std::min<long long>(max_blocks, want);
+    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    ProfScope prof(h, s);
+    kern<<<blocks, WARPS * 32, smem, s>>>(P, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved,
+                                       b.retcode, b.stats, queue);
+    CK(cudaGetLastError());
+    h->launches++;
+    return (int)CRNN_OK;
+  }, np, post);
 }
 
 }  // namespace
@@ -130,7 +204,7 @@ void crnn_destroy(crnn_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum};
+  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
     DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s], &h->d_loss[s], &h->d_nsaved[s],
@@ -208,11 +282,13 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
   if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG)
     return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
   if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
-  if (o->sens_mode != CRNN_SENS_FORWARD)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "only CRNN_SENS_FORWARD is implemented");
+  if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be CRNN_SENS_FORWARD or CRNN_SENS_INTERP_ADJOINT");
   if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, data, pred, loss, n_saved, retcode, stats};
+  if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT)
+    return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -68,7 +69,7 @@ struct crnn_handle {
   // staging for the host-buffer path (per pipeline slot) and full-batch gradients
   DevBuf d_u0[kPipe], d_nsu[kPipe], d_data[kPipe], d_pred[kPipe], d_loss[kPipe], d_nsaved[kPipe], d_ret[kPipe],
       d_stats[kPipe];
-  DevBuf d_grad_each, d_grad_sum;
+  DevBuf d_grad_each, d_grad_sum, d_grad_out, adj_scratch;
   // optional kernel timing (crnn_profile_begin/_end)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -353,9 +354,14 @@ struct HostIO {
   double* pred; double* loss; int32_t* n_saved; int32_t* retcode; crnn_stats* stats;
 };
 
+// `post` (optional): maps the reduced per-trajectory vector (length np, device) to the final gradient
+// (length nout, device) — the adjoint path contracts vec(G) with dW/dp there.
+using PostFn = std::function<int(const double* red_dev, double* out_dev, cudaStream_t)>;
+
 template <class F>
 int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N, bool want_loss,
-              int np, double* grad_sum, F&& launch) {
+              int np, double* grad_sum, F&& launch, int nout = -1, const PostFn& post = nullptr) {
+  if (nout < 0) nout = np;
   const size_t ns = m->n_state, ps = (size_t)o->n_obs * o->n_save;
   if (o->buffers_on_device) {
     cudaStream_t st = (cudaStream_t)o->stream;
@@ -367,8 +373,13 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
     int rc = launch(b, st);
     if (rc) return rc;
     if (want_loss && np > 0 && grad_sum) {
-      if (N == 0) { CK(cudaMemsetAsync(grad_sum, 0, np * sizeof(double), st)); }
-      else { rc = launch_grad_reduce(h, b.grad_each, N, np, grad_sum, st); if (rc) return rc; }
+      if (N == 0) { CK(cudaMemsetAsync(grad_sum, 0, nout * sizeof(double), st)); }
+      else if (!post) { rc = launch_grad_reduce(h, b.grad_each, N, np, grad_sum, st); if (rc) return rc; }
+      else {
+        CK(h->d_grad_sum.reserve(np * sizeof(double)));
+        rc = launch_grad_reduce(h, b.grad_each, N, np, h->d_grad_sum.as<double>(), st); if (rc) return rc;
+        rc = post(h->d_grad_sum.as<double>(), grad_sum, st); if (rc) return rc;
+      }
     }
     return CRNN_OK;
   }
@@ -421,12 +432,19 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   for (int s = 0; s < kPipe && s < nchunk; ++s) CK(cudaStreamWaitEvent(h->s_compute, h->ev_done[s], 0));
   if (want_loss && np > 0 && grad_sum) {
     if (N == 0) {
-      std::memset(grad_sum, 0, np * sizeof(double));
+      std::memset(grad_sum, 0, nout * sizeof(double));
     } else {
       CK(h->d_grad_sum.reserve(np * sizeof(double)));
       int rc = launch_grad_reduce(h, h->d_grad_each.as<double>(), N, np, h->d_grad_sum.as<double>(), h->s_compute);
       if (rc) return rc;
-      CK(cudaMemcpyAsync(grad_sum, h->d_grad_sum.p, np * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
+      const double* src = h->d_grad_sum.as<double>();
+      if (post) {
+        CK(h->d_grad_out.reserve(std::max<size_t>(8, nout * sizeof(double))));
+        rc = post(src, h->d_grad_out.as<double>(), h->s_compute);
+        if (rc) return rc;
+        src = h->d_grad_out.as<double>();
+      }
+      CK(cudaMemcpyAsync(grad_sum, src, nout * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
     }
   }
   CK(cudaStreamSynchronize(h->s_h2d));

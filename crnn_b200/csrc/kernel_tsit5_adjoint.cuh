@@ -1,0 +1,407 @@
+// kernel_tsit5_adjoint.cuh — loss + gradient by the INTERPOLATING ADJOINT (BASELINE config 4): one WARP
+// owns one trajectory, lane i owns state component i (n_state <= 32, n_reac <= 32, runtime dimensions).
+//
+// The reference never runs an adjoint (its scripts differentiate forward-mode only), so the
+// policies are ours and are spelled out in oracle/crnn_oracle.c (solve_one_adjoint), which this kernel
+// mirrors step for step:
+//   forward   Tsit5 value solve; every accepted step's (t_n, dt_n, u_n, k1..k7) is recorded — in SHARED
+//             memory for the first `cap_s` steps (the usual case: nothing touches HBM), spilling to a
+//             per-warp global scratch beyond that;
+//   backward  lambda' = -J(u(t))^T lambda by adaptive Tsit5 (error control on lambda only) from t_reached
+//             to t0, stopping at every save time where lambda jumps by dL/du(t_k) (loss fused here);
+//             u(t) from the recorded dense output; the parameter quadrature rides the step's own
+//             b-weights as three outer products in physical-weight space
+//                 G_in[i,j] = int x_i g_j r_j, G_b[j] = int g_j r_j, G_out[i,j] = int s_i lambda_i r_j.
+//   output    vec(G) per trajectory; k_grad_reduce sums over trajectories (deterministic order) and
+//             k_seed_contract applies dW/dp^T.
+// Cost is independent of np: the right tool for case3 (np = 153) and larger parameter vectors.
+#pragma once
+#include "crnn_dev.cuh"
+#include "kernel_kencarp4_wide.cuh"  // WideP, WideBlock, KW_MAXN
+
+namespace crnn {
+
+namespace tsc {
+__constant__ double A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {ts::a21, 0, 0, 0, 0, 0},
+    {ts::a31, ts::a32, 0, 0, 0, 0},
+    {ts::a41, ts::a42, ts::a43, 0, 0, 0},
+    {ts::a51, ts::a52, ts::a53, ts::a54, 0, 0},
+    {ts::a61, ts::a62, ts::a63, ts::a64, ts::a65, 0},
+    {ts::a71, ts::a72, ts::a73, ts::a74, ts::a75, ts::a76}};
+__constant__ double BT[7] = {ts::bt1, ts::bt2, ts::bt3, ts::bt4, ts::bt5, ts::bt6, ts::bt7};
+__constant__ double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+__constant__ double R[7][4] = {{ts::r11, ts::r12, ts::r13, ts::r14}, {0.0, ts::r22, ts::r23, ts::r24},
+                               {0.0, ts::r32, ts::r33, ts::r34}, {0.0, ts::r42, ts::r43, ts::r44},
+                               {0.0, ts::r52, ts::r53, ts::r54}, {0.0, ts::r62, ts::r63, ts::r64},
+                               {0.0, ts::r72, ts::r73, ts::r74}};
+}  // namespace tsc
+
+struct AdjP {
+  WideP w;                 // dimensions, tolerances, weights (w_out WITH out_scale folded), saveat, row2obs
+  const double* scale;     // device [n_species] out_scale (1 if none): G_out needs it separately
+  const double* inv_ys;    // device [n_state] 1/yscale per state row (1 where unused)
+  double* scratch;         // global overflow record, per warp slot
+  int cap_s, cap_g;        // record capacity (steps) in shared / global memory
+  int nw, loss_kind;
+};
+
+constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
+                long long ntraj, const double* __restrict__ data, double* __restrict__ loss,
+                double* __restrict__ gw_each, double* __restrict__ pred, int* __restrict__ n_saved,
+                int* __restrict__ retcode, crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const WideP& W = P.w;
+  const int n = W.n, ns = W.ns, nin = W.nin, nr = W.nr, nw = P.nw;
+  const int stride = 8 * n + 2;  // doubles per recorded step: t, dt, u, k1..k7
+  WideBlock& sb = *reinterpret_cast<WideBlock*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per-warp region: x[32] r[32] lam[32] gr[32] | GW[nw] GS[nw] | record[cap_s][stride]
+  const size_t per_warp = 4 * 32 + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
+  double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlock)) + per_warp * warp;
+  double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
+  double* GW = wbase + 128; double* GS = GW + ((nw + 1) & ~1);
+  double* rec_s = GS + ((nw + 1) & ~1);
+  double* rec_g = P.scratch + ((size_t)blockIdx.x * WARPS + warp) * (size_t)P.cap_g * stride;
+
+  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
+    const int i = q / KW_MAXN, j = q % KW_MAXN;
+    sb.w_inT[i][j] = (i < nin && j < nr) ? W.w_inT[i * KW_MAXN + j] : 0.0;
+    sb.w_out[i][j] = (i < nr && j < ns) ? W.w_out[j + ns * i] : 0.0;  // [reaction][species], scaled
+  }
+  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? W.w_b[q] : 0.0;
+  __syncthreads();
+
+  const bool isp = lane < ns;
+  const double my_at = lane < n ? W.abstol[lane] : 1.0, my_rt = lane < n ? W.reltol[lane] : 0.0;
+  const int my_obs = lane < n ? W.row2obs[lane] : -1;
+  const double my_iys = lane < n ? P.inv_ys[lane] : 1.0;
+  const double my_scale = isp ? P.scale[lane] : 0.0;
+  // quadrature entries of this lane: e = lane + 32*q ; packed (kind, i, j)
+  int ent[ADJ_MAX_ENT];
+#pragma unroll
+  for (int q = 0; q < ADJ_MAX_ENT; ++q) {
+    const int e = lane + 32 * q;
+    int code = -1;
+    if (e < nin * nr) code = (0 << 16) | ((e % nin) << 8) | (e / nin);
+    else if (e < nin * nr + nr) code = (1 << 16) | (e - nin * nr);
+    else if (e < nw) { const int f = e - nin * nr - nr; code = (2 << 16) | ((f % ns) << 8) | (f / ns); }
+    ent[q] = code;
+  }
+
+  auto rec_ptr = [&](int step) -> double* {
+    return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
+  };
+  // forward RHS: lane i holds y_i -> f_i (x, r left in shared memory)
+  auto rhs = [&](double y) -> double {
+    __syncwarp();
+    double xi = 0.0;
+    if (isp) xi = log(clampd(y, W.lb, W.ub));
+    else if (W.kind == 1 && lane == ns) xi = -1.0 / (W.gas_R * y);
+    s_x[lane] = xi;
+    __syncwarp();
+    if (lane < nr) {
+      double z = sb.w_b[lane];
+      for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+      s_r[lane] = exp(z);
+    }
+    __syncwarp();
+    double f = 0.0;
+    if (isp)
+      for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], s_r[j], f);
+    return f;
+  };
+  // u_i(ts) from the recorded dense output of step `ir`
+  auto dense_u = [&](int ir, double tsx) -> double {
+    const double* r0 = rec_ptr(ir);
+    const double th = (tsx - r0[0]) / r0[1];
+    double acc = 0.0;
+    if (lane < n) {
+#pragma unroll
+      for (int q7 = 0; q7 < 7; ++q7) {
+        const double b = th * (tsc::R[q7][0] + th * (tsc::R[q7][1] + th * (tsc::R[q7][2] + th * tsc::R[q7][3])));
+        acc = fma(b, r0[2 + (1 + q7) * n + lane], acc);
+      }
+      acc = fma(r0[1], acc, r0[2 + lane]);
+    }
+    return acc;
+  };
+  auto wrms = [&](double v, double a, double b) -> double {
+    double q = 0.0;
+    if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
+    return sqrt(warp_sum(q) / n);
+  };
+
+  while (true) {
+    unsigned long long tq = 0;
+    if (lane == 0) tq = atomicAdd(queue, 1ull);
+    const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
+    if (traj >= ntraj) break;
+
+    double u = lane < n ? __ldg(u0 + traj * n + lane) : 0.0;
+    const double u_init = u;
+    int nsave = W.n_save;
+    double tend = W.t1;
+    if (n_save_used) {
+      int q = __ldg(n_save_used + traj);
+      if (q > 0 && q <= W.n_save) { nsave = q; tend = __ldg(W.saveat + q - 1); }
+    }
+    const double t0 = W.t0, dtmax = tend - t0;
+    const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
+    const size_t pbase = (size_t)traj * W.n_obs * W.n_save;
+
+    // ================= forward: Tsit5 value solve, recording every accepted step =================
+    int n_rhs = 0, n_acc = 0, n_rej = 0, n_back = 0, nrec = 0;
+    double k[7];
+    k[0] = rhs(u); ++n_rhs;
+    double dt;
+    {
+      const double sk = my_at + fabs(u) * my_rt;
+      double a = 0.0, b = 0.0;
+      if (lane < n) { a = u / sk; a *= a; b = k[0] / sk; b *= b; }
+      const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+      double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+      dt0 = jmin(dt0, dtmax);
+      const double f1 = rhs(fma(dt0, k[0], u)); ++n_rhs;
+      double c = 0.0;
+      if (lane < n) { c = (f1 - k[0]) / sk; c *= c; }
+      const double d2 = sqrt(warp_sum(c) / n) / dt0;
+      const double dm = jmax(d1, d2);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * W.inv_order);
+      dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
+    }
+    double t = t0, qold = 1e-4, dt_last = 0.0;
+    int isave = 0, ret = CRNN_RET_DEFAULT;
+    long long iter = 0;
+    while (isave < nsave && __ldg(W.saveat + isave) <= t0) ++isave;
+    while (t < tend) {
+      ++iter;
+      if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
+      if (iter > W.maxiters) { ret = CRNN_RET_MAXITERS; break; }
+      dt = jmin(dt, dtmax);
+      dt = jmin(dt, tend - t);
+      if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+      if (__any_sync(0xffffffffu, lane < n && u != u)) { ret = CRNN_RET_UNSTABLE; break; }
+      double un = u;
+#pragma unroll 1
+      for (int s = 1; s < 7; ++s) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (j < s) acc = (j == 0) ? tsc::A[s][0] * k[0] : fma(tsc::A[s][j], k[j], acc);
+        un = fma(dt, acc, u);
+        const double f = rhs(un); ++n_rhs;
+#pragma unroll
+        for (int j = 1; j < 7; ++j)
+          if (j == s) k[j] = f;
+      }
+      double e = tsc::BT[0] * k[0];
+#pragma unroll
+      for (int j = 1; j < 7; ++j) e = fma(tsc::BT[j], k[j], e);
+      const double EEst = wrms(dt * e, u, un);
+      double q11, q;
+      if (EEst == 0.0) { q11 = 0.0; q = W.inv_qmax; }
+      else { q11 = pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / pow(qold, W.beta2) / W.gamma)); }
+      dt_last = dt;
+      if (EEst <= 1.0) {
+        ++n_acc;
+        qold = jmax(EEst, 1e-4);
+        const double dtnew = dt / q;
+        if (nrec >= P.cap_s + P.cap_g) { ret = CRNN_RET_MAXITERS; break; }  // record capacity (documented limit)
+        double* r0 = rec_ptr(nrec);
+        if (lane == 0) { r0[0] = t; r0[1] = dt; }
+        if (lane < n) {
+          r0[2 + lane] = u;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) r0[2 + (1 + j) * n + lane] = k[j];
+        }
+        ++nrec;
+        t = snap_t(t + dt, tend);
+        while (isave < nsave && __ldg(W.saveat + isave) <= t) ++isave;
+        u = un; k[0] = k[6];
+        dt = jmin(dtnew, dtmax);
+      } else {
+        ++n_rej;
+        dt = dt / jmin(W.inv_qmin, q11 / W.gamma);
+      }
+    }
+    if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+    const double t_reached = t;
+    const double cnt = (double)W.n_obs * (double)isave;
+    __syncwarp();
+
+    // ================= backward: adjoint sweep with jumps at the save times =================
+    for (int e = lane; e < nw; e += 32) GW[e] = 0.0;
+    double lam = 0.0, loss_acc = 0.0;
+    double cur = t_reached, bdt = 0.0, bq = 1e-4;
+    int ir = nrec - 1;
+    bool have_dt = false;
+    long long biter = 0;
+    double K[7];
+    // adjoint RHS at state component u_i (lane), multiplier value in s_lam: returns (J^T lambda)_i and leaves
+    // x in s_x, r in s_r, g.*r in s_gr
+    auto adj_rhs = [&](double ui, double li) -> double {
+      __syncwarp();
+      double xi = 0.0, dxi = 0.0;
+      if (isp) {
+        const double uc = clampd(ui, W.lb, W.ub);
+        xi = log(uc);
+        dxi = (ui >= W.lb && ui <= W.ub) ? __drcp_rn(uc) : 0.0;
+      } else if (W.kind == 1 && lane == ns) {
+        xi = -1.0 / (W.gas_R * ui);
+      }
+      s_x[lane] = xi;
+      s_lam[lane] = isp ? li : 0.0;
+      __syncwarp();
+      if (lane < nr) {
+        double z = sb.w_b[lane], gs = 0.0;
+        for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+        for (int i = 0; i < ns; ++i) gs = fma(sb.w_out[lane][i], s_lam[i], gs);
+        const double r = exp(z);
+        s_r[lane] = r;
+        s_gr[lane] = gs * r;
+      }
+      __syncwarp();
+      double s = 0.0;
+      if (isp)
+        for (int j = 0; j < nr; ++j) s = fma(sb.w_inT[lane][j], s_gr[j], s);
+      return dxi * s;
+    };
+
+    if (isave > 0) {
+      for (int ks = isave; ks >= 0; --ks) {
+        const double tlo = (ks > 0) ? __ldg(W.saveat + ks - 1) : t0;
+        if (ks < isave) {
+          while (cur > tlo) {
+            if (++biter > W.maxiters) { ret = CRNN_RET_MAXITERS; break; }
+            if (!have_dt) {  // Hairer initial step of the lambda system at `cur`
+              while (ir > 0 && rec_ptr(ir)[0] >= cur) --ir;
+              K[0] = adj_rhs(dense_u(ir, cur), lam); ++n_rhs;
+              const double sk = my_at + fabs(lam) * my_rt;
+              double a = 0.0, b = 0.0;
+              if (lane < n) { a = lam / sk; a *= a; b = K[0] / sk; b *= b; }
+              const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+              bdt = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+              have_dt = true;
+            }
+            const double h = jmin(bdt, cur - tlo);
+            if (!(h > 0.0)) break;
+            for (int e = lane; e < nw; e += 32) GS[e] = 0.0;
+            double ln = lam;
+#pragma unroll 1
+            for (int s = 0; s < 7; ++s) {
+              double y = lam;
+              if (s > 0) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                  if (j < s) acc = (j == 0) ? tsc::A[s][0] * K[0] : fma(tsc::A[s][j], K[j], acc);
+                y = fma(h, acc, lam);
+              }
+              if (s == 6) ln = y;
+              const double tsx = cur - tsc::C[s] * h;
+              while (ir > 0 && rec_ptr(ir)[0] > tsx) --ir;
+              while (ir < nrec - 1 && rec_ptr(ir)[0] + rec_ptr(ir)[1] < tsx) ++ir;
+              const double f = adj_rhs(dense_u(ir, tsx), y); ++n_rhs;
+#pragma unroll
+              for (int j = 0; j < 7; ++j)
+                if (j == s) K[j] = f;
+              if (s < 6) {  // quadrature: b-weights of the 5th-order solution (b7 = 0)
+                const double bw = tsc::A[6][s];
+#pragma unroll
+                for (int q = 0; q < ADJ_MAX_ENT; ++q) {
+                  const int code = ent[q];
+                  if (code >= 0) {
+                    const int kind = code >> 16, i = (code >> 8) & 255, j = code & 255;
+                    double val;
+                    if (kind == 0) val = s_x[i] * s_gr[j];
+                    else if (kind == 1) val = s_gr[j];
+                    else val = P.scale[i] * s_lam[i] * s_r[j];
+                    GS[lane + 32 * q] = fma(bw, val, GS[lane + 32 * q]);
+                  }
+                }
+              }
+            }
+            double e = tsc::BT[0] * K[0];
+#pragma unroll
+            for (int j = 1; j < 7; ++j) e = fma(tsc::BT[j], K[j], e);
+            const double EEst = wrms(h * e, lam, ln);
+            double q11, q;
+            if (EEst == 0.0) { q11 = 0.0; q = W.inv_qmax; }
+            else { q11 = pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / pow(bq, W.beta2) / W.gamma)); }
+            if (EEst <= 1.0) {
+              bq = jmax(EEst, 1e-4);
+              for (int ee = lane; ee < nw; ee += 32) GW[ee] = fma(h, GS[ee], GW[ee]);
+              lam = ln;
+              const double nxt = cur - h;
+              cur = (fabs(nxt - tlo) < 100.0 * 2.220446049250313e-16 * fmax(fabs(cur), fabs(tlo))) ? tlo : nxt;
+              bdt = jmin(h / q, dtmax);
+              ++n_back;
+            } else {
+              bdt = h / jmin(W.inv_qmin, q11 / W.gamma);
+            }
+          }
+        }
+        if (ks > 0) {
+          // jump at save ks-1: lambda += dL/du(t_k); loss term and pred fused here
+          const int kk = ks - 1;
+          const double tsv = __ldg(W.saveat + kk);
+          int jr = ir;
+          while (jr > 0 && rec_ptr(jr)[0] >= tsv) --jr;
+          while (jr < nrec - 1 && rec_ptr(jr)[0] + rec_ptr(jr)[1] < tsv) ++jr;
+          double y;
+          if (tsv <= t0) y = u_init;                                        // t0 itself is saved exactly
+          else if (kk == isave - 1 && tsv == t_reached) y = u;              // last save = end state, exactly
+          else y = dense_u(jr, tsv);
+          if (my_obs >= 0) {
+            const double yc = clampd(y, W.pred_lo, W.pred_hi);
+            const bool inside = (y >= W.pred_lo) && (y <= W.pred_hi);
+            const size_t off = pbase + my_obs + (size_t)W.n_obs * kk;
+            if (pred) pred[off] = yc;
+            const double d = __ldg(data + off);
+            double diff, g;
+            if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
+            else { diff = log(clampd(d, W.pred_lo, W.pred_hi)) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+            loss_acc += fabs(diff);
+            if (inside && isp) lam += g / cnt;
+          }
+          if (tsv < cur) cur = tsv;
+        }
+      }
+    }
+    const double ltot = warp_sum(loss_acc);
+    __syncwarp();
+    for (int e = lane; e < nw; e += 32) gw_each[(size_t)traj * nw + e] = isave > 0 ? GW[e] : 0.0;
+    if (lane == 0) {
+      loss[traj] = isave > 0 ? ltot / cnt : __longlong_as_double(0x7ff8000000000000LL);
+      if (n_saved) n_saved[traj] = isave;
+      if (retcode) retcode[traj] = ret;
+      if (stats) {
+        crnn_stats s;
+        s.n_accept = n_acc; s.n_reject = n_rej; s.n_rhs = n_rhs; s.n_jac = n_back;
+        s.t_reached = t_reached; s.dt_last = dt_last;
+        stats[traj] = s;
+      }
+    }
+    if (pred && my_obs >= 0)
+      for (int ks = isave; ks < W.n_save; ++ks) pred[pbase + my_obs + (size_t)W.n_obs * ks] = 0.0;
+    __syncwarp();
+  }
+}
+
+// grad_sum[c] = sum_w dW_dp[w, c] * gw_sum[w]   (dW_dp col-major [nw, np], with out_scale NOT folded: G_out carries it)
+static __global__ void k_seed_contract(const double* __restrict__ seed, const double* __restrict__ gw_sum, int nw, int np,
+                                       double* __restrict__ grad_sum) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < np; c += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s = fma(seed[w + (size_t)nw * c], gw_sum[w], s);
+    grad_sum[c] = s;
+  }
+}
+
+}  // namespace crnn

@@ -671,6 +671,220 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
   free(buf);
 }
 
+/* ---- Interpolating adjoint (BASELINE config 4).  NOT exercised by the reference
+ * (its scripts differentiate forward-mode only), so the policies are OURS — parity unpinned:
+ *  forward: the Tsit5 value solve of solve_one, recording (t_n, dt_n, u_n, k1..k7) of every accepted step;
+ *  backward: lambda' = -J(u(t))^T lambda integrated by adaptive Tsit5 (same tolerances, error control on
+ *  lambda only) from t_reached to t0 with a stop at every save time, where lambda jumps by dL/du(t_k);
+ *  u(t) comes from the recorded dense output; the parameter quadrature is carried with the step's own
+ *  b-weights in physical-weight space as three outer products (App. B.4)
+ *      G_in[i,j] = int x_i g_j r_j,  G_b[j] = int g_j r_j,  G_out[i,j] = int s_i lambda_i r_j,  g = W_out^T (s.lambda)
+ *  and contracted with dW/dp at the end.  A continuous adjoint: its gradient differs from the discrete
+ *  forward-mode one by O(tolerance). */
+typedef struct { double t, dt; } rec_hdr;
+
+static void adj_rhs(const ctx_t* c, const double* u, const double* lam, double* dlam, double* gw /* nw integrand or NULL */) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  rhs_cache k; double du[MAXN], g[MAXR];
+  rhs_value(c, u, du, &k);
+  for (int j = 0; j < nr; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < ns; ++i) s += m->w_out[i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * lam[i];
+    g[j] = s * k.r[j];
+  }
+  for (int l = 0; l < ns; ++l) {
+    double s = 0.0;
+    for (int j = 0; j < nr; ++j) s += m->w_in[l + nin * j] * g[j];
+    dlam[l] = k.dx[l] * s; /* (J^T lambda)_l, reverse time */
+  }
+  for (int l = ns; l < c->n; ++l) dlam[l] = 0.0; /* lambda_T never feeds back (row T of J is zero) */
+  if (gw) {
+    for (int j = 0; j < nr; ++j) {
+      for (int i = 0; i < nin; ++i) gw[i + nin * j] = k.x[i] * g[j];
+      gw[nin * nr + j] = g[j];
+      for (int i = 0; i < ns; ++i) gw[nin * nr + nr + i + ns * j] = (m->out_scale ? m->out_scale[i] : 1.0) * lam[i] * k.r[j];
+    }
+  }
+}
+
+static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, const double* data, const double* yscale,
+                              int loss_kind, double* loss_out, double* gw_out /* nw */, double* pred, traj_result* res) {
+  const crnn_opts* o = c->o;
+  const int n = c->n, nw = c->nw;
+  const double t0 = o->t0;
+  const double tend = (n_save_use > 0 && n_save_use <= o->n_save) ? o->saveat[n_save_use - 1] : o->t1;
+  const int nsave = (n_save_use > 0 && n_save_use <= o->n_save) ? n_save_use : o->n_save;
+  const double dtmax = tend - t0;
+  const double dtmin = fmax(nextafter(fabs(t0), INFINITY) - fabs(t0), nextafter(fabs(tend), INFINITY) - fabs(tend));
+  int cap = 64, nrec = 0;
+  rec_hdr* hdr = (rec_hdr*)malloc(sizeof(rec_hdr) * cap);
+  double* rec = (double*)malloc(sizeof(double) * (size_t)cap * 8 * n); /* u, k1..k7 per step */
+  double* ysave = (double*)calloc((size_t)o->n_save * n, sizeof(double)); /* unclamped u(t_k) */
+  double* buf = (double*)calloc((size_t)n * 12 + (size_t)nw * 2 + 8 * n, sizeof(double));
+  double* U = buf; double* Un = U + n; double* K[7];
+  for (int s = 0; s < 7; ++s) K[s] = Un + n * (s + 1);
+  double* TMP = K[6] + n; double* E = TMP + n; double* W2 = E + n; /* 2n */
+  double* GW = W2 + 2 * n; double* GS = GW + nw;
+  rhs_cache kc;
+  memcpy(U, u0, sizeof(double) * n);
+  double t = t0, dt, qold = 1e-4;
+  int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
+  memset(&res->st, 0, sizeof(res->st));
+  rhs_value(c, U, K[0], &kc); res->st.n_rhs++;
+  { /* initial_dt wants ncol-strided arrays: ncol == 1 here */
+    dt = initial_dt(c, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
+  }
+  while (isave < nsave && o->saveat[isave] <= t0) { memcpy(ysave + (size_t)isave * n, U, sizeof(double) * n); ++isave; }
+  /* ---------------- forward (identical to solve_one's Tsit5 value path) ---------------- */
+  while (t < tend) {
+    ++iter;
+    if (isnan(dt)) { ret = CRNN_RET_DTNAN; break; }
+    if (iter > o->maxiters) { ret = CRNN_RET_MAXITERS; break; }
+    dt = jmin(dt, dtmax);
+    dt = jmin(dt, tend - t);
+    if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+    if (has_nan(U, n)) { ret = CRNN_RET_UNSTABLE; break; }
+    for (int s = 1; s < 7; ++s) {
+      double* Y = (s == 6) ? Un : TMP;
+      for (int q = 0; q < n; ++q) {
+        double acc = TS_A[s][0] * K[0][q];
+        for (int j = 1; j < s; ++j) acc += TS_A[s][j] * K[j][q];
+        Y[q] = U[q] + dt * acc;
+      }
+      rhs_value(c, Y, K[s], &kc); res->st.n_rhs++;
+    }
+    for (int q = 0; q < n; ++q) {
+      double acc = TS_BT[0] * K[0][q];
+      for (int j = 1; j < 7; ++j) acc += TS_BT[j] * K[j][q];
+      E[q] = dt * acc;
+    }
+    double EEst = err_norm(c, E, U, Un);
+    double q11, q = pi_q(c, EEst, qold, &q11);
+    res->st.dt_last = dt;
+    if (EEst <= 1.0) {
+      res->st.n_accept++;
+      qold = jmax(EEst, 1e-4);
+      double dtnew = dt / q, tprev = t;
+      t = snap_t(t + dt, tend);
+      if (nrec == cap) { cap *= 2; hdr = (rec_hdr*)realloc(hdr, sizeof(rec_hdr) * cap); rec = (double*)realloc(rec, sizeof(double) * (size_t)cap * 8 * n); }
+      hdr[nrec].t = tprev; hdr[nrec].dt = dt;
+      memcpy(rec + (size_t)nrec * 8 * n, U, sizeof(double) * n);
+      for (int s = 0; s < 7; ++s) memcpy(rec + ((size_t)nrec * 8 + 1 + s) * n, K[s], sizeof(double) * n);
+      ++nrec;
+      while (isave < nsave && o->saveat[isave] <= t) {
+        double ts = o->saveat[isave];
+        double* ys = ysave + (size_t)isave * n;
+        if (ts == t) memcpy(ys, Un, sizeof(double) * n);
+        else {
+          double th = (ts - tprev) / dt, b[7];
+          for (int s = 0; s < 7; ++s) b[s] = th * (TS_R[s][0] + th * (TS_R[s][1] + th * (TS_R[s][2] + th * TS_R[s][3])));
+          for (int q = 0; q < n; ++q) {
+            double acc = b[0] * K[0][q];
+            for (int s = 1; s < 7; ++s) acc += b[s] * K[s][q];
+            ys[q] = U[q] + dt * acc;
+          }
+        }
+        ++isave;
+      }
+      memcpy(U, Un, sizeof(double) * n); memcpy(K[0], K[6], sizeof(double) * n);
+      dt = jmin(dtnew, dtmax);
+    } else {
+      res->st.n_reject++;
+      dt = dt / jmin(1.0 / c->qmin, q11 / c->gamma);
+    }
+  }
+  if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+  res->retcode = ret; res->n_saved = isave; res->st.t_reached = t;
+  /* ---------------- loss and the jumps dL/du(t_k) ---------------- */
+  const double cnt = (double)o->n_obs * (double)isave;
+  double lsum = 0.0;
+  double* jump = (double*)calloc((size_t)(isave > 0 ? isave : 1) * n, sizeof(double));
+  for (int k = 0; k < isave; ++k)
+    for (int qo = 0; qo < o->n_obs; ++qo) {
+      int i = o->obs_idx[qo];
+      double y = ysave[(size_t)k * n + i];
+      double yc = clampd(y, o->pred_clamp_lo, o->pred_clamp_hi);
+      int inside = (y >= o->pred_clamp_lo) && (y <= o->pred_clamp_hi);
+      if (pred) pred[qo + o->n_obs * k] = yc;
+      double d = data[qo + o->n_obs * k], diff, g;
+      if (loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d / yscale[qo] - yc / yscale[qo]; g = (signbit(diff) ? 1.0 : -1.0) / yscale[qo]; }
+      else { double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi); diff = log(dc) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+      lsum += fabs(diff);
+      if (inside) jump[(size_t)k * n + i] += g / cnt;
+    }
+  *loss_out = isave > 0 ? lsum / cnt : NAN;
+  /* ---------------- backward ---------------- */
+  memset(GW, 0, sizeof(double) * nw);
+  if (isave > 0) {
+    double* L = U; double* Ln = Un; /* reuse buffers: lambda, proposed lambda */
+    memset(L, 0, sizeof(double) * n);
+    double cur = t; /* t_reached */
+    double bdt = 0.0, bq = 1e-4;
+    int ir = nrec - 1, have_dt = 0;
+    long long biter = 0;
+    double* gtmp = (double*)malloc(sizeof(double) * nw);
+    double uu[MAXN];
+    for (int k = isave; k >= 0; --k) {
+      double tlo = (k > 0) ? o->saveat[k - 1] : t0;
+      if (k < isave) { /* segment [tlo, cur] with lambda != 0 */
+        while (cur > tlo) {
+          if (++biter > o->maxiters) { res->retcode = CRNN_RET_MAXITERS; break; }
+          if (!have_dt) { /* Hairer initial step on the lambda system at `cur` */
+            /* u(cur) */
+            while (ir > 0 && hdr[ir].t >= cur) --ir;
+            { double th = (cur - hdr[ir].t) / hdr[ir].dt, b[7]; const double* r0 = rec + (size_t)ir * 8 * n;
+              for (int s = 0; s < 7; ++s) b[s] = th * (TS_R[s][0] + th * (TS_R[s][1] + th * (TS_R[s][2] + th * TS_R[s][3])));
+              for (int q = 0; q < n; ++q) { double acc = 0.0; for (int s = 0; s < 7; ++s) acc += b[s] * r0[(1 + s) * n + q]; uu[q] = r0[q] + hdr[ir].dt * acc; } }
+            adj_rhs(c, uu, L, K[0], NULL); res->st.n_rhs++;
+            double d0 = 0.0, d1 = 0.0;
+            for (int i = 0; i < n; ++i) { double at = o->abstol[o->n_abstol > 1 ? i : 0], rt = o->reltol[o->n_reltol > 1 ? i : 0];
+              double sk = at + fabs(L[i]) * rt; d0 += (L[i] / sk) * (L[i] / sk); d1 += (K[0][i] / sk) * (K[0][i] / sk); }
+            d0 = sqrt(d0 / n); d1 = sqrt(d1 / n);
+            bdt = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            have_dt = 1;
+          }
+          double h = jmin(bdt, cur - tlo);
+          if (!(h > 0.0)) break;
+          /* stages at times cur - c_s h */
+          static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+          memset(GS, 0, sizeof(double) * nw);
+          for (int s = 0; s < 7; ++s) {
+            double* Y = (s == 6) ? Ln : TMP;
+            if (s == 0) memcpy(TMP, L, sizeof(double) * n);
+            else for (int q = 0; q < n; ++q) { double acc = TS_A[s][0] * K[0][q]; for (int j = 1; j < s; ++j) acc += TS_A[s][j] * K[j][q]; Y[q] = L[q] + h * acc; }
+            double ts = cur - TS_C[s] * h;
+            while (ir > 0 && hdr[ir].t > ts) --ir;
+            while (ir < nrec - 1 && hdr[ir].t + hdr[ir].dt < ts) ++ir;
+            { double th = (ts - hdr[ir].t) / hdr[ir].dt, b[7]; const double* r0 = rec + (size_t)ir * 8 * n;
+              for (int q7 = 0; q7 < 7; ++q7) b[q7] = th * (TS_R[q7][0] + th * (TS_R[q7][1] + th * (TS_R[q7][2] + th * TS_R[q7][3])));
+              for (int q = 0; q < n; ++q) { double acc = 0.0; for (int q7 = 0; q7 < 7; ++q7) acc += b[q7] * r0[(1 + q7) * n + q]; uu[q] = r0[q] + hdr[ir].dt * acc; } }
+            adj_rhs(c, uu, (s == 0) ? L : Y, K[s], gtmp); res->st.n_rhs++;
+            if (s < 6) { double bw = TS_A[6][s]; for (int w = 0; w < nw; ++w) GS[w] += bw * gtmp[w]; }
+          }
+          for (int q = 0; q < n; ++q) { double acc = TS_BT[0] * K[0][q]; for (int j = 1; j < 7; ++j) acc += TS_BT[j] * K[j][q]; E[q] = h * acc; }
+          double EEst = err_norm(c, E, L, Ln);
+          double q11, q = pi_q(c, EEst, bq, &q11);
+          if (EEst <= 1.0) {
+            bq = jmax(EEst, 1e-4);
+            for (int w = 0; w < nw; ++w) GW[w] += h * GS[w];
+            memcpy(L, Ln, sizeof(double) * n);
+            cur = (fabs((cur - h) - tlo) < 100.0 * 2.220446049250313e-16 * fmax(fabs(cur), fabs(tlo))) ? tlo : cur - h;
+            bdt = jmin(h / q, dtmax); /* h/q: grow from the step actually taken */
+            res->st.n_jac++; /* counts accepted backward steps */
+          } else {
+            bdt = h / jmin(1.0 / c->qmin, q11 / c->gamma);
+          }
+        }
+      }
+      if (k > 0) { for (int i = 0; i < n; ++i) L[i] += jump[(size_t)(k - 1) * n + i]; cur = o->saveat[k - 1] < cur ? o->saveat[k - 1] : cur; }
+    }
+    free(gtmp);
+  }
+  memcpy(gw_out, GW, sizeof(double) * nw);
+  free(jump); free(buf); free(ysave); free(rec); free(hdr);
+}
+
 static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const double* seed, int np) {
   c->m = m; c->o = o;
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
@@ -727,6 +941,8 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   int rc = check_dims(m, o);
   if (rc) return rc;
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
+  const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT);
+  if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));
@@ -740,6 +956,23 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
     sk.pred = pred ? pred + pstride * i : NULL;
     if (sk.pred) memset(sk.pred, 0, sizeof(double) * pstride);
     traj_result r;
+    if (adjoint) {
+      double* gw = (double*)malloc(sizeof(double) * c.nw);
+      double li = 0.0;
+      solve_one_adjoint(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, data + pstride * i, yscale,
+                        loss_kind, &li, gw, sk.pred, &r);
+      loss[i] = li;
+      for (int q = 0; q < np; ++q) { /* grad = dW/dp^T vec(G) */
+        double sacc = 0.0;
+        for (int w = 0; w < c.nw; ++w) sacc += dW_dp[w + (size_t)c.nw * q] * gw[w];
+        gall[(size_t)np * i + q] = r.n_saved > 0 ? sacc : 0.0;
+      }
+      free(gw);
+      if (n_saved) n_saved[i] = r.n_saved;
+      if (retcode) retcode[i] = r.retcode;
+      if (stats) stats[i] = r.st;
+      continue;
+    }
     solve_one(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, &sk, &r);
     double cnt = (double)o->n_obs * (double)r.n_saved;
     if (r.n_saved > 0) {

@@ -360,3 +360,48 @@ def test_kencarp4_against_radau_and_conservation(golden):
     from crnn_b200.engine import EngineError  # noqa: F401  (KenCarp4 has no sensitivity path: value only)
     with pytest.raises(RuntimeError):
         oracle.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+
+
+# ---------------------------------------------------------------- interpolating adjoint (BASELINE config 4; not in the reference)
+@pytest.mark.parametrize("name", ["case2", "case3", "case1"])
+def test_adjoint_gradient_matches_forward_mode_and_fd(golden, name):
+    """Continuous adjoint vs the discrete forward-mode gradient: O(tolerance) apart at run tolerances,
+    identical in the limit; and vs central finite differences of a tight solve."""
+    pb = make_problem(name, golden, 3)
+    c = pb["case"]
+    data = np.abs(pb["data"]) + 1e-6 if name == "case3" else pb["data"]
+    args = (pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    # case1's random weights with b0 = -10 give O(1e-3) gradients: the absolute tolerance shows
+    for (at, rt), tol in (((1e-6, 1e-3), 1e-3), ((1e-11, 1e-9), 1e-5 if name == "case1" else 2e-8)):
+        of = c.opts(obs_idx=np.arange(c.ns), abstol=at, reltol=rt)
+        oa = c.opts(obs_idx=np.arange(c.ns), abstol=at, reltol=rt, sens_mode=_abi.SENS_INTERP_ADJOINT)
+        rf = oracle.loss_grad_batch(pb["model"], of, *args)
+        ra = oracle.loss_grad_batch(pb["model"], oa, *args, want_pred=True)
+        np.testing.assert_allclose(ra["loss"], oracle.loss_grad_batch(pb["model"], c.opts(
+            obs_idx=np.arange(c.ns), abstol=at, reltol=rt, err_norm_includes_sens=False), *args)["loss"], rtol=1e-12)
+        assert np.linalg.norm(ra["grad_sum"] - rf["grad_sum"]) / np.linalg.norm(rf["grad_sum"]) < tol
+        # the adjoint's forward pass is the plain value solve
+        val = oracle.solve_batch(pb["model"], of, pb["u0"])
+        assert np.array_equal(ra["stats"]["n_accept"], val["stats"]["n_accept"])
+        np.testing.assert_allclose(ra["pred"], val["pred"], rtol=1e-12, atol=1e-15)
+    if name == "case2":
+        p = np.array(golden["case2"]["p"])
+        ot = c.opts(obs_idx=np.arange(c.ns), abstol=1e-12, reltol=1e-10)
+        L = lambda q: oracle.loss_grad_batch(c.model(q)[0], ot, *args)["loss"].sum()
+        fd = np.array([(L(p + 1e-6 * e) - L(p - 1e-6 * e)) / 2e-6 for e in np.eye(len(p))])
+        assert np.linalg.norm(ra["grad_sum"] - fd) / np.linalg.norm(fd) < 1e-6
+
+
+def test_adjoint_truncation_and_missing_species(golden):
+    pb = make_problem("case2", golden, 4, obs=np.array([0, 1, 3, 4, 5]))
+    nsu = np.array([50, 7, 1, 30], dtype=np.int32)
+    c = pb["case"]
+    oa = c.opts(obs_idx=np.array([0, 1, 3, 4, 5]), sens_mode=_abi.SENS_INTERP_ADJOINT)
+    of = c.opts(obs_idx=np.array([0, 1, 3, 4, 5]))
+    args = (pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    ra = oracle.loss_grad_batch(pb["model"], oa, *args, n_save_used=nsu, want_grad_each=True)
+    rf = oracle.loss_grad_batch(pb["model"], of, *args, n_save_used=nsu, want_grad_each=True)
+    assert np.array_equal(ra["n_saved"], nsu)
+    for i in range(4):
+        gn = np.linalg.norm(rf["grad_each"][i])
+        assert np.linalg.norm(ra["grad_each"][i] - rf["grad_each"][i]) <= 3e-4 * gn + 1e-12

@@ -353,3 +353,52 @@ def test_kencarp4_hychem_sized(engine):
     nsu = np.random.default_rng(1).integers(5, 41, size=256).astype(np.int32)
     g2 = engine.solve_batch(m, o, u0, n_save_used=nsu)
     assert np.array_equal(g2["n_saved"], nsu)
+
+
+# ---------------------------------------------------------------- interpolating adjoint (BASELINE config 4)
+@pytest.mark.parametrize("name,N", [("case2", 192), ("case3", 96), ("case1", 48)])
+def test_adjoint_matches_oracle_and_forward_mode(engine, golden, name, N):
+    pb = make_problem(name, golden, N)
+    c = pb["case"]
+    data = np.abs(pb["data"]) + 1e-6 if name == "case3" else pb["data"]
+    oa = c.opts(obs_idx=np.arange(c.ns), sens_mode=_abi.SENS_INTERP_ADJOINT)
+    args = (pb["model"], oa, pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    amp = name == "case3"                        # rounding-amplifying random weights (see test_tsit5_value)
+    if amp:
+        # ~100 backward segments per trajectory with an accept test each: a last-ulp difference can flip one;
+        # forward counts, retcodes and saves must still match, backward counts for all but a few
+        for k in ("n_accept", "n_reject"):
+            assert np.array_equal(got["stats"][k], ref["stats"][k])
+        assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["n_saved"], ref["n_saved"])
+        assert (got["stats"]["n_jac"] == ref["stats"]["n_jac"]).mean() >= 0.95
+    else:
+        _counts_equal(got, ref)                  # forward steps, backward steps (n_jac), RHS counts, retcodes
+    _states_close(got["pred"], ref["pred"], rtol=1e-5 if amp else RTOL_STATE, scaled=1e-9 if amp else 1e-12)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-7 if amp else RTOL_LOSS)
+    _grad_close(got, ref, rtol=1e-5 if amp else 1e-7)
+    # and the continuous adjoint agrees with the discrete forward-mode gradient to O(tolerance)
+    of = c.opts(obs_idx=np.arange(c.ns))
+    fwd = engine.loss_grad_batch(pb["model"], of, pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    assert np.linalg.norm(got["grad_sum"] - fwd["grad_sum"]) / np.linalg.norm(fwd["grad_sum"]) < 1e-3
+
+
+def test_adjoint_ragged_missing_species_and_device_buffers(engine, golden):
+    import torch
+    obs = np.array([0, 1, 3, 4, 5])
+    pb = make_problem("case2", golden, 130, obs=obs)
+    oa = pb["case"].opts(obs_idx=obs, sens_mode=_abi.SENS_INTERP_ADJOINT)
+    nsu = np.random.default_rng(11).integers(1, 51, size=130).astype(np.int32)
+    args = (pb["model"], oa, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, n_save_used=nsu)
+    ref = oracle.loss_grad_batch(*args, n_save_used=nsu, n_threads=8)
+    _counts_equal(got, ref)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=RTOL_LOSS)
+    _grad_close(got, ref, rtol=1e-7)
+    dev = engine.loss_grad_batch(pb["model"], oa, pb["seed"], torch.from_numpy(pb["u0"]).cuda(),
+                                 torch.from_numpy(pb["data"]).cuda(), pb["yscale"], pb["loss_kind"],
+                                 n_save_used=torch.from_numpy(nsu).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dev["grad_sum"].cpu().numpy(), got["grad_sum"], rtol=1e-11)
+    assert np.array_equal(dev["loss"].cpu().numpy(), got["loss"])
