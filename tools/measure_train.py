@@ -18,14 +18,17 @@ def main():
     eng = Engine(0)
     out = {}
     which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["case2", "robertson", "case3"]
-    for name, N in (("case2", 65536), ("robertson", 262144), ("case3", 131072)):
+    for name, N, mode in (("case2", 65536, "forward"), ("case2", 65536, "adjoint"), ("robertson", 65536, "forward"),
+                          ("case3", 65536, "forward"), ("case3", 65536, "adjoint")):
         if name not in which:
             continue
         c = cases.CASES[name]
         u0 = synth.make_u0(name, N)
         obs = np.arange(c.ns)
         truth = eng.solve_batch(TRUE[name](), c.opts(obs_idx=obs, pred_clamp=(-np.inf, np.inf)), u0, want_stats=False)["pred"]
-        data = np.abs(synth.noisy_targets(truth, 0.05 if name != "robertson" else 1e-4)) + (1e-6 if name == "case3" else 0.0)
+        g = np.random.default_rng(1)
+        noise = 0.05 if name != "robertson" else 1e-4
+        data = np.abs(truth * (1.0 + noise * g.standard_normal(truth.shape, dtype=np.float32))) + (1e-6 if name == "case3" else 0.0)
         ys = synth.yscale_from(data[:4096], c.lb if name != "robertson" else 0.0)
         out_scale = ys / c.tspan[1] if name in ("robertson", "case3") else None
         if name in ("case2", "robertson"):
@@ -33,7 +36,7 @@ def main():
         else:
             g = np.random.default_rng(0); p = (g.random(c.n_p) - 0.5) * 2 * np.sqrt(6 / (c.ns + c.nr)); p[-1] = 0.1
         model, seed = c.model(p, out_scale)
-        opts = c.opts(obs_idx=obs)
+        opts = c.opts(obs_idx=obs, sens_mode=_abi.SENS_INTERP_ADJOINT if mode == "adjoint" else _abi.SENS_FORWARD)
         u0_d = torch.from_numpy(u0).cuda(); data_d = torch.from_numpy(data).cuda()
         for _ in range(2):
             r = eng.loss_grad_batch(model, opts, seed, u0_d, data_d, ys, c.loss_kind)
@@ -46,12 +49,12 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
         st = stats_from_torch(r["stats"])
-        out[name] = {"N": N, "np": int(seed.shape[1]), "ms": ms, "traj_per_s": N / ms * 1e3,
+        out[name + "_" + mode] = {"N": N, "np": int(seed.shape[1]), "ms": ms, "traj_per_s": N / ms * 1e3,
                      "rhs_per_s": float(st["n_rhs"].sum()) / ms * 1e3,
-                     "steps_mean": float((st["n_accept"] + st["n_reject"]).mean()),
+                     "steps_mean": float((st["n_accept"] + st["n_reject"]).mean()), "back_steps_mean": float(st["n_jac"].mean()),
                      "success_frac": float((r["retcode"] == 1).float().mean().item()),
                      "loss_mean": float(torch.nanmean(r["loss"]).item())}
-        print(name, out[name])
+        print(name, mode, out[name + "_" + mode])
     if len(sys.argv) > 1:
         json.dump(out, open(sys.argv[1], "w"), indent=1)
 
