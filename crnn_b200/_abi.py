@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libcrnn_b200.so")
 # enums (include/crnn_b200.h)
 RHS_F0, RHS_F1 = 0, 1
 ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4 = 0, 1, 2
-SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT = 0, 1, 2
+SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT, SENS_DISCRETE_ADJOINT = 0, 1, 2, 3
 LOSS_MAE_SCALED, LOSS_MAE_LOG = 0, 1
 RET_DEFAULT, RET_SUCCESS, RET_DTNAN, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 3, 4, 5, 6
 ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4

@@ -127,6 +127,7 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   P.scale = extra_dev; P.inv_ys = extra_dev + ns;
   const double* seed_dev = extra_dev + ns + n;
   P.nw = nw; P.loss_kind = loss_kind;
+  P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
   constexpr int WARPS = 4;
   auto kern = k_tsit5_adjoint<WARPS>;
   const int stride = 8 * n + 2;
@@ -282,12 +283,13 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
   if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG)
     return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
   if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
-  if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be CRNN_SENS_FORWARD or CRNN_SENS_INTERP_ADJOINT");
+  if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT &&
+      o->sens_mode != CRNN_SENS_DISCRETE_ADJOINT)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be FORWARD, INTERP_ADJOINT or DISCRETE_ADJOINT");
   if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, data, pred, loss, n_saved, retcode, stats};
-  if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT)
+  if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT)
     return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \

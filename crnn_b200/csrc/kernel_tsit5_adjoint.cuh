@@ -45,6 +45,7 @@ struct AdjP {
   double* scratch;         // global overflow record, per warp slot
   int cap_s, cap_g;        // record capacity (steps) in shared / global memory
   int nw, loss_kind;
+  int discrete, pad;       // 1: discrete adjoint (reverse-mode through the recorded steps), 0: interpolating adjoint
 };
 
 constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
@@ -273,7 +274,103 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       return dxi * s;
     };
 
-    if (isave > 0) {
+    // loss term and pred of save column kk (value y_i in this lane); returns this lane's dL/du_i(t_k)
+    auto save_term = [&](int kk, double y) -> double {
+      double gret = 0.0;
+      if (my_obs >= 0) {
+        const double yc = clampd(y, W.pred_lo, W.pred_hi);
+        const bool inside = (y >= W.pred_lo) && (y <= W.pred_hi);
+        const size_t off = pbase + my_obs + (size_t)W.n_obs * kk;
+        if (pred) pred[off] = yc;
+        const double d = __ldg(data + off);
+        double diff, g;
+        if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
+        else { diff = log(clampd(d, W.pred_lo, W.pred_hi)) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+        loss_acc += fabs(diff);
+        if (inside && isp) gret = g / cnt;
+      }
+      return gret;
+    };
+    // GW/GS-style accumulation of the three outer products left in shared memory by adj_rhs
+    auto accum = [&](double* dst, double bw) {
+#pragma unroll
+      for (int q = 0; q < ADJ_MAX_ENT; ++q) {
+        const int code = ent[q];
+        if (code >= 0) {
+          const int kind = code >> 16, i = (code >> 8) & 255, j = code & 255;
+          double val;
+          if (kind == 0) val = s_x[i] * s_gr[j];
+          else if (kind == 1) val = s_gr[j];
+          else val = P.scale[i] * s_lam[i] * s_r[j];
+          dst[lane + 32 * q] = fma(bw, val, dst[lane + 32 * q]);
+        }
+      }
+    };
+
+    if (P.discrete && isave > 0) {
+      // ---- discrete adjoint: reverse-mode through the recorded steps and the dense-output saves ----
+      double ubar = 0.0;
+      int ks = isave - 1;
+#pragma unroll 1
+      for (int st = nrec - 1; st >= 0; --st) {
+        const double* r0 = rec_ptr(st);
+        const double tn = r0[0], h = r0[1];
+        const double tnext = (st + 1 < nrec) ? rec_ptr(st + 1)[0] : t_reached;
+        const double unext = (st + 1 < nrec) ? (lane < n ? rec_ptr(st + 1)[2 + lane] : 0.0) : u;
+        double kbar[7], ubn = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kbar[j] = 0.0;
+        while (ks >= 0) {
+          const double tsv = __ldg(W.saveat + ks);
+          if (!(tsv > tn)) break;
+          if (tsv == tnext) {
+            ubar += save_term(ks, unext);
+          } else {
+            const double g = save_term(ks, dense_u(st, tsv));
+            const double th = (tsv - tn) / h;
+            ubn += g;
+#pragma unroll
+            for (int q7 = 0; q7 < 7; ++q7) {
+              const double b = th * (tsc::R[q7][0] + th * (tsc::R[q7][1] + th * (tsc::R[q7][2] + th * tsc::R[q7][3])));
+              kbar[q7] = fma(h * b, g, kbar[q7]);
+            }
+          }
+          --ks;
+        }
+        double kk[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kk[j] = lane < n ? r0[2 + (1 + j) * n + lane] : 0.0;
+        const double un0 = lane < n ? r0[2 + lane] : 0.0;
+#pragma unroll 1
+        for (int j = 6; j >= 0; --j) {
+          // stage point Y_j = u_n + h sum_{l<j} a_jl k_l  (j = 6: u_{n+1}, whose f is k7 of the dense output)
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < 6; ++l)
+            if (l < j) acc = fma(tsc::A[j][l], kk[l], acc);
+          double kb = 0.0;
+#pragma unroll
+          for (int l = 0; l < 7; ++l)
+            if (l == j) kb = kbar[l];
+          const double vj = adj_rhs(fma(h, acc, un0), kb); ++n_rhs;
+          accum(GW, 1.0);
+          if (j == 6) {
+            ubar += vj;
+#pragma unroll
+            for (int l = 0; l < 6; ++l) kbar[l] = fma(h * tsc::A[6][l], ubar, kbar[l]);
+            ubn += ubar;
+          } else {
+            ubn += vj;
+#pragma unroll
+            for (int l = 0; l < 6; ++l)
+              if (l < j) kbar[l] = fma(h * tsc::A[j][l], vj, kbar[l]);
+          }
+        }
+        ubar = ubn;
+        ++n_back;
+      }
+      while (ks >= 0) { (void)save_term(ks, u_init); --ks; }  // saves at t0: loss only, u0 does not depend on p
+    } else if (isave > 0) {
       for (int ks = isave; ks >= 0; --ks) {
         const double tlo = (ks > 0) ? __ldg(W.saveat + ks - 1) : t0;
         if (ks < isave) {
@@ -311,21 +408,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
 #pragma unroll
               for (int j = 0; j < 7; ++j)
                 if (j == s) K[j] = f;
-              if (s < 6) {  // quadrature: b-weights of the 5th-order solution (b7 = 0)
-                const double bw = tsc::A[6][s];
-#pragma unroll
-                for (int q = 0; q < ADJ_MAX_ENT; ++q) {
-                  const int code = ent[q];
-                  if (code >= 0) {
-                    const int kind = code >> 16, i = (code >> 8) & 255, j = code & 255;
-                    double val;
-                    if (kind == 0) val = s_x[i] * s_gr[j];
-                    else if (kind == 1) val = s_gr[j];
-                    else val = P.scale[i] * s_lam[i] * s_r[j];
-                    GS[lane + 32 * q] = fma(bw, val, GS[lane + 32 * q]);
-                  }
-                }
-              }
+              if (s < 6) accum(GS, tsc::A[6][s]);  // quadrature: b-weights of the 5th-order solution (b7 = 0)
             }
             double e = tsc::BT[0] * K[0];
 #pragma unroll
@@ -358,18 +441,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
           if (tsv <= t0) y = u_init;                                        // t0 itself is saved exactly
           else if (kk == isave - 1 && tsv == t_reached) y = u;              // last save = end state, exactly
           else y = dense_u(jr, tsv);
-          if (my_obs >= 0) {
-            const double yc = clampd(y, W.pred_lo, W.pred_hi);
-            const bool inside = (y >= W.pred_lo) && (y <= W.pred_hi);
-            const size_t off = pbase + my_obs + (size_t)W.n_obs * kk;
-            if (pred) pred[off] = yc;
-            const double d = __ldg(data + off);
-            double diff, g;
-            if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
-            else { diff = log(clampd(d, W.pred_lo, W.pred_hi)) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
-            loss_acc += fabs(diff);
-            if (inside && isp) lam += g / cnt;
-          }
+          lam += save_term(kk, y);
           if (tsv < cur) cur = tsv;
         }
       }

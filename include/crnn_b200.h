@@ -72,7 +72,9 @@ enum crnn_alg {
 enum crnn_sens_mode {
   CRNN_SENS_NONE = 0,
   CRNN_SENS_FORWARD = 1,       /* duals-through-the-solver semantics: case2.jl:195 */
-  CRNN_SENS_INTERP_ADJOINT = 2 /* BASELINE config 4 (not in the reference) */
+  CRNN_SENS_INTERP_ADJOINT = 2, /* BASELINE config 4 (not in the reference): continuous adjoint, jumps at save times */
+  CRNN_SENS_DISCRETE_ADJOINT = 3 /* reverse-mode through the recorded Tsit5 steps + dense output: the forward-mode
+                                    gradient (value-only error norm) at a cost independent of np and n_save */
 };
 
 enum crnn_loss_kind {

@@ -709,7 +709,8 @@ static void adj_rhs(const ctx_t* c, const double* u, const double* lam, double* 
 }
 
 static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, const double* data, const double* yscale,
-                              int loss_kind, double* loss_out, double* gw_out /* nw */, double* pred, traj_result* res) {
+                              int loss_kind, double* loss_out, double* gw_out /* nw */, double* pred, traj_result* res,
+                              int discrete) {
   const crnn_opts* o = c->o;
   const int n = c->n, nw = c->nw;
   const double t0 = o->t0;
@@ -816,7 +817,57 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
   *loss_out = isave > 0 ? lsum / cnt : NAN;
   /* ---------------- backward ---------------- */
   memset(GW, 0, sizeof(double) * nw);
-  if (isave > 0) {
+  if (discrete && isave > 0) {
+    /* Discrete adjoint: reverse-mode differentiation of the recorded Tsit5 steps and of the dense-output
+     * saves, step sizes held constant — exactly the derivative forward-mode duals compute (with the
+     * value-only error norm), at a cost independent of np and of the number of save points. */
+    double* ubar = U; double* ubn = Un; /* adjoint of u_{n+1}, of u_n */
+    double* kbar[7]; for (int q7 = 0; q7 < 7; ++q7) kbar[q7] = K[q7];
+    double* gtmp = (double*)malloc(sizeof(double) * nw);
+    double yy[MAXN], vj[MAXN];
+    memset(ubar, 0, sizeof(double) * n);
+    int ks = isave - 1;
+    for (int st = nrec - 1; st >= 0; --st) {
+      const double* r0 = rec + (size_t)st * 8 * n;
+      const double tn = hdr[st].t, h = hdr[st].dt;
+      const double tnext = (st + 1 < nrec) ? hdr[st + 1].t : t;
+      for (int q7 = 0; q7 < 7; ++q7) memset(kbar[q7], 0, sizeof(double) * n);
+      memset(ubn, 0, sizeof(double) * n);
+      /* saves that belong to this step: tn < ts <= tnext */
+      while (ks >= 0 && o->saveat[ks] > tn) {
+        double ts = o->saveat[ks];
+        const double* g = jump + (size_t)ks * n;
+        if (ts == tnext) { for (int i = 0; i < n; ++i) ubar[i] += g[i]; }
+        else {
+          double th = (ts - tn) / h;
+          for (int i = 0; i < n; ++i) ubn[i] += g[i];
+          for (int q7 = 0; q7 < 7; ++q7) {
+            double b = th * (TS_R[q7][0] + th * (TS_R[q7][1] + th * (TS_R[q7][2] + th * TS_R[q7][3])));
+            for (int i = 0; i < n; ++i) kbar[q7][i] += h * b * g[i];
+          }
+        }
+        --ks;
+      }
+      /* k7 = f(u_{n+1}) enters only the dense output */
+      for (int i = 0; i < n; ++i) { double acc = 0.0; for (int j = 0; j < 6; ++j) acc += TS_A[6][j] * r0[(1 + j) * n + i]; yy[i] = r0[i] + h * acc; }
+      adj_rhs(c, yy, kbar[6], vj, gtmp); res->st.n_rhs++;
+      for (int i = 0; i < n; ++i) ubar[i] += vj[i];
+      for (int w = 0; w < nw; ++w) GW[w] += gtmp[w];
+      /* u_{n+1} = u_n + h sum_j b_j k_j */
+      for (int j = 0; j < 6; ++j) for (int i = 0; i < n; ++i) kbar[j][i] += h * TS_A[6][j] * ubar[i];
+      for (int i = 0; i < n; ++i) ubn[i] += ubar[i];
+      for (int j = 5; j >= 0; --j) {
+        for (int i = 0; i < n; ++i) { double acc = 0.0; for (int l = 0; l < j; ++l) acc += TS_A[j][l] * r0[(1 + l) * n + i]; yy[i] = r0[i] + h * acc; }
+        adj_rhs(c, yy, kbar[j], vj, gtmp); res->st.n_rhs++;
+        for (int w = 0; w < nw; ++w) GW[w] += gtmp[w];
+        for (int i = 0; i < n; ++i) ubn[i] += vj[i];
+        for (int l = 0; l < j; ++l) for (int i = 0; i < n; ++i) kbar[l][i] += h * TS_A[j][l] * vj[i];
+      }
+      memcpy(ubar, ubn, sizeof(double) * n);
+      res->st.n_jac++;
+    }
+    free(gtmp);
+  } else if (isave > 0) {
     double* L = U; double* Ln = Un; /* reuse buffers: lambda, proposed lambda */
     memset(L, 0, sizeof(double) * n);
     double cur = t; /* t_reached */
@@ -941,7 +992,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   int rc = check_dims(m, o);
   if (rc) return rc;
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
-  const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT);
+  const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
@@ -960,7 +1011,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
       double* gw = (double*)malloc(sizeof(double) * c.nw);
       double li = 0.0;
       solve_one_adjoint(&c, u0 + (size_t)m->n_state * i, n_save_used ? n_save_used[i] : 0, data + pstride * i, yscale,
-                        loss_kind, &li, gw, sk.pred, &r);
+                        loss_kind, &li, gw, sk.pred, &r, o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
       loss[i] = li;
       for (int q = 0; q < np; ++q) { /* grad = dW/dp^T vec(G) */
         double sacc = 0.0;

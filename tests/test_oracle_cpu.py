@@ -405,3 +405,26 @@ def test_adjoint_truncation_and_missing_species(golden):
     for i in range(4):
         gn = np.linalg.norm(rf["grad_each"][i])
         assert np.linalg.norm(ra["grad_each"][i] - rf["grad_each"][i]) <= 3e-4 * gn + 1e-12
+
+
+@pytest.mark.parametrize("name", ["case2", "case3", "case1"])
+def test_discrete_adjoint_equals_forward_mode(golden, name):
+    """Reverse-mode through the recorded Tsit5 steps + dense output = the forward-mode (dual) gradient of the
+    same discrete solve (value-only error norm), to rounding; truncation and missing species included."""
+    obs = np.array([0, 1, 3, 4, 5]) if name == "case2" else None
+    pb = make_problem(name, golden, 6, obs=obs)
+    c = pb["case"]
+    oi = np.arange(c.ns) if obs is None else obs
+    data = np.abs(pb["data"]) + 1e-6 if name == "case3" else pb["data"]
+    nsu = np.array([c.n_save, 3, 1, c.n_save // 2, c.n_save, 2], dtype=np.int32)
+    of = c.opts(obs_idx=oi, err_norm_includes_sens=False)
+    od = c.opts(obs_idx=oi, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    args = (pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    rf = oracle.loss_grad_batch(pb["model"], of, *args, n_save_used=nsu, want_grad_each=True, want_pred=True)
+    rd = oracle.loss_grad_batch(pb["model"], od, *args, n_save_used=nsu, want_grad_each=True, want_pred=True)
+    np.testing.assert_allclose(rd["loss"], rf["loss"], rtol=1e-13)
+    np.testing.assert_allclose(rd["pred"], rf["pred"], rtol=1e-13, atol=1e-300)
+    assert np.array_equal(rd["stats"]["n_accept"], rf["stats"]["n_accept"])
+    for i in range(6):
+        gn = np.linalg.norm(rf["grad_each"][i])
+        assert np.linalg.norm(rd["grad_each"][i] - rf["grad_each"][i]) <= 1e-11 * gn + 1e-300

@@ -408,3 +408,31 @@ def test_adjoint_ragged_missing_species_and_device_buffers(engine, golden):
     torch.cuda.synchronize()
     np.testing.assert_allclose(dev["grad_sum"].cpu().numpy(), got["grad_sum"], rtol=1e-11)
     assert np.array_equal(dev["loss"].cpu().numpy(), got["loss"])
+
+
+@pytest.mark.parametrize("name,N", [("case2", 256), ("case3", 128), ("case1", 64)])
+def test_discrete_adjoint_equals_forward_mode_on_gpu(engine, golden, name, N):
+    """CRNN_SENS_DISCRETE_ADJOINT: same gradient as the forward-mode kernel with the value-only error norm
+    (two independent CUDA code paths), and parity with the oracle."""
+    pb = make_problem(name, golden, N)
+    c = pb["case"]
+    data = np.abs(pb["data"]) + 1e-6 if name == "case3" else pb["data"]
+    nsu = np.random.default_rng(5).integers(1, c.n_save + 1, size=N).astype(np.int32)
+    od = c.opts(obs_idx=np.arange(c.ns), sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    of = c.opts(obs_idx=np.arange(c.ns), err_norm_includes_sens=False)
+    args = (pb["seed"], pb["u0"], data, pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(pb["model"], od, *args, n_save_used=nsu, want_pred=True)
+    ref = oracle.loss_grad_batch(pb["model"], od, *args, n_save_used=nsu, want_pred=True, n_threads=8)
+    fwd = engine.loss_grad_batch(pb["model"], of, *args, n_save_used=nsu, want_pred=True)
+    _counts_equal(got, ref)
+    amp = name == "case3"
+    _states_close(got["pred"], ref["pred"], rtol=1e-5 if amp else RTOL_STATE, scaled=1e-9 if amp else 1e-12)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-7 if amp else RTOL_LOSS)
+    _grad_close(got, ref, rtol=1e-5 if amp else 1e-8)
+    assert np.array_equal(got["stats"]["n_accept"], fwd["stats"]["n_accept"])
+    # two different CUDA code paths for the same discrete solve: rounding only (amplified for case3)
+    np.testing.assert_allclose(got["loss"], fwd["loss"], rtol=1e-6 if amp else 1e-11)
+    if amp:
+        assert np.linalg.norm(got["grad_sum"] - fwd["grad_sum"]) / np.linalg.norm(fwd["grad_sum"]) < 1e-5
+    else:
+        _grad_close(got, fwd, rtol=1e-8)

@@ -18,8 +18,9 @@ def main():
     eng = Engine(0)
     out = {}
     which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["case2", "robertson", "case3"]
-    for name, N, mode in (("case2", 65536, "forward"), ("case2", 65536, "adjoint"), ("robertson", 65536, "forward"),
-                          ("case3", 65536, "forward"), ("case3", 65536, "adjoint")):
+    for name, N, mode in (("case2", 65536, "forward"), ("case2", 65536, "adjoint"), ("case2", 65536, "discrete"),
+                          ("robertson", 65536, "forward"), ("case3", 65536, "forward"), ("case3", 65536, "adjoint"),
+                          ("case3", 65536, "discrete")):
         if name not in which:
             continue
         c = cases.CASES[name]
@@ -36,7 +37,7 @@ def main():
         else:
             g = np.random.default_rng(0); p = (g.random(c.n_p) - 0.5) * 2 * np.sqrt(6 / (c.ns + c.nr)); p[-1] = 0.1
         model, seed = c.model(p, out_scale)
-        opts = c.opts(obs_idx=obs, sens_mode=_abi.SENS_INTERP_ADJOINT if mode == "adjoint" else _abi.SENS_FORWARD)
+        opts = c.opts(obs_idx=obs, sens_mode={"adjoint": _abi.SENS_INTERP_ADJOINT, "discrete": _abi.SENS_DISCRETE_ADJOINT, "forward": _abi.SENS_FORWARD}[mode])
         u0_d = torch.from_numpy(u0).cuda(); data_d = torch.from_numpy(data).cuda()
         for _ in range(2):
             r = eng.loss_grad_batch(model, opts, seed, u0_d, data_d, ys, c.loss_kind)
