@@ -205,11 +205,11 @@ void crnn_destroy(crnn_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch};
+  DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch,
+                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
-    DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s], &h->d_loss[s], &h->d_nsaved[s],
-                    &h->d_ret[s], &h->d_stats[s]};
+    DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s]};
     for (DevBuf* b : sb) b->release();
     if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
     if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);

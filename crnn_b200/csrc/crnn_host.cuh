@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -67,8 +68,10 @@ struct crnn_handle {
   // small per-call device state.  ctr: [0] work queue (device mode), [1] reduce ticket, [2+s] queue of slot s
   DevBuf cfg, seed, desc, ctr, partial;
   // staging for the host-buffer path (per pipeline slot) and full-batch gradients
-  DevBuf d_u0[kPipe], d_nsu[kPipe], d_data[kPipe], d_pred[kPipe], d_loss[kPipe], d_nsaved[kPipe], d_ret[kPipe],
-      d_stats[kPipe];
+  DevBuf d_u0[kPipe], d_nsu[kPipe], d_data[kPipe], d_pred[kPipe];
+  // small per-trajectory outputs: full batch on the device, copied back once at the end (a D2H into
+  // pageable host memory blocks the host thread, which would serialise the chunk pipeline)
+  DevBuf d_loss, d_nsaved, d_ret, d_stats;
   DevBuf d_grad_each, d_grad_sum, d_grad_out, adj_scratch;
   // optional kernel timing (crnn_profile_begin/_end)
   bool profiling = false;
@@ -388,17 +391,20 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   if (want_loss && np > 0) CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
   CK(cudaEventRecord(h->ev_cfg, h->s_compute));  // model/option uploads were enqueued on s_compute
   for (int s = 0; s < kPipe; ++s) CK(cudaStreamWaitEvent(h->s_slot[s], h->ev_cfg, 0));
-  const int64_t chunk = std::max<int64_t>(2048, std::min<int64_t>(16384, (N + 7) / 8));
+  int64_t nsplit = 8;  // chunks per call; CRNN_B200_CHUNKS overrides (tuning knob of the host pipeline)
+  if (const char* e = std::getenv("CRNN_B200_CHUNKS")) nsplit = std::max(1, std::atoi(e));
+  const int64_t chunk = std::max<int64_t>(2048, (N + nsplit - 1) / nsplit);
   const int64_t nchunk = (N + chunk - 1) / chunk;
   for (int s = 0; s < kPipe; ++s) {
     CK(h->d_u0[s].reserve(chunk * ns * sizeof(double)));
     if (io.nsu) CK(h->d_nsu[s].reserve(chunk * sizeof(int)));
-    if (want_loss) { CK(h->d_data[s].reserve(std::max<size_t>(8, chunk * ps * sizeof(double)))); CK(h->d_loss[s].reserve(chunk * sizeof(double))); }
+    if (want_loss) CK(h->d_data[s].reserve(std::max<size_t>(8, chunk * ps * sizeof(double))));
     if (io.pred) CK(h->d_pred[s].reserve(std::max<size_t>(8, chunk * ps * sizeof(double))));
-    CK(h->d_nsaved[s].reserve(chunk * sizeof(int)));
-    CK(h->d_ret[s].reserve(chunk * sizeof(int)));
-    if (io.stats) CK(h->d_stats[s].reserve(chunk * sizeof(crnn_stats)));
   }
+  if (want_loss) CK(h->d_loss.reserve(std::max<size_t>(8, N * sizeof(double))));
+  CK(h->d_nsaved.reserve(std::max<size_t>(8, N * sizeof(int))));
+  CK(h->d_ret.reserve(std::max<size_t>(8, N * sizeof(int))));
+  if (io.stats) CK(h->d_stats.reserve(std::max<size_t>(8, N * sizeof(crnn_stats))));
   for (int64_t c = 0; c < nchunk; ++c) {
     const int s = (int)(c % kPipe);
     const int64_t lo = c * chunk, n = std::min<int64_t>(chunk, N - lo);
@@ -414,19 +420,16 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
     if (c >= kPipe) CK(cudaStreamWaitEvent(sc, h->ev_out[s], 0));
     BatchPtrs b{h->d_u0[s].as<double>(), io.nsu ? h->d_nsu[s].as<int>() : nullptr,
                 want_loss ? h->d_data[s].as<double>() : nullptr, io.pred ? h->d_pred[s].as<double>() : nullptr,
-                want_loss ? h->d_loss[s].as<double>() : nullptr, h->d_nsaved[s].as<int>(), h->d_ret[s].as<int>(),
-                io.stats ? h->d_stats[s].as<crnn_stats>() : nullptr,
+                want_loss ? h->d_loss.as<double>() + lo : nullptr, h->d_nsaved.as<int>() + lo, h->d_ret.as<int>() + lo,
+                io.stats ? h->d_stats.as<crnn_stats>() + lo : nullptr,
                 (want_loss && np > 0) ? h->d_grad_each.as<double>() + (size_t)lo * np : nullptr, n, 2 + s};
     int rc = launch(b, sc);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev_done[s], sc));
-    // D2H of this chunk's results on its own stream (a second copy engine)
+    // D2H of this chunk's saved states on its own stream (a second copy engine; asynchronous when
+    // the caller's buffer is pinned)
     CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[s], 0));
     if (io.pred && ps) CK(cudaMemcpyAsync(io.pred + lo * ps, h->d_pred[s].p, n * ps * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
-    if (want_loss && io.loss) CK(cudaMemcpyAsync(io.loss + lo, h->d_loss[s].p, n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
-    if (io.n_saved) CK(cudaMemcpyAsync(io.n_saved + lo, h->d_nsaved[s].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
-    if (io.retcode) CK(cudaMemcpyAsync(io.retcode + lo, h->d_ret[s].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
-    if (io.stats) CK(cudaMemcpyAsync(io.stats + lo, h->d_stats[s].p, n * sizeof(crnn_stats), cudaMemcpyDeviceToHost, h->s_d2h));
     CK(cudaEventRecord(h->ev_out[s], h->s_d2h));
   }
   for (int s = 0; s < kPipe && s < nchunk; ++s) CK(cudaStreamWaitEvent(h->s_compute, h->ev_done[s], 0));
@@ -446,6 +449,13 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
       }
       CK(cudaMemcpyAsync(grad_sum, src, nout * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
     }
+  }
+  // small outputs: one copy each, after every chunk's kernel (s_compute has waited on them above)
+  if (N > 0) {
+    if (want_loss && io.loss) CK(cudaMemcpyAsync(io.loss, h->d_loss.p, N * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
+    if (io.n_saved) CK(cudaMemcpyAsync(io.n_saved, h->d_nsaved.p, N * sizeof(int), cudaMemcpyDeviceToHost, h->s_compute));
+    if (io.retcode) CK(cudaMemcpyAsync(io.retcode, h->d_ret.p, N * sizeof(int), cudaMemcpyDeviceToHost, h->s_compute));
+    if (io.stats) CK(cudaMemcpyAsync(io.stats, h->d_stats.p, N * sizeof(crnn_stats), cudaMemcpyDeviceToHost, h->s_compute));
   }
   CK(cudaStreamSynchronize(h->s_h2d));
   CK(cudaStreamSynchronize(h->s_d2h));
