@@ -76,6 +76,7 @@ struct alignas(16) WarpBuf {
   double g[C::N];
   double b[8];                // dense-output weights b_j(theta)
   double term[2][C::N];
+  double rp[C::NS][8];        // partial row sums (RP lanes share one row of `red`)
   double part[8][C::N];       // WPT > 1: per-warp partial row sums of the trajectory's warp group
   long long trajslot;         // WPT > 1: trajectory index broadcast
   int flag, pad;              // WPT > 1: NaN flag of the group
@@ -96,7 +97,11 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
   static_assert(WPT >= 1 && WPT <= 8 && WARPS % WPT == 0 && (WPT == 1 || CT == 1), "bad warp grouping");
   SensSmem<C, CT, R1, WPT>& sm = *reinterpret_cast<SensSmem<C, CT, R1, WPT>*>(smem_raw);
   WarpBuf<C, CT>* wbs = reinterpret_cast<WarpBuf<C, CT>*>(smem_raw + sizeof(SensSmem<C, CT, R1, WPT>));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // volatile: keeps lane/warp in registers (the compiler otherwise re-derives them from %tid all over the loop)
+  unsigned lane_u, tid_u;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_u));
+  const int lane = (int)lane_u, warp = (int)(tid_u >> 5);
   const int wig = warp % WPT, grp = warp / WPT;  // warp in group, group in block
   WarpBuf<C, CT>& wb = wbs[warp];        // own: K, red
   WarpBuf<C, CT>& gb = wbs[warp - wig];  // group leader's: broadcast arrays
@@ -344,10 +349,20 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               wb.red[i][lane] = sa;
             }
             __syncwarp();
+            // RP lanes share a row: partial sums of 32/RP skewed (conflict-free) columns, then lane i adds them
+            constexpr int RP = NS <= 4 ? 8 : (NS <= 8 ? 4 : (NS <= 16 ? 2 : 1)), SEG = 32 / RP;
+            if (lane < NS * RP) {
+              const int row = lane / RP, part = lane % RP;
+              double ps = 0.0;
+#pragma unroll
+              for (int k = 0; k < SEG; ++k) ps += wb.red[row][(part * SEG + k + row) & 31];
+              wb.rp[row][part] = ps;
+            }
+            __syncwarp();
             double tot = 0.0;
             if (lane < NS) {
-#pragma unroll 8
-              for (int k = 0; k < 32; ++k) tot += wb.red[lane][(k + lane) & 31];  // skewed: conflict-free
+#pragma unroll
+              for (int p = 0; p < RP; ++p) tot += wb.rp[lane][p];
               if (WPT > 1) gb.part[wig][lane] = tot;
             }
             if (WPT > 1) {  // combine the group's per-warp partial sums (same order in every warp)
@@ -436,29 +451,17 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
 #pragma unroll
               for (int i = 0; i < NS; ++i) KO[tt][i] = Y[tt][i];
           } else {
-            const double th = (tsv - tprev) / dt;
-            gsync();
-            if (wig == 0 && lane < 7)
-              gb.b[lane] = th * (sm.dense_r[lane][0] + th * (sm.dense_r[lane][1] +
-                                 th * (sm.dense_r[lane][2] + th * sm.dense_r[lane][3])));
-            gsync();
+            double b[7];
+            ts::dense_b((tsv - tprev) / dt, b);  // every lane evaluates the seven weights itself: no barrier
+            const int k7s = 6 - k1s;
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
-              for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < 7; ++j) {
-              const double bj = gb.b[j];
-              const int slot = (j == 0) ? k1s : (j == 6 ? 6 - k1s : j);
-#pragma unroll
-              for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(bj, wb.K[slot][tt][i][lane], KO[tt][i]);
-            }
-#pragma unroll
-            for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-              for (int i = 0; i < NS; ++i) KO[tt][i] = fma(dt, KO[tt][i], U[tt][i]);
+              for (int i = 0; i < NS; ++i)
+                KO[tt][i] = fma(dt, fma(b[6], wb.K[k7s][tt][i][lane], fma(b[5], wb.K[5][tt][i][lane],
+                                fma(b[4], wb.K[4][tt][i][lane], fma(b[3], wb.K[3][tt][i][lane],
+                                fma(b[2], wb.K[2][tt][i][lane], fma(b[1], wb.K[1][tt][i][lane],
+                                    b[0] * wb.K[k1s][tt][i][lane])))))), U[tt][i]);
           }
           if (isval[0]) {
 #pragma unroll
