@@ -66,7 +66,7 @@ assert STATS_DTYPE.itemsize == C.sizeof(CStats) == 32
 # every symbol include/crnn_b200.h declares
 EXPORTS = (
     "crnn_create", "crnn_destroy", "crnn_last_error", "crnn_version", "crnn_launch_count",
-    "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end",
+    "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end", "crnn_copy_grad_each",
 )
 
 _lib = None
@@ -97,6 +97,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crnn_profile_begin.restype = C.c_int
     lib.crnn_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.crnn_profile_end.restype = C.c_int
+    lib.crnn_copy_grad_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.crnn_copy_grad_each.restype = C.c_int
     lib.crnn_solve_batch.argtypes = [
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -228,6 +228,18 @@ const char* crnn_last_error(const crnn_handle* h) { return h ? h->err.c_str() : 
 
 int64_t crnn_launch_count(const crnn_handle* h) { return h ? h->launches : 0; }
 
+int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int32_t on_device, void* stream) {
+  if (!h || !dst || N < 0 || np <= 0) return CRNN_ERR_BAD_ARG;
+  const size_t bytes = (size_t)N * np * sizeof(double);
+  if (h->last_grad_np != np || h->last_grad_n != N || h->d_grad_each.cap < bytes)
+    return fail(h, CRNN_ERR_BAD_ARG, "no forward-mode gradients of that shape from the last call");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = on_device ? (cudaStream_t)stream : h->s_compute;
+  CK(cudaMemcpyAsync(dst, h->d_grad_each.p, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!on_device) CK(cudaStreamSynchronize(st));
+  return CRNN_OK;
+}
+
 int crnn_profile_begin(crnn_handle* h) {
   if (!h) return CRNN_ERR_BAD_ARG;
   h->profiling = true;
@@ -289,8 +301,10 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
   if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, data, pred, loss, n_saved, retcode, stats};
+  h->last_grad_np = -1; h->last_grad_n = -1;
   if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT)
     return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+  h->last_grad_np = np; h->last_grad_n = N;
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);

@@ -62,6 +62,8 @@ struct crnn_handle {
   int num_sms = 0;
   std::string err;
   int64_t launches = 0;
+  int64_t last_grad_n = -1;  // shape of the per-trajectory gradients left in d_grad_each (crnn_copy_grad_each)
+  int last_grad_np = -1;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaStream_t s_slot[kPipe] = {};  // one compute stream per pipeline slot: chunk c+1 fills the SMs chunk c's tail leaves idle
   cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {}, ev_out[kPipe] = {}, ev_cfg = nullptr;

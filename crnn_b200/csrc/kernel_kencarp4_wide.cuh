@@ -91,7 +91,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
     dxi = 0.0;
     if (isp) {
       const double uc = clampd(y, P.lb, P.ub);
-      xi = log(uc);
+      xi = lean_log(uc);
       dxi = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
     } else if (P.kind == 1 && lane == ns) {
       xi = -1.0 / (P.gas_R * y);
@@ -101,7 +101,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
     if (lane < nr) {
       double z = sb.w_b[lane];
       for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
-      ww.r[lane] = exp(z);
+      ww.r[lane] = lean_exp(z);
     }
     __syncwarp();
     double f = 0.0;
@@ -286,8 +286,8 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
       double q11, q;
       if (EEst == 0.0) { q11 = 0.0; q = P.inv_qmax; }
       else {
-        q11 = pow(EEst, P.beta1);
-        q = jmax(P.inv_qmax, jmin(P.inv_qmin, q11 / pow(qold, P.beta2) / P.gamma));
+        q11 = lean_pow(EEst, P.beta1);
+        q = jmax(P.inv_qmax, jmin(P.inv_qmin, q11 / lean_pow(qold, P.beta2) / P.gamma));
       }
       if (EEst <= 1.0) {
         ++n_acc;

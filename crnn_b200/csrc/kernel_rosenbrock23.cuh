@@ -20,7 +20,7 @@ __device__ __forceinline__ void rhs_value_full(const ModelP<C>& mp, const double
 #pragma unroll
   for (int i = 0; i < C::NS; ++i) {
     const double uc = clampd(u[i], mp.lb, mp.ub);
-    x[i] = log(uc);
+    x[i] = lean_log(uc);
     dx[i] = (u[i] >= mp.lb && u[i] <= mp.ub) ? 1.0 / uc : 0.0;
   }
 #pragma unroll
@@ -28,7 +28,7 @@ __device__ __forceinline__ void rhs_value_full(const ModelP<C>& mp, const double
     double z = bT[j];
 #pragma unroll
     for (int i = 0; i < C::NS; ++i) z = fma(mp.w_in[i + C::NIN * j], x[i], z);
-    r[j] = exp(z);
+    r[j] = lean_exp(z);
   }
 #pragma unroll
   for (int i = 0; i < C::NS; ++i) {

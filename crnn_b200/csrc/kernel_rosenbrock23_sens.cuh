@@ -139,7 +139,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
           const double yi = wb.y[lane];
           const double uc = clampd(yi, mp.lb, mp.ub);
           const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
-          wb.x[lane] = log(uc);
+          wb.x[lane] = lean_log(uc);
           wb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
         __syncwarp();
@@ -147,7 +147,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
           double z = mybT;
 #pragma unroll
           for (int i = 0; i < NS; ++i) z = fma(sm.w_in[i + NIN * lane], wb.x[i], z);
-          wb.r[lane] = exp(z);
+          wb.r[lane] = lean_exp(z);
         }
         __syncwarp();
         {

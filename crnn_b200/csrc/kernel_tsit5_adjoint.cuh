@@ -102,14 +102,14 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   auto rhs = [&](double y) -> double {
     __syncwarp();
     double xi = 0.0;
-    if (isp) xi = log(clampd(y, W.lb, W.ub));
+    if (isp) xi = lean_log(clampd(y, W.lb, W.ub));
     else if (W.kind == 1 && lane == ns) xi = -1.0 / (W.gas_R * y);
     s_x[lane] = xi;
     __syncwarp();
     if (lane < nr) {
       double z = sb.w_b[lane];
       for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
-      s_r[lane] = exp(z);
+      s_r[lane] = lean_exp(z);
     }
     __syncwarp();
     double f = 0.0;
@@ -207,7 +207,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       const double EEst = wrms(dt * e, u, un);
       double q11, q;
       if (EEst == 0.0) { q11 = 0.0; q = W.inv_qmax; }
-      else { q11 = pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / pow(qold, W.beta2) / W.gamma)); }
+      else { q11 = lean_pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / lean_pow(qold, W.beta2) / W.gamma)); }
       dt_last = dt;
       if (EEst <= 1.0) {
         ++n_acc;
@@ -251,7 +251,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       double xi = 0.0, dxi = 0.0;
       if (isp) {
         const double uc = clampd(ui, W.lb, W.ub);
-        xi = log(uc);
+        xi = lean_log(uc);
         dxi = (ui >= W.lb && ui <= W.ub) ? __drcp_rn(uc) : 0.0;
       } else if (W.kind == 1 && lane == ns) {
         xi = -1.0 / (W.gas_R * ui);
@@ -263,7 +263,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         double z = sb.w_b[lane], gs = 0.0;
         for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
         for (int i = 0; i < ns; ++i) gs = fma(sb.w_out[lane][i], s_lam[i], gs);
-        const double r = exp(z);
+        const double r = lean_exp(z);
         s_r[lane] = r;
         s_gr[lane] = gs * r;
       }
@@ -416,7 +416,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
             const double EEst = wrms(h * e, lam, ln);
             double q11, q;
             if (EEst == 0.0) { q11 = 0.0; q = W.inv_qmax; }
-            else { q11 = pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / pow(bq, W.beta2) / W.gamma)); }
+            else { q11 = lean_pow(EEst, W.beta1); q = jmax(W.inv_qmax, jmin(W.inv_qmin, q11 / lean_pow(bq, W.beta2) / W.gamma)); }
             if (EEst <= 1.0) {
               bq = jmax(EEst, 1e-4);
               for (int ee = lane; ee < nw; ee += 32) GW[ee] = fma(h, GS[ee], GW[ee]);

@@ -238,7 +238,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           const double yi = gb.y[lane];
           const double uc = clampd(yi, mp.lb, mp.ub);
           const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
-          gb.x[lane] = log(uc);
+          gb.x[lane] = lean_log(uc);
           gb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
         gsync();
@@ -246,7 +246,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           double z = mybT;
 #pragma unroll
           for (int i = 0; i < NS; ++i) z = fma(sm.w_in[i + NIN * lane], gb.x[i], z);
-          gb.r[lane] = exp(z);
+          gb.r[lane] = lean_exp(z);
         }
         gsync();
         {

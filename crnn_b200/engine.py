@@ -64,6 +64,13 @@ class Engine:
         self._check(self._lib.crnn_profile_end(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def grad_each(self, N: int, n_p: int) -> np.ndarray:
+        """[N, np] per-trajectory gradients d loss_i / d p of the last forward-mode loss_grad_batch call
+        (rober_crnn_lm.jl:216-218 takes the Jacobian of the per-experiment losses)."""
+        out = np.empty((N, n_p))
+        self._check(self._lib.crnn_copy_grad_each(self._h, out.ctypes.data_as(C.c_void_p), N, n_p, 0, None))
+        return out
+
     def _check(self, rc: int):
         if rc != 0:
             raise EngineError(f"crnn_b200 error {rc}: {self._lib.crnn_last_error(self._h).decode()}")

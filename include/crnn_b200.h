@@ -177,6 +177,12 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
                          double* loss, double* grad_sum, double* pred,
                          int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
 
+/* Per-trajectory gradients of the LAST crnn_loss_grad_batch call made with CRNN_SENS_FORWARD:
+ * dst[np, N] (column-major: np fastest) <- d loss_i / d p.  What robertson/rober_crnn_lm.jl's
+ * Levenberg-Marquardt variant needs (ForwardDiff.jacobian of the per-experiment losses, :216-218).
+ * dst is host memory (on_device = 0) or device memory (on_device = 1, copied on `stream`). */
+int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int32_t on_device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

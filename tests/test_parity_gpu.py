@@ -436,3 +436,14 @@ def test_discrete_adjoint_equals_forward_mode_on_gpu(engine, golden, name, N):
         assert np.linalg.norm(got["grad_sum"] - fwd["grad_sum"]) / np.linalg.norm(fwd["grad_sum"]) < 1e-5
     else:
         _grad_close(got, fwd, rtol=1e-8)
+
+
+def test_per_trajectory_gradients(engine, golden):
+    """crnn_copy_grad_each: the per-experiment gradients robertson/rober_crnn_lm.jl's LM variant needs."""
+    pb = make_problem("case2", golden, 50)
+    args = (pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args)
+    ge = engine.grad_each(50, pb["seed"].shape[1])
+    ref = oracle.loss_grad_batch(*args, want_grad_each=True, n_threads=4)
+    np.testing.assert_allclose(ge, ref["grad_each"], rtol=1e-7, atol=1e-10 * np.abs(ref["grad_each"]).max())
+    np.testing.assert_allclose(ge.sum(axis=0), got["grad_sum"], rtol=1e-11)
