@@ -66,15 +66,14 @@ constexpr double r42 = -12.411077166933676, r43 = 30.33818863028232, r44 = -16.5
 constexpr double r52 = 37.50931341651104, r53 = -88.1789048947664, r54 = 47.37952196281928;
 constexpr double r62 = -27.896526289197286, r63 = 65.09189467479366, r64 = -34.87065786149661;
 constexpr double r72 = 1.5, r73 = -4.0, r74 = 2.5;
+// coefficients read from constant memory: as literals each one costs two register moves per use
+__constant__ double c_dense[22] = {r11, r12, r13, r14, r22, r23, r24, r32, r33, r34, r42, r43, r44,
+                                   r52, r53, r54, r62, r63, r64, r72, r73, r74};
 __device__ __forceinline__ void dense_b(double th, double (&b)[7]) {
-  b[0] = th * (r11 + th * (r12 + th * (r13 + th * r14)));
-  double t2 = th * th;
-  b[1] = t2 * (r22 + th * (r23 + th * r24));
-  b[2] = t2 * (r32 + th * (r33 + th * r34));
-  b[3] = t2 * (r42 + th * (r43 + th * r44));
-  b[4] = t2 * (r52 + th * (r53 + th * r54));
-  b[5] = t2 * (r62 + th * (r63 + th * r64));
-  b[6] = t2 * (r72 + th * (r73 + th * r74));
+  b[0] = th * (c_dense[0] + th * (c_dense[1] + th * (c_dense[2] + th * c_dense[3])));
+  const double t2 = th * th;
+#pragma unroll
+  for (int j = 1; j < 7; ++j) b[j] = t2 * (c_dense[1 + 3 * j] + th * (c_dense[2 + 3 * j] + th * c_dense[3 + 3 * j]));
 }
 }  // namespace ts
 

@@ -63,8 +63,10 @@ struct alignas(16) SensSmem {
   int row2obs[C::N];
 };
 
-// Per-warp working set.  K holds the seven stage derivatives of every column: lane l owns
-// K[slot][tile][i][l], so all accesses are conflict-free 256 B rows.
+// Per-warp working set.  K holds the seven stage derivatives of every column.  Inside a
+// (slot, tile) block the components of lane l are stored as lane-interleaved PAIRS -
+// (2p, 2p+1) at double2 index p*32 + l, an odd last component as a plain row - so one
+// LDS.128 / STS.128 moves two components (kload / kstore below), conflict-free.
 template <class C, int CT>
 struct alignas(16) WarpBuf {
   double K[7][CT][C::NS][32];
@@ -77,6 +79,7 @@ struct alignas(16) WarpBuf {
   double b[8];                // dense-output weights b_j(theta)
   double term[2][C::N];
   double rp[C::NS][8];        // partial row sums (RP lanes share one row of `red`)
+  double cold[4];             // rarely-read scalars kept out of registers: tend, dtmax, dtmin, dt of the last attempt
   double part[8][C::N];       // WPT > 1: per-warp partial row sums of the trajectory's warp group
   long long trajslot;         // WPT > 1: trajectory index broadcast
   int flag, pad;              // WPT > 1: NaN flag of the group
@@ -105,6 +108,21 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
   const int wig = warp % WPT, grp = warp / WPT;  // warp in group, group in block
   WarpBuf<C, CT>& wb = wbs[warp];        // own: K, red
   WarpBuf<C, CT>& gb = wbs[warp - wig];  // group leader's: broadcast arrays
+  auto kload = [&](int slot, int tt, double (&v)[NS]) {
+    const double* base = &wb.K[slot][tt][0][0];
+#pragma unroll
+    for (int p = 0; p < NS / 2; ++p) {
+      const double2 w = reinterpret_cast<const double2*>(base)[p * 32 + lane];
+      v[2 * p] = w.x; v[2 * p + 1] = w.y;
+    }
+    if (NS & 1) v[NS - 1] = base[(NS - 1) * 32 + lane];
+  };
+  auto kstore = [&](int slot, int tt, const double (&v)[NS]) {
+    double* base = &wb.K[slot][tt][0][0];
+#pragma unroll
+    for (int p = 0; p < NS / 2; ++p) reinterpret_cast<double2*>(base)[p * 32 + lane] = make_double2(v[2 * p], v[2 * p + 1]);
+    if (NS & 1) base[(NS - 1) * 32 + lane] = v[NS - 1];
+  };
   auto gsync = [&]() {
     if (WPT == 1) __syncwarp();
     else if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPT * 32) : "memory");  // immediate ids: a register id
@@ -168,7 +186,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // U: state; Y: stage state (holds the proposed u_{n+1} from stage 6 through the save phase);
     // KO: RHS output / scratch
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
-    double Tval = 0.0, xT = 0.0, mybT = 0.0, my_sk = 1.0, my_u0 = 0.0;
+    double Tval = 0.0, xT = 0.0, mybT = 0.0;
     if (C::KIND == 1) { Tval = __ldg(u0 + traj * N + NS); xT = -1.0 / (mp.gas_R * Tval); }
     if (lane < NR) {
       mybT = sm.w_b[lane];
@@ -179,48 +197,65 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     for (int t = 0; t < CT; ++t)
 #pragma unroll
       for (int i = 0; i < NS; ++i) U[t][i] = isval[t] ? __ldg(u0 + traj * N + i) : 0.0;
-    if (lane < NS) {
-      my_u0 = __ldg(u0 + traj * N + lane);
-      my_sk = my_at + fabs(my_u0) * my_rt;
-    }
 
     int nsave = sp.n_save;
-    double tend = sp.t1;
-    if (n_save_used) {
-      int q = __ldg(n_save_used + traj);
-      if (q > 0 && q <= sp.n_save) { nsave = q; tend = __ldg(sp.saveat + q - 1); }
+    const double t0 = sp.t0;
+    {
+      double tend = sp.t1;
+      if (n_save_used) {
+        int q = __ldg(n_save_used + traj);
+        if (q > 0 && q <= sp.n_save) { nsave = q; tend = __ldg(sp.saveat + q - 1); }
+      }
+      if (lane == 0) { wb.cold[0] = tend; wb.cold[1] = tend - t0; wb.cold[2] = fmax(ulp_of(t0), ulp_of(tend)); wb.cold[3] = 0.0; }
+      __syncwarp();
     }
-    const double t0 = sp.t0, dtmax = tend - t0;
-    const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
     const size_t pbase = (size_t)traj * sp.n_obs * sp.n_save;
 
-    int n_rhs = 0, n_acc = 0, n_rej = 0;
+    int n_acc = 0, n_rej = 0;  // RHS evaluations = 2 + 6 * attempts, loop iterations = attempts (derived, not counted)
     double G[CT], loss_acc = 0.0;
 #pragma unroll
     for (int t = 0; t < CT; ++t) G[t] = 0.0;
-    double asum = my_u0 * my_u0, bsum = 0.0;  // lane i < NS: dual magnitude^2 of u_i at t_n / t_{n+1}
-    double t = t0, tprev = t0, dt = 0.0, dt0 = 0.0, d1 = 0.0, dtnew = 0.0, qold = 1e-4, dt_last = 0.0;
+    double asum = 0.0, bsum = 0.0;  // lane i < NS: dual magnitude^2 of u_i at t_n / t_{n+1}
+    if (lane < NS) { const double v = __ldg(u0 + traj * N + lane); asum = v * v; }
+    // during the two initial-step phases dt holds dt0 and dtnew holds d1 (both are free until the first step)
+    double t = t0, tprev = t0, dt = 0.0, dtnew = 0.0, qold = 1e-4;
     int isave = 0, ret = CRNN_RET_DEFAULT, phase = PH_F0, k1s = 0;  // k1s: slot of K1 (0 or 6), K7 in 6-k1s
-    long long iter = 0;
+    // the next save time and this lane's next target are fetched one save ahead: their global-load
+    // latency then overlaps the step in between instead of stalling the save phase
+    const int my_q = (wig == 0 && lane < N) ? sm.row2obs[lane] : -1;
+    double ts_next = __ldg(sp.saveat), d_next = 0.0;
+    if (my_q >= 0) d_next = __ldg(data + pbase + my_q);
 
     while (true) {
       if (phase != PH_SAVE) {
         // ---- stage state Y = U + h * sum_{j<nj} A[phase][j] K_j ----
         {
           const int nj = (phase == PH_F1) ? 1 : phase;
-          const double h = (phase == PH_F1) ? dt0 : dt;
+          const double h = dt;
+          double kv[NS];
+          if (nj > 0) {  // j = 0 reads K1 from its FSAL slot; the rest are slots 1..nj-1
+            const double a0 = c_tsA[phase][0];
 #pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
+            for (int tt = 0; tt < CT; ++tt) {
+              kload(k1s, tt, kv);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
-#pragma unroll 1
-          for (int j = 0; j < nj; ++j) {
-            const double a = c_tsA[phase][j];
-            const int slot = (j == 0) ? k1s : j;
+              for (int i = 0; i < NS; ++i) KO[tt][i] = a0 * kv[i];
+            }
+#pragma unroll 2
+            for (int j = 1; j < nj; ++j) {
+              const double a = c_tsA[phase][j];
+#pragma unroll
+              for (int tt = 0; tt < CT; ++tt) {
+                kload(j, tt, kv);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, kv[i], KO[tt][i]);
+              }
+            }
+          } else {
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
-              for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, wb.K[slot][tt][i][lane], KO[tt][i]);
+              for (int i = 0; i < NS; ++i) KO[tt][i] = 0.0;
           }
 #pragma unroll
           for (int tt = 0; tt < CT; ++tt)
@@ -291,16 +326,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             }
           }
         }
-        ++n_rhs;
 
         // ---- store KO into its stage slot ----
         {
           // F0 -> K1 ; F1 -> slot 1 (scratch, free until stage 1 writes K2) ; stage s -> K_{s+1}
           const int dst = (phase == PH_F0) ? k1s : (phase == PH_F1) ? 1 : (phase == 6 ? 6 - k1s : phase);
 #pragma unroll
-          for (int tt = 0; tt < CT; ++tt)
-#pragma unroll
-            for (int i = 0; i < NS; ++i) wb.K[dst][tt][i][lane] = KO[tt][i];
+          for (int tt = 0; tt < CT; ++tt) kstore(dst, tt, KO[tt]);
         }
 
         if (phase >= 1 && phase < 6) {
@@ -309,9 +341,12 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           // ---- phases that need a norm: F0 (|f0|), F1 (|f1 - f0|), stage 6 (error estimate) ----
           if (phase == PH_F1) {
 #pragma unroll
-            for (int tt = 0; tt < CT; ++tt)
+            for (int tt = 0; tt < CT; ++tt) {
+              double kv[NS];
+              kload(k1s, tt, kv);
 #pragma unroll
-              for (int i = 0; i < NS; ++i) KO[tt][i] -= wb.K[k1s][tt][i][lane];
+              for (int i = 0; i < NS; ++i) KO[tt][i] -= kv[i];
+            }
           } else if (phase == 6) {
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
@@ -322,9 +357,12 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const double a = c_tsBT[j];
               const int slot = (j == 0) ? k1s : j;
 #pragma unroll
-              for (int tt = 0; tt < CT; ++tt)
+              for (int tt = 0; tt < CT; ++tt) {
+                double kv[NS];
+                kload(slot, tt, kv);
 #pragma unroll
-                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, wb.K[slot][tt][i][lane], KO[tt][i]);
+                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(a, kv[i], KO[tt][i]);
+              }
             }
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt)
@@ -383,6 +421,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const double sc = fma(sqrt(fmax(asum, bsum)), my_rt, my_at);
               term0 = rsum / (sc * sc);
             } else {
+              const double my_u0 = __ldg(u0 + traj * N + lane), my_sk = my_at + fabs(my_u0) * my_rt;
               const double a = my_u0 / my_sk;
               term0 = rsum / (my_sk * my_sk);
               term1 = a * a;
@@ -398,25 +437,28 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             // initial step size, part 1 (ode_determine_initdt)
             if (C::KIND == 1) { const double a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]); s1 = fma(a, a, s1); }
             const double d0 = sqrt(s1 / N);
-            d1 = sqrt(s0 / N);
-            dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-            dt0 = jmin(dt0, dtmax);
+            const double d1 = sqrt(s0 / N);
+            const double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            dt = jmin(dt0, wb.cold[1]);
+            dtnew = d1;
             phase = PH_F1;
           } else if (phase == PH_F1) {
             // initial step size, part 2; then the pseudo-step that saves t0
+            const double dt0 = dt, d1 = dtnew;
             const double d2 = sqrt(s0 / N) / dt0;
             const double dm = jmax(d1, d2);
             const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
-            dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
+            dt = jmin(jmin(100.0 * dt0, dt1), wb.cold[1]);
             dtnew = dt;
             // pseudo-step: proposed state = U, K7 = K1, so the commit below is a no-op
 #pragma unroll
-            for (int tt = 0; tt < CT; ++tt)
+            for (int tt = 0; tt < CT; ++tt) {
+              double kv[NS];
+              kload(k1s, tt, kv);
+              kstore(6 - k1s, tt, kv);
 #pragma unroll
-              for (int i = 0; i < NS; ++i) {
-                Y[tt][i] = U[tt][i];
-                wb.K[6 - k1s][tt][i][lane] = wb.K[k1s][tt][i][lane];
-              }
+              for (int i = 0; i < NS; ++i) Y[tt][i] = U[tt][i];
+            }
             bsum = asum;
             phase = PH_SAVE;
           } else {
@@ -424,13 +466,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             const double EEst = sqrt(s0 / N);
             double q11;
             const double q = pi_controller<C>(sp, EEst, qold, q11);
-            dt_last = dt;
+            if (isval[0]) wb.cold[3] = dt;
             if (EEst <= 1.0) {
               ++n_acc;
               qold = jmax(EEst, 1e-4);
               dtnew = dt / q;
               tprev = t;
-              t = snap_t(t + dt, tend);
+              t = snap_t(t + dt, wb.cold[0]);
               phase = PH_SAVE;
             } else {
               ++n_rej;
@@ -443,7 +485,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         // ---- SAVE phase: every save time in (tprev, t] via the dense interpolant, loss and
         //      gradient fused (single instance), then commit the accepted step ----
         while (isave < nsave) {
-          const double tsv = __ldg(sp.saveat + isave);
+          const double tsv = ts_next;
           if (!(tsv <= t)) break;
           if (tsv == t) {
 #pragma unroll
@@ -453,15 +495,21 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           } else {
             double b[7];
             ts::dense_b((tsv - tprev) / dt, b);  // every lane evaluates the seven weights itself: no barrier
-            const int k7s = 6 - k1s;
 #pragma unroll
-            for (int tt = 0; tt < CT; ++tt)
+            for (int tt = 0; tt < CT; ++tt) {
+              double kv[NS];
+              kload(k1s, tt, kv);
 #pragma unroll
-              for (int i = 0; i < NS; ++i)
-                KO[tt][i] = fma(dt, fma(b[6], wb.K[k7s][tt][i][lane], fma(b[5], wb.K[5][tt][i][lane],
-                                fma(b[4], wb.K[4][tt][i][lane], fma(b[3], wb.K[3][tt][i][lane],
-                                fma(b[2], wb.K[2][tt][i][lane], fma(b[1], wb.K[1][tt][i][lane],
-                                    b[0] * wb.K[k1s][tt][i][lane])))))), U[tt][i]);
+              for (int i = 0; i < NS; ++i) KO[tt][i] = b[0] * kv[i];
+#pragma unroll
+              for (int j = 1; j < 7; ++j) {
+                kload(j == 6 ? 6 - k1s : j, tt, kv);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) KO[tt][i] = fma(b[j], kv[i], KO[tt][i]);
+              }
+#pragma unroll
+              for (int i = 0; i < NS; ++i) KO[tt][i] = fma(dt, KO[tt][i], U[tt][i]);
+            }
           }
           if (isval[0]) {
 #pragma unroll
@@ -469,7 +517,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           }
           gsync();
           if (wig == 0 && lane < N) {
-            const int q = sm.row2obs[lane];
+            const int q = my_q;
             double g = 0.0;
             if (q >= 0) {
               const double y = (lane < NS) ? gb.y[lane] : Tval;
@@ -477,7 +525,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const bool inside = (y >= sp.pred_lo) && (y <= sp.pred_hi);
               const size_t off = pbase + q + (size_t)sp.n_obs * isave;
               if (pred) pred[off] = yc;
-              const double d = __ldg(data + off);
+              const double d = d_next;
               double diff;
               if (sp.loss_kind == CRNN_LOSS_MAE_SCALED) {
                 const double iy = sm.inv_ys[lane];
@@ -500,6 +548,10 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             for (int tt = 0; tt < CT; ++tt) G[tt] = fma(g, KO[tt][i], G[tt]);
           }
           ++isave;
+          if (isave < nsave) {
+            ts_next = __ldg(sp.saveat + isave);
+            if (my_q >= 0) d_next = __ldg(data + pbase + my_q + (size_t)sp.n_obs * isave);
+          }
         }
         // commit: u_n <- u_{n+1}, K1 <- K7 (FSAL: swap the slot roles, no copy)
 #pragma unroll
@@ -508,16 +560,16 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           for (int i = 0; i < NS; ++i) U[tt][i] = Y[tt][i];
         k1s = 6 - k1s;
         asum = bsum;
-        dt = jmin(dtnew, dtmax);
+        dt = jmin(dtnew, wb.cold[1]);
         phase = 1;
       }
 
       if (phase == 1) {  // loopheader! + check_error! before every step attempt
+        const double tend = wb.cold[0], dtmin = wb.cold[2];
         if (!(t < tend)) break;
-        ++iter;
         if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
-        if (iter > sp.maxiters) { ret = CRNN_RET_MAXITERS; break; }
-        dt = jmin(dt, dtmax);
+        if ((long long)n_acc + n_rej + 1 > sp.maxiters) { ret = CRNN_RET_MAXITERS; break; }
+        dt = jmin(dt, wb.cold[1]);
         dt = jmin(dt, tend - t);
         if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
         bool bad = false;
@@ -545,8 +597,8 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       if (retcode) retcode[traj] = ret;
       if (stats) {
         crnn_stats s;
-        s.n_accept = n_acc; s.n_reject = n_rej; s.n_rhs = n_rhs; s.n_jac = 0;
-        s.t_reached = t; s.dt_last = dt_last;
+        s.n_accept = n_acc; s.n_reject = n_rej; s.n_rhs = 2 + 6 * (n_acc + n_rej); s.n_jac = 0;
+        s.t_reached = t; s.dt_last = wb.cold[3];
         stats[traj] = s;
       }
     }
