@@ -34,6 +34,10 @@ sys.path.insert(0, ROOT)
 
 N_PER_GPU = 65536
 BYTES_PER_TRAJ = 8 * (7 + 2 * 6 * 50 + 1)   # u0 + targets read + saved states written + loss
+FP64_PEAK_TFLOPS = 37.106   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak.json)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_tsit5_sens launch of this exact workload, from the committed
+# `ncu --set full` capture (profiles/r1_sens_v11.txt): 161.9 MB + 129.1 MB; algorithmic bytes are 318.8 MB
+NCU_DRAM_BYTES_PER_LAUNCH = 291.04e6
 METRIC = "trajectories/sec (case2: Tsit5 + 25 forward sensitivities + fused loss, 65 536 ICs per B200)"
 
 
@@ -225,6 +229,7 @@ def main():
     from crnn_b200.engine import stats_from_torch
     st = stats_from_torch(rs["stats"])
     rhs_per_traj = float(st["n_rhs"].mean())
+    attempts_per_traj = float((st["n_accept"] + st["n_reject"]).mean())
 
     # ---- timed region 2: end to end with host (pinned) buffers through the public API ----
     u0_p = torch.from_numpy(u0_h).pin_memory(); data_p = torch.from_numpy(data_h).pin_memory()
@@ -257,6 +262,14 @@ def main():
         peak, which = measured_peaks()
         kms = kern_ms / max(1, kern_n)
         achieved = BYTES_PER_TRAJ * N_PER_GPU / (kms * 1e-3) / 1e9
+        # secondary (and binding) roofline: algorithmic fp64 flops of the path (DESIGN.md "flop model") against the
+        # measured DFMA peak (profiles/r1_fp64_peak.json, tools/fp64_peak.cu)
+        ns, nr, nin, ncol, nsave = 6, 3, 7, seed.shape[1] + 1, 50
+        f_rhs = (2 * nin * nr + 2 * ns * nr + 40 * ns + 30 * nr) + ncol * (ns + 4 * ns * nr + 3 * nr + 2)
+        f_step = ncol * ns * 2 * (21 + 6 + 7 + 2)
+        f_save = ncol * ns * 2 * 9
+        flop_traj = rhs_per_traj * f_rhs + attempts_per_traj * f_step + nsave * f_save
+        fp64_tflops = flop_traj * N_PER_GPU / (kms * 1e-3) / 1e12
         out = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -267,9 +280,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "peak_source": which,
                          "kernel": "k_tsit5_sens<Cfg<6,3,1>,1,...>", "kernel_ms": kms, "kernel_launches": int(kern_n),
-                         "note": "fp64-ALU bound by construction (~1e2-1e3 flop/B); see DESIGN.md and profiles/"},
+                         "fp64": {"achieved": fp64_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": fp64_tflops / FP64_PEAK_TFLOPS, "flop_per_trajectory": flop_traj,
+                                  "peak_source": "measured DFMA microbenchmark (profiles/r1_fp64_peak.json)"},
+                         "note": "HBM is the nominal roofline of the task's taxonomy; the kernel is fp64-issue bound by "
+                                 "construction (~2e2 flop/B), so the fp64 fraction is the meaningful one; see DESIGN.md"},
         }
         if a.gpus == 1:
             v, ms, cores = cpu_reference(1, 1, min(a.cpu_sample, N_PER_GPU))

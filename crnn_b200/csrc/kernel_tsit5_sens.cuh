@@ -163,9 +163,6 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     }
     live[t] = (lane + 32 * (t + CT * wig)) < ncol && (sp.incl_sens || isval[t]);
   }
-  // lane i < NS keeps the per-row controller state (tolerances, |u| magnitudes)
-  double my_at = 0.0, my_rt = 0.0;
-  if (lane < NS) { my_at = sm.abstol[lane]; my_rt = sm.reltol[lane]; }
 
   constexpr int PH_F0 = 0, PH_F1 = 7, PH_SAVE = 8;  // phases 1..6 are the Tsit5 stages
 
@@ -186,8 +183,8 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // U: state; Y: stage state (holds the proposed u_{n+1} from stage 6 through the save phase);
     // KO: RHS output / scratch
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
-    double Tval = 0.0, xT = 0.0, mybT = 0.0;
-    if (C::KIND == 1) { Tval = __ldg(u0 + traj * N + NS); xT = -1.0 / (mp.gas_R * Tval); }
+    double xT = 0.0, mybT = 0.0;
+    if (C::KIND == 1) xT = -1.0 / (mp.gas_R * __ldg(u0 + traj * N + NS));
     if (lane < NR) {
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
@@ -418,10 +415,10 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           if (lane < NS) {
             if (phase == 6) {
               // max(|u0|,|u1|) with dual magnitudes; sqrt is monotone, so one sqrt serves both
-              const double sc = fma(sqrt(fmax(asum, bsum)), my_rt, my_at);
+              const double sc = fma(sqrt(fmax(asum, bsum)), sm.reltol[lane], sm.abstol[lane]);
               term0 = rsum / (sc * sc);
             } else {
-              const double my_u0 = __ldg(u0 + traj * N + lane), my_sk = my_at + fabs(my_u0) * my_rt;
+              const double my_u0 = __ldg(u0 + traj * N + lane), my_sk = sm.abstol[lane] + fabs(my_u0) * sm.reltol[lane];
               const double a = my_u0 / my_sk;
               term0 = rsum / (my_sk * my_sk);
               term1 = a * a;
@@ -435,7 +432,10 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
 
           if (phase == PH_F0) {
             // initial step size, part 1 (ode_determine_initdt)
-            if (C::KIND == 1) { const double a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]); s1 = fma(a, a, s1); }
+            if (C::KIND == 1) {
+              const double Tval = __ldg(u0 + traj * N + NS), a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]);
+              s1 = fma(a, a, s1);
+            }
             const double d0 = sqrt(s1 / N);
             const double d1 = sqrt(s0 / N);
             const double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
@@ -520,7 +520,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             const int q = my_q;
             double g = 0.0;
             if (q >= 0) {
-              const double y = (lane < NS) ? gb.y[lane] : Tval;
+              const double y = (lane < NS) ? gb.y[lane] : __ldg(u0 + traj * N + NS);  // the T row never changes
               const double yc = clampd(y, sp.pred_lo, sp.pred_hi);
               const bool inside = (y >= sp.pred_lo) && (y <= sp.pred_hi);
               const size_t off = pbase + q + (size_t)sp.n_obs * isave;
