@@ -111,4 +111,17 @@ function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array
     sum(loss[ok]) / max(count(ok), 1), grad ./ max(count(ok), 1)
 end
 
+"""
+    grad_each(e, N, np) -> np × N matrix
+
+Per-experiment gradients d loss_i / d p of the last forward-mode `loss_grad` call - the rows
+`rober_crnn_lm.jl:216-218` assembles with `ForwardDiff.jacobian` for its Levenberg-Marquardt step.
+"""
+function grad_each(e::Engine, N::Integer, np_::Integer)
+    g = zeros(np_, N)
+    check(e, ccall((:crnn_copy_grad_each, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Cvoid}),
+                   e.h, g, N, np_, 0, C_NULL))
+    g
+end
+
 end # module
