@@ -55,7 +55,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The
+    timed region is ~150 ms, shorter than nvidia-smi's start-up, so NVML is polled in-process every
+    5 ms from a thread; `nvidia-smi -lms` is the fallback when the binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -64,20 +66,74 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.sm, self.reasons, self.smax, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thr = None
+        self.nv = None
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            except Exception:
+                pass
+            hnd = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        hnd = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        hnd = None
+            if hnd is None:
+                hnd = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv, self.hnd = nv, hnd
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(hnd, nv.NVML_CLOCK_SM))
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, hnd = self.nv, self.hnd
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hnd))
+                for nm, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(hnd) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self._thr.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "power_w_max": max(self.power) if self.power else None, "source": "nvml, 5 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def build_inputs(eng, rank):

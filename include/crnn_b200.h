@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CRNN_B200_VERSION 100 /* 0.1.0 */
+#define CRNN_B200_VERSION 101 /* 0.1.1: F2 RHS, AutoTsit5(Rosenbrock23), generic-dimension solve path */
 
 typedef struct crnn_handle crnn_handle;
 
@@ -60,13 +60,21 @@ enum crnn_status {
 /* RHS flavours. */
 enum crnn_rhs_kind {
   CRNN_RHS_F0 = 0, /* du = s .* W_out*exp(W_in'*log(clamp(u,lb,ub)) + b): case1.jl:80-83, case3.jl:162-166, rober_crnn.jl:113-116 */
-  CRNN_RHS_F1_ARRH_TSTATE = 1 /* state [X;T], x=[log clamp X; -1/(R T)], dT/dt=0: case2.jl:113-118 */
+  CRNN_RHS_F1_ARRH_TSTATE = 1, /* state [X;T], x=[log clamp X; -1/(R T)], dT/dt=0: case2.jl:113-118 */
+  CRNN_RHS_F2_MASSFRAC_TP = 2  /* mass fractions under tabulated T(t), P(t) (non-autonomous):
+                                  Y=clamp(u,lb,ub), rho=P/(8314.46261815324 T sum(Y/MW)), C=rho Y/MW 1e3,
+                                  x=[log clamp(C,lb,ub); -1/(R T); log T], du = W_out*exp(W_in'x+b) .* MW / rho .* out_scale:
+                                  HyChem/crnn_pyrolysis_mass.jl:107-114,121-131 */
 };
 
 enum crnn_alg {
   CRNN_ALG_TSIT5 = 0,        /* case1.jl:28, case3.jl:29, non-stiff half of case2.jl:26 */
   CRNN_ALG_ROSENBROCK23 = 1, /* rober_crnn.jl:33 */
-  CRNN_ALG_KENCARP4 = 2      /* BASELINE config 5 (not in the reference) */
+  CRNN_ALG_KENCARP4 = 2,     /* BASELINE config 5 (not in the reference) */
+  CRNN_ALG_AUTO_TSIT5_ROS23 = 3 /* AutoTsit5(Rosenbrock23()): case2.jl:26, HyChem/crnn_pyrolysis_mass.jl:29 — Tsit5 with
+                                   OrdinaryDiffEq's AutoSwitch stiffness detection (maxstiffstep 10, maxnonstiffstep 3,
+                                   tolerances 9/10, dtfac 2) switching to Rosenbrock23 (analytic J) and back;
+                                   crnn_stats.n_jac counts the Rosenbrock23 step attempts */
 };
 
 enum crnn_sens_mode {
@@ -96,16 +104,22 @@ enum crnn_retcode {
 typedef struct crnn_model {
   int32_t n_state;   /* length of u (F1: n_species + 1) */
   int32_t n_species; /* rows of w_out */
-  int32_t n_in;      /* rows of w_in (== n_state for F0 and F1) */
+  int32_t n_in;      /* rows of w_in (== n_state for F0 and F1, n_species + 2 for F2) */
   int32_t n_reac;    /* columns of w_in / w_out */
   int32_t rhs_kind;  /* crnn_rhs_kind */
-  int32_t reserved0;
+  int32_t n_tab;     /* F2 only: length of tab_t / tab_T / tab_P (>= 2) */
   double lb, ub;     /* clamp bounds inside the RHS; ub may be +Inf (rober_crnn.jl:114) */
-  double gas_R;      /* F1 only: 1.98720425864083e-3 (case2.jl:113) */
+  double gas_R;      /* F1, F2: 1.98720425864083e-3 (case2.jl:113; a Float32 literal at crnn_pyrolysis_mass.jl:106) */
   const double* out_scale; /* [n_species] or NULL: dy_std_ (case3.jl:165), dydt_scale (rober_crnn.jl:115) */
   const double* w_in;      /* [n_in x n_reac] col-major */
   const double* w_b;       /* [n_reac] */
   const double* w_out;     /* [n_species x n_reac] col-major */
+  /* F2 only (NULL otherwise): molar masses l_MW (crnn_pyrolysis_mass.jl:58) and the T(t), P(t) tables the script
+   * interpolates linearly (itpT, itpP, :103-104); tab_t ascending and covering [t0, t1]. */
+  const double* mw;        /* [n_species] */
+  const double* tab_t;     /* [n_tab] */
+  const double* tab_T;     /* [n_tab] */
+  const double* tab_P;     /* [n_tab] */
 } crnn_model;
 
 typedef struct crnn_opts {
