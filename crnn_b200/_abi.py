@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libcrnn_b200.so")
 
 # enums (include/crnn_b200.h)
-RHS_F0, RHS_F1 = 0, 1
-ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4 = 0, 1, 2
+RHS_F0, RHS_F1, RHS_F2 = 0, 1, 2
+ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4, ALG_AUTO_TSIT5_ROS23 = 0, 1, 2, 3
 SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT, SENS_DISCRETE_ADJOINT = 0, 1, 2, 3
 LOSS_MAE_SCALED, LOSS_MAE_LOG = 0, 1
 RET_DEFAULT, RET_SUCCESS, RET_DTNAN, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 3, 4, 5, 6
@@ -29,9 +29,10 @@ c_int32_p = C.POINTER(C.c_int32)
 class CModel(C.Structure):
     _fields_ = [
         ("n_state", C.c_int32), ("n_species", C.c_int32), ("n_in", C.c_int32), ("n_reac", C.c_int32),
-        ("rhs_kind", C.c_int32), ("reserved0", C.c_int32),
+        ("rhs_kind", C.c_int32), ("n_tab", C.c_int32),
         ("lb", C.c_double), ("ub", C.c_double), ("gas_R", C.c_double),
         ("out_scale", c_double_p), ("w_in", c_double_p), ("w_b", c_double_p), ("w_out", c_double_p),
+        ("mw", c_double_p), ("tab_t", c_double_p), ("tab_T", c_double_p), ("tab_P", c_double_p),
     ]
 
 

@@ -273,3 +273,86 @@ def synthetic_stiff_opts(alg=_abi.ALG_KENCARP4, ns=29, n_save=40, t1=1.0) -> Sol
     """HyChem-like settings: abstol 1e-8 / reltol 1e-3 (crnn_pyrolysis_mass.jl:26-27), 40 log-spaced saves."""
     return SolveOpts(saveat=t1 * 10.0 ** np.linspace(-6.0, 0.0, n_save), t0=0.0, t1=t1, alg=alg, abstol=1e-8,
                      reltol=1e-3, maxiters=100000, obs_idx=np.arange(ns))
+
+
+# ---- HyChem (JP-10 pyrolysis on mass fractions): HyChem/crnn_pyrolysis_mass.jl ----
+
+HYCHEM_MW = np.array([136.238, 2.016, 16.043, 26.038, 28.054, 28.014, 56.108, 1.008, 15.035])  # :58
+HYCHEM_GAS_R = float(np.float32(1.98720425864083e-3))  # a Float32 literal in the script (:106)
+
+
+def p2vec_hychem(p, ns=9, nr=10):
+    """HyChem/crnn_pyrolysis_mass.jl:78-90: w_in = [clamp(w_in_raw, 0, 2.5); Ea'; b'] (n_in = ns + 2)."""
+    d = _D.seed(p)
+    slope = d[nr * (2 * ns + 3)] * 10.0
+    slope_v = slope.broadcast_scalar((nr,))
+    w_b = d[0:nr] * slope_v
+    w_in_b = d[nr:2 * nr]
+    w_in_Ea = d[2 * nr:3 * nr] * slope_v
+    w_out_raw = d[3 * nr:nr * (ns + 3)].reshape_f(ns, nr)
+    w_in_raw = d[nr * (ns + 3):nr * (2 * ns + 3)].reshape_f(ns, nr)
+    w_out = (-w_in_raw) * w_out_raw.pow10()
+    w_in_c = w_in_raw.clamp(0.0, 2.5)
+    w_in = _D(np.vstack([w_in_c.v, w_in_Ea.v[None, :], w_in_b.v[None, :]]),
+              np.concatenate([w_in_c.j, w_in_Ea.j[None, :, :], w_in_b.j[None, :, :]], axis=0))
+    return _pack(w_in, w_b, w_out)
+
+
+def hychem_tables(t_end=0.01, n_tab=48):
+    """Synthetic stand-in for the script's T(t), P(t) columns (its data file `data/10atm_1300K_0.01.txt`, :32, is not
+    in the reference tree): a 10 atm / 1300 K pyrolysis history cooling by ~12 % as the endothermic cracking proceeds,
+    on non-uniform knots (0 and a log-spaced grid, like the script's resampled `_tsteps`, :41-42)."""
+    tab_t = np.concatenate([[0.0], t_end * 10.0 ** np.linspace(-5.0, 0.0, n_tab - 1)])
+    s = np.sqrt(tab_t / t_end)
+    tab_T = 1300.0 - 160.0 * s
+    tab_P = 10.0 * 101325.0 * (1.0 + 0.02 * np.sin(3.0 * s))
+    return tab_t, tab_T, tab_P
+
+
+def hychem_saveat(t_end=0.01, n_save=40):
+    """`_tsteps` of crnn_pyrolysis_mass.jl:41-42: 40 log-spaced points in [t_end/100, t_end/1.01], the first forced to 0."""
+    ts = 10.0 ** np.linspace(np.log10(t_end / 100.0), np.log10(t_end / 1.01), n_save)
+    ts[0] = 0.0
+    return ts
+
+
+def hychem_model(p, yscale, t_end=0.01, lb=1e-8, ns=9, nr=10):
+    """(CRNNModel, seed) of the HyChem script for a parameter vector p[211]; dydt_scale = yscale / t_end (:119)."""
+    w_in, w_b, w_out, seed = p2vec_hychem(p, ns, nr)
+    tab_t, tab_T, tab_P = hychem_tables(t_end)
+    m = CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F2, lb=lb, ub=10.0,
+                  out_scale=np.asarray(yscale, dtype=np.float64) / t_end, gas_R=HYCHEM_GAS_R,
+                  mw=HYCHEM_MW[:ns], tab_t=tab_t, tab_T=tab_T, tab_P=tab_P)
+    return m, seed
+
+
+def hychem_opts(alg=_abi.ALG_AUTO_TSIT5_ROS23, t_end=0.01, **kw) -> SolveOpts:
+    """atol = lb = 1e-8, rtol = 1e-3, maxiters = 10000 (:21,26-28); tspan = [0, tsteps[sample]] (:137)."""
+    ts = hychem_saveat(t_end)
+    base = dict(saveat=ts, t0=0.0, t1=float(ts[-1]), alg=alg, abstol=1e-8, reltol=1e-3, maxiters=10000)
+    base.update(kw)
+    return SolveOpts(**base)
+
+
+def hychem_u0(N, seed=1234, start=0, ns=9) -> np.ndarray:
+    """Fuel (C10H16) at 3-8 % in N2, traces of the products (the script has ONE measured initial state, :73)."""
+    from . import synth
+    r = synth._blocked(seed, 11, start, N, (ns,), lambda g, shp: g.random(shp))
+    u0 = 1e-6 * (1.0 + r)
+    u0[:, 0] = 0.03 + 0.05 * r[:, 0]
+    u0[:, 5] = 1.0 - u0[:, 0] - (u0[:, 1:5].sum(1) + u0[:, 6:].sum(1))
+    return u0
+
+
+def hychem_p(seed=0, ns=9, nr=10, sigma=0.1, slope=0.1, stiff=0.0):
+    """`p = randn(np) .* 0.1; p[end] = 0.1` (:75-76).  `stiff` > 0 spreads ln A over that many e-folds and switches a few
+    fast consumption channels on — a stand-in for a trained stiff pyrolysis model."""
+    g = np.random.default_rng(seed)
+    n_p = nr * (2 * ns + 3) + 1
+    p = g.standard_normal(n_p) * sigma
+    p[-1] = slope
+    if stiff > 0:
+        p[0:nr] += np.linspace(0.0, stiff, nr)            # ln A / slope
+        w_in_raw = p[nr * (ns + 3):nr * (2 * ns + 3)].reshape(nr, ns)
+        w_in_raw[:, 0] = np.abs(w_in_raw[:, 0]) + 0.5      # every reaction consumes fuel
+    return p

@@ -6,6 +6,7 @@
 #include "crnn_host.cuh"
 #include "kernel_kencarp4_wide.cuh"
 #include "kernel_tsit5_adjoint.cuh"
+#include "kernel_wide_solve.cuh"
 
 namespace crnn_host {
 #define X(NS_, NR_, K_)                                                                                     \
@@ -25,9 +26,11 @@ namespace {
 // its device arrays: w_inT [nin][32] | w_b | w_out (scaled) | saveat | row2obs | extra doubles.
 int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int order, const std::vector<double>& extra,
                cudaStream_t st, WideP& P, const double** extra_dev) {
-  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state <= 32 and n_reac <= 32");
+  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
   const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
+  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int ntab = f2 ? m->n_tab : 0;
   std::vector<int> row2obs(n, -1);
   for (int q = 0; q < o->n_obs; ++q) {
     const int r = o->obs_idx[q];
@@ -50,8 +53,12 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.maxiters = o->maxiters;
   P.n = n; P.ns = ns; P.nin = nin; P.nr = nr; P.kind = m->rhs_kind;
   P.n_save = o->n_save; P.n_obs = o->n_obs;
+  P.alg = o->alg; P.n_tab = ntab;
+  P.beta2_ros = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * 2.0);
+  P.beta1_ros = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * 2.0);
   const size_t n_r2o = (n + 1) / 2 + 1;
-  std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + n_r2o + extra.size() + 2, 0.0);
+  std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + n_r2o + extra.size() + 2 +
+                           (f2 ? ns + 3 * (size_t)ntab : 0), 0.0);
   double* p_winT = blob.data();
   double* p_wb = p_winT + (size_t)nin * KW_MAXN;
   double* p_wout = p_wb + nr;
@@ -61,11 +68,20 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   for (int j = 0; j < nr; ++j) {
     for (int i = 0; i < nin; ++i) p_winT[(size_t)i * KW_MAXN + j] = m->w_in[i + nin * j];
     p_wb[j] = m->w_b[j];
-    for (int i = 0; i < ns; ++i) p_wout[i + ns * j] = m->w_out[i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0);
+    // out_scale (and, for F2, the molar mass of `wdot * l_MW / density * dydt_scale`) folded into the rows of w_out
+    for (int i = 0; i < ns; ++i)
+      p_wout[i + ns * j] = m->w_out[i + ns * j] * (f2 ? m->mw[i] : 1.0) * (m->out_scale ? m->out_scale[i] : 1.0);
   }
   for (int k = 0; k < o->n_save; ++k) p_save[k] = o->saveat[k];
   for (int i = 0; i < n; ++i) p_r2o[i] = row2obs[i];
   for (size_t q = 0; q < extra.size(); ++q) p_extra[q] = extra[q];
+  double* p_f2 = p_extra + extra.size() + 1;
+  if (f2) {
+    for (int i = 0; i < ns; ++i) p_f2[i] = m->mw[i];
+    for (int k = 0; k < ntab; ++k) {
+      p_f2[ns + k] = m->tab_t[k]; p_f2[ns + ntab + k] = m->tab_T[k]; p_f2[ns + 2 * ntab + k] = m->tab_P[k];
+    }
+  }
   CK(h->cfg.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
   CK(cudaMemcpyAsync(h->cfg.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   double* d = h->cfg.as<double>();
@@ -73,11 +89,45 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.saveat = d + (p_save - blob.data());
   P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
   if (extra_dev) *extra_dev = d + (p_extra - blob.data());
+  if (f2) {
+    const double* df2 = d + (p_f2 - blob.data());
+    P.mw = df2; P.tab_t = df2 + ns; P.tab_T = df2 + ns + ntab; P.tab_P = df2 + ns + 2 * ntab;
+  }
   return CRNN_OK;
+}
+
+// Generic predict path (kernel_wide_solve.cuh): Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23) for any
+// dimensions <= 32 and every RHS flavour.
+int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  WideP P{};
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  int rcw = build_wide(h, m, o, order, {}, st, P, nullptr);
+  if (rcw) return rcw;
+  constexpr int WARPS = 4;
+  auto kern = k_wide_solve<WARPS>;
+  const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+  if (bps < 1) bps = 1;
+  return run_batch(h, m, o, io, N, false, 0, nullptr, [&](const BatchPtrs& b, cudaStream_t s) -> int {
+    if (b.n == 0) return (int)CRNN_OK;
+    const long long want = (b.n + WARPS - 1) / WARPS;
+    const unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, want);
+    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    ProfScope prof(h, s);
+    kern<<<blocks, WARPS * 32, smem, s>>>(P, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode, b.stats, queue);
+    CK(cudaGetLastError());
+    h->launches++;
+    return (int)CRNN_OK;
+  });
 }
 
 // KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
 int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 is implemented for the F0 and F1 RHS flavours");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
@@ -108,6 +158,7 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
 int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                       const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
   if (o->alg != CRNN_ALG_TSIT5) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for Tsit5");
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for the F0 and F1 RHS flavours");
   const int n = m->n_state, ns = m->n_species, nr = m->n_reac;
   const int nw = nr * (m->n_in + 1 + ns);
   if (nw > 32 * ADJ_MAX_ENT) return fail(h, CRNN_ERR_UNSUPPORTED, "adjoint kernel supports n_w <= 512");
@@ -270,17 +321,23 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
   int rc = validate(h, m, o, N);
   if (rc) return rc;
   if (N > 0 && !u0) return fail(h, CRNN_ERR_BAD_ARG, "null u0");
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4)
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4 &&
+      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
     return fail(h, CRNN_ERR_UNSUPPORTED, "alg not supported by solve_batch");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, nullptr, pred, nullptr, n_saved, retcode, stats};
   if (o->alg == CRNN_ALG_KENCARP4) return solve_kencarp4(h, m, o, io, N);
+  // dimension-specialised thread-per-trajectory kernels for the instantiated configurations ...
+  const char* force = std::getenv("CRNN_B200_FORCE_WIDE");
+  if (o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return solve_impl<Cfg<NS_, NR_, K_>>(h, m, o, io, N);
-  CRNN_FOR_EACH_CFG(X)
+    CRNN_FOR_EACH_CFG(X)
 #undef X
-  return fail(h, CRNN_ERR_UNSUPPORTED, "no kernel instantiated for this (n_species, n_reac, rhs_kind)");
+  }
+  // ... and the generic warp-per-trajectory kernel for everything else (any dimensions <= 32, F2, AutoTsit5)
+  return solve_wide(h, m, o, io, N);
 }
 
 int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,

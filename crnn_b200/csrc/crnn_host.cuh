@@ -123,10 +123,19 @@ struct Packed {
 inline int validate(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int64_t N) {
   if (!m || !o) return fail(h, CRNN_ERR_BAD_ARG, "null model/opts");
   if (N < 0) return fail(h, CRNN_ERR_BAD_ARG, "negative N");
-  if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE)
+  if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP)
     return fail(h, CRNN_ERR_UNSUPPORTED, "rhs_kind not supported");
-  if (m->n_in != m->n_state || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
+  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  if (m->n_in != m->n_state + (f2 ? 2 : 0) || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
     return fail(h, CRNN_ERR_BAD_ARG, "inconsistent n_state / n_species / n_in for rhs_kind");
+  if (f2) {
+    if (!m->mw || !m->tab_t || !m->tab_T || !m->tab_P || m->n_tab < 2)
+      return fail(h, CRNN_ERR_BAD_ARG, "F2 needs mw and the tab_t / tab_T / tab_P tables (n_tab >= 2)");
+    for (int k = 1; k < m->n_tab; ++k)
+      if (!(m->tab_t[k] > m->tab_t[k - 1])) return fail(h, CRNN_ERR_BAD_ARG, "tab_t must be strictly ascending");
+    if (m->tab_t[0] > o->t0 || m->tab_t[m->n_tab - 1] < o->t1)
+      return fail(h, CRNN_ERR_BAD_ARG, "tab_t must cover [t0, t1]");
+  }
   if (!m->w_in || !m->w_b || !m->w_out) return fail(h, CRNN_ERR_BAD_ARG, "null weights");
   if (!(m->lb > 0.0) || !(m->ub > m->lb)) return fail(h, CRNN_ERR_BAD_ARG, "need 0 < lb < ub");
   if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(h, CRNN_ERR_BAD_ARG, "bad saveat");

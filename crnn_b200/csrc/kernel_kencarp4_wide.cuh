@@ -32,6 +32,13 @@ struct WideP {
   const int* row2obs;    // device [n_state]
   int n, ns, nin, nr, kind;
   int n_save, n_obs;
+  // generic solve path (kernel_wide_solve.cuh)
+  int alg, n_tab;
+  double beta1_ros, beta2_ros;  // PI exponents while AutoTsit5 runs Rosenbrock23 (beta1/beta2 above: Tsit5)
+  const double* mw;      // device [n_species]           (F2)
+  const double* tab_t;   // device [n_tab] knots         (F2)
+  const double* tab_T;   // device [n_tab]
+  const double* tab_P;   // device [n_tab]
 };
 
 namespace kc {
@@ -51,6 +58,9 @@ struct alignas(16) WideWarp {
   double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
   double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
   int perm[KW_MAXN];
+  // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
+  double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
+  double k[7][KW_MAXN];
 };
 
 struct alignas(16) WideBlock {

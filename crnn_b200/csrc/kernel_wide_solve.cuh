@@ -1,0 +1,414 @@
+// kernel_wide_solve.cuh — the GENERIC predict path: any CRNN the reference scripts define, with runtime
+// dimensions (n_state <= 32, n_reac <= 32), every RHS flavour (F0, F1 Arrhenius/T-state, F2 HyChem mass
+// fractions under tabulated T(t), P(t)) and the three explicit/linearly-implicit steppers of the reference:
+//   Tsit5                              case1/case1.jl:28, case3/case3.jl:29
+//   Rosenbrock23 (analytic J, df/dt)   robertson/rober_crnn.jl:33
+//   AutoTsit5(Rosenbrock23())          case2/case2.jl:26, HyChem/crnn_pyrolysis_mass.jl:29
+// One WARP owns one trajectory and lane i owns state component i (the layout of k_kencarp4_wide): the RHS
+// issues ONE log and ONE exp per evaluation for the whole state, the Jacobian is assembled analytically in
+// shared memory and LU-factored cooperatively.  It mirrors oracle/crnn_oracle.c::solve_one operation by
+// operation (stage order, norm, PI controller, AutoSwitch counter, dense output).
+//
+// The dimension-specialised thread-per-trajectory kernels (kernel_tsit5_value.cuh, kernel_rosenbrock23.cuh)
+// stay the fast path for the instantiated configurations; this kernel serves everything else.
+#pragma once
+#include "crnn_dev.cuh"
+#include "kernel_kencarp4_wide.cuh"
+#include "kernel_tsit5_adjoint.cuh"  // tsc:: tableau in constant memory
+
+namespace crnn {
+
+constexpr double kGasRu = 8.31446261815324e3;  // HyChem/crnn_pyrolysis_mass.jl:108
+
+struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobian needs)
+  double dx;       // d x_l / d u_l (F2: at fixed density)
+  double rr;       // F2: d log(rho) / d u_l = -chi_l / (MW_l S)
+  double wdot;     // sum_j w_out[l,j] r_j (scaled; F2: before the 1/rho)
+  double inv_rho;  // F2
+  double chiC;     // F2: 1 if lb <= C_l <= ub
+};
+
+struct TabVal { double T, P, Td, Pd; };
+
+// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t
+__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
+  int lo = 0, hi = P.n_tab - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
+  }
+  const double ta = __ldg(P.tab_t + lo), h = __ldg(P.tab_t + lo + 1) - ta, w = (t - ta) / h;
+  const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
+  const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
+  TabVal v;
+  v.T = T0 + w * (T1 - T0); v.P = P0 + w * (P1 - P0);
+  v.Td = (T1 - T0) / h; v.Pd = (P1 - P0) / h;
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
+// f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
+__device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double mw,
+                                           double t, double y, WideAux& a) {
+  const int ns = P.ns, nin = P.nin, nr = P.nr;
+  const bool isp = lane < ns;
+  __syncwarp();
+  double xi = 0.0, rho = 1.0;
+  a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
+  if (P.kind == 2) {
+    const TabVal tv = wide_tab(P, t);
+    double Y = 1.0, chi = 0.0, ymw = 0.0;
+    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
+    const double S = warp_sum(ymw);
+    rho = tv.P / (kGasRu * tv.T * S);
+    if (isp) {
+      const double C = rho * ymw * 1e3;
+      a.chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
+      xi = lean_log(clampd(C, P.lb, P.ub));
+      a.dx = a.chiC * chi / Y;
+      a.rr = -chi / (mw * S);
+    } else if (lane == ns) {
+      xi = -1.0 / P.gas_R / tv.T;
+    } else if (lane == ns + 1) {
+      xi = lean_log(tv.T);
+    }
+    a.inv_rho = 1.0 / rho;
+  } else if (isp) {
+    const double uc = clampd(y, P.lb, P.ub);
+    xi = lean_log(uc);
+    a.dx = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
+  } else if (P.kind == 1 && lane == ns) {
+    xi = -1.0 / (P.gas_R * y);
+    a.dx = 1.0 / (P.gas_R * y * y);
+  }
+  ww.x[lane] = xi;
+  __syncwarp();
+  if (lane < nr) {
+    double z = sb.w_b[lane];
+    for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
+    ww.r[lane] = lean_exp(z);
+  }
+  __syncwarp();
+  double f = 0.0;
+  if (isp)
+    for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+  a.wdot = f;
+  if (P.kind == 2) f = f / rho;
+  return f;
+}
+
+// df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
+__device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double t,
+                                                  const double* rsrc, const WideAux& a) {
+  if (P.kind != 2) return 0.0;
+  const int ns = P.ns, nr = P.nr;
+  const TabVal tv = wide_tab(P, t);
+  const double rr = tv.Pd / tv.P - tv.Td / tv.T;
+  __syncwarp();
+  ww.bchi[lane] = a.chiC;
+  __syncwarp();
+  if (lane < nr) {
+    double zd = 0.0;
+    for (int i = 0; i < ns; ++i) zd = fma(sb.w_inT[i][lane], ww.bchi[i] * rr, zd);
+    zd = fma(sb.w_inT[ns][lane], tv.Td / (P.gas_R * tv.T * tv.T), zd);
+    zd = fma(sb.w_inT[ns + 1][lane], tv.Td / tv.T, zd);
+    ww.ws[lane] = rsrc[lane] * zd;
+  }
+  __syncwarp();
+  double s = 0.0;
+  if (lane < ns) {
+    for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane], ww.ws[j], s);
+    s = (s - a.wdot * rr) * a.inv_rho;
+  }
+  __syncwarp();
+  return s;
+}
+
+// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
+// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
+__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane,
+                                                const double* rsrc, const WideAux& a, double gdt) {
+  const int n = P.n, ns = P.ns, nr = P.nr;
+  const bool isp = lane < ns;
+  __syncwarp();
+  ww.bdx[lane] = a.dx; ww.brr[lane] = a.rr; ww.bchi[lane] = a.chiC;
+  __syncwarp();
+  if (P.kind == 2 && lane < nr) {
+    double ws = 0.0;
+    for (int i = 0; i < ns; ++i) ws = fma(sb.w_inT[i][lane], ww.bchi[i], ws);
+    ww.ws[lane] = ws;
+  }
+  __syncwarp();
+  double rowsum = 0.0;
+  if (isp) {
+    double coef = 0.0;
+    if (P.kind == 2) {
+      for (int j = 0; j < nr; ++j) coef = fma(sb.w_out[j][lane] * rsrc[j], ww.ws[j], coef);
+      coef -= a.wdot;
+    }
+    for (int l = 0; l < n; ++l) {
+      double s = 0.0;
+      for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
+      double Jil = s * ww.bdx[l];
+      if (P.kind == 2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
+      rowsum += fabs(Jil);
+      if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
+    }
+  }
+  const double eig = warp_max(rowsum);
+  ww.perm[lane] = lane;
+  __syncwarp();
+  for (int k = 0; k < ns; ++k) {
+    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
+    int bi = lane;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi != k) {
+      if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
+      if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
+    }
+    __syncwarp();
+    if (lane > k && isp) {
+      const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
+      ww.A[lane][k] = l;
+      for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
+    }
+    __syncwarp();
+  }
+  return eig;
+}
+
+// b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
+__device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int ns, double b) {
+  const bool isp = lane < ns;
+  b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
+  for (int k = 0; k + 1 < ns; ++k) {
+    const double bk = __shfl_sync(0xffffffffu, b, k);
+    if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
+  }
+  for (int k = ns - 1; k >= 0; --k) {
+    if (lane == k) b = b / ww.A[k][k];
+    const double bk = __shfl_sync(0xffffffffu, b, k);
+    if (lane < k) b = fma(-ww.A[lane][k], bk, b);
+  }
+  return isp ? b : 0.0;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 3)
+k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
+             long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
+             crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WideBlock& sb = *reinterpret_cast<WideBlock*>(smem_raw);
+  WideWarp* wws = reinterpret_cast<WideWarp*>(smem_raw + sizeof(WideBlock));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WideWarp& ww = wws[warp];
+  const int n = P.n, ns = P.ns, nin = P.nin, nr = P.nr;
+
+  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
+    const int i = q / KW_MAXN, j = q % KW_MAXN;
+    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
+    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
+  }
+  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
+  __syncthreads();
+
+  const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23);
+  const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
+  const int my_obs = lane < n ? P.row2obs[lane] : -1;
+  const double my_mw = (P.kind == 2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
+  double* const kk = &ww.k[0][lane];  // this lane's stage column, stride KW_MAXN
+#define KS(s) kk[(s) * KW_MAXN]
+
+  auto wrms = [&](double v, double a, double b) -> double {
+    double q = 0.0;
+    if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
+    return sqrt(warp_sum(q) / n);
+  };
+
+  while (true) {
+    unsigned long long tq = 0;
+    if (lane == 0) tq = atomicAdd(queue, 1ull);
+    const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
+    if (traj >= ntraj) break;
+
+    double u = lane < n ? __ldg(u0 + traj * n + lane) : 0.0;
+    int nsave = P.n_save;
+    double tend = P.t1;
+    if (n_save_used) {
+      const int q = __ldg(n_save_used + traj);
+      if (q > 0 && q <= P.n_save) { nsave = q; tend = __ldg(P.saveat + q - 1); }
+    }
+    const double t0 = P.t0, dtmax = tend - t0;
+    const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
+    double* mypred = pred ? pred + (size_t)traj * P.n_obs * P.n_save : nullptr;
+    auto save = [&](int ks, double y) {
+      if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
+    };
+
+    int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
+    WideAux a0, as;  // by-products at u_n / at the last evaluation
+    KS(0) = wide_rhs(P, sb, ww, lane, my_mw, t0, u, a0); ++n_rhs;
+    ww.r0[lane] = ww.r[lane];
+    // ---- initial step (Hairer-Wanner; the order of the FIRST algorithm) ----
+    double dt;
+    {
+      const double f0 = KS(0);
+      const double sk = my_at + fabs(u) * my_rt;
+      double a = 0.0, b = 0.0;
+      if (lane < n) { a = u / sk; a *= a; b = f0 / sk; b *= b; }
+      const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+      double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+      dt0 = jmin(dt0, dtmax);
+      const double f1p = wide_rhs(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
+      double c = 0.0;
+      if (lane < n) { c = (f1p - f0) / sk; c *= c; }
+      const double d2 = sqrt(warp_sum(c) / n) / dt0;
+      const double dm = jmax(d1, d2);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * P.inv_order);
+      dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
+    }
+    double t = t0, qold = 1e-4, dt_last = 0.0, eigen_est = 0.0;
+    int isave = 0, ret = CRNN_RET_DEFAULT, sw_count = 0;
+    bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23);
+    long long iter = 0;
+    while (isave < nsave && __ldg(P.saveat + isave) <= t0) { save(isave, u); ++isave; }
+
+    while (t < tend) {
+      ++iter;
+      if (autosw && iter > 1) {  // OrdinaryDiffEq AutoSwitch (oracle solve_one header comment)
+        const bool stiff = fabs(eigen_est * dt / 3.5068) > 0.9;
+        sw_count = stiff ? (sw_count < 0 ? 1 : sw_count + 1) : (sw_count > 0 ? -1 : sw_count - 1);
+        bool want = rosen;
+        if (!rosen && sw_count > 10) { dt = dt * 2.0; want = true; }
+        else if (rosen && sw_count < -3) { dt = dt / 2.0; want = false; }
+        if (want != rosen) {
+          rosen = want;
+          KS(0) = wide_rhs(P, sb, ww, lane, my_mw, t, u, a0); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
+          __syncwarp();
+          ww.r0[lane] = ww.r[lane];
+        }
+      }
+      if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
+      if (iter > P.maxiters) { ret = CRNN_RET_MAXITERS; break; }
+      dt = jmin(dt, dtmax);
+      dt = jmin(dt, tend - t);
+      if (dt <= dtmin && tend - t > dtmin) { ret = CRNN_RET_DTLESSTHANMIN; break; }
+      if (__any_sync(0xffffffffu, lane < n && u != u)) { ret = CRNN_RET_UNSTABLE; break; }
+
+      double un, e;
+      if (!rosen) {
+        // ---- Tsit5 ----
+        double g6 = u;
+#pragma unroll 1
+        for (int s = 1; s < 7; ++s) {
+          double acc = tsc::A[s][0] * KS(0);
+          for (int j = 1; j < s; ++j) acc = fma(tsc::A[s][j], KS(j), acc);
+          const double y = fma(dt, acc, u);
+          if (s == 5) g6 = y;
+          un = y;
+          KS(s) = wide_rhs(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as); ++n_rhs;
+        }
+        double acc = tsc::BT[0] * KS(0);
+#pragma unroll
+        for (int j = 1; j < 7; ++j) acc = fma(tsc::BT[j], KS(j), acc);
+        e = dt * acc;
+        if (autosw) {
+          double a = 0.0, b = 0.0;
+          if (lane < n) { a = KS(6) - KS(5); a *= a; b = un - g6; b *= b; }
+          eigen_est = sqrt(warp_sum(a) / n) / sqrt(warp_sum(b) / n);
+        }
+      } else {
+        // ---- Rosenbrock23 = ode23s: KS(0)=f0, KS(1..3)=k1..k3, KS(4)=f1, KS(5)=f2 ----
+        const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
+        const double g = d * dt;
+        const double dTv = wide_time_deriv(P, sb, ww, lane, t, ww.r0, a0);
+        const double eig = wide_build_lu(P, sb, ww, lane, ww.r0, a0, g);
+        ++n_jac;
+        if (autosw) eigen_est = eig;
+        const double f0 = KS(0);
+        const double k1 = wide_lusolve(ww, lane, ns, fma(g, dTv, f0));
+        const double f1 = wide_rhs(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as); ++n_rhs;
+        const double k2 = wide_lusolve(ww, lane, ns, f1 - k1) + k1;
+        un = fma(dt, k2, u);
+        const double f2 = wide_rhs(P, sb, ww, lane, my_mw, t + dt, un, as); ++n_rhs;
+        const double k3 = wide_lusolve(ww, lane, ns, f2 - e32 * (k2 - f1) - 2.0 * (k1 - f0) + dt * dTv);
+        e = dt / 6.0 * (k1 - 2.0 * k2 + k3);
+        KS(1) = k1; KS(2) = k2; KS(5) = f2;
+      }
+      const double EEst = wrms(e, u, un);
+      const double b1 = (autosw && rosen) ? P.beta1_ros : P.beta1, b2 = (autosw && rosen) ? P.beta2_ros : P.beta2;
+      double q11, q;
+      if (EEst == 0.0) { q11 = 0.0; q = P.inv_qmax; }
+      else {
+        q11 = lean_pow(EEst, b1);
+        q = jmax(P.inv_qmax, jmin(P.inv_qmin, q11 / lean_pow(qold, b2) / P.gamma));
+      }
+      dt_last = dt;
+      if (EEst <= 1.0) {
+        ++n_acc;
+        qold = jmax(EEst, 1e-4);
+        const double dtnew = dt / q, tprev = t;
+        t = snap_t(t + dt, tend);
+        while (isave < nsave) {
+          const double tsv = __ldg(P.saveat + isave);
+          if (!(tsv <= t)) break;
+          if (tsv == t) save(isave, un);
+          else {
+            const double th = (tsv - tprev) / dt;
+            if (!rosen) {
+              double acc = 0.0;
+#pragma unroll
+              for (int s = 0; s < 7; ++s) {
+                const double bs = th * (tsc::R[s][0] + th * (tsc::R[s][1] + th * (tsc::R[s][2] + th * tsc::R[s][3])));
+                acc = s == 0 ? bs * KS(0) : fma(bs, KS(s), acc);
+              }
+              save(isave, fma(dt, acc, u));
+            } else {
+              const double d = 1.0 / (2.0 + 1.4142135623730951);
+              const double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
+              save(isave, u + dt * (c1 * KS(1) + c2 * KS(2)));
+            }
+          }
+          ++isave;
+        }
+        u = un;
+        KS(0) = rosen ? KS(5) : KS(6);  // FSAL
+        a0 = as;
+        __syncwarp();
+        ww.r0[lane] = ww.r[lane];
+        dt = jmin(dtnew, dtmax);
+      } else {
+        ++n_rej;
+        dt = dt / jmin(P.inv_qmin, q11 / P.gamma);
+      }
+    }
+    if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+    if (mypred && my_obs >= 0)
+      for (int ks = isave; ks < P.n_save; ++ks) mypred[my_obs + P.n_obs * ks] = 0.0;
+    if (lane == 0) {
+      if (n_saved) n_saved[traj] = isave;
+      if (retcode) retcode[traj] = ret;
+      if (stats) {
+        crnn_stats s;
+        s.n_accept = n_acc; s.n_reject = n_rej; s.n_rhs = n_rhs; s.n_jac = n_jac;
+        s.t_reached = t; s.dt_last = dt_last;
+        stats[traj] = s;
+      }
+    }
+    __syncwarp();
+  }
+#undef KS
+}
+
+}  // namespace crnn

@@ -28,6 +28,11 @@ class CRNNModel:
     ub: float = 10.0
     out_scale: np.ndarray | None = None
     gas_R: float = GAS_R
+    # F2 only (HyChem/crnn_pyrolysis_mass.jl:58,103-104): molar masses and the T(t), P(t) tables
+    mw: np.ndarray | None = None
+    tab_t: np.ndarray | None = None
+    tab_T: np.ndarray | None = None
+    tab_P: np.ndarray | None = None
 
     def __post_init__(self):
         self.w_in = np.asarray(self.w_in, dtype=np.float64)
@@ -45,6 +50,18 @@ class CRNNModel:
             raise ValueError("F1 needs n_in == n_species + 1 (Arrhenius row)")
         if self.out_scale is not None and self.out_scale.shape[0] != ns:
             raise ValueError("out_scale must have n_species entries")
+        if self.rhs_kind == _abi.RHS_F2:
+            if n_in != ns + 2:
+                raise ValueError("F2 needs n_in == n_species + 2 (Arrhenius and log T rows)")
+            if self.mw is None or self.tab_t is None or self.tab_T is None or self.tab_P is None:
+                raise ValueError("F2 needs mw and the tab_t / tab_T / tab_P tables")
+            self.mw = np.ascontiguousarray(self.mw, dtype=np.float64).reshape(-1)
+            self.tab_t, self.tab_T, self.tab_P = (np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+                                                  for a in (self.tab_t, self.tab_T, self.tab_P))
+            if self.mw.shape[0] != ns or not (self.tab_t.size == self.tab_T.size == self.tab_P.size >= 2):
+                raise ValueError("F2: mw must have n_species entries and the tables equal length >= 2")
+            if np.any(np.diff(self.tab_t) <= 0):
+                raise ValueError("F2: tab_t must be strictly ascending")
 
     @property
     def n_species(self) -> int:
@@ -84,6 +101,10 @@ class CRNNModel:
         m.lb, m.ub, m.gas_R = float(self.lb), float(self.ub), float(self.gas_R)
         m.w_in, m.w_b, m.w_out = dptr(keep[0]), dptr(keep[1]), dptr(keep[2])
         m.out_scale = dptr(keep[3])
+        if self.rhs_kind == _abi.RHS_F2:
+            keep += [self.mw, self.tab_t, self.tab_T, self.tab_P]
+            m.n_tab = int(self.tab_t.size)
+            m.mw, m.tab_t, m.tab_T, m.tab_P = dptr(self.mw), dptr(self.tab_t), dptr(self.tab_T), dptr(self.tab_P)
         return m, keep
 
 

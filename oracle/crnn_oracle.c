@@ -27,6 +27,8 @@
 #include <string.h>
 #include "../include/crnn_b200.h"
 
+int crnn_oracle_rhs_t(const crnn_model* m, double t, const double* u, double* du, double* J, double* dT);
+
 #define MAXN 64 /* max n_state */
 #define MAXR 64 /* max n_reac  */
 
@@ -38,11 +40,29 @@ typedef struct {
   int nw;
   const double* seed; /* [nw, np] col-major */
   double qmin, qmax, gamma, beta1, beta2;
+  double beta1_alg[2], beta2_alg[2]; /* AutoTsit5: controller exponents of the CURRENT algorithm (0 Tsit5, 1 Rosenbrock23) */
   int order;
 } ctx_t;
 
+#define GAS_RU 8.31446261815324e3 /* HyChem/crnn_pyrolysis_mass.jl:108 */
+
+/* Interpolations.LinearInterpolation(tab_t, tab_v)(t) and its slope (HyChem/crnn_pyrolysis_mass.jl:103-104).
+ * The segment is the last one whose left knot is <= t (the right-most segment at t == tab_t[end]). */
+static void tab_lookup(const crnn_model* m, double t, double* T, double* P, double* Tdot, double* Pdot) {
+  int n = m->n_tab, lo = 0, hi = n - 1;
+  while (hi - lo > 1) { int mid = (lo + hi) / 2; if (m->tab_t[mid] <= t) lo = mid; else hi = mid; }
+  double h = m->tab_t[lo + 1] - m->tab_t[lo], w = (t - m->tab_t[lo]) / h;
+  *T = m->tab_T[lo] + w * (m->tab_T[lo + 1] - m->tab_T[lo]);
+  *P = m->tab_P[lo] + w * (m->tab_P[lo + 1] - m->tab_P[lo]);
+  *Tdot = (m->tab_T[lo + 1] - m->tab_T[lo]) / h;
+  *Pdot = (m->tab_P[lo + 1] - m->tab_P[lo]) / h;
+}
+
 typedef struct {
-  double x[MAXN], dx[MAXN], d2x[MAXN], r[MAXR];
+  double x[MAXN + 2], dx[MAXN + 2], d2x[MAXN + 2], r[MAXR];
+  /* F2 only */
+  double chi[MAXN], chiC[MAXN], Y[MAXN], wdot[MAXN];
+  double rho, S, T, P, Tdot, Pdot;
 } rhs_cache;
 
 /* Julia's min/max propagate NaN (C fmin/fmax drop it): a NaN RHS must surface as a NaN dt. */
@@ -56,22 +76,46 @@ static inline double clampd(double v, double lo, double hi) {
 
 /* RHS value.  F0: case1/case1.jl:80-83, case3/case3.jl:162-166,
  * robertson/rober_crnn.jl:113-116.  F1: case2/case2.jl:113-118.
+ * F2: HyChem/crnn_pyrolysis_mass.jl:107-114,121-131 (non-autonomous through T(t), P(t)).
  * Also returns x = W_in-side inputs, dx = dx_i/du_i, d2x, r = exp(z). */
-static void rhs_value(const ctx_t* c, const double* u, double* du, rhs_cache* k) {
+static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs_cache* k) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  for (int i = 0; i < ns; ++i) {
-    double uc = clampd(u[i], m->lb, m->ub);
-    int inside = (u[i] >= m->lb) && (u[i] <= m->ub); /* dual clamp passes derivative 1 on the closed interval */
-    k->x[i] = log(uc);
-    k->dx[i] = inside ? 1.0 / uc : 0.0;
-    k->d2x[i] = inside ? -1.0 / (uc * uc) : 0.0;
-  }
-  if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE) {
-    double T = u[ns];
-    k->x[ns] = -1.0 / (m->gas_R * T); /* inv_R / u[end], case2.jl:113,116 */
-    k->dx[ns] = 1.0 / (m->gas_R * T * T);
-    k->d2x[ns] = -2.0 / (m->gas_R * T * T * T);
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) {
+    tab_lookup(m, t, &k->T, &k->P, &k->Tdot, &k->Pdot);
+    double S = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      k->Y[i] = clampd(u[i], m->lb, m->ub);               /* Y = clamp.(u, lb, 10), :124 */
+      k->chi[i] = (u[i] >= m->lb && u[i] <= m->ub) ? 1.0 : 0.0;
+      S += k->Y[i] / m->mw[i];
+    }
+    k->S = S;
+    k->rho = k->P / (GAS_RU * k->T * S);                   /* Y2density, :107-109 */
+    for (int i = 0; i < ns; ++i) {
+      double C = k->rho * (k->Y[i] / m->mw[i]) * 1e3;      /* Y2C, :112-114 */
+      double Cc = clampd(C, m->lb, m->ub);
+      k->chiC[i] = (C >= m->lb && C <= m->ub) ? 1.0 : 0.0;
+      k->x[i] = log(Cc);
+      k->dx[i] = k->chiC[i] * k->chi[i] / k->Y[i];         /* d x_i / d u_i at fixed density */
+      k->d2x[i] = 0.0;
+    }
+    k->x[ns] = -1.0 / m->gas_R / k->T;                     /* - 1 / R / T, :128 */
+    k->x[ns + 1] = log(k->T);
+    k->dx[ns] = k->dx[ns + 1] = 0.0; k->d2x[ns] = k->d2x[ns + 1] = 0.0;
+  } else {
+    for (int i = 0; i < ns; ++i) {
+      double uc = clampd(u[i], m->lb, m->ub);
+      int inside = (u[i] >= m->lb) && (u[i] <= m->ub); /* dual clamp passes derivative 1 on the closed interval */
+      k->x[i] = log(uc);
+      k->dx[i] = inside ? 1.0 / uc : 0.0;
+      k->d2x[i] = inside ? -1.0 / (uc * uc) : 0.0;
+    }
+    if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE) {
+      double T = u[ns];
+      k->x[ns] = -1.0 / (m->gas_R * T); /* inv_R / u[end], case2.jl:113,116 */
+      k->dx[ns] = 1.0 / (m->gas_R * T * T);
+      k->d2x[ns] = -2.0 / (m->gas_R * T * T * T);
+    }
   }
   for (int j = 0; j < nr; ++j) {
     double z = m->w_b[j];
@@ -81,9 +125,20 @@ static void rhs_value(const ctx_t* c, const double* u, double* du, rhs_cache* k)
   for (int i = 0; i < ns; ++i) {
     double s = 0.0;
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * k->r[j];
+    if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) {
+      k->wdot[i] = s;
+      s = s * m->mw[i] / k->rho;                          /* wdot * l_MW / density, :130 */
+    }
     du[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) du[i] = 0.0; /* vcat(..., 0.f0), case2.jl:117 */
+}
+
+/* F2: the density couples every species: d log(rho) = -sum_l chi_l du_l / MW_l / S. */
+static double f2_dlogrho(const ctx_t* c, const rhs_cache* k, const double* S) {
+  double sd = 0.0;
+  for (int l = 0; l < c->ns; ++l) sd += k->chi[l] * S[l] / c->m->mw[l];
+  return -sd / k->S;
 }
 
 /* Directional derivative of f along (S for u, seed column for the weights):
@@ -92,10 +147,13 @@ static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
                          const double* sd /* seed column or NULL */, double* dS) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
+  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const double rr = f2 ? f2_dlogrho(c, k, S) : 0.0;
   double zq[MAXR];
   for (int j = 0; j < nr; ++j) {
     double zd = 0.0;
-    for (int i = 0; i < nin; ++i) zd += m->w_in[i + nin * j] * (S[i] * k->dx[i]);
+    if (f2) { for (int i = 0; i < ns; ++i) zd += m->w_in[i + nin * j] * (k->chiC[i] * rr + S[i] * k->dx[i]); }
+    else { for (int i = 0; i < nin; ++i) zd += m->w_in[i + nin * j] * (S[i] * k->dx[i]); }
     if (sd) {
       for (int i = 0; i < nin; ++i) zd += sd[i + nin * j] * k->x[i];
       zd += sd[nin * nr + j];
@@ -107,15 +165,39 @@ static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * zq[j];
     if (sd)
       for (int j = 0; j < nr; ++j) s += sd[nin * nr + nr + i + ns * j] * k->r[j];
+    if (f2) s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
     dS[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) dS[i] = 0.0;
 }
 
+/* d f / d t at fixed u (Rosenbrock23's dT term; non-zero only for the non-autonomous F2). */
+static void rhs_time_deriv(const ctx_t* c, const rhs_cache* k, double* dT) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  for (int i = 0; i < c->n; ++i) dT[i] = 0.0;
+  if (m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP) return;
+  const double rr = k->Pdot / k->P - k->Tdot / k->T; /* d log(rho) / dt */
+  double zq[MAXR];
+  for (int j = 0; j < nr; ++j) {
+    double zd = 0.0;
+    for (int i = 0; i < ns; ++i) zd += m->w_in[i + nin * j] * (k->chiC[i] * rr);
+    zd += m->w_in[ns + nin * j] * (k->Tdot / (m->gas_R * k->T * k->T));
+    zd += m->w_in[ns + 1 + nin * j] * (k->Tdot / k->T);
+    zq[j] = k->r[j] * zd;
+  }
+  for (int i = 0; i < ns; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * zq[j];
+    s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
+    dT[i] = m->out_scale ? s * m->out_scale[i] : s;
+  }
+}
+
 /* f on all columns: Y[col][n] -> dY[col][n]; col 0 is the value. */
-static void eval_cols(const ctx_t* c, const double* Y, double* dY, rhs_cache* k) {
+static void eval_cols(const ctx_t* c, double t, const double* Y, double* dY, rhs_cache* k) {
   int n = c->n;
-  rhs_value(c, Y, dY, k);
+  rhs_value(c, t, Y, dY, k);
   for (int col = 1; col < c->ncol; ++col)
     rhs_sens_col(c, k, Y + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, dY + col * n);
 }
@@ -125,6 +207,15 @@ static void jac_value(const ctx_t* c, const rhs_cache* k, double* J) {
   const crnn_model* m = c->m;
   int n = c->n, ns = c->ns, nin = c->nin, nr = c->nr;
   memset(J, 0, sizeof(double) * n * n);
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) { /* column l = directional derivative along e_l (density coupling) */
+    double e[MAXN], col[MAXN];
+    for (int l = 0; l < n; ++l) {
+      memset(e, 0, sizeof(e)); e[l] = 1.0;
+      rhs_sens_col(c, k, e, NULL, col);
+      for (int i = 0; i < n; ++i) J[i * n + l] = col[i];
+    }
+    return;
+  }
   for (int i = 0; i < ns; ++i)
     for (int l = 0; l < nin; ++l) {
       double s = 0.0;
@@ -218,7 +309,7 @@ static double initdt_norm(const ctx_t* c, const double* V, const double* U0, dou
 /* Hairer-Wanner initial step as OrdinaryDiffEq's ode_determine_initdt
  * (SURVEY App. C.3).  F0 = f(U0) on all columns (in), two RHS evaluations
  * are charged to the trajectory (f0 is shared with the first stage). */
-static double initial_dt(const ctx_t* c, const double* U0, const double* F0, double tspan_len,
+static double initial_dt(const ctx_t* c, double t0, const double* U0, const double* F0, double tspan_len,
                          double* work /* 2*ncol*n */, rhs_cache* k) {
   int n = c->n, tot = c->ncol * n;
   double d0 = initdt_norm(c, U0, U0, 1.0);
@@ -227,7 +318,7 @@ static double initial_dt(const ctx_t* c, const double* U0, const double* F0, dou
   dt0 = jmin(dt0, tspan_len);
   double* U1 = work; double* F1 = work + tot;
   for (int q = 0; q < tot; ++q) U1[q] = U0[q] + dt0 * F0[q];
-  eval_cols(c, U1, F1, k);
+  eval_cols(c, t0 + dt0, U1, F1, k);
   for (int q = 0; q < tot; ++q) F1[q] -= F0[q];
   double d2 = initdt_norm(c, F1, U0, 1.0) / dt0;
   double dm = jmax(d1, d2);
@@ -344,15 +435,39 @@ typedef struct {
   crnn_stats st;
 } traj_result;
 
-/* One trajectory, Tsit5 or Rosenbrock23, value + optional forward-sensitivity
+/* PI controller with explicit exponents (AutoTsit5 swaps them with the algorithm, see solve_one). */
+static double pi_q_b(const ctx_t* c, double b1, double b2, double EEst, double qold, double* q11) {
+  if (EEst == 0.0) { *q11 = 0.0; return 1.0 / c->qmax; }
+  *q11 = pow(EEst, b1);
+  double q = *q11 / pow(qold, b2);
+  return jmax(1.0 / c->qmax, jmin(1.0 / c->qmin, q / c->gamma));
+}
+
+static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+
+/* One trajectory, Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23), value + optional forward-sensitivity
  * columns.  Mirrors OrdinaryDiffEq's solve! loop (loopheader!/perform_step!/
  * loopfooter!), saveat by dense interpolation without stopping at save points
- * (SURVEY App. C.2 "saveat semantics"). */
+ * (SURVEY App. C.2 "saveat semantics").
+ *
+ * AutoTsit5(Rosenbrock23()) (case2/case2.jl:26, HyChem/crnn_pyrolysis_mass.jl:29) = CompositeAlgorithm with
+ * OrdinaryDiffEq's AutoSwitch choice function [UPSTREAM-RECALL of composite_algs.jl / composite_perform_step.jl,
+ * defaults maxstiffstep=10, maxnonstiffstep=3, nonstifftol=stifftol=9/10, dtfac=2, stiffalgfirst=false]:
+ *   - evaluated in loopheader!, i.e. before EVERY step attempt except the first, on the dt the controller just
+ *     proposed: stiffness = |eigen_est * dt / 3.5068| (Tsit5's stability size), stiff iff > 9/10;
+ *   - eigen_est after a Tsit5 step = ||k7 - k6|| / ||u_{n+1} - g6|| (g6 = the stage-6 state; Hairer II p.22),
+ *     after a Rosenbrock23 step = opnorm(J, Inf) (value part);
+ *   - a signed run-length counter: more than 10 consecutive stiff verdicts under Tsit5 -> Rosenbrock23 with
+ *     dt *= 2; more than 3 consecutive non-stiff verdicts under Rosenbrock23 -> Tsit5 with dt /= 2;
+ *   - on a switch the new algorithm re-initialises: f(u_n, t_n) is re-evaluated (one RHS call) and the PI
+ *     exponents become those of the new algorithm's order (reset_alg_dependent_opts!).
+ * Not modelled: do_error_check (skipping check_error! while stiffness is being counted). */
 static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sink* sk, traj_result* res) {
   const crnn_opts* o = c->o;
   const int n = c->n, ncol = c->ncol, tot = n * ncol;
-  const int rosen = (o->alg == CRNN_ALG_ROSENBROCK23);
-  double* buf = (double*)calloc((size_t)tot * 14 + (size_t)n * n * 2 + 8 * n, sizeof(double));
+  const int autosw = (o->alg == CRNN_ALG_AUTO_TSIT5_ROS23);
+  int rosen = (o->alg == CRNN_ALG_ROSENBROCK23);
+  double* buf = (double*)calloc((size_t)tot * 14 + (size_t)n * n * 2 + 9 * n, sizeof(double));
   double* U = buf;              /* current state, all columns */
   double* Un = U + tot;         /* proposed state */
   double* K[7];
@@ -363,6 +478,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
   double* Jm = W2 + 2 * tot;    /* n*n */
   double* LU = Jm + n * n;      /* n*n */
   double* vtmp = LU + n * n;    /* 8n */
+  double* dTv = vtmp + 8 * n;   /* n: df/dt */
   int piv[MAXN];
   rhs_cache kc, kc0;
 
@@ -374,16 +490,29 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
   const double dtmin = fmax(nextafter(fabs(t0), INFINITY) - fabs(t0), nextafter(fabs(tend), INFINITY) - fabs(tend));
   double t = t0, dt, qold = 1e-4;
   int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
+  double eigen_est = 0.0; int sw_count = 0;
   memset(&res->st, 0, sizeof(res->st));
 
-  eval_cols(c, U, K[0], &kc); res->st.n_rhs++;
+  eval_cols(c, t0, U, K[0], &kc); res->st.n_rhs++;
   kc0 = kc;
-  dt = initial_dt(c, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
+  dt = initial_dt(c, t0, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
   /* save_start: t0 is saved iff it is in saveat */
   while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
 
   while (t < tend) {
     ++iter;
+    if (autosw && iter > 1) { /* AutoSwitch choice function (see header comment) */
+      const double stiffness = fabs(eigen_est * dt / 3.5068);
+      const int stiff = stiffness > 0.9;
+      sw_count = stiff ? (sw_count < 0 ? 1 : sw_count + 1) : (sw_count > 0 ? -1 : sw_count - 1);
+      int want = rosen;
+      if (!rosen && sw_count > 10) { dt = dt * 2.0; want = 1; }
+      else if (rosen && sw_count < -3) { dt = dt / 2.0; want = 0; }
+      if (want != rosen) {
+        rosen = want;
+        eval_cols(c, t, U, K[0], &kc0); res->st.n_rhs++; /* initialize!(integrator, new cache): fsalfirst = f(uprev) */
+      }
+    }
     /* check_error! order: DtNaN, MaxIters, DtLessThanMin, Unstable */
     if (isnan(dt)) { ret = CRNN_RET_DTNAN; break; }
     if (iter > o->maxiters) { ret = CRNN_RET_MAXITERS; break; }
@@ -400,20 +529,35 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
           for (int j = 1; j < s; ++j) acc += TS_A[s][j] * K[j][q];
           Y[q] = U[q] + dt * acc;
         }
-        eval_cols(c, Y, K[s], &kc); res->st.n_rhs++;
+        eval_cols(c, t + TS_C[s] * dt, Y, K[s], &kc); res->st.n_rhs++;
       }
       for (int q = 0; q < tot; ++q) {
         double acc = TS_BT[0] * K[0][q];
         for (int j = 1; j < 7; ++j) acc += TS_BT[j] * K[j][q];
         E[q] = dt * acc;
       }
+      if (autosw) { /* TMP still holds g6 */
+        const int nc = o->err_norm_includes_sens ? ncol : 1;
+        double num = 0.0, den = 0.0;
+        for (int q = 0; q < nc * n; ++q) {
+          double a = K[6][q] - K[5][q], b = Un[q] - TMP[q];
+          num += a * a; den += b * b;
+        }
+        eigen_est = sqrt(num / (nc * n)) / sqrt(den / (nc * n));
+      }
     } else {
       /* Rosenbrock23 = Shampine-Reichelt ode23s.  K[0]=f0
        * (FSAL), K[1]=k1, K[2]=k2, K[3]=k3, K[4]=f1, K[5]=f2. */
       const double d = 1.0 / (2.0 + sqrt(2.0)), e32 = 6.0 + sqrt(2.0);
       const double g = d * dt;
-      /* kc0 holds the cache at U (value); J = df/du(U) */
+      /* kc0 holds the cache at U (value); J = df/du(U), dT = df/dt(U) */
       jac_value(c, &kc0, Jm); res->st.n_jac++;
+      rhs_time_deriv(c, &kc0, dTv);
+      if (autosw) {
+        double best = 0.0;
+        for (int i = 0; i < n; ++i) { double rs = 0.0; for (int l = 0; l < n; ++l) rs += fabs(Jm[i * n + l]); if (rs > best) best = rs; }
+        eigen_est = best; /* opnorm(J, Inf) */
+      }
       for (int i = 0; i < n; ++i)
         for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - g * Jm[i * n + l];
       lu_factor(LU, piv, n);
@@ -421,6 +565,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       for (int col = 0; col < ncol; ++col) {
         double* k1 = K[1] + col * n;
         for (int i = 0; i < n; ++i) k1[i] = K[0][col * n + i];
+        if (col == 0) { for (int i = 0; i < n; ++i) k1[i] += g * dTv[i]; }
         if (col > 0) { /* + gamma * dJ * k1(value) */
           djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[1], vtmp);
           for (int i = 0; i < n; ++i) k1[i] += g * vtmp[i];
@@ -428,7 +573,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
         lu_solve(LU, piv, n, k1);
       }
       for (int q = 0; q < tot; ++q) TMP[q] = U[q] + 0.5 * dt * K[1][q];
-      eval_cols(c, TMP, K[4], &kc); res->st.n_rhs++;
+      eval_cols(c, t + 0.5 * dt, TMP, K[4], &kc); res->st.n_rhs++;
       /* k2 = W\(f1 - k1) + k1 */
       for (int i = 0; i < n; ++i) vtmp[n + i] = 0.0;
       for (int col = 0; col < ncol; ++col) {
@@ -445,7 +590,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
         }
       }
       for (int q = 0; q < tot; ++q) Un[q] = U[q] + dt * K[2][q];
-      eval_cols(c, Un, K[5], &kc); res->st.n_rhs++;
+      eval_cols(c, t + dt, Un, K[5], &kc); res->st.n_rhs++;
       for (int col = 0; col < ncol; ++col) {
         double* k3 = K[3] + col * n;
         for (int i = 0; i < n; ++i) {
@@ -453,6 +598,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
           k3[i] = K[5][q] - e32 * (K[2][q] - K[4][q]) - 2.0 * (K[1][q] - K[0][q]);
         }
         if (col == 0) {
+          for (int i = 0; i < n; ++i) k3[i] += dt * dTv[i];
           lu_solve(LU, piv, n, k3);
         } else {
           djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[3], vtmp);
@@ -464,7 +610,8 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
     }
 
     double EEst = err_norm(c, E, U, Un);
-    double q11, q = pi_q(c, EEst, qold, &q11);
+    const double b1 = autosw ? c->beta1_alg[rosen] : c->beta1, b2 = autosw ? c->beta2_alg[rosen] : c->beta2;
+    double q11, q = pi_q_b(c, b1, b2, EEst, qold, &q11);
     res->st.dt_last = dt;
     if (EEst <= 1.0) {
       res->st.n_accept++;
@@ -499,7 +646,8 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       }
       memcpy(U, Un, sizeof(double) * tot);
       if (!rosen) memcpy(K[0], K[6], sizeof(double) * tot);
-      else { memcpy(K[0], K[5], sizeof(double) * tot); kc0 = kc; }
+      else memcpy(K[0], K[5], sizeof(double) * tot);
+      kc0 = kc; /* cache of the last evaluation = at the new U (stage 7 / f2) */
       dt = jmin(dtnew, dtmax);
     } else {
       res->st.n_reject++;
@@ -568,9 +716,10 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
   double t = t0, dt, qold = 1e-4, eta_old = 1.0;
   int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
   memset(&res->st, 0, sizeof(res->st));
-  rhs_value(c, U, F0, &kc); res->st.n_rhs++;
+  static const double KC_C[6] = {0.0, 0.5, 83.0 / 250.0, 31.0 / 50.0, 17.0 / 20.0, 1.0};
+  rhs_value(c, t0, U, F0, &kc); res->st.n_rhs++;
   kc0 = kc;
-  dt = initial_dt(c, U, F0, dtmax, W2, &kc); res->st.n_rhs++;
+  dt = initial_dt(c, t0, U, F0, dtmax, W2, &kc); res->st.n_rhs++;
   while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
 
   while (t < tend) {
@@ -600,7 +749,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
         double ndz_prev = 0.0, eta = pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
         for (int it = 1; it <= 10; ++it) {
           for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
-          rhs_value(c, Yk, DZ, &kc); res->st.n_rhs++;
+          rhs_value(c, t + KC_C[s] * dt, Yk, DZ, &kc); res->st.n_rhs++;
           for (int i = 0; i < n; ++i) DZ[i] = dt * DZ[i] - Z[s][i];
           lu_solve(LU, piv, n, DZ);
           double ndz = wrms(c, DZ, U, Yk);
@@ -620,7 +769,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
           if (refreshed || has_nan(Z[s], n)) break;
           refreshed = 1;
           for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
-          rhs_value(c, Yk, DZ, &kc); res->st.n_rhs++;
+          rhs_value(c, t + KC_C[s] * dt, Yk, DZ, &kc); res->st.n_rhs++;
           jac_value(c, &kc, Jm); res->st.n_jac++;
           for (int i = 0; i < n; ++i)
             for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - KC_G * dt * Jm[i * n + l];
@@ -646,7 +795,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
       qold = jmax(EEst, 1e-4);
       double dtnew = dt / q, tprev = t;
       t = snap_t(t + dt, tend);
-      rhs_value(c, Un, F1, &kc); res->st.n_rhs++;
+      rhs_value(c, t, Un, F1, &kc); res->st.n_rhs++;
       while (isave < nsave && o->saveat[isave] <= t) {
         double ts = o->saveat[isave];
         if (ts == t) emit_save(c, sk, isave, Un);
@@ -684,10 +833,11 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
 typedef struct { double t, dt; } rec_hdr;
 
 static void adj_rhs(const ctx_t* c, const double* u, const double* lam, double* dlam, double* gw /* nw integrand or NULL */) {
+  const double t_unused = c->o->t0; /* F0/F1 are autonomous; F2 is rejected for the adjoint in check_dims */
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
   rhs_cache k; double du[MAXN], g[MAXR];
-  rhs_value(c, u, du, &k);
+  rhs_value(c, t_unused, u, du, &k);
   for (int j = 0; j < nr; ++j) {
     double s = 0.0;
     for (int i = 0; i < ns; ++i) s += m->w_out[i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * lam[i];
@@ -732,9 +882,9 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
   double t = t0, dt, qold = 1e-4;
   int isave = 0, iter = 0, ret = CRNN_RET_DEFAULT;
   memset(&res->st, 0, sizeof(res->st));
-  rhs_value(c, U, K[0], &kc); res->st.n_rhs++;
+  rhs_value(c, t0, U, K[0], &kc); res->st.n_rhs++;
   { /* initial_dt wants ncol-strided arrays: ncol == 1 here */
-    dt = initial_dt(c, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
+    dt = initial_dt(c, t0, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
   }
   while (isave < nsave && o->saveat[isave] <= t0) { memcpy(ysave + (size_t)isave * n, U, sizeof(double) * n); ++isave; }
   /* ---------------- forward (identical to solve_one's Tsit5 value path) ---------------- */
@@ -753,7 +903,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
         for (int j = 1; j < s; ++j) acc += TS_A[s][j] * K[j][q];
         Y[q] = U[q] + dt * acc;
       }
-      rhs_value(c, Y, K[s], &kc); res->st.n_rhs++;
+      rhs_value(c, t + TS_C[s] * dt, Y, K[s], &kc); res->st.n_rhs++;
     }
     for (int q = 0; q < n; ++q) {
       double acc = TS_BT[0] * K[0][q];
@@ -898,7 +1048,6 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
           double h = jmin(bdt, cur - tlo);
           if (!(h > 0.0)) break;
           /* stages at times cur - c_s h */
-          static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
           memset(GS, 0, sizeof(double) * nw);
           for (int s = 0; s < 7; ++s) {
             double* Y = (s == 6) ? Ln : TMP;
@@ -941,19 +1090,28 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
   c->nw = m->n_reac * (m->n_in + 1 + m->n_species);
   c->seed = seed; c->ncol = 1 + np;
-  c->order = (o->alg == CRNN_ALG_TSIT5) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
+  c->order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
   c->qmin = o->qmin > 0 ? o->qmin : 0.2;
   c->qmax = o->qmax > 0 ? o->qmax : 10.0;
   c->gamma = o->gamma > 0 ? o->gamma : 0.9;
   c->beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * c->order);
   c->beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * c->order);
+  for (int a = 0; a < 2; ++a) {
+    const double ord = a ? 2.0 : 5.0;
+    c->beta2_alg[a] = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * ord);
+    c->beta1_alg[a] = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * ord);
+  }
 }
 
 static int check_dims(const crnn_model* m, const crnn_opts* o) {
-  if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state) return CRNN_ERR_BAD_ARG;
-  if (m->rhs_kind == CRNN_RHS_F0 && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
+  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state + (f2 ? 2 : 0)) return CRNN_ERR_BAD_ARG;
+  if ((m->rhs_kind == CRNN_RHS_F0 || f2) && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE && m->n_species + 1 != m->n_state) return CRNN_ERR_BAD_ARG;
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED;
+  if (f2 && (!m->mw || !m->tab_t || !m->tab_T || !m->tab_P || m->n_tab < 2)) return CRNN_ERR_BAD_ARG;
+  if (f2 && (m->tab_t[0] > o->t0 || m->tab_t[m->n_tab - 1] < o->t1)) return CRNN_ERR_BAD_ARG;
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4 &&
+      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23) return CRNN_ERR_UNSUPPORTED;
   return CRNN_OK;
 }
 
@@ -994,6 +1152,8 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
+  /* F2: forward sensitivities ride Tsit5 only (the nested-dual dJ terms of Rosenbrock23 are not restated for F2) */
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (adjoint || o->alg != CRNN_ALG_TSIT5)) return CRNN_ERR_UNSUPPORTED;
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));
@@ -1052,11 +1212,17 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
 
 /* Exposed pieces for unit tests (RHS / Jacobian / J*v / dJ*v). */
 int crnn_oracle_rhs(const crnn_model* m, const double* u, double* du, double* J /* n*n row-major or NULL */) {
+  return crnn_oracle_rhs_t(m, 0.0, u, du, J, NULL);
+}
+
+/* non-autonomous form: f(u, t), J = df/du, dT = df/dt */
+int crnn_oracle_rhs_t(const crnn_model* m, double t, const double* u, double* du, double* J, double* dT) {
   crnn_opts o; memset(&o, 0, sizeof(o));
   ctx_t c; make_ctx(&c, m, &o, NULL, 0);
   rhs_cache k;
-  rhs_value(&c, u, du, &k);
+  rhs_value(&c, t, u, du, &k);
   if (J) jac_value(&c, &k, J);
+  if (dT) rhs_time_deriv(&c, &k, dT);
   return CRNN_OK;
 }
 
@@ -1065,7 +1231,7 @@ int crnn_oracle_rhs_sens(const crnn_model* m, const double* u, const double* S, 
   crnn_opts o; memset(&o, 0, sizeof(o));
   ctx_t c; make_ctx(&c, m, &o, NULL, 0);
   rhs_cache k; double du[MAXN];
-  rhs_value(&c, u, du, &k);
+  rhs_value(&c, m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? m->tab_t[0] : 0.0, u, du, &k);
   rhs_sens_col(&c, &k, S, seedcol, dS);
   if (v && dJv) djac_vec(&c, &k, S, seedcol, v, dJv);
   (void)jac_vec;

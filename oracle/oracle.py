@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib.crnn_oracle_rhs.restype = C.c_int
         _lib.crnn_oracle_rhs.argtypes = [C.POINTER(CModel), C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.crnn_oracle_rhs_t.restype = C.c_int
+        _lib.crnn_oracle_rhs_t.argtypes = [C.POINTER(CModel), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.crnn_oracle_rhs_sens.restype = C.c_int
         _lib.crnn_oracle_rhs_sens.argtypes = [C.POINTER(CModel)] + [C.c_void_p] * 6
         _lib.crnn_oracle_tsit5_tableau.restype = None
@@ -118,6 +120,16 @@ def rhs(model, u, want_jac=False):
     J = np.zeros((model.n_state, model.n_state)) if want_jac else None
     lib().crnn_oracle_rhs(C.byref(cm), _p(u), _p(du), _p(J))
     return (du, J) if want_jac else du
+
+
+def rhs_t(model, t, u):
+    """non-autonomous form: (f(u, t), J = df/du, dT = df/dt)"""
+    cm, k = model.to_c()
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    n = model.n_state
+    du = np.zeros(n); J = np.zeros((n, n)); dT = np.zeros(n)
+    lib().crnn_oracle_rhs_t(C.byref(cm), float(t), _p(u), _p(du), _p(J), _p(dT))
+    return du, J, dT
 
 
 def rhs_sens(model, u, S, seedcol=None, v=None):

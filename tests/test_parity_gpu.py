@@ -179,9 +179,13 @@ def test_bad_arguments_are_engine_errors(engine, golden):
     pb = make_problem("case2", golden, 4)
     with pytest.raises(EngineError):
         engine.solve_batch(pb["model"], pb["case"].opts(obs_idx=np.array([0, 0])), pb["u0"])
-    with pytest.raises(EngineError):   # Rosenbrock23 forward sensitivities / unsupported dims
+    with pytest.raises(EngineError):   # beyond the generic kernel's 32 state components
+        m = cases.CRNNModel(w_in=np.ones((40, 2)), w_b=np.zeros(2), w_out=np.ones((40, 2)))
+        engine.solve_batch(m, pb["case"].opts(obs_idx=np.arange(40)), np.ones((2, 40)))
+    with pytest.raises(EngineError):   # forward sensitivities exist only for the instantiated dimensions
         m = cases.CRNNModel(w_in=np.ones((4, 2)), w_b=np.zeros(2), w_out=np.ones((4, 2)))
-        engine.solve_batch(m, pb["case"].opts(obs_idx=np.arange(4)), np.ones((2, 4)))
+        engine.loss_grad_batch(m, pb["case"].opts(obs_idx=np.arange(4)), np.zeros((m.n_w, 3)), np.ones((2, 4)),
+                               np.ones((2, 50, 4)), np.ones(4))
 
 
 def test_full_size_properties_case2(engine, golden):

@@ -1,0 +1,144 @@
+"""GPU parity tests of the GENERIC predict path (kernel_wide_solve.cuh: runtime dimensions, F0/F1/F2,
+Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23)) against the CPU oracle, through the C-ABI.
+Bar: step / RHS / Jacobian counts, retcodes and n_saved identical; saved states within the written tolerance."""
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases, synth
+from crnn_b200.model import CRNNModel, SolveOpts
+from oracle import oracle
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+
+ALG = {"tsit5": _abi.ALG_TSIT5, "ros23": _abi.ALG_ROSENBROCK23, "auto": _abi.ALG_AUTO_TSIT5_ROS23}
+YS_HYCHEM = np.array([0.05, 0.01, 0.01, 0.01, 0.02, 0.9, 0.01, 1e-4, 1e-3])
+
+
+def _counts_equal(got, ref):
+    for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+        bad = np.nonzero(got["stats"][k] != ref["stats"][k])[0]
+        assert bad.size == 0, f"{k} differs from the oracle for trajectories {bad[:8]}"
+    assert np.array_equal(got["retcode"], ref["retcode"])
+    assert np.array_equal(got["n_saved"], ref["n_saved"])
+
+
+def _rel_err(got, ref):
+    scale = np.abs(ref).max(axis=(0, 1)) + 1e-300
+    return (np.abs(got - ref) / scale).max()
+
+
+@pytest.mark.parametrize("name,alg,N,tol", [
+    ("case2", "tsit5", 512, 1e-9), ("case2", "ros23", 256, 1e-9), ("case2", "auto", 512, 1e-9),
+    ("case1", "auto", 64, 1e-9), ("robertson", "ros23", 256, 1e-5), ("robertson", "auto", 256, 1e-5)])
+def test_generic_path_matches_oracle_on_the_reference_models(engine, golden, monkeypatch, name, alg, N, tol):
+    """same models as the dimension-specialised kernels, forced through the generic kernel
+    (robertson's trained CRNN, |w_out| up to 800, amplifies rounding: 1e-5)"""
+    monkeypatch.setenv("CRNN_B200_FORCE_WIDE", "1")
+    pb = make_problem(name, golden, N)
+    o = pb["case"].opts(alg=ALG[alg], obs_idx=pb["opts"].obs_idx)
+    got = engine.solve_batch(pb["model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["model"], o, pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < tol
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+
+
+@pytest.mark.parametrize("alg", ["ros23", "auto"])
+def test_autoswitch_on_the_true_robertson_mechanism(engine, golden, alg):
+    """AutoTsit5(Rosenbrock23()) on the stiff generating mechanism (rober_crnn.jl:56-63): starts with Tsit5, detects
+    stiffness, finishes with Rosenbrock23 — counts identical to the oracle, sum(y) conserved"""
+    pb = make_problem("robertson", golden, 256)
+    c = pb["case"]
+    o = c.opts(alg=ALG[alg], pred_clamp=(-np.inf, np.inf))
+    got = engine.solve_batch(pb["true_model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["true_model"], o, pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    att = got["stats"]["n_accept"] + got["stats"]["n_reject"]
+    if alg == "auto":
+        assert (got["stats"]["n_jac"] > 0).all() and (got["stats"]["n_jac"] < att).all()   # both halves ran
+    mass = got["pred"].sum(axis=2)
+    np.testing.assert_allclose(mass, pb["u0"].sum(axis=1)[:, None] * np.ones_like(mass), rtol=2e-3)
+
+
+def test_dimensions_without_a_specialised_kernel(engine):
+    """(n_species, n_reac) = (4, 5) has no template instantiation: solve_batch serves it from the generic kernel"""
+    g = np.random.default_rng(3)
+    ns, nr = 4, 5
+    w_in = np.clip(g.normal(0.6, 0.6, (ns, nr)), 0.0, 2.0)
+    # consumption only of a reaction's own reactants (rate -> 0 with them), production elsewhere: states stay positive
+    w_out = -w_in * 10.0 ** g.normal(0.0, 0.2, (ns, nr)) + np.abs(g.normal(0.0, 0.3, (ns, nr))) * (w_in == 0.0)
+    m = CRNNModel(w_in=w_in, w_b=g.normal(-1.0, 1.0, nr), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=1e-6, ub=10.0,
+                  out_scale=np.array([1.0, 0.5, 2.0, 1.0]))
+    u0 = 0.2 + g.random((200, ns))
+    for alg in ALG.values():
+        o = SolveOpts(saveat=np.linspace(0.0, 5.0, 30), t0=0.0, t1=5.0, alg=alg, abstol=1e-7, reltol=1e-4)
+        got = engine.solve_batch(m, o, u0)
+        ref = oracle.solve_batch(m, o, u0, n_threads=8)
+        _counts_equal(got, ref)
+        # a trajectory whose species cross the lb clamp (a kink of the RHS) amplifies rounding: two CPU builds of
+        # the oracle (with / without FMA contraction) differ by 3e-9 there and by 1e-14 elsewhere
+        smooth = ref["pred"].min(axis=(1, 2)) > 1e-3
+        assert smooth.sum() > 100
+        assert _rel_err(got["pred"][smooth], ref["pred"][smooth]) < 1e-11
+        assert _rel_err(got["pred"], ref["pred"]) < 1e-6
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "ros23", "auto"])
+def test_hychem_f2_matches_oracle(engine, alg):
+    """HyChem/crnn_pyrolysis_mass.jl's RHS (mass fractions, density coupling, tabulated T(t), P(t), non-autonomous
+    Rosenbrock23 with df/dt) with the script's own initialisation p = 0.1 randn, slope 0.1"""
+    N = 384
+    m, _ = cases.hychem_model(cases.hychem_p(0), YS_HYCHEM)
+    o = cases.hychem_opts(alg=ALG[alg])
+    u0 = cases.hychem_u0(N)
+    got = engine.solve_batch(m, o, u0)
+    ref = oracle.solve_batch(m, o, u0, n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    if alg == "auto":   # this problem is mildly stiff (the N2 row is scaled by 90/t_end): the switch happens
+        att = got["stats"]["n_accept"] + got["stats"]["n_reject"]
+        assert (got["stats"]["n_jac"] > 0).all() and (got["stats"]["n_jac"] < att).all()
+
+
+def test_hychem_truncation_device_buffers_and_maxiters(engine):
+    """random time truncation `sample = rand(batch_size:ntotal)` (crnn_pyrolysis_mass.jl:199), torch device
+    buffers, and the maxiters retcode on the generic path"""
+    import torch
+    N = 200
+    m, _ = cases.hychem_model(cases.hychem_p(1), YS_HYCHEM)
+    o = cases.hychem_opts(alg=ALG["auto"])
+    u0 = cases.hychem_u0(N, seed=7)
+    nsu = np.random.default_rng(0).integers(32, 41, N).astype(np.int32)
+    got = engine.solve_batch(m, o, u0, n_save_used=nsu)
+    ref = oracle.solve_batch(m, o, u0, n_save_used=nsu, n_threads=8)
+    _counts_equal(got, ref)
+    assert np.array_equal(got["n_saved"], nsu)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    dev = engine.solve_batch(m, o, torch.from_numpy(u0).cuda(), n_save_used=torch.from_numpy(nsu).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["pred"].cpu().numpy(), got["pred"])
+    o2 = cases.hychem_opts(alg=ALG["auto"], maxiters=12)
+    got2 = engine.solve_batch(m, o2, u0)
+    ref2 = oracle.solve_batch(m, o2, u0, n_threads=8)
+    _counts_equal(got2, ref2)
+    assert (got2["retcode"] == _abi.RET_MAXITERS).all() and (got2["n_saved"] < o2.n_save).all()
+    for i in range(0, N, 37):
+        k = got2["n_saved"][i]
+        np.testing.assert_allclose(got2["pred"][i, :k], ref2["pred"][i, :k], rtol=1e-8, atol=1e-14)
+
+
+def test_generic_path_full_size_properties(engine, golden, monkeypatch):
+    """65 536 case2 trajectories through the generic kernel: equal to the specialised kernel's saved states
+    (two different CUDA formulations of the same algorithm) and every trajectory successful"""
+    pb = make_problem("case2", golden, 64)
+    u0 = synth.make_u0("case2", 65536)
+    fast = engine.solve_batch(pb["model"], pb["opts"], u0)
+    monkeypatch.setenv("CRNN_B200_FORCE_WIDE", "1")
+    wide = engine.solve_batch(pb["model"], pb["opts"], u0)
+    assert (wide["retcode"] == _abi.RET_SUCCESS).all()
+    for k in ("n_accept", "n_reject", "n_rhs"):
+        assert np.array_equal(wide["stats"][k], fast["stats"][k])
+    assert _rel_err(wide["pred"], fast["pred"]) < 1e-9
