@@ -344,13 +344,16 @@ def hychem_u0(N, seed=1234, start=0, ns=9) -> np.ndarray:
     return u0
 
 
-def hychem_p(seed=0, ns=9, nr=10, sigma=0.1, slope=0.1, stiff=0.0):
+def hychem_p(seed=0, ns=9, nr=10, sigma=0.1, slope=0.1, stiff=0.0, lnA_shift=0.0):
     """`p = randn(np) .* 0.1; p[end] = 0.1` (:75-76).  `stiff` > 0 spreads ln A over that many e-folds and switches a few
-    fast consumption channels on — a stand-in for a trained stiff pyrolysis model."""
+    fast consumption channels on — a stand-in for a trained stiff pyrolysis model; `lnA_shift` < 0 slows every reaction
+    down by that many e-folds (a NON-stiff variant: with the script's initialisation the fastest time scale is
+    ~1/50 of t_end and explicit Tsit5 runs at its stability limit)."""
     g = np.random.default_rng(seed)
     n_p = nr * (2 * ns + 3) + 1
     p = g.standard_normal(n_p) * sigma
     p[-1] = slope
+    p[0:nr] += lnA_shift / (10.0 * slope)
     if stiff > 0:
         p[0:nr] += np.linspace(0.0, stiff, nr)            # ln A / slope
         w_in_raw = p[nr * (ns + 3):nr * (2 * ns + 3)].reshape(nr, ns)

@@ -158,13 +158,14 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
 int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                       const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
   if (o->alg != CRNN_ALG_TSIT5) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for Tsit5");
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for the F0 and F1 RHS flavours");
   const int n = m->n_state, ns = m->n_species, nr = m->n_reac;
   const int nw = nr * (m->n_in + 1 + ns);
   if (nw > 32 * ADJ_MAX_ENT) return fail(h, CRNN_ERR_UNSUPPORTED, "adjoint kernel supports n_w <= 512");
   // extra device doubles: scale[ns] | inv_ys[n] | seed [nw*np]
   std::vector<double> extra((size_t)ns + n + (size_t)nw * np, 1.0);
-  for (int i = 0; i < ns; ++i) extra[i] = m->out_scale ? m->out_scale[i] : 1.0;
+  // scale[i] multiplies lambda_i in the w_out quadrature: out_scale, times the molar mass for F2 (f_i = wdot_i MW_i / rho s_i)
+  for (int i = 0; i < ns; ++i)
+    extra[i] = (m->out_scale ? m->out_scale[i] : 1.0) * (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? m->mw[i] : 1.0);
   for (int q = 0; q < o->n_obs; ++q) {
     const int r = o->obs_idx[q];
     if (r >= 0 && r < n && loss_kind == CRNN_LOSS_MAE_SCALED) extra[ns + r] = 1.0 / yscale[q];
@@ -184,7 +185,7 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   const int stride = 8 * n + 2;
   // forward-record capacity in shared memory: two blocks of 4 warps per SM
   const size_t budget = (size_t)(227 * 1024 / 2) - 2048 - sizeof(WideBlock);
-  const size_t fixed_pw = (128 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
+  const size_t fixed_pw = (160 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
   if (fixed_pw * WARPS > budget) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
   P.cap_s = (int)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
   P.cap_g = 512;

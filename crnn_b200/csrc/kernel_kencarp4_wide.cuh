@@ -41,6 +41,33 @@ struct WideP {
   const double* tab_P;   // device [n_tab]
 };
 
+// ---- shared by the lane-per-component kernels (k_wide_solve, k_tsit5_adjoint): F2 tables ----
+constexpr double kGasRu = 8.31446261815324e3;  // HyChem/crnn_pyrolysis_mass.jl:108
+
+struct TabVal { double T, P, Td, Pd; };
+
+// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t
+__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
+  int lo = 0, hi = P.n_tab - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
+  }
+  const double ta = __ldg(P.tab_t + lo), h = __ldg(P.tab_t + lo + 1) - ta, w = (t - ta) / h;
+  const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
+  const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
+  TabVal v;
+  v.T = T0 + w * (T1 - T0); v.P = P0 + w * (P1 - P0);
+  v.Td = (T1 - T0) / h; v.Pd = (P1 - P0) / h;
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
 namespace kc {
 constexpr double g = 0.25;
 __constant__ double A[6][5] = {

@@ -62,11 +62,12 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const int stride = 8 * n + 2;  // doubles per recorded step: t, dt, u, k1..k7
   WideBlock& sb = *reinterpret_cast<WideBlock*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per-warp region: x[32] r[32] lam[32] gr[32] | GW[nw] GS[nw] | record[cap_s][stride]
-  const size_t per_warp = 4 * 32 + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
+  // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] | GW[nw] GS[nw] | record[cap_s][stride]
+  const size_t per_warp = 5 * 32 + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
   double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlock)) + per_warp * warp;
   double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
-  double* GW = wbase + 128; double* GS = GW + ((nw + 1) & ~1);
+  double* s_chi = wbase + 128;
+  double* GW = wbase + 160; double* GS = GW + ((nw + 1) & ~1);
   double* rec_s = GS + ((nw + 1) & ~1);
   double* rec_g = P.scratch + ((size_t)blockIdx.x * WARPS + warp) * (size_t)P.cap_g * stride;
 
@@ -83,6 +84,8 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const int my_obs = lane < n ? W.row2obs[lane] : -1;
   const double my_iys = lane < n ? P.inv_ys[lane] : 1.0;
   const double my_scale = isp ? P.scale[lane] : 0.0;
+  const bool f2 = (W.kind == 2);
+  const double my_mw = (f2 && isp) ? __ldg(W.mw + lane) : 1.0;
   // quadrature entries of this lane: e = lane + 32*q ; packed (kind, i, j)
   int ent[ADJ_MAX_ENT];
 #pragma unroll
@@ -99,10 +102,18 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
   };
   // forward RHS: lane i holds y_i -> f_i (x, r left in shared memory)
-  auto rhs = [&](double y) -> double {
+  auto rhs = [&](double tt, double y) -> double {
     __syncwarp();
-    double xi = 0.0;
-    if (isp) xi = lean_log(clampd(y, W.lb, W.ub));
+    double xi = 0.0, rho = 1.0;
+    if (f2) {  // HyChem mass fractions (kernel_wide_solve.cuh::wide_rhs)
+      const TabVal tv = wide_tab(W, tt);
+      const double ymw = isp ? clampd(y, W.lb, W.ub) / my_mw : 0.0;
+      const double S = warp_sum(ymw);
+      rho = tv.P / (kGasRu * tv.T * S);
+      if (isp) xi = lean_log(clampd(rho * ymw * 1e3, W.lb, W.ub));
+      else if (lane == ns) xi = -1.0 / W.gas_R / tv.T;
+      else if (lane == ns + 1) xi = lean_log(tv.T);
+    } else if (isp) xi = lean_log(clampd(y, W.lb, W.ub));
     else if (W.kind == 1 && lane == ns) xi = -1.0 / (W.gas_R * y);
     s_x[lane] = xi;
     __syncwarp();
@@ -115,6 +126,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     double f = 0.0;
     if (isp)
       for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], s_r[j], f);
+    if (f2) f = f / rho;
     return f;
   };
   // u_i(ts) from the recorded dense output of step `ir`
@@ -159,7 +171,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     // ================= forward: Tsit5 value solve, recording every accepted step =================
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_back = 0, nrec = 0;
     double k[7];
-    k[0] = rhs(u); ++n_rhs;
+    k[0] = rhs(t0, u); ++n_rhs;
     double dt;
     {
       const double sk = my_at + fabs(u) * my_rt;
@@ -168,7 +180,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
-      const double f1 = rhs(fma(dt0, k[0], u)); ++n_rhs;
+      const double f1 = rhs(t0 + dt0, fma(dt0, k[0], u)); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1 - k[0]) / sk; c *= c; }
       const double d2 = sqrt(warp_sum(c) / n) / dt0;
@@ -196,7 +208,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         for (int j = 0; j < 6; ++j)
           if (j < s) acc = (j == 0) ? tsc::A[s][0] * k[0] : fma(tsc::A[s][j], k[j], acc);
         un = fma(dt, acc, u);
-        const double f = rhs(un); ++n_rhs;
+        const double f = rhs(t + tsc::C[s] * dt, un); ++n_rhs;
 #pragma unroll
         for (int j = 1; j < 7; ++j)
           if (j == s) k[j] = f;
@@ -246,10 +258,28 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     double K[7];
     // adjoint RHS at state component u_i (lane), multiplier value in s_lam: returns (J^T lambda)_i and leaves
     // x in s_x, r in s_r, g.*r in s_gr
-    auto adj_rhs = [&](double ui, double li) -> double {
+    // F2 (oracle adj_rhs): s_lam holds lambda_i / rho (MW_i s_i are folded into w_out and P.scale), and the
+    // density couples every species: + rr_l * sum_j (WS_j - 1) g_j r_j with WS_j = sum_i w_in[i,j] chiC_i.
+    auto adj_rhs = [&](double tt, double ui, double li) -> double {
       __syncwarp();
-      double xi = 0.0, dxi = 0.0;
-      if (isp) {
+      double xi = 0.0, dxi = 0.0, rrl = 0.0, chiC = 0.0, inv_rho = 1.0;
+      if (f2) {
+        const TabVal tv = wide_tab(W, tt);
+        double Y = 1.0, chi = 0.0, ymw = 0.0;
+        if (isp) { Y = clampd(ui, W.lb, W.ub); chi = (ui >= W.lb && ui <= W.ub) ? 1.0 : 0.0; ymw = Y / my_mw; }
+        const double S = warp_sum(ymw);
+        const double rho = tv.P / (kGasRu * tv.T * S);
+        inv_rho = 1.0 / rho;
+        if (isp) {
+          const double C = rho * ymw * 1e3;
+          chiC = (C >= W.lb && C <= W.ub) ? 1.0 : 0.0;
+          xi = lean_log(clampd(C, W.lb, W.ub));
+          dxi = chiC * chi / Y;
+          rrl = -chi / (my_mw * S);
+        } else if (lane == ns) xi = -1.0 / W.gas_R / tv.T;
+        else if (lane == ns + 1) xi = lean_log(tv.T);
+        s_chi[lane] = chiC;
+      } else if (isp) {
         const double uc = clampd(ui, W.lb, W.ub);
         xi = lean_log(uc);
         dxi = (ui >= W.lb && ui <= W.ub) ? __drcp_rn(uc) : 0.0;
@@ -257,8 +287,9 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         xi = -1.0 / (W.gas_R * ui);
       }
       s_x[lane] = xi;
-      s_lam[lane] = isp ? li : 0.0;
+      s_lam[lane] = isp ? li * inv_rho : 0.0;
       __syncwarp();
+      double brk = 0.0;
       if (lane < nr) {
         double z = sb.w_b[lane], gs = 0.0;
         for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
@@ -266,12 +297,18 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         const double r = lean_exp(z);
         s_r[lane] = r;
         s_gr[lane] = gs * r;
+        if (f2) {
+          double ws = 0.0;
+          for (int i = 0; i < ns; ++i) ws = fma(sb.w_inT[i][lane], s_chi[i], ws);
+          brk = (ws - 1.0) * (gs * r);
+        }
       }
+      if (f2) brk = warp_sum(brk);
       __syncwarp();
       double s = 0.0;
       if (isp)
         for (int j = 0; j < nr; ++j) s = fma(sb.w_inT[lane][j], s_gr[j], s);
-      return dxi * s;
+      return fma(rrl, brk, dxi * s);
     };
 
     // loss term and pred of save column kk (value y_i in this lane); returns this lane's dL/du_i(t_k)
@@ -352,7 +389,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
 #pragma unroll
           for (int l = 0; l < 7; ++l)
             if (l == j) kb = kbar[l];
-          const double vj = adj_rhs(fma(h, acc, un0), kb); ++n_rhs;
+          const double vj = adj_rhs(tn + tsc::C[j] * h, fma(h, acc, un0), kb); ++n_rhs;
           accum(GW, 1.0);
           if (j == 6) {
             ubar += vj;
@@ -378,7 +415,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
             if (++biter > W.maxiters) { ret = CRNN_RET_MAXITERS; break; }
             if (!have_dt) {  // Hairer initial step of the lambda system at `cur`
               while (ir > 0 && rec_ptr(ir)[0] >= cur) --ir;
-              K[0] = adj_rhs(dense_u(ir, cur), lam); ++n_rhs;
+              K[0] = adj_rhs(cur, dense_u(ir, cur), lam); ++n_rhs;
               const double sk = my_at + fabs(lam) * my_rt;
               double a = 0.0, b = 0.0;
               if (lane < n) { a = lam / sk; a *= a; b = K[0] / sk; b *= b; }
@@ -404,7 +441,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
               const double tsx = cur - tsc::C[s] * h;
               while (ir > 0 && rec_ptr(ir)[0] > tsx) --ir;
               while (ir < nrec - 1 && rec_ptr(ir)[0] + rec_ptr(ir)[1] < tsx) ++ir;
-              const double f = adj_rhs(dense_u(ir, tsx), y); ++n_rhs;
+              const double f = adj_rhs(tsx, dense_u(ir, tsx), y); ++n_rhs;
 #pragma unroll
               for (int j = 0; j < 7; ++j)
                 if (j == s) K[j] = f;

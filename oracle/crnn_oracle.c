@@ -832,28 +832,39 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
  *  forward-mode one by O(tolerance). */
 typedef struct { double t, dt; } rec_hdr;
 
-static void adj_rhs(const ctx_t* c, const double* u, const double* lam, double* dlam, double* gw /* nw integrand or NULL */) {
-  const double t_unused = c->o->t0; /* F0/F1 are autonomous; F2 is rejected for the adjoint in check_dims */
+static void adj_rhs(const ctx_t* c, double t, const double* u, const double* lam, double* dlam, double* gw /* nw integrand or NULL */) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  rhs_cache k; double du[MAXN], g[MAXR];
-  rhs_value(c, t_unused, u, du, &k);
+  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  rhs_cache k; double du[MAXN], g[MAXR], mu[MAXN];
+  rhs_value(c, t, u, du, &k);
+  /* mu_i = d(lambda^T f)/d(wdot_i): s_i lambda_i, times MW_i / rho for F2 (f_i = wdot_i MW_i / rho s_i) */
+  for (int i = 0; i < ns; ++i) mu[i] = (m->out_scale ? m->out_scale[i] : 1.0) * lam[i] * (f2 ? m->mw[i] / k.rho : 1.0);
   for (int j = 0; j < nr; ++j) {
     double s = 0.0;
-    for (int i = 0; i < ns; ++i) s += m->w_out[i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * lam[i];
+    for (int i = 0; i < ns; ++i) s += m->w_out[i + ns * j] * mu[i];
     g[j] = s * k.r[j];
+  }
+  double bracket = 0.0;
+  if (f2) { /* density coupling: sum_j (WS_j - 1) g_j r_j, WS_j = sum_i w_in[i,j] chiC_i */
+    for (int j = 0; j < nr; ++j) {
+      double ws = 0.0;
+      for (int i = 0; i < ns; ++i) ws += m->w_in[i + nin * j] * k.chiC[i];
+      bracket += (ws - 1.0) * g[j];
+    }
   }
   for (int l = 0; l < ns; ++l) {
     double s = 0.0;
     for (int j = 0; j < nr; ++j) s += m->w_in[l + nin * j] * g[j];
     dlam[l] = k.dx[l] * s; /* (J^T lambda)_l, reverse time */
+    if (f2) dlam[l] += -k.chi[l] / (m->mw[l] * k.S) * bracket;
   }
   for (int l = ns; l < c->n; ++l) dlam[l] = 0.0; /* lambda_T never feeds back (row T of J is zero) */
   if (gw) {
     for (int j = 0; j < nr; ++j) {
       for (int i = 0; i < nin; ++i) gw[i + nin * j] = k.x[i] * g[j];
       gw[nin * nr + j] = g[j];
-      for (int i = 0; i < ns; ++i) gw[nin * nr + nr + i + ns * j] = (m->out_scale ? m->out_scale[i] : 1.0) * lam[i] * k.r[j];
+      for (int i = 0; i < ns; ++i) gw[nin * nr + nr + i + ns * j] = mu[i] * k.r[j];
     }
   }
 }
@@ -1000,7 +1011,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
       }
       /* k7 = f(u_{n+1}) enters only the dense output */
       for (int i = 0; i < n; ++i) { double acc = 0.0; for (int j = 0; j < 6; ++j) acc += TS_A[6][j] * r0[(1 + j) * n + i]; yy[i] = r0[i] + h * acc; }
-      adj_rhs(c, yy, kbar[6], vj, gtmp); res->st.n_rhs++;
+      adj_rhs(c, tn + h, yy, kbar[6], vj, gtmp); res->st.n_rhs++;
       for (int i = 0; i < n; ++i) ubar[i] += vj[i];
       for (int w = 0; w < nw; ++w) GW[w] += gtmp[w];
       /* u_{n+1} = u_n + h sum_j b_j k_j */
@@ -1008,7 +1019,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
       for (int i = 0; i < n; ++i) ubn[i] += ubar[i];
       for (int j = 5; j >= 0; --j) {
         for (int i = 0; i < n; ++i) { double acc = 0.0; for (int l = 0; l < j; ++l) acc += TS_A[j][l] * r0[(1 + l) * n + i]; yy[i] = r0[i] + h * acc; }
-        adj_rhs(c, yy, kbar[j], vj, gtmp); res->st.n_rhs++;
+        adj_rhs(c, tn + TS_C[j] * h, yy, kbar[j], vj, gtmp); res->st.n_rhs++;
         for (int w = 0; w < nw; ++w) GW[w] += gtmp[w];
         for (int i = 0; i < n; ++i) ubn[i] += vj[i];
         for (int l = 0; l < j; ++l) for (int i = 0; i < n; ++i) kbar[l][i] += h * TS_A[j][l] * vj[i];
@@ -1037,7 +1048,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
             { double th = (cur - hdr[ir].t) / hdr[ir].dt, b[7]; const double* r0 = rec + (size_t)ir * 8 * n;
               for (int s = 0; s < 7; ++s) b[s] = th * (TS_R[s][0] + th * (TS_R[s][1] + th * (TS_R[s][2] + th * TS_R[s][3])));
               for (int q = 0; q < n; ++q) { double acc = 0.0; for (int s = 0; s < 7; ++s) acc += b[s] * r0[(1 + s) * n + q]; uu[q] = r0[q] + hdr[ir].dt * acc; } }
-            adj_rhs(c, uu, L, K[0], NULL); res->st.n_rhs++;
+            adj_rhs(c, cur, uu, L, K[0], NULL); res->st.n_rhs++;
             double d0 = 0.0, d1 = 0.0;
             for (int i = 0; i < n; ++i) { double at = o->abstol[o->n_abstol > 1 ? i : 0], rt = o->reltol[o->n_reltol > 1 ? i : 0];
               double sk = at + fabs(L[i]) * rt; d0 += (L[i] / sk) * (L[i] / sk); d1 += (K[0][i] / sk) * (K[0][i] / sk); }
@@ -1059,7 +1070,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
             { double th = (ts - hdr[ir].t) / hdr[ir].dt, b[7]; const double* r0 = rec + (size_t)ir * 8 * n;
               for (int q7 = 0; q7 < 7; ++q7) b[q7] = th * (TS_R[q7][0] + th * (TS_R[q7][1] + th * (TS_R[q7][2] + th * TS_R[q7][3])));
               for (int q = 0; q < n; ++q) { double acc = 0.0; for (int q7 = 0; q7 < 7; ++q7) acc += b[q7] * r0[(1 + q7) * n + q]; uu[q] = r0[q] + hdr[ir].dt * acc; } }
-            adj_rhs(c, uu, (s == 0) ? L : Y, K[s], gtmp); res->st.n_rhs++;
+            adj_rhs(c, ts, uu, (s == 0) ? L : Y, K[s], gtmp); res->st.n_rhs++;
             if (s < 6) { double bw = TS_A[6][s]; for (int w = 0; w < nw; ++w) GS[w] += bw * gtmp[w]; }
           }
           for (int q = 0; q < n; ++q) { double acc = TS_BT[0] * K[0][q]; for (int j = 1; j < 7; ++j) acc += TS_BT[j] * K[j][q]; E[q] = h * acc; }
@@ -1152,8 +1163,8 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
-  /* F2: forward sensitivities ride Tsit5 only (the nested-dual dJ terms of Rosenbrock23 are not restated for F2) */
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (adjoint || o->alg != CRNN_ALG_TSIT5)) return CRNN_ERR_UNSUPPORTED;
+  /* F2: gradients ride Tsit5 only (the nested-dual dJ terms of Rosenbrock23 are not restated for F2) */
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));

@@ -142,3 +142,37 @@ def test_generic_path_full_size_properties(engine, golden, monkeypatch):
     for k in ("n_accept", "n_reject", "n_rhs"):
         assert np.array_equal(wide["stats"][k], fast["stats"][k])
     assert _rel_err(wide["pred"], fast["pred"]) < 1e-9
+
+
+@pytest.mark.parametrize("mode", ["discrete", "interp"])
+def test_hychem_f2_gradient_np211_by_the_adjoints(engine, mode):
+    """loss + gradient of the HyChem model (np = 211, crnn_pyrolysis_mass.jl:143-147,201) on the GPU by the adjoint
+    kernels (cost independent of np), against the oracle's adjoint of the same kind and against the oracle's
+    FORWARD-mode gradient (211 dual columns through Tsit5 — what ForwardDiff.gradient computes)"""
+    N = 96
+    # the NON-stiff variant (every reaction two e-folds slower): with the script's own initialisation explicit Tsit5
+    # runs at its stability limit, where accept/reject decisions sit within rounding of EEst = 1 (no step-count parity)
+    # and value-only-controlled tangents are unstable.  Seeds 0 / 1: random CRNN weights whose trajectories do not sit on
+    # a clamp kink (for most other seeds two CPU builds of the oracle, with / without FMA contraction, differ by 1e-6 .. 0.5)
+    m, seed = cases.hychem_model(cases.hychem_p(0, lnA_shift=-2.0), YS_HYCHEM)
+    u0 = cases.hychem_u0(N)
+    data = oracle.solve_batch(cases.hychem_model(cases.hychem_p(1, lnA_shift=-2.0), YS_HYCHEM)[0],
+                              cases.hychem_opts(alg=ALG["ros23"]), u0, n_threads=8)["pred"]
+    sm = _abi.SENS_DISCRETE_ADJOINT if mode == "discrete" else _abi.SENS_INTERP_ADJOINT
+    tol = {}
+    o = cases.hychem_opts(alg=ALG["tsit5"], sens_mode=sm, maxiters=100000, **tol)
+    got = engine.loss_grad_batch(m, o, seed, u0, data, YS_HYCHEM, want_pred=True)
+    ref = oracle.loss_grad_batch(m, o, seed, u0, data, YS_HYCHEM, want_pred=True, n_threads=8)
+    assert np.array_equal(got["retcode"], ref["retcode"]) and (got["retcode"] == _abi.RET_SUCCESS).all()
+    for k in ("n_accept", "n_reject"):
+        assert np.array_equal(got["stats"][k], ref["stats"][k])
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-9)
+    gmax = np.abs(ref["grad_sum"]).max()
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=1e-6, atol=1e-8 * gmax)
+    if mode == "discrete":
+        # the discrete adjoint IS the forward-mode derivative of the same step sequence (value-only error norm)
+        of = cases.hychem_opts(alg=ALG["tsit5"], sens_mode=_abi.SENS_FORWARD, err_norm_includes_sens=False, maxiters=100000, **tol)
+        fwd = oracle.loss_grad_batch(m, of, seed, u0[:16], data[:16], YS_HYCHEM, n_threads=8)
+        g16 = engine.loss_grad_batch(m, o, seed, u0[:16], data[:16], YS_HYCHEM)
+        np.testing.assert_allclose(g16["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())
