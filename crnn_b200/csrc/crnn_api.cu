@@ -127,7 +127,6 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
 
 // KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
 int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 is implemented for the F0 and F1 RHS flavours");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);

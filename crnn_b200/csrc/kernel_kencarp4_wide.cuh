@@ -14,59 +14,9 @@
 // one exp issued per evaluation for the whole state.
 #pragma once
 #include "crnn_dev.cuh"
+#include "wide_common.cuh"
 
 namespace crnn {
-
-constexpr int KW_MAXN = 32;
-
-struct WideP {
-  double abstol[KW_MAXN], reltol[KW_MAXN];
-  double lb, ub, gas_R;
-  double t0, t1, pred_lo, pred_hi;
-  double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
-  long long maxiters;
-  const double* w_inT;   // device [n_in][nrp]: w_in transposed (reaction fastest), nrp = 32
-  const double* w_b;     // device [n_reac]
-  const double* w_out;   // device [n_species x n_reac] col-major, out_scale folded in
-  const double* saveat;  // device [n_save]
-  const int* row2obs;    // device [n_state]
-  int n, ns, nin, nr, kind;
-  int n_save, n_obs;
-  // generic solve path (kernel_wide_solve.cuh)
-  int alg, n_tab;
-  double beta1_ros, beta2_ros;  // PI exponents while AutoTsit5 runs Rosenbrock23 (beta1/beta2 above: Tsit5)
-  const double* mw;      // device [n_species]           (F2)
-  const double* tab_t;   // device [n_tab] knots         (F2)
-  const double* tab_T;   // device [n_tab]
-  const double* tab_P;   // device [n_tab]
-};
-
-// ---- shared by the lane-per-component kernels (k_wide_solve, k_tsit5_adjoint): F2 tables ----
-constexpr double kGasRu = 8.31446261815324e3;  // HyChem/crnn_pyrolysis_mass.jl:108
-
-struct TabVal { double T, P, Td, Pd; };
-
-// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t
-__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
-  int lo = 0, hi = P.n_tab - 1;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
-  }
-  const double ta = __ldg(P.tab_t + lo), h = __ldg(P.tab_t + lo + 1) - ta, w = (t - ta) / h;
-  const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
-  const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
-  TabVal v;
-  v.T = T0 + w * (T1 - T0); v.P = P0 + w * (P1 - P0);
-  v.Td = (T1 - T0) / h; v.Pd = (P1 - P0) / h;
-  return v;
-}
-
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
-  return v;
-}
 
 namespace kc {
 constexpr double g = 0.25;
@@ -77,24 +27,10 @@ __constant__ double A[6][5] = {
     {5012029.0 / 34652500.0, -654441.0 / 2922500.0, 174375.0 / 388108.0, 0, 0},
     {15267082809.0 / 155376265600.0, -71443401.0 / 120774400.0, 730878875.0 / 902184768.0, 2285395.0 / 8070912.0, 0},
     {82889.0 / 524892.0, 0.0, 15625.0 / 83664.0, 69875.0 / 102672.0, -2260.0 / 8211.0}};
+__constant__ double C[6] = {0.0, 0.5, 83.0 / 250.0, 31.0 / 50.0, 17.0 / 20.0, 1.0};
 __constant__ double BHAT[6] = {4586570599.0 / 29645900160.0, 0.0, 178811875.0 / 945068544.0,
                                814220225.0 / 1159782912.0, -3700637.0 / 11593932.0, 61727.0 / 225920.0};
 }  // namespace kc
-
-struct alignas(16) WideWarp {
-  double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
-  double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
-  int perm[KW_MAXN];
-  // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
-  double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
-  double k[7][KW_MAXN];
-};
-
-struct alignas(16) WideBlock {
-  double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
-  double w_out[KW_MAXN][KW_MAXN];  // [j][i]: lane i reads consecutive addresses for fixed j
-  double w_b[KW_MAXN];
-};
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 3)
@@ -121,90 +57,17 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
   const int my_obs = lane < n ? P.row2obs[lane] : -1;
 
-  // f(y): lane i holds y_i in, f_i out; leaves x in ww.x, r in ww.r; returns dx_i = d log(clamp y_i)/dy_i
-  auto rhs = [&](double y, double& dxi) -> double {
-    __syncwarp();
-    double xi = 0.0;
-    dxi = 0.0;
-    if (isp) {
-      const double uc = clampd(y, P.lb, P.ub);
-      xi = lean_log(uc);
-      dxi = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
-    } else if (P.kind == 1 && lane == ns) {
-      xi = -1.0 / (P.gas_R * y);
-    }
-    ww.x[lane] = xi;
-    __syncwarp();
-    if (lane < nr) {
-      double z = sb.w_b[lane];
-      for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
-      ww.r[lane] = lean_exp(z);
-    }
-    __syncwarp();
-    double f = 0.0;
-    if (isp)
-      for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
-    return f;
-  };
+  const double my_mw = (P.kind == 2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
+  // f(y, t), W = I - gdt*J and the triangular solves come from wide_common.cuh (all RHS flavours)
+  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs(P, sb, ww, lane, my_mw, tt, y, ax); };
+  auto lusolve = [&](double b) -> double { return wide_lusolve(ww, lane, ns, b); };
+  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { (void)wide_build_lu(P, sb, ww, lane, rsrc, ax, gdt); };
   // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;
     if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
     return sqrt(warp_sum(q) / n);
   };
-  // b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
-  auto lusolve = [&](double b) -> double {
-    b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
-    for (int k = 0; k + 1 < ns; ++k) {
-      const double bk = __shfl_sync(0xffffffffu, b, k);
-      if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
-    }
-    for (int k = ns - 1; k >= 0; --k) {
-      if (lane == k) b = b / ww.A[k][k];
-      const double bk = __shfl_sync(0xffffffffu, b, k);
-      if (lane < k) b = fma(-ww.A[lane][k], bk, b);
-    }
-    return isp ? b : 0.0;
-  };
-
-  // W = I - gdt*J from the RHS intermediates (r in rsrc, this lane's dx), then the cooperative LU
-  auto build_lu = [&](const double* rsrc, double dxl, double gdt) {
-    __syncwarp();
-    ww.x[lane] = dxl;  // broadcast dx_l
-    __syncwarp();
-    if (isp) {
-      for (int l = 0; l < ns; ++l) {
-        double s = 0.0;
-        for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
-        ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * (s * ww.x[l]);
-      }
-    }
-    ww.perm[lane] = lane;
-    __syncwarp();
-    for (int k = 0; k < ns; ++k) {
-      // pivot: first strict maximum of |A[i][k]|, i >= k
-      double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
-      int bi = lane;
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (bi != k) {
-        if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
-        if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
-      }
-      __syncwarp();
-      if (lane > k && isp) {
-        const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
-        ww.A[lane][k] = l;
-        for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
-      }
-      __syncwarp();
-    }
-  };
-
   while (true) {
     unsigned long long tq = 0;
     if (lane == 0) tq = atomicAdd(queue, 1ull);
@@ -226,8 +89,8 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
     };
 
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
-    double dx0, dxs;
-    double f0 = rhs(u, dx0); ++n_rhs;
+    WideAux a0, as;
+    double f0 = rhs(t0, u, a0); ++n_rhs;
     ww.r0[lane] = ww.r[lane];
     // ---- initial step (Hairer-Wanner, order 4) ----
     double dt;
@@ -238,7 +101,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
       const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
-      const double f1p = rhs(fma(dt0, f0, u), dxs); ++n_rhs;
+      const double f1p = rhs(t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(warp_sum(c) / n) / dt0;
@@ -262,7 +125,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
 
       // ---- W = I - g dt J(u_n), J[i][l] = sum_j w_out[i,j] r0_j w_in[l,j] dx0_l ; LU ----
       const double gdt = kc::g * dt;
-      build_lu(ww.r0, dx0, gdt);
+      build_lu(ww.r0, a0, gdt);
       ++n_jac;
 
       // ---- stages ----
@@ -283,7 +146,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
 #pragma unroll 1
           for (int it = 1; it <= 10; ++it) {
             yk = fma(kc::g, zs, tmp);
-            double dz = fma(dt, rhs(yk, dxs), -zs); ++n_rhs;
+            double dz = fma(dt, rhs(t + kc::C[s] * dt, yk, as), -zs); ++n_rhs;
             dz = lusolve(dz);
             const double ndz = wrms(dz, u, yk);
             zs += dz;
@@ -301,8 +164,8 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
             if (refreshed || __any_sync(0xffffffffu, lane < n && zs != zs)) break;
             refreshed = true;
             yk = fma(kc::g, zs, tmp);
-            (void)rhs(yk, dxs); ++n_rhs;
-            build_lu(ww.r, dxs, gdt);
+            (void)rhs(t + kc::C[s] * dt, yk, as); ++n_rhs;
+            build_lu(ww.r, as, gdt);
             ++n_jac;
           }
         }
@@ -331,8 +194,8 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
         qold = jmax(EEst, 1e-4);
         const double dtnew = dt / q, tprev = t;
         t = snap_t(t + dt, tend);
-        double dx1;
-        const double f1 = rhs(un, dx1); ++n_rhs;
+        WideAux a1;
+        const double f1 = rhs(t, un, a1); ++n_rhs;
         while (isave < nsave) {
           const double tsv = __ldg(P.saveat + isave);
           if (!(tsv <= t)) break;
@@ -344,7 +207,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
           }
           ++isave;
         }
-        u = un; f0 = f1; dx0 = dx1;
+        u = un; f0 = f1; a0 = a1;
         __syncwarp();
         ww.r0[lane] = ww.r[lane];
         dt = jmin(dtnew, dtmax);

@@ -17,7 +17,7 @@
 // Cost is independent of np: the right tool for case3 (np = 153) and larger parameter vectors.
 #pragma once
 #include "crnn_dev.cuh"
-#include "kernel_kencarp4_wide.cuh"  // WideP, WideBlock, KW_MAXN
+#include "wide_common.cuh"  // WideP, WideBlock, KW_MAXN, F2 tables
 
 namespace crnn {
 

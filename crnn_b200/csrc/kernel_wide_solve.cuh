@@ -13,169 +13,10 @@
 // stay the fast path for the instantiated configurations; this kernel serves everything else.
 #pragma once
 #include "crnn_dev.cuh"
-#include "kernel_kencarp4_wide.cuh"
+#include "wide_common.cuh"
 #include "kernel_tsit5_adjoint.cuh"  // tsc:: tableau in constant memory
 
 namespace crnn {
-
-struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobian needs)
-  double dx;       // d x_l / d u_l (F2: at fixed density)
-  double rr;       // F2: d log(rho) / d u_l = -chi_l / (MW_l S)
-  double wdot;     // sum_j w_out[l,j] r_j (scaled; F2: before the 1/rho)
-  double inv_rho;  // F2
-  double chiC;     // F2: 1 if lb <= C_l <= ub
-};
-
-// f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
-__device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double mw,
-                                           double t, double y, WideAux& a) {
-  const int ns = P.ns, nin = P.nin, nr = P.nr;
-  const bool isp = lane < ns;
-  __syncwarp();
-  double xi = 0.0, rho = 1.0;
-  a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
-  if (P.kind == 2) {
-    const TabVal tv = wide_tab(P, t);
-    double Y = 1.0, chi = 0.0, ymw = 0.0;
-    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
-    const double S = warp_sum(ymw);
-    rho = tv.P / (kGasRu * tv.T * S);
-    if (isp) {
-      const double C = rho * ymw * 1e3;
-      a.chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
-      xi = lean_log(clampd(C, P.lb, P.ub));
-      a.dx = a.chiC * chi / Y;
-      a.rr = -chi / (mw * S);
-    } else if (lane == ns) {
-      xi = -1.0 / P.gas_R / tv.T;
-    } else if (lane == ns + 1) {
-      xi = lean_log(tv.T);
-    }
-    a.inv_rho = 1.0 / rho;
-  } else if (isp) {
-    const double uc = clampd(y, P.lb, P.ub);
-    xi = lean_log(uc);
-    a.dx = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
-  } else if (P.kind == 1 && lane == ns) {
-    xi = -1.0 / (P.gas_R * y);
-    a.dx = 1.0 / (P.gas_R * y * y);
-  }
-  ww.x[lane] = xi;
-  __syncwarp();
-  if (lane < nr) {
-    double z = sb.w_b[lane];
-    for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
-    ww.r[lane] = lean_exp(z);
-  }
-  __syncwarp();
-  double f = 0.0;
-  if (isp)
-    for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
-  a.wdot = f;
-  if (P.kind == 2) f = f / rho;
-  return f;
-}
-
-// df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
-__device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double t,
-                                                  const double* rsrc, const WideAux& a) {
-  if (P.kind != 2) return 0.0;
-  const int ns = P.ns, nr = P.nr;
-  const TabVal tv = wide_tab(P, t);
-  const double rr = tv.Pd / tv.P - tv.Td / tv.T;
-  __syncwarp();
-  ww.bchi[lane] = a.chiC;
-  __syncwarp();
-  if (lane < nr) {
-    double zd = 0.0;
-    for (int i = 0; i < ns; ++i) zd = fma(sb.w_inT[i][lane], ww.bchi[i] * rr, zd);
-    zd = fma(sb.w_inT[ns][lane], tv.Td / (P.gas_R * tv.T * tv.T), zd);
-    zd = fma(sb.w_inT[ns + 1][lane], tv.Td / tv.T, zd);
-    ww.ws[lane] = rsrc[lane] * zd;
-  }
-  __syncwarp();
-  double s = 0.0;
-  if (lane < ns) {
-    for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane], ww.ws[j], s);
-    s = (s - a.wdot * rr) * a.inv_rho;
-  }
-  __syncwarp();
-  return s;
-}
-
-// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
-// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
-__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane,
-                                                const double* rsrc, const WideAux& a, double gdt) {
-  const int n = P.n, ns = P.ns, nr = P.nr;
-  const bool isp = lane < ns;
-  __syncwarp();
-  ww.bdx[lane] = a.dx; ww.brr[lane] = a.rr; ww.bchi[lane] = a.chiC;
-  __syncwarp();
-  if (P.kind == 2 && lane < nr) {
-    double ws = 0.0;
-    for (int i = 0; i < ns; ++i) ws = fma(sb.w_inT[i][lane], ww.bchi[i], ws);
-    ww.ws[lane] = ws;
-  }
-  __syncwarp();
-  double rowsum = 0.0;
-  if (isp) {
-    double coef = 0.0;
-    if (P.kind == 2) {
-      for (int j = 0; j < nr; ++j) coef = fma(sb.w_out[j][lane] * rsrc[j], ww.ws[j], coef);
-      coef -= a.wdot;
-    }
-    for (int l = 0; l < n; ++l) {
-      double s = 0.0;
-      for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
-      double Jil = s * ww.bdx[l];
-      if (P.kind == 2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
-      rowsum += fabs(Jil);
-      if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
-    }
-  }
-  const double eig = warp_max(rowsum);
-  ww.perm[lane] = lane;
-  __syncwarp();
-  for (int k = 0; k < ns; ++k) {
-    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
-    int bi = lane;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (bi != k) {
-      if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
-      if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
-    }
-    __syncwarp();
-    if (lane > k && isp) {
-      const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
-      ww.A[lane][k] = l;
-      for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
-    }
-    __syncwarp();
-  }
-  return eig;
-}
-
-// b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
-__device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int ns, double b) {
-  const bool isp = lane < ns;
-  b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
-  for (int k = 0; k + 1 < ns; ++k) {
-    const double bk = __shfl_sync(0xffffffffu, b, k);
-    if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
-  }
-  for (int k = ns - 1; k >= 0; --k) {
-    if (lane == k) b = b / ww.A[k][k];
-    const double bk = __shfl_sync(0xffffffffu, b, k);
-    if (lane < k) b = fma(-ww.A[lane][k], bk, b);
-  }
-  return isp ? b : 0.0;
-}
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 3)

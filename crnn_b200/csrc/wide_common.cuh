@@ -1,0 +1,235 @@
+// wide_common.cuh — building blocks of the lane-per-component kernels (k_wide_solve, k_kencarp4_wide,
+// k_tsit5_adjoint): one WARP owns one trajectory, lane i owns state component i, dimensions are RUNTIME values
+// (n_state, n_in, n_reac <= 32).  The RHS of every flavour (F0, F1, F2), its analytic Jacobian assembled in
+// shared memory, df/dt for the non-autonomous F2, the cooperative LU and the triangular solves live here.
+#pragma once
+#include "crnn_dev.cuh"
+
+namespace crnn {
+
+constexpr int KW_MAXN = 32;
+
+struct WideP {
+  double abstol[KW_MAXN], reltol[KW_MAXN];
+  double lb, ub, gas_R;
+  double t0, t1, pred_lo, pred_hi;
+  double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
+  long long maxiters;
+  const double* w_inT;   // device [n_in][nrp]: w_in transposed (reaction fastest), nrp = 32
+  const double* w_b;     // device [n_reac]
+  const double* w_out;   // device [n_species x n_reac] col-major, out_scale folded in
+  const double* saveat;  // device [n_save]
+  const int* row2obs;    // device [n_state]
+  int n, ns, nin, nr, kind;
+  int n_save, n_obs;
+  // generic solve path (kernel_wide_solve.cuh)
+  int alg, n_tab;
+  double beta1_ros, beta2_ros;  // PI exponents while AutoTsit5 runs Rosenbrock23 (beta1/beta2 above: Tsit5)
+  const double* mw;      // device [n_species]           (F2)
+  const double* tab_t;   // device [n_tab] knots         (F2)
+  const double* tab_T;   // device [n_tab]
+  const double* tab_P;   // device [n_tab]
+};
+
+// ---- shared by the lane-per-component kernels (k_wide_solve, k_tsit5_adjoint): F2 tables ----
+constexpr double kGasRu = 8.31446261815324e3;  // HyChem/crnn_pyrolysis_mass.jl:108
+
+struct TabVal { double T, P, Td, Pd; };
+
+// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t
+__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
+  int lo = 0, hi = P.n_tab - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
+  }
+  const double ta = __ldg(P.tab_t + lo), h = __ldg(P.tab_t + lo + 1) - ta, w = (t - ta) / h;
+  const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
+  const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
+  TabVal v;
+  v.T = T0 + w * (T1 - T0); v.P = P0 + w * (P1 - P0);
+  v.Td = (T1 - T0) / h; v.Pd = (P1 - P0) / h;
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
+struct alignas(16) WideWarp {
+  double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
+  double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
+  int perm[KW_MAXN];
+  // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
+  double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
+  double k[7][KW_MAXN];
+};
+
+struct alignas(16) WideBlock {
+  double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
+  double w_out[KW_MAXN][KW_MAXN];  // [j][i]: lane i reads consecutive addresses for fixed j
+  double w_b[KW_MAXN];
+};
+
+struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobian needs)
+  double dx;       // d x_l / d u_l (F2: at fixed density)
+  double rr;       // F2: d log(rho) / d u_l = -chi_l / (MW_l S)
+  double wdot;     // sum_j w_out[l,j] r_j (scaled; F2: before the 1/rho)
+  double inv_rho;  // F2
+  double chiC;     // F2: 1 if lb <= C_l <= ub
+};
+
+// f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
+__device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double mw,
+                                           double t, double y, WideAux& a) {
+  const int ns = P.ns, nin = P.nin, nr = P.nr;
+  const bool isp = lane < ns;
+  __syncwarp();
+  double xi = 0.0, rho = 1.0;
+  a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
+  if (P.kind == 2) {
+    const TabVal tv = wide_tab(P, t);
+    double Y = 1.0, chi = 0.0, ymw = 0.0;
+    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
+    const double S = warp_sum(ymw);
+    rho = tv.P / (kGasRu * tv.T * S);
+    if (isp) {
+      const double C = rho * ymw * 1e3;
+      a.chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
+      xi = lean_log(clampd(C, P.lb, P.ub));
+      a.dx = a.chiC * chi / Y;
+      a.rr = -chi / (mw * S);
+    } else if (lane == ns) {
+      xi = -1.0 / P.gas_R / tv.T;
+    } else if (lane == ns + 1) {
+      xi = lean_log(tv.T);
+    }
+    a.inv_rho = 1.0 / rho;
+  } else if (isp) {
+    const double uc = clampd(y, P.lb, P.ub);
+    xi = lean_log(uc);
+    a.dx = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
+  } else if (P.kind == 1 && lane == ns) {
+    xi = -1.0 / (P.gas_R * y);
+    a.dx = 1.0 / (P.gas_R * y * y);
+  }
+  ww.x[lane] = xi;
+  __syncwarp();
+  if (lane < nr) {
+    double z = sb.w_b[lane];
+    for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
+    ww.r[lane] = lean_exp(z);
+  }
+  __syncwarp();
+  double f = 0.0;
+  if (isp)
+    for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+  a.wdot = f;
+  if (P.kind == 2) f = f / rho;
+  return f;
+}
+
+// df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
+__device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double t,
+                                                  const double* rsrc, const WideAux& a) {
+  if (P.kind != 2) return 0.0;
+  const int ns = P.ns, nr = P.nr;
+  const TabVal tv = wide_tab(P, t);
+  const double rr = tv.Pd / tv.P - tv.Td / tv.T;
+  __syncwarp();
+  ww.bchi[lane] = a.chiC;
+  __syncwarp();
+  if (lane < nr) {
+    double zd = 0.0;
+    for (int i = 0; i < ns; ++i) zd = fma(sb.w_inT[i][lane], ww.bchi[i] * rr, zd);
+    zd = fma(sb.w_inT[ns][lane], tv.Td / (P.gas_R * tv.T * tv.T), zd);
+    zd = fma(sb.w_inT[ns + 1][lane], tv.Td / tv.T, zd);
+    ww.ws[lane] = rsrc[lane] * zd;
+  }
+  __syncwarp();
+  double s = 0.0;
+  if (lane < ns) {
+    for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane], ww.ws[j], s);
+    s = (s - a.wdot * rr) * a.inv_rho;
+  }
+  __syncwarp();
+  return s;
+}
+
+// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
+// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
+__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane,
+                                                const double* rsrc, const WideAux& a, double gdt) {
+  const int n = P.n, ns = P.ns, nr = P.nr;
+  const bool isp = lane < ns;
+  __syncwarp();
+  ww.bdx[lane] = a.dx; ww.brr[lane] = a.rr; ww.bchi[lane] = a.chiC;
+  __syncwarp();
+  if (P.kind == 2 && lane < nr) {
+    double ws = 0.0;
+    for (int i = 0; i < ns; ++i) ws = fma(sb.w_inT[i][lane], ww.bchi[i], ws);
+    ww.ws[lane] = ws;
+  }
+  __syncwarp();
+  double rowsum = 0.0;
+  if (isp) {
+    double coef = 0.0;
+    if (P.kind == 2) {
+      for (int j = 0; j < nr; ++j) coef = fma(sb.w_out[j][lane] * rsrc[j], ww.ws[j], coef);
+      coef -= a.wdot;
+    }
+    for (int l = 0; l < n; ++l) {
+      double s = 0.0;
+      for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
+      double Jil = s * ww.bdx[l];
+      if (P.kind == 2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
+      rowsum += fabs(Jil);
+      if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
+    }
+  }
+  const double eig = warp_max(rowsum);
+  ww.perm[lane] = lane;
+  __syncwarp();
+  for (int k = 0; k < ns; ++k) {
+    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
+    int bi = lane;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi != k) {
+      if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
+      if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
+    }
+    __syncwarp();
+    if (lane > k && isp) {
+      const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
+      ww.A[lane][k] = l;
+      for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
+    }
+    __syncwarp();
+  }
+  return eig;
+}
+
+// b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
+__device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int ns, double b) {
+  const bool isp = lane < ns;
+  b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
+  for (int k = 0; k + 1 < ns; ++k) {
+    const double bk = __shfl_sync(0xffffffffu, b, k);
+    if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
+  }
+  for (int k = ns - 1; k >= 0; --k) {
+    if (lane == k) b = b / ww.A[k][k];
+    const double bk = __shfl_sync(0xffffffffu, b, k);
+    if (lane < k) b = fma(-ww.A[lane][k], bk, b);
+  }
+  return isp ? b : 0.0;
+}
+
+}  // namespace crnn

@@ -176,3 +176,21 @@ def test_hychem_f2_gradient_np211_by_the_adjoints(engine, mode):
         fwd = oracle.loss_grad_batch(m, of, seed, u0[:16], data[:16], YS_HYCHEM, n_threads=8)
         g16 = engine.loss_grad_batch(m, o, seed, u0[:16], data[:16], YS_HYCHEM)
         np.testing.assert_allclose(g16["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())
+
+
+def test_kencarp4_on_the_hychem_f2_model(engine):
+    """BASELINE config 5 as named: the HyChem pyrolysis RHS (F2, non-autonomous: the implicit stages are evaluated at
+    t + c_i dt) integrated by KenCarp4.  Newton iteration counts may flip on rounding for a few trajectories."""
+    N = 256
+    m, _ = cases.hychem_model(cases.hychem_p(0), YS_HYCHEM)
+    o = cases.hychem_opts(alg=_abi.ALG_KENCARP4)
+    u0 = cases.hychem_u0(N)
+    got = engine.solve_batch(m, o, u0)
+    ref = oracle.solve_batch(m, o, u0, n_threads=8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all() and np.array_equal(got["n_saved"], ref["n_saved"])
+    same = (got["stats"]["n_rhs"] == ref["stats"]["n_rhs"]) & (got["stats"]["n_accept"] == ref["stats"]["n_accept"]) & \
+           (got["stats"]["n_reject"] == ref["stats"]["n_reject"])
+    assert same.mean() >= 0.95, f"{(~same).sum()} of {N} trajectories differ in step/RHS counts"
+    scale = np.abs(ref["pred"]).max(axis=(0, 1))
+    err = np.abs(got["pred"] - ref["pred"]) / scale
+    assert err[same].max() < 1e-7 and err.max() < 5e-3
