@@ -359,3 +359,40 @@ def hychem_p(seed=0, ns=9, nr=10, sigma=0.1, slope=0.1, stiff=0.0, lnA_shift=0.0
         w_in_raw = p[nr * (ns + 3):nr * (2 * ns + 3)].reshape(nr, ns)
         w_in_raw[:, 0] = np.abs(w_in_raw[:, 0]) + 0.5      # every reaction consumes fuel
     return p
+
+
+# ---- reversible CRNN ("case1 rev/case1.jl"): an F0 model with 2*nr reactions ----
+
+def p2vec_case1_rev(p, ns=5, nr=10):
+    """`case1 rev/case1.jl:72-89`: du = w_out * (exp(w_in_f' log u + w_kf) - exp(w_in_b' log u + w_kb)) with
+    w_in_f = clamp(-w_out, 0, 2.5), w_in_b = clamp(w_out, 0, 2.5), w_kb = w_kf (Kc = 1) and w_out clamped to
+    [-2.5, 2.5].  That is the plain F0 CRNN with the 2*nr reactions [forward; backward]:
+    w_in = [w_in_f  w_in_b], w_b = [w_kf; w_kb], w_out = [w_out  -w_out] — no extra RHS flavour is needed."""
+    d = _D.seed(p)
+    w_kf = d[0:nr]
+    w_o = d[nr:nr * (ns + 1)].reshape_f(ns, nr).clamp(-2.5, 2.5)
+    w_in_f = (-w_o).clamp(0.0, 2.5)
+    w_in_b = w_o.clamp(0.0, 2.5)
+    cat = lambda a, b, ax: _D(np.concatenate([a.v, b.v], axis=ax), np.concatenate([a.j, b.j], axis=ax))
+    return _pack(cat(w_in_f, w_in_b, 1), cat(w_kf, w_kf, 0), cat(w_o, -w_o, 1))
+
+
+def true_model_case1_rev(lb=1e-30) -> CRNNModel:
+    """the generating network A<->B, B<->C, C<->D, 2C<->D+E with unit rate constants (`case1 rev/case1.jl:31-38`)"""
+    ns = 5
+    fw = [({0: 1}, {1: 1}), ({1: 1}, {2: 1}), ({2: 1}, {3: 1}), ({2: 2}, {3: 1, 4: 1})]
+    cols_in, cols_out = [], []
+    for reac, prod in fw:
+        for a, b in ((reac, prod), (prod, reac)):
+            wi = np.zeros(ns); wo = np.zeros(ns)
+            for i, nu in a.items():
+                wi[i] = nu; wo[i] -= nu
+            for i, nu in b.items():
+                wo[i] += nu
+            cols_in.append(wi); cols_out.append(wo)
+    return CRNNModel(w_in=np.array(cols_in).T, w_b=np.zeros(len(cols_in)), w_out=np.array(cols_out).T,
+                     rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)
+
+
+CASES["case1_rev"] = Case("case1_rev", 5, 20, 60, _abi.RHS_F0, 1e-5, INF, _abi.ALG_TSIT5, 1e-6, 1e-3,
+                          (0.0, 10.0), 100, p2vec_case1_rev, (-INF, INF), _abi.LOSS_MAE_SCALED, maxiters=10000)

@@ -405,7 +405,19 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   int64_t nsplit = 8;  // chunks per call; CRNN_B200_CHUNKS overrides (tuning knob of the host pipeline)
   if (const char* e = std::getenv("CRNN_B200_CHUNKS")) nsplit = std::max(1, std::atoi(e));
   const int64_t chunk = std::max<int64_t>(2048, (N + nsplit - 1) / nsplit);
-  const int64_t nchunk = (N + chunk - 1) / chunk;
+  // chunk boundaries: the H2D of the FIRST chunk cannot overlap any compute, so the pipeline ramps up — 1/4, 1/2 of
+  // a chunk, then full chunks (CRNN_B200_RAMP=0 switches the ramp off)
+  std::vector<int64_t> bounds{0};
+  {
+    bool ramp = true;
+    if (const char* e = std::getenv("CRNN_B200_RAMP")) ramp = std::atoi(e) != 0;
+    int64_t sz = ramp ? std::max<int64_t>(2048, chunk / 4) : chunk;
+    while (bounds.back() < N) {
+      bounds.push_back(std::min<int64_t>(N, bounds.back() + std::min(sz, chunk)));
+      sz *= 2;
+    }
+  }
+  const int64_t nchunk = (int64_t)bounds.size() - 1;
   for (int s = 0; s < kPipe; ++s) {
     CK(h->d_u0[s].reserve(chunk * ns * sizeof(double)));
     if (io.nsu) CK(h->d_nsu[s].reserve(chunk * sizeof(int)));
@@ -418,7 +430,7 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   if (io.stats) CK(h->d_stats.reserve(std::max<size_t>(8, N * sizeof(crnn_stats))));
   for (int64_t c = 0; c < nchunk; ++c) {
     const int s = (int)(c % kPipe);
-    const int64_t lo = c * chunk, n = std::min<int64_t>(chunk, N - lo);
+    const int64_t lo = bounds[c], n = bounds[c + 1] - lo;
     // slot reuse: inputs may be overwritten once the kernel of chunk c-kPipe is done,
     // outputs once their D2H copies are done
     if (c >= kPipe) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[s], 0));

@@ -16,9 +16,10 @@ const LIB = get(ENV, "CRNN_B200_LIB", "libcrnn_b200.so")
 
 # mirrors of the C structs (include/crnn_b200.h)
 struct CModel
-    n_state::Int32; n_species::Int32; n_in::Int32; n_reac::Int32; rhs_kind::Int32; reserved0::Int32
+    n_state::Int32; n_species::Int32; n_in::Int32; n_reac::Int32; rhs_kind::Int32; n_tab::Int32
     lb::Float64; ub::Float64; gas_R::Float64
     out_scale::Ptr{Float64}; w_in::Ptr{Float64}; w_b::Ptr{Float64}; w_out::Ptr{Float64}
+    mw::Ptr{Float64}; tab_t::Ptr{Float64}; tab_T::Ptr{Float64}; tab_P::Ptr{Float64}   # F2 (HyChem) only
 end
 struct COpts
     alg::Int32; sens_mode::Int32; err_norm_includes_sens::Int32; n_save::Int32; n_obs::Int32
@@ -43,8 +44,15 @@ check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:crnn_last_error, L
 
 "Problem constants a script defines once (tsteps, tolerances, lb/ub, i_obs, dydt_scale ...)."
 Base.@kwdef struct Setup
-    rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state)
-    alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23
+    rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state),
+                                   # 2: F2 (HyChem/crnn_pyrolysis_mass.jl: mass fractions, tabulated T(t), P(t))
+    alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23, 2 KenCarp4, 3 AutoTsit5(Rosenbrock23())
+    sens_mode::Int32 = 1           # 1 forward (ForwardDiff semantics), 2 interpolating adjoint, 3 discrete adjoint
+    gas_R::Float64 = 1.98720425864083e-3
+    mw::Vector{Float64} = Float64[]        # F2: l_MW
+    tab_t::Vector{Float64} = Float64[]     # F2: knots of itpT / itpP
+    tab_T::Vector{Float64} = Float64[]
+    tab_P::Vector{Float64} = Float64[]
     lb::Float64; ub::Float64
     abstol::Vector{Float64} = [1e-6]; reltol::Vector{Float64} = [1e-3]
     tspan::Tuple{Float64,Float64}; saveat::Vector{Float64}
@@ -60,9 +68,12 @@ function with_structs(f, s::Setup, w_in, w_b, w_out)
     ns, nr = size(w_out); n_in = size(w_in, 1)
     osc = s.out_scale === nothing ? Float64[] : s.out_scale
     GC.@preserve w_in w_b w_out osc s begin
-        m = CModel(n_in, ns, n_in, nr, s.rhs_kind, 0, s.lb, s.ub, 1.98720425864083e-3,
-                   isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out))
-        o = COpts(s.alg, 1, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
+        n_state = s.rhs_kind == 2 ? ns : n_in      # F0/F1: n_in == n_state; F2: n_in = n_species + 2
+        f2p(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
+        m = CModel(n_state, ns, n_in, nr, s.rhs_kind, length(s.tab_t), s.lb, s.ub, s.gas_R,
+                   isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out),
+                   f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P))
+        o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
                   0.0, 0.0, 0.0, 0.0, 0.0, C_NULL)

@@ -179,3 +179,30 @@ def test_f2_argument_validation():
     o.t1 = 1.0; o.saveat = np.array([0.0, 1.0])       # beyond the T(t), P(t) tables
     with pytest.raises(RuntimeError):
         oracle.solve_batch(m, o, cases.hychem_u0(1))
+
+
+def test_reversible_crnn_is_an_f0_model_with_twice_the_reactions():
+    """`case1 rev/case1.jl:80-89` transcribed literally vs the F0 oracle RHS on p2vec_case1_rev's weights; seed vs FD"""
+    g = np.random.default_rng(4)
+    ns, nr = 5, 10
+    p = g.standard_normal(nr * (ns + 1)) * 0.5
+    p[12] = 3.1; p[30] = -2.9                       # beyond the [-2.5, 2.5] clamp of w_out
+    w_in, w_b, w_out, seed = cases.p2vec_case1_rev(p)
+    assert w_in.shape == (5, 20) and w_out.shape == (5, 20) and seed.shape == (20 * 11, 60)
+    w_kf = p[:nr]; wo = np.clip(p[nr:].reshape(nr, ns).T, -2.5, 2.5)
+    u = 0.1 + g.random(ns)
+    u_in = np.log(np.clip(u, 1e-5, np.inf))
+    lit = wo @ (np.exp(np.clip(-wo, 0, 2.5).T @ u_in + w_kf) - np.exp(np.clip(wo, 0, 2.5).T @ u_in + w_kf))
+    m, _ = cases.CASES["case1_rev"].model(p)
+    np.testing.assert_allclose(oracle.rhs(m, u), lit, rtol=1e-13, atol=1e-15)
+    flat = lambda q: np.concatenate([a.reshape(-1, order="F") for a in cases.p2vec_case1_rev(q)[:3]])
+    for k in (0, 9, 11, 12, 30, 59):
+        h = 1e-6
+        pp, pm = p.copy(), p.copy(); pp[k] += h; pm[k] -= h
+        np.testing.assert_allclose(seed[:, k], (flat(pp) - flat(pm)) / (2 * h), rtol=1e-6, atol=1e-9)
+    # the generating network conserves A+B+C+D+E... (every reaction is 1 <-> 1 or 2 <-> 2 molecules)
+    mt = cases.true_model_case1_rev()
+    u0 = g.random((4, 5)); u0[:, :2] += 0.2
+    r = oracle.solve_batch(mt, cases.CASES["case1_rev"].opts(), u0)
+    assert (r["retcode"] == _abi.RET_SUCCESS).all()
+    np.testing.assert_allclose(r["pred"].sum(axis=2), u0.sum(axis=1)[:, None] * np.ones((1, 100)), rtol=1e-9)

@@ -194,3 +194,26 @@ def test_kencarp4_on_the_hychem_f2_model(engine):
     scale = np.abs(ref["pred"]).max(axis=(0, 1))
     err = np.abs(got["pred"] - ref["pred"]) / scale
     assert err[same].max() < 1e-7 and err.max() < 5e-3
+
+
+def test_reversible_crnn_case1_rev_on_the_generic_path(engine):
+    """`case1 rev/case1.jl`: 5 species, 10 reversible reactions = an F0 CRNN with 20 reactions, np = 60.  No specialised
+    kernel has these dimensions: predict runs on the generic kernel, the gradient on the discrete adjoint, which
+    equals the oracle's forward-mode (ForwardDiff-semantics) gradient with the value-only error norm."""
+    c = cases.CASES["case1_rev"]
+    g = np.random.default_rng(11)
+    N = 128
+    u0 = g.random((N, 5)); u0[:, :2] += 0.2
+    data = oracle.solve_batch(cases.true_model_case1_rev(), c.opts(), u0, n_threads=8)["pred"]
+    ys = synth.yscale_from(data, c.lb)
+    m, seed = c.model(g.standard_normal(c.n_p) * 0.5)
+    got = engine.solve_batch(m, c.opts(), u0)
+    ref = oracle.solve_batch(m, c.opts(), u0, n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-9
+    o = c.opts(sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    ga = engine.loss_grad_batch(m, o, seed, u0, data, ys, c.loss_kind)
+    of = c.opts(sens_mode=_abi.SENS_FORWARD, err_norm_includes_sens=False)
+    fwd = oracle.loss_grad_batch(m, of, seed, u0, data, ys, c.loss_kind, n_threads=8)
+    np.testing.assert_allclose(ga["loss"], fwd["loss"], rtol=1e-9)
+    np.testing.assert_allclose(ga["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())

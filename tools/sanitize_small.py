@@ -1,0 +1,44 @@
+"""One small call of every kernel family (run under compute-sanitizer: memcheck / racecheck / initcheck)."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from crnn_b200 import cases, synth, _abi
+from crnn_b200.engine import Engine
+from problems import make_problem
+
+N = int(os.environ.get("SAN_N", "48"))
+golden = json.load(open(os.path.join(ROOT, "tests", "golden", "checkpoints.json")))
+eng = Engine(0)
+YS = np.array([0.05, 0.01, 0.01, 0.01, 0.02, 0.9, 0.01, 1e-4, 1e-3])
+done = []
+for name in ("case2", "case1", "case3", "robertson"):
+    pb = make_problem(name, golden, N)
+    eng.solve_batch(pb["model"], pb["opts"], pb["u0"]); done.append(f"{name} value")
+    r = eng.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"], want_pred=True)
+    done.append(f"{name} forward sens")
+    if name != "robertson":
+        for sm in (_abi.SENS_INTERP_ADJOINT, _abi.SENS_DISCRETE_ADJOINT):
+            o = pb["case"].opts(obs_idx=pb["opts"].obs_idx, sens_mode=sm)
+            eng.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+        done.append(f"{name} adjoints")
+    o = pb["case"].opts(obs_idx=pb["opts"].obs_idx, alg=_abi.ALG_KENCARP4)
+    eng.solve_batch(pb["model"], o, pb["u0"]); done.append(f"{name} kencarp4")
+    os.environ["CRNN_B200_FORCE_WIDE"] = "1"
+    for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23):
+        if name == "robertson" and alg == _abi.ALG_TSIT5:
+            continue
+        eng.solve_batch(pb["model"], pb["case"].opts(obs_idx=pb["opts"].obs_idx, alg=alg), pb["u0"])
+    os.environ["CRNN_B200_FORCE_WIDE"] = "0"
+    done.append(f"{name} generic path")
+m, seed = cases.hychem_model(cases.hychem_p(0, lnA_shift=-2.0), YS)
+u0 = cases.hychem_u0(N)
+for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23, _abi.ALG_KENCARP4):
+    pr = eng.solve_batch(m, cases.hychem_opts(alg=alg), u0)
+for smode in (_abi.SENS_INTERP_ADJOINT, _abi.SENS_DISCRETE_ADJOINT):
+    eng.loss_grad_batch(m, cases.hychem_opts(alg=_abi.ALG_TSIT5, sens_mode=smode), seed, u0, pr["pred"] * 1.01, YS)
+done.append("hychem F2 all")
+ms = cases.synthetic_stiff_model()
+eng.solve_batch(ms, cases.synthetic_stiff_opts(), cases.synthetic_stiff_u0(N)); done.append("kencarp4 30-state")
+eng.close()
+print("sanitize_small ok:", "; ".join(done))
