@@ -402,16 +402,16 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   if (want_loss && np > 0) CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
   CK(cudaEventRecord(h->ev_cfg, h->s_compute));  // model/option uploads were enqueued on s_compute
   for (int s = 0; s < kPipe; ++s) CK(cudaStreamWaitEvent(h->s_slot[s], h->ev_cfg, 0));
-  int64_t nsplit = 8;  // chunks per call; CRNN_B200_CHUNKS overrides (tuning knob of the host pipeline)
+  int64_t nsplit = 4;  // full-size chunks per call; CRNN_B200_CHUNKS overrides (tuning knob of the host pipeline)
   if (const char* e = std::getenv("CRNN_B200_CHUNKS")) nsplit = std::max(1, std::atoi(e));
   const int64_t chunk = std::max<int64_t>(2048, (N + nsplit - 1) / nsplit);
-  // chunk boundaries: the H2D of the FIRST chunk cannot overlap any compute, so the pipeline ramps up — 1/4, 1/2 of
-  // a chunk, then full chunks (CRNN_B200_RAMP=0 switches the ramp off)
+  // chunk boundaries: the H2D of the FIRST chunk cannot overlap any compute, so the pipeline ramps up — 1/8, 1/4, 1/2 of
+  // a chunk, then full chunks (CRNN_B200_RAMP = first-chunk divisor, 0 or 1 switches the ramp off)
   std::vector<int64_t> bounds{0};
   {
-    bool ramp = true;
-    if (const char* e = std::getenv("CRNN_B200_RAMP")) ramp = std::atoi(e) != 0;
-    int64_t sz = ramp ? std::max<int64_t>(2048, chunk / 4) : chunk;
+    int ramp = 8;
+    if (const char* e = std::getenv("CRNN_B200_RAMP")) ramp = std::atoi(e);
+    int64_t sz = ramp > 1 ? std::max<int64_t>(2048, chunk / ramp) : chunk;
     while (bounds.back() < N) {
       bounds.push_back(std::min<int64_t>(N, bounds.back() + std::min(sz, chunk)));
       sz *= 2;
