@@ -105,7 +105,7 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
   int rcw = build_wide(h, m, o, order, {}, st, P, nullptr);
   if (rcw) return rcw;
   constexpr int WARPS = 4;
-  auto kern = k_wide_solve<WARPS>;
+  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_wide_solve<WARPS, true> : k_wide_solve<WARPS, false>;
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
@@ -132,7 +132,7 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
   if (rcw) return rcw;
   constexpr int WARPS = 4;
-  auto kern = k_kencarp4_wide<WARPS>;
+  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_kencarp4_wide<WARPS, true> : k_kencarp4_wide<WARPS, false>;
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
@@ -180,7 +180,7 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   P.nw = nw; P.loss_kind = loss_kind;
   P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
   constexpr int WARPS = 4;
-  auto kern = k_tsit5_adjoint<WARPS>;
+  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_tsit5_adjoint<WARPS, true> : k_tsit5_adjoint<WARPS, false>;
   const int stride = 8 * n + 2;
   // forward-record capacity in shared memory: two blocks of 4 warps per SM
   const size_t budget = (size_t)(227 * 1024 / 2) - 2048 - sizeof(WideBlock);

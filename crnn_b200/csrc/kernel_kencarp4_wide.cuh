@@ -32,7 +32,7 @@ __constant__ double BHAT[6] = {4586570599.0 / 29645900160.0, 0.0, 178811875.0 / 
                                814220225.0 / 1159782912.0, -3700637.0 / 11593932.0, 61727.0 / 225920.0};
 }  // namespace kc
 
-template <int WARPS>
+template <int WARPS, bool F2>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
                 const int* __restrict__ n_save_used, long long ntraj, double* __restrict__ pred,
@@ -57,11 +57,11 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
   const int my_obs = lane < n ? P.row2obs[lane] : -1;
 
-  const double my_mw = (P.kind == 2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
+  const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
   // f(y, t), W = I - gdt*J and the triangular solves come from wide_common.cuh (all RHS flavours)
-  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs(P, sb, ww, lane, my_mw, tt, y, ax); };
+  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2>(P, sb, ww, lane, my_mw, tt, y, ax); };
   auto lusolve = [&](double b) -> double { return wide_lusolve(ww, lane, ns, b); };
-  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { (void)wide_build_lu(P, sb, ww, lane, rsrc, ax, gdt); };
+  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { (void)wide_build_lu<F2>(P, sb, ww, lane, rsrc, ax, gdt); };
   // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;

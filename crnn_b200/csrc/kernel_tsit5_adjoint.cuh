@@ -50,7 +50,7 @@ struct AdjP {
 
 constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
 
-template <int WARPS>
+template <int WARPS, bool F2>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
                 long long ntraj, const double* __restrict__ data, double* __restrict__ loss,
@@ -84,7 +84,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const int my_obs = lane < n ? W.row2obs[lane] : -1;
   const double my_iys = lane < n ? P.inv_ys[lane] : 1.0;
   const double my_scale = isp ? P.scale[lane] : 0.0;
-  const bool f2 = (W.kind == 2);
+  constexpr bool f2 = F2;
   const double my_mw = (f2 && isp) ? __ldg(W.mw + lane) : 1.0;
   // quadrature entries of this lane: e = lane + 32*q ; packed (kind, i, j)
   int ent[ADJ_MAX_ENT];

@@ -18,7 +18,7 @@
 
 namespace crnn {
 
-template <int WARPS>
+template <int WARPS, bool F2>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
              long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
@@ -41,7 +41,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
   const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23);
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
   const int my_obs = lane < n ? P.row2obs[lane] : -1;
-  const double my_mw = (P.kind == 2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
+  const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
   double* const kk = &ww.k[0][lane];  // this lane's stage column, stride KW_MAXN
 #define KS(s) kk[(s) * KW_MAXN]
 
@@ -73,7 +73,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
 
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
     WideAux a0, as;  // by-products at u_n / at the last evaluation
-    KS(0) = wide_rhs(P, sb, ww, lane, my_mw, t0, u, a0); ++n_rhs;
+    KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0, u, a0); ++n_rhs;
     ww.r0[lane] = ww.r[lane];
     // ---- initial step (Hairer-Wanner; the order of the FIRST algorithm) ----
     double dt;
@@ -85,7 +85,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
-      const double f1p = wide_rhs(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
+      const double f1p = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(warp_sum(c) / n) / dt0;
@@ -109,7 +109,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         else if (rosen && sw_count < -3) { dt = dt / 2.0; want = false; }
         if (want != rosen) {
           rosen = want;
-          KS(0) = wide_rhs(P, sb, ww, lane, my_mw, t, u, a0); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
+          KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t, u, a0); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
           __syncwarp();
           ww.r0[lane] = ww.r[lane];
         }
@@ -132,7 +132,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
           const double y = fma(dt, acc, u);
           if (s == 5) g6 = y;
           un = y;
-          KS(s) = wide_rhs(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as); ++n_rhs;
+          KS(s) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as); ++n_rhs;
         }
         double acc = tsc::BT[0] * KS(0);
 #pragma unroll
@@ -147,16 +147,16 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         // ---- Rosenbrock23 = ode23s: KS(0)=f0, KS(1..3)=k1..k3, KS(4)=f1, KS(5)=f2 ----
         const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
         const double g = d * dt;
-        const double dTv = wide_time_deriv(P, sb, ww, lane, t, ww.r0, a0);
-        const double eig = wide_build_lu(P, sb, ww, lane, ww.r0, a0, g);
+        const double dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, ww.r0, a0);
+        const double eig = wide_build_lu<F2>(P, sb, ww, lane, ww.r0, a0, g);
         ++n_jac;
         if (autosw) eigen_est = eig;
         const double f0 = KS(0);
         const double k1 = wide_lusolve(ww, lane, ns, fma(g, dTv, f0));
-        const double f1 = wide_rhs(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as); ++n_rhs;
+        const double f1 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as); ++n_rhs;
         const double k2 = wide_lusolve(ww, lane, ns, f1 - k1) + k1;
         un = fma(dt, k2, u);
-        const double f2 = wide_rhs(P, sb, ww, lane, my_mw, t + dt, un, as); ++n_rhs;
+        const double f2 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + dt, un, as); ++n_rhs;
         const double k3 = wide_lusolve(ww, lane, ns, f2 - e32 * (k2 - f1) - 2.0 * (k1 - f0) + dt * dTv);
         e = dt / 6.0 * (k1 - 2.0 * k2 + k3);
         KS(1) = k1; KS(2) = k2; KS(5) = f2;

@@ -82,6 +82,7 @@ struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobi
 };
 
 // f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
+template <bool F2>
 __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double mw,
                                            double t, double y, WideAux& a) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
@@ -89,7 +90,7 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   __syncwarp();
   double xi = 0.0, rho = 1.0;
   a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
-  if (P.kind == 2) {
+  if (F2) {
     const TabVal tv = wide_tab(P, t);
     double Y = 1.0, chi = 0.0, ymw = 0.0;
     if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
@@ -111,7 +112,7 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
     const double uc = clampd(y, P.lb, P.ub);
     xi = lean_log(uc);
     a.dx = (y >= P.lb && y <= P.ub) ? __drcp_rn(uc) : 0.0;
-  } else if (P.kind == 1 && lane == ns) {
+  } else if (!F2 && P.kind == 1 && lane == ns) {
     xi = -1.0 / (P.gas_R * y);
     a.dx = 1.0 / (P.gas_R * y * y);
   }
@@ -127,14 +128,15 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   if (isp)
     for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
   a.wdot = f;
-  if (P.kind == 2) f = f / rho;
+  if (F2) f = f / rho;
   return f;
 }
 
 // df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
+template <bool F2>
 __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double t,
                                                   const double* rsrc, const WideAux& a) {
-  if (P.kind != 2) return 0.0;
+  if (!F2) return 0.0;
   const int ns = P.ns, nr = P.nr;
   const TabVal tv = wide_tab(P, t);
   const double rr = tv.Pd / tv.P - tv.Td / tv.T;
@@ -160,6 +162,7 @@ __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBloc
 
 // W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
 // pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
+template <bool F2>
 __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane,
                                                 const double* rsrc, const WideAux& a, double gdt) {
   const int n = P.n, ns = P.ns, nr = P.nr;
@@ -167,7 +170,7 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
   __syncwarp();
   ww.bdx[lane] = a.dx; ww.brr[lane] = a.rr; ww.bchi[lane] = a.chiC;
   __syncwarp();
-  if (P.kind == 2 && lane < nr) {
+  if (F2 && lane < nr) {
     double ws = 0.0;
     for (int i = 0; i < ns; ++i) ws = fma(sb.w_inT[i][lane], ww.bchi[i], ws);
     ww.ws[lane] = ws;
@@ -176,7 +179,7 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
   double rowsum = 0.0;
   if (isp) {
     double coef = 0.0;
-    if (P.kind == 2) {
+    if (F2) {
       for (int j = 0; j < nr; ++j) coef = fma(sb.w_out[j][lane] * rsrc[j], ww.ws[j], coef);
       coef -= a.wdot;
     }
@@ -184,7 +187,7 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
       double s = 0.0;
       for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
       double Jil = s * ww.bdx[l];
-      if (P.kind == 2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
+      if (F2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
       rowsum += fabs(Jil);
       if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
     }
