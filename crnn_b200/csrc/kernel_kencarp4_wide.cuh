@@ -48,6 +48,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
     const int i = q / KW_MAXN, j = q % KW_MAXN;
     sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
+    sb.w_inJ[j][i] = sb.w_inT[i][j];
     sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
   }
   for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;

@@ -63,6 +63,7 @@ __device__ __forceinline__ void lu_factor(double (&A)[NS][NS], int (&piv)[NS]) {
       }
     }
     const double d = 1.0 / A[k][k];
+    A[k][k] = d;  // the diagonal keeps 1/u_kk: back-substitution multiplies (an fp64 division is ~30 instructions)
 #pragma unroll
     for (int i = k + 1; i < NS; ++i) {
       const double l = A[i][k] * d;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void lu_solve(const double (&A)[NS][NS], const int (&
     double s = b[i];
 #pragma unroll
     for (int j = i + 1; j < NS; ++j) s = fma(-A[i][j], b[j], s);
-    b[i] = s / A[i][i];
+    b[i] = s * A[i][i];  // A[i][i] holds 1/u_ii (lu_factor)
   }
 }
 

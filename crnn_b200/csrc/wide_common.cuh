@@ -64,11 +64,13 @@ struct alignas(16) WideWarp {
   int perm[KW_MAXN];
   // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
   double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
+  double dinv[KW_MAXN];  // 1/u_kk of the LU: back-substitution multiplies instead of dividing
   double k[7][KW_MAXN];
 };
 
 struct alignas(16) WideBlock {
   double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
+  double w_inJ[KW_MAXN][KW_MAXN];  // [j][i]: the Jacobian assembly reads 8 consecutive inputs of a reaction with 4 LDS.128
   double w_out[KW_MAXN][KW_MAXN];  // [j][i]: lane i reads consecutive addresses for fixed j
   double w_b[KW_MAXN];
 };
@@ -183,13 +185,31 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
       for (int j = 0; j < nr; ++j) coef = fma(sb.w_out[j][lane] * rsrc[j], ww.ws[j], coef);
       coef -= a.wdot;
     }
-    for (int l = 0; l < n; ++l) {
-      double s = 0.0;
-      for (int j = 0; j < nr; ++j) s = fma(sb.w_out[j][lane] * rsrc[j], sb.w_inT[l][j], s);
-      double Jil = s * ww.bdx[l];
-      if (F2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
-      rowsum += fabs(Jil);
-      if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
+    // J[i][l] = (sum_j w_out[i,j] r_j w_in[l,j]) dx_l (+ F2 density terms), eight columns l per pass over the reactions
+    for (int l0 = 0; l0 < n; l0 += 8) {
+      double s[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] = 0.0;
+      for (int j = 0; j < nr; ++j) {
+        const double wr = sb.w_out[j][lane] * rsrc[j];
+        const double2* wj = reinterpret_cast<const double2*>(&sb.w_inJ[j][l0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 v = wj[q];
+          s[2 * q] = fma(wr, v.x, s[2 * q]);
+          s[2 * q + 1] = fma(wr, v.y, s[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int l = l0 + q;
+        if (l < n) {
+          double Jil = s[q] * ww.bdx[l];
+          if (F2) Jil = (Jil + coef * ww.brr[l]) * a.inv_rho;
+          rowsum += fabs(Jil);
+          if (l < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
+        }
+      }
     }
   }
   const double eig = warp_max(rowsum);
@@ -209,8 +229,10 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
       if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
     }
     __syncwarp();
+    const double rk = 1.0 / ww.A[k][k];
+    if (lane == k) ww.dinv[k] = rk;
     if (lane > k && isp) {
-      const double l = ww.A[lane][k] * (1.0 / ww.A[k][k]);
+      const double l = ww.A[lane][k] * rk;
       ww.A[lane][k] = l;
       for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
     }
@@ -228,7 +250,7 @@ __device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int
     if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
   }
   for (int k = ns - 1; k >= 0; --k) {
-    if (lane == k) b = b / ww.A[k][k];
+    if (lane == k) b = b * ww.dinv[k];
     const double bk = __shfl_sync(0xffffffffu, b, k);
     if (lane < k) b = fma(-ww.A[lane][k], bk, b);
   }

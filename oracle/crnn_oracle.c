@@ -409,7 +409,9 @@ static double snap_t(double tnew, double tend) {
   return tnew;
 }
 
-/* LU with partial pivoting, row-major A[n*n] in place; piv[n]. */
+/* LU with partial pivoting, row-major A[n*n] in place; piv[n].  The diagonal of U is stored INVERTED (1/u_kk, the
+ * value the elimination multipliers use anyway) and the back-substitution multiplies by it: on the GPU an fp64
+ * division is a ~30-instruction sequence that sat on the serial path of every triangular solve. */
 static void lu_factor(double* A, int* piv, int n) {
   for (int k = 0; k < n; ++k) {
     int p = k; double best = fabs(A[k * n + k]);
@@ -417,6 +419,7 @@ static void lu_factor(double* A, int* piv, int n) {
     piv[k] = p;
     if (p != k) for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
     double d = 1.0 / A[k * n + k];
+    A[k * n + k] = d;
     for (int i = k + 1; i < n; ++i) {
       double l = A[i * n + k] * d; A[i * n + k] = l;
       for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
@@ -427,7 +430,7 @@ static void lu_solve(const double* A, const int* piv, int n, double* b) {
   for (int k = 0; k < n; ++k) { int p = piv[k]; if (p != k) { double t = b[k]; b[k] = b[p]; b[p] = t; } }
   for (int i = 1; i < n; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= A[i * n + j] * b[j]; b[i] = s; }
   /* column-oriented order (j descending), the order a lane-per-row GPU solve produces */
-  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = n - 1; j > i; --j) s -= A[i * n + j] * b[j]; b[i] = s / A[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = n - 1; j > i; --j) s -= A[i * n + j] * b[j]; b[i] = s * A[i * n + i]; }
 }
 
 typedef struct {
