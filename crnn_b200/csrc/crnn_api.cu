@@ -329,14 +329,14 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
   if (o->alg == CRNN_ALG_KENCARP4) return solve_kencarp4(h, m, o, io, N);
   // dimension-specialised thread-per-trajectory kernels for the instantiated configurations ...
   const char* force = std::getenv("CRNN_B200_FORCE_WIDE");
-  if (o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {
+  if (m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return solve_impl<Cfg<NS_, NR_, K_>>(h, m, o, io, N);
     CRNN_FOR_EACH_CFG(X)
 #undef X
   }
-  // ... and the generic warp-per-trajectory kernel for everything else (any dimensions <= 32, F2, AutoTsit5)
+  // ... and the generic warp-per-trajectory kernel for everything else (any dimensions <= 32, F2)
   return solve_wide(h, m, o, io, N);
 }
 

@@ -38,6 +38,7 @@ struct SolveP {
   double inv_yscale[C::N];  // per state row (1 where unused)
   double t0, t1, pred_lo, pred_hi;
   double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
+  double beta1_ros, beta2_ros;  // AutoTsit5: PI exponents while the Rosenbrock23 half runs
   long long maxiters;
   const double* saveat;  // device [n_save]
   const int* row2obs;    // device [N]: observation slot of state row i, or -1

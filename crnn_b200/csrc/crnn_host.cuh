@@ -21,6 +21,7 @@
 #include "kernel_tsit5_sens.cuh"
 #include "kernel_rosenbrock23.cuh"
 #include "kernel_rosenbrock23_sens.cuh"
+#include "kernel_auto_value.cuh"
 
 using namespace crnn;
 
@@ -162,7 +163,7 @@ int pack(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* 
     for (int i = 0; i < C::NS; ++i)
       mp.w_out[i + C::NS * j] = m->w_out[i + C::NS * j] * (m->out_scale ? m->out_scale[i] : 1.0);
   mp.lb = m->lb; mp.ub = m->ub; mp.gas_R = m->gas_R;
-  const int order = (o->alg == CRNN_ALG_TSIT5) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
+  const int order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
   for (int i = 0; i < C::N; ++i) {
     sp.abstol[i] = o->abstol[o->n_abstol > 1 ? i : 0];
     sp.reltol[i] = o->reltol[o->n_reltol > 1 ? i : 0];
@@ -184,6 +185,8 @@ int pack(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* 
   sp.beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * order);
   sp.beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * order);
   sp.inv_order = 1.0 / order;
+  sp.beta2_ros = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * 2.0);
+  sp.beta1_ros = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * 2.0);
   sp.maxiters = o->maxiters;
   sp.n_save = o->n_save; sp.n_obs = o->n_obs;
   sp.incl_sens = o->err_norm_includes_sens;
@@ -222,6 +225,8 @@ int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& 
   ProfScope prof(h, st);
   if (alg == CRNN_ALG_TSIT5)
     k_tsit5_value<C><<<blocks, threads, 0, st>>>(mp, sp, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode, b.stats);
+  else if (alg == CRNN_ALG_AUTO_TSIT5_ROS23)
+    k_auto_value<C><<<blocks, threads, 0, st>>>(mp, sp, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode, b.stats);
   else
     k_rosenbrock23_value<C><<<blocks, threads, 0, st>>>(mp, sp, b.u0, b.nsu, b.n, b.pred, b.n_saved, b.retcode,
                                                        b.stats);

@@ -44,6 +44,23 @@ def test_generic_path_matches_oracle_on_the_reference_models(engine, golden, mon
     assert (got["retcode"] == _abi.RET_SUCCESS).all()
 
 
+@pytest.mark.parametrize("name,N,tol", [("case2", 512, 1e-9), ("case1", 64, 1e-9), ("robertson", 256, 1e-5), ("case3", 96, 1e-5)])
+def test_autoswitch_thread_per_trajectory_kernel_matches_oracle(engine, golden, name, N, tol):
+    """AutoTsit5(Rosenbrock23()) on the dimension-specialised path (k_auto_value: the Tsit5 and Rosenbrock23 steps of the
+    thread-per-trajectory kernels behind OrdinaryDiffEq's AutoSwitch counter) — case2.jl:26 as written"""
+    pb = make_problem(name, golden, N)
+    o = pb["case"].opts(alg=ALG["auto"], obs_idx=pb["opts"].obs_idx)
+    got = engine.solve_batch(pb["model"], o, pb["u0"])
+    ref = oracle.solve_batch(pb["model"], o, pb["u0"], n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < tol
+    if name == "robertson":   # the trained stiff CRNN: both halves ran
+        att = got["stats"]["n_accept"] + got["stats"]["n_reject"]
+        assert (got["stats"]["n_jac"] > 0).all() and (got["stats"]["n_jac"] < att).all()
+    else:
+        assert (got["stats"]["n_jac"] == 0).all()
+
+
 @pytest.mark.parametrize("alg", ["ros23", "auto"])
 def test_autoswitch_on_the_true_robertson_mechanism(engine, golden, alg):
     """AutoTsit5(Rosenbrock23()) on the stiff generating mechanism (rober_crnn.jl:56-63): starts with Tsit5, detects

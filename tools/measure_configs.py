@@ -55,10 +55,20 @@ def main():
     mh, seedh = cases.hychem_model(cases.hychem_p(0), YS)
     for alg in (_abi.ALG_AUTO_TSIT5_ROS23, _abi.ALG_ROSENBROCK23, _abi.ALG_KENCARP4, _abi.ALG_TSIT5):
         value(f"hychem_f2_{ALGN[alg]}", mh, cases.hychem_u0, cases.hychem_opts(alg=alg), 65536, 8192)
-    # robertson on the generic path with the composite algorithm (stiff generating mechanism)
+    # the composite algorithm on the dimension-specialised thread-per-trajectory kernel (k_auto_value) and, for contrast,
+    # on the generic lane-per-component kernel (3 of 32 lanes busy for robertson)
     cr = cases.CASES["robertson"]
     value("robertson_true_auto", cases.true_model_robertson(), lambda n: synth.make_u0("robertson", n),
           cr.opts(alg=_abi.ALG_AUTO_TSIT5_ROS23, pred_clamp=(-np.inf, np.inf)), 262144, 16384)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "checkpoints.json")))
+    c2 = cases.CASES["case2"]
+    m2, _ = c2.model(np.array(golden["case2"]["p"]))
+    value("case2_auto", m2, lambda n: synth.make_u0("case2", n), c2.opts(alg=_abi.ALG_AUTO_TSIT5_ROS23), 65536, 16384)
+    os.environ["CRNN_B200_FORCE_WIDE"] = "1"
+    value("robertson_true_auto_generic_kernel", cases.true_model_robertson(), lambda n: synth.make_u0("robertson", n),
+          cr.opts(alg=_abi.ALG_AUTO_TSIT5_ROS23, pred_clamp=(-np.inf, np.inf)), 262144, 16384)
+    value("case2_auto_generic_kernel", m2, lambda n: synth.make_u0("case2", n), c2.opts(alg=_abi.ALG_AUTO_TSIT5_ROS23), 65536, 16384)
+    os.environ["CRNN_B200_FORCE_WIDE"] = "0"
     # HyChem gradient (np = 211) by the adjoints, non-stiff variant
     mg, seedg = cases.hychem_model(cases.hychem_p(0, lnA_shift=-2.0), YS)
     N = 65536
