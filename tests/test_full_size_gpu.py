@@ -1,0 +1,101 @@
+"""BASELINE configs 3, 4, 5 at their full per-GPU sizes: size-independent properties (conservation laws, idempotence
+of the sharded sum, agreement between independent gradient algorithms) plus a random sample against the oracle."""
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases, synth
+from oracle import oracle
+from problems import make_problem, trained_p
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config3_robertson_262144(engine, golden):
+    """robertson, Rosenbrock23 with the analytic Jacobian + in-register LU, 262 144 ICs on one B200"""
+    c = cases.CASES["robertson"]
+    N = 262144
+    u0 = synth.make_u0("robertson", N)
+    o = c.opts(pred_clamp=(-np.inf, np.inf))
+    tr = engine.solve_batch(cases.true_model_robertson(), o, u0)
+    assert (tr["retcode"] == _abi.RET_SUCCESS).all() and (tr["n_saved"] == 40).all()
+    y = tr["pred"]
+    # y1 + y2 + y3 is conserved by the mechanism (rober_crnn.jl:56-63), by every Rosenbrock stage and by the dense output
+    mass = y.sum(axis=2)
+    assert np.abs(mass - u0.sum(axis=1)[:, None]).max() < 1e-9
+    assert y.min() > -1e-6 and (np.diff(y[:, :, 2], axis=1) > -1e-9).all()     # y3 only grows
+    # the composite algorithm lands on the same solution within the tolerance
+    ta = engine.solve_batch(cases.true_model_robertson(), c.opts(alg=_abi.ALG_AUTO_TSIT5_ROS23, pred_clamp=(-np.inf, np.inf)), u0)
+    assert (ta["retcode"] == _abi.RET_SUCCESS).all()
+    assert (np.abs(ta["pred"] - y) / np.abs(y).max(axis=(0, 1))).max() < 2e-2
+    # trained stiff CRNN (the reference's checkpoint): every trajectory integrates, a sample equals the oracle
+    pb = make_problem("robertson", golden, 64)
+    got = engine.solve_batch(pb["model"], pb["opts"], u0)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    idx = np.random.default_rng(0).choice(N, 48, replace=False)
+    ref = oracle.solve_batch(pb["model"], pb["opts"], u0[idx], n_threads=8)
+    assert np.array_equal(got["stats"]["n_accept"][idx], ref["stats"]["n_accept"])
+    assert np.array_equal(got["stats"]["n_reject"][idx], ref["stats"]["n_reject"])
+    assert (np.abs(got["pred"][idx] - ref["pred"]) / np.abs(ref["pred"]).max(axis=(0, 1))).max() < 1e-5
+
+
+def test_config4_case3_adjoint_131072(engine, golden):
+    """case3 (MAPK, np = 153), one GPU's share of the 1 048 576 ICs: loss + gradient by the interpolating adjoint,
+    the discrete adjoint and (on a slice) the 153-column forward mode"""
+    c = cases.CASES["case3"]
+    N = 131072
+    u0 = synth.make_u0("case3", N)
+    o = c.opts(obs_idx=np.arange(c.ns), pred_clamp=(-np.inf, np.inf))
+    tr = engine.solve_batch(cases.true_model_case3(), o, u0)
+    assert (tr["retcode"] == _abi.RET_SUCCESS).all()
+    y = tr["pred"]
+    # MAPK cascade: each kinase's two forms are conserved (case3.jl:83-103): y2+y3, y4+y5, y6+y7, y8+y9
+    for a in (1, 3, 5, 7):
+        tot = y[:, :, a] + y[:, :, a + 1]
+        assert np.abs(tot - tot[:, :1]).max() < 1e-9
+    data = np.abs(synth.noisy_targets(y, 0.05)) + 1e-6
+    ys = synth.yscale_from(data[:4096], c.lb)
+    # a CRNN near the generating mechanism, written in case3.jl's own parametrisation (w_in = clamp(w_in_raw, 0, 4),
+    # w_out = -w_in_raw * |w_out_raw|: a product is a negative w_in_raw), rate constants and orders off by ~10 %.
+    # (With the script's random initialisation the trajectories sit on clamp kinks and the DISCRETE derivative of a few
+    # of them is astronomically large — the continuous adjoint then differs from it by construction.)
+    mt = cases.true_model_case3()
+    g = np.random.default_rng(5)
+    w_in_raw = np.where(mt.w_in > 0, mt.w_in, np.where(mt.w_out > 0, -1.0, 0.0)) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    w_out_raw = np.where(mt.w_out != 0, np.abs(mt.w_out), 0.0) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    p = np.concatenate([0.1 * g.standard_normal(c.nr), w_out_raw.reshape(-1, order="F"), w_in_raw.reshape(-1, order="F"), [0.1]])
+    model, seed = c.model(p)
+    res = {}
+    for name, sm in (("interp", _abi.SENS_INTERP_ADJOINT), ("discrete", _abi.SENS_DISCRETE_ADJOINT)):
+        res[name] = engine.loss_grad_batch(model, c.opts(obs_idx=np.arange(c.ns), sens_mode=sm), seed, u0, data, ys, c.loss_kind)
+        assert (res[name]["retcode"] == _abi.RET_SUCCESS).all()
+    np.testing.assert_array_equal(res["interp"]["loss"], res["discrete"]["loss"])      # same forward solve
+    gd, gi = res["discrete"]["grad_sum"], res["interp"]["grad_sum"]
+    # continuous vs discrete adjoint: equal up to the integration tolerance (reltol 1e-3)
+    assert np.abs(gi - gd).max() < 5e-2 * np.abs(gd).max()
+    # sharded sum == whole-batch sum, as the multi-GPU all-reduce assumes
+    parts = [engine.loss_grad_batch(model, c.opts(obs_idx=np.arange(c.ns), sens_mode=_abi.SENS_DISCRETE_ADJOINT), seed,
+                                    u0[a:b], data[a:b], ys, c.loss_kind)["grad_sum"] for a, b in ((0, 50000), (50000, N))]
+    np.testing.assert_allclose(parts[0] + parts[1], gd, rtol=1e-9, atol=1e-12 * np.abs(gd).max())
+    # forward mode with the value-only norm is the same derivative as the discrete adjoint
+    M = 4096
+    fw = engine.loss_grad_batch(model, c.opts(obs_idx=np.arange(c.ns), err_norm_includes_sens=False), seed, u0[:M], data[:M], ys, c.loss_kind)
+    da = engine.loss_grad_batch(model, c.opts(obs_idx=np.arange(c.ns), sens_mode=_abi.SENS_DISCRETE_ADJOINT), seed, u0[:M], data[:M], ys, c.loss_kind)
+    np.testing.assert_allclose(da["grad_sum"], fw["grad_sum"], rtol=1e-5, atol=1e-8 * np.abs(fw["grad_sum"]).max())
+
+
+def test_config5_hychem_sized_kencarp4_16384(engine):
+    """30 states / 30 reactions, stiff, KenCarp4: one GPU's share of the 131 072 ICs"""
+    N = 16384
+    m = cases.synthetic_stiff_model(); u0 = cases.synthetic_stiff_u0(N); o = cases.synthetic_stiff_opts()
+    got = engine.solve_batch(m, o, u0)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all() and (got["n_saved"] == o.n_save).all()
+    # every reaction is k <-> k molecules: sum(u) is conserved by the mechanism, the ESDIRK stages and the Hermite output
+    assert np.abs(got["pred"].sum(axis=2) - u0[:, :29].sum(axis=1)[:, None]).max() < 1e-6
+    assert got["pred"].min() > -5e-3          # undershoot within the solver tolerance (reltol 1e-3 on O(1) states)
+    # an independent stiff method (Rosenbrock23 on the generic kernel) agrees within the tolerance
+    ros = engine.solve_batch(m, cases.synthetic_stiff_opts(alg=_abi.ALG_ROSENBROCK23), u0[:2048])
+    assert (ros["retcode"] == _abi.RET_SUCCESS).all()
+    assert np.abs(ros["pred"] - got["pred"][:2048]).max() < 2e-2       # O(1) states, two methods at reltol 1e-3
+    idx = np.random.default_rng(0).choice(N, 32, replace=False)
+    ref = oracle.solve_batch(m, o, u0[idx], n_threads=8)
+    assert (np.abs(got["pred"][idx] - ref["pred"]) / np.maximum(np.abs(ref["pred"]).max(axis=(0, 1)), 1e-4)).max() < 5e-3
