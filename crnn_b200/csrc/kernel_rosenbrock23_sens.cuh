@@ -29,6 +29,7 @@ struct alignas(16) RosWarpBuf {
   double x0[C::N], dx0[C::N], r0[C::NR];  // RHS intermediates cached at u_n (Jacobian, dJ*k)
   double v[C::N];                         // value lane's k for the dJ*k products
   double term[2][C::N];
+  double rp[C::NS][8];                    // partial row sums of the norm reduction (RP lanes share one row of `red`)
 };
 
 template <class C, int CT, int WARPS, int MINB>
@@ -362,10 +363,21 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             wb.red[i][lane] = sa;
           }
           __syncwarp();
+          // RP lanes share a row: partial sums of 32/RP skewed (conflict-free) columns, then lane i adds them
+          // (k_tsit5_sens does the same; one lane summing all 32 entries was 10 % of this kernel's instructions)
+          constexpr int RP = NS <= 4 ? 8 : 4, SEG = 32 / RP;
+          if (lane < NS * RP) {
+            const int row = lane / RP, part = lane % RP;
+            double ps = 0.0;
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) ps += wb.red[row][(part * SEG + k + row) & 31];
+            wb.rp[row][part] = ps;
+          }
+          __syncwarp();
           if (lane < NS) {
             double tot = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) tot += wb.red[lane][(k + lane) & 31];
+#pragma unroll
+            for (int pq = 0; pq < RP; ++pq) tot += wb.rp[lane][pq];
             if (pass == 0) rsum = tot; else bsum = tot;
           }
         }
