@@ -109,7 +109,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     if (f2) {  // HyChem mass fractions (kernel_wide_solve.cuh::wide_rhs)
       const TabVal tv = wide_tab(W, tt);
       const double ymw = isp ? clampd(y, W.lb, W.ub) / my_mw : 0.0;
-      const double S = warp_sum(ymw);
+      const double S = wsum(ymw);
       rho = tv.P / (kGasRu * tv.T * S);
       if (isp) xi = lean_log(clampd(rho * ymw * 1e3, W.lb, W.ub));
       else if (lane == ns) xi = -1.0 / W.gas_R / tv.T;
@@ -120,12 +120,14 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     __syncwarp();
     if (lane < nr) {
       double z = sb.w_b[lane];
+#pragma unroll 2
       for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
       s_r[lane] = lean_exp(z);
     }
     __syncwarp();
     double f = 0.0;
     if (isp)
+#pragma unroll 2
       for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], s_r[j], f);
     if (f2) f = f / rho;
     return f;
@@ -148,7 +150,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;
     if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
-    return sqrt(warp_sum(q) / n);
+    return sqrt(wsum(q) / n);
   };
 
   while (true) {
@@ -178,13 +180,13 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       const double sk = my_at + fabs(u) * my_rt;
       double a = 0.0, b = 0.0;
       if (lane < n) { a = u / sk; a *= a; b = k[0] / sk; b *= b; }
-      const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+      const double d0 = sqrt(wsum(a) / n), d1 = sqrt(wsum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
       const double f1 = rhs(t0 + dt0, fma(dt0, k[0], u)); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1 - k[0]) / sk; c *= c; }
-      const double d2 = sqrt(warp_sum(c) / n) / dt0;
+      const double d2 = sqrt(wsum(c) / n) / dt0;
       const double dm = jmax(d1, d2);
       const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * W.inv_order);
       dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
@@ -268,7 +270,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         const TabVal tv = wide_tab(W, tt);
         double Y = 1.0, chi = 0.0, ymw = 0.0;
         if (isp) { Y = clampd(ui, W.lb, W.ub); chi = (ui >= W.lb && ui <= W.ub) ? 1.0 : 0.0; ymw = Y / my_mw; }
-        const double S = warp_sum(ymw);
+        const double S = wsum(ymw);
         const double rho = tv.P / (kGasRu * tv.T * S);
         inv_rho = 1.0 / rho;
         if (isp) {
@@ -293,7 +295,9 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       double brk = 0.0;
       if (lane < nr) {
         double z = sb.w_b[lane], gs = 0.0;
-        for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+#pragma unroll 2
+      for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+#pragma unroll 2
         for (int i = 0; i < ns; ++i) gs = fma(sb.w_out[lane][i], s_lam[i], gs);
         const double r = lean_exp(z);
         s_r[lane] = r;
@@ -304,10 +308,11 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
           brk = (ws - 1.0) * (gs * r);
         }
       }
-      if (f2) brk = warp_sum(brk);
+      if (f2) brk = wsum(brk);
       __syncwarp();
       double s = 0.0;
       if (isp)
+#pragma unroll 2
         for (int j = 0; j < nr; ++j) s = fma(sb.w_inT[lane][j], s_gr[j], s);
       return fma(rrl, brk, dxi * s);
     };
@@ -323,7 +328,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         const double d = __ldg(data + off);
         double diff, g;
         if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
-        else { diff = log(clampd(d, W.pred_lo, W.pred_hi)) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+        else { diff = lib_log(clampd(d, W.pred_lo, W.pred_hi)) - lib_log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }  // one out-of-line copy of log
         loss_acc += fabs(diff);
         if (inside && isp) gret = g / cnt;
       }
@@ -420,7 +425,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
               const double sk = my_at + fabs(lam) * my_rt;
               double a = 0.0, b = 0.0;
               if (lane < n) { a = lam / sk; a *= a; b = K[0] / sk; b *= b; }
-              const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+              const double d0 = sqrt(wsum(a) / n), d1 = sqrt(wsum(b) / n);
               bdt = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
               have_dt = true;
             }
@@ -484,7 +489,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         }
       }
     }
-    const double ltot = warp_sum(loss_acc);
+    const double ltot = wsum(loss_acc);
     __syncwarp();
     for (int e = lane; e < nw; e += 32) gw_each[(size_t)traj * nw + e] = isave > 0 ? GW[e] : 0.0;
     if (lane == 0) {

@@ -49,7 +49,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;
     if (lane < n) { const double sc = my_at + fmax(fabs(a), fabs(b)) * my_rt; q = v / sc; q *= q; }
-    return sqrt(warp_sum(q) / n);
+    return sqrt(wsum(q) / n);
   };
 
   while (true) {
@@ -83,13 +83,13 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       const double sk = my_at + fabs(u) * my_rt;
       double a = 0.0, b = 0.0;
       if (lane < n) { a = u / sk; a *= a; b = f0 / sk; b *= b; }
-      const double d0 = sqrt(warp_sum(a) / n), d1 = sqrt(warp_sum(b) / n);
+      const double d0 = sqrt(wsum(a) / n), d1 = sqrt(wsum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
       const double f1p = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
-      const double d2 = sqrt(warp_sum(c) / n) / dt0;
+      const double d2 = sqrt(wsum(c) / n) / dt0;
       const double dm = jmax(d1, d2);
       const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * P.inv_order);
       dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
@@ -142,7 +142,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         if (autosw) {
           double a = 0.0, b = 0.0;
           if (lane < n) { a = KS(6) - KS(5); a *= a; b = un - g6; b *= b; }
-          eigen_est = sqrt(warp_sum(a) / n) / sqrt(warp_sum(b) / n);
+          eigen_est = sqrt(wsum(a) / n) / sqrt(wsum(b) / n);
         }
       } else {
         // ---- Rosenbrock23 = ode23s: KS(0)=f0, KS(1..3)=k1..k3, KS(4)=f1, KS(5)=f2 ----

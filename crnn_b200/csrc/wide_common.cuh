@@ -52,6 +52,14 @@ __device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
   return v;
 }
 
+// out-of-line warp sum for the lane-per-component kernels: they reduce at dozens of sites (norms, Newton tests), and every
+// inlined copy is ten shuffles plus their convergence-barrier code — instruction-cache pressure is what binds these kernels
+static __device__ __noinline__ double wsum(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
@@ -96,7 +104,7 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
     const TabVal tv = wide_tab(P, t);
     double Y = 1.0, chi = 0.0, ymw = 0.0;
     if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
-    const double S = warp_sum(ymw);
+    const double S = wsum(ymw);
     rho = tv.P / (kGasRu * tv.T * S);
     if (isp) {
       const double C = rho * ymw * 1e3;
@@ -122,13 +130,16 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   __syncwarp();
   if (lane < nr) {
     double z = sb.w_b[lane];
+#pragma unroll 2
     for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
     ww.r[lane] = lean_exp(z);
   }
   __syncwarp();
   double f = 0.0;
-  if (isp)
+  if (isp) {
+#pragma unroll 2
     for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+  }
   a.wdot = f;
   if (F2) f = f / rho;
   return f;
@@ -234,6 +245,7 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
     if (lane > k && isp) {
       const double l = ww.A[lane][k] * rk;
       ww.A[lane][k] = l;
+#pragma unroll 2
       for (int j = k + 1; j < ns; ++j) ww.A[lane][j] = fma(-l, ww.A[k][j], ww.A[lane][j]);
     }
     __syncwarp();
@@ -245,10 +257,12 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
 __device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int ns, double b) {
   const bool isp = lane < ns;
   b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
+#pragma unroll 2
   for (int k = 0; k + 1 < ns; ++k) {
     const double bk = __shfl_sync(0xffffffffu, b, k);
     if (lane > k && isp) b = fma(-ww.A[lane][k], bk, b);
   }
+#pragma unroll 2
   for (int k = ns - 1; k >= 0; --k) {
     if (lane == k) b = b * ww.dinv[k];
     const double bk = __shfl_sync(0xffffffffu, b, k);
