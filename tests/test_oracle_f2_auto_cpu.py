@@ -206,3 +206,23 @@ def test_reversible_crnn_is_an_f0_model_with_twice_the_reactions():
     r = oracle.solve_batch(mt, cases.CASES["case1_rev"].opts(), u0)
     assert (r["retcode"] == _abi.RET_SUCCESS).all()
     np.testing.assert_allclose(r["pred"].sum(axis=2), u0.sum(axis=1)[:, None] * np.ones((1, 100)), rtol=1e-9)
+
+
+def test_golden_oracle_vectors_f2_auto():
+    """Regression pin of the oracle's F2 / AutoTsit5 / adjoint-with-F2 parts (tests/golden/make_oracle_vectors_f2.py)."""
+    import json, os, importlib.util
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("mk_f2", os.path.join(here, "make_oracle_vectors_f2.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    gv = json.load(open(os.path.join(here, "oracle_vectors_f2_auto.json")))
+    for name, (m, o, u0) in mk.problems().items():
+        r = oracle.solve_batch(m, o, u0)
+        for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+            assert r["stats"][k].tolist() == gv[name][k], (name, k)
+        np.testing.assert_allclose(r["pred"][:, ::7, :], np.array(gv[name]["pred_every7"]), rtol=1e-6, atol=1e-12)
+    m, seed, u0, data = mk.gradient_problem()
+    for mode, sm in (("forward", _abi.SENS_FORWARD), ("discrete", _abi.SENS_DISCRETE_ADJOINT), ("interp", _abi.SENS_INTERP_ADJOINT)):
+        r = oracle.loss_grad_batch(m, cases.hychem_opts(alg=ALG["tsit5"], sens_mode=sm), seed, u0, data, YS)
+        v = gv[f"hychem_grad_{mode}"]
+        np.testing.assert_allclose(r["loss"], v["loss"], rtol=1e-9)
+        np.testing.assert_allclose(r["grad_sum"], v["grad_sum"], rtol=1e-6, atol=1e-9 * np.abs(v["grad_sum"]).max())

@@ -24,6 +24,8 @@ for name in ("case2", "case1", "case3", "robertson"):
         done.append(f"{name} adjoints")
     o = pb["case"].opts(obs_idx=pb["opts"].obs_idx, alg=_abi.ALG_KENCARP4)
     eng.solve_batch(pb["model"], o, pb["u0"]); done.append(f"{name} kencarp4")
+    eng.solve_batch(pb["model"], pb["case"].opts(obs_idx=pb["opts"].obs_idx, alg=_abi.ALG_AUTO_TSIT5_ROS23), pb["u0"])
+    done.append(f"{name} auto (thread per trajectory)")
     os.environ["CRNN_B200_FORCE_WIDE"] = "1"
     for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23):
         if name == "robertson" and alg == _abi.ALG_TSIT5:
