@@ -234,3 +234,36 @@ def test_reversible_crnn_case1_rev_on_the_generic_path(engine):
     fwd = oracle.loss_grad_batch(m, of, seed, u0, data, ys, c.loss_kind, n_threads=8)
     np.testing.assert_allclose(ga["loss"], fwd["loss"], rtol=1e-9)
     np.testing.assert_allclose(ga["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())
+
+
+def test_generic_path_edge_cases_empty_single_nan_weights(engine):
+    """N = 0, N = 1, and a model whose weights contain NaN (retcode, no abort) on the generic kernels"""
+    m, seed = cases.hychem_model(cases.hychem_p(0, lnA_shift=-2.0), YS_HYCHEM)
+    for alg in ALG.values():
+        o = cases.hychem_opts(alg=alg)
+        r0 = engine.solve_batch(m, o, np.zeros((0, 9)))
+        assert r0["pred"].shape == (0, 40, 9) and r0["retcode"].shape == (0,)
+        u1 = cases.hychem_u0(1)
+        r1 = engine.solve_batch(m, o, u1)
+        ref1 = oracle.solve_batch(m, o, u1)
+        _counts_equal(r1, ref1)
+        assert _rel_err(r1["pred"], ref1["pred"]) < 1e-9
+    data = ref1["pred"] * 1.02
+    for sm in (_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT):
+        o = cases.hychem_opts(alg=ALG["tsit5"], sens_mode=sm)
+        g0 = engine.loss_grad_batch(m, o, seed, np.zeros((0, 9)), np.zeros((0, 40, 9)), YS_HYCHEM)
+        assert g0["loss"].shape == (0,) and np.all(g0["grad_sum"] == 0.0)
+        g1 = engine.loss_grad_batch(m, o, seed, u1, data, YS_HYCHEM)
+        gr = oracle.loss_grad_batch(m, o, seed, u1, data, YS_HYCHEM)
+        np.testing.assert_allclose(g1["loss"], gr["loss"], rtol=1e-9)
+        np.testing.assert_allclose(g1["grad_sum"], gr["grad_sum"], rtol=1e-6, atol=1e-9 * np.abs(gr["grad_sum"]).max())
+    # NaN in the weights: every trajectory reports a failure code, the batch still returns (rober_crnn.jl:130-134 prints and goes on)
+    import copy
+    mb = copy.deepcopy(m); mb.w_b = mb.w_b.copy(); mb.w_b[3] = np.nan
+    u8 = cases.hychem_u0(8)
+    for alg in ALG.values():
+        o = cases.hychem_opts(alg=alg)
+        rb = engine.solve_batch(mb, o, u8)
+        rr = oracle.solve_batch(mb, o, u8)
+        assert np.array_equal(rb["retcode"], rr["retcode"]) and (rb["retcode"] != _abi.RET_SUCCESS).all()
+        assert np.array_equal(rb["n_saved"], rr["n_saved"])
