@@ -104,7 +104,7 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
   const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
   int rcw = build_wide(h, m, o, order, {}, st, P, nullptr);
   if (rcw) return rcw;
-  constexpr int WARPS = 4;
+  constexpr int WARPS = 7;   // two blocks of seven warps per SM (shared memory: 24.8 KB per block + 12.4 KB per warp)
   auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_wide_solve<WARPS, true> : k_wide_solve<WARPS, false>;
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -131,9 +131,9 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
   if (rcw) return rcw;
-  constexpr int WARPS = 4;
+  constexpr int WARPS = 8;   // two blocks of eight warps per SM
   auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_kencarp4_wide<WARPS, true> : k_kencarp4_wide<WARPS, false>;
-  const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
+  const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarpT<0>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));

@@ -19,7 +19,7 @@
 namespace crnn {
 
 template <int WARPS, bool F2>
-__global__ void __launch_bounds__(WARPS * 32, 3)
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 3 : 2)
 k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
              long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
              crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {

@@ -66,15 +66,17 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-struct alignas(16) WideWarp {
+template <int NK>   // NK stage-vector slots (k_wide_solve: 7; k_kencarp4_wide keeps its stages in registers: 0)
+struct alignas(16) WideWarpT {
   double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
   double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
   int perm[KW_MAXN];
   // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
   double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
   double dinv[KW_MAXN];  // 1/u_kk of the LU: back-substitution multiplies instead of dividing
-  double k[7][KW_MAXN];
+  double k[NK > 0 ? NK : 1][NK > 0 ? KW_MAXN : 2];
 };
+using WideWarp = WideWarpT<7>;
 
 struct alignas(16) WideBlock {
   double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
@@ -92,8 +94,8 @@ struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobi
 };
 
 // f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
-template <bool F2>
-__device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double mw,
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WW& ww, int lane, double mw,
                                            double t, double y, WideAux& a) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
   const bool isp = lane < ns;
@@ -146,8 +148,8 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
 }
 
 // df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
-template <bool F2>
-__device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane, double t,
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WW& ww, int lane, double t,
                                                   const double* rsrc, const WideAux& a) {
   if (!F2) return 0.0;
   const int ns = P.ns, nr = P.nr;
@@ -175,8 +177,8 @@ __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBloc
 
 // W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
 // pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
-template <bool F2>
-__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WideWarp& ww, int lane,
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WW& ww, int lane,
                                                 const double* rsrc, const WideAux& a, double gdt) {
   const int n = P.n, ns = P.ns, nr = P.nr;
   const bool isp = lane < ns;
@@ -254,7 +256,8 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
 }
 
 // b <- W^{-1} b with the factored W in ww.A (lane i holds b_i)
-__device__ __forceinline__ double wide_lusolve(const WideWarp& ww, int lane, int ns, double b) {
+template <class WW>
+__device__ __forceinline__ double wide_lusolve(const WW& ww, int lane, int ns, double b) {
   const bool isp = lane < ns;
   b = __shfl_sync(0xffffffffu, b, ww.perm[lane]);
 #pragma unroll 2
