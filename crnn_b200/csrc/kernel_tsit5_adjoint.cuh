@@ -338,6 +338,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     auto accum = [&](double* dst, double bw) {
 #pragma unroll
       for (int q = 0; q < ADJ_MAX_ENT; ++q) {
+        if (32 * q >= nw) break;  // uniform: the remaining entries are empty for every lane
         const int code = ent[q];
         if (code >= 0) {
           const int kind = code >> 16, i = (code >> 8) & 255, j = code & 255;
