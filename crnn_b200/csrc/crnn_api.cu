@@ -180,10 +180,14 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   P.nw = nw; P.loss_kind = loss_kind;
   P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
   constexpr int WARPS = 4;
-  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_tsit5_adjoint<WARPS, true> : k_tsit5_adjoint<WARPS, false>;
+  // blocks per SM: three (12 warps, <= 168 registers) unless CRNN_B200_ADJ_BLOCKS=2 asks for the two-block build
+  static const int minb = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return e ? std::atoi(e) : 3; }();
+  const bool f2 = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP;
+  auto kern = minb == 3 ? (f2 ? k_tsit5_adjoint<WARPS, true, 3> : k_tsit5_adjoint<WARPS, false, 3>)
+                        : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
   const int stride = 8 * n + 2;
-  // forward-record capacity in shared memory: two blocks of 4 warps per SM
-  const size_t budget = (size_t)(227 * 1024 / 2) - 2048 - sizeof(WideBlock);
+  // forward-record capacity in shared memory: `minb` blocks of 4 warps per SM
+  const size_t budget = (size_t)(227 * 1024 / (minb == 3 ? 3 : 2)) - 2048 - sizeof(WideBlock);
   const size_t fixed_pw = (160 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
   if (fixed_pw * WARPS > budget) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
   P.cap_s = (int)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
@@ -194,7 +198,10 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
   if (bps < 1) bps = 1;
   const long long max_blocks = (long long)h->num_sms * bps;
-  CK(h->adj_scratch.reserve((size_t)max_blocks * WARPS * P.cap_g * stride * sizeof(double)));
+  // overflow record (steps beyond cap_s): one region per block and warp, and one copy PER PIPELINE SLOT — the chunks of the
+  // host-buffer path run their kernels concurrently on the slots' streams and must not share it
+  const size_t scratch_doubles = (size_t)max_blocks * WARPS * P.cap_g * stride;
+  CK(h->adj_scratch.reserve(scratch_doubles * (o->buffers_on_device ? 1 : kPipe) * sizeof(double)));
   P.scratch = h->adj_scratch.as<double>();
   PostFn post = [=](const double* red, double* out, cudaStream_t s) -> int {
     k_seed_contract<<<1, 256, 0, s>>>(seed_dev, red, nw, np, out);
@@ -208,8 +215,10 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
     const unsigned blocks = (unsigned)std::min<long long>(max_blocks, want);
     unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
     CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    AdjP Pl = P;
+    if (b.qslot >= 2) Pl.scratch = P.scratch + scratch_doubles * (size_t)(b.qslot - 2);
     ProfScope prof(h, s);
-    kern<<<blocks, WARPS * 32, smem, s>>>(P, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved,
+    kern<<<blocks, WARPS * 32, smem, s>>>(Pl, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved,
                                        b.retcode, b.stats, queue);
     CK(cudaGetLastError());
     h->launches++;

@@ -50,8 +50,8 @@ struct AdjP {
 
 constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
 
-template <int WARPS, bool F2>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <int WARPS, bool F2, int MINB = 2>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
                 long long ntraj, const double* __restrict__ data, double* __restrict__ loss,
                 double* __restrict__ gw_each, double* __restrict__ pred, int* __restrict__ n_saved,

@@ -68,7 +68,8 @@ def test_config4_case3_adjoint_131072(engine, golden):
     for name, sm in (("interp", _abi.SENS_INTERP_ADJOINT), ("discrete", _abi.SENS_DISCRETE_ADJOINT)):
         res[name] = engine.loss_grad_batch(model, c.opts(obs_idx=np.arange(c.ns), sens_mode=sm), seed, u0, data, ys, c.loss_kind)
         assert (res[name]["retcode"] == _abi.RET_SUCCESS).all()
-    np.testing.assert_array_equal(res["interp"]["loss"], res["discrete"]["loss"])      # same forward solve
+    # same forward solve (the two sweeps evaluate the dense output in differently contracted copies: rounding-level)
+    np.testing.assert_allclose(res["interp"]["loss"], res["discrete"]["loss"], rtol=1e-12)
     gd, gi = res["discrete"]["grad_sum"], res["interp"]["grad_sum"]
     # continuous vs discrete adjoint: equal up to the integration tolerance (reltol 1e-3)
     assert np.abs(gi - gd).max() < 5e-2 * np.abs(gd).max()
