@@ -272,7 +272,7 @@ int launch_ros_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, in
     return fail(h, CRNN_ERR_UNSUPPORTED, "Rosenbrock23 forward sensitivities need n_species <= 6");
   } else {
     if (b.n == 0) return CRNN_OK;
-    constexpr int WARPS = 4, MINB = 2;
+    constexpr int WARPS = 4, MINB = 3;
     auto kern = k_rosenbrock23_sens<C, CT, WARPS, MINB>;
     const size_t smem = sizeof(SensSmem<C, CT, true>) + WARPS * sizeof(RosWarpBuf<C, CT>);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
