@@ -145,8 +145,13 @@ class Case:
     loss_kind: int
     maxiters: int = 100000
     log_saveat: bool = False
+    saveat_fn: object = None      # custom save grid (HyChem's `_tsteps`)
+    model_extra: object = None    # extra CRNNModel fields (F2: gas_R, mw, tab_t, tab_T, tab_P)
+    sens_mode: int = _abi.SENS_FORWARD
 
     def saveat(self) -> np.ndarray:
+        if self.saveat_fn is not None:
+            return self.saveat_fn()
         if self.log_saveat:  # tsteps = 10 .^ range(0, 5, length=datasize), rober_crnn.jl:48
             return 10.0 ** np.linspace(0.0, 5.0, self.n_save)
         return np.linspace(self.tspan[0], self.tspan[1], self.n_save)
@@ -154,13 +159,13 @@ class Case:
     def model(self, p, out_scale=None):
         w_in, w_b, w_out, seed = self.p2vec(p)
         m = CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=self.rhs_kind, lb=self.lb, ub=self.ub,
-                      out_scale=out_scale)
+                      out_scale=out_scale, **(self.model_extra or {}))
         return m, seed
 
     def opts(self, **kw) -> SolveOpts:
         base = dict(saveat=self.saveat(), t0=self.tspan[0], t1=self.tspan[1], alg=self.alg,
                     abstol=self.abstol, reltol=self.reltol, maxiters=self.maxiters,
-                    pred_clamp=self.pred_clamp)
+                    pred_clamp=self.pred_clamp, sens_mode=self.sens_mode)
         base.update(kw)
         return SolveOpts(**base)
 
@@ -396,3 +401,15 @@ def true_model_case1_rev(lb=1e-30) -> CRNNModel:
 
 CASES["case1_rev"] = Case("case1_rev", 5, 20, 60, _abi.RHS_F0, 1e-5, INF, _abi.ALG_TSIT5, 1e-6, 1e-3,
                           (0.0, 10.0), 100, p2vec_case1_rev, (-INF, INF), _abi.LOSS_MAE_SCALED, maxiters=10000)
+
+
+def hychem_case(t_end=0.01, alg=_abi.ALG_TSIT5, sens_mode=_abi.SENS_DISCRETE_ADJOINT) -> Case:
+    """HyChem/crnn_pyrolysis_mass.jl as a `Case` for the front-end mirror (`CRNNProblem(hychem_case(), ...)`, with
+    `out_scale = yscale / t_end`): F2 RHS under the synthetic T(t), P(t) tables, the script's tolerances and save grid.
+    The gradient of its 211 parameters comes from the adjoint kernels (Tsit5), see DESIGN.md §3.2d / §8."""
+    tab_t, tab_T, tab_P = hychem_tables(t_end)
+    ts = hychem_saveat(t_end)
+    return Case("hychem", 9, 10, 211, _abi.RHS_F2, 1e-8, 10.0, alg, 1e-8, 1e-3, (0.0, float(ts[-1])), 40, p2vec_hychem,
+                (-INF, INF), _abi.LOSS_MAE_SCALED, maxiters=10000, saveat_fn=lambda: hychem_saveat(t_end),
+                model_extra=dict(gas_R=HYCHEM_GAS_R, mw=HYCHEM_MW, tab_t=tab_t, tab_T=tab_T, tab_P=tab_P),
+                sens_mode=sens_mode)

@@ -42,3 +42,26 @@ def test_case2_training_loop_descends_like_the_reference(engine, golden):
     loss_b, grad_b = prob.loss_grad(p_end, np.arange(n_exp_train))
     grads = [prob.loss_grad(p_end, i)[1] for i in range(n_exp_train)]
     np.testing.assert_allclose(grad_b, np.mean(grads, axis=0), rtol=1e-9, atol=1e-12)
+
+
+def test_hychem_training_loop_with_the_adjoint_gradient(engine):
+    """HyChem/crnn_pyrolysis_mass.jl's loop (:197-212) on the engine: F2 RHS, 211 parameters, random time truncation
+    `sample = rand(batch_size:ntotal)`, gradient clipping at 10, ADAMW(5e-3) — with the gradient from the discrete
+    adjoint kernel instead of 18 chunked ForwardDiff re-solves.  Synthetic targets from a second random CRNN of the same
+    shape (the script's data file is not in the reference tree); non-stiff variant, see DESIGN.md §8.1."""
+    ys = np.array([0.05, 0.01, 0.01, 0.01, 0.02, 0.9, 0.01, 1e-4, 1e-3])
+    c = cases.hychem_case()
+    n_exp = 8
+    u0 = cases.hychem_u0(n_exp)
+    m_true, _ = c.model(cases.hychem_p(1, lnA_shift=-2.0), out_scale=ys / 0.01)
+    data = engine.solve_batch(m_true, c.opts(alg=1), u0)["pred"]                  # targets by Rosenbrock23
+    yscale = np.maximum(data.max(axis=(0, 1)) - data.min(axis=(0, 1)), 1e-8)      # clamp.(ymax - ymin, lb, Inf) (:71)
+    prob = CRNNProblem(c, u0, data, yscale, out_scale=ys / 0.01, engine=engine)
+    p0 = cases.hychem_p(0, lnA_shift=-2.0)
+    g = np.random.default_rng(0)
+    opt = optim.ADAMW(0.005, (0.9, 0.999), 1e-6)
+    p_end, hist = prob.train(p0, opt, n_epoch=40, n_exp_train=n_exp, batch=n_exp, grad_max=10.0, rng=g, sample_range=(32, 40))
+    losses = [h[0] for h in hist]
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
+    assert min(losses) > 0.0
