@@ -164,6 +164,8 @@ int crnn_profile_begin(crnn_handle* h);
 int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches);
 
 /* predict_neuralode for a batch of N initial conditions.
+ * Every alg (Tsit5, Rosenbrock23, KenCarp4, AutoTsit5(Rosenbrock23)) and every rhs_kind is served for n_state, n_in,
+ * n_reac <= 32; the (n_species, n_reac, rhs_kind) of the reference scripts run dimension-specialised kernels.
  *   u0      [n_state, N]
  *   n_save_used [N] or NULL: trajectory i integrates only to
  *           saveat[n_save_used[i]-1] (random time truncation, rober_crnn.jl:218)
@@ -175,6 +177,9 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
                      crnn_stats* stats);
 
 /* loss_neuralode + its gradient for a batch.
+ * sens_mode FORWARD (ForwardDiff semantics: every dual column rides the adaptive solve, partials in the error norm):
+ *   Tsit5 (np <= 255) and Rosenbrock23 (np <= 63, n_species <= 6) for the reference scripts' dimensions, F0 / F1.
+ * sens_mode INTERP_ADJOINT / DISCRETE_ADJOINT: Tsit5, any dimensions <= 32, any np, n_w <= 512, F0 / F1 / F2.
  *   dW_dp   [n_w, np] col-major HOST seed matrix = Jacobian of p2vec, with the
  *           n_w = n_reac*(n_in + 1 + n_species) rows ordered
  *           [vec(w_in); w_b; vec(w_out)]
