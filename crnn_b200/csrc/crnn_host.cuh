@@ -236,13 +236,13 @@ int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& 
 }
 
 // ---------------- sensitivity path launchers ----------------
-template <class C, int CT, bool R1, int WPT = 1>
+template <class C, int CT, bool R1, int WPT = 1, int NGRP = 0>
 int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
                 cudaStream_t st) {
   if (b.n == 0) return CRNN_OK;
   // warps per block: 16 warps/SM in two blocks for the single-warp layouts; one or two warp
-  // groups per block when WPT warps share a trajectory
-  constexpr int WARPS = WPT == 1 ? (CT == 1 ? 8 : 4) : (WPT <= 4 ? 2 * WPT : WPT);
+  // groups per block when WPT warps share a trajectory (NGRP overrides the number of groups)
+  constexpr int WARPS = WPT == 1 ? (CT == 1 ? 8 : 4) : (NGRP > 0 ? NGRP * WPT : (WPT <= 4 ? 2 * WPT : WPT));
   constexpr int MINB = WPT == 1 ? 2 : 1;
   auto kern = k_tsit5_sens<C, CT, WARPS, MINB, R1, WPT>;
   const size_t smem = sizeof(SensSmem<C, CT, R1, WPT>) + WARPS * sizeof(WarpBuf<C, CT>);
@@ -544,7 +544,13 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
     if (ros) return ct == 1 ? launch_ros_sens<C, 1>(h, mp, sp, ncol, b, s) : launch_ros_sens<C, 2>(h, mp, sp, ncol, b, s);
     if (r1 && ct > 2) {  // several warps per trajectory
       if (ct <= 3) return launch_sens<C, 1, true, 3>(h, mp, sp, ncol, b, s);
-      if (ct <= 5) return launch_sens<C, 1, true, 5>(h, mp, sp, ncol, b, s);
+      if (ct <= 5) {
+        // two trajectories per block (and per SM) when their stage vectors fit the 227 KB: case3's np = 153 does
+        // (224 KB), and a block of one group leaves the SM with a single trajectory in flight between barriers
+        constexpr size_t smem2 = sizeof(SensSmem<C, 1, true, 5>) + 10 * sizeof(WarpBuf<C, 1>);
+        if constexpr (smem2 <= 227 * 1024) return launch_sens<C, 1, true, 5, 2>(h, mp, sp, ncol, b, s);
+        else return launch_sens<C, 1, true, 5>(h, mp, sp, ncol, b, s);
+      }
       return launch_sens<C, 1, true, 8>(h, mp, sp, ncol, b, s);
     }
     if (r1) return ct == 1 ? launch_sens<C, 1, true>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, true>(h, mp, sp, ncol, b, s);
