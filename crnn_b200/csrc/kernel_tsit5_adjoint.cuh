@@ -60,11 +60,11 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const WideP& W = P.w;
   const int n = W.n, ns = W.ns, nin = W.nin, nr = W.nr, nw = P.nw;
   const int stride = 8 * n + 2;  // doubles per recorded step: t, dt, u, k1..k7
-  WideBlock& sb = *reinterpret_cast<WideBlock*>(smem_raw);
+  WideBlockLite& sb = *reinterpret_cast<WideBlockLite*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] | GW[nw] GS[nw] | record[cap_s][stride]
   const size_t per_warp = 5 * 32 + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
-  double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlock)) + per_warp * warp;
+  double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlockLite)) + per_warp * warp;
   double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
   double* s_chi = wbase + 128;
   double* GW = wbase + 160; double* GS = GW + ((nw + 1) & ~1);
@@ -74,7 +74,6 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
     const int i = q / KW_MAXN, j = q % KW_MAXN;
     sb.w_inT[i][j] = (i < nin && j < nr) ? W.w_inT[i * KW_MAXN + j] : 0.0;
-    sb.w_inJ[j][i] = sb.w_inT[i][j];
     sb.w_out[i][j] = (i < nr && j < ns) ? W.w_out[j + ns * i] : 0.0;  // [reaction][species], scaled
   }
   for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? W.w_b[q] : 0.0;

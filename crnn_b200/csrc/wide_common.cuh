@@ -85,6 +85,13 @@ struct alignas(16) WideBlock {
   double w_b[KW_MAXN];
 };
 
+// the adjoint kernel assembles no Jacobian: no reaction-major copy of w_in (8 KB more room for its step record)
+struct alignas(16) WideBlockLite {
+  double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
+  double w_out[KW_MAXN][KW_MAXN];  // [j][i]
+  double w_b[KW_MAXN];
+};
+
 struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobian needs)
   double dx;       // d x_l / d u_l (F2: at fixed density)
   double rr;       // F2: d log(rho) / d u_l = -chi_l / (MW_l S)
