@@ -267,3 +267,23 @@ def test_generic_path_edge_cases_empty_single_nan_weights(engine):
         rr = oracle.solve_batch(mb, o, u8)
         assert np.array_equal(rb["retcode"], rr["retcode"]) and (rb["retcode"] != _abi.RET_SUCCESS).all()
         assert np.array_equal(rb["n_saved"], rr["n_saved"])
+
+
+@pytest.mark.parametrize("force_wide", [False, True])
+def test_autoswitch_back_to_tsit5_when_the_stiffness_goes_away(engine, monkeypatch, force_wide):
+    """A -> B slow, B -> C fast: B sits in quasi-steady state (stiff: Tsit5 alone needs 13 000 steps, the composite hands
+    over to Rosenbrock23) until it falls below the lb clamp, where its Jacobian column vanishes and the composite must
+    switch BACK to Tsit5 (dt /= 2, controller exponents of order 5 again).  Both GPU formulations against the oracle."""
+    if force_wide:
+        monkeypatch.setenv("CRNN_B200_FORCE_WIDE", "1")
+    w_out = np.zeros((3, 3)); w_out[:, 0] = [-1, 1, 0]; w_out[:, 1] = [0, -1, 1]
+    m = CRNNModel(w_in=np.eye(3), w_b=np.log([1.0, 1e4, 1e-30]), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=1e-6, ub=np.inf)
+    g = np.random.default_rng(0)
+    u0 = np.c_[0.5 + g.random(192), 1e-4 * g.random(192), 0.1 * g.random(192)]
+    o = SolveOpts(saveat=np.linspace(0.0, 10.0, 26), t0=0.0, t1=10.0, alg=ALG["auto"], abstol=1e-8, reltol=1e-4, maxiters=200000)
+    got = engine.solve_batch(m, o, u0)
+    ref = oracle.solve_batch(m, o, u0, n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    tsit5_attempts = got["stats"]["n_accept"] + got["stats"]["n_reject"] - got["stats"]["n_jac"]
+    assert (got["stats"]["n_jac"] > 20).all() and (tsit5_attempts > 25).all()   # > the ~12 attempts before the first switch
