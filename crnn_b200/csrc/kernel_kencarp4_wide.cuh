@@ -61,7 +61,8 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
 
   const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
   // f(y, t), W = I - gdt*J and the triangular solves come from wide_common.cuh (all RHS flavours)
-  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2>(P, sb, ww, lane, my_mw, tt, y, ax); };
+  int tab_seg = 0;  // F2: segment hint of the T(t), P(t) lookup
+  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2>(P, sb, ww, lane, my_mw, tt, y, ax, tab_seg); };
   auto lusolve = [&](double b) -> double { return wide_lusolve(ww, lane, ns, b); };
   auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { (void)wide_build_lu<F2>(P, sb, ww, lane, rsrc, ax, gdt); };
   // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)

@@ -102,11 +102,12 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
   };
   // forward RHS: lane i holds y_i -> f_i (x, r left in shared memory)
+  int tab_seg = 0;  // F2: segment hint of the T(t), P(t) lookup
   auto rhs = [&](double tt, double y) -> double {
     __syncwarp();
     double xi = 0.0, rho = 1.0;
     if (f2) {  // HyChem mass fractions (kernel_wide_solve.cuh::wide_rhs)
-      const TabVal tv = wide_tab(W, tt);
+      const TabVal tv = wide_tab(W, tt, tab_seg);
       const double ymw = isp ? clampd(y, W.lb, W.ub) / my_mw : 0.0;
       const double S = wsum(ymw);
       rho = tv.P / (kGasRu * tv.T * S);
@@ -266,7 +267,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       __syncwarp();
       double xi = 0.0, dxi = 0.0, rrl = 0.0, chiC = 0.0, inv_rho = 1.0;
       if (f2) {
-        const TabVal tv = wide_tab(W, tt);
+        const TabVal tv = wide_tab(W, tt, tab_seg);
         double Y = 1.0, chi = 0.0, ymw = 0.0;
         if (isp) { Y = clampd(ui, W.lb, W.ub); chi = (ui >= W.lb && ui <= W.ub) ? 1.0 : 0.0; ymw = Y / my_mw; }
         const double S = wsum(ymw);

@@ -72,9 +72,9 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
     };
 
-    int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
+    int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0, tab_seg = 0;
     WideAux a0, as;  // by-products at u_n / at the last evaluation
-    KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0, u, a0); ++n_rhs;
+    KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0, u, a0, tab_seg); ++n_rhs;
     ww.r0[lane] = ww.r[lane];
     // ---- initial step (Hairer-Wanner; the order of the FIRST algorithm) ----
     double dt;
@@ -86,7 +86,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       const double d0 = sqrt(wsum(a) / n), d1 = sqrt(wsum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
-      const double f1p = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as); ++n_rhs;
+      const double f1p = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as, tab_seg); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(wsum(c) / n) / dt0;
@@ -110,7 +110,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         else if (rosen && sw_count < -3) { dt = dt / 2.0; want = false; }
         if (want != rosen) {
           rosen = want;
-          KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t, u, a0); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
+          KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t, u, a0, tab_seg); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
           __syncwarp();
           ww.r0[lane] = ww.r[lane];
         }
@@ -133,7 +133,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
           const double y = fma(dt, acc, u);
           if (s == 5) g6 = y;
           un = y;
-          KS(s) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as); ++n_rhs;
+          KS(s) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as, tab_seg); ++n_rhs;
         }
         double acc = tsc::BT[0] * KS(0);
 #pragma unroll
@@ -148,16 +148,16 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         // ---- Rosenbrock23 = ode23s: KS(0)=f0, KS(1..3)=k1..k3, KS(4)=f1, KS(5)=f2 ----
         const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
         const double g = d * dt;
-        const double dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, ww.r0, a0);
+        const double dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, ww.r0, a0, tab_seg);
         const double eig = wide_build_lu<F2>(P, sb, ww, lane, ww.r0, a0, g);
         ++n_jac;
         if (autosw) eigen_est = eig;
         const double f0 = KS(0);
         const double k1 = wide_lusolve(ww, lane, ns, fma(g, dTv, f0));
-        const double f1 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as); ++n_rhs;
+        const double f1 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as, tab_seg); ++n_rhs;
         const double k2 = wide_lusolve(ww, lane, ns, f1 - k1) + k1;
         un = fma(dt, k2, u);
-        const double f2 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + dt, un, as); ++n_rhs;
+        const double f2 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + dt, un, as, tab_seg); ++n_rhs;
         const double k3 = wide_lusolve(ww, lane, ns, f2 - e32 * (k2 - f1) - 2.0 * (k1 - f0) + dt * dTv);
         e = dt / 6.0 * (k1 - 2.0 * k2 + k3);
         KS(1) = k1; KS(2) = k2; KS(5) = f2;

@@ -36,14 +36,23 @@ constexpr double kGasRu = 8.31446261815324e3;  // HyChem/crnn_pyrolysis_mass.jl:
 
 struct TabVal { double T, P, Td, Pd; };
 
-// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t
-__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t) {
-  int lo = 0, hi = P.n_tab - 1;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
+// Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t.
+// `seg` is the caller's hint (the segment of its previous lookup): stage times move monotonically inside a step, so the
+// hint nearly always holds and the six dependent loads of the binary search are skipped.
+__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t, int& seg) {
+  int lo = seg;
+  double ta = __ldg(P.tab_t + lo), tb = __ldg(P.tab_t + lo + 1);
+  if (!(ta <= t && (t < tb || lo == P.n_tab - 2))) {
+    lo = 0;
+    int hi = P.n_tab - 1;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.tab_t + mid) <= t) lo = mid; else hi = mid;
+    }
+    ta = __ldg(P.tab_t + lo); tb = __ldg(P.tab_t + lo + 1);
+    seg = lo;
   }
-  const double ta = __ldg(P.tab_t + lo), h = __ldg(P.tab_t + lo + 1) - ta, w = (t - ta) / h;
+  const double h = tb - ta, w = (t - ta) / h;
   const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
   const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
   TabVal v;
@@ -103,14 +112,14 @@ struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobi
 // f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
 template <bool F2, class WW>
 __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WW& ww, int lane, double mw,
-                                           double t, double y, WideAux& a) {
+                                           double t, double y, WideAux& a, int& seg) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
   const bool isp = lane < ns;
   __syncwarp();
   double xi = 0.0, rho = 1.0;
   a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
   if (F2) {
-    const TabVal tv = wide_tab(P, t);
+    const TabVal tv = wide_tab(P, t, seg);
     double Y = 1.0, chi = 0.0, ymw = 0.0;
     if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
     const double S = wsum(ymw);
@@ -157,10 +166,10 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
 // df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
 template <bool F2, class WW>
 __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WW& ww, int lane, double t,
-                                                  const double* rsrc, const WideAux& a) {
+                                                  const double* rsrc, const WideAux& a, int& seg) {
   if (!F2) return 0.0;
   const int ns = P.ns, nr = P.nr;
-  const TabVal tv = wide_tab(P, t);
+  const TabVal tv = wide_tab(P, t, seg);
   const double rr = tv.Pd / tv.P - tv.Td / tv.T;
   __syncwarp();
   ww.bchi[lane] = a.chiC;
