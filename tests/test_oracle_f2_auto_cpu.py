@@ -226,3 +226,29 @@ def test_golden_oracle_vectors_f2_auto():
         v = gv[f"hychem_grad_{mode}"]
         np.testing.assert_allclose(r["loss"], v["loss"], rtol=1e-9)
         np.testing.assert_allclose(r["grad_sum"], v["grad_sum"], rtol=1e-6, atol=1e-9 * np.abs(v["grad_sum"]).max())
+
+
+def test_f2_model_validation_and_front_end_case():
+    """host-side checks of the F2 model description (shapes, tables) and the HyChem `Case` of the front-end mirror"""
+    from crnn_b200.model import CRNNModel
+    w_in = np.zeros((11, 10)); w_out = np.zeros((9, 10)); w_b = np.zeros(10)
+    tab = dict(tab_t=[0.0, 1.0], tab_T=[1300.0, 1200.0], tab_P=[1e6, 1e6])
+    with pytest.raises(ValueError):
+        CRNNModel(w_in=w_in[:10], w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F2, mw=cases.HYCHEM_MW, **tab)      # n_in != ns + 2
+    with pytest.raises(ValueError):
+        CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F2, **tab)                               # no molar masses
+    with pytest.raises(ValueError):
+        CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F2, mw=cases.HYCHEM_MW,
+                  tab_t=[0.0, 0.0], tab_T=[1.0, 1.0], tab_P=[1.0, 1.0])                                       # knots not ascending
+    m = CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F2, mw=cases.HYCHEM_MW, **tab)
+    assert (m.n_state, m.n_species, m.n_in, m.n_w) == (9, 9, 11, 10 * (11 + 1 + 9))
+    cm, keep = m.to_c()
+    assert cm.n_tab == 2 and cm.n_state == 9 and cm.n_in == 11
+    c = cases.hychem_case()
+    mc, seed = c.model(cases.hychem_p(0), out_scale=YS / 0.01)
+    mh, _ = cases.hychem_model(cases.hychem_p(0), YS)
+    assert np.array_equal(mc.w_out, mh.w_out) and np.array_equal(mc.tab_T, mh.tab_T) and mc.gas_R == mh.gas_R
+    o = c.opts()
+    assert o.sens_mode == _abi.SENS_DISCRETE_ADJOINT and o.n_save == 40 and o.saveat[0] == 0.0
+    assert abs(o.t1 - 0.01 / 1.01) < 1e-15 and np.all(np.diff(o.saveat) > 0)
+    assert seed.shape == (mc.n_w, 211)
