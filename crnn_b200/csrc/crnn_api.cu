@@ -376,7 +376,17 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
     return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
   CRNN_FOR_EACH_CFG(X)
 #undef X
-  return fail(h, CRNN_ERR_UNSUPPORTED, "no kernel instantiated for this (n_species, n_reac, rhs_kind)");
+  // No dimension-specialised forward-mode kernel.  With the value-only error norm the forward-mode gradient IS the
+  // derivative of the recorded step sequence, i.e. what the discrete adjoint computes (any dimensions <= 32, F2 included).
+  h->last_grad_np = -1; h->last_grad_n = -1;
+  if (o->alg == CRNN_ALG_TSIT5 && !o->err_norm_includes_sens) {
+    crnn_opts oa = *o;
+    oa.sens_mode = CRNN_SENS_DISCRETE_ADJOINT;
+    return loss_grad_adjoint(h, m, &oa, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+  }
+  return fail(h, CRNN_ERR_UNSUPPORTED,
+              "no forward-mode kernel instantiated for this (n_species, n_reac, rhs_kind): use an adjoint sens_mode, or "
+              "err_norm_includes_sens = 0 (served by the discrete adjoint)");
 }
 
 }  // extern "C"

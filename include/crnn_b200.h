@@ -178,7 +178,9 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
 
 /* loss_neuralode + its gradient for a batch.
  * sens_mode FORWARD (ForwardDiff semantics: every dual column rides the adaptive solve, partials in the error norm):
- *   Tsit5 (np <= 255) and Rosenbrock23 (np <= 63, n_species <= 6) for the reference scripts' dimensions, F0 / F1.
+ *   Tsit5 (np <= 255) and Rosenbrock23 (np <= 63, n_species <= 6) for the reference scripts' dimensions, F0 / F1;
+ *   with err_norm_includes_sens = 0 and Tsit5 every other model (<= 32, F2) is served by the discrete adjoint, which
+ *   computes exactly that derivative.
  * sens_mode INTERP_ADJOINT / DISCRETE_ADJOINT: Tsit5, any dimensions <= 32, any np, n_w <= 512, F0 / F1 / F2.
  *   dW_dp   [n_w, np] col-major HOST seed matrix = Jacobian of p2vec, with the
  *           n_w = n_reac*(n_in + 1 + n_species) rows ordered

@@ -234,6 +234,13 @@ def test_reversible_crnn_case1_rev_on_the_generic_path(engine):
     fwd = oracle.loss_grad_batch(m, of, seed, u0, data, ys, c.loss_kind, n_threads=8)
     np.testing.assert_allclose(ga["loss"], fwd["loss"], rtol=1e-9)
     np.testing.assert_allclose(ga["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())
+    # FORWARD with the value-only norm on dimensions without a forward kernel is served by the same discrete adjoint ...
+    gf = engine.loss_grad_batch(m, of, seed, u0, data, ys, c.loss_kind)
+    np.testing.assert_array_equal(gf["grad_sum"], ga["grad_sum"])
+    # ... and with the partials in the norm (a different step sequence) it is refused, not approximated
+    from crnn_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        engine.loss_grad_batch(m, c.opts(sens_mode=_abi.SENS_FORWARD), seed, u0, data, ys, c.loss_kind)
 
 
 def test_generic_path_edge_cases_empty_single_nan_weights(engine):
