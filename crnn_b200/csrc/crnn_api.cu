@@ -181,16 +181,23 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
   constexpr int WARPS = 4;
   // blocks per SM: four (16 warps, 128 registers with 116 B spilled) unless CRNN_B200_ADJ_BLOCKS=2 asks for the two-block build
-  static const int minb = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return e ? std::atoi(e) : 3; }();
+  static const bool want_four = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return !e || std::atoi(e) != 2; }();
   const bool f2 = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP;
-  auto kern = minb == 3 ? (f2 ? k_tsit5_adjoint<WARPS, true, 4> : k_tsit5_adjoint<WARPS, false, 4>)
-                        : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
   const int stride = 8 * n + 2;
-  // forward-record capacity in shared memory: that many blocks of 4 warps per SM
-  const size_t budget = (size_t)(227 * 1024 / (minb == 3 ? 4 : 2)) - 2048 - sizeof(WideBlockLite);
   const size_t fixed_pw = (160 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
-  if (fixed_pw * WARPS > budget) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
-  P.cap_s = (int)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
+  // forward-record capacity in shared memory for `nb` blocks of 4 warps per SM (steps per warp; < 0: does not fit)
+  auto cap_for = [&](int nb) -> long long {
+    const size_t budget = (size_t)(227 * 1024 / nb) - 2048 - sizeof(WideBlockLite);
+    if (fixed_pw * WARPS > budget) return -1;
+    return (long long)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
+  };
+  // large models (n_w towards 512) leave a four-block build no room for the record: they keep two blocks per SM
+  const bool four_blocks = want_four && cap_for(4) >= 4;
+  const long long cap = cap_for(four_blocks ? 4 : 2);
+  if (cap < 1) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
+  auto kern = four_blocks ? (f2 ? k_tsit5_adjoint<WARPS, true, 4> : k_tsit5_adjoint<WARPS, false, 4>)
+                          : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
+  P.cap_s = (int)cap;
   P.cap_g = 512;
   const size_t smem = sizeof(WideBlockLite) + WARPS * (fixed_pw + (size_t)P.cap_s * stride * sizeof(double));
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -294,3 +294,25 @@ def test_autoswitch_back_to_tsit5_when_the_stiffness_goes_away(engine, monkeypat
     assert _rel_err(got["pred"], ref["pred"]) < 1e-8
     tsit5_attempts = got["stats"]["n_accept"] + got["stats"]["n_reject"] - got["stats"]["n_jac"]
     assert (got["stats"]["n_jac"] > 20).all() and (tsit5_attempts > 25).all()   # > the ~12 attempts before the first switch
+
+
+def test_adjoint_on_a_large_model_keeps_two_blocks_per_sm(engine):
+    """n_w = 496 of the 512 the adjoint kernel supports (15 species, 16 reactions): the quadrature accumulators leave a
+    four-block build no room for the step record, the host falls back to two blocks per SM; gradient vs the oracle"""
+    g = np.random.default_rng(8)
+    ns, nr = 15, 16
+    w_in = np.clip(g.normal(0.4, 0.5, (ns, nr)), 0.0, 2.0) * (g.random((ns, nr)) < 0.3)
+    w_out = -w_in * 10.0 ** g.normal(0.0, 0.2, (ns, nr)) + np.abs(g.normal(0.0, 0.3, (ns, nr))) * (w_in == 0.0) * (g.random((ns, nr)) < 0.2)
+    m = CRNNModel(w_in=w_in, w_b=g.normal(-2.5, 0.5, nr), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=1e-6, ub=10.0)
+    assert m.n_w == 496
+    u0 = 0.5 + g.random((64, ns))
+    n_p = 40
+    seed = np.zeros((m.n_w, n_p)); seed[g.choice(m.n_w, n_p, replace=False), np.arange(n_p)] = 1.0   # 40 of the weights are trainable
+    o = SolveOpts(saveat=np.linspace(0.0, 2.0, 21), t0=0.0, t1=2.0, abstol=1e-7, reltol=1e-4, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    data = oracle.solve_batch(m, o, u0, n_threads=8)["pred"] * (1.0 + 0.05 * g.standard_normal((64, 21, ns)))
+    ys = np.ones(ns)
+    got = engine.loss_grad_batch(m, o, seed, u0, data, ys)
+    of = SolveOpts(saveat=o.saveat, t0=0.0, t1=2.0, abstol=1e-7, reltol=1e-4, sens_mode=_abi.SENS_FORWARD, err_norm_includes_sens=False)
+    ref = oracle.loss_grad_batch(m, of, seed, u0, data, ys, n_threads=8)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-9)
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(ref["grad_sum"]).max())
