@@ -237,6 +237,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (crnn_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
     c, model, seed, opts, u0_h, data_h, yscale = build_inputs(eng, rank)
