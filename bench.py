@@ -230,6 +230,10 @@ def main():
             "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes; WARN prints it too)
+    # off it; NCCL caches the setting at its first call, so this has to happen before torch is imported
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]
     import torch
     import torch.distributed as dist
     from crnn_b200.engine import Engine
@@ -237,9 +241,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (crnn_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
     c, model, seed, opts, u0_h, data_h, yscale = build_inputs(eng, rank)
