@@ -23,5 +23,11 @@ for k, r in c.items():
     else:
         L.append(f"{k:36s} {r['N']:7d} {r['ms']:8.2f} ms {r['traj_per_s']/1e6:7.3f} M traj/s  cpu oracle forward mode (211 columns) {r['cpu_oracle_forward_mode_traj_per_s']/1e3:.2f} K traj/s "
                  f"on {r['cpu_cores']} cores ({r['traj_per_s']/r['cpu_oracle_forward_mode_traj_per_s']:.0f}x)")
+import os
+if os.path.exists('gpurun_out/r1_config4_full.json'):
+    f4 = json.load(open('gpurun_out/r1_config4_full.json'))
+    L.append(f"# BASELINE config 4 at its full size on ONE B200: case3 (np = 153), {f4['N']} ICs, {f4['targets_GB']:.2f} GB of targets resident in HBM (tools/measure_config4_full.py)")
+    for k in ('interp_adjoint', 'discrete_adjoint', 'forward_153_columns'):
+        r = f4[k]; L.append(f"case3 {k:22s} {f4['N']:8d} {r['ms']:9.1f} ms {r['traj_per_s']/1e6:6.2f} M traj/s  success {r['success_frac']:.3f}")
 open('profiles/r1_throughput_all_configs.txt', 'w').write("\n".join(L) + "\n")
 print("\n".join(L))
