@@ -413,3 +413,41 @@ def hychem_case(t_end=0.01, alg=_abi.ALG_TSIT5, sens_mode=_abi.SENS_DISCRETE_ADJ
                 (-INF, INF), _abi.LOSS_MAE_SCALED, maxiters=10000, saveat_fn=lambda: hychem_saveat(t_end),
                 model_extra=dict(gas_R=HYCHEM_GAS_R, mw=HYCHEM_MW, tab_t=tab_t, tab_T=tab_T, tab_P=tab_P),
                 sens_mode=sens_mode)
+
+
+# ---- gene-regulatory network (gene-regulatory-network/gene-regulatory.jl): 9 species, 15 reactions, np = 285 ----
+
+def p2vec_gene(p, ns=9, nr=15):
+    """gene-regulatory.jl:39-50: like case3 (w_out = -w_in_raw * |w_out_raw|, w_in = clamp(w_in_raw, 0, 4)) with the
+    three DNA rows of w_out_raw zeroed (`w_out[[1, 4, 7], :] .= 0`: the catalysts are never consumed or produced)."""
+    d = _D.seed(p)
+    w_b = d[0:nr]
+    w_in_raw = d[nr * (ns + 1):nr * (2 * ns + 1)].reshape_f(ns, nr)
+    w_out_raw = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    mask = np.ones((ns, nr)); mask[[0, 3, 6], :] = 0.0
+    w_out_raw = _D(w_out_raw.v * mask, w_out_raw.j * mask[..., None])
+    w_out = (-w_in_raw) * w_out_raw.abs()
+    w_in = w_in_raw.clamp(0.0, 4.0)
+    return _pack(w_in, w_b, w_out)
+
+
+def true_model_gene(lb=1e-30) -> CRNNModel:
+    """trueODEfunc of gene-regulatory.jl:75-131 (k at :141) as an F0 CRNN: transcription / translation with the template
+    as a catalyst, first-order decays, and the cyclic repression mRNA_i + protein_j -> protein_j."""
+    ns, nr = 9, 15
+    k = np.array([1.8, 2.1, 1.3, 1.5, 2.2, 2, 2, 2.5, 3.2, 3, 2.3, 2.5, 6, 4, 3])
+    w_in = np.zeros((ns, nr)); w_out = np.zeros((ns, nr))
+    for g in range(3):                      # gene g: DNA 3g, mRNA 3g+1, protein 3g+2; reactions 4g .. 4g+3
+        dna, mrna, prot = 3 * g, 3 * g + 1, 3 * g + 2
+        w_in[dna, 4 * g] = 1; w_out[mrna, 4 * g] = 1            # DNA -> DNA + mRNA
+        w_in[mrna, 4 * g + 1] = 1; w_out[prot, 4 * g + 1] = 1   # mRNA -> mRNA + protein
+        w_in[mrna, 4 * g + 2] = 1; w_out[mrna, 4 * g + 2] = -1  # mRNA -> 0
+        w_in[prot, 4 * g + 3] = 1; w_out[prot, 4 * g + 3] = -1  # protein -> 0
+    for j, (mrna, prot) in enumerate(((7, 2), (4, 8), (1, 5))):  # R13 = k y8 y3, R14 = k y5 y9, R15 = k y2 y6 (1-based)
+        w_in[[mrna, prot], 12 + j] = 1; w_out[mrna, 12 + j] = -1
+    return CRNNModel(w_in=w_in, w_b=np.log(k), w_out=w_out, rhs_kind=_abi.RHS_F0, lb=lb, ub=INF)
+
+
+# as written: atol 1e-5 / rtol 1e-2 under the silently ignored keywords (SURVEY §0.4) -> the solver defaults
+CASES["gene"] = Case("gene", 9, 15, 285, _abi.RHS_F0, 1e-5, 100.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
+                     (0.0, 4.0), 40, p2vec_gene, (1e-5, 100.0), _abi.LOSS_MAE_SCALED, sens_mode=_abi.SENS_DISCRETE_ADJOINT)

@@ -316,3 +316,25 @@ def test_adjoint_on_a_large_model_keeps_two_blocks_per_sm(engine):
     ref = oracle.loss_grad_batch(m, of, seed, u0, data, ys, n_threads=8)
     np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-9)
     np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(ref["grad_sum"]).max())
+
+
+def test_gene_regulatory_checkpoint_on_the_gpu(engine, golden):
+    """gene-regulatory.jl (9 species, 15 reactions, np = 285 > the forward kernel's 255 columns): the committed checkpoint
+    on the dimension-specialised predict kernel, its gradient by the discrete adjoint vs the oracle's forward mode"""
+    c = cases.CASES["gene"]
+    m, seed = c.model(np.array(golden["gene"]["p"]))
+    u0 = np.random.default_rng(0).random((160, 9))
+    got = engine.solve_batch(m, c.opts(), u0)
+    ref = oracle.solve_batch(m, c.opts(), u0, n_threads=8)
+    _counts_equal(got, ref)
+    assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+    truth = oracle.solve_batch(cases.true_model_gene(), c.opts(pred_clamp=(-np.inf, np.inf)), u0, n_threads=8)["pred"]
+    data = np.clip(truth * (1.0 + 0.01 * np.random.default_rng(2).standard_normal(truth.shape)), c.lb, c.ub)
+    ys = np.ones(9)
+    ga = engine.loss_grad_batch(m, c.opts(), seed, u0, data, ys, c.loss_kind)
+    assert 1e-3 < ga["loss"].mean() < 1.5e-2                          # the checkpoint's loss level on 1 %-noisy data
+    of = c.opts(sens_mode=_abi.SENS_FORWARD, err_norm_includes_sens=False)
+    fwd = oracle.loss_grad_batch(m, of, seed, u0[:48], data[:48], ys, c.loss_kind, n_threads=8)
+    g48 = engine.loss_grad_batch(m, c.opts(), seed, u0[:48], data[:48], ys, c.loss_kind)
+    np.testing.assert_allclose(g48["loss"], fwd["loss"], rtol=1e-9)
+    np.testing.assert_allclose(g48["grad_sum"], fwd["grad_sum"], rtol=1e-6, atol=1e-8 * np.abs(fwd["grad_sum"]).max())
