@@ -65,3 +65,21 @@ def test_hychem_training_loop_with_the_adjoint_gradient(engine):
     assert np.isfinite(losses).all()
     assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
     assert min(losses) > 0.0
+
+
+def test_readme_python_example_runs(engine):
+    """the code block under 'Using it from Python' in README.md, executed as written"""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "README.md")).read()
+    block = re.search(r"## Using it from Python.*?```python\n(.*?)```", txt, flags=re.S).group(1)
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        ns = {}
+        exec(compile(block, "README.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    assert ns["pred"].shape == (6, 50) and np.isfinite(ns["loss"]) and ns["grad"].shape == (25,)
+    assert len(ns["hist"]) == 10 and ns["hist"][-1][0] < 0.05
+    ns["eng"].close()
