@@ -185,3 +185,54 @@ def test_two_rank_shard_and_allreduce_over_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK 2" in r.stdout
+
+
+# ---------------------------------------------------------------- BSON.jl checkpoints (host-side utility)
+def test_checkpoint_round_trip(tmp_path):
+    from crnn_b200 import checkpoint as ck
+    p = np.random.default_rng(0).standard_normal(25)
+    f = str(tmp_path / "mymodel.bson")
+    ck.save(f, p, 3700, l_loss_train=[0.139, 0.0165], l_loss_val=[0.1235, 0.01396])
+    c = ck.load(f)
+    assert np.array_equal(c["p"], p) and c["iter"] == 3700 and c["opt"] is None
+    np.testing.assert_allclose(c["l_loss_train"], [0.139, 0.0165], rtol=1e-7)      # Float32 on disk, like the reference's
+    np.testing.assert_allclose(c["l_loss_val"], [0.1235, 0.01396], rtol=1e-7)
+    raw = open(f, "rb").read()
+    doc, end = ck.parse(raw)
+    assert end == len(raw) and ck.encode(doc) == raw
+    assert list(doc.keys()) == ["iter", "p", "l_loss_train", "l_loss_val"] and doc["p"]["type"]["name"] == ["Core", "Float64"]
+    # matrices are stored column-major, like Julia
+    m = np.arange(6.0).reshape(2, 3)
+    node = ck.lower_array(m)
+    assert node["size"] == [2, 3] and np.array_equal(ck.resolve({}, node), m)
+    assert np.frombuffer(bytes(node["data"])).tolist() == [0.0, 3.0, 1.0, 4.0, 2.0, 5.0]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the authoring container")
+def test_checkpoint_reader_writer_speak_the_reference_dialect(golden):
+    """the four checkpoints the reference commits: parse -> encode is byte-exact, our array lowering equals theirs node for
+    node, and the decoded parameter vectors are the golden fixtures"""
+    from crnn_b200 import checkpoint as ck
+    for name, key in (("case2", "case2"), ("robertson", "robertson"), ("gene-regulatory-network", "gene"), ("yeast-glycolysis", None)):
+        path = f"/root/reference/{name}/checkpoint/mymodel.bson"
+        raw = open(path, "rb").read()
+        doc, end = ck.parse(raw)
+        assert end == len(raw) and ck.encode(doc) == raw, name
+        c = ck.load(path)
+        node = doc["p"]
+        if isinstance(node, dict) and node.get("tag") == "backref":
+            node = doc["_backrefs"][node["ref"] - 1]
+        assert ck.encode(ck.lower_array(c["p"])) == ck.encode(node), name
+        if key:
+            assert np.array_equal(c["p"], np.array(golden[key]["p"])) and c["iter"] == golden[key]["iter"]
+        hist = [k for k in c if k.startswith("l_loss") or k.startswith("list_loss")]
+        assert len(hist) >= 1 and all(len(c[k]) == c["iter"] for k in hist), name
+    # carrying the optimiser state and the shared-object table over: still a well-formed document with the same p
+    import tempfile
+    c = ck.load("/root/reference/case2/checkpoint/mymodel.bson")
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "resaved.bson")
+        ck.save(f, c["p"], c["iter"] + 1, opt=c["opt"], backrefs=c["doc"]["_backrefs"], l_loss_train=c["l_loss_train"], l_loss_val=c["l_loss_val"])
+        c2 = ck.load(f)
+        assert np.array_equal(c2["p"], c["p"]) and c2["iter"] == c["iter"] + 1 and c2["opt"] == c["opt"]
+        np.testing.assert_allclose(c2["l_loss_train"], c["l_loss_train"], rtol=0, atol=0)
