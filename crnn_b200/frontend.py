@@ -99,3 +99,20 @@ class CRNNProblem:
             if callback is not None:
                 callback(p, loss_train, loss_val)
         return p, history
+
+
+def save_checkpoint(path, p, history, iter_=None):
+    """`@save "./checkpoint/mymodel.bson" p opt l_loss_train l_loss_val iter` (case2/case2.jl:178) for a `train` history
+    (list of (loss_train, loss_val, grad_norm)); see crnn_b200/checkpoint.py for what is and is not written."""
+    from . import checkpoint
+    checkpoint.save(path, p, len(history) if iter_ is None else iter_,
+                    l_loss_train=[h[0] for h in history], l_loss_val=[h[1] for h in history])
+
+
+def load_checkpoint(path):
+    """`@load` (case2/case2.jl:183-186): -> (p, iter, l_loss_train, l_loss_val); also reads the reference's own files."""
+    from . import checkpoint
+    c = checkpoint.load(path)
+    tr = c.get("l_loss_train", c.get("list_loss_train", []))
+    va = c.get("l_loss_val", c.get("list_loss_val", []))
+    return c["p"], c["iter"], tr, va
