@@ -80,36 +80,51 @@ def _pack(w_in: _D, w_b: _D, w_out: _D):
     return w_in.v.copy(), w_b.v.copy(), w_out.v.copy(), np.asfortranarray(seed)
 
 
-def p2vec_case1(p, ns=5, nr=4, b0=-10.0):
-    """case1/case1.jl:70-78."""
+def _hard_threshold(x: "_D", cutoff: float, ref=None) -> "_D":
+    """`w[findall(abs.(w) .< p_cutoff)] .= 0` of the pruning scripts (case1_hardthreshhold.jl:76-77, case2_pruning.jl:105-106);
+    `ref` is the array the threshold is tested on when it is not `x` itself (case3_pruning.jl:243-247)."""
+    if not cutoff:
+        return x
+    keep = (np.abs(x.v if ref is None else ref) >= cutoff).astype(np.float64)
+    return _D(x.v * keep, x.j * keep[..., None])
+
+
+def p2vec_case1(p, ns=5, nr=4, b0=-10.0, p_cutoff=0.0):
+    """case1/case1.jl:70-78; `p_cutoff` > 0: the evaluate-only pruned variant, case1_hardthreshhold.jl:72-81."""
     d = _D.seed(p)
     w_b = d[0:nr] + b0
-    w_out = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_out = _hard_threshold(d[nr:nr * (ns + 1)].reshape_f(ns, nr), p_cutoff)
     w_in = (-w_out).clamp(0.0, 2.5)
     return _pack(w_in, w_b, w_out)
 
 
-def p2vec_case2(p, ns=6, nr=3):
-    """case2/case2.jl:91-99; last row of w_in is the Arrhenius Ea row."""
+def p2vec_case2(p, ns=6, nr=3, p_cutoff=0.0):
+    """case2/case2.jl:91-99; last row of w_in is the Arrhenius Ea row.  `p_cutoff` > 0: case2_pruning.jl:98-117."""
     d = _D.seed(p)
     slope = d[nr * (ns + 2)] * 100.0
     slope_v = slope.broadcast_scalar((nr,))
     w_b = d[0:nr] * slope_v
-    w_out = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
+    w_out = _hard_threshold(d[nr:nr * (ns + 1)].reshape_f(ns, nr), p_cutoff)
     w_in_Ea = (d[nr * (ns + 1):nr * (ns + 2)] * slope_v).abs()
     w_in = (-w_out).clamp(0.0, 4.0)
     w_in = _D(np.vstack([w_in.v, w_in_Ea.v[None, :]]), np.concatenate([w_in.j, w_in_Ea.j[None, :, :]], axis=0))
     return _pack(w_in, w_b, w_out)
 
 
-def p2vec_case3(p, ns=9, nr=8):
-    """case3/case3.jl:42-53 (p[end] is unused by the weights)."""
+def p2vec_case3(p, ns=9, nr=8, p_cutoff=0.0, dy_std=None):
+    """case3/case3.jl:42-53 (p[end] is unused by the weights).  `p_cutoff` > 0: case3_pruning.jl:233-250 — w_out is tested
+    after scaling each reaction's column by dy_std and normalising by its largest entry, w_in on its own magnitude."""
     d = _D.seed(p)
     w_b = d[0:nr]
     w_in_raw = d[nr * (ns + 1):nr * (2 * ns + 1)].reshape_f(ns, nr)
     w_out_raw = d[nr:nr * (ns + 1)].reshape_f(ns, nr)
     w_out = (-w_in_raw) * w_out_raw.abs()
     w_in = w_in_raw.clamp(0.0, 4.0)
+    if p_cutoff:
+        scaled = w_out.v * (np.ones(ns) if dy_std is None else np.asarray(dy_std, dtype=np.float64).reshape(-1))[:, None]
+        scaled = scaled / scaled.max(axis=0, keepdims=True)      # maximum(w_out_, dims=2) per reaction (signed, as written)
+        w_out = _hard_threshold(w_out, p_cutoff, ref=scaled)
+        w_in = _hard_threshold(w_in, p_cutoff)
     return _pack(w_in, w_b, w_out)
 
 

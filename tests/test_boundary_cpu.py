@@ -236,3 +236,35 @@ def test_checkpoint_reader_writer_speak_the_reference_dialect(golden):
         c2 = ck.load(f)
         assert np.array_equal(c2["p"], c["p"]) and c2["iter"] == c["iter"] + 1 and c2["opt"] == c["opt"]
         np.testing.assert_allclose(c2["l_loss_train"], c["l_loss_train"], rtol=0, atol=0)
+
+
+def test_pruned_p2vec_variants(golden):
+    """the evaluate-only pruning scripts: hard thresholds inside p2vec (case1_hardthreshhold.jl:76-77, case2_pruning.jl:105-106,
+    case3_pruning.jl:243-247) — the engine serves them unchanged, the map zeroes weights and their seed rows"""
+    p = np.array(golden["case2"]["p"])
+    w_in, w_b, w_out, seed = cases.p2vec_case2(p, p_cutoff=0.2)
+    w_in0, w_b0, w_out0, _ = cases.p2vec_case2(p)
+    raw = p[3:21].reshape(3, 6).T
+    assert np.array_equal(w_out == 0.0, np.abs(raw) < 0.2) and (np.abs(raw) < 0.2).sum() >= 5
+    assert np.array_equal(w_out[w_out != 0], w_out0[w_out != 0]) and np.array_equal(w_b, w_b0)
+    assert np.all(w_in[:6][w_out == 0.0] == 0.0) and np.array_equal(w_in[6], w_in0[6])       # Ea row untouched
+    off_out = 7 * 3 + 3
+    assert np.all(seed[off_out:][(w_out == 0.0).reshape(-1, order="F")] == 0.0)              # pruned weights do not train
+    # the pruned trained model still follows the generating mechanism (the trained w_out is near-integer, SURVEY App. D.1)
+    from oracle import oracle
+    c = cases.CASES["case2"]
+    u0 = synth.make_u0("case2", 16)
+    m = cases.CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, rhs_kind=_abi.RHS_F1, lb=c.lb, ub=c.ub)
+    m0, _ = c.model(p)
+    a = oracle.solve_batch(m, c.opts(obs_idx=np.arange(6)), u0)["pred"]
+    b = oracle.solve_batch(m0, c.opts(obs_idx=np.arange(6)), u0)["pred"]
+    assert np.abs(a - b).max() < 0.05
+    g = np.random.default_rng(0)
+    p1 = g.standard_normal(24)
+    w_in1, _, w_out1, _ = cases.p2vec_case1(p1, p_cutoff=0.5)
+    assert np.array_equal(w_out1 == 0.0, np.abs(p1[4:].reshape(4, 5).T) < 0.5) and np.all(w_in1[w_out1 == 0.0] == 0.0)
+    p3 = (g.random(153) - 0.5) * 2 * np.sqrt(6 / 17)
+    w_in3, _, w_out3, seed3 = cases.p2vec_case3(p3, p_cutoff=0.1, dy_std=np.linspace(0.5, 1.5, 9))
+    w_in3f, _, w_out3f, _ = cases.p2vec_case3(p3)
+    assert (w_out3 == 0).sum() > (w_out3f == 0).sum() and np.all(np.abs(w_in3[w_in3 != 0]) >= 0.1)
+    assert np.array_equal(w_out3[w_out3 != 0], w_out3f[w_out3 != 0])
