@@ -268,3 +268,56 @@ def test_pruned_p2vec_variants(golden):
     w_in3f, _, w_out3f, _ = cases.p2vec_case3(p3)
     assert (w_out3 == 0).sum() > (w_out3f == 0).sum() and np.all(np.abs(w_in3[w_in3 != 0]) >= 0.1)
     assert np.array_equal(w_out3[w_out3 != 0], w_out3f[w_out3 != 0])
+
+
+def test_julia_shim_structs_follow_the_header():
+    """julia/CRNNB200.jl cannot be executed here (no Julia): at least its struct mirrors must list the header's fields in the
+    header's order with matching widths, and every ccall must name an exported symbol."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    jl = open(os.path.join(ROOT, "julia", "CRNNB200.jl")).read()
+    jl_nocomment = re.sub(r"#.*", "", jl)
+    ctype = {"int32_t": "Int32", "int64_t": "Int64", "double": "Float64"}
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, flags=re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)", decl)
+            base, ptr, names = m.group(2), m.group(3), m.group(4)
+            for nm in names.split(","):
+                nm = nm.strip()
+                is_ptr = bool(ptr) or nm.startswith("*")
+                nm = nm.lstrip("* ")
+                if base == "void":
+                    jt = "Ptr{Cvoid}"
+                else:
+                    jt = f"Ptr{{{ctype[base]}}}" if is_ptr else ctype[base]
+                out.append((nm, jt))
+        return out
+
+    def jl_fields(struct):
+        body = re.search(r"struct %s\n(.*?)\nend" % struct, jl_nocomment, flags=re.S).group(1)
+        return [(n, t) for n, t in re.findall(r"(\w+)::([\w{}]+)", body)]
+
+    assert jl_fields("CModel") == c_fields("crnn_model")
+    assert jl_fields("COpts") == c_fields("crnn_opts")
+    called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", jl))
+    assert called and called <= set(_abi.EXPORTS), called - set(_abi.EXPORTS)
+    assert {"crnn_create", "crnn_destroy", "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_last_error"} <= called
+    # every ccall passes as many arguments as the C prototype declares
+    flat = re.sub(r"\s+", " ", hdr)
+    for fn in called:
+        proto = re.search(r"\b%s\s*\((.*?)\)\s*;" % fn, flat).group(1)
+        n_c = 0 if proto.strip() in ("", "void") else proto.count(",") + 1
+        m = re.search(r"ccall\(\(:%s, LIB\), \w+,\s*\((.*?)\),\s*\n?\s*(.*?)\)\)?\s*(?:\n|$)" % fn, jl, flags=re.S)
+        types = m.group(1)
+        depth = 0; n_j = 1 if types.strip() else 0
+        for ch in types:
+            depth += ch == "{"; depth -= ch == "}"
+            n_j += (ch == "," and depth == 0)
+        if types.rstrip().endswith(","):
+            n_j -= 1
+        assert n_j == n_c, (fn, n_j, n_c)
