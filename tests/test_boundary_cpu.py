@@ -3,6 +3,7 @@ every symbol include/crnn_b200.h declares (no compute calls: there is no GPU her
 mirror matches the header, the product path fails loudly without CUDA, and the host-side
 pieces (optimisers, sharding, synthetic inputs, the world_size-2 exchange over gloo) work."""
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -321,3 +322,24 @@ def test_julia_shim_structs_follow_the_header():
         if types.rstrip().endswith(","):
             n_j -= 1
         assert n_j == n_c, (fn, n_j, n_c)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a small sample: exactly one JSON line with the
+    contract's keys; needs no GPU"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-sample", "512"], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "trajectories/s" and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and "workload" in d["config"]
+    # a non-zero rank of a torchrun launch exits silently
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                        text=True, cwd=ROOT, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
