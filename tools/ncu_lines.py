@@ -16,13 +16,13 @@ def main():
         if r[0] == "Function Name": continue
         if r[0] == "Line No":
             hdr = r; ia = hdr.index("Instructions Executed"); ism = hdr.index("# Samples")
-            iw = hdr.index("L1 Wavefronts Shared"); continue
+            iw = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else -1; continue
         if hdr is None: continue
         if r[0] != "":
             cur = (fname, r[0], r[1].strip()[:90])
             a = agg.setdefault(cur, [0, 0, 0])
             try:
-                a[0] += int(r[ia]); a[1] += int(r[ism]); a[2] += int(r[iw] or 0)
+                a[0] += int(r[ia]); a[1] += int(r[ism]); a[2] += int(r[iw] or 0) if iw >= 0 else 0
             except (ValueError, IndexError):
                 pass
     tot = sum(v[0] for v in agg.values()) or 1; ts = sum(v[1] for v in agg.values()) or 1
