@@ -48,6 +48,8 @@ class COpts(C.Structure):
         ("qmin", C.c_double), ("qmax", C.c_double), ("gamma", C.c_double),
         ("beta1", C.c_double), ("beta2", C.c_double),
         ("stream", C.c_void_p),
+        ("qsteady_min", C.c_double), ("qsteady_max", C.c_double),
+        ("err_norm_mean_over_state_only", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -50,6 +50,11 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * order);
   P.beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * order);
   P.inv_order = 1.0 / order;
+  {
+    const bool implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4);
+    P.qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
+    P.qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
+  }
   P.maxiters = o->maxiters;
   P.n = n; P.ns = ns; P.nin = nin; P.nr = nr; P.kind = m->rhs_kind;
   P.n_save = o->n_save; P.n_obs = o->n_obs;

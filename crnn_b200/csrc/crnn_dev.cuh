@@ -39,6 +39,8 @@ struct SolveP {
   double t0, t1, pred_lo, pred_hi;
   double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
   double beta1_ros, beta2_ros;  // AutoTsit5: PI exponents while the Rosenbrock23 half runs
+  double qs_min, qs_max;        // step_accept_controller!'s dead-band: qs_min <= q <= qs_max keeps dt
+  double norm_cnt;              // divisor of the dual-aware norms: totallength(u) = N*(1+np), or N (crnn_opts)
   long long maxiters;
   const double* saveat;  // device [n_save]
   const int* row2obs;    // device [N]: observation slot of state row i, or -1

@@ -190,6 +190,11 @@ int pack(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* 
   sp.maxiters = o->maxiters;
   sp.n_save = o->n_save; sp.n_obs = o->n_obs;
   sp.incl_sens = o->err_norm_includes_sens;
+  // qsteady defaults: 1 / 1 for explicit and composite algorithms, 1 / (6//5) for the adaptive implicit ones
+  const bool implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4);
+  sp.qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
+  sp.qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
+  sp.norm_cnt = (double)C::N;  // loss_grad_impl multiplies by (1 + np) when the partials share the mean
   sp.loss_kind = loss_kind;
   return CRNN_OK;
 }
@@ -522,6 +527,7 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   ModelP<C> mp; SolveP<C> sp; Packed pk;
   int rc = pack<C>(h, m, o, yscale, loss_kind, mp, sp, pk);
   if (rc) return rc;
+  if (o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) sp.norm_cnt = (double)C::N * ncol;  // totallength(u)
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   rc = upload_cfg<C>(h, o, pk, sp, st);
   if (rc) return rc;

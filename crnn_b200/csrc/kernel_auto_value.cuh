@@ -213,7 +213,7 @@ k_auto_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     if (EEst <= 1.0) {
       ++n_acc;
       qold = jmax(EEst, 1e-4);
-      const double dtnew = dt / q;
+      const double dtnew = dt / (q >= sp.qs_min && q <= sp.qs_max ? 1.0 : q);  // steady-state dead-band
       const double tprev = t;
       t = snap_t(t + dt, tend);
       while (isave < nsave) {

@@ -401,8 +401,8 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
 
         if (phase == PH_F0) {
           if (C::KIND == 1) { const double a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]); s1 = fma(a, a, s1); }
-          const double d0 = sqrt(s1 / N);
-          d1 = sqrt(s0 / N);
+          const double d0 = sqrt(s1 / sp.norm_cnt);
+          d1 = sqrt(s0 / sp.norm_cnt);
           dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
           dt0 = jmin(dt0, dtmax);
 #pragma unroll
@@ -411,7 +411,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             for (int i = 0; i < NS; ++i) Y[tt][i] = fma(dt0, wb.K[f0s][tt][i][lane], U[tt][i]);
           phase = PH_F1;
         } else if (phase == PH_F1) {
-          const double d2 = sqrt(s0 / N) / dt0;
+          const double d2 = sqrt(s0 / sp.norm_cnt) / dt0;
           const double dm = jmax(d1, d2);
           const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
           dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
@@ -432,14 +432,14 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
           bsum = asum;
           phase = PH_SAVE;
         } else {
-          const double EEst = sqrt(s0 / N);
+          const double EEst = sqrt(s0 / sp.norm_cnt);
           double q11;
           const double q = pi_controller<C>(sp, EEst, qold, q11);
           dt_last = dt;
           if (EEst <= 1.0) {
             ++n_acc;
             qold = jmax(EEst, 1e-4);
-            dtnew = dt / q;
+            dtnew = dt / (q >= sp.qs_min && q <= sp.qs_max ? 1.0 : q);  // steady-state dead-band
             tprev = t;
             t = snap_t(t + dt, tend);
             phase = PH_SAVE;

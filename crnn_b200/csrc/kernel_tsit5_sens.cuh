@@ -436,8 +436,8 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const double Tval = __ldg(u0 + traj * N + NS), a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]);
               s1 = fma(a, a, s1);
             }
-            const double d0 = sqrt(s1 / N);
-            const double d1 = sqrt(s0 / N);
+            const double d0 = sqrt(s1 / sp.norm_cnt);
+            const double d1 = sqrt(s0 / sp.norm_cnt);
             const double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
             dt = jmin(dt0, wb.cold[1]);
             dtnew = d1;
@@ -445,7 +445,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           } else if (phase == PH_F1) {
             // initial step size, part 2; then the pseudo-step that saves t0
             const double dt0 = dt, d1 = dtnew;
-            const double d2 = sqrt(s0 / N) / dt0;
+            const double d2 = sqrt(s0 / sp.norm_cnt) / dt0;
             const double dm = jmax(d1, d2);
             const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
             dt = jmin(jmin(100.0 * dt0, dt1), wb.cold[1]);
@@ -463,7 +463,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             phase = PH_SAVE;
           } else {
             // all seven stages done: PI controller, accept / reject
-            const double EEst = sqrt(s0 / N);
+            const double EEst = sqrt(s0 / sp.norm_cnt);
             double q11;
             const double q = pi_controller<C>(sp, EEst, qold, q11);
             if (isval[0]) wb.cold[3] = dt;

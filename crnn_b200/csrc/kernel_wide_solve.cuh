@@ -174,7 +174,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       if (EEst <= 1.0) {
         ++n_acc;
         qold = jmax(EEst, 1e-4);
-        const double dtnew = dt / q, tprev = t;
+        const double dtnew = dt / (q >= P.qs_min && q <= P.qs_max ? 1.0 : q), tprev = t;  // steady-state dead-band
         t = snap_t(t + dt, tend);
         while (isave < nsave) {
           const double tsv = __ldg(P.saveat + isave);

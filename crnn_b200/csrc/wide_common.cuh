@@ -14,6 +14,7 @@ struct WideP {
   double lb, ub, gas_R;
   double t0, t1, pred_lo, pred_hi;
   double inv_qmin, inv_qmax, gamma, beta1, beta2, inv_order;
+  double qs_min, qs_max;  // step_accept_controller!'s dead-band
   long long maxiters;
   const double* w_inT;   // device [n_in][nrp]: w_in transposed (reaction fastest), nrp = 32
   const double* w_b;     // device [n_reac]

@@ -121,7 +121,9 @@ class SolveOpts:
     pred_clamp: tuple[float, float] = (-np.inf, np.inf)
     sens_mode: int = _abi.SENS_FORWARD
     err_norm_includes_sens: bool = True
-    controller: dict = field(default_factory=dict)  # qmin,qmax,gamma,beta1,beta2 overrides
+    # True: DiffEqBase's norm over Dual arrays, mean over n_state*(1+np) numbers; False: over n_state rows
+    err_norm_mean_over_partials: bool = True
+    controller: dict = field(default_factory=dict)  # qmin,qmax,gamma,beta1,beta2,qsteady_min,qsteady_max overrides
 
     def to_c(self, n_state: int, buffers_on_device: bool = False, stream: int = 0):
         saveat = _f64(self.saveat).reshape(-1)
@@ -146,8 +148,9 @@ class SolveOpts:
         o.t0, o.t1 = float(self.t0), float(self.t1)
         o.pred_clamp_lo, o.pred_clamp_hi = float(self.pred_clamp[0]), float(self.pred_clamp[1])
         o.abstol, o.reltol, o.saveat, o.obs_idx = dptr(abstol), dptr(reltol), dptr(saveat), iptr(obs)
-        for k in ("qmin", "qmax", "gamma", "beta1", "beta2"):
+        for k in ("qmin", "qmax", "gamma", "beta1", "beta2", "qsteady_min", "qsteady_max"):
             setattr(o, k, float(self.controller.get(k, 0.0)))
+        o.err_norm_mean_over_state_only = int(not self.err_norm_mean_over_partials)
         o.stream = C.c_void_p(stream)
         return o, [saveat, abstol, reltol, obs]
 

@@ -45,7 +45,8 @@
 extern "C" {
 #endif
 
-#define CRNN_B200_VERSION 101 /* 0.1.1: F2 RHS, AutoTsit5(Rosenbrock23), generic-dimension solve path */
+#define CRNN_B200_VERSION 200 /* 0.2.0: DiffEqBase dual norm (mean over n_state*(1+np)), qsteady dead-band, device-resident
+                                 datasets, single-process multi-GPU handles */
 
 typedef struct crnn_handle crnn_handle;
 
@@ -140,6 +141,16 @@ typedef struct crnn_opts {
   const int32_t* obs_idx;         /* [n_obs] 0-based rows of u that are observed (case2.jl:131) */
   double qmin, qmax, gamma, beta1, beta2; /* step controller; <= 0 selects the OrdinaryDiffEq defaults */
   void* stream;                   /* cudaStream_t, used when buffers_on_device == 1 */
+  /* Dead-band of step_accept_controller!: qsteady_min <= q <= qsteady_max keeps dt.  <= 0 selects OrdinaryDiffEq's
+   * defaults: 1 / 1 (no dead-band) for Tsit5 and the AutoTsit5 composite, 1 / 1.2 for the adaptive implicit
+   * algorithms Rosenbrock23 and KenCarp4 (qsteady_max_default(::OrdinaryDiffEqAdaptiveImplicitAlgorithm) = 6//5). */
+  double qsteady_min, qsteady_max;
+  /* Divisor of the dual-aware norms when err_norm_includes_sens == 1.
+   * 0 (default): DiffEqBase's ODE_DEFAULT_NORM over Dual arrays, sqrt(sum(sse) / totallength(u)) — the mean runs over
+   *    all n_state*(1+np) numbers;
+   * 1: the mean runs over the n_state rows only (what releases before 0.2.0 did). */
+  int32_t err_norm_mean_over_state_only;
+  int32_t reserved0;
 } crnn_opts;
 
 typedef struct crnn_stats {

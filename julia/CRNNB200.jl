@@ -29,6 +29,8 @@ struct COpts
     abstol::Ptr{Float64}; reltol::Ptr{Float64}; saveat::Ptr{Float64}; obs_idx::Ptr{Int32}
     qmin::Float64; qmax::Float64; gamma::Float64; beta1::Float64; beta2::Float64
     stream::Ptr{Cvoid}
+    qsteady_min::Float64; qsteady_max::Float64
+    err_norm_mean_over_state_only::Int32; reserved0::Int32
 end
 
 mutable struct Engine
@@ -76,7 +78,7 @@ function with_structs(f, s::Setup, w_in, w_b, w_out)
         o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
-                  0.0, 0.0, 0.0, 0.0, 0.0, C_NULL)
+                  0.0, 0.0, 0.0, 0.0, 0.0, C_NULL, 0.0, 0.0, 0, 0)
         f(Ref(m), Ref(o))
     end
 end

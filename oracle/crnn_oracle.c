@@ -41,6 +41,8 @@ typedef struct {
   const double* seed; /* [nw, np] col-major */
   double qmin, qmax, gamma, beta1, beta2;
   double beta1_alg[2], beta2_alg[2]; /* AutoTsit5: controller exponents of the CURRENT algorithm (0 Tsit5, 1 Rosenbrock23) */
+  double qs_min, qs_max;            /* qsteady dead-band of step_accept_controller! */
+  double norm_cnt;                  /* divisor of the (dual-aware) norms: totallength(u) = n*(1+np), or n */
   int order;
 } ctx_t;
 
@@ -266,8 +268,11 @@ static void djac_vec(const ctx_t* c, const rhs_cache* k, const double* S, const 
   for (int i = ns; i < c->n; ++i) out[i] = 0.0;
 }
 
-/* DiffEqBase norm over (dual) arrays: sse(dual) = value^2 + sum(partials^2),
- * calculate_residuals scale uses the dual magnitude. */
+/* DiffEqBase norm over (dual) arrays (DiffEqBase's ForwardDiff extension):
+ *   ODE_DEFAULT_NORM(u::AbstractArray{<:Dual}, t) = sqrt(sum(sse, u) / totallength(u)),
+ *   sse(dual) = value^2 + sum(partials^2), totallength(u) = n*(1+np);
+ * the scale of calculate_residuals uses the scalar dual magnitude ODE_DEFAULT_NORM(u::Dual, t) = sqrt(sse(u)).
+ * c->norm_cnt holds the divisor (n*(1+np); n with err_norm_mean_over_state_only or a value-only norm). */
 static double err_norm(const ctx_t* c, const double* E, const double* U0, const double* U1) {
   int n = c->n;
   int nc = c->o->err_norm_includes_sens ? c->ncol : 1;
@@ -284,7 +289,7 @@ static double err_norm(const ctx_t* c, const double* E, const double* U0, const 
     double sc = at + mag * rt;
     acc += e2 / (sc * sc);
   }
-  return sqrt(acc / n);
+  return sqrt(acc / c->norm_cnt);
 }
 
 /* rms( V ./ sk ) with sk = abstol + |u0| * reltol, dual-aware. */
@@ -303,7 +308,7 @@ static double initdt_norm(const ctx_t* c, const double* V, const double* U0, dou
     double sk = at + sqrt(a2) * rt;
     acc += v2 / (sk * sk);
   }
-  return sqrt(acc / n);
+  return sqrt(acc / c->norm_cnt);
 }
 
 /* Hairer-Wanner initial step as OrdinaryDiffEq's ode_determine_initdt
@@ -409,28 +414,39 @@ static double snap_t(double tnew, double tend) {
   return tnew;
 }
 
-/* LU with partial pivoting, row-major A[n*n] in place; piv[n].  The diagonal of U is stored INVERTED (1/u_kk, the
- * value the elimination multipliers use anyway) and the back-substitution multiplies by it: on the GPU an fp64
- * division is a ~30-instruction sequence that sat on the serial path of every triangular solve. */
+/* LU with partial pivoting, row-major A[n*n] in place; piv[n]: the generic `lu!` + `ldiv!` OrdinaryDiffEq runs on the
+ * small dense W (LinearAlgebra.generic_lufact! divides the sub-column by the pivot; the triangular solves divide by
+ * the diagonal).  That literal form is the DEFAULT.
+ * Named switch crnn_oracle_set_lu_reciprocal(1): the diagonal of U is stored INVERTED and both the elimination
+ * multipliers and the back-substitution multiply by it — what the CUDA kernels do (an fp64 division is a
+ * ~30-instruction sequence on the serial path of every triangular solve).  The two forms differ by rounding only. */
+static int g_lu_reciprocal = 0;
+void crnn_oracle_set_lu_reciprocal(int on) { g_lu_reciprocal = on; }
+int crnn_oracle_get_lu_reciprocal(void) { return g_lu_reciprocal; }
 static void lu_factor(double* A, int* piv, int n) {
+  const int recip = g_lu_reciprocal;
   for (int k = 0; k < n; ++k) {
     int p = k; double best = fabs(A[k * n + k]);
     for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + k]) > best) { best = fabs(A[i * n + k]); p = i; }
     piv[k] = p;
     if (p != k) for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
-    double d = 1.0 / A[k * n + k];
-    A[k * n + k] = d;
+    const double piv_v = A[k * n + k], d = 1.0 / piv_v;
+    if (recip) A[k * n + k] = d;
     for (int i = k + 1; i < n; ++i) {
-      double l = A[i * n + k] * d; A[i * n + k] = l;
+      double l = recip ? A[i * n + k] * d : A[i * n + k] / piv_v; A[i * n + k] = l;
       for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
     }
   }
 }
 static void lu_solve(const double* A, const int* piv, int n, double* b) {
+  const int recip = g_lu_reciprocal;
   for (int k = 0; k < n; ++k) { int p = piv[k]; if (p != k) { double t = b[k]; b[k] = b[p]; b[p] = t; } }
   for (int i = 1; i < n; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= A[i * n + j] * b[j]; b[i] = s; }
   /* column-oriented order (j descending), the order a lane-per-row GPU solve produces */
-  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = n - 1; j > i; --j) s -= A[i * n + j] * b[j]; b[i] = s * A[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i]; for (int j = n - 1; j > i; --j) s -= A[i * n + j] * b[j];
+    b[i] = recip ? s * A[i * n + i] : s / A[i * n + i];
+  }
 }
 
 typedef struct {
@@ -619,6 +635,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
     if (EEst <= 1.0) {
       res->st.n_accept++;
       qold = jmax(EEst, 1e-4);
+      if (q >= c->qs_min && q <= c->qs_max) q = 1.0; /* step_accept_controller!: steady-state dead-band */
       double dtnew = dt / q;
       double tprev = t;
       t = snap_t(t + dt, tend);
@@ -796,6 +813,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
     if (EEst <= 1.0) {
       res->st.n_accept++;
       qold = jmax(EEst, 1e-4);
+      if (q >= c->qs_min && q <= c->qs_max) q = 1.0; /* step_accept_controller!: steady-state dead-band */
       double dtnew = dt / q, tprev = t;
       t = snap_t(t + dt, tend);
       rhs_value(c, t, Un, F1, &kc); res->st.n_rhs++;
@@ -1110,6 +1128,12 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
   c->gamma = o->gamma > 0 ? o->gamma : 0.9;
   c->beta2 = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * c->order);
   c->beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * c->order);
+  /* qsteady_{min,max}_default: 1 / 1 for explicit and composite algorithms, 1 / (6//5) for the adaptive implicit ones
+   * [UPSTREAM-RECALL alg_utils.jl: qsteady_max_default(::OrdinaryDiffEqAdaptiveImplicitAlgorithm) = 6//5] */
+  const int implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4);
+  c->qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
+  c->qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
+  c->norm_cnt = (double)c->n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)c->ncol : 1.0);
   for (int a = 0; a < 2; ++a) {
     const double ord = a ? 2.0 : 5.0;
     c->beta2_alg[a] = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * ord);

@@ -52,7 +52,27 @@ def lib() -> C.CDLL:
         _lib.crnn_oracle_tsit5_tableau.argtypes = [C.c_void_p] * 3
         _lib.crnn_oracle_kencarp4_tableau.restype = None
         _lib.crnn_oracle_kencarp4_tableau.argtypes = [C.c_void_p] * 2
+        _lib.crnn_oracle_set_lu_reciprocal.restype = None
+        _lib.crnn_oracle_set_lu_reciprocal.argtypes = [C.c_int]
+        _lib.crnn_oracle_get_lu_reciprocal.restype = C.c_int
     return _lib
+
+
+class lu_reciprocal:
+    """Context manager for the oracle's named LU switch: inside it the diagonal of U is stored inverted and the
+    triangular solves multiply (the CUDA kernels' form); outside, the literal division form (default)."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = lib().crnn_oracle_get_lu_reciprocal()
+        lib().crnn_oracle_set_lu_reciprocal(int(self.on))
+        return self
+
+    def __exit__(self, *exc):
+        lib().crnn_oracle_set_lu_reciprocal(self.prev)
+        return False
 
 
 def _p(a):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_abi.EXPORTS), (declared, _abi.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.crnn_version() == 101
+    assert lib.crnn_version() == 200
 
 
 def test_ctypes_mirror_matches_header_layout():

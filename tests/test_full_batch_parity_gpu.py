@@ -1,0 +1,160 @@
+"""Full-batch parity at the BASELINE sizes: EVERY trajectory of a configuration's per-GPU batch is solved by the CUDA
+path (through the C-ABI) and by the CPU oracle on the same seeded inputs, and compared one by one.
+
+What is counted per configuration: trajectories whose (n_accept, n_reject, n_rhs, n_jac, retcode, n_saved) differ
+from the oracle's — the north star's "bit-exact on step counts" — and the worst relative error of the saved states,
+the losses and the gradient.  The report goes to stdout and to gpurun_out/full_batch_parity.json (copied to
+profiles/ by hand); bench.py carries the same counters in its `parity` key.
+
+The oracle runs with its named LU switch set to the kernels' reciprocal-diagonal form (tests/conftest.py); the
+literal division form is compared against it on the Rosenbrock23 configuration below.
+CRNN_PARITY_REPORT_ONLY=1 prints the numbers without asserting (used while profiling)."""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases, synth
+from oracle import oracle
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT_ONLY = os.environ.get("CRNN_PARITY_REPORT_ONLY", "0") == "1"
+CORES = os.cpu_count() or 8
+_report = {}
+
+
+def compare(name, got, ref, keys=("n_accept", "n_reject", "n_rhs", "n_jac")):
+    N = len(ref["retcode"])
+    bad = np.zeros(N, dtype=bool)
+    per = {}
+    for k in keys:
+        d = np.asarray(got["stats"][k]) != np.asarray(ref["stats"][k])
+        per[k] = int(d.sum()); bad |= d
+    for k in ("retcode", "n_saved"):
+        d = np.asarray(got[k]) != np.asarray(ref[k])
+        per[k] = int(d.sum()); bad |= d
+    out = {"N": int(N), "count_mismatches": int(bad.sum()), "by_field": per}
+    if got.get("pred") is not None and ref.get("pred") is not None:
+        scale = np.maximum(np.abs(ref["pred"]).max(axis=(0, 1), keepdims=True), 1e-300)
+        err = np.abs(got["pred"] - ref["pred"]) / scale
+        out["state_max_err_rel_to_row_range"] = float(err.max())
+        out["state_max_err_same_counts"] = float(err[~bad].max()) if (~bad).any() else None
+    if "loss" in ref and ref["loss"] is not None:
+        ok = np.isfinite(ref["loss"])
+        out["loss_max_rel"] = float((np.abs(got["loss"][ok] - ref["loss"][ok]) / np.abs(ref["loss"][ok])).max())
+        out["grad_rel_l2"] = float(np.linalg.norm(got["grad_sum"] - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]))
+        out["grad_max_rel_to_max"] = float(np.abs(got["grad_sum"] - ref["grad_sum"]).max() / np.abs(ref["grad_sum"]).max())
+    _report[name] = out
+    print(f"[full-batch parity] {name}: {json.dumps(out)}", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "full_batch_parity.json"), "w") as f:
+        json.dump(_report, f, indent=1)
+    return out
+
+
+def case2_inputs(engine, golden, N):
+    c = cases.CASES["case2"]
+    u0 = synth.make_u0("case2", N)
+    obs = np.arange(c.ns)
+    truth = engine.solve_batch(cases.true_model_case2(), c.opts(obs_idx=obs, pred_clamp=(-np.inf, np.inf)), u0, want_stats=False)
+    data = synth.noisy_targets(truth["pred"], 0.05)
+    ys = synth.yscale_from(data[:1024], c.lb)
+    model, seed = c.model(np.array(golden["case2"]["p"]))
+    return c, model, seed, u0, data, ys
+
+
+@pytest.mark.parametrize("norm", ["totallength", "state_only", "value_only"])
+def test_config2_case2_all_65536(engine, golden, norm):
+    """BASELINE configs[1]: Tsit5 + 25 forward sensitivities + fused loss, all 65 536 ICs, under the default dual norm
+    (DiffEqBase: mean over n_state*(1+np)) and under both named switches."""
+    c, model, seed, u0, data, ys = case2_inputs(engine, golden, 65536)
+    kw = {"totallength": {}, "state_only": dict(err_norm_mean_over_partials=False), "value_only": dict(err_norm_includes_sens=False)}[norm]
+    o = c.opts(obs_idx=np.arange(c.ns), **kw)
+    got = engine.loss_grad_batch(model, o, seed, u0, data, ys, c.loss_kind, want_pred=True)
+    t = time.time()
+    ref = oracle.loss_grad_batch(model, o, seed, u0, data, ys, c.loss_kind, want_pred=True, n_threads=CORES)
+    r = compare(f"config2_case2_tsit5_fwdsens_{norm}", got, ref)
+    r["oracle_seconds"] = time.time() - t
+    if REPORT_ONLY:
+        return
+    assert r["count_mismatches"] == 0
+    assert r["state_max_err_rel_to_row_range"] < 1e-9 and r["loss_max_rel"] < 1e-10 and r["grad_rel_l2"] < 1e-9
+    assert (got["stats"]["n_rhs"] == 2 + 6 * (got["stats"]["n_accept"] + got["stats"]["n_reject"])).all()
+
+
+def test_config3_robertson_all_262144(engine, golden):
+    """BASELINE configs[2]: the reference's trained stiff Robertson CRNN, Rosenbrock23 (analytic J + register LU),
+    all 262 144 ICs on the value path; the forward-sensitivity path (np = 43) on the first 65 536."""
+    c = cases.CASES["robertson"]
+    N = 262144
+    u0 = synth.make_u0("robertson", N)
+    pb = make_problem("robertson", golden, 64)
+    got = engine.solve_batch(pb["model"], pb["opts"], u0)
+    ref = oracle.solve_batch(pb["model"], pb["opts"], u0, n_threads=CORES)
+    r = compare("config3_robertson_ros23_value", got, ref)
+    with oracle.lu_reciprocal(False):   # the literal generic lu!/ldiv! form against the kernels' reciprocal diagonal
+        lit = oracle.solve_batch(pb["model"], pb["opts"], u0, n_threads=CORES)
+    r2 = compare("config3_robertson_ros23_value_vs_literal_division_lu", got, lit)
+    M = 65536
+    truth = engine.solve_batch(pb["true_model"], c.opts(pred_clamp=(-np.inf, np.inf)), u0[:M], want_stats=False)
+    data = synth.noisy_targets(truth["pred"], 1e-4)
+    gs = engine.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], u0[:M], data, pb["yscale"], c.loss_kind, want_pred=True)
+    rs = oracle.loss_grad_batch(pb["model"], pb["opts"], pb["seed"], u0[:M], data, pb["yscale"], c.loss_kind, want_pred=True, n_threads=CORES)
+    r3 = compare("config3_robertson_ros23_fwdsens_np43", gs, rs)
+    if REPORT_ONLY:
+        return
+    assert r["count_mismatches"] == 0 and r["state_max_err_rel_to_row_range"] < 1e-7
+    assert r2["count_mismatches"] <= N // 1000          # rounding-level form difference: a handful of flipped steps at most
+    assert r3["count_mismatches"] == 0 and r3["loss_max_rel"] < 1e-7 and r3["grad_rel_l2"] < 1e-6
+
+
+def case3_near_true_model(c):
+    mt = cases.true_model_case3()
+    g = np.random.default_rng(5)
+    w_in_raw = np.where(mt.w_in > 0, mt.w_in, np.where(mt.w_out > 0, -1.0, 0.0)) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    w_out_raw = np.where(mt.w_out != 0, np.abs(mt.w_out), 0.0) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    p = np.concatenate([0.1 * g.standard_normal(c.nr), w_out_raw.reshape(-1, order="F"), w_in_raw.reshape(-1, order="F"), [0.1]])
+    return c.model(p)
+
+
+@pytest.mark.parametrize("mode", ["interp", "discrete"])
+def test_config4_case3_adjoint_share(engine, golden, mode):
+    """BASELINE configs[3]: case3 (np = 153) by the interpolating adjoint — one GPU's share (131 072) of the 1 048 576
+    ICs on the GPU, the first 32 768 of them against the oracle."""
+    c = cases.CASES["case3"]
+    N, M = 131072, 32768
+    u0 = synth.make_u0("case3", N)
+    o = c.opts(obs_idx=np.arange(c.ns), pred_clamp=(-np.inf, np.inf))
+    y = engine.solve_batch(cases.true_model_case3(), o, u0, want_stats=False)["pred"]
+    data = np.abs(synth.noisy_targets(y, 0.05)) + 1e-6
+    ys = synth.yscale_from(data[:4096], c.lb)
+    model, seed = case3_near_true_model(c)
+    sm = _abi.SENS_INTERP_ADJOINT if mode == "interp" else _abi.SENS_DISCRETE_ADJOINT
+    oa = c.opts(obs_idx=np.arange(c.ns), sens_mode=sm)
+    got = engine.loss_grad_batch(model, oa, seed, u0, data, ys, c.loss_kind, want_pred=True)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    ref = oracle.loss_grad_batch(model, oa, seed, u0[:M], data[:M], ys, c.loss_kind, want_pred=True, n_threads=CORES)
+    sub = {k: (v[:M] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in got.items()}
+    sub["grad_sum"] = engine.loss_grad_batch(model, oa, seed, u0[:M], data[:M], ys, c.loss_kind)["grad_sum"]
+    r = compare(f"config4_case3_{mode}_adjoint", sub, ref)
+    if REPORT_ONLY:
+        return
+    assert r["count_mismatches"] == 0
+    assert r["loss_max_rel"] < 1e-9 and r["grad_rel_l2"] < 1e-6
+
+
+def test_config5_hychem_sized_kencarp4_share(engine):
+    """BASELINE configs[4]: 30 states / 30 reactions, stiff, KenCarp4 — one GPU's share (16 384) of the 131 072 ICs."""
+    N = 16384
+    m = cases.synthetic_stiff_model(); u0 = cases.synthetic_stiff_u0(N); o = cases.synthetic_stiff_opts()
+    got = engine.solve_batch(m, o, u0)
+    ref = oracle.solve_batch(m, o, u0, n_threads=CORES)
+    r = compare("config5_hychem_sized_kencarp4", got, ref)
+    if REPORT_ONLY:
+        return
+    assert r["count_mismatches"] == 0
+    assert r["state_max_err_rel_to_row_range"] < 1e-6

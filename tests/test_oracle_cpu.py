@@ -201,8 +201,18 @@ def test_tsit5_case2_against_radau(golden):
                     rtol=1e-12, atol=1e-14, t_eval=tight.saveat)
     assert np.abs(sol.y[:6].T - rt["pred"][0]).max() < 2e-9
     # survey scratch value: IC [1.2,1.5,0,0,0,0,333] takes 17 steps / 104 RHS evaluations
-    s = oracle.solve_batch(pb["model"], pb["opts"], np.array([[1.2, 1.5, 0, 0, 0, 0, 333.0]]))["stats"]
+    ic = np.array([[1.2, 1.5, 0, 0, 0, 0, 333.0]])
+    s = oracle.solve_batch(pb["model"], pb["opts"], ic)["stats"]
     assert (s["n_accept"][0], s["n_reject"][0], s["n_rhs"][0]) == (17, 0, 104)
+    # ... and, with the 25 forward-sensitivity columns in DiffEqBase's dual norm (mean over n_state*(1+np) numbers,
+    # SURVEY App. C.3), 20 steps / 122 RHS evaluations
+    counts = lambda st: (int(st["n_accept"][0]), int(st["n_reject"][0]), int(st["n_rhs"][0]))
+    lg = lambda **kw: oracle.loss_grad_batch(pb["model"], pb["case"].opts(obs_idx=np.arange(6), **kw), pb["seed"], ic,
+                                             pb["data"][:1], pb["yscale"])["stats"]
+    assert counts(lg()) == (20, 0, 122)
+    # named switches: the mean over the n_state rows only (releases before 0.2.0), and the value-only norm
+    assert counts(lg(err_norm_mean_over_partials=False)) == (23, 0, 140)
+    assert counts(lg(err_norm_includes_sens=False)) == (17, 0, 104)
 
 
 def test_rosenbrock23_robertson_against_radau_and_mass(golden):
@@ -272,6 +282,68 @@ def test_partials_in_error_norm_switch(golden):
     assert np.array_equal(off["stats"]["n_accept"], val["stats"]["n_accept"])     # value-only norm
     assert (on["stats"]["n_accept"] >= off["stats"]["n_accept"]).all()            # partials tighten steps
     assert (on["stats"]["n_accept"] > off["stats"]["n_accept"]).any()
+
+
+def test_config1_case1_as_written_and_effective_tolerances(golden):
+    """BASELINE config 1: case1.jl:29-30 writes atol 1e-5 / rtol 1e-2 (as `atol=`/`rtol=`, which the
+    Julia-1.6-era solver ignored, so the effective values were 1e-6 / 1e-3): both are run, against Radau."""
+    pb = make_problem("case1", golden, 3)
+    c = pb["case"]
+    at, rt = cases.AS_WRITTEN_TOL["case1"]
+    written = c.opts(abstol=at, reltol=rt)
+    rw = oracle.solve_batch(pb["true_model"], written, pb["u0"])
+    re = oracle.solve_batch(pb["true_model"], c.opts(), pb["u0"])
+    assert (rw["retcode"] == 1).all() and (re["retcode"] == 1).all()
+    assert (rw["stats"]["n_accept"] <= re["stats"]["n_accept"]).all() and (rw["stats"]["n_accept"] < re["stats"]["n_accept"]).any()
+    for i in range(3):
+        sol = solve_ivp(lambda t, u: oracle.rhs(pb["true_model"], u), c.tspan, pb["u0"][i], method="Radau",
+                        rtol=1e-12, atol=1e-14, t_eval=written.saveat)
+        ew, ee = np.abs(sol.y.T - rw["pred"][i]).max(), np.abs(sol.y.T - re["pred"][i]).max()
+        assert ew < 5e-3 and ee < 5e-4, (ew, ee)
+    # loss + gradient at both settings: forward mode vs the discrete adjoint of the value-norm solve
+    for o in (written, c.opts()):
+        ov = c.opts(abstol=o.abstol, reltol=o.reltol, err_norm_includes_sens=False)
+        oa = c.opts(abstol=o.abstol, reltol=o.reltol, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+        f = oracle.loss_grad_batch(pb["model"], ov, pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+        a = oracle.loss_grad_batch(pb["model"], oa, pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+        np.testing.assert_allclose(a["loss"], f["loss"], rtol=1e-12)
+        np.testing.assert_allclose(a["grad_sum"], f["grad_sum"], rtol=1e-8, atol=1e-11)
+
+
+def test_qsteady_dead_band_defaults_and_switch(golden):
+    """step_accept_controller!: qsteady_min <= q <= qsteady_max keeps dt.  Defaults 1 / 1.2 for Rosenbrock23 and
+    KenCarp4 (adaptive implicit), 1 / 1 for Tsit5 and the composite; both are overridable."""
+    c = cases.CASES["robertson"]
+    pbr = make_problem("robertson", golden, 64)
+    mt, u0 = pbr["model"], pbr["u0"]
+    dflt = oracle.solve_batch(mt, c.opts(), u0)
+    explicit = oracle.solve_batch(mt, c.opts(controller=dict(qsteady_min=1.0, qsteady_max=1.2)), u0)
+    none = oracle.solve_batch(mt, c.opts(controller=dict(qsteady_min=1.0, qsteady_max=1.0)), u0)
+    assert np.array_equal(dflt["pred"], explicit["pred"])
+    assert not np.array_equal(dflt["pred"], none["pred"])          # the dead-band is hit on the trained stiff CRNN
+    assert np.abs(dflt["pred"] - none["pred"]).max() < 5e-3       # same solution within the tolerance
+    # Tsit5: no dead-band by default; switching one on changes the step sequence
+    pb = make_problem("case2", golden, 4)
+    a = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"])
+    b = oracle.solve_batch(pb["model"], pb["case"].opts(obs_idx=np.arange(6), controller=dict(qsteady_min=1.0, qsteady_max=1.0)), pb["u0"])
+    d = oracle.solve_batch(pb["model"], pb["case"].opts(obs_idx=np.arange(6), controller=dict(qsteady_min=0.5, qsteady_max=1.3)), pb["u0"])
+    assert np.array_equal(a["pred"], b["pred"]) and not np.array_equal(a["pred"], d["pred"])
+
+
+def test_lu_literal_division_is_the_default_and_reciprocal_is_a_switch(golden):
+    """The oracle's LU follows the generic lu!/ldiv! (divisions) by default; the CUDA kernels' reciprocal-diagonal form
+    is a named switch.  The two differ by rounding only: same step counts, states to ~1e-9."""
+    c = cases.CASES["robertson"]
+    pb = make_problem("robertson", golden, 16)
+    assert oracle.lib().crnn_oracle_get_lu_reciprocal() == 0
+    lit = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"])
+    with oracle.lu_reciprocal():
+        rec = oracle.solve_batch(pb["model"], pb["opts"], pb["u0"])
+    assert oracle.lib().crnn_oracle_get_lu_reciprocal() == 0
+    assert np.array_equal(lit["stats"]["n_accept"], rec["stats"]["n_accept"])
+    assert np.array_equal(lit["stats"]["n_reject"], rec["stats"]["n_reject"])
+    assert not np.array_equal(lit["pred"], rec["pred"])           # the switch does something
+    np.testing.assert_allclose(rec["pred"], lit["pred"], rtol=1e-8, atol=1e-14)
 
 
 # ---------------------------------------------------------------- failure / truncation paths
