@@ -70,6 +70,7 @@ assert STATS_DTYPE.itemsize == C.sizeof(CStats) == 32
 EXPORTS = (
     "crnn_create", "crnn_destroy", "crnn_last_error", "crnn_version", "crnn_launch_count",
     "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end", "crnn_copy_grad_each",
+    "crnn_debug_lean_math",
 )
 
 _lib = None
@@ -102,6 +103,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crnn_profile_end.restype = C.c_int
     lib.crnn_copy_grad_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.crnn_copy_grad_each.restype = C.c_int
+    lib.crnn_debug_lean_math.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.crnn_debug_lean_math.restype = C.c_int
     lib.crnn_solve_batch.argtypes = [
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

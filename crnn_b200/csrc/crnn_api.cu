@@ -238,9 +238,34 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   }, np, post);
 }
 
+// lean_math.h on the device, elementwise (crnn_debug_lean_math)
+__global__ void k_lean_math(int op, const double* __restrict__ x, const double* __restrict__ y2, double* __restrict__ y, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  y[i] = op == 0 ? lean_log(v) : op == 1 ? lean_exp(v) : op == 2 ? lean_pow(v, y2[i]) : op == 3 ? lean_log10(v) : lean_exp10(v);
+}
+
 }  // namespace
 
 extern "C" {
+
+int crnn_debug_lean_math(crnn_handle* h, int32_t op, const double* x, const double* x2, double* y, int64_t n) {
+  if (!h || !x || !y || n < 0 || op < 0 || op > 4 || (op == 2 && !x2)) return CRNN_ERR_BAD_ARG;
+  if (n == 0) return CRNN_OK;
+  CK(cudaSetDevice(h->device));
+  DevBuf bx, by, b2;
+  CK(bx.reserve(n * sizeof(double))); CK(by.reserve(n * sizeof(double)));
+  CK(cudaMemcpy(bx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
+  if (op == 2) { CK(b2.reserve(n * sizeof(double))); CK(cudaMemcpy(b2.p, x2, n * sizeof(double), cudaMemcpyHostToDevice)); }
+  k_lean_math<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(op, bx.as<double>(), b2.as<double>(), by.as<double>(), n);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaStreamSynchronize(h->s_compute));
+  CK(cudaMemcpy(y, by.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  bx.release(); by.release(); b2.release();
+  return CRNN_OK;
+}
 
 int crnn_version(void) { return CRNN_B200_VERSION; }
 

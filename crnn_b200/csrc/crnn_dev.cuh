@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cmath>
 #include "../../include/crnn_b200.h"
+#include "lean_math.h"
 
 namespace crnn {
 
@@ -89,61 +90,10 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) {
   return v > hi ? hi : (v < lo ? lo : v);
 }
 
-// ------------------------------------------------------------------------------------------
-// Lean log / exp.  The RHS spends its transcendental calls on NS (log) and NR (exp) lanes of a
-// warp, so what they cost is ISSUE SLOTS, not flops: CUDA's log/exp are ~85/~60 instructions each,
-// a third of them moving 64-bit literals into registers.  These keep the classic argument
-// reductions (log: m in [sqrt(1/2), sqrt 2), s = f/(2+f), odd series in s; exp: k = rint(x/ln 2),
-// Taylor degree 13 on |r| <= ln2/2), read their constants pairwise from constant memory, and send
-// anything outside the plain range (zero, negative, subnormal, inf, NaN; |x| >= 700 for exp) to
-// the library call.  Measured against long double on 4e7 samples: <= 0.76 ulp (log), <= 0.89 ulp
-// (exp) - the same class as the library versions (1 ulp), so parity tolerances are unchanged.
-// ------------------------------------------------------------------------------------------
-__constant__ double c_lm[26] = {
-    /* 0..6  */ 6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
-    /* 7,8   */ 6.93147180369123816490e-01, 1.90821492927058770002e-10,
-    /* 9,10  */ 1.4426950408889634074, 6755399441055744.0,
-    /* 11..  */ 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0, 0.0};
-
-static __device__ __noinline__ double lib_log(double x) { return log(x); }
-static __device__ __noinline__ double lib_exp(double x) { return exp(x); }
-
-__device__ __forceinline__ double lean_log(double x) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return lib_log(x);
-  const int hx = hi & 0xfffff, i = (hx + 0x95f64) & 0x100000;
-  const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lo);
-  const double dk = (double)((hi >> 20) - 1023 + (i >> 20));
-  const double f = m - 1.0, d = 2.0 + f;
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  const double s = f * r, z = s * s, w = z * z;
-  const double t1 = w * fma(w, fma(w, c_lm[5], c_lm[3]), c_lm[1]);
-  const double t2 = z * fma(w, fma(w, fma(w, c_lm[6], c_lm[4]), c_lm[2]), c_lm[0]);
-  const double hfsq = 0.5 * f * f;
-  return fma(dk, c_lm[7], -((hfsq - fma(s, hfsq + (t2 + t1), dk * c_lm[8])) - f));
-}
-
-__device__ __forceinline__ double lean_exp(double x) {
-  if ((unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x4085e000u) return lib_exp(x);
-  const double t = fma(x, c_lm[9], c_lm[10]);
-  const double kf = t - c_lm[10];
-  double r = fma(kf, -c_lm[7], x);
-  r = fma(kf, -c_lm[8], r);
-  double p = c_lm[11];
-#pragma unroll
-  for (int n = 12; n <= 24; ++n) p = fma(p, r, c_lm[n]);
-  return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
-}
-
-// x^y for x > 0 (step-size controller exponents): a few ulp, see pi_controller.
-__device__ __forceinline__ double lean_pow(double x, double y) { return lean_exp(y * lean_log(x)); }
+// lean_log / lean_exp / lean_pow / lean_log10 / lean_exp10: lean_math.h — one definition shared with host code
+// (the CPU oracle's shared-math build runs the very same functions, bit for bit).
+// out-of-line copy for cold call sites of the instruction-fetch-bound kernels
+static __device__ __noinline__ double lean_log_nl(double x) { return lean_log(x); }
 
 // OrdinaryDiffEq PI controller.
 template <class C>

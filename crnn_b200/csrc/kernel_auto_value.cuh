@@ -77,7 +77,7 @@ k_auto_value(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     for (int i = 0; i < NS; ++i) { double b = (k[1][i] - k[0][i]) / sk[i]; s2 = fma(b, b, s2); }
     double d2 = sqrt(s2 / N) / dt0;
     double dm = jmax(d1, d2);
-    double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
+    double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : lean_exp10(-(2.0 + lean_log10(dm)) * sp.inv_order);
     dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
   }
 

@@ -109,7 +109,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(wsum(c) / n) / dt0;
       const double dm = jmax(d1, d2);
-      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * P.inv_order);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : lean_exp10(-(2.0 + lean_log10(dm)) * P.inv_order);
       dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
     }
     double t = t0, qold = 1e-4, eta_old = 1.0, dt_last = 0.0;
@@ -145,7 +145,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
         bool conv = false;
 #pragma unroll 1
         for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
-          double ndz_prev = 0.0, eta = pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+          double ndz_prev = 0.0, eta = lean_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
 #pragma unroll 1
           for (int it = 1; it <= 10; ++it) {
             yk = fma(kc::g, zs, tmp);

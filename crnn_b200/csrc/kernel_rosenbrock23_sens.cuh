@@ -413,7 +413,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
         } else if (phase == PH_F1) {
           const double d2 = sqrt(s0 / sp.norm_cnt) / dt0;
           const double dm = jmax(d1, d2);
-          const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * sp.inv_order);
+          const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : lean_exp10(-(2.0 + lean_log10(dm)) * sp.inv_order);
           dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
           dtnew = dt;
           // pseudo-step that saves t0: proposed state = U, f2 = f0 (commit is then a no-op)
@@ -489,7 +489,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
                 diff = d * iy - yc * iy;
                 g = signbit(diff) ? iy : -iy;
               } else {
-                diff = log(clampd(d, sp.pred_lo, sp.pred_hi)) - log(yc);
+                diff = lean_log(clampd(d, sp.pred_lo, sp.pred_hi)) - lean_log(yc);
                 g = (signbit(diff) ? 1.0 : -1.0) / yc;
               }
               loss_acc += fabs(diff);

@@ -188,7 +188,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       if (lane < n) { c = (f1 - k[0]) / sk; c *= c; }
       const double d2 = sqrt(wsum(c) / n) / dt0;
       const double dm = jmax(d1, d2);
-      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * W.inv_order);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : lean_exp10(-(2.0 + lean_log10(dm)) * W.inv_order);
       dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
     }
     double t = t0, qold = 1e-4, dt_last = 0.0;
@@ -328,7 +328,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         const double d = __ldg(data + off);
         double diff, g;
         if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
-        else { diff = lib_log(clampd(d, W.pred_lo, W.pred_hi)) - lib_log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }  // one out-of-line copy of log
+        else { diff = lean_log_nl(clampd(d, W.pred_lo, W.pred_hi)) - lean_log_nl(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }  // one out-of-line copy of log
         loss_acc += fabs(diff);
         if (inside && isp) gret = g / cnt;
       }

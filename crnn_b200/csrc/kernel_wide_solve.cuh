@@ -91,7 +91,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(wsum(c) / n) / dt0;
       const double dm = jmax(d1, d2);
-      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) * P.inv_order);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : lean_exp10(-(2.0 + lean_log10(dm)) * P.inv_order);
       dt = jmin(jmin(100.0 * dt0, dt1), dtmax);
     }
     double t = t0, qold = 1e-4, dt_last = 0.0, eigen_est = 0.0;

@@ -71,6 +71,16 @@ class Engine:
         self._check(self._lib.crnn_copy_grad_each(self._h, out.ctypes.data_as(C.c_void_p), N, n_p, 0, None))
         return out
 
+    def lean_math(self, op: str, x, x2=None) -> np.ndarray:
+        """The device copy of crnn_b200/csrc/lean_math.h evaluated elementwise (diagnostic; op in log, exp, pow, log10, exp10)."""
+        code = {"log": 0, "exp": 1, "pow": 2, "log10": 3, "exp10": 4}[op]
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        x2 = None if x2 is None else np.ascontiguousarray(x2, dtype=np.float64).reshape(-1)
+        y = np.empty_like(x)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.crnn_debug_lean_math(self._h, code, vp(x), vp(x2), vp(y), x.size))
+        return y
+
     def _check(self, rc: int):
         if rc != 0:
             raise EngineError(f"crnn_b200 error {rc}: {self._lib.crnn_last_error(self._h).decode()}")

@@ -215,6 +215,11 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
  * dst is host memory (on_device = 0) or device memory (on_device = 1, copied on `stream`). */
 int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int32_t on_device, void* stream);
 
+/* Diagnostic: evaluates the engine's device log / exp / pow (crnn_b200/csrc/lean_math.h) elementwise on host arrays,
+ * op 0: y = log(x), 1: exp(x), 2: x^x2, 3: log10(x), 4: 10^x.  The same header compiles for the host; the tests
+ * use this entry point to show the two copies agree bit for bit. */
+int crnn_debug_lean_math(crnn_handle* h, int32_t op, const double* x, const double* x2, double* y, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,26 @@
 
 int crnn_oracle_rhs_t(const crnn_model* m, double t, const double* u, double* du, double* J, double* dT);
 
+/* Transcendental functions.  DEFAULT: the C library (the literal restatement: Julia calls its own libm-class
+ * log/exp/^).  Named switch crnn_oracle_set_shared_math(1): the lean log/exp/pow the CUDA kernels use, compiled from
+ * the same header (crnn_b200/csrc/lean_math.h via lean_math_host.c) — bit-identical on host and device, so that
+ * step-count comparisons do not hinge on glibc-vs-CUDA last-ulp differences. */
+double crnn_lean_log(double), crnn_lean_exp(double), crnn_lean_pow(double, double), crnn_lean_log10(double), crnn_lean_exp10(double);
+static int g_shared_math = 0;
+static double (*m_log)(double) = log;
+static double (*m_exp)(double) = exp;
+static double (*m_pow)(double, double) = pow;
+void crnn_oracle_set_shared_math(int on) {
+  g_shared_math = on;
+  m_log = on ? crnn_lean_log : log; m_exp = on ? crnn_lean_exp : exp; m_pow = on ? crnn_lean_pow : pow;
+}
+int crnn_oracle_get_shared_math(void) { return g_shared_math; }
+/* 10^(-(2 + log10 dm)/order) of the initial-step heuristic */
+static double initdt_pow10(double dm, int order) {
+  if (g_shared_math) return crnn_lean_exp10(-(2.0 + crnn_lean_log10(dm)) * (1.0 / order));
+  return pow(10.0, -(2.0 + log10(dm)) / order);
+}
+
 #define MAXN 64 /* max n_state */
 #define MAXR 64 /* max n_reac  */
 
@@ -97,18 +117,18 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
       double C = k->rho * (k->Y[i] / m->mw[i]) * 1e3;      /* Y2C, :112-114 */
       double Cc = clampd(C, m->lb, m->ub);
       k->chiC[i] = (C >= m->lb && C <= m->ub) ? 1.0 : 0.0;
-      k->x[i] = log(Cc);
+      k->x[i] = m_log(Cc);
       k->dx[i] = k->chiC[i] * k->chi[i] / k->Y[i];         /* d x_i / d u_i at fixed density */
       k->d2x[i] = 0.0;
     }
     k->x[ns] = -1.0 / m->gas_R / k->T;                     /* - 1 / R / T, :128 */
-    k->x[ns + 1] = log(k->T);
+    k->x[ns + 1] = m_log(k->T);
     k->dx[ns] = k->dx[ns + 1] = 0.0; k->d2x[ns] = k->d2x[ns + 1] = 0.0;
   } else {
     for (int i = 0; i < ns; ++i) {
       double uc = clampd(u[i], m->lb, m->ub);
       int inside = (u[i] >= m->lb) && (u[i] <= m->ub); /* dual clamp passes derivative 1 on the closed interval */
-      k->x[i] = log(uc);
+      k->x[i] = m_log(uc);
       k->dx[i] = inside ? 1.0 / uc : 0.0;
       k->d2x[i] = inside ? -1.0 / (uc * uc) : 0.0;
     }
@@ -122,7 +142,7 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
   for (int j = 0; j < nr; ++j) {
     double z = m->w_b[j];
     for (int i = 0; i < nin; ++i) z += m->w_in[i + nin * j] * k->x[i];
-    k->r[j] = exp(z);
+    k->r[j] = m_exp(z);
   }
   for (int i = 0; i < ns; ++i) {
     double s = 0.0;
@@ -327,7 +347,7 @@ static double initial_dt(const ctx_t* c, double t0, const double* U0, const doub
   for (int q = 0; q < tot; ++q) F1[q] -= F0[q];
   double d2 = initdt_norm(c, F1, U0, 1.0) / dt0;
   double dm = jmax(d1, d2);
-  double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / c->order);
+  double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : initdt_pow10(dm, c->order);
   return jmin(jmin(100.0 * dt0, dt1), tspan_len);
 }
 
@@ -386,7 +406,7 @@ static void emit_save(const ctx_t* c, save_sink* sk, int ksave, const double* Ys
       g = (signbit(diff) ? 1.0 : -1.0) / sk->yscale[q];
     } else {
       double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi);
-      diff = log(dc) - log(yc);
+      diff = m_log(dc) - m_log(yc);
       g = (signbit(diff) ? 1.0 : -1.0) / yc;
     }
     sk->loss += fabs(diff);
@@ -403,8 +423,8 @@ static int has_nan(const double* v, int len) {
 /* PI controller of OrdinaryDiffEq: returns q; *q11 out. */
 static double pi_q(const ctx_t* c, double EEst, double qold, double* q11) {
   if (EEst == 0.0) { *q11 = 0.0; return 1.0 / c->qmax; }
-  *q11 = pow(EEst, c->beta1);
-  double q = *q11 / pow(qold, c->beta2);
+  *q11 = m_pow(EEst, c->beta1);
+  double q = *q11 / m_pow(qold, c->beta2);
   return jmax(1.0 / c->qmax, jmin(1.0 / c->qmin, q / c->gamma));
 }
 
@@ -457,8 +477,8 @@ typedef struct {
 /* PI controller with explicit exponents (AutoTsit5 swaps them with the algorithm, see solve_one). */
 static double pi_q_b(const ctx_t* c, double b1, double b2, double EEst, double qold, double* q11) {
   if (EEst == 0.0) { *q11 = 0.0; return 1.0 / c->qmax; }
-  *q11 = pow(EEst, b1);
-  double q = *q11 / pow(qold, b2);
+  *q11 = m_pow(EEst, b1);
+  double q = *q11 / m_pow(qold, b2);
   return jmax(1.0 / c->qmax, jmin(1.0 / c->qmin, q / c->gamma));
 }
 
@@ -766,7 +786,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
       }
       int conv = 0;
       for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
-        double ndz_prev = 0.0, eta = pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+        double ndz_prev = 0.0, eta = m_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
         for (int it = 1; it <= 10; ++it) {
           for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
           rhs_value(c, t + KC_C[s] * dt, Yk, DZ, &kc); res->st.n_rhs++;
@@ -992,7 +1012,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
       if (pred) pred[qo + o->n_obs * k] = yc;
       double d = data[qo + o->n_obs * k], diff, g;
       if (loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d / yscale[qo] - yc / yscale[qo]; g = (signbit(diff) ? 1.0 : -1.0) / yscale[qo]; }
-      else { double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi); diff = log(dc) - log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+      else { double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi); diff = m_log(dc) - m_log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
       lsum += fabs(diff);
       if (inside) jump[(size_t)k * n + i] += g / cnt;
     }

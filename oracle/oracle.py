@@ -22,8 +22,9 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(HERE, "crnn_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "crnn_oracle.c"), os.path.join(HERE, "lean_math_host.c"),
+            os.path.join(HERE, "..", "crnn_b200", "csrc", "lean_math.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", HERE, "-B", "liboracle_crnn.so"], check=True, capture_output=True)
     return LIB
 
@@ -55,7 +56,30 @@ def lib() -> C.CDLL:
         _lib.crnn_oracle_set_lu_reciprocal.restype = None
         _lib.crnn_oracle_set_lu_reciprocal.argtypes = [C.c_int]
         _lib.crnn_oracle_get_lu_reciprocal.restype = C.c_int
+        _lib.crnn_oracle_set_shared_math.restype = None
+        _lib.crnn_oracle_set_shared_math.argtypes = [C.c_int]
+        _lib.crnn_oracle_get_shared_math.restype = C.c_int
+        for fn, na in (("crnn_lean_log", 1), ("crnn_lean_exp", 1), ("crnn_lean_pow", 2), ("crnn_lean_log10", 1), ("crnn_lean_exp10", 1)):
+            getattr(_lib, fn).restype = C.c_double
+            getattr(_lib, fn).argtypes = [C.c_double] * na
     return _lib
+
+
+class shared_math:
+    """Context manager for the oracle's named math switch: inside it log/exp/pow are the lean functions of
+    crnn_b200/csrc/lean_math.h (the kernels' own, bit-identical on host and device); outside, the C library."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = lib().crnn_oracle_get_shared_math()
+        lib().crnn_oracle_set_shared_math(int(self.on))
+        return self
+
+    def __exit__(self, *exc):
+        lib().crnn_oracle_set_shared_math(self.prev)
+        return False
 
 
 class lu_reciprocal:

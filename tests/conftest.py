@@ -31,12 +31,14 @@ def engine():
 
 @pytest.fixture(autouse=True)
 def _oracle_lu_form(request):
-    """GPU parity tests compare against the oracle with its named LU switch ON: the CUDA kernels store the diagonal of U
-    inverted and multiply in the triangular solves (DESIGN.md "Named deviations").  The CPU tests keep the oracle's
-    default, the literal division form; tests/test_full_batch_parity_gpu.py measures the two against each other."""
+    """GPU parity tests compare against the oracle with its two named switches ON: the CUDA kernels store the diagonal
+    of U inverted and multiply in the triangular solves, and their log/exp/pow are the lean functions of
+    crnn_b200/csrc/lean_math.h, which the oracle then runs from the same header (DESIGN.md "Named deviations").  The
+    CPU tests keep the oracle's defaults (division LU, C library math); tests/test_full_batch_parity_gpu.py measures
+    the literal forms against the kernels as well."""
     if request.node.get_closest_marker("gpu") is None:
         yield
         return
     from oracle import oracle
-    with oracle.lu_reciprocal(True):
+    with oracle.lu_reciprocal(True), oracle.shared_math(True):
         yield
