@@ -9,13 +9,21 @@ with N > 1 ranks each rank owns its own 65 536 trajectories and the only exchang
 all-reduce of [sum loss, grad_sum] (26 doubles).
 
   value  : whole-job trajectories/s with inputs resident in HBM (device buffers)
-  e2e    : same metric through the public API with HOST (pinned) buffers; the H2D copy of
-           u0 + targets and the D2H read of loss/grad are inside the timed region
+  e2e    : same metric through the public API a training loop calls (crnn_dataset_create once, then
+           crnn_loss_grad_indexed per optimiser step): every timed step copies that step's inputs — the
+           weights, the seed matrix dW/dp and the solver options, from host memory — to the device and
+           reads [sum loss, n, grad] back; the training set itself is constant across optimiser steps
+           (case2.jl:62-83) and is uploaded once, outside the timed region (its upload time is reported).
+           `e2e_host_buffers` keeps the round-1 form (u0 + targets re-uploaded from pinned memory each step).
   roofline: dominant kernel (k_tsit5_sens) vs the measured HBM peak; algorithmic bytes are
            4 864 B/trajectory.  The kernel is fp64-ALU bound, so the fp64 FMA
            fraction is reported next to it.
   cpu_baseline / --impl reference: the CPU oracle (a port: Julia cannot run here) on the
            host cores, on a bounded sample of the same workload.
+  parity : the oracle pass of cpu_baseline is compared with the GPU result trajectory by trajectory
+           (count mismatches over the whole 65 536-trajectory batch, max loss / gradient error).
+  configs: BASELINE configs 3, 4, 5 where BASELINE puts them (robertson 262 144 per GPU; case3 1 048 576
+           sharded over the N GPUs, interpolating + discrete adjoint; HyChem-sized KenCarp4 131 072 sharded).
 """
 from __future__ import annotations
 
@@ -176,27 +184,182 @@ def build_inputs(eng, rank):
     return c, model, seed, c.opts(obs_idx=obs), u0, data, yscale
 
 
-def cpu_reference(steps, warmup, sample):
-    """The reference arm / cpu_baseline: the CPU oracle (port) on all host cores."""
+def cpu_reference(steps, warmup, sample, keep=False, inputs=None):
+    """The reference arm / cpu_baseline: the CPU oracle (port) on all host cores.  `inputs` = (u0, data, yscale) reuses
+    the GPU arm's arrays (so that the same pass doubles as the full-batch parity check)."""
     from crnn_b200 import cases, synth
     from oracle import oracle
     c = cases.CASES["case2"]
     cores = os.cpu_count() or 1
-    u0 = synth.make_u0("case2", sample)
     obs = np.arange(c.ns)
-    truth = oracle.solve_batch(cases.true_model_case2(), c.opts(obs_idx=obs, pred_clamp=(-np.inf, np.inf)), u0,
-                               n_threads=cores)["pred"]
-    data = synth.noisy_targets(truth, 0.05)
-    ys = synth.yscale_from(data, c.lb)
+    if inputs is not None:
+        u0, data, ys = inputs[0][:sample], inputs[1][:sample], inputs[2]
+    else:
+        u0 = synth.make_u0("case2", sample)
+        truth = oracle.solve_batch(cases.true_model_case2(), c.opts(obs_idx=obs, pred_clamp=(-np.inf, np.inf)), u0,
+                                   n_threads=cores)["pred"]
+        data = synth.noisy_targets(truth, 0.05)
+        ys = synth.yscale_from(data, c.lb)
     model, seed = c.model(np.array(load_golden()["case2"]["p"]))
     opts = c.opts(obs_idx=obs)
     for _ in range(warmup):
         oracle.loss_grad_batch(model, opts, seed, u0[:256], data[:256], ys, n_threads=cores)
     t = time.perf_counter()
     for _ in range(steps):
-        oracle.loss_grad_batch(model, opts, seed, u0, data, ys, n_threads=cores)
+        last = oracle.loss_grad_batch(model, opts, seed, u0, data, ys, n_threads=cores)
     dt = (time.perf_counter() - t) / steps
-    return sample / dt, dt * 1e3, cores
+    return (sample / dt, dt * 1e3, cores) + ((last,) if keep else ())
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5 (extra keys of the JSON line)
+# ---------------------------------------------------------------------------------------------
+def _timed(fn, steps, world, dev):
+    import torch
+    import torch.distributed as dist
+    fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), r
+
+
+def _flops_value_rhs(ns, nr, nin):
+    return 2 * nin * nr + 2 * ns * nr + 40 * ns + 30 * nr
+
+
+def _entry(n_total, ms, rhs_per_traj, bytes_per_traj, flop_per_traj, world, peak):
+    tps = n_total / (ms * 1e-3)
+    return {"n_trajectories": int(n_total), "ms_per_step": ms, "trajectories_per_s": tps,
+            "rhs_evals_per_traj": rhs_per_traj, "rhs_evals_per_s": tps * rhs_per_traj,
+            "hbm_frac": tps * bytes_per_traj / 1e9 / (peak * world),
+            "fp64_frac": tps * flop_per_traj / 1e12 / (FP64_PEAK_TFLOPS * world),
+            "bytes_per_trajectory": bytes_per_traj, "flop_per_trajectory_model": flop_per_traj}
+
+
+def extra_configs(eng, rank, world, dev, steps, with_cpu):
+    """BASELINE configs 3, 4, 5 at BASELINE's sizes: device-resident inputs, CUDA-event timing, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from crnn_b200 import _abi, cases, synth
+    from crnn_b200.engine import stats_from_torch
+    peak, _ = measured_peaks()
+    cores = os.cpu_count() or 1
+    out = {}
+    golden = load_golden()
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def noisy(t, noise, seed):   # multiplicative Gaussian noise generated on the device (seeded per rank)
+        g = torch.Generator(device=dev); g.manual_seed(seed + 7919 * rank)
+        return t * (1.0 + noise * torch.randn(t.shape, generator=g, device=dev, dtype=torch.float64))
+
+    def allreduce(r):            # the path's one exchange: [sum loss, grad_sum]
+        if world > 1:
+            buf = torch.cat([r["loss"].nan_to_num().sum().reshape(1), r["grad_sum"]])
+            dist.all_reduce(buf)
+        return r
+
+    # ---- config 3: robertson, Rosenbrock23 (analytic J + register LU), 262 144 ICs per GPU ----
+    c = cases.CASES["robertson"]
+    N3 = 262144
+    u0 = synth.make_u0("robertson", N3, start=rank * N3)
+    truth1k = eng.solve_batch(cases.true_model_robertson(), c.opts(pred_clamp=(-np.inf, np.inf)), synth.make_u0("robertson", 1024), want_stats=False)["pred"]
+    ys = synth.yscale_from(synth.noisy_targets(truth1k, 1e-4), 0.0)
+    model, seed = c.model(np.array(golden["robertson"]["p"]), out_scale=ys / c.tspan[1])
+    u0_d = T(u0)
+    data_d = noisy(eng.solve_batch(cases.true_model_robertson(), c.opts(pred_clamp=(-np.inf, np.inf)), u0_d, want_stats=False)["pred"], 1e-4, 3)
+    o = c.opts()
+    ms, _ = _timed(lambda: eng.solve_batch(model, o, u0_d, want_stats=False), steps, world, dev)
+    st = stats_from_torch(eng.solve_batch(model, o, u0_d)["stats"])
+    n, nr = 3, 6
+    att = float((st["n_accept"] + st["n_reject"]).mean())
+    f_step = 2 * n * n * nr + (2 * n ** 3) // 3 + 3 * 2 * n * n + 30 * n          # J assembly, LU, 3 solves, stage algebra
+    out["config3_robertson_rosenbrock23_predict"] = _entry(
+        N3 * world, ms, float(st["n_rhs"].mean()), 8 * (3 + 3 * 40), st["n_rhs"].mean() * _flops_value_rhs(3, 6, 3) + att * f_step, world, peak)
+    ms, r = _timed(lambda: allreduce(eng.loss_grad_batch(model, o, seed, u0_d, data_d, ys, c.loss_kind, want_stats=False)), steps, world, dev)
+    st = stats_from_torch(eng.loss_grad_batch(model, o, seed, u0_d, data_d, ys, c.loss_kind)["stats"])
+    ncol = seed.shape[1] + 1
+    att = float((st["n_accept"] + st["n_reject"]).mean())
+    f_rhs_s = _flops_value_rhs(3, 6, 3) + ncol * (n + 4 * n * nr + 3 * nr + 2)
+    f_step_s = f_step + ncol * (3 * (2 * n * n + 8 * n * nr) + 2 * n * 12)             # 3 solves + 3 dJ*k products per column
+    out["config3_robertson_rosenbrock23_forward_sens_np43"] = _entry(
+        N3 * world, ms, float(st["n_rhs"].mean()), 8 * (3 + 2 * 3 * 40 + 1), st["n_rhs"].mean() * f_rhs_s + att * f_step_s + 40 * ncol * n * 2 * 4, world, peak)
+    out["config3_robertson_rosenbrock23_forward_sens_np43"]["loss_mean"] = float(r["loss"].nanmean().item())
+    if with_cpu:
+        from oracle import oracle
+        M = 16384
+        t0 = time.perf_counter(); oracle.solve_batch(model, o, u0[:M], n_threads=cores); t1 = time.perf_counter()
+        oracle.loss_grad_batch(model, o, seed, u0[:4096], data_d[:4096].cpu().numpy(), ys, c.loss_kind, n_threads=cores); t2 = time.perf_counter()
+        out["config3_robertson_rosenbrock23_predict"]["cpu_port_trajectories_per_s"] = M / (t1 - t0)
+        out["config3_robertson_rosenbrock23_forward_sens_np43"]["cpu_port_trajectories_per_s"] = 4096 / (t2 - t1)
+    del u0_d, data_d
+
+    # ---- config 4: case3 (MAPK, np = 153), 1 048 576 ICs sharded over the N GPUs, adjoint training step ----
+    c = cases.CASES["case3"]
+    N4 = 1048576 // world
+    u0 = synth.make_u0("case3", N4, start=rank * N4)
+    u0_d = T(u0)
+    obs = np.arange(c.ns)
+    y = eng.solve_batch(cases.true_model_case3(), c.opts(obs_idx=obs, pred_clamp=(-np.inf, np.inf)), u0_d, want_stats=False)["pred"]
+    data_d = noisy(y, 0.05, 4).abs_().add_(1e-6)
+    del y
+    mt = cases.true_model_case3()
+    g = np.random.default_rng(5)   # a CRNN near the generating mechanism in case3.jl's own parametrisation (see tests/test_full_size_gpu.py)
+    w_in_raw = np.where(mt.w_in > 0, mt.w_in, np.where(mt.w_out > 0, -1.0, 0.0)) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    w_out_raw = np.where(mt.w_out != 0, np.abs(mt.w_out), 0.0) * (1.0 + 0.1 * g.standard_normal(mt.w_in.shape))
+    p = np.concatenate([0.1 * g.standard_normal(c.nr), w_out_raw.reshape(-1, order="F"), w_in_raw.reshape(-1, order="F"), [0.1]])
+    model, seed = c.model(p)
+    ys = np.ones(c.ns)
+    n, nr = 9, 8
+    for key, sm in (("interpolating_adjoint", _abi.SENS_INTERP_ADJOINT), ("discrete_adjoint", _abi.SENS_DISCRETE_ADJOINT)):
+        o = c.opts(obs_idx=obs, sens_mode=sm)
+        ms, r = _timed(lambda: allreduce(eng.loss_grad_batch(model, o, seed, u0_d, data_d, ys, c.loss_kind, want_stats=False)), steps, world, dev)
+        st = stats_from_torch(eng.loss_grad_batch(model, o, seed, u0_d[:65536], data_d[:65536], ys, c.loss_kind)["stats"])
+        f_rhs_a = _flops_value_rhs(n, nr, n) + 2 * (2 * n * nr) + 2 * nr * (2 * n + 1)        # + J^T lambda + the three outer products
+        e = _entry(N4 * world, ms, float(st["n_rhs"].mean()), 8 * (9 + 2 * 9 * 100 + 1), st["n_rhs"].mean() * f_rhs_a, world, peak)
+        e["loss_mean"] = float(r["loss"].nanmean().item()); e["n_per_gpu"] = N4
+        if with_cpu:
+            from oracle import oracle
+            M = 8192
+            t0 = time.perf_counter()
+            oracle.loss_grad_batch(model, o, seed, u0[:M], data_d[:M].cpu().numpy(), ys, c.loss_kind, n_threads=cores)
+            e["cpu_port_trajectories_per_s"] = M / (time.perf_counter() - t0)
+        out[f"config4_case3_{key}"] = e
+    del u0_d, data_d
+
+    # ---- config 5: HyChem-sized (30 states / 30 reactions, stiff) KenCarp4, 131 072 ICs sharded over the N GPUs ----
+    N5 = 131072 // world
+    m5 = cases.synthetic_stiff_model(); o5 = cases.synthetic_stiff_opts()
+    u0 = cases.synthetic_stiff_u0(N5, start=rank * N5)
+    u0_d = T(u0)
+    ms, _ = _timed(lambda: eng.solve_batch(m5, o5, u0_d, want_stats=False), steps, world, dev)
+    st = stats_from_torch(eng.solve_batch(m5, o5, u0_d)["stats"])
+    n, nr = 30, 30
+    att = float((st["n_accept"] + st["n_reject"]).mean())
+    f_step5 = 2 * n * n * nr + (2 * n ** 3) // 3 + 40 * n                              # J assembly + LU per attempt
+    f_rhs5 = _flops_value_rhs(29, 30, 30) + 2 * n * n + 10 * n                          # every Newton iterate: RHS + triangular solves + norms
+    e = _entry(N5 * world, ms, float(st["n_rhs"].mean()), 8 * (30 + 29 * 40), st["n_rhs"].mean() * f_rhs5 + att * f_step5, world, peak)
+    e["n_per_gpu"] = N5; e["retcode_success_frac"] = float((eng.solve_batch(m5, o5, u0_d)["retcode"] == 1).double().mean().item())
+    if with_cpu:
+        from oracle import oracle
+        M = 2048
+        t0 = time.perf_counter(); oracle.solve_batch(m5, o5, u0[:M], n_threads=cores)
+        e["cpu_port_trajectories_per_s"] = M / (time.perf_counter() - t0)
+    out["config5_hychem_sized_kencarp4_predict"] = e
+    if with_cpu:
+        out["cpu_port_cores"] = cores
+    return out
 
 
 def main():
@@ -206,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3-5 (headline only)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,6 +377,7 @@ def main():
     config = {"workload": "case2 (ns=6+T, nr=3, np=25) Tsit5 + forward sensitivities + fused MAE loss, "
                           f"{N_PER_GPU} ICs per GPU, abstol 1e-6 reltol 1e-3, t in [0,50], 50 saves",
               "n_traj_per_gpu": N_PER_GPU, "parallelism": f"dp{a.gpus} (trajectory shards, all-reduce of [loss, grad])",
+              "error_norm": "DiffEqBase dual norm: partials included, mean over n_state*(1+np) numbers (SURVEY App. C.3)",
               "l2": "inputs larger than L2 (157 MB targets read + 157 MB saved states written per step)"}
 
     if a.impl == "reference":
@@ -230,21 +395,25 @@ def main():
             "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes; WARN prints it too)
-    # off it; NCCL caches the setting at its first call, so this has to happen before torch is imported
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-        del os.environ["NCCL_DEBUG"]
     import torch
     import torch.distributed as dist
-    from crnn_b200.engine import Engine
+    from crnn_b200.engine import Engine, stats_from_torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (crnn_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries ONE JSON line: while NCCL initialises (it prints its version banner on stdout under
+        # NCCL_DEBUG=VERSION/WARN) fd 1 points at stderr; the driver's NCCL_DEBUG setting itself is left alone
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     eng = Engine(local_rank)
     c, model, seed, opts, u0_h, data_h, yscale = build_inputs(eng, rank)
-    dev = torch.device("cuda", local_rank)
     u0_d = torch.from_numpy(u0_h).to(dev)
     data_d = torch.from_numpy(data_h).to(dev)
     red = torch.zeros(seed.shape[1] + 1, dtype=torch.float64, device=dev)
@@ -286,37 +455,67 @@ def main():
     value = N_PER_GPU * world / (ms_step * 1e-3)
     # RHS evaluations per trajectory from the engine's own counters (one extra untimed pass)
     rs = eng.loss_grad_batch(model, opts, seed, u0_d, data_d, yscale, c.loss_kind, want_stats=True)
-    from crnn_b200.engine import stats_from_torch
     st = stats_from_torch(rs["stats"])
     rhs_per_traj = float(st["n_rhs"].mean())
     attempts_per_traj = float((st["n_accept"] + st["n_reject"]).mean())
+    gpu_loss = rs["loss"].cpu().numpy(); gpu_grad = rs["grad_sum"].cpu().numpy()
+    del u0_d, data_d
 
-    # ---- timed region 2: end to end with host (pinned) buffers through the public API ----
+    # ---- timed region 2: end to end through the training-loop API (dataset resident, weights in, loss + grad out) ----
+    t_up = time.perf_counter()
+    ds = eng.dataset(u0_h, data_h)
+    upload_ms = (time.perf_counter() - t_up) * 1e3
+    red_h = torch.zeros(seed.shape[1] + 2, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        rr = eng.loss_grad_indexed(model, opts, seed, ds, yscale, c.loss_kind)      # H2D: weights + seed + options; D2H: [sum loss, n, grad]
+        if world > 1:
+            red_h[0] = rr["loss_sum"]; red_h[1] = rr["n_ok"]; red_h[2:] = torch.from_numpy(rr["grad_sum"])
+            rd = red_h.to(dev, non_blocking=True)
+            dist.all_reduce(rd)
+            rd.cpu()
+        return rr
+
+    def time_host_steps(fn, nsteps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            out_ = fn()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item()) / nsteps, out_
+
+    e2e_steps = max(3, min(a.steps, 20))
+    e2e_ms, rh = time_host_steps(step_e2e, e2e_steps)
+    e2e_value = N_PER_GPU * world / (e2e_ms * 1e-3)
+    nw = model.n_w
+    h2d = 8 * (nw + 2 * 3 * 32 + 50 + 7 * 3 + 16) + 32 * 24        # weights (kernel parameters), structured seed rows + descriptors, saveat, tolerances
+    d2h = 8 * (seed.shape[1] + 2)
+    assert np.array_equal(rh["grad_sum"], gpu_grad), "the dataset path must give the device-buffer path's gradient"
+    ds.close()
+
+    # round-1 form for comparison: host (pinned) u0 + targets re-uploaded every step
     u0_p = torch.from_numpy(u0_h).pin_memory(); data_p = torch.from_numpy(data_h).pin_memory()
     u0_n, data_n = u0_p.numpy(), data_p.numpy()
 
     def step_host():
-        r = eng.loss_grad_batch(model, opts, seed, u0_n, data_n, yscale, c.loss_kind, want_stats=False)
+        rr = eng.loss_grad_batch(model, opts, seed, u0_n, data_n, yscale, c.loss_kind, want_stats=False)
         if world > 1:
-            red.copy_(torch.from_numpy(np.concatenate([[r["loss"].sum()], r["grad_sum"]])))
+            red.copy_(torch.from_numpy(np.concatenate([[rr["loss"].sum()], rr["grad_sum"]])))
             dist.all_reduce(red)
             red.cpu()
-        return r
+        return rr
 
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(3, min(a.steps, 10))
-    for _ in range(e2e_steps):
-        rh = step_host()
-    barrier()
-    te = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = N_PER_GPU * world / (float(te.item()) / e2e_steps * 1e-3)
-    h2d = u0_h.nbytes + data_h.nbytes
-    d2h = N_PER_GPU * (8 + 4 + 4) + 8 * seed.shape[1]
+    hb_ms, _ = time_host_steps(step_host, max(3, min(a.steps, 6)))
+    del u0_p, data_p
+
+    extra = None
+    if not a.no_extra:
+        extra = extra_configs(eng, rank, world, dev, 2, with_cpu=(rank == 0 and a.gpus == 1))
 
     if rank == 0:
         peak, which = measured_peaks()
@@ -335,10 +534,19 @@ def main():
             "warmup": max(3, a.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "rhs_evals_per_s": value * rhs_per_traj, "rhs_evals_per_traj": rhs_per_traj,
+            "step_attempts_per_traj": attempts_per_traj,
             "loss_mean": float(r["loss"].mean().item()),
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms,
+                    "api": "crnn_dataset_create (once) + crnn_loss_grad_indexed per step",
+                    "dataset_upload_ms_once": upload_ms, "dataset_bytes": int(u0_h.nbytes + data_h.nbytes),
+                    "note": "a gradient call: [sum loss, n, grad] come back, the saved states are not stored (the value arm "
+                            "also writes its 157 MB of saved states per step)"},
+            "e2e_host_buffers": {"value": N_PER_GPU * world / (hb_ms * 1e-3), "unit": "trajectories/s", "ms_per_step": hb_ms,
+                                 "h2d_bytes_per_step": int(u0_h.nbytes + data_h.nbytes),
+                                 "d2h_bytes_per_step": int(N_PER_GPU * (8 + 4 + 4) + 8 * seed.shape[1]),
+                                 "api": "crnn_loss_grad_batch with host (pinned) u0 + targets every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "peak_source": which,
                          "kernel": "k_tsit5_sens<Cfg<6,3,1>,1,...>", "kernel_ms": kms, "kernel_launches": int(kern_n),
@@ -349,10 +557,22 @@ def main():
                                  "construction (~2e2 flop/B), so the fp64 fraction is the meaningful one; see DESIGN.md"},
         }
         if a.gpus == 1:
-            v, ms, cores = cpu_reference(1, 1, min(a.cpu_sample, N_PER_GPU))
+            sample = min(a.cpu_sample, N_PER_GPU)
+            from oracle import oracle
+            with oracle.lu_reciprocal(True), oracle.shared_math(True):
+                v, ms, cores, ref = cpu_reference(1, 1, sample, keep=True, inputs=(u0_h, data_h, yscale))
             out["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                                   "sample": f"{min(a.cpu_sample, N_PER_GPU)} of the {N_PER_GPU} trajectories, one pass, "
+                                   "sample": f"{sample} of the {N_PER_GPU} trajectories, one pass, "
                                              "OpenMP over all host cores"}
+            if sample == N_PER_GPU:   # the same pass is the full-batch parity check
+                bad = ((st["n_accept"] != ref["stats"]["n_accept"]) | (st["n_reject"] != ref["stats"]["n_reject"]) |
+                       (st["n_rhs"] != ref["stats"]["n_rhs"]))
+                out["parity"] = {"checker": "CPU oracle (shared lean math), every trajectory of the step",
+                                 "n_compared": int(sample), "count_mismatches": int(bad.sum()),
+                                 "loss_max_rel": float(np.max(np.abs(gpu_loss - ref["loss"]) / np.abs(ref["loss"]))),
+                                 "grad_rel_l2": float(np.linalg.norm(gpu_grad - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]))}
+        if extra is not None:
+            out["configs"] = extra
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -70,7 +70,8 @@ assert STATS_DTYPE.itemsize == C.sizeof(CStats) == 32
 EXPORTS = (
     "crnn_create", "crnn_destroy", "crnn_last_error", "crnn_version", "crnn_launch_count",
     "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end", "crnn_copy_grad_each",
-    "crnn_debug_lean_math",
+    "crnn_debug_lean_math", "crnn_create_multi", "crnn_device_count", "crnn_dataset_create", "crnn_dataset_destroy",
+    "crnn_dataset_size", "crnn_loss_grad_indexed",
 )
 
 _lib = None
@@ -105,6 +106,21 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crnn_copy_grad_each.restype = C.c_int
     lib.crnn_debug_lean_math.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.crnn_debug_lean_math.restype = C.c_int
+    lib.crnn_create_multi.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32]
+    lib.crnn_create_multi.restype = C.c_int
+    lib.crnn_device_count.argtypes = [C.c_void_p]
+    lib.crnn_device_count.restype = C.c_int32
+    lib.crnn_dataset_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                        C.POINTER(C.c_void_p)]
+    lib.crnn_dataset_create.restype = C.c_int
+    lib.crnn_dataset_destroy.argtypes = [C.c_void_p]
+    lib.crnn_dataset_destroy.restype = None
+    lib.crnn_dataset_size.argtypes = [C.c_void_p]
+    lib.crnn_dataset_size.restype = C.c_int64
+    lib.crnn_loss_grad_indexed.argtypes = [
+        C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.crnn_loss_grad_indexed.restype = C.c_int
     lib.crnn_solve_batch.argtypes = [
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

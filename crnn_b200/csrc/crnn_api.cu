@@ -231,7 +231,7 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
     if (b.qslot >= 2) Pl.scratch = P.scratch + scratch_doubles * (size_t)(b.qslot - 2);
     ProfScope prof(h, s);
     kern<<<blocks, WARPS * 32, smem, s>>>(Pl, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved,
-                                       b.retcode, b.stats, queue);
+                                       b.retcode, b.stats, queue, b.in_idx);
     CK(cudaGetLastError());
     h->launches++;
     return (int)CRNN_OK;
@@ -247,6 +247,45 @@ __global__ void k_lean_math(int op, const double* __restrict__ x, const double* 
 }
 
 }  // namespace
+
+namespace crnn_host {
+// Validation + dispatch shared by crnn_loss_grad_batch and crnn_loss_grad_indexed (crnn_dataset.cu).
+int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,
+                   const double* yscale, int32_t loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  int rc = validate(h, m, o, N);
+  if (rc) return rc;
+  if (N > 0 && (!io.u0 || !io.data || !io.loss)) return fail(h, CRNN_ERR_BAD_ARG, "null u0/data/loss");
+  if (np < 0 || (np > 0 && !dW_dp)) return fail(h, CRNN_ERR_BAD_ARG, "bad seed matrix");
+  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG)
+    return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
+  if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
+  if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT &&
+      o->sens_mode != CRNN_SENS_DISCRETE_ADJOINT)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be FORWARD, INTERP_ADJOINT or DISCRETE_ADJOINT");
+  if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
+  CK(cudaSetDevice(h->device));
+  h->last_grad_np = -1; h->last_grad_n = -1;
+  if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT)
+    return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+  h->last_grad_np = np; h->last_grad_n = N;
+#define X(NS_, NR_, K_)                                                              \
+  if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
+    return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+  CRNN_FOR_EACH_CFG(X)
+#undef X
+  // No dimension-specialised forward-mode kernel.  With the value-only error norm the forward-mode gradient IS the
+  // derivative of the recorded step sequence, i.e. what the discrete adjoint computes (any dimensions <= 32, F2 included).
+  h->last_grad_np = -1; h->last_grad_n = -1;
+  if (o->alg == CRNN_ALG_TSIT5 && !o->err_norm_includes_sens) {
+    crnn_opts oa = *o;
+    oa.sens_mode = CRNN_SENS_DISCRETE_ADJOINT;
+    return loss_grad_adjoint(h, m, &oa, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+  }
+  return fail(h, CRNN_ERR_UNSUPPORTED,
+              "no forward-mode kernel instantiated for this (n_species, n_reac, rhs_kind): use an adjoint sens_mode, or "
+              "err_norm_includes_sens = 0 (served by the discrete adjoint)");
+}
+}  // namespace crnn_host
 
 extern "C" {
 
@@ -300,10 +339,16 @@ int crnn_create(crnn_handle** out, int device_id) {
 
 void crnn_destroy(crnn_handle* h) {
   if (!h) return;
+  if (!h->kids.empty()) {  // multi-device parent: communicators first, then the per-device handles
+    multi_release_comms(h);
+    for (crnn_handle* k : h->kids) crnn_destroy(k);
+    delete h;
+    return;
+  }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch,
-                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats};
+                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats, &h->d_idx, &h->d_nsu_ix, &h->d_result};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
     DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s]};
@@ -323,10 +368,16 @@ void crnn_destroy(crnn_handle* h) {
 
 const char* crnn_last_error(const crnn_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-int64_t crnn_launch_count(const crnn_handle* h) { return h ? h->launches : 0; }
+int64_t crnn_launch_count(const crnn_handle* h) {
+  if (!h) return 0;
+  int64_t n = h->launches;
+  for (const crnn_handle* k : h->kids) n += k->launches;
+  return n;
+}
 
 int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int32_t on_device, void* stream) {
   if (!h || !dst || N < 0 || np <= 0) return CRNN_ERR_BAD_ARG;
+  if (!h->kids.empty()) return fail(h, CRNN_ERR_UNSUPPORTED, "crnn_copy_grad_each needs a single-device handle");
   const size_t bytes = (size_t)N * np * sizeof(double);
   if (h->last_grad_np != np || h->last_grad_n != N || h->d_grad_each.cap < bytes)
     return fail(h, CRNN_ERR_BAD_ARG, "no forward-mode gradients of that shape from the last call");
@@ -339,6 +390,7 @@ int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int3
 
 int crnn_profile_begin(crnn_handle* h) {
   if (!h) return CRNN_ERR_BAD_ARG;
+  for (crnn_handle* k : h->kids) crnn_profile_begin(k);
   h->profiling = true;
   h->prof_used = 0;
   return CRNN_OK;
@@ -348,6 +400,13 @@ int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches) {
   if (!h) return CRNN_ERR_BAD_ARG;
   h->profiling = false;
   double tot = 0.0;
+  int64_t nk = 0;
+  for (crnn_handle* k : h->kids) {  // multi-device parent: sums over its devices
+    double ms = 0.0; int64_t n = 0;
+    int rc = crnn_profile_end(k, &ms, &n);
+    if (rc) { h->err = k->err; return rc; }
+    tot += ms; nk += n;
+  }
   for (size_t q = 0; q < h->prof_used; ++q) {
     float ms = 0.f;
     CK(cudaEventSynchronize(h->prof_events[q].second));
@@ -355,7 +414,7 @@ int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches) {
     tot += ms;
   }
   if (total_ms) *total_ms = tot;
-  if (n_launches) *n_launches = (int64_t)h->prof_used;
+  if (n_launches) *n_launches = (int64_t)h->prof_used + nk;
   h->prof_used = 0;
   return CRNN_OK;
 }
@@ -364,6 +423,7 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
                      const int32_t* n_save_used, double* pred, int32_t* n_saved, int32_t* retcode,
                      crnn_stats* stats) {
   if (!h) return CRNN_ERR_BAD_ARG;
+  if (!h->kids.empty()) return multi_solve_batch(h, m, o, u0, N, n_save_used, pred, n_saved, retcode, stats);
   int rc = validate(h, m, o, N);
   if (rc) return rc;
   if (N > 0 && !u0) return fail(h, CRNN_ERR_BAD_ARG, "null u0");
@@ -391,39 +451,10 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
                          const double* yscale, int32_t loss_kind, double* loss, double* grad_sum, double* pred,
                          int32_t* n_saved, int32_t* retcode, crnn_stats* stats) {
   if (!h) return CRNN_ERR_BAD_ARG;
-  int rc = validate(h, m, o, N);
-  if (rc) return rc;
-  if (N > 0 && (!u0 || !data || !loss)) return fail(h, CRNN_ERR_BAD_ARG, "null u0/data/loss");
-  if (np < 0 || (np > 0 && !dW_dp)) return fail(h, CRNN_ERR_BAD_ARG, "bad seed matrix");
-  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG)
-    return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
-  if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
-  if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT &&
-      o->sens_mode != CRNN_SENS_DISCRETE_ADJOINT)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be FORWARD, INTERP_ADJOINT or DISCRETE_ADJOINT");
-  if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
-  CK(cudaSetDevice(h->device));
+  if (!h->kids.empty()) return multi_loss_grad_batch(h, m, o, dW_dp, np, u0, N, n_save_used, data, yscale, loss_kind, loss,
+                                                     grad_sum, pred, n_saved, retcode, stats);
   HostIO io{u0, n_save_used, data, pred, loss, n_saved, retcode, stats};
-  h->last_grad_np = -1; h->last_grad_n = -1;
-  if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT)
-    return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
-  h->last_grad_np = np; h->last_grad_n = N;
-#define X(NS_, NR_, K_)                                                              \
-  if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
-    return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
-  CRNN_FOR_EACH_CFG(X)
-#undef X
-  // No dimension-specialised forward-mode kernel.  With the value-only error norm the forward-mode gradient IS the
-  // derivative of the recorded step sequence, i.e. what the discrete adjoint computes (any dimensions <= 32, F2 included).
-  h->last_grad_np = -1; h->last_grad_n = -1;
-  if (o->alg == CRNN_ALG_TSIT5 && !o->err_norm_includes_sens) {
-    crnn_opts oa = *o;
-    oa.sens_mode = CRNN_SENS_DISCRETE_ADJOINT;
-    return loss_grad_adjoint(h, m, &oa, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
-  }
-  return fail(h, CRNN_ERR_UNSUPPORTED,
-              "no forward-mode kernel instantiated for this (n_species, n_reac, rhs_kind): use an adjoint sens_mode, or "
-              "err_norm_includes_sens = 0 (served by the discrete adjoint)");
+  return loss_grad_core(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
 }
 
 }  // extern "C"

@@ -76,6 +76,11 @@ struct crnn_handle {
   // pageable host memory blocks the host thread, which would serialise the chunk pipeline)
   DevBuf d_loss, d_nsaved, d_ret, d_stats;
   DevBuf d_grad_each, d_grad_sum, d_grad_out, adj_scratch;
+  // device-resident dataset path (crnn_loss_grad_indexed): row indices, n_save_used, [sum loss, n finite, grad(np)]
+  DevBuf d_idx, d_nsu_ix, d_result;
+  // multi-device parent (crnn_create_multi): the children own all per-device state, the parent launches nothing itself
+  std::vector<crnn_handle*> kids;
+  std::vector<void*> comms;  // ncclComm_t per child (NCCL is dlopen'ed: crnn_dataset.cu)
   // optional kernel timing (crnn_profile_begin/_end)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -92,6 +97,19 @@ struct crnn_handle {
   } while (0)
 
 namespace crnn_host {
+
+struct HostIO;
+// crnn_api.cu: validation + dispatch of one loss/gradient call on ONE device
+int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,
+                   const double* yscale, int32_t loss_kind, const HostIO& io, int64_t N, double* grad_sum);
+// crnn_dataset.cu: the host-buffer entry points on a multi-device handle (contiguous shards, one host thread per device)
+int multi_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,
+                          const double* u0, int64_t N, const int32_t* n_save_used, const double* data, const double* yscale,
+                          int32_t loss_kind, double* loss, double* grad_sum, double* pred, int32_t* n_saved,
+                          int32_t* retcode, crnn_stats* stats);
+void multi_release_comms(crnn_handle* h);
+int multi_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* u0, int64_t N,
+                      const int32_t* n_save_used, double* pred, int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
 
 inline int fail(crnn_handle* h, int code, const std::string& msg) {
   h->err = msg;
@@ -218,6 +236,7 @@ struct BatchPtrs {  // device pointers of one (sub)batch
   double* grad_each;
   long long n;
   int qslot;  // which work-queue counter of the handle this launch uses
+  const long long* in_idx = nullptr;  // device [n] dataset rows of the inputs (crnn_loss_grad_indexed), or NULL
 };
 
 // ---------------- value path launchers ----------------
@@ -263,7 +282,7 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
   CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
   ProfScope prof(h, st);
   kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
-                                      b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue);
+                                      b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx);
   CK(cudaGetLastError());
   h->launches++;
   return CRNN_OK;
@@ -290,7 +309,7 @@ int launch_ros_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, in
     CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     ProfScope prof(h, st);
     kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
-                                        b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue);
+                                        b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx);
     CK(cudaGetLastError());
     h->launches++;
     return CRNN_OK;
@@ -376,6 +395,7 @@ int upload_seed(crnn_handle* h, const crnn_model* m, const double* dW_dp, int np
 struct HostIO {
   const double* u0; const int32_t* nsu; const double* data;
   double* pred; double* loss; int32_t* n_saved; int32_t* retcode; crnn_stats* stats;
+  const long long* in_idx = nullptr;  // device buffers only: dataset rows of the inputs
 };
 
 // `post` (optional): maps the reduced per-trajectory vector (length np, device) to the final gradient
@@ -389,7 +409,7 @@ int run_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Hos
   const size_t ns = m->n_state, ps = (size_t)o->n_obs * o->n_save;
   if (o->buffers_on_device) {
     cudaStream_t st = (cudaStream_t)o->stream;
-    BatchPtrs b{io.u0, io.nsu, io.data, io.pred, io.loss, io.n_saved, io.retcode, io.stats, nullptr, N, 0};
+    BatchPtrs b{io.u0, io.nsu, io.data, io.pred, io.loss, io.n_saved, io.retcode, io.stats, nullptr, N, 0, io.in_idx};
     if (want_loss && np > 0) {
       CK(h->d_grad_each.reserve(std::max<size_t>(8, (size_t)N * np * sizeof(double))));
       b.grad_each = h->d_grad_each.as<double>();

@@ -39,7 +39,8 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
                     const double* __restrict__ u0, const int* __restrict__ n_save_used, long long ntraj,
                     const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
                     double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
-                    crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
+                    crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
+                    const long long* __restrict__ in_idx) {
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN;
   static_assert(NS <= 6, "per-lane register LU");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -82,10 +83,12 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
     if (lane == 0) tq = atomicAdd(queue, 1ull);
     const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
     if (traj >= ntraj) break;
+    const long long src = in_idx ? __ldg(in_idx + traj) : traj;  // dataset row of the inputs (outputs stay at traj)
+    const double* __restrict__ u0t = u0 + src * N;
 
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
     double Tval = 0.0, xT = 0.0, mybT = 0.0, my_sk = 1.0, my_u0 = 0.0;
-    if (C::KIND == 1) { Tval = __ldg(u0 + traj * N + NS); xT = -1.0 / (mp.gas_R * Tval); }
+    if (C::KIND == 1) { Tval = __ldg(u0t + NS); xT = -1.0 / (mp.gas_R * Tval); }
     if (lane < NR) {
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
@@ -94,9 +97,9 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
 #pragma unroll
     for (int t = 0; t < CT; ++t)
 #pragma unroll
-      for (int i = 0; i < NS; ++i) U[t][i] = isval[t] ? __ldg(u0 + traj * N + i) : 0.0;
+      for (int i = 0; i < NS; ++i) U[t][i] = isval[t] ? __ldg(u0t + i) : 0.0;
     if (lane < NS) {
-      my_u0 = __ldg(u0 + traj * N + lane);
+      my_u0 = __ldg(u0t + lane);
       my_sk = my_at + fabs(my_u0) * my_rt;
     }
 
@@ -109,6 +112,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
     const double t0 = sp.t0, dtmax = tend - t0;
     const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
     const size_t pbase = (size_t)traj * sp.n_obs * sp.n_save;
+    const double* __restrict__ datat = data + (size_t)src * sp.n_obs * sp.n_save - pbase;  // datat + off reads row src
 
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0;
     double G[CT], loss_acc = 0.0;
@@ -482,7 +486,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
               const bool inside = (y >= sp.pred_lo) && (y <= sp.pred_hi);
               const size_t off = pbase + q + (size_t)sp.n_obs * isave;
               if (pred) pred[off] = yc;
-              const double d = __ldg(data + off);
+              const double d = __ldg(datat + off);
               double diff;
               if (sp.loss_kind == CRNN_LOSS_MAE_SCALED) {
                 const double iy = sm.inv_ys[lane];

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
                 long long ntraj, const double* __restrict__ data, double* __restrict__ loss,
                 double* __restrict__ gw_each, double* __restrict__ pred, int* __restrict__ n_saved,
-                int* __restrict__ retcode, crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
+                int* __restrict__ retcode, crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
+                const long long* __restrict__ in_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const WideP& W = P.w;
   const int n = W.n, ns = W.ns, nin = W.nin, nr = W.nr, nw = P.nw;
@@ -159,7 +160,8 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     const long long traj = (long long)__shfl_sync(0xffffffffu, tq, 0);
     if (traj >= ntraj) break;
 
-    double u = lane < n ? __ldg(u0 + traj * n + lane) : 0.0;
+    const long long src = in_idx ? __ldg(in_idx + traj) : traj;  // dataset row of the inputs (outputs stay at traj)
+    double u = lane < n ? __ldg(u0 + src * n + lane) : 0.0;
     const double u_init = u;
     int nsave = W.n_save;
     double tend = W.t1;
@@ -170,6 +172,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     const double t0 = W.t0, dtmax = tend - t0;
     const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
     const size_t pbase = (size_t)traj * W.n_obs * W.n_save;
+    const double* __restrict__ datat = data + (size_t)src * W.n_obs * W.n_save - pbase;  // datat + off reads row src
 
     // ================= forward: Tsit5 value solve, recording every accepted step =================
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_back = 0, nrec = 0;
@@ -325,7 +328,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
         const bool inside = (y >= W.pred_lo) && (y <= W.pred_hi);
         const size_t off = pbase + my_obs + (size_t)W.n_obs * kk;
         if (pred) pred[off] = yc;
-        const double d = __ldg(data + off);
+        const double d = __ldg(datat + off);
         double diff, g;
         if (P.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
         else { diff = lean_log_nl(clampd(d, W.pred_lo, W.pred_hi)) - lean_log_nl(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }  // one out-of-line copy of log

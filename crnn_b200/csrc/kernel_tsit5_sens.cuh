@@ -94,7 +94,10 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
              const double* __restrict__ u0, const int* __restrict__ n_save_used, long long ntraj,
              const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
              double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
-             crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue) {
+             crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
+             const long long* __restrict__ in_idx) {
+  // in_idx (or NULL): trajectory `traj` of this call reads u0 / data of dataset row in_idx[traj] (crnn_loss_grad_indexed);
+  // every output stays at position traj
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   static_assert(WPT >= 1 && WPT <= 8 && WARPS % WPT == 0 && (WPT == 1 || CT == 1), "bad warp grouping");
@@ -179,12 +182,13 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       gsync();
     }
     if (traj >= ntraj) break;
+    const double* __restrict__ u0t = u0 + (in_idx ? __ldg(in_idx + traj) : traj) * N;
 
     // U: state; Y: stage state (holds the proposed u_{n+1} from stage 6 through the save phase);
     // KO: RHS output / scratch
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
     double xT = 0.0, mybT = 0.0;
-    if (C::KIND == 1) xT = -1.0 / (mp.gas_R * __ldg(u0 + traj * N + NS));
+    if (C::KIND == 1) xT = -1.0 / (mp.gas_R * __ldg(u0t + NS));
     if (lane < NR) {
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
@@ -193,7 +197,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
 #pragma unroll
     for (int t = 0; t < CT; ++t)
 #pragma unroll
-      for (int i = 0; i < NS; ++i) U[t][i] = isval[t] ? __ldg(u0 + traj * N + i) : 0.0;
+      for (int i = 0; i < NS; ++i) U[t][i] = isval[t] ? __ldg(u0t + i) : 0.0;
 
     int nsave = sp.n_save;
     const double t0 = sp.t0;
@@ -207,13 +211,14 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       __syncwarp();
     }
     const size_t pbase = (size_t)traj * sp.n_obs * sp.n_save;
+    const double* __restrict__ datat = data + (size_t)(in_idx ? __ldg(in_idx + traj) : traj) * sp.n_obs * sp.n_save;
 
     int n_acc = 0, n_rej = 0;  // RHS evaluations = 2 + 6 * attempts, loop iterations = attempts (derived, not counted)
     double G[CT], loss_acc = 0.0;
 #pragma unroll
     for (int t = 0; t < CT; ++t) G[t] = 0.0;
     double asum = 0.0, bsum = 0.0;  // lane i < NS: dual magnitude^2 of u_i at t_n / t_{n+1}
-    if (lane < NS) { const double v = __ldg(u0 + traj * N + lane); asum = v * v; }
+    if (lane < NS) { const double v = __ldg(u0t + lane); asum = v * v; }
     // during the two initial-step phases dt holds dt0 and dtnew holds d1 (both are free until the first step)
     double t = t0, tprev = t0, dt = 0.0, dtnew = 0.0, qold = 1e-4;
     int isave = 0, ret = CRNN_RET_DEFAULT, phase = PH_F0, k1s = 0;  // k1s: slot of K1 (0 or 6), K7 in 6-k1s
@@ -221,7 +226,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // latency then overlaps the step in between instead of stalling the save phase
     const int my_q = (wig == 0 && lane < N) ? sm.row2obs[lane] : -1;
     double ts_next = __ldg(sp.saveat), d_next = 0.0;
-    if (my_q >= 0) d_next = __ldg(data + pbase + my_q);
+    if (my_q >= 0) d_next = __ldg(datat + my_q);
 
     while (true) {
       if (phase != PH_SAVE) {
@@ -418,7 +423,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
               const double sc = fma(sqrt(fmax(asum, bsum)), sm.reltol[lane], sm.abstol[lane]);
               term0 = rsum / (sc * sc);
             } else {
-              const double my_u0 = __ldg(u0 + traj * N + lane), my_sk = sm.abstol[lane] + fabs(my_u0) * sm.reltol[lane];
+              const double my_u0 = __ldg(u0t + lane), my_sk = sm.abstol[lane] + fabs(my_u0) * sm.reltol[lane];
               const double a = my_u0 / my_sk;
               term0 = rsum / (my_sk * my_sk);
               term1 = a * a;
@@ -433,7 +438,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           if (phase == PH_F0) {
             // initial step size, part 1 (ode_determine_initdt)
             if (C::KIND == 1) {
-              const double Tval = __ldg(u0 + traj * N + NS), a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]);
+              const double Tval = __ldg(u0t + NS), a = Tval / (sm.abstol[NS] + fabs(Tval) * sm.reltol[NS]);
               s1 = fma(a, a, s1);
             }
             const double d0 = sqrt(s1 / sp.norm_cnt);
@@ -520,7 +525,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             const int q = my_q;
             double g = 0.0;
             if (q >= 0) {
-              const double y = (lane < NS) ? gb.y[lane] : __ldg(u0 + traj * N + NS);  // the T row never changes
+              const double y = (lane < NS) ? gb.y[lane] : __ldg(u0t + NS);  // the T row never changes
               const double yc = clampd(y, sp.pred_lo, sp.pred_hi);
               const bool inside = (y >= sp.pred_lo) && (y <= sp.pred_hi);
               const size_t off = pbase + q + (size_t)sp.n_obs * isave;
@@ -550,7 +555,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           ++isave;
           if (isave < nsave) {
             ts_next = __ldg(sp.saveat + isave);
-            if (my_q >= 0) d_next = __ldg(data + pbase + my_q + (size_t)sp.n_obs * isave);
+            if (my_q >= 0) d_next = __ldg(datat + my_q + (size_t)sp.n_obs * isave);
           }
         }
         // commit: u_n <- u_{n+1}, K1 <- K7 (FSAL: swap the slot roles, no copy)

@@ -31,14 +31,88 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+class Dataset:
+    """Device-resident u0_list / ode_data_list of a script (case2/case2.jl:62-83), uploaded once
+    (`crnn_dataset_create`); split into contiguous shards on a multi-device Engine."""
+
+    def __init__(self, engine: "Engine", u0, data):
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if u0.ndim != 2 or data.ndim != 3 or data.shape[0] != u0.shape[0]:
+            raise ValueError("u0 must be [N, n_state] and data [N, n_save, n_obs]")
+        self.engine, self.N = engine, u0.shape[0]
+        self.n_state, self.n_save, self.n_obs = u0.shape[1], data.shape[1], data.shape[2]
+        d = C.c_void_p()
+        engine._check(engine._lib.crnn_dataset_create(engine._h, u0.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p),
+                                                      self.n_state, self.n_obs, self.n_save, self.N, C.byref(d)))
+        self._d = d
+
+    def close(self):
+        if getattr(self, "_d", None) and getattr(self.engine, "_h", None):
+            self.engine._lib.crnn_dataset_destroy(self._d)
+        self._d = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.N
+
+
 class Engine:
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, devices=None):
+        """`device`: one CUDA device (-1 = current).  `devices`: a list of device ids (or an int n = devices 0..n-1) for
+        ONE handle over several GPUs of this process (`crnn_create_multi`: shards + NCCL all-reduce of the gradient)."""
         self._lib = _abi.load_library()
         h = C.c_void_p()
-        rc = self._lib.crnn_create(C.byref(h), int(device))
+        if devices is not None:
+            ids = np.arange(int(devices), dtype=np.int32) if np.isscalar(devices) else np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self._lib.crnn_create_multi(C.byref(h), ids.ctypes.data_as(C.c_void_p), int(ids.size))
+            what = f"crnn_create_multi({ids.tolist()})"
+        else:
+            rc = self._lib.crnn_create(C.byref(h), int(device))
+            what = "crnn_create"
         if rc != 0:
-            raise EngineError(f"crnn_create failed ({rc}): no usable CUDA device; crnn_b200 has no CPU path")
+            raise EngineError(f"{what} failed ({rc}): no usable CUDA device (or NCCL); crnn_b200 has no CPU path")
         self._h = h
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._lib.crnn_device_count(self._h))
+
+    def dataset(self, u0, data) -> Dataset:
+        return Dataset(self, u0, data)
+
+    def loss_grad_indexed(self, model: CRNNModel, opts: SolveOpts, seed, ds: Dataset, yscale,
+                          loss_kind=_abi.LOSS_MAE_SCALED, idx=None, n_save_used=None, want_loss=False, want_stats=False):
+        """`crnn_loss_grad_indexed`: loss + gradient over rows `idx` (None = all) of a device-resident dataset.
+        -> dict(loss_sum, n_ok, loss_mean, grad_sum [np], and loss / n_saved / retcode / stats when asked for)."""
+        n_obs, n = opts.n_obs(model.n_state), model.n_state
+        cm, k1 = model.to_c()
+        co, k2 = opts.to_c(n, False)
+        seed = np.asarray(seed, dtype=np.float64)
+        if seed.ndim != 2 or seed.shape[0] != model.n_w:
+            raise ValueError(f"seed must be [n_w={model.n_w}, np]")
+        n_p = seed.shape[1]
+        seed_flat = np.ascontiguousarray(seed.reshape(-1, order="F"))
+        ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (n_obs,), "yscale")
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.int64).reshape(-1)
+        M = ds.N if ix is None else ix.size
+        nsu = None if n_save_used is None else self._host(n_save_used, np.int32, (M,), "n_save_used")
+        ls, grad = np.zeros(2), np.zeros(n_p)
+        loss = np.empty(M) if want_loss else None
+        n_saved = np.empty(M, dtype=np.int32) if want_loss else None
+        ret = np.empty(M, dtype=np.int32) if want_loss else None
+        stats = np.empty(M, dtype=STATS_DTYPE) if want_stats else None
+        hp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.crnn_loss_grad_indexed(
+            self._h, C.byref(cm), C.byref(co), hp(seed_flat), n_p, ds._d, hp(ix), M, hp(nsu), hp(ys), int(loss_kind),
+            hp(ls), hp(grad), hp(loss), hp(n_saved), hp(ret), hp(stats)))
+        return dict(loss_sum=float(ls[0]), n_ok=int(ls[1]), loss_mean=float(ls[0] / max(ls[1], 1.0)), grad_sum=grad,
+                    loss=loss, n_saved=n_saved, retcode=ret, stats=stats)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -32,6 +32,9 @@ class CRNNProblem:
         self.out_scale = out_scale
         self.engine = engine or Engine()
         self.opts = self.case.opts(obs_idx=self.i_obs, **opt_overrides)
+        # the training set lives on the device(s): uploaded once, every optimiser step then moves only weights in and
+        # [loss, gradient] out (crnn_dataset_create / crnn_loss_grad_indexed)
+        self.dataset = self.engine.dataset(self.u0_list, self.ode_data_list)
 
     # -- the scripts' functions ------------------------------------------------------------
     def p2vec(self, p):
@@ -62,11 +65,10 @@ class CRNNProblem:
         idx = np.atleast_1d(np.asarray(idx))
         model, seed = self.case.model(p, self.out_scale)
         nsu = None if sample is None else np.broadcast_to(np.asarray(sample, dtype=np.int32), idx.shape).copy()
-        r = self.engine.loss_grad_batch(model, self.opts, seed, self.u0_list[idx], self.ode_data_list[idx],
-                                        self.yscale, self.case.loss_kind, n_save_used=nsu)
-        ok = r["n_saved"] > 0
-        n = max(int(ok.sum()), 1)
-        return float(np.nansum(r["loss"]) / n), r["grad_sum"] / n
+        r = self.engine.loss_grad_indexed(model, self.opts, seed, self.dataset, self.yscale, self.case.loss_kind,
+                                          idx=idx, n_save_used=nsu)
+        n = max(r["n_ok"], 1)
+        return r["loss_sum"] / n, r["grad_sum"] / n
 
     # -- the epoch loop ---------------------------------------------------------------------
     def train(self, p, opt: _optim.Optimiser, n_epoch, n_exp_train, batch=None, grad_max=None, rng=None,
@@ -91,8 +93,8 @@ class CRNNProblem:
                 opt.update(p, grad)
             n_exp = self.u0_list.shape[0]
             model, seed = self.case.model(p, self.out_scale)
-            losses = self.engine.loss_grad_batch(model, self.opts, seed, self.u0_list, self.ode_data_list,
-                                                 self.yscale, self.case.loss_kind)["loss"]
+            losses = self.engine.loss_grad_indexed(model, self.opts, seed, self.dataset, self.yscale,
+                                                   self.case.loss_kind, want_loss=True)["loss"]
             loss_train = float(np.mean(losses[:n_exp_train]))
             loss_val = float(np.mean(losses[n_exp_train:])) if n_exp > n_exp_train else float("nan")
             history.append((loss_train, loss_val, float(np.mean(gnorms))))

@@ -215,6 +215,40 @@ int crnn_loss_grad_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o
  * dst is host memory (on_device = 0) or device memory (on_device = 1, copied on `stream`). */
 int crnn_copy_grad_each(crnn_handle* h, double* dst, int64_t N, int32_t np, int32_t on_device, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident training sets and multi-GPU handles.
+ *
+ * The scripts' epoch loop (case2/case2.jl:192-207) evaluates loss and gradient over the SAME u0_list /
+ * ode_data_list (case2.jl:62-83) at every optimiser step; only p changes.  crnn_dataset_create uploads the
+ * arrays once; crnn_loss_grad_indexed then moves only weights + seed in and [sum loss, n, grad_sum] out.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct crnn_dataset crnn_dataset;
+
+/* One handle over several CUDA devices of this process (device_ids == NULL: devices 0..n_devices-1).  Datasets are
+ * split into contiguous shards, one per device; every device solves its rows on its own stream and the only exchange,
+ * [sum loss, n, grad_sum] (np + 2 doubles), is an ncclAllReduce over NVLink enqueued on the compute streams
+ * (ncclCommInitAll; libnccl.so.2 is loaded with dlopen, CRNN_ERR_UNSUPPORTED if n_devices > 1 and it is missing).
+ * crnn_solve_batch / crnn_loss_grad_batch on such a handle take HOST buffers and shard them the same way. */
+int crnn_create_multi(crnn_handle** h, const int32_t* device_ids, int32_t n_devices);
+int32_t crnn_device_count(const crnn_handle* h);
+
+/* u0 [n_state, N], data [n_obs, n_save, N] (host) -> device memory of the handle's device(s). */
+int crnn_dataset_create(crnn_handle* h, const double* u0, const double* data, int32_t n_state, int32_t n_obs,
+                        int32_t n_save, int64_t N, crnn_dataset** ds);
+void crnn_dataset_destroy(crnn_dataset* ds);
+int64_t crnn_dataset_size(const crnn_dataset* ds);
+
+/* crnn_loss_grad_batch over rows idx[0..n_idx) of a dataset (idx == NULL: every row, in order) — the mini-batch
+ * `for i_exp in randperm(n_exp_train)` picks (case2.jl:194).  All pointers are HOST memory.
+ *   n_save_used [n_idx] or NULL (per picked row, rober_crnn.jl:218)
+ *   loss_sum    [2]: sum of the finite per-trajectory losses and how many there were (mean loss = [0]/[1])
+ *   grad_sum    [np]: sum over the picked rows of d loss_i / d p (all devices)
+ *   loss, n_saved, retcode, stats: [n_idx] each or NULL (skipping them skips their device->host copies) */
+int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int32_t np,
+                           const crnn_dataset* ds, const int64_t* idx, int64_t n_idx, const int32_t* n_save_used,
+                           const double* yscale, int32_t loss_kind, double* loss_sum, double* grad_sum, double* loss,
+                           int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
+
 /* Diagnostic: evaluates the engine's device log / exp / pow (crnn_b200/csrc/lean_math.h) elementwise on host arrays,
  * op 0: y = log(x), 1: exp(x), 2: x^x2, 3: log10(x), 4: 10^x.  The same header compiles for the host; the tests
  * use this entry point to show the two copies agree bit for bit. */

@@ -41,6 +41,25 @@ mutable struct Engine
         rc == 0 || error("crnn_create failed ($rc): no CUDA device (there is no CPU fallback)")
         e = new(ref[]); finalizer(x -> ccall((:crnn_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), e); e
     end
+    "One handle over several GPUs of this process: `Engine([0,1,2,3,4,5,6,7])` (crnn_create_multi)."
+    function Engine(devices::AbstractVector{<:Integer})
+        ids = Vector{Int32}(devices); ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:crnn_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Int32}, Int32), ref, ids, length(ids))
+        rc == 0 || error("crnn_create_multi failed ($rc)")
+        e = new(ref[]); finalizer(x -> ccall((:crnn_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), e); e
+    end
+end
+
+"Device-resident `u0_list` / `ode_data_list` (uploaded once; sharded over the GPUs of a multi-device Engine)."
+mutable struct Dataset
+    d::Ptr{Cvoid}; N::Int
+    function Dataset(e::Engine, u0s::Matrix{Float64}, data::Array{Float64,3})   # n_state × N, n_obs × n_save × N
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(e, ccall((:crnn_dataset_create, LIB), Cint,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int64, Ref{Ptr{Cvoid}}),
+              e.h, u0s, data, size(u0s, 1), size(data, 1), size(data, 2), size(u0s, 2), ref))
+        ds = new(ref[], size(u0s, 2)); finalizer(x -> ccall((:crnn_dataset_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.d), ds); ds
+    end
 end
 check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:crnn_last_error, LIB), Cstring, (Ptr{Cvoid},), e.h)))
 
@@ -63,7 +82,9 @@ Base.@kwdef struct Setup
     out_scale::Union{Nothing,Vector{Float64}} = nothing
     maxiters::Int64 = 100_000
     loss_kind::Int32 = 0           # 0 MAE-scaled, 1 MAE-log (case3)
+    yscale::Vector{Float64} = Float64[]    # per observed species (case2.jl:83); used by the Dataset form of loss_grad
 end
+yscale_of(s::Setup) = isempty(s.yscale) ? ones(length(s.obs_idx)) : s.yscale
 
 function with_structs(f, s::Setup, w_in, w_b, w_out)
     w_in = Matrix{Float64}(w_in); w_b = Vector{Float64}(w_b); w_out = Matrix{Float64}(w_out)
@@ -88,15 +109,16 @@ end
 
 Drop-in for the scripts' `predict_neuralode(u0, p)`, batched: `u0s` is n_state × N.
 """
-function predict_neuralode(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, p)
+function predict_neuralode(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, p; sample=nothing)
     w_in, w_b, w_out = p2vec(p)
     N = size(u0s, 2)
+    nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)   # n_save_used: tspan = [0, tsteps[sample]] (rober_crnn.jl:125)
     pred = zeros(length(s.obs_idx), length(s.saveat), N)
     n_saved = zeros(Int32, N); ret = zeros(Int32, N)
     with_structs(s, w_in, w_b, w_out) do m, o
         check(e, ccall((:crnn_solve_batch, LIB), Cint,
               (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
-              e.h, m, o, u0s, N, C_NULL, pred, n_saved, ret, C_NULL))
+              e.h, m, o, u0s, N, sample === nothing ? C_NULL : nsu, pred, n_saved, ret, C_NULL))
     end
     pred, n_saved, ret
 end
@@ -108,7 +130,8 @@ Replaces `ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` for a batch of
 `data` is n_obs × n_save × N (a `permutedims` of the scripts' `ode_data_list[i, :, :]`).
 The result feeds the unchanged `update!(opt, p, grad)` line.
 """
-function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array{Float64,3}, yscale::Vector{Float64}, p)
+function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array{Float64,3}, yscale::Vector{Float64}, p; sample=nothing)
+    nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)   # per-experiment n_save_used (rober_crnn.jl:218)
     flat(q) = (w = p2vec(q); vcat(vec(w[1]), vec(w[2]), vec(w[3])))
     w_in, w_b, w_out = p2vec(p)
     dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat, p))      # n_w × np seed matrix
@@ -118,10 +141,36 @@ function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array
         check(e, ccall((:crnn_loss_grad_batch, LIB), Cint,
               (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int32},
                Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
-              e.h, m, o, dWdp, np_, u0s, N, C_NULL, data, yscale, s.loss_kind, loss, grad, C_NULL, n_saved, ret, C_NULL))
+              e.h, m, o, dWdp, np_, u0s, N, sample === nothing ? C_NULL : nsu, data, yscale, s.loss_kind, loss, grad,
+              C_NULL, n_saved, ret, C_NULL))
     end
     ok = n_saved .> 0
     sum(loss[ok]) / max(count(ok), 1), grad ./ max(count(ok), 1)
+end
+
+"""
+    loss_grad(e, s, p2vec, ds, idx, p; sample=nothing) -> (mean loss, mean gradient)
+
+The training-loop form: `ds` is a device-resident `Dataset`, `idx` the 1-based experiments of this step
+(`randperm(n_exp_train)[...]`, case2.jl:194; `nothing` = all of them), `sample` the per-experiment random
+time truncation of robertson/rober_crnn.jl:218 (`n_save_used`).  Per step only the weights and the seed matrix
+travel to the GPU(s) and np + 2 doubles come back.
+"""
+function loss_grad(e::Engine, s::Setup, p2vec, ds::Dataset, idx, p; sample=nothing)
+    flat(q) = (w = p2vec(q); vcat(vec(w[1]), vec(w[2]), vec(w[3])))
+    w_in, w_b, w_out = p2vec(p)
+    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat, p))
+    np_ = length(p); lsum = zeros(2); grad = zeros(np_)
+    ix = idx === nothing ? Int64[] : Vector{Int64}(idx .- 1)
+    nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)
+    with_structs(s, w_in, w_b, w_out) do m, o
+        check(e, ccall((:crnn_loss_grad_indexed, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int32, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int32},
+               Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+              e.h, m, o, dWdp, np_, ds.d, idx === nothing ? C_NULL : ix, idx === nothing ? ds.N : length(ix),
+              sample === nothing ? C_NULL : nsu, yscale_of(s), s.loss_kind, lsum, grad, C_NULL, C_NULL, C_NULL, C_NULL))
+    end
+    lsum[1] / max(lsum[2], 1.0), grad ./ max(lsum[2], 1.0)
 end
 
 """
