@@ -220,7 +220,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     double asum = 0.0, bsum = 0.0;  // lane i < NS: dual magnitude^2 of u_i at t_n / t_{n+1}
     if (lane < NS) { const double v = __ldg(u0t + lane); asum = v * v; }
     // during the two initial-step phases dt holds dt0 and dtnew holds d1 (both are free until the first step)
-    double t = t0, tprev = t0, dt = 0.0, dtnew = 0.0, qold = 1e-4;
+    double t = t0, tprev = t0, dt = 0.0, dtnew = 0.0, lqold = lean_log(1e-4);  // log(qoldinit)
     int isave = 0, ret = CRNN_RET_DEFAULT, phase = PH_F0, k1s = 0;  // k1s: slot of K1 (0 or 6), K7 in 6-k1s
     // the next save time and this lane's next target are fetched one save ahead: their global-load
     // latency then overlaps the step in between instead of stalling the save phase
@@ -469,12 +469,18 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           } else {
             // all seven stages done: PI controller, accept / reject
             const double EEst = sqrt(s0 / sp.norm_cnt);
-            double q11;
-            const double q = pi_controller<C>(sp, EEst, qold, q11);
+            // PI controller (pi_controller of crnn_dev.cuh) with log(qold) carried between steps: qold is the previous
+            // step's max(EEst, 1e-4), whose log this code already took — same values, one lean_log less per step
+            double q11 = 0.0, q = sp.inv_qmax, lE = 0.0;
+            if (EEst != 0.0) {
+              lE = lean_log(EEst);
+              q11 = lean_exp(LM_MUL(sp.beta1, lE));
+              q = jmax(sp.inv_qmax, jmin(sp.inv_qmin, q11 / lean_exp(LM_MUL(sp.beta2, lqold)) / sp.gamma));
+            }
             if (isval[0]) wb.cold[3] = dt;
             if (EEst <= 1.0) {
               ++n_acc;
-              qold = jmax(EEst, 1e-4);
+              lqold = (EEst > 1e-4) ? lE : lean_log(1e-4);   // log(qold), qold = max(EEst, qoldinit)
               dtnew = dt / q;
               tprev = t;
               t = snap_t(t + dt, wb.cold[0]);
