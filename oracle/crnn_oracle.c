@@ -252,37 +252,67 @@ static void jac_vec(const ctx_t* c, const rhs_cache* k, const double* v, double*
   rhs_sens_col(c, k, v, NULL, out);
 }
 
-/* d/d eps [ J(u + eps S, W + eps dW) v ] with v fixed: the partials a nested
- * dual Jacobian carries (Rosenbrock23(autodiff=true) under ForwardDiff.gradient,
- * robertson/rober_crnn.jl:33,219).  SURVEY §7.3 "Rosenbrock sensitivities". */
+/* Mixed second directional derivative D^2 f [ (S, dW) , (v, tau) ] of the RHS at the cached point: first direction = a
+ * dual column (state part S, weight part sd = one column of dW/dp or NULL), second direction = a state vector v
+ * (may be NULL) and a TIME component tau.  With tau = 0 this is d/d eps [ J(u + eps S, W + eps dW) v ], the partials a
+ * nested-dual Jacobian carries (Rosenbrock23(autodiff=true) under ForwardDiff.gradient, robertson/rober_crnn.jl:33,219;
+ * SURVEY §7.3); the tau part is the same for df/dt of the non-autonomous F2 (HyChem/crnn_pyrolysis_mass.jl:121-131,201).
+ * F2: with lr = log(rho), g_i = MW_i s_i / rho and ' / . for the two directions,
+ *   f'. = g [ (lr' lr. - lr'.) wdot - lr' wdot. - lr. wdot' + wdot'. ],  x_i = chiC_i (lr + log Y_i) + const. */
 static void djac_vec(const ctx_t* c, const rhs_cache* k, const double* S, const double* sd,
-                     const double* v, double* out) {
+                     const double* v, double tau, double* out) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  double q1[MAXR], q2[MAXR]; /* q1 = r.*a ; q2 = r.*(zd.*a + ad) */
+  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  double x1[MAXN + 2], x2[MAXN + 2], x12[MAXN + 2];
+  double lr1 = 0.0, lr2 = 0.0, lr12 = 0.0;
+  if (f2) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int l = 0; l < ns; ++l) { s1 += k->chi[l] * S[l] / m->mw[l]; if (v) s2 += k->chi[l] * v[l] / m->mw[l]; }
+    lr1 = -s1 / k->S;
+    lr2 = tau * (k->Pdot / k->P - k->Tdot / k->T) - s2 / k->S;
+    lr12 = s1 * s2 / (k->S * k->S);
+    for (int i = 0; i < ns; ++i) {
+      const double vi = v ? v[i] : 0.0;
+      x1[i] = k->chiC[i] * (lr1 + k->chi[i] * S[i] / k->Y[i]);
+      x2[i] = k->chiC[i] * (lr2 + k->chi[i] * vi / k->Y[i]);
+      x12[i] = k->chiC[i] * (lr12 - k->chi[i] * S[i] * vi / (k->Y[i] * k->Y[i]));
+    }
+    x1[ns] = 0.0; x2[ns] = tau * k->Tdot / (m->gas_R * k->T * k->T); x12[ns] = 0.0;
+    x1[ns + 1] = 0.0; x2[ns + 1] = tau * k->Tdot / k->T; x12[ns + 1] = 0.0;
+  } else {
+    for (int i = 0; i < nin; ++i) {
+      const double vi = v ? v[i] : 0.0;
+      x1[i] = S[i] * k->dx[i]; x2[i] = vi * k->dx[i]; x12[i] = vi * k->d2x[i] * S[i];
+    }
+  }
+  double r1[MAXR], r2[MAXR], r12[MAXR];
   for (int j = 0; j < nr; ++j) {
-    double a = 0.0, zd = 0.0, ad = 0.0;
+    double z1 = 0.0, z2 = 0.0, z12 = 0.0;
     for (int i = 0; i < nin; ++i) {
       double w = m->w_in[i + nin * j];
-      a += w * (v[i] * k->dx[i]);
-      zd += w * (S[i] * k->dx[i]);
-      ad += w * (v[i] * k->d2x[i] * S[i]);
+      z2 += w * x2[i]; z1 += w * x1[i]; z12 += w * x12[i];
     }
     if (sd) {
-      for (int i = 0; i < nin; ++i) {
-        zd += sd[i + nin * j] * k->x[i];
-        ad += sd[i + nin * j] * (v[i] * k->dx[i]);
-      }
-      zd += sd[nin * nr + j];
+      for (int i = 0; i < nin; ++i) { z1 += sd[i + nin * j] * k->x[i]; z12 += sd[i + nin * j] * x2[i]; }
+      z1 += sd[nin * nr + j];
     }
-    q1[j] = k->r[j] * a;
-    q2[j] = k->r[j] * (zd * a + ad);
+    r1[j] = k->r[j] * z1;
+    r2[j] = k->r[j] * z2;
+    r12[j] = k->r[j] * (z1 * z2 + z12);
   }
   for (int i = 0; i < ns; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * q2[j];
+    double w12 = 0.0;
+    for (int j = 0; j < nr; ++j) w12 += m->w_out[i + ns * j] * r12[j];
     if (sd)
-      for (int j = 0; j < nr; ++j) s += sd[nin * nr + nr + i + ns * j] * q1[j];
+      for (int j = 0; j < nr; ++j) w12 += sd[nin * nr + nr + i + ns * j] * r2[j];
+    double s;
+    if (f2) {
+      double w1 = 0.0, w2 = 0.0;
+      for (int j = 0; j < nr; ++j) { w1 += m->w_out[i + ns * j] * r1[j]; w2 += m->w_out[i + ns * j] * r2[j]; }
+      if (sd) for (int j = 0; j < nr; ++j) w1 += sd[nin * nr + nr + i + ns * j] * k->r[j];
+      s = ((lr1 * lr2 - lr12) * k->wdot[i] - lr1 * w2 - lr2 * w1 + w12) * m->mw[i] / k->rho;
+    } else s = w12;
     out[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) out[i] = 0.0;
@@ -606,7 +636,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
         for (int i = 0; i < n; ++i) k1[i] = K[0][col * n + i];
         if (col == 0) { for (int i = 0; i < n; ++i) k1[i] += g * dTv[i]; }
         if (col > 0) { /* + gamma * dJ * k1(value) */
-          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[1], vtmp);
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[1], 1.0, vtmp); /* + the dual part of g*dT */
           for (int i = 0; i < n; ++i) k1[i] += g * vtmp[i];
         }
         lu_solve(LU, piv, n, k1);
@@ -622,7 +652,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
           lu_solve(LU, piv, n, k2);
           for (int i = 0; i < n; ++i) { vtmp[n + i] = k2[i]; /* k2 - k1 (value) */ k2[i] += K[1][i]; }
         } else {
-          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, vtmp + n, vtmp);
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, vtmp + n, 0.0, vtmp);
           for (int i = 0; i < n; ++i) k2[i] += g * vtmp[i];
           lu_solve(LU, piv, n, k2);
           for (int i = 0; i < n; ++i) k2[i] += K[1][col * n + i];
@@ -640,7 +670,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
           for (int i = 0; i < n; ++i) k3[i] += dt * dTv[i];
           lu_solve(LU, piv, n, k3);
         } else {
-          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[3], vtmp);
+          djac_vec(c, &kc0, U + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, K[3], 1.0 / d, vtmp); /* g*tau = dt: the dual part of dt*dT */
           for (int i = 0; i < n; ++i) k3[i] += g * vtmp[i];
           lu_solve(LU, piv, n, k3);
         }
@@ -1210,8 +1240,6 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
-  /* F2: gradients ride Tsit5 only (the nested-dual dJ terms of Rosenbrock23 are not restated for F2) */
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));
@@ -1284,6 +1312,18 @@ int crnn_oracle_rhs_t(const crnn_model* m, double t, const double* u, double* du
   return CRNN_OK;
 }
 
+/* at time t: dS = f'[(S, seedcol)], dJv = D^2 f[(S, seedcol), (v, tau)] */
+int crnn_oracle_rhs_sens_t(const crnn_model* m, double t, const double* u, const double* S, const double* seedcol,
+                           const double* v, double tau, double* dS, double* dJv) {
+  crnn_opts o; memset(&o, 0, sizeof(o));
+  ctx_t c; make_ctx(&c, m, &o, NULL, 0);
+  rhs_cache k; double du[MAXN];
+  rhs_value(&c, t, u, du, &k);
+  rhs_sens_col(&c, &k, S, seedcol, dS);
+  if (dJv) djac_vec(&c, &k, S, seedcol, v, tau, dJv);
+  return CRNN_OK;
+}
+
 int crnn_oracle_rhs_sens(const crnn_model* m, const double* u, const double* S, const double* seedcol,
                          const double* v, double* dS, double* dJv) {
   crnn_opts o; memset(&o, 0, sizeof(o));
@@ -1291,7 +1331,7 @@ int crnn_oracle_rhs_sens(const crnn_model* m, const double* u, const double* S, 
   rhs_cache k; double du[MAXN];
   rhs_value(&c, m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? m->tab_t[0] : 0.0, u, du, &k);
   rhs_sens_col(&c, &k, S, seedcol, dS);
-  if (v && dJv) djac_vec(&c, &k, S, seedcol, v, dJv);
+  if (v && dJv) djac_vec(&c, &k, S, seedcol, v, 0.0, dJv);
   (void)jac_vec;
   return CRNN_OK;
 }

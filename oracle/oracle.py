@@ -186,6 +186,20 @@ def rhs_sens(model, u, S, seedcol=None, v=None):
     return dS, dJv
 
 
+def rhs_sens_t(model, t, u, S, seedcol=None, v=None, tau=0.0):
+    """(f'[(S, seedcol)], D^2 f[(S, seedcol), (v, tau)]) at (u, t): first and mixed second directional derivatives"""
+    cm, k = model.to_c()
+    u = np.ascontiguousarray(u, dtype=np.float64); S = np.ascontiguousarray(S, dtype=np.float64)
+    sc = None if seedcol is None else np.ascontiguousarray(seedcol, dtype=np.float64)
+    vv = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    dS = np.zeros(model.n_state); dJv = np.zeros(model.n_state)
+    f = lib().crnn_oracle_rhs_sens_t
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(CModel), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    f(C.byref(cm), float(t), _p(u), _p(S), _p(sc), _p(vv), float(tau), _p(dS), _p(dJv))
+    return dS, dJv
+
+
 def tsit5_tableau():
     a = np.zeros((7, 6)); bt = np.zeros(7); r = np.zeros((7, 4))
     lib().crnn_oracle_tsit5_tableau(_p(a), _p(bt), _p(r))

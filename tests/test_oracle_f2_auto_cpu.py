@@ -280,3 +280,55 @@ def test_gene_regulatory_checkpoint_reproduces_the_generating_mechanism(golden):
     assert mae < 4.3e-3, mae                                          # measured 1.9e-3 on noise-free targets
     # the DNA species are constants of the trained model too
     np.testing.assert_allclose(pred["pred"][:, :, [0, 3, 6]], np.repeat(np.clip(u0[:, None, [0, 3, 6]], c.lb, c.ub), 40, axis=1), rtol=1e-12)
+
+
+def test_mixed_second_derivative_of_the_f2_rhs_against_finite_differences():
+    """D^2 f[(S, dW), (v, tau)] - the partials a nested-dual Jacobian / time derivative carry when
+    ForwardDiff.gradient runs through Rosenbrock23 (crnn_pyrolysis_mass.jl:29,201) - against central differences of the
+    first directional derivative, state AND time direction, on the non-autonomous density-coupled F2 RHS."""
+    m, seed = cases.hychem_model(cases.hychem_p(3, stiff=2.0), YS)
+    g = np.random.default_rng(0)
+    u = cases.hychem_u0(4)[2]
+    t = 0.37 * m.tab_t[-1]
+    for col in (0, 5, 33, 120, 210):
+        S = g.standard_normal(9) * u
+        v = g.standard_normal(9) * u
+        sc = seed[:, col]
+        for tau in (0.0, 1.0, 2.5):
+            _, d2 = oracle.rhs_sens_t(m, t, u, S, sc, v, tau)
+            h = 1e-6
+            hp = oracle.rhs_sens_t(m, t + h * tau * m.tab_t[-1] * 0 + h * tau, u + h * v, S, sc)[0]
+            hm = oracle.rhs_sens_t(m, t - h * tau, u - h * v, S, sc)[0]
+            fd = (hp - hm) / (2 * h)
+            np.testing.assert_allclose(d2, fd, rtol=2e-5, atol=2e-6 * np.abs(fd).max())
+
+
+@pytest.mark.parametrize("alg", ["ros23", "auto"])
+def test_f2_stiff_forward_gradient_through_rosenbrock23_and_the_composite(alg):
+    """What the HyChem script really runs: ForwardDiff.gradient through AutoTsit5(Rosenbrock23) on the F2 model
+    (crnn_pyrolysis_mass.jl:29,201).  All 211 columns, vs central differences of tight solves."""
+    p = cases.hychem_p(2, stiff=4.0)
+    m, seed = cases.hychem_model(p, YS)
+    u0 = cases.hychem_u0(1)
+    data = oracle.solve_batch(cases.hychem_model(cases.hychem_p(5, stiff=4.0), YS)[0],
+                              cases.hychem_opts(alg=ALG["ros23"], abstol=1e-12, reltol=1e-9), u0)["pred"]
+    o = cases.hychem_opts(alg=ALG[alg], abstol=1e-11, reltol=1e-7, maxiters=1000000)
+    r = oracle.loss_grad_batch(m, o, seed, u0, data, YS)
+    assert r["retcode"][0] == _abi.RET_SUCCESS
+    if alg == "auto":
+        assert r["stats"]["n_jac"][0] > 0          # the composite did switch to Rosenbrock23
+
+    def loss_at(pv):
+        mm, _ = cases.hychem_model(pv, YS)
+        pr = oracle.solve_batch(mm, o, u0)["pred"]
+        return np.mean(np.abs(pr / YS - data / YS))
+    # the composite's switch points move discretely with p: its loss is only piecewise smooth, a wider difference
+    # averages over the jumps
+    h, tol = (1e-4, 5e-3) if alg == "ros23" else (1e-3, 2e-2)
+    for k in (0, 7, 12, 24, 33, 101, 125, 199, 210):
+        pp, pm = p.copy(), p.copy(); pp[k] += h; pm[k] -= h
+        fd = (loss_at(pp) - loss_at(pm)) / (2 * h)
+        assert abs(r["grad_sum"][k] - fd) < tol * max(abs(fd), np.abs(r["grad_sum"]).max() * 1e-2), (k, r["grad_sum"][k], fd)
+    if alg == "auto":   # and it is the derivative Rosenbrock23 alone gives, to the integration tolerance
+        rr = oracle.loss_grad_batch(m, cases.hychem_opts(alg=ALG["ros23"], abstol=1e-11, reltol=1e-7, maxiters=1000000), seed, u0, data, YS)
+        np.testing.assert_allclose(r["grad_sum"], rr["grad_sum"], rtol=1e-3, atol=1e-4 * np.abs(rr["grad_sum"]).max())
