@@ -7,6 +7,7 @@
 #include "kernel_kencarp4_wide.cuh"
 #include "kernel_tsit5_adjoint.cuh"
 #include "kernel_wide_solve.cuh"
+#include "kernel_gen_sens.cuh"
 
 namespace crnn_host {
 #define X(NS_, NR_, K_)                                                                                     \
@@ -238,6 +239,90 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   }, np, post);
 }
 
+// Generic forward sensitivities (kernel_gen_sens.cuh): any dimensions <= 32, F0 / F1 / F2, Tsit5 / Rosenbrock23 /
+// AutoTsit5(Rosenbrock23), np <= 255, structured seed columns (one w_in row and at most one w_out entry per column - the
+// shape of every p2vec of the reference).  Returns CRNN_ERR_UNSUPPORTED (with *fits = false) when the model cannot be
+// served so that the caller can try the adjoint route.
+int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                      const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
+  if (np < 1 || np > 255) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel supports 1 <= np <= 255");
+  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
+  const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
+  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int cols = 32 * ((np + 31) / 32);
+  const size_t smem = sizeof(GenShared) + (size_t)9 * n * cols * sizeof(double);
+  if (smem > 227 * 1024)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "n_state * np too large for the generic forward-sensitivity kernel's shared memory");
+  // structured seed columns
+  const int off_b = nin * nr, off_out = off_b + nr, nw = nr * (nin + 1 + ns);
+  std::vector<R1Desc> desc(cols, R1Desc{});
+  std::vector<double> rows((size_t)2 * nr * cols, 0.0);
+  for (int c = 0; c < np; ++c) {
+    const double* s = dW_dp + (size_t)nw * c;
+    R1Desc d{};
+    int i_in = -1, n_out = 0;
+    for (int j = 0; j < nr; ++j) {
+      for (int i = 0; i < nin; ++i)
+        if (s[i + nin * j] != 0.0) {
+          if (i_in >= 0 && i_in != i) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel needs structured seed columns (one w_in row per parameter)");
+          i_in = i;
+        }
+      for (int i = 0; i < ns; ++i)
+        if (s[off_out + i + ns * j] != 0.0) {
+          if (++n_out > 1) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel needs structured seed columns (one w_out entry per parameter)");
+          d.i_out = i; d.j_out = j;
+          d.o = s[off_out + i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * (f2 ? m->mw[i] : 1.0);
+        }
+    }
+    d.i_in = i_in < 0 ? 0 : i_in;
+    desc[c] = d;
+    for (int j = 0; j < nr; ++j) {
+      rows[(size_t)j * cols + c] = i_in < 0 ? 0.0 : s[i_in + nin * j];
+      rows[(size_t)(nr + j) * cols + c] = s[off_b + j];
+    }
+  }
+  // extra device doubles: inv_ys[n] | rows[2*nr*cols] | desc[cols] (3 doubles each)
+  static_assert(sizeof(R1Desc) == 24, "R1Desc is packed as three doubles");
+  std::vector<double> extra((size_t)n + rows.size() + 3 * (size_t)cols, 1.0);
+  for (int q = 0; q < o->n_obs; ++q) {
+    const int r = o->obs_idx[q];
+    if (r >= 0 && r < n && loss_kind == CRNN_LOSS_MAE_SCALED) extra[r] = 1.0 / yscale[q];
+  }
+  std::memcpy(extra.data() + n, rows.data(), rows.size() * sizeof(double));
+  std::memcpy(extra.data() + n + rows.size(), desc.data(), desc.size() * sizeof(R1Desc));
+  GenP G{};
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  const double* extra_dev = nullptr;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  int rcw = build_wide(h, m, o, order, extra, st, G.w, &extra_dev);
+  if (rcw) return rcw;
+  G.inv_ys = extra_dev; G.seed_rows = extra_dev + n;
+  G.desc = reinterpret_cast<const R1Desc*>(extra_dev + n + rows.size());
+  G.np = np; G.cols = cols; G.loss_kind = loss_kind; G.incl_sens = o->err_norm_includes_sens ? 1 : 0;
+  G.norm_cnt = (double)n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)(np + 1) : 1.0);
+  auto kern = f2 ? k_gen_sens<true> : k_gen_sens<false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, cols, smem));
+  if (bps < 1) bps = 1;
+  const long long max_blocks = (long long)h->num_sms * bps;
+  return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) -> int {
+    if (b.n == 0) return (int)CRNN_OK;
+    const unsigned blocks = (unsigned)std::min<long long>(max_blocks, b.n);
+    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    ProfScope prof(h, s);
+    kern<<<blocks, cols, smem, s>>>(G, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode,
+                                    b.stats, queue, b.in_idx);
+    CK(cudaGetLastError());
+    h->launches++;
+    return (int)CRNN_OK;
+  });
+}
+
 // lean_math.h on the device, elementwise (crnn_debug_lean_math)
 __global__ void k_lean_math(int op, const double* __restrict__ x, const double* __restrict__ y2, double* __restrict__ y, long long n) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -268,22 +353,33 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   if (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT)
     return loss_grad_adjoint(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
   h->last_grad_np = np; h->last_grad_n = N;
+  // the dimension-specialised warp-per-trajectory kernels where they exist (Tsit5: np <= 255; Rosenbrock23: n_species <= 6,
+  // np <= 63) ...
+  const char* force = std::getenv("CRNN_B200_FORCE_GENERIC");
+  const bool spec_alg = o->alg == CRNN_ALG_TSIT5 || (o->alg == CRNN_ALG_ROSENBROCK23 && m->n_species <= 6 && np <= 63);
+  if (spec_alg && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
-  CRNN_FOR_EACH_CFG(X)
+    CRNN_FOR_EACH_CFG(X)
 #undef X
-  // No dimension-specialised forward-mode kernel.  With the value-only error norm the forward-mode gradient IS the
-  // derivative of the recorded step sequence, i.e. what the discrete adjoint computes (any dimensions <= 32, F2 included).
+  }
+  // ... and the generic block-per-trajectory kernel for everything else: gradients through AutoTsit5(Rosenbrock23), stiff
+  // gradients of F2 and of models with more than 6 species, any (n_species, n_reac) <= 32
+  {
+    const int rcg = loss_grad_generic(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+    if (rcg != CRNN_ERR_UNSUPPORTED) return rcg;
+  }
+  // Not servable in forward mode (dense seed, np > 255, shared memory).  With the value-only error norm the forward-mode
+  // gradient IS the derivative of the recorded step sequence, i.e. what the discrete adjoint computes.
   h->last_grad_np = -1; h->last_grad_n = -1;
   if (o->alg == CRNN_ALG_TSIT5 && !o->err_norm_includes_sens) {
     crnn_opts oa = *o;
     oa.sens_mode = CRNN_SENS_DISCRETE_ADJOINT;
     return loss_grad_adjoint(h, m, &oa, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
   }
-  return fail(h, CRNN_ERR_UNSUPPORTED,
-              "no forward-mode kernel instantiated for this (n_species, n_reac, rhs_kind): use an adjoint sens_mode, or "
-              "err_norm_includes_sens = 0 (served by the discrete adjoint)");
+  return fail(h, CRNN_ERR_UNSUPPORTED, "forward mode cannot serve this call (" + h->err + "): use an adjoint sens_mode, or "
+              "err_norm_includes_sens = 0 with Tsit5 (served by the discrete adjoint)");
 }
 }  // namespace crnn_host
 

@@ -81,6 +81,7 @@ struct alignas(16) WideWarpT {
   double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
   double x[KW_MAXN], r[KW_MAXN], r0[KW_MAXN];
   int perm[KW_MAXN];
+  int piv[KW_MAXN];   // pivot row chosen at elimination step k (LAPACK ipiv): lets a thread permute its own right-hand side in place
   // generic solve path: broadcast slots of the per-lane Jacobian factors, stage vectors
   double bdx[KW_MAXN], brr[KW_MAXN], bchi[KW_MAXN], ws[KW_MAXN];
   double dinv[KW_MAXN];  // 1/u_kk of the LU: back-substitution multiplies instead of dividing
@@ -258,6 +259,7 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
       if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
       if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
     }
+    if (lane == 0) ww.piv[k] = bi;
     __syncwarp();
     const double rk = 1.0 / ww.A[k][k];
     if (lane == k) ww.dinv[k] = rk;

@@ -1,0 +1,111 @@
+"""The generic block-per-trajectory forward-sensitivity kernel (kernel_gen_sens.cuh) against the oracle's forward mode:
+gradients through AutoTsit5(Rosenbrock23) (what case2.jl:26,195 and crnn_pyrolysis_mass.jl:29,201 run), stiff gradients
+of the F2 model and of models with more than 6 species, and every reference model on the generic path."""
+import numpy as np
+import pytest
+
+from crnn_b200 import _abi, cases
+from oracle import oracle
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+ALG = {"tsit5": _abi.ALG_TSIT5, "ros23": _abi.ALG_ROSENBROCK23, "auto": _abi.ALG_AUTO_TSIT5_ROS23}
+YS_HYCHEM = np.array([0.05, 0.02, 0.01, 0.02, 0.01, 0.02, 0.01, 0.01, 0.9])
+
+
+def _compare(got, ref, rtol_state=1e-9, rtol_loss=1e-10, rtol_grad=1e-8, counts=True):
+    if counts:
+        for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+            bad = np.nonzero(got["stats"][k] != ref["stats"][k])[0]
+            assert bad.size == 0, f"{k} differs from the oracle for trajectories {bad[:8]}"
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["n_saved"], ref["n_saved"])
+    scale = np.abs(ref["pred"]).max(axis=(0, 1), keepdims=True)
+    assert (np.abs(got["pred"] - ref["pred"]) <= rtol_state * np.abs(ref["pred"]) + 1e-12 * scale).all()
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=rtol_loss)
+    gmax = np.abs(ref["grad_sum"]).max()
+    np.testing.assert_allclose(got["grad_sum"], ref["grad_sum"], rtol=rtol_grad, atol=1e-9 * gmax)
+
+
+@pytest.mark.parametrize("name,alg,N", [("case2", "tsit5", 96), ("case1", "tsit5", 48), ("robertson", "ros23", 64),
+                                        ("case2", "ros23", 64), ("case2", "auto", 96), ("robertson", "auto", 64)])
+def test_generic_kernel_on_the_reference_models(engine, golden, monkeypatch, name, alg, N):
+    """same models as the dimension-specialised kernels serve, forced onto the generic one; partials in the error norm"""
+    monkeypatch.setenv("CRNN_B200_FORCE_GENERIC", "1")
+    pb = make_problem(name, golden, N)
+    c = pb["case"]
+    o = c.opts(obs_idx=np.arange(c.ns), alg=ALG[alg])
+    args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    stiff = alg != "tsit5"
+    _compare(got, ref, rtol_state=1e-7 if stiff else 1e-9, rtol_loss=1e-7 if stiff else 1e-10, rtol_grad=1e-6 if stiff else 1e-8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    if name == "case2" and alg == "auto":      # never stiff: the composite is bit-identical to Tsit5 (case2.jl:26 as written)
+        monkeypatch.delenv("CRNN_B200_FORCE_GENERIC")
+        fast = engine.loss_grad_batch(pb["model"], c.opts(obs_idx=np.arange(c.ns)), *args[2:], want_pred=True)
+        assert np.array_equal(fast["stats"]["n_accept"], got["stats"]["n_accept"])
+        np.testing.assert_allclose(got["grad_sum"], fast["grad_sum"], rtol=1e-10)
+    if name == "robertson" and alg == "auto":
+        assert (got["stats"]["n_jac"] > 0).any()          # the composite did switch
+
+
+def test_generic_kernel_norm_switches_and_truncation(engine, golden, monkeypatch):
+    monkeypatch.setenv("CRNN_B200_FORCE_GENERIC", "1")
+    pb = make_problem("case2", golden, 64, obs=np.array([0, 1, 3, 4, 5]))
+    nsu = np.random.default_rng(0).integers(1, 51, size=64).astype(np.int32)
+    for kw in (dict(err_norm_includes_sens=False), dict(err_norm_mean_over_partials=False), dict(alg=ALG["auto"])):
+        o = pb["case"].opts(obs_idx=np.array([0, 1, 3, 4, 5]), **kw)
+        args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+        got = engine.loss_grad_batch(*args, n_save_used=nsu, want_pred=True)
+        ref = oracle.loss_grad_batch(*args, n_save_used=nsu, want_pred=True, n_threads=8)
+        _compare(got, ref)
+        assert np.array_equal(got["n_saved"], nsu)
+
+
+def test_case3_np153_and_stiff_gradient_beyond_six_species(engine, golden, monkeypatch):
+    """Rosenbrock23 forward sensitivities for n_species = 9 (the register-LU kernel stops at 6) and the 153-column
+    Tsit5 gradient on the generic kernel; near-true weights (see tests/test_full_size_gpu.py)"""
+    from test_full_batch_parity_gpu import case3_near_true_model
+    c = cases.CASES["case3"]
+    model, seed = case3_near_true_model(c)
+    pb = make_problem("case3", golden, 48)
+    data = np.abs(pb["data"]) + 1e-6
+    for alg in ("ros23", "auto", "tsit5"):
+        if alg == "tsit5":
+            monkeypatch.setenv("CRNN_B200_FORCE_GENERIC", "1")
+        o = c.opts(obs_idx=np.arange(c.ns), alg=ALG[alg])
+        args = (model, o, seed, pb["u0"], data, pb["yscale"], c.loss_kind)
+        got = engine.loss_grad_batch(*args, want_pred=True)
+        ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+        _compare(got, ref, rtol_state=1e-6, rtol_loss=1e-6, rtol_grad=1e-5)
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "ros23", "auto"])
+def test_hychem_f2_forward_gradient_np211(engine, alg):
+    """ForwardDiff.gradient through the solver on the HyChem model (crnn_pyrolysis_mass.jl:143-147,201): 211 dual columns,
+    the non-autonomous density-coupled F2 RHS, Tsit5 / Rosenbrock23 / the composite the script names"""
+    N = 48
+    stiff = 0.0 if alg == "tsit5" else 4.0
+    kw = dict(lnA_shift=-2.0) if alg == "tsit5" else dict(stiff=stiff)
+    m, seed = cases.hychem_model(cases.hychem_p(0, **kw), YS_HYCHEM)
+    u0 = cases.hychem_u0(N)
+    data = oracle.solve_batch(cases.hychem_model(cases.hychem_p(1, **kw), YS_HYCHEM)[0],
+                              cases.hychem_opts(alg=ALG["ros23"]), u0, n_threads=8)["pred"]
+    o = cases.hychem_opts(alg=ALG[alg], maxiters=100000)
+    got = engine.loss_grad_batch(m, o, seed, u0, data, YS_HYCHEM, want_pred=True)
+    ref = oracle.loss_grad_batch(m, o, seed, u0, data, YS_HYCHEM, want_pred=True, n_threads=8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    _compare(got, ref, rtol_state=1e-6, rtol_loss=1e-7, rtol_grad=1e-5)
+    if alg == "auto":
+        assert (got["stats"]["n_jac"] > 0).any()
+
+
+def test_indexed_dataset_call_on_the_generic_kernel(engine, golden):
+    pb = make_problem("case2", golden, 150)
+    o = pb["case"].opts(obs_idx=np.arange(6), alg=ALG["auto"])
+    ds = engine.dataset(pb["u0"], pb["data"])
+    idx = np.random.default_rng(3).permutation(150)[:40]
+    a = engine.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"][idx], pb["data"][idx], pb["yscale"], pb["loss_kind"])
+    b = engine.loss_grad_indexed(pb["model"], o, pb["seed"], ds, pb["yscale"], pb["loss_kind"], idx=idx, want_loss=True)
+    assert np.array_equal(a["loss"], b["loss"]) and np.array_equal(a["grad_sum"], b["grad_sum"])
+    ds.close()
