@@ -182,10 +182,16 @@ def test_bad_arguments_are_engine_errors(engine, golden):
     with pytest.raises(EngineError):   # beyond the generic kernel's 32 state components
         m = cases.CRNNModel(w_in=np.ones((40, 2)), w_b=np.zeros(2), w_out=np.ones((40, 2)))
         engine.solve_batch(m, pb["case"].opts(obs_idx=np.arange(40)), np.ones((2, 40)))
-    with pytest.raises(EngineError):   # forward sensitivities exist only for the instantiated dimensions
-        m = cases.CRNNModel(w_in=np.ones((4, 2)), w_b=np.zeros(2), w_out=np.ones((4, 2)))
-        engine.loss_grad_batch(m, pb["case"].opts(obs_idx=np.arange(4)), np.zeros((m.n_w, 3)), np.ones((2, 4)),
+    m = cases.CRNNModel(w_in=np.ones((4, 2)), w_b=np.zeros(2), w_out=np.ones((4, 2)))
+    with pytest.raises(EngineError):   # a DENSE seed column (several w_in rows) on dimensions without a specialised kernel,
+        # partials in the error norm: neither the generic forward kernel nor the discrete adjoint computes that
+        engine.loss_grad_batch(m, pb["case"].opts(obs_idx=np.arange(4)), np.ones((m.n_w, 3)), np.ones((2, 4)),
                                np.ones((2, 50, 4)), np.ones(4))
+    # structured columns on the same dimensions are served by the generic forward kernel
+    sd = np.zeros((m.n_w, 3)); sd[0, 0] = 1.0; sd[8, 1] = 1.0; sd[10, 2] = 1.0
+    r = engine.loss_grad_batch(m, pb["case"].opts(obs_idx=np.arange(4), t1=1.0, saveat=np.linspace(0, 1, 50)), sd,
+                               np.full((2, 4), 0.5), np.ones((2, 50, 4)), np.ones(4))
+    assert (r["retcode"] == 1).all() and np.isfinite(r["grad_sum"]).all()
 
 
 def test_full_size_properties_case2(engine, golden):
