@@ -15,10 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libcrnn_b200.so")
 
 # enums (include/crnn_b200.h)
-RHS_F0, RHS_F1, RHS_F2 = 0, 1, 2
+RHS_F0, RHS_F1, RHS_F2, RHS_F5 = 0, 1, 2, 3
 ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4, ALG_AUTO_TSIT5_ROS23 = 0, 1, 2, 3
 SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT, SENS_DISCRETE_ADJOINT = 0, 1, 2, 3
-LOSS_MAE_SCALED, LOSS_MAE_LOG = 0, 1
+LOSS_MAE_SCALED, LOSS_MAE_LOG, LOSS_MSE = 0, 1, 2
 RET_DEFAULT, RET_SUCCESS, RET_DTNAN, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 3, 4, 5, 6
 ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4
 
@@ -33,6 +33,7 @@ class CModel(C.Structure):
         ("lb", C.c_double), ("ub", C.c_double), ("gas_R", C.c_double),
         ("out_scale", c_double_p), ("w_in", c_double_p), ("w_b", c_double_p), ("w_out", c_double_p),
         ("mw", c_double_p), ("tab_t", c_double_p), ("tab_T", c_double_p), ("tab_P", c_double_p),
+        ("w_obs", c_double_p),
     ]
 
 
@@ -71,7 +72,7 @@ EXPORTS = (
     "crnn_create", "crnn_destroy", "crnn_last_error", "crnn_version", "crnn_launch_count",
     "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end", "crnn_copy_grad_each",
     "crnn_debug_lean_math", "crnn_create_multi", "crnn_device_count", "crnn_dataset_create", "crnn_dataset_destroy",
-    "crnn_dataset_size", "crnn_loss_grad_indexed",
+    "crnn_dataset_size", "crnn_loss_grad_indexed", "crnn_loss_grad_particles",
 )
 
 _lib = None
@@ -121,6 +122,11 @@ def load_library(path: str | None = None) -> C.CDLL:
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.crnn_loss_grad_indexed.restype = C.c_int
+    lib.crnn_loss_grad_particles.argtypes = [
+        C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p]
+    lib.crnn_loss_grad_particles.restype = C.c_int
     lib.crnn_solve_batch.argtypes = [
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

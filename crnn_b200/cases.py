@@ -466,3 +466,78 @@ def true_model_gene(lb=1e-30) -> CRNNModel:
 # as written: atol 1e-5 / rtol 1e-2 under the silently ignored keywords -> the solver defaults
 CASES["gene"] = Case("gene", 9, 15, 285, _abi.RHS_F0, 1e-5, 100.0, _abi.ALG_TSIT5, 1e-6, 1e-3,
                      (0.0, 4.0), 40, p2vec_gene, (1e-5, 100.0), _abi.LOSS_MAE_SCALED, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Cathode thermal decomposition (DSC): three sequential reactions c1 -> c2 -> c3 -> products under a linear temperature
+# ramp, observed through the heat release.  RHS flavour F5 + observable post-map.
+#   Cathode/src/network.jl                     deterministic fit, MAE loss, clamped p2vec (:27-50)
+#   Cathode_NCM333_UQ/src_333/network.jl       SVGD: 100 particles x 5 heating rates, linear p2vec with p_scales, MSE loss
+# ---------------------------------------------------------------------------------------------------------------------
+CATHODE_GAS_R = 8.314          # `const R = -1.0 / 8.314` (Cathode/src/network.jl:67): x = R/T = -1/(8.314 T)
+CATHODE_T0 = 100.0 + 273.15    # K (network.jl:106, src_333/network.jl:196)
+
+
+def _pack_cathode(order: _D, Ea: _D, b: _D, lnA: _D, nu: _D, delH: _D):
+    """-> (w_in [5,3], w_b [3], w_out [3,3], w_obs [3], dW_dp [n_w = 30, np]) of the F5 form of `crnn!` / `HRR_getter`:
+    w_in = [diag(order); (Ea 1e5)'; b'], w_b = ln A, w_out = [[-1,0,0],[nu2,-1,0],[0,nu3,-1]], w_obs = delH."""
+    n_p = lnA.j.shape[-1]
+    w_in = np.zeros((5, 3)); j_in = np.zeros((5, 3, n_p))
+    for k in range(3):
+        w_in[k, k] = order.v[k]; j_in[k, k] = order.j[k]
+        w_in[3, k] = Ea.v[k] * 1e5; j_in[3, k] = Ea.j[k] * 1e5
+        w_in[4, k] = b.v[k]; j_in[4, k] = b.j[k]
+    w_out = -np.eye(3); j_out = np.zeros((3, 3, n_p))
+    w_out[1, 0] = nu.v[0]; j_out[1, 0] = nu.j[0]     # du[2] += w_out[2] * rxn_rates[1]
+    w_out[2, 1] = nu.v[1]; j_out[2, 1] = nu.j[1]     # du[3] += w_out[3] * rxn_rates[2]
+    seed = np.concatenate([j_in.reshape(-1, n_p, order="F"), lnA.j.reshape(-1, n_p), j_out.reshape(-1, n_p, order="F"),
+                           delH.j.reshape(-1, n_p)], axis=0)
+    return w_in, lnA.v.copy(), w_out, delH.v.copy(), np.asfortranarray(seed)
+
+
+def p2vec_cathode(p):
+    """Cathode/src/network.jl:27-50 (18 parameters, slope last, clamps as written)."""
+    d = _D.seed(p)
+    slope = d[17] * 10.0
+    lnA = (d[0:3] * (slope * 20.0).broadcast_scalar((3,))).clamp(0.0, 50.0)
+    nu = d[15:17].clamp(0.01, 5.0)
+    order = d[12:15].clamp(0.01, 10.0)
+    Ea = d[3:6].abs().clamp(0.0, 3.0)
+    b = d[6:9]
+    delH = (d[9:12].abs() * 100.0).clamp(10.0, 300.0)
+    return _pack_cathode(order, Ea, b, lnA, nu, delH)
+
+
+def p2vec_cathode_uq(p, p_scales):
+    """Cathode_NCM333_UQ/src_333/network.jl:93-108,153-168: linear in p, every entry scaled by p_scales (17 parameters)."""
+    d = _D.seed(p)
+    sc = np.asarray(p_scales, dtype=np.float64)
+    scaled = lambda a, b_: _D(d.v[a:b_] * sc[a:b_], d.j[a:b_] * sc[a:b_, None])
+    lnA, Ea, b, delH, order, nu = scaled(0, 3), scaled(3, 6), scaled(6, 9), scaled(9, 12), scaled(12, 15), scaled(15, 17)
+    return _pack_cathode(order, Ea, b, lnA, nu, delH)
+
+
+def cathode_ramp(beta_K_per_min, t_end, T0=CATHODE_T0):
+    """`getsampletemp`: T = T0 + beta/60 t (network.jl:59-64) as a two-knot table."""
+    return np.array([0.0, t_end]), np.array([T0, T0 + beta_K_per_min / 60.0 * t_end])
+
+
+def cathode_model(w_in, w_b, w_out, w_obs, beta, t_end, lb=1e-8):
+    tab_t, tab_T = cathode_ramp(beta, t_end)
+    return CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out, w_obs=w_obs, rhs_kind=_abi.RHS_F5, lb=lb, ub=10.0,
+                     gas_R=CATHODE_GAS_R, tab_t=tab_t, tab_T=tab_T)
+
+
+def cathode_opts(ts, alg=_abi.ALG_AUTO_TSIT5_ROS23, lb=1e-8, **kw) -> SolveOpts:
+    """`ODEProblem(crnn!, u0, tspan, p, abstol = lb)`, `saveat = ts` (network.jl:96,103-116); the stiff half of the
+    script's composite is TRBDF2, here Rosenbrock23 (DESIGN.md "Named deviations")."""
+    ts = np.asarray(ts, dtype=np.float64)
+    base = dict(saveat=ts, t0=float(ts[0]), t1=float(ts[-1]), alg=alg, abstol=lb, reltol=1e-3, maxiters=100000,
+                obs_idx=np.array([0]))
+    base.update(kw)
+    return SolveOpts(**base)
+
+
+def cathode_p_true():
+    """A physically plausible parameter set in the UQ script's (scaled) coordinates: ln A, Ea [1e5 J/mol], b, delH, orders, nu."""
+    return np.array([28.0, 30.0, 33.0, 1.25, 1.40, 1.60, 0.0, 0.0, 0.0, 120.0, 40.0, 60.0, 1.0, 1.2, 1.0, 0.9, 0.8])

@@ -30,7 +30,8 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
     return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
   const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
-  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const bool dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const bool f2 = dens || m->rhs_kind == CRNN_RHS_F5_TRAMP;   // inputs from T(t) tables
   const int ntab = f2 ? m->n_tab : 0;
   std::vector<int> row2obs(n, -1);
   for (int q = 0; q < o->n_obs; ++q) {
@@ -76,16 +77,16 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
     p_wb[j] = m->w_b[j];
     // out_scale (and, for F2, the molar mass of `wdot * l_MW / density * dydt_scale`) folded into the rows of w_out
     for (int i = 0; i < ns; ++i)
-      p_wout[i + ns * j] = m->w_out[i + ns * j] * (f2 ? m->mw[i] : 1.0) * (m->out_scale ? m->out_scale[i] : 1.0);
+      p_wout[i + ns * j] = m->w_out[i + ns * j] * (dens ? m->mw[i] : 1.0) * (m->out_scale ? m->out_scale[i] : 1.0);
   }
   for (int k = 0; k < o->n_save; ++k) p_save[k] = o->saveat[k];
   for (int i = 0; i < n; ++i) p_r2o[i] = row2obs[i];
   for (size_t q = 0; q < extra.size(); ++q) p_extra[q] = extra[q];
   double* p_f2 = p_extra + extra.size() + 1;
   if (f2) {
-    for (int i = 0; i < ns; ++i) p_f2[i] = m->mw[i];
+    for (int i = 0; i < ns; ++i) p_f2[i] = dens ? m->mw[i] : 1.0;
     for (int k = 0; k < ntab; ++k) {
-      p_f2[ns + k] = m->tab_t[k]; p_f2[ns + ntab + k] = m->tab_T[k]; p_f2[ns + 2 * ntab + k] = m->tab_P[k];
+      p_f2[ns + k] = m->tab_t[k]; p_f2[ns + ntab + k] = m->tab_T[k]; p_f2[ns + 2 * ntab + k] = dens ? m->tab_P[k] : 1.0;
     }
   }
   CK(h->cfg.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
@@ -105,13 +106,15 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
 // Generic predict path (kernel_wide_solve.cuh): Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23) for any
 // dimensions <= 32 and every RHS flavour.
 int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  if (m->w_obs) return fail(h, CRNN_ERR_UNSUPPORTED, "the observable post-map is served by the loss / gradient entry points");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
   int rcw = build_wide(h, m, o, order, {}, st, P, nullptr);
   if (rcw) return rcw;
   constexpr int WARPS = 7;   // two blocks of seven warps per SM (shared memory: 24.8 KB per block + 12.4 KB per warp)
-  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_wide_solve<WARPS, true> : k_wide_solve<WARPS, false>;
+  auto kern = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP) ? k_wide_solve<WARPS, true>
+                                                                                           : k_wide_solve<WARPS, false>;
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
@@ -133,6 +136,7 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
 
 // KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
 int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
+  if (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs) return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 serves F0 / F1 / F2 without an observable post-map");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
@@ -163,6 +167,8 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
 int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                       const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
   if (o->alg != CRNN_ALG_TSIT5) return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint is implemented for Tsit5");
+  if (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs || loss_kind == CRNN_LOSS_MSE)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint kernels serve F0 / F1 / F2 with the MAE losses on the states (use sens_mode FORWARD)");
   const int n = m->n_state, ns = m->n_species, nr = m->n_reac;
   const int nw = nr * (m->n_in + 1 + ns);
   if (nw > 32 * ADJ_MAX_ENT) return fail(h, CRNN_ERR_UNSUPPORTED, "adjoint kernel supports n_w <= 512");
@@ -239,27 +245,14 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   }, np, post);
 }
 
-// Generic forward sensitivities (kernel_gen_sens.cuh): any dimensions <= 32, F0 / F1 / F2, Tsit5 / Rosenbrock23 /
-// AutoTsit5(Rosenbrock23), np <= 255, structured seed columns (one w_in row and at most one w_out entry per column - the
-// shape of every p2vec of the reference).  Returns CRNN_ERR_UNSUPPORTED (with *fits = false) when the model cannot be
-// served so that the caller can try the adjoint route.
-int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
-                      const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
-  if (np < 1 || np > 255) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel supports 1 <= np <= 255");
-  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
-  const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
-  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
-  const int cols = 32 * ((np + 31) / 32);
-  const size_t smem = sizeof(GenShared) + (size_t)9 * n * cols * sizeof(double);
-  if (smem > 227 * 1024)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "n_state * np too large for the generic forward-sensitivity kernel's shared memory");
-  // structured seed columns
-  const int off_b = nin * nr, off_out = off_b + nr, nw = nr * (nin + 1 + ns);
-  std::vector<R1Desc> desc(cols, R1Desc{});
-  std::vector<double> rows((size_t)2 * nr * cols, 0.0);
+// Structured ("R1") form of one seed matrix for the generic forward kernel: every column touches w_in in at most ONE row
+// and w_out in at most ONE entry - the shape of every p2vec of the reference.  rows: [(2 or 3)*nr][cols]
+// (a_j = dW_in[i_in, j]; b_j = db_j; with an observable post-map also d w_obs_j), desc: [cols].
+int gen_plan_seed(crnn_handle* h, const crnn_model* m, const double* dW_dp, int np, int cols, bool has_obs,
+                  R1Desc* desc, double* rows) {
+  const int ns = m->n_species, nin = m->n_in, nr = m->n_reac;
+  const bool dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int off_b = nin * nr, off_out = off_b + nr, off_obs = off_out + ns * nr, nw = off_obs + (has_obs ? nr : 0);
   for (int c = 0; c < np; ++c) {
     const double* s = dW_dp + (size_t)nw * c;
     R1Desc d{};
@@ -274,7 +267,7 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
         if (s[off_out + i + ns * j] != 0.0) {
           if (++n_out > 1) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel needs structured seed columns (one w_out entry per parameter)");
           d.i_out = i; d.j_out = j;
-          d.o = s[off_out + i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * (f2 ? m->mw[i] : 1.0);
+          d.o = s[off_out + i + ns * j] * (m->out_scale ? m->out_scale[i] : 1.0) * (dens ? m->mw[i] : 1.0);
         }
     }
     d.i_in = i_in < 0 ? 0 : i_in;
@@ -282,17 +275,64 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
     for (int j = 0; j < nr; ++j) {
       rows[(size_t)j * cols + c] = i_in < 0 ? 0.0 : s[i_in + nin * j];
       rows[(size_t)(nr + j) * cols + c] = s[off_b + j];
+      if (has_obs) rows[(size_t)(2 * nr + j) * cols + c] = s[off_obs + j];
     }
   }
-  // extra device doubles: inv_ys[n] | rows[2*nr*cols] | desc[cols] (3 doubles each)
+  return CRNN_OK;
+}
+
+int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_t& smem, long long& max_blocks, bool f2k,
+                   void (**kern_out)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*,
+                                     int*, crnn_stats*, unsigned long long*, const long long*)) {
+  if (np < 1 || np > 255) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel supports 1 <= np <= 255");
+  if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
+  cols = 32 * ((np + 31) / 32);
+  smem = sizeof(GenShared) + (size_t)9 * m->n_state * cols * sizeof(double);
+  if (smem > 227 * 1024)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "n_state * np too large for the generic forward-sensitivity kernel's shared memory");
+  auto kern = f2k ? k_gen_sens<true> : k_gen_sens<false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, cols, smem));
+  if (bps < 1) bps = 1;
+  max_blocks = (long long)h->num_sms * bps;
+  *kern_out = kern;
+  return CRNN_OK;
+}
+
+// Generic forward sensitivities (kernel_gen_sens.cuh): any dimensions <= 32, F0 / F1 / F2 / F5, Tsit5 / Rosenbrock23 /
+// AutoTsit5(Rosenbrock23), np <= 255, structured seed columns, optional observable post-map, all three losses.
+// Returns CRNN_ERR_UNSUPPORTED when the model cannot be served so that the caller can try the adjoint route.
+int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                      const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
+  const int n = m->n_state, nr = m->n_reac;
+  const bool f2k = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);
+  const bool has_obs = m->w_obs != nullptr;
+  int cols = 0; size_t smem = 0; long long max_blocks = 0;
+  void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
+               unsigned long long*, const long long*) = nullptr;
+  int rc = gen_launch_cfg(h, m, np, cols, smem, max_blocks, f2k, &kern);
+  if (rc) return rc;
+  const int nrow = (has_obs ? 3 : 2) * nr;
+  std::vector<R1Desc> desc(cols, R1Desc{});
+  std::vector<double> rows((size_t)nrow * cols, 0.0);
+  rc = gen_plan_seed(h, m, dW_dp, np, cols, has_obs, desc.data(), rows.data());
+  if (rc) return rc;
+  // extra device doubles: inv_ys[n] | rows | desc[cols] (3 doubles each) | w_obs[nr]
   static_assert(sizeof(R1Desc) == 24, "R1Desc is packed as three doubles");
-  std::vector<double> extra((size_t)n + rows.size() + 3 * (size_t)cols, 1.0);
-  for (int q = 0; q < o->n_obs; ++q) {
-    const int r = o->obs_idx[q];
-    if (r >= 0 && r < n && loss_kind == CRNN_LOSS_MAE_SCALED) extra[r] = 1.0 / yscale[q];
-  }
+  std::vector<double> extra((size_t)n + rows.size() + 3 * (size_t)cols + nr, 1.0);
+  if (has_obs) { if (loss_kind != CRNN_LOSS_MAE_LOG && yscale) extra[0] = 1.0 / yscale[0]; }
+  else
+    for (int q = 0; q < o->n_obs; ++q) {
+      const int r = o->obs_idx[q];
+      if (r >= 0 && r < n && loss_kind != CRNN_LOSS_MAE_LOG) extra[r] = 1.0 / yscale[q];
+    }
   std::memcpy(extra.data() + n, rows.data(), rows.size() * sizeof(double));
   std::memcpy(extra.data() + n + rows.size(), desc.data(), desc.size() * sizeof(R1Desc));
+  for (int j = 0; j < nr; ++j) extra[(size_t)n + rows.size() + 3 * (size_t)cols + j] = has_obs ? m->w_obs[j] : 0.0;
   GenP G{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   const double* extra_dev = nullptr;
@@ -301,14 +341,9 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   if (rcw) return rcw;
   G.inv_ys = extra_dev; G.seed_rows = extra_dev + n;
   G.desc = reinterpret_cast<const R1Desc*>(extra_dev + n + rows.size());
+  G.w_obs = has_obs ? extra_dev + n + rows.size() + 3 * (size_t)cols : nullptr;
   G.np = np; G.cols = cols; G.loss_kind = loss_kind; G.incl_sens = o->err_norm_includes_sens ? 1 : 0;
   G.norm_cnt = (double)n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)(np + 1) : 1.0);
-  auto kern = f2 ? k_gen_sens<true> : k_gen_sens<false>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int bps = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, cols, smem));
-  if (bps < 1) bps = 1;
-  const long long max_blocks = (long long)h->num_sms * bps;
   return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) -> int {
     if (b.n == 0) return (int)CRNN_OK;
     const unsigned blocks = (unsigned)std::min<long long>(max_blocks, b.n);
@@ -321,6 +356,16 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
     h->launches++;
     return (int)CRNN_OK;
   });
+}
+
+// grad[c + np*p] = sum over the experiments e of grad_each[(e + E*p)*np + c], in experiment order (deterministic)
+__global__ void k_particle_reduce(const double* __restrict__ grad_each, int np, int E, int P, double* __restrict__ grad) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= np * P) return;
+  const int c = q % np, p = q / np;
+  double s = 0.0;
+  for (int e = 0; e < E; ++e) s += grad_each[((size_t)e + (size_t)E * p) * np + c];
+  grad[q] = s;
 }
 
 // lean_math.h on the device, elementwise (crnn_debug_lean_math)
@@ -341,9 +386,9 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   if (rc) return rc;
   if (N > 0 && (!io.u0 || !io.data || !io.loss)) return fail(h, CRNN_ERR_BAD_ARG, "null u0/data/loss");
   if (np < 0 || (np > 0 && !dW_dp)) return fail(h, CRNN_ERR_BAD_ARG, "bad seed matrix");
-  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG)
+  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG && loss_kind != CRNN_LOSS_MSE)
     return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
-  if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
+  if (loss_kind != CRNN_LOSS_MAE_LOG && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
   if (o->sens_mode != CRNN_SENS_FORWARD && o->sens_mode != CRNN_SENS_INTERP_ADJOINT &&
       o->sens_mode != CRNN_SENS_DISCRETE_ADJOINT)
     return fail(h, CRNN_ERR_UNSUPPORTED, "sens_mode must be FORWARD, INTERP_ADJOINT or DISCRETE_ADJOINT");
@@ -357,7 +402,8 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   // np <= 63) ...
   const char* force = std::getenv("CRNN_B200_FORCE_GENERIC");
   const bool spec_alg = o->alg == CRNN_ALG_TSIT5 || (o->alg == CRNN_ALG_ROSENBROCK23 && m->n_species <= 6 && np <= 63);
-  if (spec_alg && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {
+  if (spec_alg && (m->rhs_kind == CRNN_RHS_F0 || m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE) && !m->w_obs &&
+      loss_kind != CRNN_LOSS_MSE && !(force && force[0] == '1')) {
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
     return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
@@ -512,6 +558,137 @@ int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches) {
   if (total_ms) *total_ms = tot;
   if (n_launches) *n_launches = (int64_t)h->prof_used + nk;
   h->prof_used = 0;
+  return CRNN_OK;
+}
+
+int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* weights,
+                             const double* dW_dp, int32_t np, int32_t P, const double* u0, int32_t E,
+                             const int32_t* n_save_used, const double* data, const double* tab_T, const double* tab_P,
+                             const double* yscale, int32_t loss_kind, double* loss, double* grad, int32_t* n_saved,
+                             int32_t* retcode, crnn_stats* stats) {
+  if (!h) return CRNN_ERR_BAD_ARG;
+  if (!h->kids.empty()) return fail(h, CRNN_ERR_UNSUPPORTED, "crnn_loss_grad_particles needs a single-device handle");
+  if (!m || !o || !weights || !dW_dp || !u0 || !data || !loss || !grad || P < 1 || E < 1 || np < 1)
+    return fail(h, CRNN_ERR_BAD_ARG, "crnn_loss_grad_particles: null argument or empty batch");
+  if (o->buffers_on_device) return fail(h, CRNN_ERR_BAD_ARG, "crnn_loss_grad_particles takes host buffers");
+  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG && loss_kind != CRNN_LOSS_MSE)
+    return fail(h, CRNN_ERR_BAD_ARG, "bad loss_kind");
+  if (loss_kind != CRNN_LOSS_MAE_LOG && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
+  if (o->sens_mode != CRNN_SENS_FORWARD) return fail(h, CRNN_ERR_UNSUPPORTED, "particles: forward mode only");
+  const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
+  const bool has_obs = m->w_obs != nullptr;
+  const int off_b = nin * nr, off_out = off_b + nr, off_obs = off_out + ns * nr, nw = off_obs + (has_obs ? nr : 0);
+  // the model seen by validation / build_wide: particle 0's weights
+  crnn_model m0 = *m;
+  m0.w_in = weights; m0.w_b = weights + off_b; m0.w_out = weights + off_out;
+  if (has_obs) m0.w_obs = weights + off_obs;
+  int rc = validate(h, &m0, o, (int64_t)P * E);
+  if (rc) return rc;
+  if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
+  const bool dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const bool f2k = dens || m->rhs_kind == CRNN_RHS_F5_TRAMP;
+  if ((tab_T || tab_P) && !f2k) return fail(h, CRNN_ERR_BAD_ARG, "per-experiment tables need rhs_kind F2 or F5");
+  CK(cudaSetDevice(h->device));
+  int cols = 0; size_t smem = 0; long long max_blocks = 0;
+  void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
+               unsigned long long*, const long long*) = nullptr;
+  rc = gen_launch_cfg(h, &m0, np, cols, smem, max_blocks, f2k, &kern);
+  if (rc) return rc;
+  cudaStream_t st = h->s_compute;
+  // ---- per-particle blocks: weights in the kernel's layout, structured seed rows, descriptors ----
+  const size_t pw_stride = (size_t)nin * KW_MAXN + nr + (size_t)ns * nr + (has_obs ? nr : 0);
+  const int nrow = (has_obs ? 3 : 2) * nr;
+  const size_t seed_stride = (size_t)nrow * cols;
+  std::vector<double> pw(pw_stride * P, 0.0), rows(seed_stride * P, 0.0);
+  std::vector<R1Desc> desc((size_t)cols * P, R1Desc{});
+  for (int p = 0; p < P; ++p) {
+    const double* w = weights + (size_t)nw * p;
+    double* d = pw.data() + pw_stride * p;
+    for (int j = 0; j < nr; ++j) {
+      for (int i = 0; i < nin; ++i) d[(size_t)i * KW_MAXN + j] = w[i + nin * j];
+      d[(size_t)nin * KW_MAXN + j] = w[off_b + j];
+      for (int i = 0; i < ns; ++i)
+        d[(size_t)nin * KW_MAXN + nr + i + ns * j] = w[off_out + i + ns * j] * (dens ? m->mw[i] : 1.0) * (m->out_scale ? m->out_scale[i] : 1.0);
+      if (has_obs) d[(size_t)nin * KW_MAXN + nr + (size_t)ns * nr + j] = w[off_obs + j];
+    }
+    rc = gen_plan_seed(h, &m0, dW_dp + (size_t)nw * np * p, np, cols, has_obs, desc.data() + (size_t)cols * p, rows.data() + seed_stride * p);
+    if (rc) return rc;
+  }
+  // per-experiment tables
+  const int ntab = f2k ? m->n_tab : 0;
+  const bool per_exp = f2k && tab_T != nullptr;
+  std::vector<double> tabs;
+  if (per_exp) {
+    tabs.assign((size_t)2 * ntab * E, 1.0);
+    for (size_t q = 0; q < (size_t)ntab * E; ++q) { tabs[q] = tab_T[q]; tabs[(size_t)ntab * E + q] = (dens && tab_P) ? tab_P[q] : 1.0; }
+  }
+  // device staging (reuses the handle's buffers): [pw | rows | desc | tabs | u0 | data | nsu] in adj_scratch
+  const int64_t N = (int64_t)P * E;
+  const size_t ps = (size_t)o->n_obs * o->n_save;
+  const size_t nd_pw = pw.size(), nd_rows = rows.size(), nd_desc = 3 * desc.size(), nd_tabs = tabs.size(),
+               nd_u0 = (size_t)n * E, nd_data = ps * E, nd_nsu = n_save_used ? ((size_t)N + 1) / 2 : 0;
+  CK(h->adj_scratch.reserve((nd_pw + nd_rows + nd_desc + nd_tabs + nd_u0 + nd_data + nd_nsu + 8) * sizeof(double)));
+  double* base = h->adj_scratch.as<double>();
+  double* d_pw = base; double* d_rows = d_pw + nd_pw; double* d_desc = d_rows + nd_rows; double* d_tabs = d_desc + nd_desc;
+  double* d_u0 = d_tabs + nd_tabs; double* d_data = d_u0 + nd_u0; int* d_nsu = reinterpret_cast<int*>(d_data + nd_data);
+  CK(cudaMemcpyAsync(d_pw, pw.data(), nd_pw * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_rows, rows.data(), nd_rows * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(R1Desc), cudaMemcpyHostToDevice, st));
+  if (per_exp) CK(cudaMemcpyAsync(d_tabs, tabs.data(), nd_tabs * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_u0, u0, nd_u0 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_data, data, nd_data * sizeof(double), cudaMemcpyHostToDevice, st));
+  std::vector<int> nsu_full;
+  if (n_save_used) {   // per experiment -> per trajectory
+    nsu_full.resize(N);
+    for (int64_t q = 0; q < N; ++q) nsu_full[q] = n_save_used[q % E];
+    CK(cudaMemcpyAsync(d_nsu, nsu_full.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  std::vector<double> extra(n, 1.0);   // inv_ys
+  if (has_obs) { if (loss_kind != CRNN_LOSS_MAE_LOG) extra[0] = 1.0 / yscale[0]; }
+  else
+    for (int q = 0; q < o->n_obs; ++q) {
+      const int r = o->obs_idx[q];
+      if (r >= 0 && r < n && loss_kind != CRNN_LOSS_MAE_LOG) extra[r] = 1.0 / yscale[q];
+    }
+  GenP G{};
+  const double* extra_dev = nullptr;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  rc = build_wide(h, &m0, o, order, extra, st, G.w, &extra_dev);
+  if (rc) return rc;
+  if (per_exp) { G.w.tab_T = d_tabs; G.w.tab_P = d_tabs + (size_t)ntab * E; }
+  G.inv_ys = extra_dev; G.seed_rows = d_rows; G.desc = reinterpret_cast<const R1Desc*>(d_desc);
+  G.w_obs = nullptr; G.pw = d_pw; G.pw_stride = (long long)pw_stride; G.seed_stride = (long long)seed_stride;
+  G.n_part = P; G.n_exp = E; G.tab_per_exp = per_exp ? 1 : 0;
+  G.np = np; G.cols = cols; G.loss_kind = loss_kind; G.incl_sens = o->err_norm_includes_sens ? 1 : 0;
+  G.norm_cnt = (double)n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)(np + 1) : 1.0);
+  CK(h->d_grad_each.reserve((size_t)N * np * sizeof(double)));
+  CK(h->d_loss.reserve(N * sizeof(double)));
+  CK(h->d_nsaved.reserve(N * sizeof(int)));
+  CK(h->d_ret.reserve(N * sizeof(int)));
+  if (stats) CK(h->d_stats.reserve(N * sizeof(crnn_stats)));
+  CK(h->d_grad_sum.reserve((size_t)np * P * sizeof(double)));
+  h->last_grad_np = -1; h->last_grad_n = -1;
+  unsigned long long* queue = h->ctr.as<unsigned long long>();
+  CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+  {
+    ProfScope prof(h, st);
+    kern<<<(unsigned)std::min<long long>(max_blocks, N), cols, smem, st>>>(
+        G, d_u0, n_save_used ? d_nsu : nullptr, N, d_data, h->d_loss.as<double>(), h->d_grad_each.as<double>(), nullptr,
+        h->d_nsaved.as<int>(), h->d_ret.as<int>(), stats ? h->d_stats.as<crnn_stats>() : nullptr, queue, nullptr);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  k_particle_reduce<<<(np * P + 255) / 256, 256, 0, st>>>(h->d_grad_each.as<double>(), np, E, P, h->d_grad_sum.as<double>());
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaMemcpyAsync(grad, h->d_grad_sum.p, (size_t)np * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(loss, h->d_loss.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (n_saved) CK(cudaMemcpyAsync(n_saved, h->d_nsaved.p, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (retcode) CK(cudaMemcpyAsync(retcode, h->d_ret.p, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (stats) CK(cudaMemcpyAsync(stats, h->d_stats.p, N * sizeof(crnn_stats), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return CRNN_OK;
 }
 

@@ -142,14 +142,15 @@ struct Packed {
 inline int validate(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int64_t N) {
   if (!m || !o) return fail(h, CRNN_ERR_BAD_ARG, "null model/opts");
   if (N < 0) return fail(h, CRNN_ERR_BAD_ARG, "negative N");
-  if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP)
+  if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP &&
+      m->rhs_kind != CRNN_RHS_F5_TRAMP)
     return fail(h, CRNN_ERR_UNSUPPORTED, "rhs_kind not supported");
-  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);  // inputs from T(t) tables
   if (m->n_in != m->n_state + (f2 ? 2 : 0) || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
     return fail(h, CRNN_ERR_BAD_ARG, "inconsistent n_state / n_species / n_in for rhs_kind");
   if (f2) {
-    if (!m->mw || !m->tab_t || !m->tab_T || !m->tab_P || m->n_tab < 2)
-      return fail(h, CRNN_ERR_BAD_ARG, "F2 needs mw and the tab_t / tab_T / tab_P tables (n_tab >= 2)");
+    if (!m->tab_t || !m->tab_T || m->n_tab < 2 || (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (!m->mw || !m->tab_P)))
+      return fail(h, CRNN_ERR_BAD_ARG, "F2 needs mw and the tab_t / tab_T / tab_P tables, F5 tab_t / tab_T (n_tab >= 2)");
     for (int k = 1; k < m->n_tab; ++k)
       if (!(m->tab_t[k] > m->tab_t[k - 1])) return fail(h, CRNN_ERR_BAD_ARG, "tab_t must be strictly ascending");
     if (m->tab_t[0] > o->t0 || m->tab_t[m->n_tab - 1] < o->t1)
@@ -168,6 +169,7 @@ inline int validate(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int
     return fail(h, CRNN_ERR_BAD_ARG, "abstol/reltol must have 1 or n_state entries");
   if (o->n_obs < 0 || o->n_obs > m->n_state || (o->n_obs > 0 && !o->obs_idx))
     return fail(h, CRNN_ERR_BAD_ARG, "bad obs_idx");
+  if (m->w_obs && o->n_obs != 1) return fail(h, CRNN_ERR_BAD_ARG, "the observable post-map w_obs defines ONE observed quantity: n_obs must be 1");
   if (o->maxiters <= 0) return fail(h, CRNN_ERR_BAD_ARG, "maxiters must be positive");
   return CRNN_OK;
 }

@@ -33,6 +33,13 @@ struct GenP {
   const R1Desc* desc;      // device [cols]
   double norm_cnt;         // divisor of the norms: n*(1+np), or n
   int np, cols, loss_kind, incl_sens;
+  // observable post-map y = sum_j w_obs[j] r_j (heat release, Cathode/src/network.jl:82-91,121): seed_rows then has
+  // 3*nr rows, the last nr being d w_obs_j / d p_c
+  const double* w_obs;     // device [nr] or NULL
+  // parameter-batched mode (crnn_loss_grad_particles): trajectory = experiment e + n_exp * particle p
+  const double* pw;        // device, per particle: w_inT [nin][32] | w_b [nr] | w_out [ns x nr] | w_obs [nr]
+  long long pw_stride, seed_stride;   // doubles per particle in pw / seed_rows (desc: cols per particle)
+  int n_part, n_exp, tab_per_exp, pad;
 };
 
 struct alignas(16) GenPoint {  // by-products of one value-path evaluation, broadcast to the column threads
@@ -58,6 +65,8 @@ struct alignas(16) GenShared {
   GenDir2 d2;
   double red[3 * KW_MAXN][8];
   double rows[3 * KW_MAXN];
+  GenPoint tmp;              // at a save point (observable post-map)
+  double wobs[KW_MAXN];
   double g[KW_MAXN];         // d loss / d yhat_i at the current save point
   double bcast[8];           // scalars broadcast from thread 0: EEst, dt, ...
   long long traj;
@@ -67,25 +76,28 @@ struct alignas(16) GenShared {
 // f(y, t) of the value column (lane i holds y_i), filling the broadcast by-products `pc` and this lane's WideAux.
 template <bool F2>
 __device__ __forceinline__ double gen_rhs(const WideP& P, const WideBlock& sb, GenPoint& pc, int lane, double mw,
-                                          double t, double y, WideAux& a, int& seg) {
+                                          double t, double y, WideAux& a, int& seg, size_t toff = 0) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
   const bool isp = lane < ns;
   __syncwarp();
   double xi = 0.0, dxi = 0.0, d2i = 0.0, chiC = 1.0, chimw = 0.0, rho = 1.0;
   a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
   if (F2) {
-    const TabVal tv = wide_tab(P, t, seg);
+    // F2: HyChem mass fractions with the density map; F5 (Cathode/src/network.jl:68-80): same inputs without it
+    const bool dens = (P.kind == CRNN_RHS_F2_MASSFRAC_TP);
+    TabVal tv = wide_tab(P, t, seg, toff);
+    if (!dens) { tv.P = 1.0; tv.Pd = 0.0; }
     double Y = 1.0, chi = 0.0, ymw = 0.0;
-    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
-    const double S = wsum(ymw);
-    rho = tv.P / (kGasRu * tv.T * S);
+    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = dens ? Y / mw : 0.0; }
+    const double S = dens ? wsum(ymw) : 1.0;
+    rho = dens ? tv.P / (kGasRu * tv.T * S) : 1.0;
     chiC = 0.0;
     if (isp) {
-      const double C = rho * ymw * 1e3;
+      const double C = dens ? rho * ymw * 1e3 : Y;
       chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
       xi = lean_log(clampd(C, P.lb, P.ub));
-      dxi = chi / Y; d2i = chi / (Y * Y); chimw = chi / mw;
-      a.chiC = chiC; a.dx = chiC * chi / Y; a.rr = -chi / (mw * S);
+      dxi = chi / Y; d2i = chi / (Y * Y); chimw = dens ? chi / mw : 0.0;
+      a.chiC = chiC; a.dx = chiC * chi / Y; a.rr = dens ? -chi / (mw * S) : 0.0;
     } else if (lane == ns) {
       xi = -1.0 / P.gas_R / tv.T;
     } else if (lane == ns + 1) {
@@ -136,7 +148,7 @@ __device__ __forceinline__ void gen_dir2(const WideP& P, const WideBlock& sb, co
   const int ns = P.ns, nin = P.nin, nr = P.nr, nsd = F2 ? ns : P.n;
   __syncwarp();
   double lr2 = 0.0, s2 = 0.0;
-  if (F2) {
+  if (F2 && P.kind == CRNN_RHS_F2_MASSFRAC_TP) {
     s2 = wsum(lane < ns ? pc.chimw[lane] * v : 0.0);
     lr2 = tau * (pc.Pd / pc.Pr - pc.Td / pc.T) - s2 / pc.Ssum;
   }
@@ -248,6 +260,47 @@ __device__ __forceinline__ void col_lusolve(const WideWarp& ww, int ns, double* 
   }
 }
 
+// One column at a save point: d/d eps of the observable y = sum_j w_obs[j] r_j along (a, dW_c), a_i = colval(i):
+// sum_j ( w_obs[j] r_j z'_j + d w_obs_j r_j ),  z'_j = a_j x[i_in] + b_j + sum_i w_in[i,j] chiC_i (lr' + a_i dx_i).
+template <bool F2, class CV>
+__device__ __forceinline__ double col_obs(const WideP& P, const WideBlock& sb, const GenPoint& pc, const double* wobs,
+                                          const double* __restrict__ srow, int cols, int tid, const R1Desc& ds, CV colval) {
+  const int n = P.n, ns = P.ns, nr = P.nr, nsd = F2 ? ns : n;
+  double lr1 = 0.0;
+  if (F2 && P.kind == CRNN_RHS_F2_MASSFRAC_TP) {
+    double s1 = 0.0;
+    for (int l = 0; l < ns; ++l) s1 = fma(pc.chimw[l], colval(l), s1);
+    lr1 = -s1 / pc.Ssum;
+  }
+  const double xin = pc.x[ds.i_in];
+  double dy = 0.0;
+  for (int j0 = 0; j0 < nr; j0 += 8) {
+    double z1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q;
+      double sa = 0.0, sbb = 0.0;
+      if (j < nr) { sa = __ldg(srow + (size_t)j * cols + tid); sbb = __ldg(srow + (size_t)(nr + j) * cols + tid); }
+      z1[q] = fma(sa, xin, sbb);
+    }
+    for (int i = 0; i < nsd; ++i) {
+      const double x1 = pc.chiC[i] * (lr1 + colval(i) * pc.dx[i]);
+      const double2* w = reinterpret_cast<const double2*>(&sb.w_inT[i][j0]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 v = w[q];
+        z1[2 * q] = fma(v.x, x1, z1[2 * q]); z1[2 * q + 1] = fma(v.y, x1, z1[2 * q + 1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q;
+      if (j < nr) dy = fma(pc.r[j], fma(wobs[j], z1[q], __ldg(srow + (size_t)(2 * nr + j) * cols + tid)), dy);
+    }
+  }
+  return dy;
+}
+
 template <bool F2>
 __global__ void __launch_bounds__(256, 1)
 k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const int* __restrict__ n_save_used,
@@ -269,14 +322,21 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
   enum { SL_U = 0, SL_Y = 1, SL_K = 2 };     // K0..K6 = slots 2..8
   auto slot = [&](int s) -> double* { return colbase + ((size_t)s * n) * cols + tid; };
 
-  for (int q = tid; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
-    const int i = q / KW_MAXN, j = q % KW_MAXN;
-    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
-    sb.w_inJ[j][i] = sb.w_inT[i][j];
-    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
-  }
-  for (int q = tid; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
-  __syncthreads();
+  const bool has_obs = G.w_obs != nullptr || (G.n_part > 0 && G.pw_stride > (long long)nin * KW_MAXN + nr + (long long)ns * nr);
+  auto load_weights = [&](const double* winT, const double* wb, const double* wout, const double* wobs) {
+    for (int q = tid; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
+      const int i = q / KW_MAXN, j = q % KW_MAXN;
+      sb.w_inT[i][j] = (i < nin && j < nr) ? winT[i * KW_MAXN + j] : 0.0;
+      sb.w_inJ[j][i] = sb.w_inT[i][j];
+      sb.w_out[i][j] = (i < nr && j < ns) ? wout[j + ns * i] : 0.0;  // [reaction][species]
+    }
+    for (int q = tid; q < KW_MAXN; q += blockDim.x) {
+      sb.w_b[q] = q < nr ? wb[q] : 0.0;
+      S.wobs[q] = (wobs && q < nr) ? wobs[q] : 0.0;
+    }
+    __syncthreads();
+  };
+  if (G.n_part == 0) load_weights(P.w_inT, P.w_b, P.w_out, G.w_obs);
 
   const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23);
   const bool incl = G.incl_sens != 0;
@@ -285,7 +345,8 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
   const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
   const double my_iys = (w0 && lane < n) ? __ldg(G.inv_ys + lane) : 1.0;
   R1Desc ds{}; ds.o = 0.0;
-  if (active) ds = G.desc[tid];
+  if (active && G.n_part == 0) ds = G.desc[tid];
+  const double* srow = G.seed_rows;
   double* const kk = &ww.k[0][lane];
 #define KS(s) kk[(s) * KW_MAXN]
 #define CKS(s) slot(SL_K + (s))
@@ -313,7 +374,18 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     const long long traj = S.traj;
     __syncthreads();
     if (traj >= ntraj) break;
-    const long long src = in_idx ? __ldg(in_idx + traj) : traj;
+    long long src = in_idx ? __ldg(in_idx + traj) : traj;
+    size_t toff = 0;
+    if (G.n_part > 0) {   // trajectory = experiment e + n_exp * particle p: this particle's weights and seed columns
+      const long long pp = traj / G.n_exp;
+      src = traj - pp * G.n_exp;
+      const double* pwp = G.pw + pp * G.pw_stride;
+      load_weights(pwp, pwp + (size_t)nin * KW_MAXN, pwp + (size_t)nin * KW_MAXN + nr,
+                   has_obs ? pwp + (size_t)nin * KW_MAXN + nr + (size_t)ns * nr : nullptr);
+      srow = G.seed_rows + pp * G.seed_stride;
+      if (active) ds = G.desc[pp * cols + tid];
+    }
+    if (G.tab_per_exp) toff = (size_t)src * P.n_tab;
 
     double u = (w0 && lane < n) ? __ldg(u0 + src * n + lane) : 0.0;
     const double u_init = u;
@@ -333,10 +405,10 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     WideAux a0, as;
     if (active) for (int i = 0; i < n; ++i) slot(SL_U)[i * cs] = 0.0;   // sensitivities of u0 are zero
     // ---- f0 on all columns ----
-    if (w0) { KS(0) = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t0, u, as, tab_seg); a0 = as; }
+    if (w0) { KS(0) = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t0, u, as, tab_seg, toff); a0 = as; }
     ++n_rhs;
     __syncthreads();
-    if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, G.seed_rows, cols, tid, ds, slot(SL_U), CKS(0), nullptr, cs);
+    if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(0), nullptr, cs);
     for (int q = tid; q < (int)(sizeof(GenPoint) / sizeof(double)); q += blockDim.x)
       reinterpret_cast<double*>(&S.base)[q] = reinterpret_cast<const double*>(&S.cur)[q];
     __syncthreads();
@@ -360,10 +432,10 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
       // f(u0 + dt0 f0, t0 + dt0) on all columns: Y = U + dt0 K0
       if (active) for (int i = 0; i < n; ++i) slot(SL_Y)[i * cs] = fma(dt0, CKS(0)[i * cs], slot(SL_U)[i * cs]);
       double f1p = 0.0;
-      if (w0) f1p = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t0 + dt0, fma(dt0, KS(0), u), as, tab_seg);
+      if (w0) f1p = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t0 + dt0, fma(dt0, KS(0), u), as, tab_seg, toff);
       ++n_rhs;
       __syncthreads();
-      if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, G.seed_rows, cols, tid, ds, slot(SL_Y), CKS(1), nullptr, cs);
+      if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_Y), CKS(1), nullptr, cs);
       if (incl) row_sums(n, [&](int i) { const double v = CKS(1)[i * cs] - CKS(0)[i * cs]; return v * v; });
       else __syncthreads();
       if (w0) {
@@ -383,8 +455,35 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23);
     long long iter = 0;
 
-    // one save point: value column yv (lane-distributed in warp 0), this thread's column value via colval(i)
-    auto emit_save = [&](double yv, auto colval) {
+    // one save point at time tsv: value column yv (lane-distributed in warp 0), this thread's column value via colval(i)
+    auto loss_term = [&](double d, double yc, double iys, double& term, double& g) {
+      if (G.loss_kind == CRNN_LOSS_MAE_SCALED) { const double diff = d * iys - yc * iys; term = fabs(diff); g = signbit(diff) ? iys : -iys; }
+      else if (G.loss_kind == CRNN_LOSS_MSE) { const double diff = d * iys - yc * iys; term = diff * diff; g = -2.0 * diff * iys; }
+      else { const double diff = lean_log(clampd(d, P.pred_lo, P.pred_hi)) - lean_log(yc); term = fabs(diff); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
+    };
+    auto emit_save = [&](double tsv, double yv, auto colval) {
+      if (has_obs) {
+        // observable post-map: y = sum_j w_obs[j] r_j(u(tsv), tsv) - one more value-path evaluation at the saved state
+        if (w0) {
+          WideAux ax; int sg = tab_seg;
+          (void)gen_rhs<F2>(P, sb, S.tmp, lane, my_mw, tsv, yv, ax, sg, toff);
+          const double y = wsum(lane < nr ? S.wobs[lane] * S.tmp.r[lane] : 0.0);
+          if (lane == 0) {
+            const double yc = clampd(y, P.pred_lo, P.pred_hi);
+            const bool inside = (y >= P.pred_lo) && (y <= P.pred_hi);
+            const size_t off = (size_t)P.n_obs * isave;
+            if (pred) pred[pbase + off] = yc;
+            double term, g;
+            loss_term(__ldg(datat + off), yc, __ldg(G.inv_ys), term, g);
+            loss_acc += term;
+            S.g[0] = inside ? g : 0.0;
+          }
+        }
+        __syncthreads();
+        if (active) Gc = fma(S.g[0], col_obs<F2>(P, sb, S.tmp, S.wobs, srow, cols, tid, ds, colval), Gc);
+        __syncthreads();
+        return;
+      }
       if (w0) {
         double g = 0.0;
         if (my_obs >= 0) {
@@ -392,11 +491,9 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           const bool inside = (yv >= P.pred_lo) && (yv <= P.pred_hi);
           const size_t off = (size_t)my_obs + (size_t)P.n_obs * isave;
           if (pred) pred[pbase + off] = yc;
-          const double d = __ldg(datat + off);
-          double diff;
-          if (G.loss_kind == CRNN_LOSS_MAE_SCALED) { diff = d * my_iys - yc * my_iys; g = signbit(diff) ? my_iys : -my_iys; }
-          else { diff = lean_log(clampd(d, P.pred_lo, P.pred_hi)) - lean_log(yc); g = (signbit(diff) ? 1.0 : -1.0) / yc; }
-          loss_acc += fabs(diff);
+          double term;
+          loss_term(__ldg(datat + off), yc, my_iys, term, g);
+          loss_acc += term;
           if (!inside) g = 0.0;
         }
         S.g[lane] = g;
@@ -407,7 +504,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     };
 
     while (isave < nsave && __ldg(P.saveat + isave) <= t0) {
-      emit_save(u, [&](int i) { return slot(SL_U)[i * cs]; });
+      emit_save(__ldg(P.saveat + isave), u, [&](int i) { return slot(SL_U)[i * cs]; });
       ++isave;
     }
 
@@ -421,10 +518,10 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
         else if (rosen && sw_count < -3) { dt = dt / 2.0; want = false; }
         if (want != rosen) {
           rosen = want;   // initialize!(integrator, new cache): fsalfirst = f(uprev) on all columns
-          if (w0) { KS(0) = gen_rhs<F2>(P, sb, S.base, lane, my_mw, t, u, a0, tab_seg); }
+          if (w0) { KS(0) = gen_rhs<F2>(P, sb, S.base, lane, my_mw, t, u, a0, tab_seg, toff); }
           ++n_rhs;
           __syncthreads();
-          if (active) col_apply<F2, false>(P, sb, S.base, S.d2, G.seed_rows, cols, tid, ds, slot(SL_U), CKS(0), nullptr, cs);
+          if (active) col_apply<F2, false>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(0), nullptr, cs);
           __syncthreads();
         }
       }
@@ -460,11 +557,11 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
             const double y = fma(dt, acc, u);
             if (s == 5) g6 = y;
             un = y;
-            KS(s) = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + tsc::C[s] * dt, y, as, tab_seg);
+            KS(s) = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + tsc::C[s] * dt, y, as, tab_seg, toff);
           }
           ++n_rhs;
           __syncthreads();
-          if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, G.seed_rows, cols, tid, ds, slot(SL_Y), CKS(s), nullptr, cs);
+          if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_Y), CKS(s), nullptr, cs);
           __syncthreads();
         }
         if (w0) {
@@ -495,7 +592,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
         const double g = d * dt;
         double k1 = 0.0, k2 = 0.0, k3 = 0.0, f1 = 0.0, f2 = 0.0, dTv = 0.0;
         if (w0) {
-          dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, S.base.r, a0, tab_seg);
+          dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, S.base.r, a0, tab_seg, toff);
           const double eig = wide_build_lu<F2>(P, sb, ww, lane, S.base.r, a0, g);
           if (autosw && lane == 0) S.bcast[1] = eig;
           k1 = wide_lusolve(ww, lane, ns, fma(g, dTv, KS(0)));
@@ -505,13 +602,13 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
         __syncthreads();
         if (autosw) eigen_est = S.bcast[1];
         if (active) {
-          col_apply<F2, true>(P, sb, S.base, S.d2, G.seed_rows, cols, tid, ds, slot(SL_U), CKS(1), CKS(0), cs);
+          col_apply<F2, true>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(1), CKS(0), cs);
           for (int i = 0; i < n; ++i) CKS(1)[i * cs] = fma(g, CKS(1)[i * cs], CKS(0)[i * cs]);
           col_lusolve(ww, ns, CKS(1), cs);
           for (int i = 0; i < n; ++i) slot(SL_Y)[i * cs] = fma(0.5 * dt, CKS(1)[i * cs], slot(SL_U)[i * cs]);
         }
         __syncthreads();   // columns are done with d2 (k1)
-        if (w0) f1 = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as, tab_seg);
+        if (w0) f1 = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as, tab_seg, toff);
         ++n_rhs;
         __syncthreads();
         if (w0) {
@@ -519,10 +616,10 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           k2 = k2v + k1;
           gen_dir2<F2>(P, sb, S.base, S.d2, lane, k2v, 0.0);         // (k2 - k1, 0)
         }
-        if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, G.seed_rows, cols, tid, ds, slot(SL_Y), CKS(4), nullptr, cs);
+        if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_Y), CKS(4), nullptr, cs);
         __syncthreads();
         if (active) {
-          col_apply<F2, true>(P, sb, S.base, S.d2, G.seed_rows, cols, tid, ds, slot(SL_U), CKS(2), CKS(0), cs);
+          col_apply<F2, true>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(2), CKS(0), cs);
           for (int i = 0; i < n; ++i) CKS(2)[i * cs] = fma(g, CKS(2)[i * cs], CKS(4)[i * cs] - CKS(1)[i * cs]);
           col_lusolve(ww, ns, CKS(2), cs);
           for (int i = 0; i < n; ++i) {
@@ -532,7 +629,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           }
         }
         __syncthreads();
-        if (w0) { un = fma(dt, k2, u); f2 = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + dt, un, as, tab_seg); }
+        if (w0) { un = fma(dt, k2, u); f2 = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t + dt, un, as, tab_seg, toff); }
         ++n_rhs;
         __syncthreads();
         if (w0) {
@@ -541,10 +638,10 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           e = dt / 6.0 * (k1 - 2.0 * k2 + k3);
           KS(1) = k1; KS(2) = k2; KS(3) = k3; KS(4) = f1; KS(5) = f2;
         }
-        if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, G.seed_rows, cols, tid, ds, slot(SL_Y), CKS(5), nullptr, cs);
+        if (active) col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_Y), CKS(5), nullptr, cs);
         __syncthreads();
         if (active) {
-          col_apply<F2, true>(P, sb, S.base, S.d2, G.seed_rows, cols, tid, ds, slot(SL_U), CKS(3), CKS(0), cs);
+          col_apply<F2, true>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(3), CKS(0), cs);
           for (int i = 0; i < n; ++i) {
             const double rhs = CKS(5)[i * cs] - e32 * (CKS(2)[i * cs] - CKS(4)[i * cs]) - 2.0 * (CKS(1)[i * cs] - CKS(0)[i * cs]);
             CKS(3)[i * cs] = fma(g, CKS(3)[i * cs], rhs);
@@ -600,7 +697,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           const double tsv = __ldg(P.saveat + isave);
           if (!(tsv <= t)) break;
           if (tsv == t) {
-            emit_save(un, [&](int i) { return slot(SL_Y)[i * cs]; });
+            emit_save(tsv, un, [&](int i) { return slot(SL_Y)[i * cs]; });
           } else {
             const double th = (tsv - tprev) / dt;
             if (!rosen) {
@@ -614,7 +711,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
                 for (int s = 1; s < 7; ++s) acc = fma(bs[s], KS(s), acc);
                 yv = fma(dt, acc, u);
               }
-              emit_save(yv, [&](int i) {
+              emit_save(tsv, yv, [&](int i) {
                 double acc = bs[0] * CKS(0)[i * cs];
 #pragma unroll
                 for (int s = 1; s < 7; ++s) acc = fma(bs[s], CKS(s)[i * cs], acc);
@@ -624,7 +721,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
               const double d = 1.0 / (2.0 + 1.4142135623730951);
               const double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
               const double yv = w0 ? u + dt * (c1 * KS(1) + c2 * KS(2)) : 0.0;
-              emit_save(yv, [&](int i) { return slot(SL_U)[i * cs] + dt * (c1 * CKS(1)[i * cs] + c2 * CKS(2)[i * cs]); });
+              emit_save(tsv, yv, [&](int i) { return slot(SL_U)[i * cs] + dt * (c1 * CKS(1)[i * cs] + c2 * CKS(2)[i * cs]); });
             }
           }
           ++isave;
@@ -650,8 +747,8 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     const double cnt = (double)P.n_obs * (double)isave;
     if (w0) {
       const double ltot = wsum(loss_acc);
-      if (pred && my_obs >= 0)
-        for (int ks = isave; ks < P.n_save; ++ks) pred[pbase + my_obs + (size_t)P.n_obs * ks] = 0.0;
+      if (pred && (has_obs ? lane == 0 : my_obs >= 0))
+        for (int ks = isave; ks < P.n_save; ++ks) pred[pbase + (has_obs ? 0 : my_obs) + (size_t)P.n_obs * ks] = 0.0;
       if (lane == 0) {
         loss[traj] = isave > 0 ? ltot / cnt : __longlong_as_double(0x7ff8000000000000LL);
         if (n_saved) n_saved[traj] = isave;

@@ -40,7 +40,8 @@ struct TabVal { double T, P, Td, Pd; };
 // Interpolations.LinearInterpolation(tab_t, v)(t) and its slope; segment = last one whose left knot is <= t.
 // `seg` is the caller's hint (the segment of its previous lookup): stage times move monotonically inside a step, so the
 // hint nearly always holds and the six dependent loads of the binary search are skipped.
-__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t, int& seg) {
+// `toff`: offset of this trajectory's T / P tables (per-experiment temperature programmes; 0 = the model's own).
+__device__ __forceinline__ TabVal wide_tab(const WideP& P, double t, int& seg, size_t toff = 0) {
   int lo = seg;
   double ta = __ldg(P.tab_t + lo), tb = __ldg(P.tab_t + lo + 1);
   if (!(ta <= t && (t < tb || lo == P.n_tab - 2))) {
@@ -54,8 +55,8 @@ __device__ __forceinline__ TabVal wide_tab(const WideP& P, double t, int& seg) {
     seg = lo;
   }
   const double h = tb - ta, w = (t - ta) / h;
-  const double T0 = __ldg(P.tab_T + lo), T1 = __ldg(P.tab_T + lo + 1);
-  const double P0 = __ldg(P.tab_P + lo), P1 = __ldg(P.tab_P + lo + 1);
+  const double T0 = __ldg(P.tab_T + toff + lo), T1 = __ldg(P.tab_T + toff + lo + 1);
+  const double P0 = __ldg(P.tab_P + toff + lo), P1 = __ldg(P.tab_P + toff + lo + 1);
   TabVal v;
   v.T = T0 + w * (T1 - T0); v.P = P0 + w * (P1 - P0);
   v.Td = (T1 - T0) / h; v.Pd = (P1 - P0) / h;
@@ -121,17 +122,18 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   double xi = 0.0, rho = 1.0;
   a.dx = 0.0; a.rr = 0.0; a.chiC = 0.0; a.inv_rho = 1.0;
   if (F2) {
+    const bool dens = (P.kind == CRNN_RHS_F2_MASSFRAC_TP);   // F5 (Cathode/src/network.jl:68-80): the same inputs, no density map
     const TabVal tv = wide_tab(P, t, seg);
     double Y = 1.0, chi = 0.0, ymw = 0.0;
-    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = Y / mw; }
-    const double S = wsum(ymw);
-    rho = tv.P / (kGasRu * tv.T * S);
+    if (isp) { Y = clampd(y, P.lb, P.ub); chi = (y >= P.lb && y <= P.ub) ? 1.0 : 0.0; ymw = dens ? Y / mw : 0.0; }
+    const double S = dens ? wsum(ymw) : 1.0;
+    rho = dens ? tv.P / (kGasRu * tv.T * S) : 1.0;
     if (isp) {
-      const double C = rho * ymw * 1e3;
+      const double C = dens ? rho * ymw * 1e3 : Y;
       a.chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
       xi = lean_log(clampd(C, P.lb, P.ub));
       a.dx = a.chiC * chi / Y;
-      a.rr = -chi / (mw * S);
+      a.rr = dens ? -chi / (mw * S) : 0.0;
     } else if (lane == ns) {
       xi = -1.0 / P.gas_R / tv.T;
     } else if (lane == ns + 1) {
@@ -168,11 +170,11 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
 // df/dt at fixed u from the by-products of the evaluation at (u, t) (r in rsrc): F2 only, 0 otherwise
 template <bool F2, class WW>
 __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBlock& sb, WW& ww, int lane, double t,
-                                                  const double* rsrc, const WideAux& a, int& seg) {
+                                                  const double* rsrc, const WideAux& a, int& seg, size_t toff = 0) {
   if (!F2) return 0.0;
   const int ns = P.ns, nr = P.nr;
-  const TabVal tv = wide_tab(P, t, seg);
-  const double rr = tv.Pd / tv.P - tv.Td / tv.T;
+  const TabVal tv = wide_tab(P, t, seg, toff);
+  const double rr = (P.kind == CRNN_RHS_F2_MASSFRAC_TP) ? tv.Pd / tv.P - tv.Td / tv.T : 0.0;  // F5: no density map
   __syncwarp();
   ww.bchi[lane] = a.chiC;
   __syncwarp();

@@ -261,6 +261,44 @@ class Engine:
         return dict(loss=loss, grad_sum=grad, pred=pred, n_saved=n_saved, retcode=ret, stats=stats)
 
 
+def _particles(self, model: CRNNModel, opts: SolveOpts, weights, seeds, u0, data, yscale, loss_kind=_abi.LOSS_MSE,
+               tab_T=None, tab_P=None, n_save_used=None, want_stats=False):
+    """`crnn_loss_grad_particles`: P parameter sets ("particles") x E experiments in one launch
+    (Cathode_NCM333_UQ/src_333/network.jl:222-260).  weights [P, n_w] (flat [vec(w_in); w_b; vec(w_out); (w_obs)] per
+    particle), seeds [P, n_w, np], u0 [E, n_state], data [E, n_save, n_obs], tab_T / tab_P [E, n_tab] or None.
+    -> dict(loss [P, E], grad [P, np], n_saved, retcode [P, E], stats)."""
+    n = model.n_state
+    cm, k1 = model.to_c()
+    co, k2 = opts.to_c(n, False)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    P, nw = weights.shape
+    if nw != model.n_w:
+        raise ValueError(f"weights must be [P, n_w={model.n_w}]")
+    seeds = np.asarray(seeds, dtype=np.float64)
+    if seeds.ndim != 3 or seeds.shape[0] != P or seeds.shape[1] != nw:
+        raise ValueError("seeds must be [P, n_w, np]")
+    n_p = seeds.shape[2]
+    seeds_f = np.ascontiguousarray(np.transpose(seeds, (0, 2, 1)))       # per particle [np][n_w] = column-major [n_w, np]
+    u0 = self._host(u0, np.float64, None, "u0")
+    E = u0.shape[0]
+    data = self._host(data, np.float64, (E, opts.n_save, opts.n_obs(n)), "data")
+    ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (opts.n_obs(n),), "yscale")
+    tT = None if tab_T is None else self._host(tab_T, np.float64, (E, model.tab_t.size), "tab_T")
+    tP = None if tab_P is None else self._host(tab_P, np.float64, (E, model.tab_t.size), "tab_P")
+    nsu = None if n_save_used is None else self._host(n_save_used, np.int32, (E,), "n_save_used")
+    loss = np.empty((P, E)); grad = np.empty((P, n_p))
+    n_saved = np.empty((P, E), dtype=np.int32); ret = np.empty((P, E), dtype=np.int32)
+    stats = np.empty((P, E), dtype=STATS_DTYPE) if want_stats else None
+    hp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    self._check(self._lib.crnn_loss_grad_particles(
+        self._h, C.byref(cm), C.byref(co), hp(weights), hp(seeds_f), n_p, P, hp(u0), E, hp(nsu), hp(data), hp(tT), hp(tP),
+        hp(ys), int(loss_kind), hp(loss), hp(grad), hp(n_saved), hp(ret), hp(stats)))
+    return dict(loss=loss, grad=grad, n_saved=n_saved, retcode=ret, stats=stats)
+
+
+Engine.loss_grad_particles = _particles
+
+
 def stats_from_torch(stats_u8) -> np.ndarray:
     """uint8 [N, 32] CUDA tensor of crnn_stats -> numpy structured array."""
     return stats_u8.cpu().numpy().view(STATS_DTYPE).reshape(-1)

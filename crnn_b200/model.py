@@ -33,6 +33,8 @@ class CRNNModel:
     tab_t: np.ndarray | None = None
     tab_T: np.ndarray | None = None
     tab_P: np.ndarray | None = None
+    # observable post-map: y = sum_j w_obs[j] r_j (heat release, Cathode/src/network.jl:82-91,121); None: rows of u
+    w_obs: np.ndarray | None = None
 
     def __post_init__(self):
         self.w_in = np.asarray(self.w_in, dtype=np.float64)
@@ -50,6 +52,20 @@ class CRNNModel:
             raise ValueError("F1 needs n_in == n_species + 1 (Arrhenius row)")
         if self.out_scale is not None and self.out_scale.shape[0] != ns:
             raise ValueError("out_scale must have n_species entries")
+        if self.w_obs is not None:
+            self.w_obs = np.ascontiguousarray(self.w_obs, dtype=np.float64).reshape(-1)
+            if self.w_obs.shape[0] != nr:
+                raise ValueError("w_obs must have n_reac entries")
+        if self.rhs_kind == _abi.RHS_F5:
+            if n_in != ns + 2:
+                raise ValueError("F5 needs n_in == n_species + 2 (Arrhenius and log T rows)")
+            if self.tab_t is None or self.tab_T is None:
+                raise ValueError("F5 needs the tab_t / tab_T temperature programme")
+            self.tab_t, self.tab_T = (np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (self.tab_t, self.tab_T))
+            self.tab_P = np.ones_like(self.tab_T)
+            self.mw = np.ones(ns)
+            if not (self.tab_t.size == self.tab_T.size >= 2) or np.any(np.diff(self.tab_t) <= 0):
+                raise ValueError("F5: tab_t / tab_T must have equal length >= 2, tab_t strictly ascending")
         if self.rhs_kind == _abi.RHS_F2:
             if n_in != ns + 2:
                 raise ValueError("F2 needs n_in == n_species + 2 (Arrhenius and log T rows)")
@@ -81,11 +97,14 @@ class CRNNModel:
 
     @property
     def n_w(self) -> int:
-        return self.n_reac * (self.n_in + 1 + self.n_species)
+        return self.n_reac * (self.n_in + 1 + self.n_species) + (self.n_reac if self.w_obs is not None else 0)
 
     def flat_weights(self) -> np.ndarray:
-        """[vec(w_in); w_b; vec(w_out)] column-major: the row order of dW_dp."""
-        return np.concatenate([self.w_in.reshape(-1, order="F"), self.w_b, self.w_out.reshape(-1, order="F")])
+        """[vec(w_in); w_b; vec(w_out); (w_obs)] column-major: the row order of dW_dp."""
+        parts = [self.w_in.reshape(-1, order="F"), self.w_b, self.w_out.reshape(-1, order="F")]
+        if self.w_obs is not None:
+            parts.append(self.w_obs)
+        return np.concatenate(parts)
 
     def to_c(self):
         """Returns (CModel, keepalive)."""
@@ -101,7 +120,10 @@ class CRNNModel:
         m.lb, m.ub, m.gas_R = float(self.lb), float(self.ub), float(self.gas_R)
         m.w_in, m.w_b, m.w_out = dptr(keep[0]), dptr(keep[1]), dptr(keep[2])
         m.out_scale = dptr(keep[3])
-        if self.rhs_kind == _abi.RHS_F2:
+        if self.w_obs is not None:
+            keep.append(self.w_obs)
+            m.w_obs = dptr(self.w_obs)
+        if self.rhs_kind in (_abi.RHS_F2, _abi.RHS_F5):
             keep += [self.mw, self.tab_t, self.tab_T, self.tab_P]
             m.n_tab = int(self.tab_t.size)
             m.mw, m.tab_t, m.tab_T, m.tab_P = dptr(self.mw), dptr(self.tab_t), dptr(self.tab_T), dptr(self.tab_P)

@@ -62,10 +62,15 @@ enum crnn_status {
 enum crnn_rhs_kind {
   CRNN_RHS_F0 = 0, /* du = s .* W_out*exp(W_in'*log(clamp(u,lb,ub)) + b): case1.jl:80-83, case3.jl:162-166, rober_crnn.jl:113-116 */
   CRNN_RHS_F1_ARRH_TSTATE = 1, /* state [X;T], x=[log clamp X; -1/(R T)], dT/dt=0: case2.jl:113-118 */
-  CRNN_RHS_F2_MASSFRAC_TP = 2  /* mass fractions under tabulated T(t), P(t) (non-autonomous):
+  CRNN_RHS_F2_MASSFRAC_TP = 2, /* mass fractions under tabulated T(t), P(t) (non-autonomous):
                                   Y=clamp(u,lb,ub), rho=P/(8314.46261815324 T sum(Y/MW)), C=rho Y/MW 1e3,
                                   x=[log clamp(C,lb,ub); -1/(R T); log T], du = W_out*exp(W_in'x+b) .* MW / rho .* out_scale:
                                   HyChem/crnn_pyrolysis_mass.jl:107-114,121-131 */
+  CRNN_RHS_F5_TRAMP = 3        /* species under a tabulated temperature programme T(t), no density map:
+                                  x=[log clamp(u,lb,ub); -1/(gas_R T(t)); log T(t)], du = W_out*exp(W_in'x+b) .* out_scale:
+                                  Cathode/src/network.jl:68-80 and Cathode_NCM333_UQ/src_333/network.jl:153-168 (there
+                                  w_in = [diag(reaction orders); (Ea 1e5)'; b'], w_b = ln A, gas_R = 8.314, T = T0 + beta/60 t
+                                  as a two-knot table); n_in = n_species + 2, tab_P unused */
 };
 
 enum crnn_alg {
@@ -88,13 +93,15 @@ enum crnn_sens_mode {
 
 enum crnn_loss_kind {
   CRNN_LOSS_MAE_SCALED = 0, /* mean|d/ys - clamp(pred)/ys|: case2.jl:132-137, rober_crnn.jl:139-144 */
-  CRNN_LOSS_MAE_LOG = 1     /* mean|log clamp d - log clamp pred|: case3.jl:183-190 */
+  CRNN_LOSS_MAE_LOG = 1,    /* mean|log clamp d - log clamp pred|: case3.jl:183-190 */
+  CRNN_LOSS_MSE = 2         /* mean (d - pred)^2 / ys^2: Cathode_NCM333_UQ/src_333/network.jl:262-275 */
 };
 
 /* Per-trajectory return codes (SciMLBase.ReturnCode values). */
 enum crnn_retcode {
   CRNN_RET_DEFAULT = 0,
   CRNN_RET_SUCCESS = 1,
+  CRNN_RET_TERMINATED = 2,
   CRNN_RET_DTNAN = 3,
   CRNN_RET_MAXITERS = 4,
   CRNN_RET_DTLESSTHANMIN = 5,
@@ -105,7 +112,7 @@ enum crnn_retcode {
 typedef struct crnn_model {
   int32_t n_state;   /* length of u (F1: n_species + 1) */
   int32_t n_species; /* rows of w_out */
-  int32_t n_in;      /* rows of w_in (== n_state for F0 and F1, n_species + 2 for F2) */
+  int32_t n_in;      /* rows of w_in (== n_state for F0 and F1, n_species + 2 for F2 and F5) */
   int32_t n_reac;    /* columns of w_in / w_out */
   int32_t rhs_kind;  /* crnn_rhs_kind */
   int32_t n_tab;     /* F2 only: length of tab_t / tab_T / tab_P (>= 2) */
@@ -121,6 +128,11 @@ typedef struct crnn_model {
   const double* tab_t;     /* [n_tab] */
   const double* tab_T;     /* [n_tab] */
   const double* tab_P;     /* [n_tab] */
+  /* Observable post-map (NULL: the observed quantities are rows of u).  With w_obs the ONE observed quantity is
+   * y = sum_j w_obs[j] r_j(u(t), t), r = exp(W_in'x + b): the heat release HRR_getter(ts, sol) * w_delH of
+   * Cathode/src/network.jl:82-91,121 (n_obs must be 1, obs_idx is ignored).  The seed matrix then carries n_reac extra
+   * rows, ordered [vec(w_in); w_b; vec(w_out); w_obs]. */
+  const double* w_obs;     /* [n_reac] or NULL */
 } crnn_model;
 
 typedef struct crnn_opts {
@@ -248,6 +260,23 @@ int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts*
                            const crnn_dataset* ds, const int64_t* idx, int64_t n_idx, const int32_t* n_save_used,
                            const double* yscale, int32_t loss_kind, double* loss_sum, double* grad_sum, double* loss,
                            int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
+
+/* Parameter-batched loss + gradient ("particles"): P parameter sets x E experiments in ONE launch, trajectory (p, e)
+ * integrating experiment e with the weights of particle p - the loop `for j = 1:size(p)[1] ... ForwardDiff.gradient`
+ * of Cathode_NCM333_UQ/src_333/network.jl:222-260 (100 SVGD particles x 5 data sets, sequential there).
+ *   m         dimensions, rhs_kind, clamps, gas_R, out_scale, mw, tab_t of the model; its weight pointers are ignored
+ *   weights   [n_w, P] col-major: [vec(w_in); w_b; vec(w_out); (w_obs)] of every particle (n_w incl. w_obs when m->w_obs != NULL)
+ *   dW_dp     [n_w, np, P]: each particle's seed matrix (its own Jacobian of p2vec)
+ *   u0        [n_state, E], data [n_obs, n_save, E], n_save_used [E] or NULL
+ *   tab_T, tab_P  [n_tab, E] per-experiment tables (F2 / F5; NULL: the model's own tables for every experiment)
+ *   loss      [E, P] (experiment fastest), grad [np, P] = sum over e of d loss(e, p) / d p_p,
+ *   n_saved, retcode, stats: [E, P] or NULL.  All pointers are HOST memory.
+ * Forward mode only (sens_mode FORWARD; Tsit5, Rosenbrock23, AutoTsit5(Rosenbrock23); structured seed columns). */
+int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* weights,
+                             const double* dW_dp, int32_t np, int32_t P, const double* u0, int32_t E,
+                             const int32_t* n_save_used, const double* data, const double* tab_T, const double* tab_P,
+                             const double* yscale, int32_t loss_kind, double* loss, double* grad, int32_t* n_saved,
+                             int32_t* retcode, crnn_stats* stats);
 
 /* Diagnostic: evaluates the engine's device log / exp / pow (crnn_b200/csrc/lean_math.h) elementwise on host arrays,
  * op 0: y = log(x), 1: exp(x), 2: x^x2, 3: log10(x), 4: 10^x.  The same header compiles for the host; the tests

@@ -67,6 +67,7 @@ typedef struct {
 } ctx_t;
 
 #define GAS_RU 8.31446261815324e3 /* HyChem/crnn_pyrolysis_mass.jl:108 */
+#define IS_TAB(m) ((m)->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || (m)->rhs_kind == CRNN_RHS_F5_TRAMP) /* inputs from T(t) tables */
 
 /* Interpolations.LinearInterpolation(tab_t, tab_v)(t) and its slope (HyChem/crnn_pyrolysis_mass.jl:103-104).
  * The segment is the last one whose left knot is <= t (the right-most segment at t == tab_t[end]). */
@@ -75,9 +76,10 @@ static void tab_lookup(const crnn_model* m, double t, double* T, double* P, doub
   while (hi - lo > 1) { int mid = (lo + hi) / 2; if (m->tab_t[mid] <= t) lo = mid; else hi = mid; }
   double h = m->tab_t[lo + 1] - m->tab_t[lo], w = (t - m->tab_t[lo]) / h;
   *T = m->tab_T[lo] + w * (m->tab_T[lo + 1] - m->tab_T[lo]);
+  if (!m->tab_P) { *P = 1.0; *Pdot = 0.0; } else {
   *P = m->tab_P[lo] + w * (m->tab_P[lo + 1] - m->tab_P[lo]);
+  *Pdot = (m->tab_P[lo + 1] - m->tab_P[lo]) / h; }
   *Tdot = (m->tab_T[lo + 1] - m->tab_T[lo]) / h;
-  *Pdot = (m->tab_P[lo + 1] - m->tab_P[lo]) / h;
 }
 
 typedef struct {
@@ -103,18 +105,22 @@ static inline double clampd(double v, double lo, double hi) {
 static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs_cache* k) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) {
+  if (IS_TAB(m)) {
+    /* F2: HyChem mass fractions with the density map.  F5 (Cathode/src/network.jl:68-80): the same inputs
+     * [log clamp(u); -1/(R T(t)); log T(t)] without it (C = Y, rho = 1). */
+    const int dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
     tab_lookup(m, t, &k->T, &k->P, &k->Tdot, &k->Pdot);
     double S = 0.0;
     for (int i = 0; i < ns; ++i) {
       k->Y[i] = clampd(u[i], m->lb, m->ub);               /* Y = clamp.(u, lb, 10), :124 */
       k->chi[i] = (u[i] >= m->lb && u[i] <= m->ub) ? 1.0 : 0.0;
-      S += k->Y[i] / m->mw[i];
+      if (dens) S += k->Y[i] / m->mw[i];
     }
-    k->S = S;
-    k->rho = k->P / (GAS_RU * k->T * S);                   /* Y2density, :107-109 */
+    k->S = dens ? S : 1.0;
+    k->rho = dens ? k->P / (GAS_RU * k->T * S) : 1.0;      /* Y2density, :107-109 */
+    if (!dens) { k->Pdot = 0.0; k->P = 1.0; }
     for (int i = 0; i < ns; ++i) {
-      double C = k->rho * (k->Y[i] / m->mw[i]) * 1e3;      /* Y2C, :112-114 */
+      double C = dens ? k->rho * (k->Y[i] / m->mw[i]) * 1e3 : k->Y[i];      /* Y2C, :112-114 */
       double Cc = clampd(C, m->lb, m->ub);
       k->chiC[i] = (C >= m->lb && C <= m->ub) ? 1.0 : 0.0;
       k->x[i] = m_log(Cc);
@@ -147,10 +153,8 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
   for (int i = 0; i < ns; ++i) {
     double s = 0.0;
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * k->r[j];
-    if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) {
-      k->wdot[i] = s;
-      s = s * m->mw[i] / k->rho;                          /* wdot * l_MW / density, :130 */
-    }
+    k->wdot[i] = s;
+    if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) s = s * m->mw[i] / k->rho;   /* wdot * l_MW / density, :130 */
     du[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) du[i] = 0.0; /* vcat(..., 0.f0), case2.jl:117 */
@@ -158,20 +162,18 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
 
 /* F2: the density couples every species: d log(rho) = -sum_l chi_l du_l / MW_l / S. */
 static double f2_dlogrho(const ctx_t* c, const rhs_cache* k, const double* S) {
+  if (c->m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP) return 0.0; /* F5: no density */
   double sd = 0.0;
   for (int l = 0; l < c->ns; ++l) sd += k->chi[l] * S[l] / c->m->mw[l];
   return -sd / k->S;
 }
 
-/* Directional derivative of f along (S for u, seed column for the weights):
- * what ForwardDiff duals compute when pushed through crnn (SURVEY App. B.3). */
-static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
-                         const double* sd /* seed column or NULL */, double* dS) {
+/* Directional derivative of the reaction rates r = exp(W_in'x + b) along (S for u, seed column for the weights). */
+static void rates_sens(const ctx_t* c, const rhs_cache* k, const double* S, const double* sd, double* zq) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int f2 = IS_TAB(m);
   const double rr = f2 ? f2_dlogrho(c, k, S) : 0.0;
-  double zq[MAXR];
   for (int j = 0; j < nr; ++j) {
     double zd = 0.0;
     if (f2) { for (int i = 0; i < ns; ++i) zd += m->w_in[i + nin * j] * (k->chiC[i] * rr + S[i] * k->dx[i]); }
@@ -182,12 +184,24 @@ static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
     }
     zq[j] = k->r[j] * zd;
   }
+}
+
+/* Directional derivative of f along (S for u, seed column for the weights):
+ * what ForwardDiff duals compute when pushed through crnn (SURVEY App. B.3). */
+static void rhs_sens_col(const ctx_t* c, const rhs_cache* k, const double* S,
+                         const double* sd /* seed column or NULL */, double* dS) {
+  const crnn_model* m = c->m;
+  int ns = c->ns, nin = c->nin, nr = c->nr;
+  const int f2 = IS_TAB(m), dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const double rr = f2 ? f2_dlogrho(c, k, S) : 0.0;
+  double zq[MAXR];
+  rates_sens(c, k, S, sd, zq);
   for (int i = 0; i < ns; ++i) {
     double s = 0.0;
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * zq[j];
     if (sd)
       for (int j = 0; j < nr; ++j) s += sd[nin * nr + nr + i + ns * j] * k->r[j];
-    if (f2) s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
+    if (dens) s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
     dS[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) dS[i] = 0.0;
@@ -198,8 +212,9 @@ static void rhs_time_deriv(const ctx_t* c, const rhs_cache* k, double* dT) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
   for (int i = 0; i < c->n; ++i) dT[i] = 0.0;
-  if (m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP) return;
-  const double rr = k->Pdot / k->P - k->Tdot / k->T; /* d log(rho) / dt */
+  if (!IS_TAB(m)) return;
+  const int dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const double rr = dens ? k->Pdot / k->P - k->Tdot / k->T : 0.0; /* d log(rho) / dt */
   double zq[MAXR];
   for (int j = 0; j < nr; ++j) {
     double zd = 0.0;
@@ -211,7 +226,7 @@ static void rhs_time_deriv(const ctx_t* c, const rhs_cache* k, double* dT) {
   for (int i = 0; i < ns; ++i) {
     double s = 0.0;
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * zq[j];
-    s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
+    if (dens) s = (s - k->wdot[i] * rr) * m->mw[i] / k->rho;
     dT[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
 }
@@ -229,7 +244,7 @@ static void jac_value(const ctx_t* c, const rhs_cache* k, double* J) {
   const crnn_model* m = c->m;
   int n = c->n, ns = c->ns, nin = c->nin, nr = c->nr;
   memset(J, 0, sizeof(double) * n * n);
-  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) { /* column l = directional derivative along e_l (density coupling) */
+  if (IS_TAB(m)) { /* column l = directional derivative along e_l (density coupling) */
     double e[MAXN], col[MAXN];
     for (int l = 0; l < n; ++l) {
       memset(e, 0, sizeof(e)); e[l] = 1.0;
@@ -263,15 +278,17 @@ static void djac_vec(const ctx_t* c, const rhs_cache* k, const double* S, const 
                      const double* v, double tau, double* out) {
   const crnn_model* m = c->m;
   int ns = c->ns, nin = c->nin, nr = c->nr;
-  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int f2 = IS_TAB(m), dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
   double x1[MAXN + 2], x2[MAXN + 2], x12[MAXN + 2];
   double lr1 = 0.0, lr2 = 0.0, lr12 = 0.0;
   if (f2) {
     double s1 = 0.0, s2 = 0.0;
-    for (int l = 0; l < ns; ++l) { s1 += k->chi[l] * S[l] / m->mw[l]; if (v) s2 += k->chi[l] * v[l] / m->mw[l]; }
-    lr1 = -s1 / k->S;
-    lr2 = tau * (k->Pdot / k->P - k->Tdot / k->T) - s2 / k->S;
-    lr12 = s1 * s2 / (k->S * k->S);
+    if (dens) {
+      for (int l = 0; l < ns; ++l) { s1 += k->chi[l] * S[l] / m->mw[l]; if (v) s2 += k->chi[l] * v[l] / m->mw[l]; }
+      lr1 = -s1 / k->S;
+      lr2 = tau * (k->Pdot / k->P - k->Tdot / k->T) - s2 / k->S;
+      lr12 = s1 * s2 / (k->S * k->S);
+    }
     for (int i = 0; i < ns; ++i) {
       const double vi = v ? v[i] : 0.0;
       x1[i] = k->chiC[i] * (lr1 + k->chi[i] * S[i] / k->Y[i]);
@@ -307,7 +324,7 @@ static void djac_vec(const ctx_t* c, const rhs_cache* k, const double* S, const 
     if (sd)
       for (int j = 0; j < nr; ++j) w12 += sd[nin * nr + nr + i + ns * j] * r2[j];
     double s;
-    if (f2) {
+    if (dens) {
       double w1 = 0.0, w2 = 0.0;
       for (int j = 0; j < nr; ++j) { w1 += m->w_out[i + ns * j] * r1[j]; w2 += m->w_out[i + ns * j] * r2[j]; }
       if (sd) for (int j = 0; j < nr; ++j) w1 += sd[nin * nr + nr + i + ns * j] * k->r[j];
@@ -419,9 +436,52 @@ typedef struct {
   double* pred;         /* [n_obs, n_save] or NULL */
 } save_sink;
 
-static void emit_save(const ctx_t* c, save_sink* sk, int ksave, const double* Ys /* ncol x n */) {
+/* loss term and d loss / d yhat for one observed value.  kind 2: the mean squared error of
+ * Cathode_NCM333_UQ/src_333/network.jl:262-275. */
+static void loss_term(const crnn_opts* o, int loss_kind, double d, double yc, double ys, double* term, double* g) {
+  if (loss_kind == CRNN_LOSS_MAE_SCALED) {
+    const double diff = d / ys - yc / ys;
+    *term = fabs(diff); *g = (signbit(diff) ? 1.0 : -1.0) / ys;
+  } else if (loss_kind == CRNN_LOSS_MSE) {
+    const double diff = d / ys - yc / ys;
+    *term = diff * diff; *g = -2.0 * diff / ys;
+  } else {
+    const double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi);
+    const double diff = m_log(dc) - m_log(yc);
+    *term = fabs(diff); *g = (signbit(diff) ? 1.0 : -1.0) / yc;
+  }
+}
+
+static void emit_save(const ctx_t* c, save_sink* sk, int ksave, double ts, const double* Ys /* ncol x n */) {
   const crnn_opts* o = c->o;
   int n = c->n;
+  if (c->m->w_obs) {
+    /* observable post-map y = sum_j w_obs[j] r_j(u(ts), ts): heat release = HRR_getter(ts, sol) * w_delH
+     * (Cathode/src/network.jl:82-91,121); its dual part along each column by the chain rule */
+    const crnn_model* m = c->m;
+    rhs_cache kk; double du[MAXN], zq[MAXR];
+    rhs_value(c, ts, Ys, du, &kk);
+    double y = 0.0;
+    for (int j = 0; j < c->nr; ++j) y += m->w_obs[j] * kk.r[j];
+    double yc = clampd(y, o->pred_clamp_lo, o->pred_clamp_hi);
+    int inside = (y >= o->pred_clamp_lo) && (y <= o->pred_clamp_hi);
+    if (sk->pred) sk->pred[o->n_obs * ksave] = yc;
+    if (!sk->data) return;
+    double term, g;
+    loss_term(o, sk->loss_kind, sk->data[o->n_obs * ksave], yc, sk->yscale ? sk->yscale[0] : 1.0, &term, &g);
+    sk->loss += term;
+    if (sk->grad && inside) {
+      const int off_obs = c->nr * (c->nin + 1 + c->ns);
+      for (int col = 1; col < c->ncol; ++col) {
+        const double* sd = c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL;
+        rates_sens(c, &kk, Ys + col * n, sd, zq);
+        double dy = 0.0;
+        for (int j = 0; j < c->nr; ++j) dy += m->w_obs[j] * zq[j] + (sd ? sd[off_obs + j] * kk.r[j] : 0.0);
+        sk->grad[col - 1] += g * dy;
+      }
+    }
+    return;
+  }
   for (int q = 0; q < o->n_obs; ++q) {
     int i = o->obs_idx[q];
     double y = Ys[i];
@@ -429,17 +489,9 @@ static void emit_save(const ctx_t* c, save_sink* sk, int ksave, const double* Ys
     int inside = (y >= o->pred_clamp_lo) && (y <= o->pred_clamp_hi);
     if (sk->pred) sk->pred[q + o->n_obs * ksave] = yc;
     if (!sk->data) continue;
-    double d = sk->data[q + o->n_obs * ksave];
-    double diff, g;
-    if (sk->loss_kind == CRNN_LOSS_MAE_SCALED) {
-      diff = d / sk->yscale[q] - yc / sk->yscale[q];
-      g = (signbit(diff) ? 1.0 : -1.0) / sk->yscale[q];
-    } else {
-      double dc = clampd(d, o->pred_clamp_lo, o->pred_clamp_hi);
-      diff = m_log(dc) - m_log(yc);
-      g = (signbit(diff) ? 1.0 : -1.0) / yc;
-    }
-    sk->loss += fabs(diff);
+    double term, g;
+    loss_term(o, sk->loss_kind, sk->data[q + o->n_obs * ksave], yc, sk->yscale ? sk->yscale[q] : 1.0, &term, &g);
+    sk->loss += term;
     if (sk->grad && inside)
       for (int col = 1; col < c->ncol; ++col) sk->grad[col - 1] += g * Ys[col * n + i];
   }
@@ -566,7 +618,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
   kc0 = kc;
   dt = initial_dt(c, t0, U, K[0], dtmax, W2, &kc); res->st.n_rhs++;
   /* save_start: t0 is saved iff it is in saveat */
-  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
+  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, o->saveat[isave], U); ++isave; }
 
   while (t < tend) {
     ++iter;
@@ -693,7 +745,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       while (isave < nsave && o->saveat[isave] <= t) {
         double ts = o->saveat[isave];
         if (ts == t) {
-          emit_save(c, sk, isave, Un);
+          emit_save(c, sk, isave, ts, Un);
         } else {
           double th = (ts - tprev) / dt;
           if (!rosen) {
@@ -710,7 +762,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
             double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
             for (int qq = 0; qq < tot; ++qq) TMP[qq] = U[qq] + dt * (c1 * K[1][qq] + c2 * K[2][qq]);
           }
-          emit_save(c, sk, isave, TMP);
+          emit_save(c, sk, isave, ts, TMP);
         }
         ++isave;
       }
@@ -790,7 +842,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
   rhs_value(c, t0, U, F0, &kc); res->st.n_rhs++;
   kc0 = kc;
   dt = initial_dt(c, t0, U, F0, dtmax, W2, &kc); res->st.n_rhs++;
-  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, U); ++isave; }
+  while (isave < nsave && o->saveat[isave] <= t0) { emit_save(c, sk, isave, o->saveat[isave], U); ++isave; }
 
   while (t < tend) {
     ++iter;
@@ -869,13 +921,13 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
       rhs_value(c, t, Un, F1, &kc); res->st.n_rhs++;
       while (isave < nsave && o->saveat[isave] <= t) {
         double ts = o->saveat[isave];
-        if (ts == t) emit_save(c, sk, isave, Un);
+        if (ts == t) emit_save(c, sk, isave, ts, Un);
         else {
           double th = (ts - tprev) / dt;
           for (int i = 0; i < n; ++i)
             TMP[i] = (1.0 - th) * U[i] + th * Un[i] +
                      th * (th - 1.0) * ((1.0 - 2.0 * th) * (Un[i] - U[i]) + (th - 1.0) * dt * F0[i] + th * dt * F1[i]);
-          emit_save(c, sk, isave, TMP);
+          emit_save(c, sk, isave, ts, TMP);
         }
         ++isave;
       }
@@ -1170,7 +1222,7 @@ static void solve_one_adjoint(const ctx_t* c, const double* u0, int n_save_use, 
 static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const double* seed, int np) {
   c->m = m; c->o = o;
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
-  c->nw = m->n_reac * (m->n_in + 1 + m->n_species);
+  c->nw = m->n_reac * (m->n_in + 1 + m->n_species) + (m->w_obs ? m->n_reac : 0);
   c->seed = seed; c->ncol = 1 + np;
   c->order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
   c->qmin = o->qmin > 0 ? o->qmin : 0.2;
@@ -1192,11 +1244,13 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
 }
 
 static int check_dims(const crnn_model* m, const crnn_opts* o) {
-  const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  const int f2 = IS_TAB(m);
   if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state + (f2 ? 2 : 0)) return CRNN_ERR_BAD_ARG;
   if ((m->rhs_kind == CRNN_RHS_F0 || f2) && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE && m->n_species + 1 != m->n_state) return CRNN_ERR_BAD_ARG;
-  if (f2 && (!m->mw || !m->tab_t || !m->tab_T || !m->tab_P || m->n_tab < 2)) return CRNN_ERR_BAD_ARG;
+  if (f2 && (!m->tab_t || !m->tab_T || m->n_tab < 2)) return CRNN_ERR_BAD_ARG;
+  if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (!m->mw || !m->tab_P)) return CRNN_ERR_BAD_ARG;
+  if (m->w_obs && o->n_obs > 1) return CRNN_ERR_BAD_ARG;
   if (f2 && (m->tab_t[0] > o->t0 || m->tab_t[m->n_tab - 1] < o->t1)) return CRNN_ERR_BAD_ARG;
   if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4 &&
       o->alg != CRNN_ALG_AUTO_TSIT5_ROS23) return CRNN_ERR_UNSUPPORTED;
@@ -1240,6 +1294,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
+  if (adjoint && (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs)) return CRNN_ERR_UNSUPPORTED; /* forward mode only */
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));
