@@ -19,7 +19,8 @@ struct CModel
     n_state::Int32; n_species::Int32; n_in::Int32; n_reac::Int32; rhs_kind::Int32; n_tab::Int32
     lb::Float64; ub::Float64; gas_R::Float64
     out_scale::Ptr{Float64}; w_in::Ptr{Float64}; w_b::Ptr{Float64}; w_out::Ptr{Float64}
-    mw::Ptr{Float64}; tab_t::Ptr{Float64}; tab_T::Ptr{Float64}; tab_P::Ptr{Float64}   # F2 (HyChem) only
+    mw::Ptr{Float64}; tab_t::Ptr{Float64}; tab_T::Ptr{Float64}; tab_P::Ptr{Float64}   # F2 (HyChem) / F5 (Cathode) only
+    w_obs::Ptr{Float64}            # observable post-map (heat release, Cathode/src/network.jl:82-91) or C_NULL
 end
 struct COpts
     alg::Int32; sens_mode::Int32; err_norm_includes_sens::Int32; n_save::Int32; n_obs::Int32
@@ -66,7 +67,8 @@ check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:crnn_last_error, L
 "Problem constants a script defines once (tsteps, tolerances, lb/ub, i_obs, dydt_scale ...)."
 Base.@kwdef struct Setup
     rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state),
-                                   # 2: F2 (HyChem/crnn_pyrolysis_mass.jl: mass fractions, tabulated T(t), P(t))
+                                   # 2: F2 (HyChem/crnn_pyrolysis_mass.jl: mass fractions, tabulated T(t), P(t)),
+                                   # 3: F5 (Cathode/src/network.jl:68-80: temperature programme T(t), no density map)
     alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23, 2 KenCarp4, 3 AutoTsit5(Rosenbrock23())
     sens_mode::Int32 = 1           # 1 forward (ForwardDiff semantics), 2 interpolating adjoint, 3 discrete adjoint
     gas_R::Float64 = 1.98720425864083e-3
@@ -74,6 +76,7 @@ Base.@kwdef struct Setup
     tab_t::Vector{Float64} = Float64[]     # F2: knots of itpT / itpP
     tab_T::Vector{Float64} = Float64[]
     tab_P::Vector{Float64} = Float64[]
+    w_obs::Vector{Float64} = Float64[]     # heat-release weights w_delH (Cathode/src/network.jl:121); empty: observe rows of u
     lb::Float64; ub::Float64
     abstol::Vector{Float64} = [1e-6]; reltol::Vector{Float64} = [1e-3]
     tspan::Tuple{Float64,Float64}; saveat::Vector{Float64}
@@ -91,11 +94,11 @@ function with_structs(f, s::Setup, w_in, w_b, w_out)
     ns, nr = size(w_out); n_in = size(w_in, 1)
     osc = s.out_scale === nothing ? Float64[] : s.out_scale
     GC.@preserve w_in w_b w_out osc s begin
-        n_state = s.rhs_kind == 2 ? ns : n_in      # F0/F1: n_in == n_state; F2: n_in = n_species + 2
+        n_state = s.rhs_kind >= 2 ? ns : n_in      # F0/F1: n_in == n_state; F2/F5: n_in = n_species + 2
         f2p(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
         m = CModel(n_state, ns, n_in, nr, s.rhs_kind, length(s.tab_t), s.lb, s.ub, s.gas_R,
                    isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out),
-                   f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P))
+                   f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P), f2p(s.w_obs))
         o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
@@ -171,6 +174,31 @@ function loss_grad(e::Engine, s::Setup, p2vec, ds::Dataset, idx, p; sample=nothi
               sample === nothing ? C_NULL : nsu, yscale_of(s), s.loss_kind, lsum, grad, C_NULL, C_NULL, C_NULL, C_NULL))
     end
     lsum[1] / max(lsum[2], 1.0), grad ./ max(lsum[2], 1.0)
+end
+
+"""
+    loss_grad_particles(e, s, weights, seeds, u0s, data, yscale; tab_T=nothing) -> (loss[E, P], grad[np, P])
+
+The SVGD loop `for j = 1:size(p)[1] ... ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p_temp)`
+(Cathode_NCM333_UQ/src_333/network.jl:222-260) as ONE launch: `weights` is n_w × P (each particle's
+`vcat(vec(w_in), w_b, vec(w_out), w_delH)`), `seeds` n_w × np × P (each particle's Jacobian of p2vec), `u0s` n_state × E,
+`data` n_obs × n_save × E, `tab_T` n_tab × E per-experiment temperature programmes.
+"""
+function loss_grad_particles(e::Engine, s::Setup, weights::Matrix{Float64}, seeds::Array{Float64,3}, u0s::Matrix{Float64},
+                             data::Array{Float64,3}, yscale::Vector{Float64}; tab_T=nothing)
+    P = size(weights, 2); E = size(u0s, 2); np_ = size(seeds, 2)
+    loss = zeros(E, P); grad = zeros(np_, P)
+    # the model struct only carries dimensions and constants here; every particle's weights come from `weights`
+    n_state = size(u0s, 1); n_in = s.rhs_kind >= 2 ? n_state + 2 : n_state
+    nreac = div(size(weights, 1), n_in + 1 + n_state + (isempty(s.w_obs) ? 0 : 1))
+    with_structs(s, zeros(n_in, nreac), zeros(nreac), zeros(n_state, nreac)) do m, o
+        check(e, ccall((:crnn_loss_grad_particles, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Int32},
+               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+              e.h, m, o, weights, seeds, np_, P, u0s, E, C_NULL, data, tab_T === nothing ? C_NULL : tab_T, C_NULL, yscale,
+              s.loss_kind, loss, grad, C_NULL, C_NULL, C_NULL))
+    end
+    loss, grad
 end
 
 """
