@@ -19,6 +19,7 @@
 #include "crnn_dev.cuh"
 #include "kernel_tsit5_value.cuh"
 #include "kernel_tsit5_sens.cuh"
+#include "kernel_tsit5_sens_pl.cuh"
 #include "kernel_rosenbrock23.cuh"
 #include "kernel_rosenbrock23_sens.cuh"
 #include "kernel_auto_value.cuh"
@@ -270,6 +271,29 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
   // groups per block when WPT warps share a trajectory (NGRP overrides the number of groups)
   constexpr int WARPS = WPT == 1 ? (CT == 1 ? 8 : 4) : (NGRP > 0 ? NGRP * WPT : (WPT <= 4 ? 2 * WPT : WPT));
   constexpr int MINB = WPT == 1 ? 2 : 1;
+  if constexpr (WPT == 1) {
+    // CRNN_B200_SENS_PIPELINED=1 selects the experimental kernel with the pipelined value path (kernel_tsit5_sens_pl.cuh:
+    // same results, measured 10-13 % SLOWER - kept for A/B measurements)
+    static const bool pipelined = [] { const char* e = std::getenv("CRNN_B200_SENS_PIPELINED"); return e && e[0] == '1'; }();
+    if (pipelined) {
+      auto kern = k_tsit5_sens_pl<C, CT, WARPS, MINB, R1>;
+      const size_t smem = sizeof(SensSmemP<C, CT, R1>) + WARPS * sizeof(WarpBufP<C, CT>);
+      if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int bps = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+      if (bps < 1) bps = 1;
+      unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, (b.n + WARPS - 1) / WARPS);
+      unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+      CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+      ProfScope prof(h, st);
+      kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
+                                          b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx);
+      CK(cudaGetLastError());
+      h->launches++;
+      return CRNN_OK;
+    }
+  }
   auto kern = k_tsit5_sens<C, CT, WARPS, MINB, R1, WPT>;
   const size_t smem = sizeof(SensSmem<C, CT, R1, WPT>) + WARPS * sizeof(WarpBuf<C, CT>);
   if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");

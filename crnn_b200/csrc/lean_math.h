@@ -117,6 +117,44 @@ CRNN_LM_FN double lean_exp(double x) {
   return LM_MK(LM_HI(p) + (int)((unsigned)LM_LO(t) << 20), LM_LO(p));
 }
 
+/* "compute, then fix" forms: the fast path runs unconditionally (straight-line code a scheduler can interleave with
+ * independent work) and the rare out-of-range argument is patched afterwards.  Same values as lean_log / lean_exp. */
+CRNN_LM_FN double lean_log_cf(double x) {
+  const int hi = LM_HI(x), lo = LM_LO(x);
+  const int hx = hi & 0xfffff, i = (hx + 0x95f64) & 0x100000;
+  const double m = LM_MK(hx | (i ^ 0x3ff00000), lo);
+  const double dk = (double)((hi >> 20) - 1023 + (i >> 20));
+  const double f = LM_SUB(m, 1.0), d = LM_ADD(2.0, f);
+  double r = LM_FMA(d, LM_C(26), LM_C(25));
+  double e = LM_FMA(-d, r, 1.0);
+  r = LM_FMA(r, LM_FMA(e, e, e), r);
+  e = LM_FMA(-d, r, 1.0);
+  r = LM_FMA(r, LM_FMA(e, e, e), r);
+  const double s = LM_MUL(f, r), z = LM_MUL(s, s), w = LM_MUL(z, z);
+  const double t1 = LM_MUL(w, LM_FMA(w, LM_FMA(w, LM_C(5), LM_C(3)), LM_C(1)));
+  const double R = LM_FMA(z, LM_FMA(w, LM_FMA(w, LM_FMA(w, LM_C(6), LM_C(4)), LM_C(2)), LM_C(0)), t1);
+  const double hfsq = LM_MUL(LM_MUL(0.5, f), f);
+  const double inner = LM_FMA(s, LM_ADD(hfsq, R), LM_MUL(dk, LM_C(8)));
+  double y = LM_FMA(dk, LM_C(7), -LM_SUB(LM_SUB(hfsq, inner), f));
+  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) y = LM_LIBLOG(x);
+  return y;
+}
+
+CRNN_LM_FN double lean_exp_cf(double x) {
+  const double t = LM_FMA(x, LM_C(9), LM_C(10));
+  const double kf = LM_SUB(t, LM_C(10));
+  double r = LM_FMA(kf, -LM_C(7), x);
+  r = LM_FMA(kf, -LM_C(8), r);
+  double p = LM_C(11);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int n = 12; n <= 24; ++n) p = LM_FMA(p, r, LM_C(n));
+  double y = LM_MK(LM_HI(p) + (int)((unsigned)LM_LO(t) << 20), LM_LO(p));
+  if ((unsigned)(LM_HI(x) & 0x7fffffff) >= 0x4085e000u) y = LM_LIBEXP(x);
+  return y;
+}
+
 /* x^y for x > 0 (step-size controller exponents; OrdinaryDiffEq uses its own `fastpow` there): a few ulp */
 CRNN_LM_FN double lean_pow(double x, double y) { return lean_exp(LM_MUL(y, lean_log(x))); }
 /* the initial-step heuristic's 10^(-(2 + log10 d)/order) */
