@@ -152,7 +152,8 @@ def load(path: str) -> dict:
         b = f.read()
     doc, _ = parse(b)
     out = {"doc": doc, "p": np.asarray(resolve(doc, doc["p"]), dtype=np.float64).reshape(-1), "iter": doc.get("iter"),
-           "opt": doc.get("opt")}
+           "opt": doc.get("opt"),
+           "p_ref": doc["p"]["ref"] if isinstance(doc["p"], dict) and doc["p"].get("tag") == "backref" else None}
     for k, v in doc.items():
         if k.startswith("l_") or k.startswith("list_"):     # l_loss_train, l_loss_val, l_grad, list_loss_*, list_grad
             r = resolve(doc, v)
@@ -165,7 +166,7 @@ def lower_float32(x) -> dict:
     return {"tag": "struct", "type": _datatype("Float32"), "data": Bin(struct.pack("<f", float(x)))}
 
 
-def save(path: str, p, iter_: int, opt=None, backrefs=None, **lists):
+def save(path: str, p, iter_: int, opt=None, backrefs=None, p_ref=None, **lists):
     """Write `p`, `iter` and the histories (keyword arguments, e.g. l_loss_train=[...]) the way `@save` lowers them in the
     reference's own files: `p` a Vector{Float64}, `iter` an Int64, each history an `Any[]` of Float32 scalars.
     `opt` / `backrefs`: subtrees returned by `load` (doc["opt"], doc["_backrefs"]) to carry over unchanged; a fresh run
@@ -175,6 +176,16 @@ def save(path: str, p, iter_: int, opt=None, backrefs=None, **lists):
         doc["opt"] = opt
     doc["iter"] = int(iter_)
     doc["p"] = lower_array(np.asarray(p, dtype=np.float64).reshape(-1))
+    if opt is not None and backrefs is not None:
+        # In the reference's files `p` is a backref to the SAME array object that keys the optimiser's IdDict state
+        # (`{tag: backref, ref: k}`): keep that identity, or Flux would resume with fresh ADAM moments for the new `p`.
+        # The carried-over `_backrefs` entry that held the old p receives the new values and `p` points at it again.
+        # `p_ref`: the 1-based index `load` reports (out["p_ref"]) when the loaded file stored p that way.
+        ref = p_ref
+        if ref is not None:
+            backrefs = list(backrefs)
+            backrefs[ref - 1] = doc["p"]
+            doc["p"] = {"tag": "backref", "ref": ref}
     for k, v in lists.items():
         doc[k] = [lower_float32(x) for x in v]
     if backrefs is not None:

@@ -15,7 +15,7 @@ namespace crnn_host {
                                                     const HostIO&, int64_t);                                \
   extern template int loss_grad_impl<Cfg<NS_, NR_, K_>>(crnn_handle*, const crnn_model*, const crnn_opts*,  \
                                                         const double*, int, const double*, int,             \
-                                                        const HostIO&, int64_t, double*);
+                                                        const HostIO&, int64_t, double*, const AutoHook*);
 CRNN_FOR_EACH_CFG(X)
 #undef X
 }  // namespace crnn_host
@@ -26,7 +26,8 @@ namespace {
 // Fills the generic-dimension parameter block shared by the lane-per-component kernels and uploads
 // its device arrays: w_inT [nin][32] | w_b | w_out (scaled) | saveat | row2obs | extra doubles.
 int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int order, const std::vector<double>& extra,
-               cudaStream_t st, WideP& P, const double** extra_dev) {
+               cudaStream_t st, WideP& P, const double** extra_dev, DevBuf* blob_buf = nullptr) {
+  DevBuf& cfgbuf = blob_buf ? *blob_buf : h->cfg;
   if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
     return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
   const int n = m->n_state, ns = m->n_species, nin = m->n_in, nr = m->n_reac;
@@ -89,9 +90,9 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
       p_f2[ns + k] = m->tab_t[k]; p_f2[ns + ntab + k] = m->tab_T[k]; p_f2[ns + 2 * ntab + k] = dens ? m->tab_P[k] : 1.0;
     }
   }
-  CK(h->cfg.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
-  CK(cudaMemcpyAsync(h->cfg.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  double* d = h->cfg.as<double>();
+  CK(cfgbuf.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
+  CK(cudaMemcpyAsync(cfgbuf.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  double* d = cfgbuf.as<double>();
   P.w_inT = d; P.w_b = d + (p_wb - blob.data()); P.w_out = d + (p_wout - blob.data());
   P.saveat = d + (p_save - blob.data());
   P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
@@ -283,7 +284,8 @@ int gen_plan_seed(crnn_handle* h, const crnn_model* m, const double* dW_dp, int 
 
 int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_t& smem, long long& max_blocks, bool f2k,
                    void (**kern_out)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*,
-                                     int*, crnn_stats*, unsigned long long*, const long long*)) {
+                                     int*, crnn_stats*, unsigned long long*, const long long*, const long long*,
+                                     const unsigned int*)) {
   if (np < 1 || np > 255) return fail(h, CRNN_ERR_UNSUPPORTED, "the generic forward-sensitivity kernel supports 1 <= np <= 255");
   if (m->n_state > KW_MAXN || m->n_reac > KW_MAXN || m->n_in > KW_MAXN)
     return fail(h, CRNN_ERR_UNSUPPORTED, "this solver's kernel supports n_state, n_in, n_reac <= 32");
@@ -304,8 +306,43 @@ int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_
 // Generic forward sensitivities (kernel_gen_sens.cuh): any dimensions <= 32, F0 / F1 / F2 / F5, Tsit5 / Rosenbrock23 /
 // AutoTsit5(Rosenbrock23), np <= 255, structured seed columns, optional observable post-map, all three losses.
 // Returns CRNN_ERR_UNSUPPORTED when the model cannot be served so that the caller can try the adjoint route.
+struct GenLaunch {
+  GenP G{};
+  void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
+               unsigned long long*, const long long*, const long long*, const unsigned int*) = nullptr;
+  int cols = 0; size_t smem = 0; long long max_blocks = 0;
+};
+
+int gen_enqueue(crnn_handle* h, const GenLaunch& L, const BatchPtrs& b, cudaStream_t s, const long long* sel,
+                const unsigned int* sel_count) {
+  if (b.n == 0) return CRNN_OK;
+  const unsigned blocks = (unsigned)std::min<long long>(L.max_blocks, b.n);
+  // the hand-over launch gets its own work-queue counter (slot 5 + qslot would collide: use the high half of the ctr block)
+  unsigned long long* queue = h->ctr.as<unsigned long long>() + (sel ? 8 + b.qslot : b.qslot);
+  CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+  ProfScope prof(h, s);
+  L.kern<<<blocks, L.cols, L.smem, s>>>(L.G, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode,
+                                        b.stats, queue, b.in_idx, sel, sel_count);
+  CK(cudaGetLastError());
+  h->launches++;
+  return CRNN_OK;
+}
+
+int gen_prepare(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                const double* yscale, int loss_kind, cudaStream_t st, DevBuf* blob_buf, GenLaunch& L);
+
 int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                       const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
+  GenLaunch L;
+  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  int rc = gen_prepare(h, m, o, dW_dp, np, yscale, loss_kind, st, nullptr, L);
+  if (rc) return rc;
+  return run_batch(h, m, o, io, N, true, np, grad_sum,
+                   [&](const BatchPtrs& b, cudaStream_t s) -> int { return gen_enqueue(h, L, b, s, nullptr, nullptr); });
+}
+
+int gen_prepare(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
+                const double* yscale, int loss_kind, cudaStream_t st, DevBuf* blob_buf, GenLaunch& L) {
   if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
     return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
   const int n = m->n_state, nr = m->n_reac;
@@ -313,7 +350,7 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   const bool has_obs = m->w_obs != nullptr;
   int cols = 0; size_t smem = 0; long long max_blocks = 0;
   void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
-               unsigned long long*, const long long*) = nullptr;
+               unsigned long long*, const long long*, const long long*, const unsigned int*) = nullptr;
   int rc = gen_launch_cfg(h, m, np, cols, smem, max_blocks, f2k, &kern);
   if (rc) return rc;
   const int nrow = (has_obs ? 3 : 2) * nr;
@@ -333,29 +370,18 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   std::memcpy(extra.data() + n, rows.data(), rows.size() * sizeof(double));
   std::memcpy(extra.data() + n + rows.size(), desc.data(), desc.size() * sizeof(R1Desc));
   for (int j = 0; j < nr; ++j) extra[(size_t)n + rows.size() + 3 * (size_t)cols + j] = has_obs ? m->w_obs[j] : 0.0;
-  GenP G{};
-  cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+  GenP& G = L.G;
   const double* extra_dev = nullptr;
   const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
-  int rcw = build_wide(h, m, o, order, extra, st, G.w, &extra_dev);
+  int rcw = build_wide(h, m, o, order, extra, st, G.w, &extra_dev, blob_buf);
   if (rcw) return rcw;
   G.inv_ys = extra_dev; G.seed_rows = extra_dev + n;
   G.desc = reinterpret_cast<const R1Desc*>(extra_dev + n + rows.size());
   G.w_obs = has_obs ? extra_dev + n + rows.size() + 3 * (size_t)cols : nullptr;
   G.np = np; G.cols = cols; G.loss_kind = loss_kind; G.incl_sens = o->err_norm_includes_sens ? 1 : 0;
   G.norm_cnt = (double)n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)(np + 1) : 1.0);
-  return run_batch(h, m, o, io, N, true, np, grad_sum, [&](const BatchPtrs& b, cudaStream_t s) -> int {
-    if (b.n == 0) return (int)CRNN_OK;
-    const unsigned blocks = (unsigned)std::min<long long>(max_blocks, b.n);
-    unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
-    CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
-    ProfScope prof(h, s);
-    kern<<<blocks, cols, smem, s>>>(G, b.u0, b.nsu, b.n, b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode,
-                                    b.stats, queue, b.in_idx);
-    CK(cudaGetLastError());
-    h->launches++;
-    return (int)CRNN_OK;
-  });
+  L.kern = kern; L.cols = cols; L.smem = smem; L.max_blocks = max_blocks;
+  return CRNN_OK;
 }
 
 // grad[c + np*p] = sum over the experiments e of grad_each[(e + E*p)*np + c], in experiment order (deterministic)
@@ -406,9 +432,38 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
       loss_kind != CRNN_LOSS_MSE && !(force && force[0] == '1')) {
 #define X(NS_, NR_, K_)                                                              \
   if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
-    return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum);
+    return loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum, nullptr);
     CRNN_FOR_EACH_CFG(X)
 #undef X
+  }
+  // AutoTsit5(Rosenbrock23) on a model with a specialised kernel (case2.jl:26 as written): Tsit5 with the AutoSwitch monitor,
+  // the trajectories that would switch handed over to the generic composite kernel on the same stream
+  if (o->alg == CRNN_ALG_AUTO_TSIT5_ROS23 && (m->rhs_kind == CRNN_RHS_F0 || m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE) && !m->w_obs &&
+      loss_kind != CRNN_LOSS_MSE && np >= 1 && np <= 63 && !(force && force[0] == '1')) {
+    bool have_cfg = false;
+#define X(NS_, NR_, K_) have_cfg = have_cfg || (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_);
+    CRNN_FOR_EACH_CFG(X)
+#undef X
+    GenLaunch L;
+    cudaStream_t stg = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
+    if (have_cfg && gen_prepare(h, m, o, dW_dp, np, yscale, loss_kind, stg, &h->cfg2, L) == CRNN_OK) {
+      AutoHook hook;
+      hook.stride = (size_t)std::max<int64_t>(N, 1);
+      const size_t nslot = 2 + kPipe;
+      CK(h->auto_sel.reserve(nslot * hook.stride * sizeof(long long) + 64));
+      hook.count = h->auto_sel.as<unsigned int>();
+      hook.sel = reinterpret_cast<long long*>(h->auto_sel.as<char>() + 64);
+      hook.fallback = [h, &L](const BatchPtrs& b, cudaStream_t s, const long long* sel, const unsigned int* cnt) -> int {
+        return gen_enqueue(h, L, b, s, sel, cnt);
+      };
+      int rca = CRNN_ERR_UNSUPPORTED;
+#define X(NS_, NR_, K_)                                                              \
+  if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
+    rca = loss_grad_impl<Cfg<NS_, NR_, K_>>(h, m, o, dW_dp, np, yscale, loss_kind, io, N, grad_sum, &hook);
+      CRNN_FOR_EACH_CFG(X)
+#undef X
+      if (rca != CRNN_ERR_UNSUPPORTED) return rca;
+    }
   }
   // ... and the generic block-per-trajectory kernel for everything else: gradients through AutoTsit5(Rosenbrock23), stiff
   // gradients of F2 and of models with more than 6 species, any (n_species, n_reac) <= 32
@@ -473,7 +528,7 @@ int crnn_create(crnn_handle** out, int device_id) {
     ok = cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && h->ctr.reserve(64) == cudaSuccess && cudaMemset(h->ctr.p, 0, 64) == cudaSuccess;
+  ok = ok && h->ctr.reserve(256) == cudaSuccess && cudaMemset(h->ctr.p, 0, 256) == cudaSuccess;
   if (!ok) { crnn_destroy(h); return CRNN_ERR_CUDA; }
   *out = h;
   return CRNN_OK;
@@ -490,7 +545,7 @@ void crnn_destroy(crnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch,
-                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats, &h->d_idx, &h->d_nsu_ix, &h->d_result};
+                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats, &h->d_idx, &h->d_nsu_ix, &h->d_result, &h->cfg2, &h->auto_sel};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
     DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s]};
@@ -593,7 +648,7 @@ int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opt
   CK(cudaSetDevice(h->device));
   int cols = 0; size_t smem = 0; long long max_blocks = 0;
   void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
-               unsigned long long*, const long long*) = nullptr;
+               unsigned long long*, const long long*, const long long*, const unsigned int*) = nullptr;
   rc = gen_launch_cfg(h, &m0, np, cols, smem, max_blocks, f2k, &kern);
   if (rc) return rc;
   cudaStream_t st = h->s_compute;
@@ -676,7 +731,7 @@ int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opt
     ProfScope prof(h, st);
     kern<<<(unsigned)std::min<long long>(max_blocks, N), cols, smem, st>>>(
         G, d_u0, n_save_used ? d_nsu : nullptr, N, d_data, h->d_loss.as<double>(), h->d_grad_each.as<double>(), nullptr,
-        h->d_nsaved.as<int>(), h->d_ret.as<int>(), stats ? h->d_stats.as<crnn_stats>() : nullptr, queue, nullptr);
+        h->d_nsaved.as<int>(), h->d_ret.as<int>(), stats ? h->d_stats.as<crnn_stats>() : nullptr, queue, nullptr, nullptr, nullptr);
     CK(cudaGetLastError());
     h->launches++;
   }

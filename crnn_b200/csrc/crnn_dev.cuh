@@ -42,6 +42,7 @@ struct SolveP {
   double beta1_ros, beta2_ros;  // AutoTsit5: PI exponents while the Rosenbrock23 half runs
   double qs_min, qs_max;        // step_accept_controller!'s dead-band: qs_min <= q <= qs_max keeps dt
   double norm_cnt;              // divisor of the dual-aware norms: totallength(u) = N*(1+np), or N (crnn_opts)
+  double eig_cnt;               // AutoSwitch eigenvalue estimate: N * (number of columns in the norm)
   long long maxiters;
   const double* saveat;  // device [n_save]
   const int* row2obs;    // device [N]: observation slot of state row i, or -1

@@ -77,6 +77,8 @@ struct crnn_handle {
   // pageable host memory blocks the host thread, which would serialise the chunk pipeline)
   DevBuf d_loss, d_nsaved, d_ret, d_stats;
   DevBuf d_grad_each, d_grad_sum, d_grad_out, adj_scratch;
+  // AutoTsit5 fast path: config blob of the generic composite kernel, hand-over lists (one per work-queue slot)
+  DevBuf cfg2, auto_sel;
   // device-resident dataset path (crnn_loss_grad_indexed): row indices, n_save_used, [sum loss, n finite, grad(np)]
   DevBuf d_idx, d_nsu_ix, d_result;
   // multi-device parent (crnn_create_multi): the children own all per-device state, the parent launches nothing itself
@@ -216,6 +218,7 @@ int pack(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* 
   sp.qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
   sp.qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
   sp.norm_cnt = (double)C::N;  // loss_grad_impl multiplies by (1 + np) when the partials share the mean
+  sp.eig_cnt = (double)C::N;
   sp.loss_kind = loss_kind;
   return CRNN_OK;
 }
@@ -232,6 +235,16 @@ int upload_cfg(crnn_handle* h, const crnn_opts* o, const Packed& pk, SolveP<C>& 
   sp.row2obs = reinterpret_cast<const int*>((char*)h->cfg.p + off_r2o);
   return CRNN_OK;
 }
+
+struct BatchPtrs;
+// AutoTsit5(Rosenbrock23) on a specialised Tsit5 kernel: the kernel monitors stiffness and hands the trajectories that
+// would switch over to `fallback` (the generic composite kernel), enqueued right behind it on the same stream.
+struct AutoHook {
+  long long* sel = nullptr;        // device [(2 + kPipe) * stride] hand-over lists, one region per work-queue slot
+  unsigned int* count = nullptr;   // device [2 + kPipe]
+  size_t stride = 0;
+  std::function<int(const BatchPtrs&, cudaStream_t, const long long* sel, const unsigned int* count)> fallback;
+};
 
 struct BatchPtrs {  // device pointers of one (sub)batch
   const double* u0; const int* nsu; const double* data;
@@ -265,8 +278,35 @@ int launch_value(crnn_handle* h, int alg, const ModelP<C>& mp, const SolveP<C>& 
 // ---------------- sensitivity path launchers ----------------
 template <class C, int CT, bool R1, int WPT = 1, int NGRP = 0>
 int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int ncol, const BatchPtrs& b,
-                cudaStream_t st) {
+                cudaStream_t st, const AutoHook* hook = nullptr) {
   if (b.n == 0) return CRNN_OK;
+  if constexpr (WPT == 1) {
+    if (hook) {   // AutoTsit5(Rosenbrock23): Tsit5 + AutoSwitch monitor here, the composite kernel for what it hands over
+      constexpr int WARPS_A = CT == 1 ? 8 : 4;
+      auto kern = k_tsit5_sens<C, CT, WARPS_A, 2, R1, 1, true>;
+      const size_t smem = sizeof(SensSmem<C, CT, R1, 1>) + WARPS_A * sizeof(WarpBuf<C, CT>);
+      if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int bps = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS_A * 32, smem));
+      if (bps < 1) bps = 1;
+      const unsigned blocks = (unsigned)std::min<long long>((long long)h->num_sms * bps, (b.n + WARPS_A - 1) / WARPS_A);
+      unsigned long long* queue = h->ctr.as<unsigned long long>() + b.qslot;
+      long long* sel = hook->sel + (size_t)b.qslot * hook->stride;
+      unsigned int* cnt = hook->count + b.qslot;
+      CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+      CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), st));
+      {
+        ProfScope prof(h, st);
+        kern<<<blocks, WARPS_A * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
+                                              b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue,
+                                              b.in_idx, sel, cnt);
+        CK(cudaGetLastError());
+        h->launches++;
+      }
+      return hook->fallback(b, st, sel, cnt);
+    }
+  }
   // warps per block: 16 warps/SM in two blocks for the single-warp layouts; one or two warp
   // groups per block when WPT warps share a trajectory (NGRP overrides the number of groups)
   constexpr int WARPS = WPT == 1 ? (CT == 1 ? 8 : 4) : (NGRP > 0 ? NGRP * WPT : (WPT <= 4 ? 2 * WPT : WPT));
@@ -308,7 +348,8 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
   CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
   ProfScope prof(h, st);
   kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
-                                      b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx);
+                                      b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx,
+                                      nullptr, nullptr);
   CK(cudaGetLastError());
   h->launches++;
   return CRNN_OK;
@@ -563,8 +604,9 @@ int solve_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
 
 template <class C>
 int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
-                   const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23)
+                   const double* yscale, int loss_kind, const HostIO& io, int64_t N, double* grad_sum,
+                   const AutoHook* hook) {
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && !(hook && o->alg == CRNN_ALG_AUTO_TSIT5_ROS23))
     return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5 and Rosenbrock23");
   const bool ros = (o->alg == CRNN_ALG_ROSENBROCK23);
   const int ncol = np + 1;
@@ -574,6 +616,8 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   int rc = pack<C>(h, m, o, yscale, loss_kind, mp, sp, pk);
   if (rc) return rc;
   if (o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) sp.norm_cnt = (double)C::N * ncol;  // totallength(u)
+  if (o->err_norm_includes_sens) sp.eig_cnt = (double)C::N * ncol;
+  if (hook && ct > 2) return fail(h, CRNN_ERR_UNSUPPORTED, "the AutoSwitch fast path serves np <= 63");
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   rc = upload_cfg<C>(h, o, pk, sp, st);
   if (rc) return rc;
@@ -605,7 +649,8 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
       }
       return launch_sens<C, 1, true, 8>(h, mp, sp, ncol, b, s);
     }
-    if (r1) return ct == 1 ? launch_sens<C, 1, true>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, true>(h, mp, sp, ncol, b, s);
+    if (r1) return ct == 1 ? launch_sens<C, 1, true>(h, mp, sp, ncol, b, s, hook) : launch_sens<C, 2, true>(h, mp, sp, ncol, b, s, hook);
+    if (hook) return fail(h, CRNN_ERR_UNSUPPORTED, "the AutoSwitch fast path needs structured seed columns");
     return ct == 1 ? launch_sens<C, 1, false>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, false>(h, mp, sp, ncol, b, s);
   });
 }

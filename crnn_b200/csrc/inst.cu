@@ -6,5 +6,5 @@ namespace crnn_host {
 using CfgT = crnn::Cfg<CRNN_NS, CRNN_NR, CRNN_KIND>;
 template int solve_impl<CfgT>(crnn_handle*, const crnn_model*, const crnn_opts*, const HostIO&, int64_t);
 template int loss_grad_impl<CfgT>(crnn_handle*, const crnn_model*, const crnn_opts*, const double*, int,
-                                  const double*, int, const HostIO&, int64_t, double*);
+                                  const double*, int, const HostIO&, int64_t, double*, const AutoHook*);
 }  // namespace crnn_host

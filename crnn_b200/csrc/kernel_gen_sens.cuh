@@ -306,7 +306,11 @@ __global__ void __launch_bounds__(256, 1)
 k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const int* __restrict__ n_save_used,
            long long ntraj, const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
            double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
-           crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue, const long long* __restrict__ in_idx) {
+           crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue, const long long* __restrict__ in_idx,
+           const long long* __restrict__ sel = nullptr, const unsigned int* __restrict__ sel_count = nullptr) {
+  // sel / sel_count (or NULL): only the trajectories sel[0 .. *sel_count) of this call are solved - the ones a specialised
+  // Tsit5 kernel's AutoSwitch monitor handed over (kernel_tsit5_sens.cuh, AUTO); the count lives in device memory, so
+  // no host synchronisation sits between the two launches
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GenShared& S = *reinterpret_cast<GenShared*>(smem_raw);
   double* const colbase = reinterpret_cast<double*>(smem_raw + sizeof(GenShared));
@@ -371,9 +375,12 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
   while (true) {
     if (tid == 0) S.traj = (long long)atomicAdd(queue, 1ull);
     __syncthreads();
-    const long long traj = S.traj;
+    long long traj = S.traj;
     __syncthreads();
-    if (traj >= ntraj) break;
+    if (sel) {
+      if (traj >= (long long)*sel_count) break;
+      traj = sel[traj];
+    } else if (traj >= ntraj) break;
     long long src = in_idx ? __ldg(in_idx + traj) : traj;
     size_t toff = 0;
     if (G.n_part > 0) {   // trajectory = experiment e + n_exp * particle p: this particle's weights and seed columns

@@ -63,8 +63,9 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   // f(y, t), W = I - gdt*J and the triangular solves come from wide_common.cuh (all RHS flavours)
   int tab_seg = 0;  // F2: segment hint of the T(t), P(t) lookup
   auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2>(P, sb, ww, lane, my_mw, tt, y, ax, tab_seg); };
-  auto lusolve = [&](double b) -> double { return wide_lusolve(ww, lane, ns, b); };
-  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { (void)wide_build_lu<F2>(P, sb, ww, lane, rsrc, ax, gdt); };
+  // W^{-1} explicitly (Gauss-Jordan, in place) and mat-vec "solves": ~20 Newton solves share one factorisation
+  auto lusolve = [&](double b) -> double { return wide_invmul(ww, lane, ns, b); };
+  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { wide_build_inv<F2>(P, sb, ww, lane, rsrc, ax, gdt); };
   // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;

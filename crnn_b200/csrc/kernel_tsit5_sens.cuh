@@ -87,7 +87,12 @@ struct alignas(16) WarpBuf {
 
 // WPT warps share one trajectory (32*CT*WPT dual columns): the group synchronises on a named
 // barrier instead of __syncwarp, the small broadcast arrays live in the group leader's WarpBuf.
-template <class C, int CT, int WARPS, int MINB, bool R1, int WPT = 1>
+// AUTO = true (WPT = 1 only): the kernel also carries OrdinaryDiffEq's AutoSwitch stiffness monitor of
+// AutoTsit5(Rosenbrock23()) (case2/case2.jl:26; oracle solve_one header).  As long as the composite stays on Tsit5 - always,
+// on the trained case2 CRNN - this IS the composite algorithm, at this kernel's speed; a trajectory whose counter asks for
+// Rosenbrock23 is abandoned and its index appended to sel_list, and the host re-runs exactly those through the generic
+// composite kernel (kernel_gen_sens.cuh), which overwrites their outputs.
+template <class C, int CT, int WARPS, int MINB, bool R1, int WPT = 1, bool AUTO = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ SolveP<C> sp,
              const double* __restrict__ seed_dev, const R1Desc* __restrict__ desc_dev, int ncol,
@@ -95,7 +100,9 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
              const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
              double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
              crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
-             const long long* __restrict__ in_idx) {
+             const long long* __restrict__ in_idx, long long* __restrict__ sel_list = nullptr,
+             unsigned int* __restrict__ sel_count = nullptr) {
+  static_assert(!AUTO || WPT == 1, "the AutoSwitch monitor is built for one warp per trajectory");
   // in_idx (or NULL): trajectory `traj` of this call reads u0 / data of dataset row in_idx[traj] (crnn_loss_grad_indexed);
   // every output stays at position traj
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN, NW = C::NW;
@@ -222,6 +229,9 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // during the two initial-step phases dt holds dt0 and dtnew holds d1 (both are free until the first step)
     double t = t0, tprev = t0, dt = 0.0, dtnew = 0.0, lqold = lean_log(1e-4);  // log(qoldinit)
     int isave = 0, ret = CRNN_RET_DEFAULT, phase = PH_F0, k1s = 0;  // k1s: slot of K1 (0 or 6), K7 in 6-k1s
+    double eigen_est = 0.0, den_l = 0.0;  // AUTO: |k7 - k6| / |u_{n+1} - g6|, this lane's share of the denominator
+    int sw_count = 0;
+    bool needs_composite = false;
     // the next save time and this lane's next target are fetched one save ahead: their global-load
     // latency then overlaps the step in between instead of stalling the save phase
     const int my_q = (wig == 0 && lane < N) ? sm.row2obs[lane] : -1;
@@ -263,6 +273,19 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
           for (int tt = 0; tt < CT; ++tt)
 #pragma unroll
             for (int i = 0; i < NS; ++i) Y[tt][i] = fma(h, KO[tt][i], U[tt][i]);
+          if (AUTO && phase == 5) {   // g6 (the stage-6 state) parked in the K7 slot, free until stage 6 stores K7
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt) kstore(6 - k1s, tt, Y[tt]);
+          }
+          if (AUTO && phase == 6) {
+            den_l = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt) {
+              kload(6 - k1s, tt, kv);
+#pragma unroll
+              for (int i = 0; i < NS; ++i) { const double dd = Y[tt][i] - kv[i]; den_l = live[tt] ? fma(dd, dd, den_l) : den_l; }
+            }
+          }
         }
 
         // ---- KO = f(Y) on all columns: the single RHS instance (3 warp barriers) ----
@@ -333,6 +356,17 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         {
           // F0 -> K1 ; F1 -> slot 1 (scratch, free until stage 1 writes K2) ; stage s -> K_{s+1}
           const int dst = (phase == PH_F0) ? k1s : (phase == PH_F1) ? 1 : (phase == 6 ? 6 - k1s : phase);
+          if (AUTO && phase == 6) {   // eigen_est = |k7 - k6| / |u_{n+1} - g6| over the columns that take part in the norm
+            double num_l = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < CT; ++tt) {
+              double kv[NS];
+              kload(5, tt, kv);
+#pragma unroll
+              for (int i = 0; i < NS; ++i) { const double dd = KO[tt][i] - kv[i]; num_l = live[tt] ? fma(dd, dd, num_l) : num_l; }
+            }
+            eigen_est = sqrt(warp_sum(num_l) / sp.eig_cnt) / sqrt(warp_sum(den_l) / sp.eig_cnt);
+          }
 #pragma unroll
           for (int tt = 0; tt < CT; ++tt) kstore(dst, tt, KO[tt]);
         }
@@ -578,6 +612,11 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       if (phase == 1) {  // loopheader! + check_error! before every step attempt
         const double tend = wb.cold[0], dtmin = wb.cold[2];
         if (!(t < tend)) break;
+        if (AUTO && n_acc + n_rej > 0) {  // AutoSwitch choice function, before every attempt but the first, on the proposed dt
+          const bool stiff = fabs(eigen_est * dt / 3.5068) > 0.9;
+          sw_count = stiff ? (sw_count < 0 ? 1 : sw_count + 1) : (sw_count > 0 ? -1 : sw_count - 1);
+          if (sw_count > 10) { needs_composite = true; break; }
+        }
         if (dt != dt) { ret = CRNN_RET_DTNAN; break; }
         if ((long long)n_acc + n_rej + 1 > sp.maxiters) { ret = CRNN_RET_MAXITERS; break; }
         dt = jmin(dt, wb.cold[1]);
@@ -598,6 +637,10 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
       }
     }
     if (ret == CRNN_RET_DEFAULT) ret = CRNN_RET_SUCCESS;
+    if (AUTO && needs_composite) {
+      ret = CRNN_RET_DEFAULT;   // provisional: the composite kernel rewrites every output of this trajectory
+      if (lane == 0) sel_list[atomicAdd(sel_count, 1u)] = traj;
+    }
 
     // ---- per-trajectory outputs ----
     const double cnt = (double)sp.n_obs * (double)isave;

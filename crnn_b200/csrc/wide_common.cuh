@@ -198,8 +198,8 @@ __device__ __forceinline__ double wide_time_deriv(const WideP& P, const WideBloc
 // W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
 // pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
 template <bool F2, class WW>
-__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WW& ww, int lane,
-                                                const double* rsrc, const WideAux& a, double gdt) {
+__device__ __forceinline__ double wide_assemble_W(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                                  const double* rsrc, const WideAux& a, double gdt) {
   const int n = P.n, ns = P.ns, nr = P.nr;
   const bool isp = lane < ns;
   __syncwarp();
@@ -246,6 +246,18 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
     }
   }
   const double eig = warp_max(rowsum);
+  __syncwarp();
+  return eig;
+}
+
+// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
+// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                                const double* rsrc, const WideAux& a, double gdt) {
+  const int ns = P.ns;
+  const bool isp = lane < ns;
+  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);
   ww.perm[lane] = lane;
   __syncwarp();
   for (int k = 0; k < ns; ++k) {
@@ -293,6 +305,63 @@ __device__ __forceinline__ double wide_lusolve(const WW& ww, int lane, int ns, d
     if (lane < k) b = fma(-ww.A[lane][k], bk, b);
   }
   return isp ? b : 0.0;
+}
+
+// W^{-1} in place of W (ww.A) by Gauss-Jordan elimination with partial pivoting, lane = row.  A solve then is one
+// mat-vec with independent loads (wide_invmul) instead of 2*ns dependent shuffle + FMA steps (wide_lusolve): the
+// simplified-Newton iterations of k_kencarp4_wide call it ~20 times per factorisation, and those dependent chains were
+// what bound that kernel.  Mirrored by the oracle's named switch crnn_oracle_set_kc4_inverse.
+template <bool F2, class WW>
+__device__ __forceinline__ void wide_build_inv(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                               const double* rsrc, const WideAux& a, double gdt) {
+  const int ns = P.ns;
+  const bool isp = lane < ns;
+  (void)wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);
+  for (int k = 0; k < ns; ++k) {
+    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
+    int bi = lane;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi != k && isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
+    if (lane == 0) ww.piv[k] = bi;
+    __syncwarp();
+    const double pinv = 1.0 / ww.A[k][k];
+    __syncwarp();
+    if (isp) ww.A[k][lane] = (lane == k) ? pinv : ww.A[k][lane] * pinv;   // lane = column: scale the pivot row
+    __syncwarp();
+    if (isp && lane != k) {                                                  // lane = row: eliminate column k
+      const double f = ww.A[lane][k];
+#pragma unroll 4
+      for (int j = 0; j < ns; ++j) {
+        const double akj = ww.A[k][j];
+        ww.A[lane][j] = (j == k) ? -f * akj : fma(-f, akj, ww.A[lane][j]);
+      }
+    }
+    __syncwarp();
+  }
+  for (int k = ns - 1; k >= 0; --k) {   // undo the row exchanges as column exchanges, in reverse order
+    const int p = ww.piv[k];
+    if (p != k && isp) { const double tmpv = ww.A[lane][k]; ww.A[lane][k] = ww.A[lane][p]; ww.A[lane][p] = tmpv; }
+  }
+  __syncwarp();
+}
+
+// b <- W^{-1} b with the explicit inverse in ww.A (lane i holds b_i); scratch: ww.ws
+template <class WW>
+__device__ __forceinline__ double wide_invmul(WW& ww, int lane, int ns, double b) {
+  __syncwarp();
+  ww.ws[lane] = b;
+  __syncwarp();
+  double s = 0.0;
+  if (lane < ns) {
+#pragma unroll 6
+    for (int j = 0; j < ns; ++j) s = fma(ww.A[lane][j], ww.ws[j], s);
+  }
+  return s;
 }
 
 }  // namespace crnn

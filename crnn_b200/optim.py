@@ -72,11 +72,16 @@ class Optimiser:
     def __init__(self, *chain):
         self.chain = list(chain)
 
-    def update(self, p, g):
+    def apply(self, p, g):
+        """Flux.Optimise.apply!(o::Optimiser, x, Δ): the chain applied in order - lets Optimisers nest, e.g. the literal
+        `Flux.Optimiser(ExpDecay(...), ADAMW(...))` of case2/case2.jl:31-32 (ADAMW itself is an Optimiser)."""
         d = np.asarray(g, dtype=np.float64)
         for o in self.chain:
             d = o.apply(p, d)
-        p -= d
+        return d
+
+    def update(self, p, g):
+        p -= self.apply(p, g)
         return p
 
 

@@ -551,6 +551,40 @@ static void lu_solve(const double* A, const int* piv, int n, double* b) {
   }
 }
 
+/* KenCarp4 only (an algorithm the reference does not contain: every policy is ours).  Named switch
+ * crnn_oracle_set_kc4_inverse(1): W^{-1} is formed explicitly by in-place Gauss-Jordan elimination with partial pivoting
+ * and every "solve" is a mat-vec - what k_kencarp4_wide does (its ~20 simplified-Newton solves per factorisation are then
+ * free of dependent substitution chains).  Default: LU + substitution like the other steppers. */
+static int g_kc4_inverse = 0;
+void crnn_oracle_set_kc4_inverse(int on) { g_kc4_inverse = on; }
+int crnn_oracle_get_kc4_inverse(void) { return g_kc4_inverse; }
+static void kc_factor(double* A, int* piv, int n) {
+  if (!g_kc4_inverse) { lu_factor(A, piv, n); return; }
+  for (int k = 0; k < n; ++k) {
+    int p = k; double best = fabs(A[k * n + k]);
+    for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + k]) > best) { best = fabs(A[i * n + k]); p = i; }
+    piv[k] = p;
+    if (p != k) for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
+    const double pinv = 1.0 / A[k * n + k];
+    for (int j = 0; j < n; ++j) A[k * n + j] = (j == k) ? pinv : A[k * n + j] * pinv;
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = A[i * n + k];
+      for (int j = 0; j < n; ++j) A[i * n + j] = (j == k) ? -f * A[k * n + j] : fma(-f, A[k * n + j], A[i * n + j]);
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    const int p = piv[k];
+    if (p != k) for (int i = 0; i < n; ++i) { double t = A[i * n + k]; A[i * n + k] = A[i * n + p]; A[i * n + p] = t; }
+  }
+}
+static void kc_solve(const double* A, const int* piv, int n, double* b) {
+  if (!g_kc4_inverse) { lu_solve(A, piv, n, b); return; }
+  double x[MAXN];
+  for (int i = 0; i < n; ++i) { double s = 0.0; for (int j = 0; j < n; ++j) s = fma(A[i * n + j], b[j], s); x[i] = s; }
+  memcpy(b, x, sizeof(double) * n);
+}
+
 typedef struct {
   int retcode, n_saved;
   crnn_stats st;
@@ -856,7 +890,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
     jac_value(c, &kc0, Jm); res->st.n_jac++;
     for (int i = 0; i < n; ++i)
       for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - KC_G * dt * Jm[i * n + l];
-    lu_factor(LU, piv, n);
+    kc_factor(LU, piv, n);
     for (int i = 0; i < n; ++i) Z[0][i] = dt * F0[i];
     int newton_ok = 1, refreshed = 0;
     for (int s = 1; s < 6 && newton_ok; ++s) {
@@ -873,7 +907,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
           for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + KC_G * Z[s][i];
           rhs_value(c, t + KC_C[s] * dt, Yk, DZ, &kc); res->st.n_rhs++;
           for (int i = 0; i < n; ++i) DZ[i] = dt * DZ[i] - Z[s][i];
-          lu_solve(LU, piv, n, DZ);
+          kc_solve(LU, piv, n, DZ);
           double ndz = wrms(c, DZ, U, Yk);
           for (int i = 0; i < n; ++i) Z[s][i] += DZ[i];
           if (it > 1) {
@@ -895,7 +929,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
           jac_value(c, &kc, Jm); res->st.n_jac++;
           for (int i = 0; i < n; ++i)
             for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - KC_G * dt * Jm[i * n + l];
-          lu_factor(LU, piv, n);
+          kc_factor(LU, piv, n);
         }
       }
       if (!conv) newton_ok = 0;
@@ -909,7 +943,7 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
       e += (KC_G - KC_BHAT[5]) * Z[5][i];
       DZ[i] = e;
     }
-    lu_solve(LU, piv, n, DZ); /* smoothed estimate */
+    kc_solve(LU, piv, n, DZ); /* smoothed estimate */
     double EEst = wrms(c, DZ, U, Un);
     double q11, q = pi_q(c, EEst, qold, &q11);
     if (EEst <= 1.0) {

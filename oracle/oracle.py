@@ -65,6 +65,24 @@ def lib() -> C.CDLL:
     return _lib
 
 
+class kc4_inverse:
+    """Context manager for the oracle's named KenCarp4 switch: W^{-1} by Gauss-Jordan + mat-vec solves (the CUDA kernel's form)."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        L = lib()
+        L.crnn_oracle_get_kc4_inverse.restype = C.c_int
+        self.prev = L.crnn_oracle_get_kc4_inverse()
+        L.crnn_oracle_set_kc4_inverse(int(self.on))
+        return self
+
+    def __exit__(self, *exc):
+        lib().crnn_oracle_set_kc4_inverse(self.prev)
+        return False
+
+
 class shared_math:
     """Context manager for the oracle's named math switch: inside it log/exp/pow are the lean functions of
     crnn_b200/csrc/lean_math.h (the kernels' own, bit-identical on host and device); outside, the C library."""

@@ -40,5 +40,5 @@ def _oracle_lu_form(request):
         yield
         return
     from oracle import oracle
-    with oracle.lu_reciprocal(True), oracle.shared_math(True):
+    with oracle.lu_reciprocal(True), oracle.shared_math(True), oracle.kc4_inverse(True):
         yield

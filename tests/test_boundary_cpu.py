@@ -126,6 +126,18 @@ def test_shard_bounds_cover_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_optimiser_chains_nest_like_flux():
+    """case2/case2.jl:31-32 written literally: Flux.Optimiser(ExpDecay(...), ADAMW(...)) - ADAMW is itself an Optimiser"""
+    from crnn_b200 import optim
+    g = np.random.default_rng(0).standard_normal(7)
+    p1, p2 = np.ones(7), np.ones(7)
+    nested = optim.Optimiser(optim.ExpDecay(5e-3, 0.5, 500, 1e-4), optim.ADAMW(5e-3, (0.9, 0.999), 1e-6))
+    flat = optim.Optimiser(optim.ExpDecay(5e-3, 0.5, 500, 1e-4), *optim.ADAMW(5e-3, (0.9, 0.999), 1e-6).chain)
+    for _ in range(5):
+        nested.update(p1, g); flat.update(p2, g)
+    assert np.array_equal(p1, p2) and not np.array_equal(p1, np.ones(7))
+
+
 def test_optimisers_match_flux_formulas():
     """ADAMW = ADAM then decoupled weight decay."""
     p = np.array([1.0, -2.0]); g = np.array([0.5, 0.25])
@@ -233,9 +245,15 @@ def test_checkpoint_reader_writer_speak_the_reference_dialect(golden):
     c = ck.load("/root/reference/case2/checkpoint/mymodel.bson")
     with tempfile.TemporaryDirectory() as d:
         f = os.path.join(d, "resaved.bson")
-        ck.save(f, c["p"], c["iter"] + 1, opt=c["opt"], backrefs=c["doc"]["_backrefs"], l_loss_train=c["l_loss_train"], l_loss_val=c["l_loss_val"])
+        pnew = c["p"] + 1e-3
+        assert c["p_ref"] == 4        # in the reference's file p is a backref: the object that keys the ADAM state's IdDict
+        ck.save(f, pnew, c["iter"] + 1, opt=c["opt"], backrefs=c["doc"]["_backrefs"], p_ref=c["p_ref"],
+                l_loss_train=c["l_loss_train"], l_loss_val=c["l_loss_val"])
         c2 = ck.load(f)
-        assert np.array_equal(c2["p"], c["p"]) and c2["iter"] == c["iter"] + 1 and c2["opt"] == c["opt"]
+        assert np.array_equal(c2["p"], pnew) and c2["iter"] == c["iter"] + 1 and c2["opt"] == c["opt"]
+        # ... and it still is one after re-saving with new values: the optimiser state stays attached to the live p
+        assert c2["doc"]["p"] == {"tag": "backref", "ref": 4}
+        assert np.array_equal(np.asarray(ck.resolve(c2["doc"], c2["doc"]["_backrefs"][3])).reshape(-1), pnew)
         np.testing.assert_allclose(c2["l_loss_train"], c["l_loss_train"], rtol=0, atol=0)
 
 

@@ -109,3 +109,46 @@ def test_indexed_dataset_call_on_the_generic_kernel(engine, golden):
     b = engine.loss_grad_indexed(pb["model"], o, pb["seed"], ds, pb["yscale"], pb["loss_kind"], idx=idx, want_loss=True)
     assert np.array_equal(a["loss"], b["loss"]) and np.array_equal(a["grad_sum"], b["grad_sum"])
     ds.close()
+
+
+@pytest.mark.parametrize("name,N", [("case2", 512), ("robertson", 96), ("case1", 64)])
+def test_autotsit5_fast_path_specialised_kernel_plus_hand_over(engine, golden, name, N):
+    """AutoTsit5(Rosenbrock23) without forcing the generic kernel: the specialised Tsit5 kernel carries the AutoSwitch
+    monitor and hands the trajectories that would switch over to the composite kernel.  Same results as the oracle's
+    composite either way: case2 / case1 never switch (case2.jl:26 as written), the stiff Robertson CRNN always does."""
+    pb = make_problem(name, golden, N)
+    c = pb["case"]
+    o = c.opts(obs_idx=np.arange(c.ns), alg=ALG["auto"])
+    args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+    stiff = name == "robertson"
+    _compare(got, ref, rtol_state=1e-7 if stiff else 1e-9, rtol_loss=1e-7 if stiff else 1e-10, rtol_grad=1e-6 if stiff else 1e-8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    if stiff:
+        assert (got["stats"]["n_jac"] > 0).all()
+    else:
+        assert (got["stats"]["n_jac"] == 0).all()
+    # ragged + indexed dataset call through the same path
+    ds = engine.dataset(pb["u0"], pb["data"])
+    idx = np.random.default_rng(5).permutation(N)[:N // 3]
+    nsu = np.random.default_rng(6).integers(1, o.n_save + 1, size=idx.size).astype(np.int32)
+    a = engine.loss_grad_indexed(pb["model"], o, pb["seed"], ds, pb["yscale"], pb["loss_kind"], idx=idx, n_save_used=nsu, want_loss=True)
+    b = oracle.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"][idx], pb["data"][idx], pb["yscale"], pb["loss_kind"], n_save_used=nsu, n_threads=8)
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-7 if stiff else 1e-10)
+    np.testing.assert_allclose(a["grad_sum"], b["grad_sum"], rtol=1e-6 if stiff else 1e-8, atol=1e-9 * np.abs(b["grad_sum"]).max())
+    ds.close()
+
+
+def test_autotsit5_fast_path_mixed_batch(engine, golden):
+    """a batch in which SOME trajectories switch: the true Robertson mechanism's rates scaled down for half of the batch is
+    not expressible with shared weights, so mix by horizon instead - short horizons never reach the switch, long ones do"""
+    pb = make_problem("robertson", golden, 64)
+    c = pb["case"]
+    o = c.opts(obs_idx=np.arange(c.ns), alg=ALG["auto"])
+    nsu = np.where(np.arange(64) % 2 == 0, 2, 40).astype(np.int32)      # tspan = [0, tsteps[sample]] (rober_crnn.jl:125)
+    args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    got = engine.loss_grad_batch(*args, n_save_used=nsu, want_pred=True)
+    ref = oracle.loss_grad_batch(*args, n_save_used=nsu, want_pred=True, n_threads=8)
+    _compare(got, ref, rtol_state=1e-7, rtol_loss=1e-7, rtol_grad=1e-6)
+    assert np.array_equal(got["n_saved"], nsu)

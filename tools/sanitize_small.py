@@ -40,6 +40,25 @@ for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23, _a
 for smode in (_abi.SENS_INTERP_ADJOINT, _abi.SENS_DISCRETE_ADJOINT):
     eng.loss_grad_batch(m, cases.hychem_opts(alg=_abi.ALG_TSIT5, sens_mode=smode), seed, u0, pr["pred"] * 1.01, YS)
 done.append("hychem F2 all")
+# round 2: generic forward-sensitivity kernel (all three algorithms, F2 with 211 columns), datasets, particles
+os.environ["CRNN_B200_FORCE_GENERIC"] = "1"
+for name, alg in (("case2", _abi.ALG_AUTO_TSIT5_ROS23), ("robertson", _abi.ALG_ROSENBROCK23), ("case1", _abi.ALG_TSIT5)):
+    pb = make_problem(name, golden, min(N, 16))
+    o = pb["case"].opts(obs_idx=pb["opts"].obs_idx, alg=alg)
+    eng.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"], want_pred=True)
+os.environ["CRNN_B200_FORCE_GENERIC"] = "0"
+mh, sh = cases.hychem_model(cases.hychem_p(0, stiff=4.0), YS)
+for alg in (_abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23):
+    eng.loss_grad_batch(mh, cases.hychem_opts(alg=alg), sh, u0[:4], pr["pred"][:4] * 1.01, YS)
+done.append("generic forward sens")
+pb = make_problem("case2", golden, N)
+ds = eng.dataset(pb["u0"], pb["data"])
+eng.loss_grad_indexed(pb["model"], pb["opts"], pb["seed"], ds, pb["yscale"], pb["loss_kind"], idx=np.arange(N)[::-2].copy(), want_loss=True)
+ds.close(); done.append("dataset indexed")
+import cathode_problem as cp
+cpb = cp.make(3, seed=1)
+eng.loss_grad_particles(cpb["model"], cpb["opts"], cpb["weights"], cpb["seeds"], cpb["u0"], cpb["data"], cpb["yscale"], _abi.LOSS_MSE, tab_T=cpb["tab_T"])
+done.append("particles F5 + observable")
 ms = cases.synthetic_stiff_model()
 eng.solve_batch(ms, cases.synthetic_stiff_opts(), cases.synthetic_stiff_u0(N)); done.append("kencarp4 30-state")
 eng.close()
