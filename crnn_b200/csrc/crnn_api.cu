@@ -492,13 +492,15 @@ int crnn_debug_lean_math(crnn_handle* h, int32_t op, const double* x, const doub
   CK(cudaSetDevice(h->device));
   DevBuf bx, by, b2;
   CK(bx.reserve(n * sizeof(double))); CK(by.reserve(n * sizeof(double)));
-  CK(cudaMemcpy(bx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
-  if (op == 2) { CK(b2.reserve(n * sizeof(double))); CK(cudaMemcpy(b2.p, x2, n * sizeof(double), cudaMemcpyHostToDevice)); }
+  // same stream as the kernel: a synchronous cudaMemcpy from pageable memory may return before its DMA has landed, and
+  // s_compute (non-blocking) does not wait for the legacy default stream
+  CK(cudaMemcpyAsync(bx.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
+  if (op == 2) { CK(b2.reserve(n * sizeof(double))); CK(cudaMemcpyAsync(b2.p, x2, n * sizeof(double), cudaMemcpyHostToDevice, h->s_compute)); }
   k_lean_math<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(op, bx.as<double>(), b2.as<double>(), by.as<double>(), n);
   CK(cudaGetLastError());
   h->launches++;
+  CK(cudaMemcpyAsync(y, by.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
   CK(cudaStreamSynchronize(h->s_compute));
-  CK(cudaMemcpy(y, by.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   bx.release(); by.release(); b2.release();
   return CRNN_OK;
 }
