@@ -54,6 +54,15 @@ class COpts(C.Structure):
     ]
 
 
+class CTrainOpts(C.Structure):
+    _fields_ = [
+        ("p2vec_kind", C.c_int32), ("optimiser", C.c_int32), ("batch", C.c_int32), ("reserved", C.c_int32),
+        ("eta", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+        ("expdecay_eta", C.c_double), ("expdecay_decay", C.c_double), ("expdecay_clip", C.c_double),
+        ("expdecay_step", C.c_int64), ("grad_max", C.c_double),
+    ]
+
+
 class CStats(C.Structure):
     _fields_ = [
         ("n_accept", C.c_int32), ("n_reject", C.c_int32), ("n_rhs", C.c_int32), ("n_jac", C.c_int32),
@@ -72,7 +81,7 @@ EXPORTS = (
     "crnn_create", "crnn_destroy", "crnn_last_error", "crnn_version", "crnn_launch_count",
     "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_profile_begin", "crnn_profile_end", "crnn_copy_grad_each",
     "crnn_debug_lean_math", "crnn_create_multi", "crnn_device_count", "crnn_dataset_create", "crnn_dataset_destroy",
-    "crnn_dataset_size", "crnn_loss_grad_indexed", "crnn_loss_grad_particles",
+    "crnn_dataset_size", "crnn_loss_grad_indexed", "crnn_loss_grad_particles", "crnn_train_steps",
 )
 
 _lib = None
@@ -127,6 +136,10 @@ def load_library(path: str | None = None) -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p]
     lib.crnn_loss_grad_particles.restype = C.c_int
+    lib.crnn_train_steps.argtypes = [
+        C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.POINTER(CTrainOpts), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.crnn_train_steps.restype = C.c_int
     lib.crnn_solve_batch.argtypes = [
         C.c_void_p, C.POINTER(CModel), C.POINTER(COpts), C.c_void_p, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -15,7 +15,10 @@ namespace crnn_host {
                                                     const HostIO&, int64_t);                                \
   extern template int loss_grad_impl<Cfg<NS_, NR_, K_>>(crnn_handle*, const crnn_model*, const crnn_opts*,  \
                                                         const double*, int, const double*, int,             \
-                                                        const HostIO&, int64_t, double*, const AutoHook*);
+                                                        const HostIO&, int64_t, double*, const AutoHook*);     \
+  extern template int train_impl<Cfg<NS_, NR_, K_>>(crnn_handle*, const crnn_model*, const crnn_opts*,      \
+                                                    const crnn_train_opts*, const crnn_dataset*, const int64_t*, int64_t, \
+                                                    const double*, int32_t, double*, double*, double*, double*);
 CRNN_FOR_EACH_CFG(X)
 #undef X
 }  // namespace crnn_host
@@ -547,7 +550,7 @@ void crnn_destroy(crnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&h->cfg, &h->seed, &h->desc, &h->ctr, &h->partial, &h->d_grad_each, &h->d_grad_sum, &h->d_grad_out, &h->adj_scratch,
-                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats, &h->d_idx, &h->d_nsu_ix, &h->d_result, &h->cfg2, &h->auto_sel};
+                    &h->d_loss, &h->d_nsaved, &h->d_ret, &h->d_stats, &h->d_idx, &h->d_nsu_ix, &h->d_result, &h->cfg2, &h->auto_sel, &h->train};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < kPipe; ++s) {
     DevBuf* sb[] = {&h->d_u0[s], &h->d_nsu[s], &h->d_data[s], &h->d_pred[s]};
@@ -616,6 +619,31 @@ int crnn_profile_end(crnn_handle* h, double* total_ms, int64_t* n_launches) {
   if (n_launches) *n_launches = (int64_t)h->prof_used + nk;
   h->prof_used = 0;
   return CRNN_OK;
+}
+
+int crnn_train_steps(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const crnn_train_opts* t,
+                     const crnn_dataset* ds, const int64_t* order, int64_t n_steps, const double* yscale,
+                     int32_t loss_kind, double* p, double* opt_state, double* step_loss, double* step_gnorm) {
+  if (!h) return CRNN_ERR_BAD_ARG;
+  if (!h->kids.empty()) return fail(h, CRNN_ERR_UNSUPPORTED, "crnn_train_steps needs a single-device handle");
+  if (!m || !o || !t || !ds || !p || !opt_state || (n_steps > 0 && !order)) return fail(h, CRNN_ERR_BAD_ARG, "crnn_train_steps: null argument");
+  if (ds->owner != h) return fail(h, CRNN_ERR_BAD_ARG, "dataset does not belong to this handle");
+  if (m->n_state != ds->n_state || o->n_obs != ds->n_obs || o->n_save != ds->n_save)
+    return fail(h, CRNN_ERR_BAD_ARG, "model / opts do not match the dataset's (n_state, n_obs, n_save)");
+  if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG) return fail(h, CRNN_ERR_UNSUPPORTED, "loss_kind");
+  if (loss_kind == CRNN_LOSS_MAE_SCALED && !yscale) return fail(h, CRNN_ERR_BAD_ARG, "null yscale");
+  {  // validate() wants weight pointers: borrow a zero block
+    std::vector<double> zw((size_t)m->n_reac * (m->n_in + 1 + m->n_species), 0.0);
+    crnn_model mm = *m; mm.w_in = zw.data(); mm.w_b = zw.data(); mm.w_out = zw.data();
+    int rc = validate(h, &mm, o, n_steps);
+    if (rc) return rc;
+  }
+#define X(NS_, NR_, K_)                                                              \
+  if (m->n_species == NS_ && m->n_reac == NR_ && m->rhs_kind == K_)                  \
+    return train_impl<Cfg<NS_, NR_, K_>>(h, m, o, t, ds, order, n_steps, yscale, loss_kind, p, opt_state, step_loss, step_gnorm);
+  CRNN_FOR_EACH_CFG(X)
+#undef X
+  return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop needs a model with a specialised kernel");
 }
 
 int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* weights,

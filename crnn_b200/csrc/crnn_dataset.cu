@@ -16,13 +16,6 @@
 
 #include "crnn_host.cuh"
 
-struct crnn_dataset {
-  crnn_handle* owner = nullptr;
-  int n_state = 0, n_obs = 0, n_save = 0;
-  int64_t N = 0;
-  std::vector<int64_t> lo;       // shard bounds, size n_dev + 1
-  std::vector<DevBuf> u0, data;  // per device
-};
 
 namespace {
 

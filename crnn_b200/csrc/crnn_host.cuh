@@ -23,6 +23,7 @@
 #include "kernel_rosenbrock23.cuh"
 #include "kernel_rosenbrock23_sens.cuh"
 #include "kernel_auto_value.cuh"
+#include "kernel_train.cuh"
 
 using namespace crnn;
 
@@ -79,6 +80,8 @@ struct crnn_handle {
   DevBuf d_grad_each, d_grad_sum, d_grad_out, adj_scratch;
   // AutoTsit5 fast path: config blob of the generic composite kernel, hand-over lists (one per work-queue slot)
   DevBuf cfg2, auto_sel;
+  // on-device training loop: p | optimiser state | ModelP | seed rows | descriptors | order | per-step loss / gnorm
+  DevBuf train;
   // device-resident dataset path (crnn_loss_grad_indexed): row indices, n_save_used, [sum loss, n finite, grad(np)]
   DevBuf d_idx, d_nsu_ix, d_result;
   // multi-device parent (crnn_create_multi): the children own all per-device state, the parent launches nothing itself
@@ -88,6 +91,14 @@ struct crnn_handle {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+};
+
+struct crnn_dataset {
+  crnn_handle* owner = nullptr;
+  int n_state = 0, n_obs = 0, n_save = 0;
+  int64_t N = 0;
+  std::vector<int64_t> lo;       // shard bounds, size n_dev + 1
+  std::vector<DevBuf> u0, data;  // per device
 };
 
 #define CK(call)                                                                               \
@@ -300,7 +311,7 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
         ProfScope prof(h, st);
         kern<<<blocks, WARPS_A * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
                                               b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue,
-                                              b.in_idx, sel, cnt);
+                                              b.in_idx, sel, cnt, nullptr);
         CK(cudaGetLastError());
         h->launches++;
       }
@@ -349,7 +360,7 @@ int launch_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, int nc
   ProfScope prof(h, st);
   kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
                                       b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx,
-                                      nullptr, nullptr);
+                                      nullptr, nullptr, nullptr);
   CK(cudaGetLastError());
   h->launches++;
   return CRNN_OK;
@@ -653,6 +664,91 @@ int loss_grad_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
     if (hook) return fail(h, CRNN_ERR_UNSUPPORTED, "the AutoSwitch fast path needs structured seed columns");
     return ct == 1 ? launch_sens<C, 1, false>(h, mp, sp, ncol, b, s) : launch_sens<C, 2, false>(h, mp, sp, ncol, b, s);
   });
+}
+
+// The on-device training loop (kernel_train.cuh): n_steps optimiser steps of `batch` experiments each, picked
+// by `order` from a device-resident dataset; p and the optimiser state are read from and written back to host memory once.
+template <class C>
+int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const crnn_train_opts* t, const crnn_dataset* ds,
+               const int64_t* order, int64_t n_steps, const double* yscale, int32_t loss_kind, double* p, double* opt_state,
+               double* step_loss, double* step_gnorm) {
+  if constexpr (!(C::NS == 6 && C::NR == 3 && C::KIND == 1)) {
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has a device p2vec for case2 (6 species, 3 reactions, F1) only");
+  } else {
+    constexpr int NP = C::NR * (C::NS + 2) + 1;   // 25
+    if (t->p2vec_kind != 2) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind: 2 (case2/case2.jl:91-99) is the one built");
+    if (o->alg != CRNN_ALG_TSIT5 || o->sens_mode != CRNN_SENS_FORWARD)
+      return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop runs Tsit5 with forward sensitivities");
+    if (t->batch < 1 || n_steps < 0) return fail(h, CRNN_ERR_BAD_ARG, "bad batch / n_steps");
+    if (m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case2 has no out_scale");
+    const int batch = t->batch;
+    for (int64_t q = 0; q < n_steps * batch; ++q)
+      if (order[q] < 0 || order[q] >= ds->N) return fail(h, CRNN_ERR_BAD_ARG, "order: dataset row index out of range");
+    ModelP<C> mp{}; SolveP<C> sp; Packed pk;
+    crnn_model mm = *m;
+    std::vector<double> zw(C::NW, 0.0);   // pack() wants weight pointers; the real weights come from the device p2vec
+    mm.w_in = zw.data(); mm.w_b = zw.data(); mm.w_out = zw.data();
+    int rc = pack<C>(h, &mm, o, yscale, loss_kind, mp, sp, pk);
+    if (rc) return rc;
+    const int ncol = NP + 1;
+    if (o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) sp.norm_cnt = (double)C::N * ncol;
+    if (o->err_norm_includes_sens) sp.eig_cnt = (double)C::N * ncol;
+    cudaStream_t st = h->s_compute;
+    CK(cudaSetDevice(h->device));
+    rc = upload_cfg<C>(h, o, pk, sp, st);
+    if (rc) return rc;
+    // device block: p[NP] | state[2NP+4] | ModelP | rows[2*NR*32] | desc[32] | loss_sum[2] | grad_sum[NP] | order | step_loss | step_gnorm
+    const size_t n_mp = (sizeof(ModelP<C>) + 7) / 8, n_rows = 2 * C::NR * 32, n_desc = 3 * 32;
+    const size_t n_order = (size_t)n_steps * batch;
+    const size_t total = NP + (2 * NP + 4) + n_mp + n_rows + n_desc + 2 + NP + n_order + 2 * (size_t)n_steps + 8;
+    CK(h->train.reserve(total * sizeof(double)));
+    double* d_p = h->train.as<double>(); double* d_st = d_p + NP;
+    ModelP<C>* d_mp = reinterpret_cast<ModelP<C>*>(d_st + 2 * NP + 4);
+    double* d_rows = reinterpret_cast<double*>(d_mp) + n_mp; R1Desc* d_desc = reinterpret_cast<R1Desc*>(d_rows + n_rows);
+    double* d_lsum = d_rows + n_rows + n_desc; double* d_gsum = d_lsum + 2;
+    long long* d_order = reinterpret_cast<long long*>(d_gsum + NP);
+    double* d_sloss = reinterpret_cast<double*>(d_order + n_order); double* d_sgn = d_sloss + n_steps;
+    CK(cudaMemcpyAsync(d_p, p, NP * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_st, opt_state, (2 * NP + 4) * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n_order) CK(cudaMemcpyAsync(d_order, order, n_order * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(h->d_loss.reserve(batch * sizeof(double)));
+    CK(h->d_nsaved.reserve(batch * sizeof(int)));
+    CK(h->d_ret.reserve(batch * sizeof(int)));
+    CK(h->d_grad_each.reserve((size_t)batch * NP * sizeof(double)));
+    h->last_grad_np = -1; h->last_grad_n = -1;
+    TrainP T{};
+    T.optimiser = t->optimiser; T.np = NP; T.eta = t->eta; T.beta1 = t->beta1; T.beta2 = t->beta2; T.eps = t->eps;
+    T.weight_decay = t->weight_decay; T.expdecay_decay = t->expdecay_decay; T.expdecay_clip = t->expdecay_clip;
+    T.expdecay_step = t->expdecay_eta > 0 ? t->expdecay_step : 0; T.grad_max = t->grad_max;
+    constexpr int WARPS = 8;
+    auto kern = k_tsit5_sens<C, 1, WARPS, 2, true, 1, false, true>;
+    const size_t smem = sizeof(SensSmem<C, 1, true, 1>) + WARPS * sizeof(WarpBuf<C, 1>);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)std::min<long long>(2LL * h->num_sms, (batch + WARPS - 1) / WARPS);
+    unsigned long long* queue = h->ctr.as<unsigned long long>();
+    const int nb_red = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (batch + 63) / 64));
+    CK(h->partial.reserve((size_t)nb_red * NP * sizeof(double)));
+    for (int64_t s = 0; s < n_steps; ++s) {
+      k_p2vec_case2<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->gas_R, d_mp, d_rows, d_desc);
+      CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+      kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nullptr, batch,
+                                          ds->data[0].as<double>(), h->d_loss.as<double>(), h->d_grad_each.as<double>(), nullptr,
+                                          h->d_nsaved.as<int>(), h->d_ret.as<int>(), nullptr, queue, d_order + s * batch,
+                                          nullptr, nullptr, d_mp);
+      k_grad_reduce<<<nb_red, 256, 0, st>>>(h->d_grad_each.as<double>(), batch, NP, h->partial.as<double>(), d_gsum,
+                                            reinterpret_cast<unsigned int*>(h->ctr.as<unsigned long long>() + 1));
+      k_train_loss_sum<<<1, 256, 0, st>>>(h->d_loss.as<double>(), batch, d_lsum);
+      k_optim_step<<<1, 256, 0, st>>>(T, d_gsum, d_lsum, d_p, d_st, step_loss ? d_sloss : nullptr, step_gnorm ? d_sgn : nullptr, s);
+      h->launches += 5;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p, d_p, NP * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(opt_state, d_st, (2 * NP + 4) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (step_loss && n_steps) CK(cudaMemcpyAsync(step_loss, d_sloss, n_steps * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (step_gnorm && n_steps) CK(cudaMemcpyAsync(step_gnorm, d_sgn, n_steps * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CRNN_OK;
+  }
 }
 
 }  // namespace crnn_host

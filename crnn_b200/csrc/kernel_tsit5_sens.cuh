@@ -61,6 +61,7 @@ struct alignas(16) SensSmem {
   double abstol[C::N], reltol[C::N];
   double dense_r[7][4];  // Tsit5 dense-output polynomial coefficients (lane j takes b_j)
   int row2obs[C::N];
+  ModelP<C> mpw;         // DEVW: the model read from DEVICE memory (on-device training loop, kernel_train.cuh)
 };
 
 // Per-warp working set.  K holds the seven stage derivatives of every column.  Inside a
@@ -92,7 +93,9 @@ struct alignas(16) WarpBuf {
 // on the trained case2 CRNN - this IS the composite algorithm, at this kernel's speed; a trajectory whose counter asks for
 // Rosenbrock23 is abandoned and its index appended to sel_list, and the host re-runs exactly those through the generic
 // composite kernel (kernel_gen_sens.cuh), which overwrites their outputs.
-template <class C, int CT, int WARPS, int MINB, bool R1, int WPT = 1, bool AUTO = false>
+// DEVW = true: weights come from device memory (mp_dev, written by a p2vec kernel of the on-device training loop) instead
+// of the by-value kernel parameter; they are staged in shared memory, everything else is unchanged.
+template <class C, int CT, int WARPS, int MINB, bool R1, int WPT = 1, bool AUTO = false, bool DEVW = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ SolveP<C> sp,
              const double* __restrict__ seed_dev, const R1Desc* __restrict__ desc_dev, int ncol,
@@ -101,7 +104,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
              double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
              crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
              const long long* __restrict__ in_idx, long long* __restrict__ sel_list = nullptr,
-             unsigned int* __restrict__ sel_count = nullptr) {
+             unsigned int* __restrict__ sel_count = nullptr, const ModelP<C>* __restrict__ mp_dev = nullptr) {
   static_assert(!AUTO || WPT == 1, "the AutoSwitch monitor is built for one warp per trajectory");
   // in_idx (or NULL): trajectory `traj` of this call reads u0 / data of dataset row in_idx[traj] (crnn_loss_grad_indexed);
   // every output stays at position traj
@@ -140,8 +143,14 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
   };
 
   for (int q = threadIdx.x; q < (R1 ? 2 * NR : NW) * 32 * CT * WPT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
-  for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = mp.w_in[q];
-  for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = mp.w_b[q];
+  if (DEVW) {
+    for (int q = threadIdx.x; q < (int)(sizeof(ModelP<C>) / sizeof(double)); q += blockDim.x)
+      reinterpret_cast<double*>(&sm.mpw)[q] = reinterpret_cast<const double*>(mp_dev)[q];
+    __syncthreads();
+  }
+  const ModelP<C>& M = DEVW ? sm.mpw : mp;   // compile-time choice: shared-memory loads or constant-bank operands
+  for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = M.w_in[q];
+  for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = M.w_b[q];
   for (int q = threadIdx.x; q < N; q += blockDim.x) {
     sm.inv_ys[q] = sp.inv_yscale[q];
     sm.row2obs[q] = sp.row2obs[q];
@@ -195,7 +204,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
     // KO: RHS output / scratch
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
     double xT = 0.0, mybT = 0.0;
-    if (C::KIND == 1) xT = -1.0 / (mp.gas_R * __ldg(u0t + NS));
+    if (C::KIND == 1) xT = -1.0 / (M.gas_R * __ldg(u0t + NS));
     if (lane < NR) {
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
@@ -296,8 +305,8 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
         gsync();
         if (wig == 0 && lane < NS) {
           const double yi = gb.y[lane];
-          const double uc = clampd(yi, mp.lb, mp.ub);
-          const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
+          const double uc = clampd(yi, M.lb, M.ub);
+          const bool inside = (yi >= M.lb) && (yi <= M.ub);
           gb.x[lane] = lean_log(uc);
           gb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
@@ -326,7 +335,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             for (int j = 0; j < NR; ++j) {
               double zd = R1 ? fma(sm.seed[j][lc], xin, sm.seed[NR + j][lc]) : sm.seed[NIN * NR + j][lc];
 #pragma unroll
-              for (int i = 0; i < NS; ++i) zd = fma(mp.w_in[i + NIN * j], sd[i], zd);
+              for (int i = 0; i < NS; ++i) zd = fma(M.w_in[i + NIN * j], sd[i], zd);
               if (!R1) {
 #pragma unroll
                 for (int i = 0; i < NS; ++i) zd = fma(sm.seed[i + NIN * j][lc], gb.x[i], zd);
@@ -340,7 +349,7 @@ k_tsit5_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ Solve
             for (int i = 0; i < NS; ++i) {
               double s = 0.0;
 #pragma unroll
-              for (int j = 0; j < NR; ++j) s = fma(mp.w_out[i + NS * j], q[j], s);
+              for (int j = 0; j < NR; ++j) s = fma(M.w_out[i + NS * j], q[j], s);
               if (!R1) {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) s = fma(sm.seed[NIN * NR + NR + i + NS * j][lc], r[j], s);

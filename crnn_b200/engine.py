@@ -299,6 +299,41 @@ def _particles(self, model: CRNNModel, opts: SolveOpts, weights, seeds, u0, data
 Engine.loss_grad_particles = _particles
 
 
+def _train_steps(self, model: CRNNModel, opts: SolveOpts, ds: Dataset, order, yscale, p, opt_state=None,
+                 loss_kind=_abi.LOSS_MAE_SCALED, p2vec_kind=2, optimiser="adam", batch=1, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, expdecay=None, grad_max=None):
+    """`crnn_train_steps`: the scripts' epoch loop (case2/case2.jl:192-198) entirely on the device - p2vec, solve +
+    forward sensitivities, gradient reduction and the Flux optimiser chain enqueued back to back, nothing returning to the
+    host between optimiser steps.  `order` [n_steps * batch] dataset rows (the host's randperm), `expdecay` =
+    (eta, decay, step, clip) or None, `opt_state` [2 np + 4] from a previous call (None: fresh).
+    -> dict(p, opt_state, step_loss [n_steps], step_gnorm [n_steps])."""
+    cm, k1 = model.to_c()
+    co, k2 = opts.to_c(model.n_state, False)
+    order = np.ascontiguousarray(order, dtype=np.int64).reshape(-1)
+    if order.size % batch:
+        raise ValueError("order must hold n_steps * batch dataset rows")
+    n_steps = order.size // batch
+    p = np.array(p, dtype=np.float64).reshape(-1)
+    n_p = p.size
+    ed = expdecay or (0.0, 1.0, 0, 0.0)
+    if opt_state is None:
+        opt_state = np.concatenate([np.zeros(2 * n_p), [beta[0], beta[1], ed[0], 0.0]])
+    opt_state = np.array(opt_state, dtype=np.float64).reshape(-1)
+    if opt_state.size != 2 * n_p + 4:
+        raise ValueError("opt_state must be [2*np + 4]")
+    t = _abi.CTrainOpts(int(p2vec_kind), {"adam": 0, "nadam": 1}[optimiser], int(batch), 0, eta, beta[0], beta[1], eps, weight_decay,
+                        ed[0], ed[1], ed[3], int(ed[2]), 0.0 if grad_max is None else float(grad_max))
+    ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (opts.n_obs(model.n_state),), "yscale")
+    sl, sg = np.empty(n_steps), np.empty(n_steps)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    self._check(self._lib.crnn_train_steps(self._h, C.byref(cm), C.byref(co), C.byref(t), ds._d, hp(order), n_steps, hp(ys),
+                                           int(loss_kind), hp(p), hp(opt_state), hp(sl), hp(sg)))
+    return dict(p=p, opt_state=opt_state, step_loss=sl, step_gnorm=sg)
+
+
+Engine.train_steps = _train_steps
+
+
 def stats_from_torch(stats_u8) -> np.ndarray:
     """uint8 [N, 32] CUDA tensor of crnn_stats -> numpy structured array."""
     return stats_u8.cpu().numpy().view(STATS_DTYPE).reshape(-1)

@@ -103,6 +103,30 @@ class CRNNProblem:
         return p, history
 
 
+    def train_on_device(self, p, n_epoch, n_exp_train, rng=None, batch=1, **optimiser):
+        """The same epoch loop with every optimiser step ON the device (`crnn_train_steps`): one C call per epoch, the
+        visiting order `randperm(n_exp_train)` (case2/case2.jl:194) drawn here.  `optimiser`: Engine.train_steps keywords
+        (optimiser, eta, beta, weight_decay, expdecay, grad_max).  -> (p, history) like `train`."""
+        rng = rng or np.random.default_rng(0)
+        p = np.array(p, dtype=np.float64)
+        model, _ = self.case.model(p, self.out_scale)
+        state, history = None, []
+        n_steps = n_exp_train // batch
+        for epoch in range(n_epoch):
+            order = rng.permutation(n_exp_train)[:n_steps * batch]
+            r = self.engine.train_steps(model, self.opts, self.dataset, order, self.yscale, p, state, self.case.loss_kind,
+                                        batch=batch, **optimiser)
+            p, state = r["p"], r["opt_state"]
+            model, seed = self.case.model(p, self.out_scale)
+            losses = self.engine.loss_grad_indexed(model, self.opts, seed, self.dataset, self.yscale,
+                                                   self.case.loss_kind, want_loss=True)["loss"]
+            n_exp = self.u0_list.shape[0]
+            history.append((float(np.mean(losses[:n_exp_train])),
+                            float(np.mean(losses[n_exp_train:])) if n_exp > n_exp_train else float("nan"),
+                            float(np.mean(r["step_gnorm"]))))
+        return p, history
+
+
 def save_checkpoint(path, p, history, iter_=None):
     """`@save "./checkpoint/mymodel.bson" p opt l_loss_train l_loss_val iter` (case2/case2.jl:178) for a `train` history
     (list of (loss_train, loss_val, grad_norm)); see crnn_b200/checkpoint.py for what is and is not written."""

@@ -261,6 +261,37 @@ int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts*
                            const double* yscale, int32_t loss_kind, double* loss_sum, double* grad_sum, double* loss,
                            int32_t* n_saved, int32_t* retcode, crnn_stats* stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * On-device training loop: the scripts' epoch loop
+ *     for i_exp in randperm(n_exp_train); grad = ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p); update!(opt, p, grad); end
+ * (case2/case2.jl:192-198) with NOTHING returning to the host between optimiser steps: a p2vec kernel (the script's own
+ * map), the forward-sensitivity kernel reading its weights from device memory, the gradient reduction and Flux's
+ * ExpDecay -> ADAM / NADAM -> WeightDecay chain (case2.jl:31-32, case3.jl:20, rober_crnn.jl:19) incl. the 2-norm clip
+ * (rober_crnn.jl:220-223) are enqueued back to back.  The host supplies the visiting order (its own randperm).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct crnn_train_opts {
+  int32_t p2vec_kind;   /* which script's p2vec runs on the device: 2 = case2/case2.jl:91-99 (the one built) */
+  int32_t optimiser;    /* 0 ADAM (+ weight_decay = ADAMW), 1 NADAM */
+  int32_t batch;        /* experiments per optimiser step (the scripts: 1) */
+  int32_t reserved;
+  double eta, beta1, beta2, eps, weight_decay;
+  double expdecay_eta;  /* > 0: a Flux.ExpDecay link before ADAM (case2.jl:31); its running eta lives in opt_state */
+  double expdecay_decay, expdecay_clip;
+  int64_t expdecay_step;
+  double grad_max;      /* > 0: clip the gradient's 2-norm (rober_crnn.jl:29,221) */
+} crnn_train_opts;
+
+/* n_steps optimiser steps; step s uses dataset rows order[s*batch .. (s+1)*batch).  Single-device handle, Tsit5 +
+ * forward sensitivities.
+ *   m          dimensions, clamps and gas_R of the model (weight pointers ignored: the device p2vec produces them)
+ *   p          [np] in/out
+ *   opt_state  [2*np + 4] in/out: ADAM m, v, beta1^t, beta2^t, ExpDecay's current eta and count
+ *              (a fresh run: zeros, beta1, beta2, expdecay_eta, 0)
+ *   step_loss, step_gnorm  [n_steps] or NULL: mean loss and gradient norm (before clipping) of every step */
+int crnn_train_steps(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const crnn_train_opts* t,
+                     const crnn_dataset* ds, const int64_t* order, int64_t n_steps, const double* yscale,
+                     int32_t loss_kind, double* p, double* opt_state, double* step_loss, double* step_gnorm);
+
 /* Parameter-batched loss + gradient ("particles"): P parameter sets x E experiments in ONE launch, trajectory (p, e)
  * integrating experiment e with the weights of particle p - the loop `for j = 1:size(p)[1] ... ForwardDiff.gradient`
  * of Cathode_NCM333_UQ/src_333/network.jl:222-260 (100 SVGD particles x 5 data sets, sequential there).

@@ -323,6 +323,8 @@ def test_julia_shim_structs_follow_the_header():
 
     assert jl_fields("CModel") == c_fields("crnn_model")
     assert jl_fields("COpts") == c_fields("crnn_opts")
+    assert jl_fields("CTrainOpts") == c_fields("crnn_train_opts")
+    assert [n for n, _ in _abi.CTrainOpts._fields_] == [n for n, _ in c_fields("crnn_train_opts")]
     called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", jl))
     assert called and called <= set(_abi.EXPORTS), called - set(_abi.EXPORTS)
     assert {"crnn_create", "crnn_destroy", "crnn_solve_batch", "crnn_loss_grad_batch", "crnn_last_error"} <= called

@@ -44,6 +44,85 @@ def test_case2_training_loop_descends_like_the_reference(engine, golden):
     np.testing.assert_allclose(grad_b, np.mean(grads, axis=0), rtol=1e-9, atol=1e-12)
 
 
+def _case2_problem(engine, n_exp=30, seed=1234):
+    c = cases.CASES["case2"]
+    u0 = synth.make_u0("case2", n_exp, seed=seed)
+    truth = engine.solve_batch(cases.true_model_case2(), c.opts(obs_idx=np.arange(c.ns), pred_clamp=(-np.inf, np.inf)), u0)
+    data = synth.noisy_targets(truth["pred"], 0.05)
+    prob = CRNNProblem("case2", u0, data, synth.yscale_from(data, c.lb), engine=engine)
+    g = np.random.default_rng(seed)
+    p = g.standard_normal(c.n_p) * 0.1
+    p[:c.nr] += 0.8
+    p[c.nr * (c.ns + 1):c.nr * (c.ns + 2)] += 0.8
+    p[-1] = 0.1
+    return prob, p, g
+
+
+@pytest.mark.parametrize("variant", ["expdecay_adamw_batch1", "nadam_clip_batch4"])
+def test_on_device_training_loop_equals_the_host_loop(engine, variant):
+    """crnn_train_steps (p2vec kernel -> sensitivity kernel -> reduction -> Flux chain, nothing returning to the host
+    between steps) against the same steps taken one C call at a time with the host mirror of Flux's optimisers
+    (case2/case2.jl:31-32,192-198; rober_crnn.jl:220-223 for the clip; case3.jl:20 for NADAM)."""
+    prob, p0, g = _case2_problem(engine)
+    n_train = 20
+    if variant == "expdecay_adamw_batch1":
+        batch, n_steps, grad_max = 1, 60, None
+        opt = optim.Optimiser(optim.ExpDecay(5e-3, 0.5, 25, 1e-4), optim.ADAMW(0.005, (0.9, 0.999), 1e-6))
+        kw = dict(optimiser="adam", eta=0.005, beta=(0.9, 0.999), weight_decay=1e-6, expdecay=(5e-3, 0.5, 25, 1e-4))
+    else:
+        batch, n_steps, grad_max = 4, 15, 0.05
+        opt = optim.Optimiser(optim.NADAM(0.002, (0.9, 0.999)))
+        kw = dict(optimiser="nadam", eta=0.002, beta=(0.9, 0.999), grad_max=grad_max)
+    order = np.concatenate([g.permutation(n_train) for _ in range(-(-n_steps * batch // n_train))])[:n_steps * batch]
+    model, _ = prob.case.model(p0)
+    adam = opt.chain[-1].chain[0] if variant == "expdecay_adamw_batch1" else opt.chain[0]
+    # (1) every device step against the host mirror taking the same step FROM THE SAME p AND STATE (a free-running
+    # comparison is not meaningful beyond ~20 steps: the adaptive solver's accept / reject decisions make loss(p)
+    # piecewise smooth, a last-bit difference in p becomes 1e-8 in the gradient at a flipped decision and ADAM amplifies it)
+    p, st = p0.copy(), None
+    gn_seen = []
+    for s in range(n_steps):
+        idx = order[s * batch:(s + 1) * batch]
+        loss, grad = prob.loss_grad(p, idx)
+        grad, gn = optim.clip_by_norm(grad, grad_max) if grad_max is not None else (grad, float(np.linalg.norm(grad)))
+        gn_seen.append(gn)
+        p_host = p.copy()
+        opt.update(p_host, grad)
+        r = engine.train_steps(model, prob.opts, prob.dataset, idx, prob.yscale, p, st, prob.case.loss_kind, batch=batch, **kw)
+        np.testing.assert_allclose(r["step_loss"][0], loss, rtol=1e-13)
+        np.testing.assert_allclose(r["step_gnorm"][0], gn, rtol=1e-13)
+        np.testing.assert_allclose(r["p"], p_host, rtol=1e-12, atol=1e-15, err_msg=f"step {s}")
+        p, st = r["p"], r["opt_state"]
+        n_p = p.size                                          # the host mirror continues from the device's state
+        np.testing.assert_allclose(st[:n_p], adam.m, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(st[n_p:2 * n_p], adam.v, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(st[2 * n_p:2 * n_p + 2], adam.bp, rtol=1e-13)
+        adam.m, adam.v = st[:n_p].copy(), st[n_p:2 * n_p].copy()
+        if variant == "expdecay_adamw_batch1":
+            assert st[2 * n_p + 2] == opt.chain[0].eta and st[2 * n_p + 3] == opt.chain[0].count
+    assert not np.allclose(p, p0, rtol=1e-3)
+    if variant == "expdecay_adamw_batch1":
+        assert opt.chain[0].eta == 5e-3 * 0.25               # two decays happened
+    else:
+        assert max(gn_seen) > grad_max                       # the clip was active
+    # (2) all steps in ONE call (and in two calls carrying the state) = the step-by-step run, bit for bit
+    r_all = engine.train_steps(model, prob.opts, prob.dataset, order, prob.yscale, p0, None, prob.case.loss_kind, batch=batch, **kw)
+    h = (n_steps // 2) * batch
+    r1 = engine.train_steps(model, prob.opts, prob.dataset, order[:h], prob.yscale, p0, None, prob.case.loss_kind, batch=batch, **kw)
+    r2 = engine.train_steps(model, prob.opts, prob.dataset, order[h:], prob.yscale, r1["p"], r1["opt_state"], prob.case.loss_kind,
+                            batch=batch, **kw)
+    assert np.array_equal(r_all["p"], p) and np.array_equal(r2["p"], p) and np.array_equal(r_all["opt_state"], st)
+    assert np.array_equal(np.concatenate([r1["step_loss"], r2["step_loss"]]), r_all["step_loss"])
+
+
+def test_on_device_epochs_descend(engine):
+    prob, p0, g = _case2_problem(engine)
+    p_end, hist = prob.train_on_device(p0, n_epoch=30, n_exp_train=20, rng=g, optimiser="adam", eta=0.005, weight_decay=1e-6,
+                                       expdecay=(5e-3, 0.5, 500 * 20, 1e-4))
+    assert np.isfinite([h[0] for h in hist]).all()
+    assert hist[-1][0] < 0.6 * hist[0][0] and hist[-1][1] < 0.6 * hist[0][1], (hist[0], hist[-1])
+
+
 def test_hychem_training_loop_with_the_adjoint_gradient(engine):
     """HyChem/crnn_pyrolysis_mass.jl's loop (:197-212) on the engine: F2 RHS, 211 parameters, random time truncation
     `sample = rand(batch_size:ntotal)`, gradient clipping at 10, ADAMW(5e-3) — with the gradient from the discrete
