@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libcrnn_b200.so")
 
 # enums (include/crnn_b200.h)
 RHS_F0, RHS_F1, RHS_F2, RHS_F5 = 0, 1, 2, 3
-ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4, ALG_AUTO_TSIT5_ROS23 = 0, 1, 2, 3
+ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4, ALG_AUTO_TSIT5_ROS23, ALG_TRBDF2, ALG_AUTO_TSIT5_TRBDF2 = 0, 1, 2, 3, 4, 5
 SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT, SENS_DISCRETE_ADJOINT = 0, 1, 2, 3
 LOSS_MAE_SCALED, LOSS_MAE_LOG, LOSS_MSE = 0, 1, 2
 RET_DEFAULT, RET_SUCCESS, RET_DTNAN, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 3, 4, 5, 6

@@ -57,7 +57,7 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * order);
   P.inv_order = 1.0 / order;
   {
-    const bool implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4);
+    const bool implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4 || o->alg == CRNN_ALG_TRBDF2);
     P.qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
     P.qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
   }
@@ -69,7 +69,7 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.beta1_ros = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * 2.0);
   const size_t n_r2o = (n + 1) / 2 + 1;
   std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + n_r2o + extra.size() + 2 +
-                           (f2 ? ns + 3 * (size_t)ntab : 0), 0.0);
+                           (f2 ? ns + 3 * (size_t)ntab : 0) + (m->w_obs ? nr : 0), 0.0);
   double* p_winT = blob.data();
   double* p_wb = p_winT + (size_t)nin * KW_MAXN;
   double* p_wout = p_wb + nr;
@@ -93,9 +93,12 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
       p_f2[ns + k] = m->tab_t[k]; p_f2[ns + ntab + k] = m->tab_T[k]; p_f2[ns + 2 * ntab + k] = dens ? m->tab_P[k] : 1.0;
     }
   }
+  double* p_obs = p_f2 + (f2 ? ns + 3 * (size_t)ntab : 0);
+  if (m->w_obs) for (int j = 0; j < nr; ++j) p_obs[j] = m->w_obs[j];
   CK(cfgbuf.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
   CK(cudaMemcpyAsync(cfgbuf.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   double* d = cfgbuf.as<double>();
+  P.w_obs = m->w_obs ? d + (p_obs - blob.data()) : nullptr;
   P.w_inT = d; P.w_b = d + (p_wb - blob.data()); P.w_out = d + (p_wout - blob.data());
   P.saveat = d + (p_save - blob.data());
   P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
@@ -110,15 +113,17 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
 // Generic predict path (kernel_wide_solve.cuh): Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23) for any
 // dimensions <= 32 and every RHS flavour.
 int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
-  if (m->w_obs) return fail(h, CRNN_ERR_UNSUPPORTED, "the observable post-map is served by the loss / gradient entry points");
+  if (m->w_obs && o->n_obs != 1) return fail(h, CRNN_ERR_BAD_ARG, "the observable post-map has one output (n_obs = 1)");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
-  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2) ? 2 : 5;
   int rcw = build_wide(h, m, o, order, {}, st, P, nullptr);
   if (rcw) return rcw;
   constexpr int WARPS = 7;   // two blocks of seven warps per SM (shared memory: 24.8 KB per block + 12.4 KB per warp)
-  auto kern = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP) ? k_wide_solve<WARPS, true>
-                                                                                           : k_wide_solve<WARPS, false>;
+  const bool tab = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);
+  const bool trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);   // TRBDF2 as the stiff stepper
+  auto kern = trb ? (tab ? k_wide_solve<WARPS, true, 1> : k_wide_solve<WARPS, false, 1>)
+                  : (tab ? k_wide_solve<WARPS, true, 0> : k_wide_solve<WARPS, false, 0>);
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
@@ -786,11 +791,12 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
   if (rc) return rc;
   if (N > 0 && !u0) return fail(h, CRNN_ERR_BAD_ARG, "null u0");
   if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4 &&
-      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
+      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && o->alg != CRNN_ALG_TRBDF2 && o->alg != CRNN_ALG_AUTO_TSIT5_TRBDF2)
     return fail(h, CRNN_ERR_UNSUPPORTED, "alg not supported by solve_batch");
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, nullptr, pred, nullptr, n_saved, retcode, stats};
   if (o->alg == CRNN_ALG_KENCARP4) return solve_kencarp4(h, m, o, io, N);
+  if (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) return solve_wide(h, m, o, io, N);
   // dimension-specialised thread-per-trajectory kernels for the instantiated configurations ...
   const char* force = std::getenv("CRNN_B200_FORCE_WIDE");
   if (m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {

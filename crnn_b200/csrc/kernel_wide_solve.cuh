@@ -18,7 +18,10 @@
 
 namespace crnn {
 
-template <int WARPS, bool F2>
+// STIFF selects the stiff stepper: 0 = Rosenbrock23 (alg ROSENBROCK23 / AUTO_TSIT5_ROS23), 1 = TRBDF2 (alg TRBDF2 /
+// AUTO_TSIT5_TRBDF2: Cathode/src/network.jl:102, yeast_glycolysis.jl:33) - separate instantiations, so neither pays for the
+// other's code (these kernels are instruction-fetch bound).
+template <int WARPS, bool F2, int STIFF = 0>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 3 : 2)
 k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
              long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
@@ -39,7 +42,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
   for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
   __syncthreads();
 
-  const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23);
+  const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23 || P.alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
   const int my_obs = lane < n ? P.row2obs[lane] : -1;
   const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
@@ -68,12 +71,26 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
     const double t0 = P.t0, dtmax = tend - t0;
     const double dtmin = fmax(ulp_of(t0), ulp_of(tend));
     double* mypred = pred ? pred + (size_t)traj * P.n_obs * P.n_save : nullptr;
-    auto save = [&](int ks, double y) {
-      if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
-    };
-
     int n_rhs = 0, n_acc = 0, n_rej = 0, n_jac = 0, tab_seg = 0;
     WideAux a0, as;  // by-products at u_n / at the last evaluation
+    // a saved state: the clamped rows of u, or - with the observable post-map (heat release = HRR_getter(ts, sol) * w_delH,
+    // Cathode/src/network.jl:82-91,121) - y = sum_j w_obs[j] r_j(u(ts), ts) from one more evaluation at the saved state
+    // (not counted in n_rhs, like the oracle's emit_save; the step's own by-products in ww.r are put back)
+    auto save = [&](int ks, double tsv, double y) {
+      if (P.w_obs) {
+        __syncwarp();
+        const double rkeep = ww.r[lane];
+        WideAux ao; int seg2 = tab_seg;
+        (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, tsv, y, ao, seg2);
+        const double obs = wsum(lane < nr ? __ldg(P.w_obs + lane) * ww.r[lane] : 0.0);
+        __syncwarp();
+        ww.r[lane] = rkeep;
+        __syncwarp();
+        if (mypred && lane == 0) mypred[P.n_obs * ks] = clampd(obs, P.pred_lo, P.pred_hi);
+        return;
+      }
+      if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
+    };
     KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0, u, a0, tab_seg); ++n_rhs;
     ww.r0[lane] = ww.r[lane];
     // ---- initial step (Hairer-Wanner; the order of the FIRST algorithm) ----
@@ -96,9 +113,10 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
     }
     double t = t0, qold = 1e-4, dt_last = 0.0, eigen_est = 0.0;
     int isave = 0, ret = CRNN_RET_DEFAULT, sw_count = 0;
-    bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23);
+    bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23 || P.alg == CRNN_ALG_TRBDF2);   // "the stiff stepper is active"
+    double eta_old = 1.0;   // TRBDF2: the Newton solver's eta, kept across steps
     long long iter = 0;
-    while (isave < nsave && __ldg(P.saveat + isave) <= t0) { save(isave, u); ++isave; }
+    while (isave < nsave && __ldg(P.saveat + isave) <= t0) { save(isave, __ldg(P.saveat + isave), u); ++isave; }
 
     while (t < tend) {
       ++iter;
@@ -144,6 +162,58 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
           if (lane < n) { a = KS(6) - KS(5); a *= a; b = un - g6; b *= b; }
           eigen_est = sqrt(wsum(a) / n) / sqrt(wsum(b) / n);
         }
+      } else if (STIFF == 1) {
+        // ---- TRBDF2 as an ESDIRK (oracle solve_one, "TRBDF2" branch): z1 = dt f0 (FSAL), z_g at t + gamma dt, z3 at t + dt,
+        //      W = I - d dt J(u_n) inverted explicitly (one Gauss-Jordan per attempt, every Newton solve a mat-vec) ----
+        constexpr double s2 = 1.4142135623730951, gam = 2.0 - s2, d = 1.0 - s2 / 2.0, w = s2 / 4.0;
+        constexpr double bt1 = (1.0 - s2) / 3.0, bt2 = 1.0 / 3.0, bt3 = (s2 - 2.0) / 3.0, al1 = -s2 / 2.0, al2 = 1.0 + s2 / 2.0;
+        const double gdt = d * dt;
+        const double eig = wide_build_inv<F2>(P, sb, ww, lane, ww.r0, a0, gdt);
+        ++n_jac;
+        if (autosw) eigen_est = eig;
+        const double z1 = dt * KS(0);
+        double zg = z1, z3 = 0.0, tmp = u;
+        bool ok = true, refreshed = false;
+#pragma unroll 1
+        for (int stg = 0; stg < 2 && ok; ++stg) {
+          double zs;
+          if (stg == 0) { tmp = fma(d, z1, u); zs = z1; }
+          else { tmp = fma(w, zg, fma(w, z1, u)); zs = fma(al2, zg, al1 * z1); }
+          const double tst = t + (stg ? 1.0 : gam) * dt;
+          bool conv = false;
+#pragma unroll 1
+          for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
+            double ndz_prev = 0.0, eta = lean_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+#pragma unroll 1
+            for (int it = 1; it <= 10; ++it) {
+              const double yk = fma(d, zs, tmp);
+              double dz = fma(dt, wide_rhs<F2>(P, sb, ww, lane, my_mw, tst, yk, as, tab_seg), -zs); ++n_rhs;
+              dz = wide_invmul(ww, lane, ns, dz);
+              const double ndz = wrms(dz, u, yk);
+              zs += dz;
+              if (it > 1) {
+                const double theta = ndz / ndz_prev;
+                if (!(theta <= 2.0)) break;
+                eta = theta / (1.0 - theta);
+              }
+              if ((eta >= 0.0 && eta * ndz < 0.01) || ndz == 0.0) { conv = true; eta_old = eta; break; }
+              ndz_prev = ndz;
+            }
+            if (!conv) {
+              if (refreshed || __any_sync(0xffffffffu, lane < n && zs != zs)) break;
+              refreshed = true;
+              (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, tst, fma(d, zs, tmp), as, tab_seg); ++n_rhs;
+              (void)wide_build_inv<F2>(P, sb, ww, lane, ww.r, as, gdt);
+              ++n_jac;
+            }
+          }
+          if (stg == 0) zg = zs; else z3 = zs;
+          if (!conv) ok = false;
+        }
+        if (!ok) { dt_last = dt; ++n_rej; dt = dt / 2.0; continue; }
+        un = fma(d, z3, tmp);
+        e = wide_invmul(ww, lane, ns, lane < ns ? fma(bt3, z3, fma(bt2, zg, bt1 * z1)) : 0.0);
+        KS(5) = z3 / dt;   // fsallast
       } else {
         // ---- Rosenbrock23 = ode23s: KS(0)=f0, KS(1..3)=k1..k3, KS(4)=f1, KS(5)=f2 ----
         const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
@@ -176,10 +246,13 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         qold = jmax(EEst, 1e-4);
         const double dtnew = dt / (q >= P.qs_min && q <= P.qs_max ? 1.0 : q), tprev = t;  // steady-state dead-band
         t = snap_t(t + dt, tend);
+        if (STIFF == 1 && rosen) {   // the next attempt's analytic Jacobian needs the RHS by-products at u_{n+1}
+          (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, t, un, as, tab_seg); ++n_rhs;
+        }
         while (isave < nsave) {
           const double tsv = __ldg(P.saveat + isave);
           if (!(tsv <= t)) break;
-          if (tsv == t) save(isave, un);
+          if (tsv == t) save(isave, tsv, un);
           else {
             const double th = (tsv - tprev) / dt;
             if (!rosen) {
@@ -189,11 +262,14 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
                 const double bs = th * (tsc::R[s][0] + th * (tsc::R[s][1] + th * (tsc::R[s][2] + th * tsc::R[s][3])));
                 acc = s == 0 ? bs * KS(0) : fma(bs, KS(s), acc);
               }
-              save(isave, fma(dt, acc, u));
+              save(isave, tsv, fma(dt, acc, u));
+            } else if (STIFF == 1) {   // Hermite on (u_n, fsalfirst) .. (u_{n+1}, fsallast)
+              save(isave, tsv, (1.0 - th) * u + th * un +
+                              th * (th - 1.0) * ((1.0 - 2.0 * th) * (un - u) + (th - 1.0) * dt * KS(0) + th * dt * KS(5)));
             } else {
               const double d = 1.0 / (2.0 + 1.4142135623730951);
               const double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
-              save(isave, u + dt * (c1 * KS(1) + c2 * KS(2)));
+              save(isave, tsv, u + dt * (c1 * KS(1) + c2 * KS(2)));
             }
           }
           ++isave;

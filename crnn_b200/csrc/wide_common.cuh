@@ -30,6 +30,7 @@ struct WideP {
   const double* tab_t;   // device [n_tab] knots         (F2)
   const double* tab_T;   // device [n_tab]
   const double* tab_P;   // device [n_tab]
+  const double* w_obs;   // device [n_reac] or NULL: observable post-map y = sum_j w_obs[j] r_j(u(ts), ts) (k_wide_solve's saves)
 };
 
 // ---- shared by the lane-per-component kernels (k_wide_solve, k_tsit5_adjoint): F2 tables ----
@@ -312,11 +313,11 @@ __device__ __forceinline__ double wide_lusolve(const WW& ww, int lane, int ns, d
 // simplified-Newton iterations of k_kencarp4_wide call it ~20 times per factorisation, and those dependent chains were
 // what bound that kernel.  Mirrored by the oracle's named switch crnn_oracle_set_kc4_inverse.
 template <bool F2, class WW>
-__device__ __forceinline__ void wide_build_inv(const WideP& P, const WideBlock& sb, WW& ww, int lane,
-                                               const double* rsrc, const WideAux& a, double gdt) {
+__device__ __forceinline__ double wide_build_inv(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                                 const double* rsrc, const WideAux& a, double gdt) {
   const int ns = P.ns;
   const bool isp = lane < ns;
-  (void)wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);
+  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);   // opnorm(J, Inf)
   for (int k = 0; k < ns; ++k) {
     double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
     int bi = lane;
@@ -348,6 +349,7 @@ __device__ __forceinline__ void wide_build_inv(const WideP& P, const WideBlock& 
     if (p != k && isp) { const double tmpv = ww.A[lane][k]; ww.A[lane][k] = ww.A[lane][p]; ww.A[lane][p] = tmpv; }
   }
   __syncwarp();
+  return eig;
 }
 
 // b <- W^{-1} b with the explicit inverse in ww.A (lane i holds b_i); scratch: ww.ws

@@ -77,10 +77,15 @@ enum crnn_alg {
   CRNN_ALG_TSIT5 = 0,        /* case1.jl:28, case3.jl:29, non-stiff half of case2.jl:26 */
   CRNN_ALG_ROSENBROCK23 = 1, /* rober_crnn.jl:33 */
   CRNN_ALG_KENCARP4 = 2,     /* BASELINE config 5 (not in the reference) */
-  CRNN_ALG_AUTO_TSIT5_ROS23 = 3 /* AutoTsit5(Rosenbrock23()): case2.jl:26, HyChem/crnn_pyrolysis_mass.jl:29 — Tsit5 with
+  CRNN_ALG_AUTO_TSIT5_ROS23 = 3,/* AutoTsit5(Rosenbrock23()): case2.jl:26, HyChem/crnn_pyrolysis_mass.jl:29 — Tsit5 with
                                    OrdinaryDiffEq's AutoSwitch stiffness detection (maxstiffstep 10, maxnonstiffstep 3,
                                    tolerances 9/10, dtfac 2) switching to Rosenbrock23 (analytic J) and back;
                                    crnn_stats.n_jac counts the Rosenbrock23 step attempts */
+  CRNN_ALG_TRBDF2 = 4,          /* TRBDF2 as an ESDIRK with simplified Newton (predict path; the stiff half of the next one) */
+  CRNN_ALG_AUTO_TSIT5_TRBDF2 = 5 /* AutoTsit5(TRBDF2()): Cathode/src/network.jl:102, Cathode_NCM333_UQ/src_333/network.jl,
+                                   yeast-glycolysis/yeast_glycolysis.jl:33 — the same AutoSwitch, TRBDF2 as the stiff stepper
+                                   (predict path; gradients through the composite use CRNN_ALG_AUTO_TSIT5_ROS23);
+                                   crnn_stats.n_jac counts the Jacobian factorisations */
 };
 
 enum crnn_sens_mode {

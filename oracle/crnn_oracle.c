@@ -600,6 +600,8 @@ static double pi_q_b(const ctx_t* c, double b1, double b2, double EEst, double q
 
 static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
 
+static double wrms(const ctx_t* c, const double* v, const double* a, const double* b);
+
 /* One trajectory, Tsit5 / Rosenbrock23 / AutoTsit5(Rosenbrock23), value + optional forward-sensitivity
  * columns.  Mirrors OrdinaryDiffEq's solve! loop (loopheader!/perform_step!/
  * loopfooter!), saveat by dense interpolation without stopping at save points
@@ -620,8 +622,10 @@ static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 
 static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sink* sk, traj_result* res) {
   const crnn_opts* o = c->o;
   const int n = c->n, ncol = c->ncol, tot = n * ncol;
-  const int autosw = (o->alg == CRNN_ALG_AUTO_TSIT5_ROS23);
-  int rosen = (o->alg == CRNN_ALG_ROSENBROCK23);
+  const int autosw = (o->alg == CRNN_ALG_AUTO_TSIT5_ROS23 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
+  const int trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2); /* the stiff stepper is TRBDF2 (value path only) */
+  int rosen = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2);          /* "the stiff stepper is active" */
+  double eta_old = 1.0;                                                                 /* TRBDF2: nlsolver.ηold, kept across steps */
   double* buf = (double*)calloc((size_t)tot * 14 + (size_t)n * n * 2 + 9 * n, sizeof(double));
   double* U = buf;              /* current state, all columns */
   double* Un = U + tot;         /* proposed state */
@@ -700,6 +704,75 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
         }
         eigen_est = sqrt(num / (nc * n)) / sqrt(den / (nc * n));
       }
+    } else if (trb) {
+      /* TRBDF2 (Bank et al. 1985 / Hosea-Shampine 1996 as an ESDIRK: OrdinaryDiffEq sdirk_perform_step.jl, TRBDF2Tableau)
+       * [UPSTREAM-RECALL]: gamma = 2 - sqrt2, d = gamma/2, w = sqrt2/4;
+       *   z1 = dt f(u_n) (FSAL);  z_g = dt f(u_n + d z1 + d z_g) at t + gamma dt, guess z1;
+       *   z3 = dt f(u_n + w z1 + w z_g + d z3) at t + dt, guess alpha1 z1 + alpha2 z_g (Shampine);  u_{n+1} = u_n + w z1 + w z_g + d z3;
+       *   error = W^{-1}(bt1 z1 + bt2 z_g + bt3 z3) (smooth_est), fsallast = z3 / dt, Hermite dense output.
+       * The nonlinear solves follow this file's ESDIRK policy (solve_one_kencarp4: W = I - d dt J(u_n) with the analytic J
+       * built every step attempt, simplified Newton, kappa = 1/100, <= 10 iterations, one refresh of W per attempt, failure
+       * => dt/2) - OrdinaryDiffEq's W-reuse heuristics are not modelled.  K[1] = z1, K[2] = z_g, K[3] = z3, K[5] = z3/dt. */
+      const double s2 = sqrt(2.0), gam = 2.0 - s2, d = 1.0 - s2 / 2.0, w = s2 / 4.0;
+      const double bt1 = (1.0 - s2) / 3.0, bt2 = 1.0 / 3.0, bt3 = (s2 - 2.0) / 3.0, al1 = -s2 / 2.0, al2 = 1.0 + s2 / 2.0;
+      const double gdt = d * dt;
+      double* Z1 = K[1]; double* ZG = K[2]; double* Z3 = K[3]; double* Yk = W2; double* DZ = W2 + n;
+      jac_value(c, &kc0, Jm); res->st.n_jac++;
+      if (autosw) {
+        double best = 0.0;
+        for (int i = 0; i < n; ++i) { double rs = 0.0; for (int l = 0; l < n; ++l) rs += fabs(Jm[i * n + l]); if (rs > best) best = rs; }
+        eigen_est = best; /* calc_J under a CompositeAlgorithm: opnorm(J, Inf) */
+      }
+      for (int i = 0; i < n; ++i)
+        for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - gdt * Jm[i * n + l];
+      kc_factor(LU, piv, n);
+      for (int i = 0; i < n; ++i) Z1[i] = dt * K[0][i];
+      int newton_ok = 1, refreshed = 0;
+      for (int stg = 0; stg < 2 && newton_ok; ++stg) {
+        double* Zs = stg ? Z3 : ZG;
+        const double cs = stg ? 1.0 : gam;
+        for (int i = 0; i < n; ++i) {
+          if (!stg) { TMP[i] = U[i] + d * Z1[i]; Zs[i] = Z1[i]; }
+          else { TMP[i] = U[i] + w * Z1[i] + w * ZG[i]; Zs[i] = al1 * Z1[i] + al2 * ZG[i]; }
+        }
+        int conv = 0;
+        for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
+          double ndz_prev = 0.0, eta = m_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+          for (int it = 1; it <= 10; ++it) {
+            for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + d * Zs[i];
+            rhs_value(c, t + cs * dt, Yk, DZ, &kc); res->st.n_rhs++;
+            for (int i = 0; i < n; ++i) DZ[i] = dt * DZ[i] - Zs[i];
+            kc_solve(LU, piv, n, DZ);
+            double ndz = wrms(c, DZ, U, Yk);
+            for (int i = 0; i < n; ++i) Zs[i] += DZ[i];
+            if (it > 1) {
+              double theta = ndz / ndz_prev;
+              if (!(theta <= 2.0)) break;
+              eta = theta / (1.0 - theta);
+            }
+            if ((eta >= 0.0 && eta * ndz < 0.01) || ndz == 0.0) { conv = 1; eta_old = eta; break; }
+            ndz_prev = ndz;
+          }
+          if (!conv) {
+            if (refreshed || has_nan(Zs, n)) break;
+            refreshed = 1;
+            for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + d * Zs[i];
+            rhs_value(c, t + cs * dt, Yk, DZ, &kc); res->st.n_rhs++;
+            jac_value(c, &kc, Jm); res->st.n_jac++;
+            for (int i = 0; i < n; ++i)
+              for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - gdt * Jm[i * n + l];
+            kc_factor(LU, piv, n);
+          }
+        }
+        if (!conv) newton_ok = 0;
+      }
+      if (!newton_ok) { res->st.dt_last = dt; res->st.n_reject++; dt = dt / 2.0; continue; }
+      for (int i = 0; i < n; ++i) {
+        Un[i] = TMP[i] + d * Z3[i];
+        E[i] = bt1 * Z1[i] + bt2 * ZG[i] + bt3 * Z3[i];
+        K[5][i] = Z3[i] / dt;
+      }
+      kc_solve(LU, piv, n, E);
     } else {
       /* Rosenbrock23 = Shampine-Reichelt ode23s.  K[0]=f0
        * (FSAL), K[1]=k1, K[2]=k2, K[3]=k3, K[4]=f1, K[5]=f2. */
@@ -775,6 +848,9 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       double dtnew = dt / q;
       double tprev = t;
       t = snap_t(t + dt, tend);
+      if (rosen && trb) { /* the analytic Jacobian of the next attempt needs the RHS by-products at u_{n+1} (fsallast stays z3/dt) */
+        rhs_value(c, t, Un, W2, &kc); res->st.n_rhs++;
+      }
       /* savevalues!: every save time in (tprev, t] via the dense interpolant */
       while (isave < nsave && o->saveat[isave] <= t) {
         double ts = o->saveat[isave];
@@ -791,6 +867,10 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
               for (int s = 1; s < 7; ++s) acc += b[s] * K[s][qq];
               TMP[qq] = U[qq] + dt * acc;
             }
+          } else if (trb) { /* Hermite on (u_n, fsalfirst) .. (u_{n+1}, fsallast = z3/dt) */
+            for (int i = 0; i < n; ++i)
+              TMP[i] = (1.0 - th) * U[i] + th * Un[i] +
+                       th * (th - 1.0) * ((1.0 - 2.0 * th) * (Un[i] - U[i]) + (th - 1.0) * dt * K[0][i] + th * dt * K[5][i]);
           } else {
             const double d = 1.0 / (2.0 + sqrt(2.0));
             double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);
@@ -1258,7 +1338,8 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
   c->nw = m->n_reac * (m->n_in + 1 + m->n_species) + (m->w_obs ? m->n_reac : 0);
   c->seed = seed; c->ncol = 1 + np;
-  c->order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23) ? 5 : (o->alg == CRNN_ALG_ROSENBROCK23 ? 2 : 4);
+  c->order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) ? 5
+             : ((o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2) ? 2 : 4);
   c->qmin = o->qmin > 0 ? o->qmin : 0.2;
   c->qmax = o->qmax > 0 ? o->qmax : 10.0;
   c->gamma = o->gamma > 0 ? o->gamma : 0.9;
@@ -1266,7 +1347,7 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
   c->beta1 = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * c->order);
   /* qsteady_{min,max}_default: 1 / 1 for explicit and composite algorithms, 1 / (6//5) for the adaptive implicit ones
    * [UPSTREAM-RECALL alg_utils.jl: qsteady_max_default(::OrdinaryDiffEqAdaptiveImplicitAlgorithm) = 6//5] */
-  const int implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4);
+  const int implicit_alg = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_KENCARP4 || o->alg == CRNN_ALG_TRBDF2);
   c->qs_min = o->qsteady_min > 0 ? o->qsteady_min : 1.0;
   c->qs_max = o->qsteady_max > 0 ? o->qsteady_max : (implicit_alg ? 1.2 : 1.0);
   c->norm_cnt = (double)c->n * ((o->err_norm_includes_sens && !o->err_norm_mean_over_state_only) ? (double)c->ncol : 1.0);
@@ -1287,7 +1368,7 @@ static int check_dims(const crnn_model* m, const crnn_opts* o) {
   if (m->w_obs && o->n_obs > 1) return CRNN_ERR_BAD_ARG;
   if (f2 && (m->tab_t[0] > o->t0 || m->tab_t[m->n_tab - 1] < o->t1)) return CRNN_ERR_BAD_ARG;
   if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_KENCARP4 &&
-      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23) return CRNN_ERR_UNSUPPORTED;
+      o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && o->alg != CRNN_ALG_TRBDF2 && o->alg != CRNN_ALG_AUTO_TSIT5_TRBDF2) return CRNN_ERR_UNSUPPORTED;
   return CRNN_OK;
 }
 
@@ -1325,7 +1406,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
                                 int n_threads) {
   int rc = check_dims(m, o);
   if (rc) return rc;
-  if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
+  if (o->alg == CRNN_ALG_KENCARP4 || o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   if (adjoint && (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs)) return CRNN_ERR_UNSUPPORTED; /* forward mode only */

@@ -68,7 +68,8 @@ def test_heat_release_trajectory_against_radau():
     ts = np.linspace(0, te, 60)
     sol = solve_ivp(lambda t, y: literal(p_phys, beta, t, y)[0], (0, te), [1.0, 0, 0], method="Radau", rtol=1e-10, atol=1e-13, t_eval=ts)
     hr = np.array([literal(p_phys, beta, t, y)[1] for t, y in zip(ts, sol.y.T)])
-    for alg in (_abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23):
+    # AutoTsit5(TRBDF2(autodiff = true)) is what the script runs (Cathode/src/network.jl:102)
+    for alg in (_abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_ROS23, _abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2):
         r = oracle.solve_batch(m, cases.cathode_opts(ts, alg=alg), np.array([[1.0, 0, 0]]))
         assert r["retcode"][0] == _abi.RET_SUCCESS and r["pred"].shape == (1, 60, 1)
         assert np.abs(r["pred"][0, :, 0] - hr).max() < 2e-3 * hr.max()

@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+from dataclasses import replace as dataclasses_replace
 import pytest
 from scipy.integrate import solve_ivp
 
@@ -432,6 +433,54 @@ def test_kencarp4_against_radau_and_conservation(golden):
     from crnn_b200.engine import EngineError  # noqa: F401  (KenCarp4 has no sensitivity path: value only)
     with pytest.raises(RuntimeError):
         oracle.loss_grad_batch(pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+
+
+# ---------------------------------------------------------------- TRBDF2 and AutoTsit5(TRBDF2) (Cathode/src/network.jl:102)
+def test_trbdf2_is_second_order_and_l_stable():
+    """the tableau the oracle hard-codes (gamma = 2 - sqrt2, d = gamma/2, w = sqrt2/4): order conditions up to 2, the
+    embedded weights sum to zero with a vanishing first moment (3rd-order companion), R(infinity) = 0; and the measured
+    convergence order of the fixed-tolerance-free method on the linear test problem through the oracle's own stepping"""
+    s2 = np.sqrt(2.0); gam = 2 - s2; d = gam / 2; w = s2 / 4
+    A = np.array([[0, 0, 0], [d, d, 0], [w, w, d]]); b = A[2]; c = A.sum(axis=1)
+    assert np.allclose(c, [0, gam, 1]) and abs(b.sum() - 1) < 1e-15 and abs(b @ c - 0.5) < 1e-15
+    bt = np.array([(1 - s2) / 3, 1 / 3, (s2 - 2) / 3])
+    assert abs(bt.sum()) < 1e-15
+    bhat = b + bt                                            # Hosea-Shampine companion: order 3
+    for got, want in [(bhat @ c, 1 / 2), (bhat @ c**2, 1 / 3), (bhat @ (A @ c), 1 / 6)]:
+        assert abs(got - want) < 1e-14
+    e = np.ones(3)                                           # stability function at z -> -inf: 1 - b^T A^{-1} e on the implicit part
+    R = lambda z: 1 + z * b @ np.linalg.solve(np.eye(3) - z * A, e)
+    assert abs(R(-1e4)) < 1e-3 and abs(R(-1e7)) < 1e-6 and abs(R(-1.0) - np.exp(-1.0)) < 2e-2
+
+
+@pytest.mark.parametrize("alg", [_abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2])
+def test_trbdf2_against_tight_reference(golden, alg):
+    c = cases.CASES["robertson"]
+    pb = make_problem("robertson", golden, 6)
+    tight = c.opts(abstol=np.array([1e-10, 1e-12, 1e-10]), reltol=np.full(3, 1e-7), maxiters=10**7)
+    for model in (pb["model"], pb["true_model"]):
+        o = c.opts(alg=alg, pred_clamp=(-np.inf, np.inf))
+        r = oracle.solve_batch(model, o, pb["u0"])
+        ref = oracle.solve_batch(model, dataclasses_replace(tight, pred_clamp=(-np.inf, np.inf)), pb["u0"])
+        assert (r["retcode"] == 1).all() and (r["n_saved"] == c.n_save).all()
+        scale = np.abs(ref["pred"]).max(axis=(0, 1))
+        assert (np.abs(r["pred"] - ref["pred"]) / scale).max() < 5e-3
+        att = r["stats"]["n_accept"] + r["stats"]["n_reject"]
+        if alg == _abi.ALG_TRBDF2:
+            assert (r["stats"]["n_jac"] >= att).all()                     # one factorisation per attempt (+ refreshes)
+        else:
+            assert (r["stats"]["n_jac"] > 0).all() and (r["stats"]["n_jac"] < att).all()   # both halves ran
+    # tighter tolerances converge towards the reference (second order: error ~ tol^(2/3)-ish, at least 10x better here)
+    o1 = c.opts(alg=alg, abstol=np.array([1e-9, 1e-11, 1e-9]), reltol=np.full(3, 1e-6), pred_clamp=(-np.inf, np.inf))
+    r1 = oracle.solve_batch(pb["true_model"], o1, pb["u0"])
+    assert (np.abs(r1["pred"] - ref["pred"]) / scale).max() < 5e-5
+    # a non-stiff model: the composite never leaves Tsit5 and equals it bit for bit
+    p2 = make_problem("case2", golden, 4)
+    a = oracle.solve_batch(p2["model"], p2["case"].opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2), p2["u0"])
+    b = oracle.solve_batch(p2["model"], p2["case"].opts(alg=_abi.ALG_TSIT5), p2["u0"])
+    assert np.array_equal(a["pred"], b["pred"]) and (a["stats"]["n_jac"] == 0).all()
+    with pytest.raises(RuntimeError):                                      # value path only
+        oracle.loss_grad_batch(pb["model"], c.opts(alg=alg), pb["seed"], pb["u0"], pb["data"], pb["yscale"])
 
 
 # ---------------------------------------------------------------- interpolating adjoint (BASELINE config 4; not in the reference)

@@ -213,6 +213,82 @@ def test_kencarp4_on_the_hychem_f2_model(engine):
     assert err[same].max() < 1e-7 and err.max() < 5e-3
 
 
+def _trb_close(got, ref, frac=0.02, tol_same=1e-7):
+    """TRBDF2's simplified-Newton iteration counts can flip on last-bit differences (like KenCarp4's): all but a few
+    trajectories must have identical counts, and those agree to rounding; the rest still solve the ODE to tolerance"""
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["n_saved"], ref["n_saved"])
+    same = np.ones(got["retcode"].shape, dtype=bool)
+    for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+        same &= got["stats"][k] == ref["stats"][k]
+    assert same.mean() >= 1.0 - frac, f"{(~same).sum()} of {same.size} trajectories differ in step / RHS / Jacobian counts"
+    scale = np.abs(ref["pred"]).max(axis=(0, 1)) + 1e-300
+    err = np.abs(got["pred"] - ref["pred"]) / scale
+    assert err[same].max() < tol_same and err.max() < 5e-3
+    return same
+
+
+@pytest.mark.parametrize("alg", [_abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2])
+def test_trbdf2_and_its_composite_match_the_oracle(engine, golden, alg):
+    """TRBDF2 as an ESDIRK and AutoTsit5(TRBDF2()) (Cathode/src/network.jl:102, yeast_glycolysis.jl:33) on the stiff models:
+    the true Robertson mechanism, the trained stiff CRNN, the HyChem F2 model (non-autonomous: stage times matter)"""
+    pb = make_problem("robertson", golden, 256)
+    c = pb["case"]
+    o = c.opts(alg=alg, pred_clamp=(-np.inf, np.inf))
+    for model, tol in ((pb["true_model"], 1e-7), (pb["model"], 1e-4)):
+        got = engine.solve_batch(model, o, pb["u0"])
+        ref = oracle.solve_batch(model, o, pb["u0"], n_threads=8)
+        assert (got["retcode"] == _abi.RET_SUCCESS).all()
+        _trb_close(got, ref, tol_same=tol)
+        att = got["stats"]["n_accept"] + got["stats"]["n_reject"]
+        if alg == _abi.ALG_AUTO_TSIT5_TRBDF2:
+            assert (got["stats"]["n_jac"] > 0).all() and (got["stats"]["n_jac"] < att).all()   # both halves ran
+    m, _ = cases.hychem_model(cases.hychem_p(0), YS_HYCHEM)
+    oh = cases.hychem_opts(alg=alg)
+    u0 = cases.hychem_u0(256)
+    got = engine.solve_batch(m, oh, u0)
+    ref = oracle.solve_batch(m, oh, u0, n_threads=8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    _trb_close(got, ref, frac=0.05)
+    # a non-stiff model: the composite never leaves Tsit5 and is the Tsit5 solve of the same kernel bit for bit
+    p2 = make_problem("case2", golden, 128)
+    a = engine.solve_batch(p2["model"], p2["case"].opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2), p2["u0"])
+    b = oracle.solve_batch(p2["model"], p2["case"].opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2), p2["u0"], n_threads=8)
+    _counts_equal(a, b)
+    assert (a["stats"]["n_jac"] == 0).all() and _rel_err(a["pred"], b["pred"]) < 1e-9
+    # value path only: a gradient through TRBDF2 is refused loudly
+    from crnn_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        engine.loss_grad_batch(pb["model"], c.opts(alg=alg), pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+
+
+def test_cathode_predict_as_written_autotsit5_trbdf2_with_heat_release(engine):
+    """pred_n_ode of Cathode/src/network.jl:104-131: AutoTsit5(TRBDF2) on the F5 model under the five temperature programmes,
+    the saved states mapped to the heat release HRR_getter(ts, sol) * w_delH inside the predict kernel"""
+    import cathode_problem as cp
+    pb = cp.make(2, seed=1)
+    for alg in (_abi.ALG_AUTO_TSIT5_TRBDF2, _abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_ROS23, _abi.ALG_ROSENBROCK23):
+        o = cases.cathode_opts(pb["opts"].saveat, alg=alg, pred_clamp=(-np.inf, np.inf))
+        for e, beta in enumerate(cp.BETAS):
+            m, _ = cp.model_for(pb["particles"][0], beta, pb["t_hi"])
+            u0 = np.tile(pb["u0"][e], (8, 1)) * (1.0 - 0.01 * np.arange(8))[:, None]
+            got = engine.solve_batch(m, o, u0)
+            ref = oracle.solve_batch(m, o, u0, n_threads=8)
+            assert got["pred"].shape == (8, cp.N_SAVE, 1) and (got["retcode"] == _abi.RET_SUCCESS).all()
+            if alg in (_abi.ALG_TRBDF2, _abi.ALG_ROSENBROCK23):
+                _counts_equal(got, ref)             # the stiff steppers alone: identical counts (TRBDF2's Newton counts too)
+                assert _rel_err(got["pred"], ref["pred"]) < 1e-8
+            else:
+                # the composites spend the ramp's stiffening phase with Tsit5 AT its stability limit (up to 20 % of the
+                # attempts rejected): accept / reject decisions there flip on summation order, for either stiff half
+                assert np.array_equal(got["n_saved"], ref["n_saved"])
+                assert _rel_err(got["pred"], ref["pred"]) < 2e-2
+                assert abs(got["stats"]["n_rhs"].sum() / ref["stats"]["n_rhs"].sum() - 1.0) < 0.03
+                att = got["stats"]["n_accept"] + got["stats"]["n_reject"]
+                assert (got["stats"]["n_jac"] <= att).all()
+                if beta <= 2.0:                      # slow ramp, never near the limit: exact
+                    _counts_equal(got, ref)
+
+
 def test_reversible_crnn_case1_rev_on_the_generic_path(engine):
     """`case1 rev/case1.jl`: 5 species, 10 reversible reactions = an F0 CRNN with 20 reactions, np = 60.  No specialised
     kernel has these dimensions: predict runs on the generic kernel, the gradient on the discrete adjoint, which
