@@ -217,22 +217,28 @@ def cpu_reference(steps, warmup, sample, keep=False, inputs=None):
 def _timed(fn, steps, world, dev):
     import torch
     import torch.distributed as dist
-    fn()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        r = fn()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()), r
+    def once(k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            r_ = fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r_
+    for _ in range(3):          # W >= 3 warm-up calls
+        fn()
+    ms, r = once(steps)
+    if ms < 50.0:               # a short step: a single allocator / page-in hiccup would dominate two steps - time twenty
+        ms, r = once(max(steps, 20))
+    return ms, r
 
 
 def _flops_value_rhs(ns, nr, nin):
@@ -360,6 +366,38 @@ def extra_configs(eng, rank, world, dev, steps, with_cpu):
     if with_cpu:
         out["cpu_port_cores"] = cores
     return out
+
+
+def train_loop_rates(eng, c, opts, u0_h, data_h, yscale, n_exp=20, n_steps=400):
+    """The reference's epoch loop as written (case2/case2.jl:192-198: batch size 1, one optimiser step per experiment,
+    20 training experiments): optimiser steps per second with every step a C call + host ADAMW (the drop-in shim's loop),
+    and with the whole loop on the device (crnn_train_steps: p2vec, solve + sensitivities, reduction, ExpDecay -> ADAMW)."""
+    from crnn_b200 import optim
+    golden = load_golden()
+    p0 = np.array(golden["case2"]["p"], dtype=np.float64)
+    ds = eng.dataset(u0_h[:n_exp], data_h[:n_exp])
+    order = np.concatenate([np.random.default_rng(0).permutation(n_exp) for _ in range(n_steps // n_exp)])
+    kw = dict(optimiser="adam", eta=0.005, beta=(0.9, 0.999), weight_decay=1e-6, expdecay=(5e-3, 0.5, 500 * n_exp, 1e-4))
+    model, _ = c.model(p0)
+    eng.train_steps(model, opts, ds, order[:20], yscale, p0, None, c.loss_kind, **kw)      # warm-up
+    t0 = time.perf_counter()
+    r = eng.train_steps(model, opts, ds, order, yscale, p0, None, c.loss_kind, **kw)
+    dev_s = time.perf_counter() - t0
+    opt = optim.Optimiser(optim.ExpDecay(5e-3, 0.5, 500 * n_exp, 1e-4), optim.ADAMW(0.005, (0.9, 0.999), 1e-6))
+    p = p0.copy()
+    n_host = min(n_steps, 200)
+    t0 = time.perf_counter()
+    for s_ in range(n_host):
+        m, seed = c.model(p)
+        rr = eng.loss_grad_indexed(m, opts, seed, ds, yscale, c.loss_kind, idx=order[s_:s_ + 1])
+        opt.update(p, rr["grad_sum"] / max(rr["n_ok"], 1))
+    host_s = time.perf_counter() - t0
+    ds.close()
+    return {"workload": "case2.jl:192-198 as written: batch 1, 20 experiments, ExpDecay -> ADAMW",
+            "device_loop_steps_per_s": n_steps / dev_s, "host_loop_steps_per_s": n_host / host_s,
+            "device_loop_api": "crnn_train_steps (5 kernels per optimiser step, nothing returns to the host between steps)",
+            "host_loop_api": "crnn_loss_grad_indexed + numpy mirror of Flux's optimisers per step",
+            "final_step_loss_device": float(r["step_loss"][-1])}
 
 
 def main():
@@ -571,6 +609,8 @@ def main():
                                  "n_compared": int(sample), "count_mismatches": int(bad.sum()),
                                  "loss_max_rel": float(np.max(np.abs(gpu_loss - ref["loss"]) / np.abs(ref["loss"]))),
                                  "grad_rel_l2": float(np.linalg.norm(gpu_grad - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]))}
+        if a.gpus == 1:
+            out["train_loop"] = train_loop_rates(eng, c, opts, u0_h, data_h, yscale)
         if extra is not None:
             out["configs"] = extra
         print(json.dumps(out))
