@@ -122,8 +122,9 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
   constexpr int WARPS = 7;   // two blocks of seven warps per SM (shared memory: 24.8 KB per block + 12.4 KB per warp)
   const bool tab = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);
   const bool trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);   // TRBDF2 as the stiff stepper
-  auto kern = trb ? (tab ? k_wide_solve<WARPS, true, 1> : k_wide_solve<WARPS, false, 1>)
-                  : (tab ? k_wide_solve<WARPS, true, 0> : k_wide_solve<WARPS, false, 0>);
+  if (m->w_obs && !tab) return fail(h, CRNN_ERR_UNSUPPORTED, "the observable post-map of the predict path is built for the tabulated-input flavours (F5: Cathode)");
+  auto kern = trb ? (tab ? (m->w_obs ? k_wide_solve<WARPS, true, 1, true> : k_wide_solve<WARPS, true, 1, false>) : k_wide_solve<WARPS, false, 1, false>)
+                  : (tab ? (m->w_obs ? k_wide_solve<WARPS, true, 0, true> : k_wide_solve<WARPS, true, 0, false>) : k_wide_solve<WARPS, false, 0, false>);
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
@@ -151,7 +152,10 @@ int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
   if (rcw) return rcw;
   constexpr int WARPS = 8;   // two blocks of eight warps per SM
-  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? k_kencarp4_wide<WARPS, true> : k_kencarp4_wide<WARPS, false>;
+  // large models: the instantiation whose RHS mat-vecs run over the non-zero weights (wide_common.cuh, WideSparse)
+  const bool big = m->n_in > 16 || m->n_reac > 16;
+  auto kern = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP ? (big ? k_kencarp4_wide<WARPS, true, true> : k_kencarp4_wide<WARPS, true, false>)
+                                                     : (big ? k_kencarp4_wide<WARPS, false, true> : k_kencarp4_wide<WARPS, false, false>);
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarpT<0>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;

@@ -32,7 +32,7 @@ __constant__ double BHAT[6] = {4586570599.0 / 29645900160.0, 0.0, 178811875.0 / 
                                814220225.0 / 1159782912.0, -3700637.0 / 11593932.0, 61727.0 / 225920.0};
 }  // namespace kc
 
-template <int WARPS, bool F2>
+template <int WARPS, bool F2, bool SPARSE = false>
 __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32))
 k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
                 const int* __restrict__ n_save_used, long long ntraj, double* __restrict__ pred,
@@ -46,14 +46,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   KcWarp& ww = wws[warp];
   const int n = P.n, ns = P.ns, nin = P.nin, nr = P.nr;
 
-  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
-    const int i = q / KW_MAXN, j = q % KW_MAXN;
-    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
-    sb.w_inJ[j][i] = sb.w_inT[i][j];
-    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
-  }
-  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
-  __syncthreads();
+  wide_block_init(P, sb);
 
   const bool isp = lane < ns;                      // lane owns a species
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
@@ -62,7 +55,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   const double my_mw = (F2 && lane < ns) ? __ldg(P.mw + lane) : 1.0;
   // f(y, t), W = I - gdt*J and the triangular solves come from wide_common.cuh (all RHS flavours)
   int tab_seg = 0;  // F2: segment hint of the T(t), P(t) lookup
-  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2>(P, sb, ww, lane, my_mw, tt, y, ax, tab_seg); };
+  auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2, SPARSE>(P, sb, ww, lane, my_mw, tt, y, ax, tab_seg); };
   // W^{-1} explicitly (Gauss-Jordan, in place) and mat-vec "solves": ~20 Newton solves share one factorisation
   auto lusolve = [&](double b) -> double { return wide_invmul(ww, lane, ns, b); };
   auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { wide_build_inv<F2>(P, sb, ww, lane, rsrc, ax, gdt); };

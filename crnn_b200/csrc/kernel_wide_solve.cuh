@@ -21,7 +21,7 @@ namespace crnn {
 // STIFF selects the stiff stepper: 0 = Rosenbrock23 (alg ROSENBROCK23 / AUTO_TSIT5_ROS23), 1 = TRBDF2 (alg TRBDF2 /
 // AUTO_TSIT5_TRBDF2: Cathode/src/network.jl:102, yeast_glycolysis.jl:33) - separate instantiations, so neither pays for the
 // other's code (these kernels are instruction-fetch bound).
-template <int WARPS, bool F2, int STIFF = 0>
+template <int WARPS, bool F2, int STIFF = 0, bool OBS = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 3 : 2)
 k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
              long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
@@ -33,14 +33,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
   WideWarp& ww = wws[warp];
   const int n = P.n, ns = P.ns, nin = P.nin, nr = P.nr;
 
-  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
-    const int i = q / KW_MAXN, j = q % KW_MAXN;
-    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
-    sb.w_inJ[j][i] = sb.w_inT[i][j];
-    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
-  }
-  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
-  __syncthreads();
+  wide_block_init(P, sb);
 
   const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23 || P.alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
@@ -77,7 +70,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
     // Cathode/src/network.jl:82-91,121) - y = sum_j w_obs[j] r_j(u(ts), ts) from one more evaluation at the saved state
     // (not counted in n_rhs, like the oracle's emit_save; the step's own by-products in ww.r are put back)
     auto save = [&](int ks, double tsv, double y) {
-      if (P.w_obs) {
+      if (OBS) {   // its own instantiations: the extra RHS copy is code the other models should not carry
         __syncwarp();
         const double rkeep = ww.r[lane];
         WideAux ao; int seg2 = tab_seg;

@@ -91,12 +91,61 @@ struct alignas(16) WideWarpT {
 };
 using WideWarp = WideWarpT<7>;
 
+// Index lists of the NON-ZERO weights, built once per block (wide_block_init).  A CRNN is sparse by construction - w_in =
+// clamp(-w_out, 0, ..) is zero wherever a species is not a reactant, pruned models (case*_pruning.jl) more so, the 30-reaction
+// HyChem-sized model has <= 3 inputs per reaction - and the two mat-vecs of the RHS are a sixth of the stiff kernels'
+// instructions when done densely.  The lists keep the dense loop's order (increasing index), so the sums are the same bits.
+constexpr int KW_SPMAX = 12;   // longest list kept; a denser row / column falls back to the dense loop
+struct WideSparse {
+  unsigned char idx_in[KW_SPMAX][KW_MAXN];   // [k][j]: k-th input row i with w_in[i,j] != 0
+  unsigned char idx_out[KW_SPMAX][KW_MAXN];  // [k][i]: k-th reaction j with w_out[i,j] != 0
+  unsigned char cnt_in[KW_MAXN], cnt_out[KW_MAXN];
+  int max_in, max_out, use_in, use_out;
+};
+
 struct alignas(16) WideBlock {
   double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
   double w_inJ[KW_MAXN][KW_MAXN];  // [j][i]: the Jacobian assembly reads 8 consecutive inputs of a reaction with 4 LDS.128
   double w_out[KW_MAXN][KW_MAXN];  // [j][i]: lane i reads consecutive addresses for fixed j
   double w_b[KW_MAXN];
+  WideSparse sp;
 };
+
+// weights into shared memory + the sparse index lists; every thread of the block calls it
+__device__ __forceinline__ void wide_block_init(const WideP& P, WideBlock& sb) {
+  const int ns = P.ns, nin = P.nin, nr = P.nr;
+  for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
+    const int i = q / KW_MAXN, j = q % KW_MAXN;
+    sb.w_inT[i][j] = (i < nin && j < nr) ? P.w_inT[i * KW_MAXN + j] : 0.0;
+    sb.w_inJ[j][i] = sb.w_inT[i][j];
+    sb.w_out[i][j] = (i < nr && j < ns) ? P.w_out[j + ns * i] : 0.0;  // [reaction][species]
+  }
+  for (int q = threadIdx.x; q < KW_MAXN; q += blockDim.x) sb.w_b[q] = q < nr ? P.w_b[q] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < KW_MAXN) {
+    const int j = threadIdx.x;
+    int c = 0;
+    for (int i = 0; i < nin; ++i)
+      if (sb.w_inT[i][j] != 0.0) { if (c < KW_SPMAX) sb.sp.idx_in[c][j] = (unsigned char)i; ++c; }
+    sb.sp.cnt_in[j] = (unsigned char)c;
+  } else if (threadIdx.x < 2 * KW_MAXN) {
+    const int i = threadIdx.x - KW_MAXN;
+    int c = 0;
+    for (int j = 0; j < nr; ++j)
+      if (sb.w_out[j][i] != 0.0) { if (c < KW_SPMAX) sb.sp.idx_out[c][i] = (unsigned char)j; ++c; }
+    sb.sp.cnt_out[i] = (unsigned char)c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int mi = 0, mo = 0;
+    for (int q = 0; q < KW_MAXN; ++q) { mi = max(mi, (int)sb.sp.cnt_in[q]); mo = max(mo, (int)sb.sp.cnt_out[q]); }
+    sb.sp.max_in = mi; sb.sp.max_out = mo;
+    // a list entry costs an index load and a gathered operand more than a dense term
+    sb.sp.use_in = (mi <= KW_SPMAX && 5 * mi < 3 * nin) ? 1 : 0;
+    sb.sp.use_out = (mo <= KW_SPMAX && 5 * mo < 3 * nr) ? 1 : 0;
+  }
+  __syncthreads();
+}
 
 // the adjoint kernel assembles no Jacobian: no reaction-major copy of w_in (8 KB more room for its step record)
 struct alignas(16) WideBlockLite {
@@ -113,8 +162,9 @@ struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobi
   double chiC;     // F2: 1 if lb <= C_l <= ub
 };
 
-// f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.
-template <bool F2, class WW>
+// f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.  SPARSE: the instantiation that consults the index
+// lists (large models; small ones keep the dense-only code - these kernels are instruction-fetch bound).
+template <bool F2, bool SPARSE = false, class WW>
 __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WW& ww, int lane, double mw,
                                            double t, double y, WideAux& a, int& seg) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
@@ -153,15 +203,29 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   __syncwarp();
   if (lane < nr) {
     double z = sb.w_b[lane];
+    if (SPARSE && sb.sp.use_in) {
+      const int c = sb.sp.cnt_in[lane], cm = sb.sp.max_in;
 #pragma unroll 2
-    for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
+      for (int k = 0; k < cm; ++k)
+        if (k < c) { const int i = sb.sp.idx_in[k][lane]; z = fma(sb.w_inT[i][lane], ww.x[i], z); }
+    } else {
+#pragma unroll 2
+      for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], ww.x[i], z);
+    }
     ww.r[lane] = lean_exp(z);
   }
   __syncwarp();
   double f = 0.0;
   if (isp) {
+    if (SPARSE && sb.sp.use_out) {
+      const int c = sb.sp.cnt_out[lane], cm = sb.sp.max_out;
 #pragma unroll 2
-    for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+      for (int k = 0; k < cm; ++k)
+        if (k < c) { const int j = sb.sp.idx_out[k][lane]; f = fma(sb.w_out[j][lane], ww.r[j], f); }
+    } else {
+#pragma unroll 2
+      for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], ww.r[j], f);
+    }
   }
   a.wdot = f;
   if (F2) f = f / rho;
@@ -308,6 +372,71 @@ __device__ __forceinline__ double wide_lusolve(const WW& ww, int lane, int ns, d
   return isp ? b : 0.0;
 }
 
+// Gauss-Jordan inversion of the ns x ns matrix in ww.A with every lane's ROW IN REGISTERS (ns > 16: BASELINE config 5).
+// The shared-memory form below reads and writes each row once per pivot (ns^2 * 16 B of shared-memory traffic per pivot,
+// 41 % of k_kencarp4_wide's wavefronts); here only the scaled pivot row passes through shared memory (16 STS.128 by the
+// pivot lane, 16 broadcast LDS.128 by all).  Two devices keep every register index a compile-time constant:
+//   * the columns live in a RING that is shifted left by one per pivot (the shift is free: the update writes a[m] from
+//     a[m+1]), so the pivot column is always a[0] and the finished column of the inverse enters at a[31];
+//   * rows never move between lanes: partial pivoting picks the pivot LANE, and each lane tracks the logical index its row
+//     would have after LAPACK-style exchanges (needed for the tie-break and for where the row is finally stored).
+// Same operations on the same numbers as the shared-memory form and as the oracle's kc_factor (inverse form).
+template <class WW>
+__device__ __noinline__ void wide_gj_regs(WW& ww, int lane, int ns) {
+  const bool isp = lane < ns;
+  double a[KW_MAXN];
+#pragma unroll
+  for (int j = 0; j < KW_MAXN; ++j) a[j] = (isp && j < ns) ? ww.A[lane][j] : 0.0;
+  double2* buf = reinterpret_cast<double2*>(ww.ws);
+  int lidx = lane;
+  bool used = false;
+#pragma unroll 1
+  for (int k = 0; k < ns; ++k) {
+    double best = (isp && !used) ? fabs(a[0]) : -1.0;
+    int key = (lidx << 8) | lane;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+      const int ok = __shfl_xor_sync(0xffffffffu, key, m);
+      if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
+    }
+    const int pl = key & 0xff, bi = key >> 8;   // the pivot row's lane / logical index
+    if (lane != pl && lidx == k) lidx = bi;     // the exchange rows k <-> bi, in logical indices only
+    if (lane == 0) ww.piv[k] = bi;
+    const double pinv = 1.0 / __shfl_sync(0xffffffffu, a[0], pl);
+    __syncwarp();
+    if (lane == pl) {
+      lidx = k; used = true;
+#pragma unroll
+      for (int m = 0; m < KW_MAXN - 1; ++m) a[m] = a[m + 1] * pinv;   // scaled and shifted
+      a[KW_MAXN - 1] = pinv;
+#pragma unroll
+      for (int q = 0; q < KW_MAXN / 2; ++q) buf[q] = make_double2(a[2 * q], a[2 * q + 1]);
+    }
+    __syncwarp();
+    if (lane != pl) {
+      const double f = a[0];
+#pragma unroll
+      for (int q = 0; q < KW_MAXN / 2; ++q) {
+        const double2 r = buf[q];
+        a[2 * q] = fma(-f, r.x, a[2 * q + 1]);
+        if (2 * q + 2 < KW_MAXN) a[2 * q + 1] = fma(-f, r.y, a[2 * q + 2]);
+        else a[2 * q + 1] = -f * r.y;
+      }
+    }
+  }
+  __syncwarp();
+  // after ns shifts ring slot m holds column m - (32 - ns)
+  if (isp) {
+#pragma unroll
+    for (int m = 0; m < KW_MAXN; ++m) {
+      const int c = m - (KW_MAXN - ns);
+      if (c >= 0) ww.A[lidx][c] = a[m];
+    }
+  }
+  __syncwarp();
+}
+
 // W^{-1} in place of W (ww.A) by Gauss-Jordan elimination with partial pivoting, lane = row.  A solve then is one
 // mat-vec with independent loads (wide_invmul) instead of 2*ns dependent shuffle + FMA steps (wide_lusolve): the
 // simplified-Newton iterations of k_kencarp4_wide call it ~20 times per factorisation, and those dependent chains were
@@ -318,6 +447,8 @@ __device__ __forceinline__ double wide_build_inv(const WideP& P, const WideBlock
   const int ns = P.ns;
   const bool isp = lane < ns;
   const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);   // opnorm(J, Inf)
+  if (ns > 16) wide_gj_regs(ww, lane, ns);
+  else
   for (int k = 0; k < ns; ++k) {
     double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
     int bi = lane;
