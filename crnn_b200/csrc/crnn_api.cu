@@ -209,7 +209,7 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   static const bool want_four = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return !e || std::atoi(e) != 2; }();
   const bool f2 = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP;
   const int stride = 8 * n + 2;
-  const size_t fixed_pw = (160 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);
+  const size_t fixed_pw = (6 * 32 + 2 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);   // kernel_tsit5_adjoint.cuh: ADJ_FIXED
   // forward-record capacity in shared memory for `nb` blocks of 4 warps per SM (steps per warp; < 0: does not fit)
   auto cap_for = [&](int nb) -> long long {
     const size_t budget = (size_t)(227 * 1024 / nb) - 2048 - sizeof(WideBlockLite);

@@ -64,11 +64,15 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   WideBlockLite& sb = *reinterpret_cast<WideBlockLite*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] | GW[nw] GS[nw] | record[cap_s][stride]
-  const size_t per_warp = 5 * 32 + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
+  // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] sl[32] one[2] | GW[nw] GS[nw] | record[cap_s][stride]
+  constexpr int ADJ_FIXED = 6 * 32 + 2;   // crnn_api.cu::loss_grad_adjoint sizes the launch with the same number
+  const size_t per_warp = ADJ_FIXED + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
   double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlockLite)) + per_warp * warp;
   double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
   double* s_chi = wbase + 128;
-  double* GW = wbase + 160; double* GS = GW + ((nw + 1) & ~1);
+  double* s_sl = wbase + 160;   // scale_i * lambda_i / rho: the left factor of the G_out outer product
+  double* GW = wbase + ADJ_FIXED; double* GS = GW + ((nw + 1) & ~1);
+  if (lane == 0) wbase[192] = 1.0;   // the unit left factor of the G_b entries
   double* rec_s = GS + ((nw + 1) & ~1);
   double* rec_g = P.scratch + ((size_t)blockIdx.x * WARPS + warp) * (size_t)P.cap_g * stride;
 
@@ -87,17 +91,17 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const double my_scale = isp ? P.scale[lane] : 0.0;
   constexpr bool f2 = F2;
   const double my_mw = (f2 && isp) ? __ldg(W.mw + lane) : 1.0;
-  // quadrature entries of this lane: e = lane + 32*q ; packed (kind, i, j)
-  int ent[ADJ_MAX_ENT];
-#pragma unroll
-  for (int q = 0; q < ADJ_MAX_ENT; ++q) {
-    const int e = lane + 32 * q;
-    int code = -1;
-    if (e < nin * nr) code = (0 << 16) | ((e % nin) << 8) | (e / nin);
-    else if (e < nin * nr + nr) code = (1 << 16) | (e - nin * nr);
-    else if (e < nw) { const int f = e - nin * nr - nr; code = (2 << 16) | ((f % ns) << 8) | (f / ns); }
-    ent[q] = code;
+  // quadrature entries: lane owns e = lane + 32*q.  Every entry is a product of two per-warp shared-memory values; the table
+  // (one per block, in shared memory - sixteen registers per thread when it was a local array) holds their offsets into wbase:
+  //   G_in[i,j] = x_i * (g_j r_j)     G_b[j] = 1 * (g_j r_j)     G_out[i,j] = (scale_i lambda_i) * r_j
+  for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+    int code = 0;
+    if (e < nin * nr) code = ((0 + e % nin) << 16) | (96 + e / nin);
+    else if (e < nin * nr + nr) code = (192 << 16) | (96 + e - nin * nr);
+    else if (e < nw) { const int f = e - nin * nr - nr; code = ((160 + f % ns) << 16) | (32 + f / ns); }
+    sb.ent[e] = code;
   }
+  __syncthreads();
 
   auto rec_ptr = [&](int step) -> double* {
     return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
@@ -294,6 +298,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       }
       s_x[lane] = xi;
       s_lam[lane] = isp ? li * inv_rho : 0.0;
+      s_sl[lane] = my_scale * (isp ? li * inv_rho : 0.0);
       __syncwarp();
       double brk = 0.0;
       if (lane < nr) {
@@ -342,14 +347,11 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
 #pragma unroll
       for (int q = 0; q < ADJ_MAX_ENT; ++q) {
         if (32 * q >= nw) break;  // uniform: the remaining entries are empty for every lane
-        const int code = ent[q];
-        if (code >= 0) {
-          const int kind = code >> 16, i = (code >> 8) & 255, j = code & 255;
-          double val;
-          if (kind == 0) val = s_x[i] * s_gr[j];
-          else if (kind == 1) val = s_gr[j];
-          else val = P.scale[i] * s_lam[i] * s_r[j];
-          dst[lane + 32 * q] = fma(bw, val, dst[lane + 32 * q]);
+        const int e = lane + 32 * q;
+        if (e < nw) {
+          const int code = sb.ent[e];
+          const double val = wbase[code >> 16] * wbase[code & 0xffff];
+          dst[e] = fma(bw, val, dst[e]);
         }
       }
     };

@@ -148,10 +148,14 @@ __device__ __forceinline__ void wide_block_init(const WideP& P, WideBlock& sb) {
 }
 
 // the adjoint kernel assembles no Jacobian: no reaction-major copy of w_in (8 KB more room for its step record)
+// rows padded to 33: the adjoint's transposed mat-vecs read these with the LANE as the row index (g_j = sum_i w_out[j][i] mu_i on
+// lane j, (J^T lambda)_l = sum_j w_in[l][j] g_j r_j on lane l) - with 32-double rows every lane hit the same bank (37 % of the
+// kernel's shared-memory wavefronts were conflict replays); both access directions are conflict-free at 33
 struct alignas(16) WideBlockLite {
-  double w_inT[KW_MAXN][KW_MAXN];  // [i][j]
-  double w_out[KW_MAXN][KW_MAXN];  // [j][i]
+  double w_inT[KW_MAXN][KW_MAXN + 1];  // [i][j]
+  double w_out[KW_MAXN][KW_MAXN + 1];  // [j][i]
   double w_b[KW_MAXN];
+  int ent[512];                        // quadrature entry e < n_w: offsets (left << 16) | right of its two factors (kernel_tsit5_adjoint.cuh)
 };
 
 struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobian needs)
