@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libcrnn_b200.so")
 
 # enums (include/crnn_b200.h)
-RHS_F0, RHS_F1, RHS_F2, RHS_F5 = 0, 1, 2, 3
+RHS_F0, RHS_F1, RHS_F2, RHS_F5, RHS_F4 = 0, 1, 2, 3, 4
 ALG_TSIT5, ALG_ROSENBROCK23, ALG_KENCARP4, ALG_AUTO_TSIT5_ROS23, ALG_TRBDF2, ALG_AUTO_TSIT5_TRBDF2 = 0, 1, 2, 3, 4, 5
 SENS_NONE, SENS_FORWARD, SENS_INTERP_ADJOINT, SENS_DISCRETE_ADJOINT = 0, 1, 2, 3
 LOSS_MAE_SCALED, LOSS_MAE_LOG, LOSS_MSE = 0, 1, 2
@@ -34,6 +34,8 @@ class CModel(C.Structure):
         ("out_scale", c_double_p), ("w_in", c_double_p), ("w_b", c_double_p), ("w_out", c_double_p),
         ("mw", c_double_p), ("tab_t", c_double_p), ("tab_T", c_double_p), ("tab_P", c_double_p),
         ("w_obs", c_double_p),
+        ("mlp_n_layers", C.c_int32), ("mlp_act_out", C.c_int32),
+        ("mlp_dims", c_int32_p), ("mlp_in_idx", c_int32_p), ("mlp_params", c_double_p), ("aug_src", c_int32_p), ("w_J", c_double_p),
     ]
 
 

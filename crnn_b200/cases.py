@@ -545,3 +545,76 @@ def cathode_opts(ts, alg=_abi.ALG_AUTO_TSIT5_ROS23, lb=1e-8, **kw) -> SolveOpts:
 def cathode_p_true():
     """A physically plausible parameter set in the UQ script's (scaled) coordinates: ln A, Ea [1e5 J/mol], b, delH, orders, nu."""
     return np.array([28.0, 30.0, 33.0, 1.25, 1.40, 1.60, 0.0, 0.0, 0.0, 120.0, 40.0, 60.0, 1.0, 1.2, 1.0, 0.9, 0.8])
+
+
+# ---- yeast glycolysis (yeast-glycolysis/yeast_glycolysis.jl): 7 observed + 5 hidden species, the hidden ones from an MLP (F4) ----
+
+YEAST_NS, YEAST_NS_, YEAST_NR = 7, 12, 12          # :29-31
+YEAST_MLP_DIMS = (7, 5, 5, 5, 5)                   # Chain(Dense(ns, node, gelu), Dense(node, node, gelu) x 2, Dense(node, ns_ - ns, softplus)), :137-142
+YEAST_IC_LB = np.array([0.15, 1.19, 0.04, 0.10, 0.08, 0.14, 0.05])   # :70-71
+YEAST_IC_UB = np.array([1.60, 2.16, 0.20, 0.35, 0.30, 2.67, 0.10])
+
+
+def yeast_true_rhs(t, s, k=(100.0, 6.0, 16.0, 100.0, 1.28, 12.0)):
+    """trueODEfunc, yeast_glycolysis.jl:47-66 (q = 4, K1 = 0.52, A = 4, N = 1, J0 = 2.5, phi = 0.1; k at :78)"""
+    q, K1, A, N, J0, phi = 4, 0.52, 4.0, 1.0, 2.5, 0.1
+    r1 = k[0] * s[0] * s[5] / (1 + (s[5] / K1) ** q)
+    r2 = k[1] * s[1] * (N - s[4])
+    r3 = k[2] * s[2] * (A - s[5])
+    r4 = k[3] * s[3] * s[4]
+    r5 = k[4] * s[5]
+    r6 = k[5] * s[1] * s[4]
+    r7 = 13 * s[6]
+    r8 = 13 * (s[3] - s[6])
+    return np.array([J0 - r1, 2 * r1 - r2 - r6, r2 - r3, r3 - r4 - r8, r2 - r4 - r6, -2 * r1 + 2 * r3 - r5, phi * r8 - r7])
+
+
+def p2vec_yeast(p):
+    """yeast_glycolysis.jl:112-123,145: p = vcat(pcrnn [164], pnn [130]); slope = pcrnn[end] * 100, w_b = pcrnn[1:nr] * slope,
+    w_out = reshape(pcrnn[nr+1 : nr (ns_+1)], ns_, nr), w_in = clamp(-w_out, 0, 4), w_J = pcrnn[nr (ns_+1)+1 : end-1];
+    pnn in Flux.destructure order.  -> (w_in [12,12], w_b, w_out [12,12], w_J [7], pnn)."""
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    ns, ns_, nr = YEAST_NS, YEAST_NS_, YEAST_NR
+    n_crnn = nr * (ns_ + 1) + ns + 1
+    pc, pnn = p[:n_crnn], p[n_crnn:]
+    slope = pc[-1] * 100.0
+    w_b = pc[:nr] * slope
+    w_out = pc[nr:nr * (ns_ + 1)].reshape(ns_, nr, order="F")
+    w_in = np.clip(-w_out, 0.0, 4.0)
+    w_J = pc[nr * (ns_ + 1):n_crnn - 1]
+    return w_in, w_b, w_out, w_J, pnn
+
+
+def yeast_model(p, lb=1e-5, ub=100.0) -> CRNNModel:
+    """`crnn` of yeast_glycolysis.jl:128-132 as an F4 model: u_ = vcat(u, rep(u)), du = (w_out * exp(w_in' log clamp(u_) + w_b))[1:ns]
+    .+ w_J — only the first ns rows of w_out enter (lb = atol = 1e-5, ub = 100, :34-37)."""
+    w_in, w_b, w_out, w_J, pnn = p2vec_yeast(p)
+    ns, ns_ = YEAST_NS, YEAST_NS_
+    return CRNNModel(w_in=w_in, w_b=w_b, w_out=w_out[:ns], rhs_kind=_abi.RHS_F4, lb=lb, ub=ub, mlp_dims=np.array(YEAST_MLP_DIMS),
+                     mlp_in_idx=np.arange(ns), mlp_params=pnn, mlp_act_out=0,
+                     aug_src=np.concatenate([np.arange(ns), -1 - np.arange(ns_ - ns)]), w_J=w_J)
+
+
+def yeast_opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2, n_save=300, t1=5.0, abstol=1e-6, reltol=1e-3, **kw) -> SolveOpts:
+    """tspan [0, 5], 300 saves (:24-27,74-75); AutoTsit5(TRBDF2(autodiff=false)) (:33); the script's `atol=`/`rtol=` keywords
+    fall back to the solver defaults; predictions clamped to [lb, ub] (:155)"""
+    kw.setdefault("pred_clamp", (1e-5, 100.0))
+    return SolveOpts(saveat=np.linspace(0.0, t1, n_save), t0=0.0, t1=t1, alg=alg, abstol=abstol, reltol=reltol,
+                     maxiters=100000, obs_idx=np.arange(YEAST_NS), **kw)
+
+
+def mlp_reference(dims, params, x, act_out=0):
+    """numpy restatement of the Flux chain (for tests): gelu hidden layers (NNlib's tanh form), softplus / exp output"""
+    a = np.asarray(x, dtype=np.float64)
+    off = 0
+    L = len(dims) - 1
+    for l in range(L):
+        din, dout = dims[l], dims[l + 1]
+        W = params[off:off + din * dout].reshape(dout, din, order="F"); off += din * dout
+        b = params[off:off + dout]; off += dout
+        s = W @ a + b
+        if l + 1 < L:
+            a = 0.5 * s * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (s + 0.044715 * s ** 3)))
+        else:
+            a = np.log1p(np.exp(-np.abs(s))) + np.maximum(s, 0.0) if act_out == 0 else np.exp(s)
+    return a

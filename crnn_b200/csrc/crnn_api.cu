@@ -68,8 +68,13 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   P.beta2_ros = o->beta2 > 0 ? o->beta2 : 2.0 / (5.0 * 2.0);
   P.beta1_ros = o->beta1 > 0 ? o->beta1 : 7.0 / (10.0 * 2.0);
   const size_t n_r2o = (n + 1) / 2 + 1;
+  // F4: MLP parameters | w_J | mlp_in_idx, aug_src (ints packed behind)
+  const bool f4 = (m->rhs_kind == CRNN_RHS_F4_MLP_AUG);
+  size_t n_mlp_par = 0;
+  if (f4) for (int l = 0; l < m->mlp_n_layers; ++l) n_mlp_par += (size_t)m->mlp_dims[l] * m->mlp_dims[l + 1] + m->mlp_dims[l + 1];
+  const size_t n_mlp = f4 ? n_mlp_par + ns + (size_t)(m->mlp_dims[0] + nin + 1) / 2 + 2 : 0;
   std::vector<double> blob((size_t)nin * KW_MAXN + nr + (size_t)ns * nr + o->n_save + n_r2o + extra.size() + 2 +
-                           (f2 ? ns + 3 * (size_t)ntab : 0) + (m->w_obs ? nr : 0), 0.0);
+                           (f2 ? ns + 3 * (size_t)ntab : 0) + (m->w_obs ? nr : 0) + n_mlp, 0.0);
   double* p_winT = blob.data();
   double* p_wb = p_winT + (size_t)nin * KW_MAXN;
   double* p_wout = p_wb + nr;
@@ -95,10 +100,26 @@ int build_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int orde
   }
   double* p_obs = p_f2 + (f2 ? ns + 3 * (size_t)ntab : 0);
   if (m->w_obs) for (int j = 0; j < nr; ++j) p_obs[j] = m->w_obs[j];
+  double* p_mlp = p_obs + (m->w_obs ? nr : 0);
+  if (f4) {
+    for (size_t q = 0; q < n_mlp_par; ++q) p_mlp[q] = m->mlp_params[q];
+    for (int i = 0; i < ns; ++i) p_mlp[n_mlp_par + i] = m->w_J ? m->w_J[i] * (m->out_scale ? m->out_scale[i] : 1.0) : 0.0;
+    int* pi = reinterpret_cast<int*>(p_mlp + n_mlp_par + ns);
+    for (int i = 0; i < m->mlp_dims[0]; ++i) pi[i] = m->mlp_in_idx[i];
+    for (int i = 0; i < nin; ++i) pi[m->mlp_dims[0] + i] = m->aug_src[i];
+  }
   CK(cfgbuf.reserve(std::max<size_t>(blob.size() * sizeof(double), 4096)));
   CK(cudaMemcpyAsync(cfgbuf.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   double* d = cfgbuf.as<double>();
   P.w_obs = m->w_obs ? d + (p_obs - blob.data()) : nullptr;
+  if (f4) {
+    const double* d_mlp = d + (p_mlp - blob.data());
+    P.mlp_layers = m->mlp_n_layers; P.mlp_act_out = m->mlp_act_out;
+    for (int l = 0; l <= m->mlp_n_layers; ++l) P.mlp_dims[l] = m->mlp_dims[l];
+    P.mlp_params = d_mlp; P.w_J = m->w_J ? d_mlp + n_mlp_par : nullptr;
+    P.mlp_in_idx = reinterpret_cast<const int*>(d_mlp + n_mlp_par + ns);
+    P.aug_src = P.mlp_in_idx + m->mlp_dims[0];
+  }
   P.w_inT = d; P.w_b = d + (p_wb - blob.data()); P.w_out = d + (p_wout - blob.data());
   P.saveat = d + (p_save - blob.data());
   P.row2obs = reinterpret_cast<const int*>(d + (p_save - blob.data()) + o->n_save);
@@ -123,7 +144,9 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
   const bool tab = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);
   const bool trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);   // TRBDF2 as the stiff stepper
   if (m->w_obs && !tab) return fail(h, CRNN_ERR_UNSUPPORTED, "the observable post-map of the predict path is built for the tabulated-input flavours (F5: Cathode)");
-  auto kern = trb ? (tab ? (m->w_obs ? k_wide_solve<WARPS, true, 1, true> : k_wide_solve<WARPS, true, 1, false>) : k_wide_solve<WARPS, false, 1, false>)
+  auto kern = (m->rhs_kind == CRNN_RHS_F4_MLP_AUG)   // MLP-augmented inputs (yeast / QSSA): own instantiations, finite-difference Jacobian
+                  ? (trb ? k_wide_solve<WARPS, false, 1, false, true> : k_wide_solve<WARPS, false, 0, false, true>)
+              : trb ? (tab ? (m->w_obs ? k_wide_solve<WARPS, true, 1, true> : k_wide_solve<WARPS, true, 1, false>) : k_wide_solve<WARPS, false, 1, false>)
                   : (tab ? (m->w_obs ? k_wide_solve<WARPS, true, 0, true> : k_wide_solve<WARPS, true, 0, false>) : k_wide_solve<WARPS, false, 0, false>);
   const size_t smem = sizeof(WideBlock) + WARPS * sizeof(WideWarp);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -146,7 +169,8 @@ int solve_wide(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const Ho
 
 // KenCarp4 (BASELINE config 5): generic-dimension warp-per-trajectory kernel, value path only.
 int solve_kencarp4(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const HostIO& io, int64_t N) {
-  if (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs) return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 serves F0 / F1 / F2 without an observable post-map");
+  if (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->rhs_kind == CRNN_RHS_F4_MLP_AUG || m->w_obs)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "KenCarp4 serves F0 / F1 / F2 without an observable post-map");
   WideP P{};
   cudaStream_t st = o->buffers_on_device ? (cudaStream_t)o->stream : h->s_compute;
   int rcw = build_wide(h, m, o, 4, {}, st, P, nullptr);
@@ -422,6 +446,8 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
                    const double* yscale, int32_t loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
   int rc = validate(h, m, o, N);
   if (rc) return rc;
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the MLP-augmented RHS (F4) is served on the predict path (crnn_solve_batch) only");
   if (N > 0 && (!io.u0 || !io.data || !io.loss)) return fail(h, CRNN_ERR_BAD_ARG, "null u0/data/loss");
   if (np < 0 || (np > 0 && !dW_dp)) return fail(h, CRNN_ERR_BAD_ARG, "bad seed matrix");
   if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG && loss_kind != CRNN_LOSS_MSE)
@@ -800,7 +826,7 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o, co
   CK(cudaSetDevice(h->device));
   HostIO io{u0, n_save_used, nullptr, pred, nullptr, n_saved, retcode, stats};
   if (o->alg == CRNN_ALG_KENCARP4) return solve_kencarp4(h, m, o, io, N);
-  if (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) return solve_wide(h, m, o, io, N);
+  if (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2 || m->rhs_kind == CRNN_RHS_F4_MLP_AUG) return solve_wide(h, m, o, io, N);
   // dimension-specialised thread-per-trajectory kernels for the instantiated configurations ...
   const char* force = std::getenv("CRNN_B200_FORCE_WIDE");
   if (m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP && !(force && force[0] == '1')) {

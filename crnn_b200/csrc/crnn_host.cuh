@@ -157,11 +157,23 @@ inline int validate(crnn_handle* h, const crnn_model* m, const crnn_opts* o, int
   if (!m || !o) return fail(h, CRNN_ERR_BAD_ARG, "null model/opts");
   if (N < 0) return fail(h, CRNN_ERR_BAD_ARG, "negative N");
   if (m->rhs_kind != CRNN_RHS_F0 && m->rhs_kind != CRNN_RHS_F1_ARRH_TSTATE && m->rhs_kind != CRNN_RHS_F2_MASSFRAC_TP &&
-      m->rhs_kind != CRNN_RHS_F5_TRAMP)
+      m->rhs_kind != CRNN_RHS_F5_TRAMP && m->rhs_kind != CRNN_RHS_F4_MLP_AUG)
     return fail(h, CRNN_ERR_UNSUPPORTED, "rhs_kind not supported");
   const bool f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);  // inputs from T(t) tables
-  if (m->n_in != m->n_state + (f2 ? 2 : 0) || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
+  const bool f4 = (m->rhs_kind == CRNN_RHS_F4_MLP_AUG);
+  if ((!f4 && m->n_in != m->n_state + (f2 ? 2 : 0)) || m->n_state != m->n_species + (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE ? 1 : 0))
     return fail(h, CRNN_ERR_BAD_ARG, "inconsistent n_state / n_species / n_in for rhs_kind");
+  if (f4) {
+    if (m->mlp_n_layers < 1 || m->mlp_n_layers > 8 || !m->mlp_dims || !m->mlp_in_idx || !m->mlp_params || !m->aug_src || m->w_obs)
+      return fail(h, CRNN_ERR_BAD_ARG, "F4 needs mlp_dims / mlp_in_idx / mlp_params / aug_src (1..8 layers) and no observable post-map");
+    if (m->n_in < 1 || m->n_in > 32) return fail(h, CRNN_ERR_BAD_ARG, "F4: n_in must be 1..32");
+    for (int l = 0; l <= m->mlp_n_layers; ++l)
+      if (m->mlp_dims[l] < 1 || m->mlp_dims[l] > 32) return fail(h, CRNN_ERR_BAD_ARG, "F4: MLP layer widths must be 1..32");
+    for (int i = 0; i < m->mlp_dims[0]; ++i)
+      if (m->mlp_in_idx[i] < 0 || m->mlp_in_idx[i] >= m->n_state) return fail(h, CRNN_ERR_BAD_ARG, "F4: mlp_in_idx out of range");
+    for (int i = 0; i < m->n_in; ++i)
+      if (m->aug_src[i] >= m->n_state || m->aug_src[i] < -m->mlp_dims[m->mlp_n_layers]) return fail(h, CRNN_ERR_BAD_ARG, "F4: aug_src out of range");
+  }
   if (f2) {
     if (!m->tab_t || !m->tab_T || m->n_tab < 2 || (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (!m->mw || !m->tab_P)))
       return fail(h, CRNN_ERR_BAD_ARG, "F2 needs mw and the tab_t / tab_T / tab_P tables, F5 tab_t / tab_T (n_tab >= 2)");

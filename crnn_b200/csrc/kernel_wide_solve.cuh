@@ -21,7 +21,7 @@ namespace crnn {
 // STIFF selects the stiff stepper: 0 = Rosenbrock23 (alg ROSENBROCK23 / AUTO_TSIT5_ROS23), 1 = TRBDF2 (alg TRBDF2 /
 // AUTO_TSIT5_TRBDF2: Cathode/src/network.jl:102, yeast_glycolysis.jl:33) - separate instantiations, so neither pays for the
 // other's code (these kernels are instruction-fetch bound).
-template <int WARPS, bool F2, int STIFF = 0, bool OBS = false>
+template <int WARPS, bool F2, int STIFF = 0, bool OBS = false, bool MLP = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 3 : 2)
 k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
              long long ntraj, double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
@@ -74,7 +74,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         __syncwarp();
         const double rkeep = ww.r[lane];
         WideAux ao; int seg2 = tab_seg;
-        (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, tsv, y, ao, seg2);
+        (void)wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, tsv, y, ao, seg2);
         const double obs = wsum(lane < nr ? __ldg(P.w_obs + lane) * ww.r[lane] : 0.0);
         __syncwarp();
         ww.r[lane] = rkeep;
@@ -84,7 +84,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       }
       if (mypred && my_obs >= 0) mypred[my_obs + P.n_obs * ks] = clampd(y, P.pred_lo, P.pred_hi);
     };
-    KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0, u, a0, tab_seg); ++n_rhs;
+    KS(0) = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t0, u, a0, tab_seg); ++n_rhs;
     ww.r0[lane] = ww.r[lane];
     // ---- initial step (Hairer-Wanner; the order of the FIRST algorithm) ----
     double dt;
@@ -96,7 +96,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
       const double d0 = sqrt(wsum(a) / n), d1 = sqrt(wsum(b) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
       dt0 = jmin(dt0, dtmax);
-      const double f1p = wide_rhs<F2>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as, tab_seg); ++n_rhs;
+      const double f1p = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t0 + dt0, fma(dt0, f0, u), as, tab_seg); ++n_rhs;
       double c = 0.0;
       if (lane < n) { c = (f1p - f0) / sk; c *= c; }
       const double d2 = sqrt(wsum(c) / n) / dt0;
@@ -121,7 +121,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         else if (rosen && sw_count < -3) { dt = dt / 2.0; want = false; }
         if (want != rosen) {
           rosen = want;
-          KS(0) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t, u, a0, tab_seg); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
+          KS(0) = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t, u, a0, tab_seg); ++n_rhs;  // initialize!: fsalfirst = f(uprev)
           __syncwarp();
           ww.r0[lane] = ww.r[lane];
         }
@@ -144,7 +144,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
           const double y = fma(dt, acc, u);
           if (s == 5) g6 = y;
           un = y;
-          KS(s) = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as, tab_seg); ++n_rhs;
+          KS(s) = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t + tsc::C[s] * dt, y, as, tab_seg); ++n_rhs;
         }
         double acc = tsc::BT[0] * KS(0);
 #pragma unroll
@@ -161,7 +161,10 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         constexpr double s2 = 1.4142135623730951, gam = 2.0 - s2, d = 1.0 - s2 / 2.0, w = s2 / 4.0;
         constexpr double bt1 = (1.0 - s2) / 3.0, bt2 = 1.0 / 3.0, bt3 = (s2 - 2.0) / 3.0, al1 = -s2 / 2.0, al2 = 1.0 + s2 / 2.0;
         const double gdt = d * dt;
-        const double eig = wide_build_inv<F2>(P, sb, ww, lane, ww.r0, a0, gdt);
+        auto rhs_fd = [&](double tt, double yy) -> double { WideAux ax; return wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, tt, yy, ax, tab_seg); };
+        double eig;
+        if (MLP) { eig = wide_assemble_W_fd(P, ww, lane, t, u, gdt, rhs_fd); wide_invert(ww, lane, ns); }   // the scripts' autodiff=false
+        else eig = wide_build_inv<F2>(P, sb, ww, lane, ww.r0, a0, gdt);
         ++n_jac;
         if (autosw) eigen_est = eig;
         const double z1 = dt * KS(0);
@@ -180,7 +183,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
 #pragma unroll 1
             for (int it = 1; it <= 10; ++it) {
               const double yk = fma(d, zs, tmp);
-              double dz = fma(dt, wide_rhs<F2>(P, sb, ww, lane, my_mw, tst, yk, as, tab_seg), -zs); ++n_rhs;
+              double dz = fma(dt, wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, tst, yk, as, tab_seg), -zs); ++n_rhs;
               dz = wide_invmul(ww, lane, ns, dz);
               const double ndz = wrms(dz, u, yk);
               zs += dz;
@@ -195,8 +198,9 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
             if (!conv) {
               if (refreshed || __any_sync(0xffffffffu, lane < n && zs != zs)) break;
               refreshed = true;
-              (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, tst, fma(d, zs, tmp), as, tab_seg); ++n_rhs;
-              (void)wide_build_inv<F2>(P, sb, ww, lane, ww.r, as, gdt);
+              (void)wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, tst, fma(d, zs, tmp), as, tab_seg); ++n_rhs;
+              if (MLP) { (void)wide_assemble_W_fd(P, ww, lane, tst, fma(d, zs, tmp), gdt, rhs_fd); wide_invert(ww, lane, ns); }
+              else (void)wide_build_inv<F2>(P, sb, ww, lane, ww.r, as, gdt);
               ++n_jac;
             }
           }
@@ -212,15 +216,19 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
         const double g = d * dt;
         const double dTv = wide_time_deriv<F2>(P, sb, ww, lane, t, ww.r0, a0, tab_seg);
-        const double eig = wide_build_lu<F2>(P, sb, ww, lane, ww.r0, a0, g);
+        double eig;
+        if (MLP) {
+          auto rhs_fd = [&](double tt, double yy) -> double { WideAux ax; return wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, tt, yy, ax, tab_seg); };
+          eig = wide_assemble_W_fd(P, ww, lane, t, u, g, rhs_fd); wide_factor_lu(ww, lane, ns);
+        } else eig = wide_build_lu<F2>(P, sb, ww, lane, ww.r0, a0, g);
         ++n_jac;
         if (autosw) eigen_est = eig;
         const double f0 = KS(0);
         const double k1 = wide_lusolve(ww, lane, ns, fma(g, dTv, f0));
-        const double f1 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as, tab_seg); ++n_rhs;
+        const double f1 = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t + 0.5 * dt, fma(0.5 * dt, k1, u), as, tab_seg); ++n_rhs;
         const double k2 = wide_lusolve(ww, lane, ns, f1 - k1) + k1;
         un = fma(dt, k2, u);
-        const double f2 = wide_rhs<F2>(P, sb, ww, lane, my_mw, t + dt, un, as, tab_seg); ++n_rhs;
+        const double f2 = wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t + dt, un, as, tab_seg); ++n_rhs;
         const double k3 = wide_lusolve(ww, lane, ns, f2 - e32 * (k2 - f1) - 2.0 * (k1 - f0) + dt * dTv);
         e = dt / 6.0 * (k1 - 2.0 * k2 + k3);
         KS(1) = k1; KS(2) = k2; KS(5) = f2;
@@ -240,7 +248,7 @@ k_wide_solve(const __grid_constant__ WideP P, const double* __restrict__ u0, con
         const double dtnew = dt / (q >= P.qs_min && q <= P.qs_max ? 1.0 : q), tprev = t;  // steady-state dead-band
         t = snap_t(t + dt, tend);
         if (STIFF == 1 && rosen) {   // the next attempt's analytic Jacobian needs the RHS by-products at u_{n+1}
-          (void)wide_rhs<F2>(P, sb, ww, lane, my_mw, t, un, as, tab_seg); ++n_rhs;
+          (void)wide_rhs<F2, false, MLP>(P, sb, ww, lane, my_mw, t, un, as, tab_seg); ++n_rhs;
         }
         while (isave < nsave) {
           const double tsv = __ldg(P.saveat + isave);

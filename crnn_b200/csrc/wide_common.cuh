@@ -31,6 +31,13 @@ struct WideP {
   const double* tab_T;   // device [n_tab]
   const double* tab_P;   // device [n_tab]
   const double* w_obs;   // device [n_reac] or NULL: observable post-map y = sum_j w_obs[j] r_j(u(ts), ts) (k_wide_solve's saves)
+  // F4 (MLP-augmented inputs, yeast_glycolysis.jl:128-142 / rober_crnn_qssa.jl:111-126): device arrays, Flux.destructure order
+  int mlp_layers, mlp_act_out;
+  int mlp_dims[10];
+  const int* mlp_in_idx;     // [d0]
+  const int* aug_src;        // [n_in]
+  const double* mlp_params;
+  const double* w_J;         // [n_species] or NULL
 };
 
 // ---- shared by the lane-per-component kernels (k_wide_solve, k_tsit5_adjoint): F2 tables ----
@@ -166,9 +173,47 @@ struct WideAux {  // per-lane by-products of one RHS evaluation (what the Jacobi
   double chiC;     // F2: 1 if lb <= C_l <= ub
 };
 
+// F4: the value of input row `lane` of the CRNN - a state row or an output of the Flux MLP of the state (oracle mlp_eval):
+// lane k of a layer computes neuron k from the previous activations broadcast through shared memory (ww.ws / ww.bchi as scratch);
+// gelu in NNlib's tanh form, tanh(y) = 1 - 2 / (exp(2y) + 1), softplus = log(1 + exp(-|x|)) + max(x, 0) with the lean functions.
+template <class WW>
+__device__ __forceinline__ double wide_mlp_aug(const WideP& P, WW& ww, int lane, double y) {
+  __syncwarp();
+  ww.ws[lane] = y;
+  __syncwarp();
+  double a = lane < P.mlp_dims[0] ? ww.ws[__ldg(P.mlp_in_idx + lane)] : 0.0;
+  const double* w = P.mlp_params;
+#pragma unroll 1
+  for (int l = 0; l < P.mlp_layers; ++l) {
+    const int din = P.mlp_dims[l], dout = P.mlp_dims[l + 1];
+    __syncwarp();
+    ww.bchi[lane] = a;
+    __syncwarp();
+    double s = 0.0;
+    if (lane < dout) {
+      for (int i = 0; i < din; ++i) s = fma(__ldg(w + lane + dout * i), ww.bchi[i], s);
+      s += __ldg(w + din * dout + lane);
+      if (l + 1 < P.mlp_layers) {
+        const double th = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (s + 0.044715 * (s * s * s)))) + 1.0);
+        s = 0.5 * s * (1.0 + th);
+      } else {
+        s = P.mlp_act_out == 0 ? lean_log(1.0 + lean_exp(-fabs(s))) + (s > 0.0 ? s : 0.0) : lean_exp(s);
+      }
+    }
+    a = s;
+    w += din * dout + dout;
+  }
+  __syncwarp();
+  ww.bchi[lane] = a;
+  __syncwarp();
+  if (lane >= P.nin) return 0.0;
+  const int src = __ldg(P.aug_src + lane);
+  return src >= 0 ? ww.ws[src] : ww.bchi[-1 - src];
+}
+
 // f(y, t): lane i holds y_i in, f_i out; leaves x in ww.x and r in ww.r.  SPARSE: the instantiation that consults the index
 // lists (large models; small ones keep the dense-only code - these kernels are instruction-fetch bound).
-template <bool F2, bool SPARSE = false, class WW>
+template <bool F2, bool SPARSE = false, bool MLP = false, class WW>
 __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, WW& ww, int lane, double mw,
                                            double t, double y, WideAux& a, int& seg) {
   const int ns = P.ns, nin = P.nin, nr = P.nr;
@@ -195,6 +240,9 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
       xi = lean_log(tv.T);
     }
     a.inv_rho = 1.0 / rho;
+  } else if (MLP) {
+    const double v = wide_mlp_aug(P, ww, lane, y);
+    if (lane < nin) xi = lean_log(clampd(v, P.lb, P.ub));   // no dx: this flavour's Jacobian is taken by finite differences
   } else if (isp) {
     const double uc = clampd(y, P.lb, P.ub);
     xi = lean_log(uc);
@@ -233,6 +281,7 @@ __device__ __forceinline__ double wide_rhs(const WideP& P, const WideBlock& sb, 
   }
   a.wdot = f;
   if (F2) f = f / rho;
+  if (MLP && isp && P.w_J) f += __ldg(P.w_J + lane);   // .+ w_J (yeast_glycolysis.jl:131); out_scale is folded into w_out only
   return f;
 }
 
@@ -319,14 +368,10 @@ __device__ __forceinline__ double wide_assemble_W(const WideP& P, const WideBloc
   return eig;
 }
 
-// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
-// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
-template <bool F2, class WW>
-__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WW& ww, int lane,
-                                                const double* rsrc, const WideAux& a, double gdt) {
-  const int ns = P.ns;
+// cooperative LU of the ns x ns matrix in ww.A (lane = row, arg-max pivoting by shuffles, reciprocal diagonal in ww.dinv)
+template <class WW>
+__device__ __forceinline__ void wide_factor_lu(WW& ww, int lane, int ns) {
   const bool isp = lane < ns;
-  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);
   ww.perm[lane] = lane;
   __syncwarp();
   for (int k = 0; k < ns; ++k) {
@@ -354,6 +399,39 @@ __device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock&
     }
     __syncwarp();
   }
+}
+
+// W = I - gdt*J(u) from the RHS by-products (r in rsrc, this lane's aux), cooperative LU with partial
+// pivoting (first strict maximum, like oracle lu_factor); returns opnorm(J, Inf).
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_build_lu(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                                const double* rsrc, const WideAux& a, double gdt) {
+  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);
+  wide_factor_lu(ww, lane, P.ns);
+  return eig;
+}
+
+// W = I - gdt*J(u) with J by FORWARD FINITE DIFFERENCES (F4: TRBDF2(autodiff=false) / Rosenbrock23(autodiff=false),
+// yeast_glycolysis.jl:33, rober_crnn_qssa.jl:30; oracle jac_value): step max(sqrt(eps)|u_l|, sqrt(eps)), f(u) evaluated afresh,
+// the n + 1 evaluations not counted in n_rhs.  `rhs(t, y)` is the caller's evaluation; returns opnorm(J, Inf).
+template <class WW, class RHS>
+__device__ __forceinline__ double wide_assemble_W_fd(const WideP& P, WW& ww, int lane, double t, double u, double gdt, RHS rhs) {
+  const int n = P.n, ns = P.ns;
+  const double f0 = rhs(t, u);
+  double rowsum = 0.0;
+#pragma unroll 1
+  for (int l = 0; l < n; ++l) {
+    const double ul = __shfl_sync(0xffffffffu, u, l);
+    const double eps = fmax(1.4901161193847656e-8 * fabs(ul), 1.4901161193847656e-8);
+    const double fl = rhs(t, lane == l ? u + eps : u);
+    const double Jil = (fl - f0) / eps;
+    if (lane < n) {
+      rowsum += fabs(Jil);
+      if (l < ns && lane < ns) ww.A[lane][l] = (lane == l ? 1.0 : 0.0) - gdt * Jil;
+    }
+  }
+  const double eig = warp_max(rowsum);
+  __syncwarp();
   return eig;
 }
 
@@ -441,16 +519,10 @@ __device__ __noinline__ void wide_gj_regs(WW& ww, int lane, int ns) {
   __syncwarp();
 }
 
-// W^{-1} in place of W (ww.A) by Gauss-Jordan elimination with partial pivoting, lane = row.  A solve then is one
-// mat-vec with independent loads (wide_invmul) instead of 2*ns dependent shuffle + FMA steps (wide_lusolve): the
-// simplified-Newton iterations of k_kencarp4_wide call it ~20 times per factorisation, and those dependent chains were
-// what bound that kernel (DESIGN.md §3.2c).  Mirrored by the oracle's named switch crnn_oracle_set_kc4_inverse.
-template <bool F2, class WW>
-__device__ __forceinline__ double wide_build_inv(const WideP& P, const WideBlock& sb, WW& ww, int lane,
-                                                 const double* rsrc, const WideAux& a, double gdt) {
-  const int ns = P.ns;
+// the ns x ns matrix in ww.A replaced by its inverse
+template <class WW>
+__device__ __forceinline__ void wide_invert(WW& ww, int lane, int ns) {
   const bool isp = lane < ns;
-  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);   // opnorm(J, Inf)
   if (ns > 16) wide_gj_regs(ww, lane, ns);
   else
   for (int k = 0; k < ns; ++k) {
@@ -484,6 +556,17 @@ __device__ __forceinline__ double wide_build_inv(const WideP& P, const WideBlock
     if (p != k && isp) { const double tmpv = ww.A[lane][k]; ww.A[lane][k] = ww.A[lane][p]; ww.A[lane][p] = tmpv; }
   }
   __syncwarp();
+}
+
+// W^{-1} in place of W (ww.A) by Gauss-Jordan elimination with partial pivoting, lane = row.  A solve then is one
+// mat-vec with independent loads (wide_invmul) instead of 2*ns dependent shuffle + FMA steps (wide_lusolve): the
+// simplified-Newton iterations of k_kencarp4_wide call it ~20 times per factorisation, and those dependent chains were
+// what bound that kernel (DESIGN.md §3.2c).  Mirrored by the oracle's named switch crnn_oracle_set_kc4_inverse.
+template <bool F2, class WW>
+__device__ __forceinline__ double wide_build_inv(const WideP& P, const WideBlock& sb, WW& ww, int lane,
+                                                 const double* rsrc, const WideAux& a, double gdt) {
+  const double eig = wide_assemble_W<F2>(P, sb, ww, lane, rsrc, a, gdt);   // opnorm(J, Inf)
+  wide_invert(ww, lane, P.ns);
   return eig;
 }
 

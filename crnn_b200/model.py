@@ -35,6 +35,13 @@ class CRNNModel:
     tab_P: np.ndarray | None = None
     # observable post-map: y = sum_j w_obs[j] r_j (heat release, Cathode/src/network.jl:82-91,121); None: rows of u
     w_obs: np.ndarray | None = None
+    # F4 (yeast_glycolysis.jl:128-142, rober_crnn_qssa.jl:111-126): a Flux MLP of the state supplies the hidden input rows
+    mlp_dims: np.ndarray | None = None      # [L + 1] layer widths d0 .. d_L
+    mlp_in_idx: np.ndarray | None = None    # [d0] state rows fed to the MLP
+    mlp_params: np.ndarray | None = None    # Flux.destructure order: per layer W (d_out x d_in, column-major), b
+    mlp_act_out: int = 0                    # 0 softplus, 1 exp; hidden layers: gelu
+    aug_src: np.ndarray | None = None       # [n_in]: >= 0 state row, < 0: MLP output -1 - value
+    w_J: np.ndarray | None = None           # [n_species] additive source term
 
     def __post_init__(self):
         self.w_in = np.asarray(self.w_in, dtype=np.float64)
@@ -56,6 +63,20 @@ class CRNNModel:
             self.w_obs = np.ascontiguousarray(self.w_obs, dtype=np.float64).reshape(-1)
             if self.w_obs.shape[0] != nr:
                 raise ValueError("w_obs must have n_reac entries")
+        if self.rhs_kind == _abi.RHS_F4:
+            self.mlp_dims = np.ascontiguousarray(self.mlp_dims, dtype=np.int32).reshape(-1)
+            self.mlp_in_idx = np.ascontiguousarray(self.mlp_in_idx, dtype=np.int32).reshape(-1)
+            self.mlp_params = np.ascontiguousarray(self.mlp_params, dtype=np.float64).reshape(-1)
+            self.aug_src = np.ascontiguousarray(self.aug_src, dtype=np.int32).reshape(-1)
+            d = self.mlp_dims
+            if d.size < 2 or d.max() > 32 or self.mlp_in_idx.size != d[0] or self.aug_src.size != n_in:
+                raise ValueError("F4: mlp_dims [L+1] (<= 32 each), mlp_in_idx [d0], aug_src [n_in]")
+            if self.mlp_params.size != int(sum(d[l] * d[l + 1] + d[l + 1] for l in range(d.size - 1))):
+                raise ValueError("F4: mlp_params must hold W and b of every layer (Flux.destructure order)")
+            if self.aug_src.max() >= ns or self.aug_src.min() < -int(d[-1]) or self.mlp_in_idx.max() >= ns:
+                raise ValueError("F4: aug_src / mlp_in_idx out of range")
+            if self.w_J is not None:
+                self.w_J = np.ascontiguousarray(self.w_J, dtype=np.float64).reshape(-1)
         if self.rhs_kind == _abi.RHS_F5:
             if n_in != ns + 2:
                 raise ValueError("F5 needs n_in == n_species + 2 (Arrhenius and log T rows)")
@@ -123,6 +144,11 @@ class CRNNModel:
         if self.w_obs is not None:
             keep.append(self.w_obs)
             m.w_obs = dptr(self.w_obs)
+        if self.rhs_kind == _abi.RHS_F4:
+            keep += [self.mlp_dims, self.mlp_in_idx, self.mlp_params, self.aug_src, self.w_J]
+            m.mlp_n_layers, m.mlp_act_out = int(self.mlp_dims.size - 1), int(self.mlp_act_out)
+            m.mlp_dims, m.mlp_in_idx, m.aug_src = iptr(self.mlp_dims), iptr(self.mlp_in_idx), iptr(self.aug_src)
+            m.mlp_params, m.w_J = dptr(self.mlp_params), dptr(self.w_J)
         if self.rhs_kind in (_abi.RHS_F2, _abi.RHS_F5):
             keep += [self.mw, self.tab_t, self.tab_T, self.tab_P]
             m.n_tab = int(self.tab_t.size)

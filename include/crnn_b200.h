@@ -66,6 +66,12 @@ enum crnn_rhs_kind {
                                   Y=clamp(u,lb,ub), rho=P/(8314.46261815324 T sum(Y/MW)), C=rho Y/MW 1e3,
                                   x=[log clamp(C,lb,ub); -1/(R T); log T], du = W_out*exp(W_in'x+b) .* MW / rho .* out_scale:
                                   HyChem/crnn_pyrolysis_mass.jl:107-114,121-131 */
+  CRNN_RHS_F4_MLP_AUG = 4,     /* CRNN whose input vector is AUGMENTED by a small MLP of the state ("neural closure" for hidden species):
+                                  u_ = [u ; mlp(u)] (yeast-glycolysis/yeast_glycolysis.jl:128-142: 7 observed + 5 hidden species, du =
+                                  (W_out*exp(W_in'*log(clamp(u_,lb,ub)) + b))[1:ns] .+ w_J) or u_ = [u1 ; mlp(u[1,3]) ; u3]
+                                  (robertson/rober_crnn_qssa.jl:111-126); see the mlp_* / aug_src / w_J fields.  Predict path
+                                  (crnn_solve_batch); the stiff steppers use the scripts' own FINITE-DIFFERENCE Jacobian
+                                  (TRBDF2 / Rosenbrock23(autodiff=false)) */
   CRNN_RHS_F5_TRAMP = 3        /* species under a tabulated temperature programme T(t), no density map:
                                   x=[log clamp(u,lb,ub); -1/(gas_R T(t)); log T(t)], du = W_out*exp(W_in'x+b) .* out_scale:
                                   Cathode/src/network.jl:68-80 and Cathode_NCM333_UQ/src_333/network.jl:153-168 (there
@@ -138,6 +144,15 @@ typedef struct crnn_model {
    * Cathode/src/network.jl:82-91,121 (n_obs must be 1, obs_idx is ignored).  The seed matrix then carries n_reac extra
    * rows, ordered [vec(w_in); w_b; vec(w_out); w_obs]. */
   const double* w_obs;     /* [n_reac] or NULL */
+  /* F4 only (zero / NULL otherwise).  The MLP is Flux's Chain(Dense(d0, d1, gelu), ..., Dense(d_{L-1}, d_L, act_out)) with its
+   * parameters in Flux.destructure order: per layer W (d_out x d_in, column-major), then b (yeast_glycolysis.jl:137-142). */
+  int32_t mlp_n_layers;    /* L >= 1 */
+  int32_t mlp_act_out;     /* last layer: 0 softplus (yeast :141), 1 exp (rober_crnn_qssa.jl:120); hidden layers: gelu (tanh form) */
+  const int32_t* mlp_dims;   /* [L + 1]: d0 (number of state rows fed to the MLP), d1, ..., d_L (number of hidden species); all <= 32 */
+  const int32_t* mlp_in_idx; /* [d0] 0-based state rows fed to the MLP (yeast: all; QSSA: rows 0 and 2) */
+  const double* mlp_params;  /* [sum_l d_l*d_{l+1} + d_{l+1}] */
+  const int32_t* aug_src;    /* [n_in] source of input row k of the CRNN: >= 0 state row, < 0 MLP output -1 - value */
+  const double* w_J;         /* [n_species] additive source term (yeast :131,143) or NULL */
 } crnn_model;
 
 typedef struct crnn_opts {

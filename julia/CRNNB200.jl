@@ -21,6 +21,8 @@ struct CModel
     out_scale::Ptr{Float64}; w_in::Ptr{Float64}; w_b::Ptr{Float64}; w_out::Ptr{Float64}
     mw::Ptr{Float64}; tab_t::Ptr{Float64}; tab_T::Ptr{Float64}; tab_P::Ptr{Float64}   # F2 (HyChem) / F5 (Cathode) only
     w_obs::Ptr{Float64}            # observable post-map (heat release, Cathode/src/network.jl:82-91) or C_NULL
+    mlp_n_layers::Int32; mlp_act_out::Int32                      # F4 (yeast / QSSA: an MLP supplies the hidden species); 0 otherwise
+    mlp_dims::Ptr{Int32}; mlp_in_idx::Ptr{Int32}; mlp_params::Ptr{Float64}; aug_src::Ptr{Int32}; w_J::Ptr{Float64}
 end
 struct COpts
     alg::Int32; sens_mode::Int32; err_norm_includes_sens::Int32; n_save::Int32; n_obs::Int32
@@ -106,7 +108,8 @@ function with_structs(f, s::Setup, w_in, w_b, w_out)
         f2p(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
         m = CModel(n_state, ns, n_in, nr, s.rhs_kind, length(s.tab_t), s.lb, s.ub, s.gas_R,
                    isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out),
-                   f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P), f2p(s.w_obs))
+                   f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P), f2p(s.w_obs),
+                   0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
         o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),

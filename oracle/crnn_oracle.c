@@ -87,6 +87,8 @@ typedef struct {
   /* F2 only */
   double chi[MAXN], chiC[MAXN], Y[MAXN], wdot[MAXN];
   double rho, S, T, P, Tdot, Pdot;
+  /* F4 only: the evaluation point (its Jacobian is taken by finite differences) */
+  double u_at[MAXN], t_at;
 } rhs_cache;
 
 /* Julia's min/max propagate NaN (C fmin/fmax drop it): a NaN RHS must surface as a NaN dt. */
@@ -96,6 +98,35 @@ static inline double jmax(double a, double b) { return a > b ? a : (b >= a ? b :
 static inline double clampd(double v, double lo, double hi) {
   /* Julia Base.clamp: ifelse(x > hi, hi, ifelse(x < lo, lo, x)) */
   return v > hi ? hi : (v < lo ? lo : v);
+}
+
+/* ---- F4: the MLP that supplies the hidden species (yeast-glycolysis/yeast_glycolysis.jl:137-142, robertson/rober_crnn_qssa.jl:
+ * 114-121): Flux's Chain(Dense(d0, d1, gelu), ..., Dense(d_{L-1}, d_L, softplus | exp)), parameters in Flux.destructure order
+ * (per layer W [d_out x d_in] column-major, then b).  gelu is NNlib's tanh form 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))),
+ * softplus its log1p(exp(-|x|)) + relu(x).  In shared-math mode tanh / log1p are spelled with the kernels' exp / log. */
+static double m_tanh(double y) { return g_shared_math ? 1.0 - 2.0 / (m_exp(2.0 * y) + 1.0) : tanh(y); }
+static double act_gelu(double x) { return 0.5 * x * (1.0 + m_tanh(0.7978845608028654 * (x + 0.044715 * (x * x * x)))); }
+static double act_softplus(double x) {
+  const double e = m_exp(-fabs(x));
+  return (g_shared_math ? m_log(1.0 + e) : log1p(e)) + (x > 0.0 ? x : 0.0);
+}
+static void mlp_eval(const crnn_model* m, const double* u, double* h) {
+  double a[MAXN], b[MAXN];
+  const int L = m->mlp_n_layers;
+  for (int i = 0; i < m->mlp_dims[0]; ++i) a[i] = u[m->mlp_in_idx[i]];
+  const double* w = m->mlp_params;
+  for (int l = 0; l < L; ++l) {
+    const int din = m->mlp_dims[l], dout = m->mlp_dims[l + 1];
+    for (int k = 0; k < dout; ++k) {
+      double s = 0.0;
+      for (int i = 0; i < din; ++i) s += w[k + dout * i] * a[i];   /* W * x */
+      s += w[din * dout + k];                                        /* .+ b */
+      b[k] = (l + 1 < L) ? act_gelu(s) : (m->mlp_act_out == 0 ? act_softplus(s) : m_exp(s));
+    }
+    memcpy(a, b, sizeof(double) * dout);
+    w += din * dout + dout;
+  }
+  memcpy(h, a, sizeof(double) * m->mlp_dims[L]);
 }
 
 /* RHS value.  F0: case1/case1.jl:80-83, case3/case3.jl:162-166,
@@ -130,6 +161,18 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
     k->x[ns] = -1.0 / m->gas_R / k->T;                     /* - 1 / R / T, :128 */
     k->x[ns + 1] = m_log(k->T);
     k->dx[ns] = k->dx[ns + 1] = 0.0; k->d2x[ns] = k->d2x[ns + 1] = 0.0;
+  } else if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) {
+    /* u_ = vcat(u, rep(u)) (yeast_glycolysis.jl:129) / vcat(u[1], rep(u[[1,3]]), u[3]) (rober_crnn_qssa.jl:124):
+     * input row k of the CRNN is a state row or an MLP output; du = (w_out * exp(w_in' log clamp(u_) + w_b))[1:ns] .+ w_J */
+    double h[MAXN];
+    mlp_eval(m, u, h);
+    for (int q = 0; q < nin; ++q) {
+      const int src = m->aug_src[q];
+      const double v = src >= 0 ? u[src] : h[-1 - src];
+      k->x[q] = m_log(clampd(v, m->lb, m->ub));
+      k->dx[q] = 0.0; k->d2x[q] = 0.0;   /* no analytic Jacobian for this flavour: jac_value takes finite differences */
+    }
+    memcpy(k->u_at, u, sizeof(double) * c->n); k->t_at = t;
   } else {
     for (int i = 0; i < ns; ++i) {
       double uc = clampd(u[i], m->lb, m->ub);
@@ -155,6 +198,7 @@ static void rhs_value(const ctx_t* c, double t, const double* u, double* du, rhs
     for (int j = 0; j < nr; ++j) s += m->w_out[i + ns * j] * k->r[j];
     k->wdot[i] = s;
     if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP) s = s * m->mw[i] / k->rho;   /* wdot * l_MW / density, :130 */
+    if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG && m->w_J) s += m->w_J[i];          /* .+ w_J, yeast_glycolysis.jl:131 */
     du[i] = m->out_scale ? s * m->out_scale[i] : s;
   }
   for (int i = ns; i < c->n; ++i) du[i] = 0.0; /* vcat(..., 0.f0), case2.jl:117 */
@@ -244,6 +288,22 @@ static void jac_value(const ctx_t* c, const rhs_cache* k, double* J) {
   const crnn_model* m = c->m;
   int n = c->n, ns = c->ns, nin = c->nin, nr = c->nr;
   memset(J, 0, sizeof(double) * n * n);
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) {
+    /* TRBDF2(autodiff=false) / Rosenbrock23(autodiff=false) (yeast_glycolysis.jl:33, rober_crnn_qssa.jl:30): FiniteDiff's forward
+     * differences, step max(sqrt(eps) |u_l|, sqrt(eps)) [UPSTREAM-RECALL FiniteDiff.compute_epsilon(Val(:forward), ...)];
+     * the n extra evaluations are not counted in n_rhs */
+    double f0[MAXN], f1[MAXN], up[MAXN];
+    rhs_cache kk;
+    rhs_value(c, k->t_at, k->u_at, f0, &kk);
+    for (int l = 0; l < n; ++l) {
+      memcpy(up, k->u_at, sizeof(double) * n);
+      const double eps = fmax(1.4901161193847656e-8 * fabs(up[l]), 1.4901161193847656e-8);
+      up[l] += eps;
+      rhs_value(c, k->t_at, up, f1, &kk);
+      for (int i = 0; i < n; ++i) J[i * n + l] = (f1[i] - f0[i]) / eps;
+    }
+    return;
+  }
   if (IS_TAB(m)) { /* column l = directional derivative along e_l (density coupling) */
     double e[MAXN], col[MAXN];
     for (int l = 0; l < n; ++l) {
@@ -1360,8 +1420,10 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
 
 static int check_dims(const crnn_model* m, const crnn_opts* o) {
   const int f2 = IS_TAB(m);
-  if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in != m->n_state + (f2 ? 2 : 0)) return CRNN_ERR_BAD_ARG;
-  if ((m->rhs_kind == CRNN_RHS_F0 || f2) && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
+  const int f4 = (m->rhs_kind == CRNN_RHS_F4_MLP_AUG);
+  if (m->n_state > MAXN || m->n_reac > MAXR || m->n_in > MAXN || (!f4 && m->n_in != m->n_state + (f2 ? 2 : 0))) return CRNN_ERR_BAD_ARG;
+  if ((m->rhs_kind == CRNN_RHS_F0 || f2 || f4) && m->n_species != m->n_state) return CRNN_ERR_BAD_ARG;
+  if (f4 && (m->mlp_n_layers < 1 || !m->mlp_dims || !m->mlp_in_idx || !m->mlp_params || !m->aug_src || m->w_obs)) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F1_ARRH_TSTATE && m->n_species + 1 != m->n_state) return CRNN_ERR_BAD_ARG;
   if (f2 && (!m->tab_t || !m->tab_T || m->n_tab < 2)) return CRNN_ERR_BAD_ARG;
   if (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP && (!m->mw || !m->tab_P)) return CRNN_ERR_BAD_ARG;
@@ -1407,6 +1469,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   int rc = check_dims(m, o);
   if (rc) return rc;
   if (o->alg == CRNN_ALG_KENCARP4 || o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) return CRNN_ERR_UNSUPPORTED; /* value path only */
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
   if (adjoint && (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs)) return CRNN_ERR_UNSUPPORTED; /* forward mode only */

@@ -114,6 +114,8 @@ def main():
         "case2": summarize(f"{REF}/case2/checkpoint/mymodel.bson"),
         "robertson": summarize(f"{REF}/robertson/checkpoint/mymodel.bson"),
         "gene": summarize(f"{REF}/gene-regulatory-network/checkpoint/mymodel.bson"),
+        # 164 CRNN + 130 MLP parameters (yeast-glycolysis/yeast_glycolysis.jl:112-114,137-145)
+        "yeast": summarize(f"{REF}/yeast-glycolysis/checkpoint/mymodel.bson"),
         # generating mechanisms (case2/case2.jl:52-53, robertson/rober_crnn.jl:52, case1/case1.jl:27)
         "case2_true": {"logA": [18.60, 19.13, 7.93], "Ea": [14.54, 14.42, 6.47], "R": 1.98720425864083e-3},
         "robertson_true": {"k": [4e-2, 3e7, 1e4]},
