@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=N_PER_GPU)
-    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3-5 (headline only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3-5 and the epoch-loop rates (headline only)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -609,7 +609,7 @@ def main():
                                  "n_compared": int(sample), "count_mismatches": int(bad.sum()),
                                  "loss_max_rel": float(np.max(np.abs(gpu_loss - ref["loss"]) / np.abs(ref["loss"]))),
                                  "grad_rel_l2": float(np.linalg.norm(gpu_grad - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]))}
-        if a.gpus == 1:
+        if a.gpus == 1 and not a.no_extra:
             out["train_loop"] = train_loop_rates(eng, c, opts, u0_h, data_h, yscale)
         if extra is not None:
             out["configs"] = extra
