@@ -85,6 +85,19 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// Partial pivoting: among the lanes with `cand`, the one whose `a` (>= 0) is largest, ties to the smallest `idx` (< 2^23);
+// returns (idx << 8) | lane of the winner in every lane.  Three REDUX instead of a 5-round butterfly of 64-bit shuffles.
+// (A NaN wins - the matrix is lost either way and the trajectory ends as Unstable.)
+__device__ __forceinline__ int warp_argmax_abs(double a, bool cand, int idx, int lane) {
+  const int hi = cand ? __double2hiint(a) : -1;
+  const int m1 = __reduce_max_sync(0xffffffffu, hi);
+  const bool c1 = cand && hi == m1;
+  const unsigned lo = c1 ? (unsigned)__double2loint(a) : 0u;
+  const unsigned m2 = __reduce_max_sync(0xffffffffu, lo);
+  const int key = (c1 && lo == m2) ? ((idx << 8) | lane) : 0x7fffffff;
+  return __reduce_min_sync(0xffffffffu, key);
+}
+
 template <int NK>   // NK stage-vector slots (k_wide_solve: 7; k_kencarp4_wide keeps its stages in registers: 0)
 struct alignas(16) WideWarpT {
   double A[KW_MAXN][KW_MAXN + 1];  // W and its LU (row i is lane i's; +1 pad: conflict-free columns)
@@ -375,14 +388,7 @@ __device__ __forceinline__ void wide_factor_lu(WW& ww, int lane, int ns) {
   ww.perm[lane] = lane;
   __syncwarp();
   for (int k = 0; k < ns; ++k) {
-    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
-    int bi = lane;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
+    const int bi = warp_argmax_abs((lane >= k && isp) ? fabs(ww.A[lane][k]) : 0.0, lane >= k && isp, lane, lane) >> 8;
     if (bi != k) {
       if (isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
       if (lane == 0) { const int tp = ww.perm[k]; ww.perm[k] = ww.perm[bi]; ww.perm[bi] = tp; }
@@ -474,14 +480,7 @@ __device__ __noinline__ void wide_gj_regs(WW& ww, int lane, int ns) {
   bool used = false;
 #pragma unroll 1
   for (int k = 0; k < ns; ++k) {
-    double best = (isp && !used) ? fabs(a[0]) : -1.0;
-    int key = (lidx << 8) | lane;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-      const int ok = __shfl_xor_sync(0xffffffffu, key, m);
-      if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
-    }
+    const int key = warp_argmax_abs(fabs(a[0]), isp && !used, lidx, lane);
     const int pl = key & 0xff, bi = key >> 8;   // the pivot row's lane / logical index
     if (lane != pl && lidx == k) lidx = bi;     // the exchange rows k <-> bi, in logical indices only
     if (lane == 0) ww.piv[k] = bi;
@@ -526,14 +525,7 @@ __device__ __forceinline__ void wide_invert(WW& ww, int lane, int ns) {
   if (ns > 16) wide_gj_regs(ww, lane, ns);
   else
   for (int k = 0; k < ns; ++k) {
-    double best = (lane >= k && isp) ? fabs(ww.A[lane][k]) : -1.0;
-    int bi = lane;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
+    const int bi = warp_argmax_abs((lane >= k && isp) ? fabs(ww.A[lane][k]) : 0.0, lane >= k && isp, lane, lane) >> 8;
     if (bi != k && isp) { const double tmpv = ww.A[k][lane]; ww.A[k][lane] = ww.A[bi][lane]; ww.A[bi][lane] = tmpv; }
     if (lane == 0) ww.piv[k] = bi;
     __syncwarp();
