@@ -61,5 +61,22 @@ eng.loss_grad_particles(cpb["model"], cpb["opts"], cpb["weights"], cpb["seeds"],
 done.append("particles F5 + observable")
 ms = cases.synthetic_stiff_model()
 eng.solve_batch(ms, cases.synthetic_stiff_opts(), cases.synthetic_stiff_u0(N)); done.append("kencarp4 30-state")
+# this session: TRBDF2 / AutoTsit5(TRBDF2) incl. the heat-release post-map, F4 (MLP inputs, finite-difference Jacobian), on-device training loop
+for alg in (_abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2):
+    eng.solve_batch(m, cases.hychem_opts(alg=alg), u0)
+    mc, _ = cp.model_for(cpb["particles"][0], 10.0, cpb["t_hi"])
+    eng.solve_batch(mc, cases.cathode_opts(cpb["opts"].saveat, alg=alg, pred_clamp=(-np.inf, np.inf)), np.tile(cpb["u0"][0], (8, 1)))
+    eng.solve_batch(make_problem("robertson", golden, 8)["true_model"], cases.CASES["robertson"].opts(alg=alg), make_problem("robertson", golden, 8)["u0"])
+done.append("trbdf2 + composite + observable")
+my = cases.yeast_model(np.array(golden["yeast"]["p"]))
+uy = cases.YEAST_IC_LB + np.random.default_rng(0).random((min(N, 16), 7)) * (cases.YEAST_IC_UB - cases.YEAST_IC_LB)
+for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_TRBDF2, _abi.ALG_TRBDF2):
+    eng.solve_batch(my, cases.yeast_opts(alg=alg, n_save=40), uy)
+done.append("F4 yeast")
+pb = make_problem("case2", golden, 20)
+ds = eng.dataset(pb["u0"], pb["data"])
+eng.train_steps(pb["model"], pb["opts"], ds, np.arange(20)[::-1].copy(), pb["yscale"], np.array(golden["case2"]["p"]), None, pb["loss_kind"],
+                batch=2, eta=5e-3, weight_decay=1e-6, expdecay=(5e-3, 0.5, 3, 1e-4), grad_max=0.5)
+ds.close(); done.append("train_steps")
 eng.close()
 print("sanitize_small ok:", "; ".join(done))
