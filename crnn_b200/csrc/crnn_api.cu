@@ -318,7 +318,7 @@ int gen_plan_seed(crnn_handle* h, const crnn_model* m, const double* dW_dp, int 
   return CRNN_OK;
 }
 
-int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_t& smem, long long& max_blocks, bool f2k,
+int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_t& smem, long long& max_blocks, bool f2k, bool trb,
                    void (**kern_out)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*,
                                      int*, crnn_stats*, unsigned long long*, const long long*, const long long*,
                                      const unsigned int*)) {
@@ -329,7 +329,7 @@ int gen_launch_cfg(crnn_handle* h, const crnn_model* m, int np, int& cols, size_
   smem = sizeof(GenShared) + (size_t)9 * m->n_state * cols * sizeof(double);
   if (smem > 227 * 1024)
     return fail(h, CRNN_ERR_UNSUPPORTED, "n_state * np too large for the generic forward-sensitivity kernel's shared memory");
-  auto kern = f2k ? k_gen_sens<true> : k_gen_sens<false>;
+  auto kern = trb ? (f2k ? k_gen_sens<true, 1> : k_gen_sens<false, 1>) : (f2k ? k_gen_sens<true, 0> : k_gen_sens<false, 0>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, cols, smem));
@@ -379,15 +379,18 @@ int loss_grad_generic(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
 
 int gen_prepare(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const double* dW_dp, int np,
                 const double* yscale, int loss_kind, cudaStream_t st, DevBuf* blob_buf, GenLaunch& L) {
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
+  const bool trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && !trb)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23, TRBDF2 and the AutoTsit5 composites");
+  if (trb && m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "sensitivities through TRBDF2 are built for F0 / F1 / F5 (the Cathode scripts); the HyChem flavour uses Rosenbrock23 (crnn_pyrolysis_mass.jl:29)");
   const int n = m->n_state, nr = m->n_reac;
   const bool f2k = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP || m->rhs_kind == CRNN_RHS_F5_TRAMP);
   const bool has_obs = m->w_obs != nullptr;
   int cols = 0; size_t smem = 0; long long max_blocks = 0;
   void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
                unsigned long long*, const long long*, const long long*, const unsigned int*) = nullptr;
-  int rc = gen_launch_cfg(h, m, np, cols, smem, max_blocks, f2k, &kern);
+  int rc = gen_launch_cfg(h, m, np, cols, smem, max_blocks, f2k, trb, &kern);
   if (rc) return rc;
   const int nrow = (has_obs ? 3 : 2) * nr;
   std::vector<R1Desc> desc(cols, R1Desc{});
@@ -408,7 +411,7 @@ int gen_prepare(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const d
   for (int j = 0; j < nr; ++j) extra[(size_t)n + rows.size() + 3 * (size_t)cols + j] = has_obs ? m->w_obs[j] : 0.0;
   GenP& G = L.G;
   const double* extra_dev = nullptr;
-  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2) ? 2 : 5;
   int rcw = build_wide(h, m, o, order, extra, st, G.w, &extra_dev, blob_buf);
   if (rcw) return rcw;
   G.inv_ys = extra_dev; G.seed_rows = extra_dev + n;
@@ -705,16 +708,18 @@ int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opt
   int rc = validate(h, &m0, o, (int64_t)P * E);
   if (rc) return rc;
   if (o->n_obs == 0 || o->n_save == 0) return fail(h, CRNN_ERR_BAD_ARG, "loss needs n_obs > 0 and n_save > 0");
-  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23 and AutoTsit5(Rosenbrock23)");
+  const bool trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);   // src_333/network.jl: AutoTsit5(TRBDF2)
+  if (o->alg != CRNN_ALG_TSIT5 && o->alg != CRNN_ALG_ROSENBROCK23 && o->alg != CRNN_ALG_AUTO_TSIT5_ROS23 && !trb)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "forward sensitivities are implemented for Tsit5, Rosenbrock23, TRBDF2 and the AutoTsit5 composites");
   const bool dens = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
+  if (trb && dens) return fail(h, CRNN_ERR_UNSUPPORTED, "sensitivities through TRBDF2 are built for F0 / F1 / F5");
   const bool f2k = dens || m->rhs_kind == CRNN_RHS_F5_TRAMP;
   if ((tab_T || tab_P) && !f2k) return fail(h, CRNN_ERR_BAD_ARG, "per-experiment tables need rhs_kind F2 or F5");
   CK(cudaSetDevice(h->device));
   int cols = 0; size_t smem = 0; long long max_blocks = 0;
   void (*kern)(GenP, const double*, const int*, long long, const double*, double*, double*, double*, int*, int*, crnn_stats*,
                unsigned long long*, const long long*, const long long*, const unsigned int*) = nullptr;
-  rc = gen_launch_cfg(h, &m0, np, cols, smem, max_blocks, f2k, &kern);
+  rc = gen_launch_cfg(h, &m0, np, cols, smem, max_blocks, f2k, trb, &kern);
   if (rc) return rc;
   cudaStream_t st = h->s_compute;
   // ---- per-particle blocks: weights in the kernel's layout, structured seed rows, descriptors ----
@@ -774,7 +779,7 @@ int crnn_loss_grad_particles(crnn_handle* h, const crnn_model* m, const crnn_opt
     }
   GenP G{};
   const double* extra_dev = nullptr;
-  const int order = (o->alg == CRNN_ALG_ROSENBROCK23) ? 2 : 5;
+  const int order = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2) ? 2 : 5;
   rc = build_wide(h, &m0, o, order, extra, st, G.w, &extra_dev);
   if (rc) return rc;
   if (per_exp) { G.w.tab_T = d_tabs; G.w.tab_P = d_tabs + (size_t)ntab * E; }

@@ -301,7 +301,9 @@ __device__ __forceinline__ double col_obs(const WideP& P, const WideBlock& sb, c
   return dy;
 }
 
-template <bool F2>
+// STIFF: the stiff stepper of this instantiation - 0 Rosenbrock23 (alg ROSENBROCK23 / AUTO_TSIT5_ROS23), 1 TRBDF2 (alg TRBDF2 /
+// AUTO_TSIT5_TRBDF2: the Cathode scripts' training path, Cathode/src/network.jl:102 + src_333/network.jl:232).
+template <bool F2, int STIFF = 0>
 __global__ void __launch_bounds__(256, 1)
 k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const int* __restrict__ n_save_used,
            long long ntraj, const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
@@ -342,7 +344,7 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
   };
   if (G.n_part == 0) load_weights(P.w_inT, P.w_b, P.w_out, G.w_obs);
 
-  const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23);
+  const bool autosw = (P.alg == CRNN_ALG_AUTO_TSIT5_ROS23 || P.alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
   const bool incl = G.incl_sens != 0;
   const double my_at = lane < n ? P.abstol[lane] : 1.0, my_rt = lane < n ? P.reltol[lane] : 0.0;
   const int my_obs = (w0 && lane < n) ? P.row2obs[lane] : -1;
@@ -459,7 +461,8 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
     }
     double t = t0, qold = 1e-4, dt_last = 0.0, eigen_est = 0.0;
     int isave = 0, ret = CRNN_RET_DEFAULT, sw_count = 0;
-    bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23);
+    bool rosen = (P.alg == CRNN_ALG_ROSENBROCK23 || P.alg == CRNN_ALG_TRBDF2);   // "the stiff stepper is active"
+    double eta_old = 1.0;   // TRBDF2: the Newton solver's eta, kept across steps (every thread holds the same value)
     long long iter = 0;
 
     // one save point at time tsv: value column yv (lane-distributed in warp 0), this thread's column value via colval(i)
@@ -593,6 +596,111 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
           __syncthreads();
           eigen_est = S.bcast[1];
         }
+      } else if (STIFF == 1) {
+        // ---- TRBDF2 with dual columns (oracle solve_one, TRBDF2 branch): duals through the SAME simplified-Newton iterations.
+        //      W dz = r(z), W = I - gdt J(u_n); column c:  W dz'_c = dt f'(y)[(y'_c, dW_c)] - z'_c + gdt D^2 f(u_n)[(S_c, dW_c), (dz, 0)];
+        //      the convergence test and the smoothed error estimate use the dual-aware norm.  No Jacobian refresh with columns
+        //      (its dual would need D^2 f at the refresh point): Newton failure => dt/2.
+        //      slots: K0 fsalfirst, K1 z1, K2 z_gamma, K3 z3, K4 tmp (then the error columns), K5 f' / dz (then fsallast), K6 D^2 ----
+        constexpr double s2 = 1.4142135623730951, gam = 2.0 - s2, d = 1.0 - s2 / 2.0, w = s2 / 4.0;
+        constexpr double bt1 = (1.0 - s2) / 3.0, bt2 = 1.0 / 3.0, bt3 = (s2 - 2.0) / 3.0, al1 = -s2 / 2.0, al2 = 1.0 + s2 / 2.0;
+        const double gdt = d * dt;
+        double z1 = 0.0, zg = 0.0, z3 = 0.0, tmpv = 0.0, zs = 0.0;
+        if (w0) {
+          const double eig = wide_build_lu<F2>(P, sb, ww, lane, S.base.r, a0, gdt);
+          if (autosw && lane == 0) S.bcast[1] = eig;
+          z1 = dt * KS(0);
+        }
+        ++n_jac;
+        if (active) for (int i = 0; i < n; ++i) CKS(1)[i * cs] = dt * CKS(0)[i * cs];
+        __syncthreads();
+        if (autosw) eigen_est = S.bcast[1];
+        bool ok = true;
+#pragma unroll 1
+        for (int stg = 0; stg < 2 && ok; ++stg) {
+          double* const ZS = CKS(stg ? 3 : 2);
+          if (w0) {
+            if (stg == 0) { tmpv = fma(d, z1, u); zs = z1; }
+            else { tmpv = fma(w, zg, fma(w, z1, u)); zs = fma(al2, zg, al1 * z1); }
+          }
+          if (active) for (int i = 0; i < n; ++i) {
+            const double uc = slot(SL_U)[i * cs], c1 = CKS(1)[i * cs];
+            if (stg == 0) { CKS(4)[i * cs] = fma(d, c1, uc); ZS[i * cs] = c1; }
+            else { const double cg = CKS(2)[i * cs]; CKS(4)[i * cs] = fma(w, cg, fma(w, c1, uc)); ZS[i * cs] = fma(al2, cg, al1 * c1); }
+          }
+          const double tst = t + (stg ? 1.0 : gam) * dt;
+          bool conv = false;
+          double ndz_prev = 0.0, eta = lean_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
+#pragma unroll 1
+          for (int it = 1; it <= 10; ++it) {
+            double dzv = 0.0, yk = 0.0;
+            if (w0) {
+              yk = fma(d, zs, tmpv);
+              const double fk = gen_rhs<F2>(P, sb, S.cur, lane, my_mw, tst, yk, as, tab_seg, toff);
+              dzv = wide_lusolve(ww, lane, ns, fma(dt, fk, -zs));
+              gen_dir2<F2>(P, sb, S.base, S.d2, lane, dzv, 0.0);                       // second direction (dz, tau = 0)
+            }
+            ++n_rhs;
+            if (active) for (int i = 0; i < n; ++i) slot(SL_Y)[i * cs] = fma(d, ZS[i * cs], CKS(4)[i * cs]);
+            __syncthreads();
+            if (active) {
+              col_apply<F2, false>(P, sb, S.cur, S.d2, srow, cols, tid, ds, slot(SL_Y), CKS(5), nullptr, cs);
+              col_apply<F2, true>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(6), CKS(0), cs);
+              for (int i = 0; i < n; ++i) CKS(5)[i * cs] = fma(gdt, CKS(6)[i * cs], fma(dt, CKS(5)[i * cs], -ZS[i * cs]));
+              col_lusolve(ww, ns, CKS(5), cs);
+            }
+            if (incl) {
+              row_sums(3 * n, [&](int rw) {
+                const int i = rw % n, what = rw / n;
+                const double v = what == 0 ? CKS(5)[i * cs] : (what == 1 ? slot(SL_U)[i * cs] : slot(SL_Y)[i * cs]);
+                return v * v;
+              });
+            } else __syncthreads();
+            if (w0) {
+              double term = 0.0;
+              if (lane < n) {
+                const double e2 = dzv * dzv + (incl ? S.rows[lane] : 0.0);
+                const double a2 = u * u + (incl ? S.rows[n + lane] : 0.0), b2 = yk * yk + (incl ? S.rows[2 * n + lane] : 0.0);
+                const double sc = my_at + fmax(sqrt(a2), sqrt(b2)) * my_rt;
+                term = e2 / (sc * sc);
+              }
+              const double nd = sqrt(wsum(term) / G.norm_cnt);
+              if (lane == 0) S.bcast[2] = nd;
+              zs += dzv;
+            }
+            if (active) for (int i = 0; i < n; ++i) ZS[i * cs] += CKS(5)[i * cs];
+            __syncthreads();
+            const double ndz = S.bcast[2];
+            if (it > 1) {
+              const double theta = ndz / ndz_prev;
+              if (!(theta <= 2.0)) break;
+              eta = theta / (1.0 - theta);
+            }
+            if ((eta >= 0.0 && eta * ndz < 0.01) || ndz == 0.0) { conv = true; eta_old = eta; break; }
+            ndz_prev = ndz;
+          }
+          if (w0) { if (stg == 0) zg = zs; else z3 = zs; }
+          if (!conv) ok = false;
+        }
+        if (!ok) { dt_last = dt; ++n_rej; dt = dt / 2.0; __syncthreads(); continue; }
+        if (w0) {
+          un = fma(d, z3, tmpv);
+          e = wide_lusolve(ww, lane, ns, lane < ns ? fma(bt3, z3, fma(bt2, zg, bt1 * z1)) : 0.0);   // smooth_est
+          gen_dir2<F2>(P, sb, S.base, S.d2, lane, e, 0.0);
+          KS(1) = z1; KS(2) = zg; KS(3) = z3; KS(5) = z3 / dt;                                        // fsallast
+        }
+        if (active) for (int i = 0; i < n; ++i) slot(SL_Y)[i * cs] = fma(d, CKS(3)[i * cs], CKS(4)[i * cs]);   // u_{n+1} of the column
+        __syncthreads();
+        if (active) {
+          col_apply<F2, true>(P, sb, S.base, S.d2, srow, cols, tid, ds, slot(SL_U), CKS(6), CKS(0), cs);
+          for (int i = 0; i < n; ++i) {
+            const double c1 = CKS(1)[i * cs], cg = CKS(2)[i * cs], c3 = CKS(3)[i * cs];
+            CKS(4)[i * cs] = fma(gdt, CKS(6)[i * cs], fma(bt3, c3, fma(bt2, cg, bt1 * c1)));
+            CKS(5)[i * cs] = c3 / dt;
+          }
+          col_lusolve(ww, ns, CKS(4), cs);                                                             // the error columns
+        }
+        __syncthreads();
       } else {
         // ---- Rosenbrock23 = ode23s: K0=f0, K1..K3=k1..k3, K4=f1, K5=f2; caches at u_n in S.base ----
         const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
@@ -668,7 +776,8 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
               double acc = tsc::BT[0] * CKS(0)[i * cs];
               for (int j = 1; j < 7; ++j) acc = fma(tsc::BT[j], CKS(j)[i * cs], acc);
               v = dt * acc;
-            } else v = dt / 6.0 * (CKS(1)[i * cs] - 2.0 * CKS(2)[i * cs] + CKS(3)[i * cs]);
+            } else if (STIFF == 1) v = CKS(4)[i * cs];
+            else v = dt / 6.0 * (CKS(1)[i * cs] - 2.0 * CKS(2)[i * cs] + CKS(3)[i * cs]);
           } else if (what == 1) v = slot(SL_U)[i * cs];
           else v = slot(SL_Y)[i * cs];
           return v * v;
@@ -700,6 +809,11 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
         qold = jmax(EEst, 1e-4);
         const double dtnew = dt / (q >= P.qs_min && q <= P.qs_max ? 1.0 : q), tprev = t;  // steady-state dead-band
         t = snap_t(t + dt, tend);
+        if (STIFF == 1 && rosen) {   // the next attempt's analytic Jacobian needs the by-products at u_{n+1} (fsallast stays z3/dt)
+          if (w0) (void)gen_rhs<F2>(P, sb, S.cur, lane, my_mw, t, un, as, tab_seg, toff);
+          ++n_rhs;
+          __syncthreads();
+        }
         while (isave < nsave) {
           const double tsv = __ldg(P.saveat + isave);
           if (!(tsv <= t)) break;
@@ -724,6 +838,12 @@ k_gen_sens(const __grid_constant__ GenP G, const double* __restrict__ u0, const 
                 for (int s = 1; s < 7; ++s) acc = fma(bs[s], CKS(s)[i * cs], acc);
                 return fma(dt, acc, slot(SL_U)[i * cs]);
               });
+            } else if (STIFF == 1) {   // Hermite on (u_n, fsalfirst) .. (u_{n+1}, fsallast), every column
+              auto herm = [&](double a, double b, double fa, double fb) {
+                return (1.0 - th) * a + th * b + th * (th - 1.0) * ((1.0 - 2.0 * th) * (b - a) + (th - 1.0) * dt * fa + th * dt * fb);
+              };
+              const double yv = w0 ? herm(u, un, KS(0), KS(5)) : 0.0;
+              emit_save(tsv, yv, [&](int i) { return herm(slot(SL_U)[i * cs], slot(SL_Y)[i * cs], CKS(0)[i * cs], CKS(5)[i * cs]); });
             } else {
               const double d = 1.0 / (2.0 + 1.4142135623730951);
               const double c1 = th * (1.0 - th) / (1.0 - 2.0 * d), c2 = th * (th - 2.0 * d) / (1.0 - 2.0 * d);

@@ -87,10 +87,10 @@ enum crnn_alg {
                                    OrdinaryDiffEq's AutoSwitch stiffness detection (maxstiffstep 10, maxnonstiffstep 3,
                                    tolerances 9/10, dtfac 2) switching to Rosenbrock23 (analytic J) and back;
                                    crnn_stats.n_jac counts the Rosenbrock23 step attempts */
-  CRNN_ALG_TRBDF2 = 4,          /* TRBDF2 as an ESDIRK with simplified Newton (predict path; the stiff half of the next one) */
+  CRNN_ALG_TRBDF2 = 4,          /* TRBDF2 as an ESDIRK with simplified Newton (the stiff half of the next one) */
   CRNN_ALG_AUTO_TSIT5_TRBDF2 = 5 /* AutoTsit5(TRBDF2()): Cathode/src/network.jl:102, Cathode_NCM333_UQ/src_333/network.jl,
                                    yeast-glycolysis/yeast_glycolysis.jl:33 — the same AutoSwitch, TRBDF2 as the stiff stepper
-                                   (predict path; gradients through the composite use CRNN_ALG_AUTO_TSIT5_ROS23);
+                                   (predict, and forward sensitivities for F0 / F1 / F5: duals through the Newton iterations);
                                    crnn_stats.n_jac counts the Jacobian factorisations */
 };
 

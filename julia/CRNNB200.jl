@@ -79,7 +79,7 @@ Base.@kwdef struct Setup
     rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state),
                                    # 2: F2 (HyChem/crnn_pyrolysis_mass.jl: mass fractions, tabulated T(t), P(t)),
                                    # 3: F5 (Cathode/src/network.jl:68-80: temperature programme T(t), no density map)
-    alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23, 2 KenCarp4, 3 AutoTsit5(Rosenbrock23()), 4 TRBDF2, 5 AutoTsit5(TRBDF2()) (predict)
+    alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23, 2 KenCarp4, 3 AutoTsit5(Rosenbrock23()), 4 TRBDF2, 5 AutoTsit5(TRBDF2())
     sens_mode::Int32 = 1           # 1 forward (ForwardDiff semantics), 2 interpolating adjoint, 3 discrete adjoint
     gas_R::Float64 = 1.98720425864083e-3
     mw::Vector{Float64} = Float64[]        # F2: l_MW

@@ -683,7 +683,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
   const crnn_opts* o = c->o;
   const int n = c->n, ncol = c->ncol, tot = n * ncol;
   const int autosw = (o->alg == CRNN_ALG_AUTO_TSIT5_ROS23 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2);
-  const int trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2); /* the stiff stepper is TRBDF2 (value path only) */
+  const int trb = (o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2); /* the stiff stepper is TRBDF2 */
   int rosen = (o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2);          /* "the stiff stepper is active" */
   double eta_old = 1.0;                                                                 /* TRBDF2: nlsolver.ηold, kept across steps */
   double* buf = (double*)calloc((size_t)tot * 14 + (size_t)n * n * 2 + 9 * n, sizeof(double));
@@ -776,7 +776,17 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       const double s2 = sqrt(2.0), gam = 2.0 - s2, d = 1.0 - s2 / 2.0, w = s2 / 4.0;
       const double bt1 = (1.0 - s2) / 3.0, bt2 = 1.0 / 3.0, bt3 = (s2 - 2.0) / 3.0, al1 = -s2 / 2.0, al2 = 1.0 + s2 / 2.0;
       const double gdt = d * dt;
-      double* Z1 = K[1]; double* ZG = K[2]; double* Z3 = K[3]; double* Yk = W2; double* DZ = W2 + n;
+      /* Forward sensitivities = duals through the SAME iterations (ForwardDiff through the solver, Cathode/src/network.jl:102 +
+       * Cathode_NCM333_UQ/src_333/network.jl:232): every quantity below carries ncol columns.  A Newton update solves
+       * W dz = r(z) with W = I - gdt J(u_J); its dual is  W dz' = r' - W' dz = r' + gdt D^2 f(u_J)[(S_c, dW_c), (dz, 0)],
+       * r'_c = dt (J(y) y'_c + f_p,c(y)) - z'_c  (eval_cols), the second-derivative term as in the Rosenbrock23 branch; the
+       * convergence test and the error estimate use the dual-aware norm (internalnorm over Dual arrays). */
+      double* Z1 = K[1]; double* ZG = K[2]; double* Z3 = K[3]; double* Yk = W2; double* DZ = W2 + tot;
+      const rhs_cache* kcJ = &kc0; const double* UJ = U;   /* where W's Jacobian was taken: u_n */
+      /* linear algebra: the ESDIRK form of this file (kc_*: LU, or the explicit inverse under its named switch) on the value path,
+       * plain LU + substitution when dual columns ride along (what the block-per-trajectory sensitivity kernel does) */
+      void (*tr_factor)(double*, int*, int) = ncol > 1 ? lu_factor : kc_factor;
+      void (*tr_solve)(const double*, const int*, int, double*) = ncol > 1 ? lu_solve : kc_solve;
       jac_value(c, &kc0, Jm); res->st.n_jac++;
       if (autosw) {
         double best = 0.0;
@@ -785,26 +795,31 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
       }
       for (int i = 0; i < n; ++i)
         for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - gdt * Jm[i * n + l];
-      kc_factor(LU, piv, n);
-      for (int i = 0; i < n; ++i) Z1[i] = dt * K[0][i];
+      tr_factor(LU, piv, n);
+      for (int q = 0; q < tot; ++q) Z1[q] = dt * K[0][q];
       int newton_ok = 1, refreshed = 0;
       for (int stg = 0; stg < 2 && newton_ok; ++stg) {
         double* Zs = stg ? Z3 : ZG;
         const double cs = stg ? 1.0 : gam;
-        for (int i = 0; i < n; ++i) {
-          if (!stg) { TMP[i] = U[i] + d * Z1[i]; Zs[i] = Z1[i]; }
-          else { TMP[i] = U[i] + w * Z1[i] + w * ZG[i]; Zs[i] = al1 * Z1[i] + al2 * ZG[i]; }
+        for (int q = 0; q < tot; ++q) {
+          if (!stg) { TMP[q] = U[q] + d * Z1[q]; Zs[q] = Z1[q]; }
+          else { TMP[q] = U[q] + w * Z1[q] + w * ZG[q]; Zs[q] = al1 * Z1[q] + al2 * ZG[q]; }
         }
         int conv = 0;
         for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
           double ndz_prev = 0.0, eta = m_pow(fmax(eta_old, 2.220446049250313e-16), 0.8);
           for (int it = 1; it <= 10; ++it) {
-            for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + d * Zs[i];
-            rhs_value(c, t + cs * dt, Yk, DZ, &kc); res->st.n_rhs++;
-            for (int i = 0; i < n; ++i) DZ[i] = dt * DZ[i] - Zs[i];
-            kc_solve(LU, piv, n, DZ);
-            double ndz = wrms(c, DZ, U, Yk);
-            for (int i = 0; i < n; ++i) Zs[i] += DZ[i];
+            for (int q = 0; q < tot; ++q) Yk[q] = TMP[q] + d * Zs[q];
+            eval_cols(c, t + cs * dt, Yk, DZ, &kc); res->st.n_rhs++;
+            for (int q = 0; q < tot; ++q) DZ[q] = dt * DZ[q] - Zs[q];
+            tr_solve(LU, piv, n, DZ);                       /* value update dz */
+            for (int col = 1; col < ncol; ++col) {
+              djac_vec(c, kcJ, UJ + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, DZ, 0.0, vtmp);
+              for (int i = 0; i < n; ++i) DZ[col * n + i] += gdt * vtmp[i];
+              tr_solve(LU, piv, n, DZ + col * n);
+            }
+            double ndz = (ncol > 1) ? err_norm(c, DZ, U, Yk) : wrms(c, DZ, U, Yk);
+            for (int q = 0; q < tot; ++q) Zs[q] += DZ[q];
             if (it > 1) {
               double theta = ndz / ndz_prev;
               if (!(theta <= 2.0)) break;
@@ -814,25 +829,31 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
             ndz_prev = ndz;
           }
           if (!conv) {
-            if (refreshed || has_nan(Zs, n)) break;
+            /* with dual columns the refresh is not taken (its dual needs D^2 f at the refresh point): failure => dt/2 */
+            if (refreshed || ncol > 1 || has_nan(Zs, tot)) break;
             refreshed = 1;
-            for (int i = 0; i < n; ++i) Yk[i] = TMP[i] + d * Zs[i];
+            for (int q = 0; q < tot; ++q) Yk[q] = TMP[q] + d * Zs[q];
             rhs_value(c, t + cs * dt, Yk, DZ, &kc); res->st.n_rhs++;
             jac_value(c, &kc, Jm); res->st.n_jac++;
             for (int i = 0; i < n; ++i)
               for (int l = 0; l < n; ++l) LU[i * n + l] = (i == l ? 1.0 : 0.0) - gdt * Jm[i * n + l];
-            kc_factor(LU, piv, n);
+            tr_factor(LU, piv, n);
           }
         }
         if (!conv) newton_ok = 0;
       }
       if (!newton_ok) { res->st.dt_last = dt; res->st.n_reject++; dt = dt / 2.0; continue; }
-      for (int i = 0; i < n; ++i) {
-        Un[i] = TMP[i] + d * Z3[i];
-        E[i] = bt1 * Z1[i] + bt2 * ZG[i] + bt3 * Z3[i];
-        K[5][i] = Z3[i] / dt;
+      for (int q = 0; q < tot; ++q) {
+        Un[q] = TMP[q] + d * Z3[q];
+        E[q] = bt1 * Z1[q] + bt2 * ZG[q] + bt3 * Z3[q];
+        K[5][q] = Z3[q] / dt;
       }
-      kc_solve(LU, piv, n, E);
+      tr_solve(LU, piv, n, E);                              /* smooth_est: W \ tmp, and its dual */
+      for (int col = 1; col < ncol; ++col) {
+        djac_vec(c, kcJ, UJ + col * n, c->seed ? c->seed + (size_t)(col - 1) * c->nw : NULL, E, 0.0, vtmp);
+        for (int i = 0; i < n; ++i) E[col * n + i] += gdt * vtmp[i];
+        tr_solve(LU, piv, n, E + col * n);
+      }
     } else {
       /* Rosenbrock23 = Shampine-Reichelt ode23s.  K[0]=f0
        * (FSAL), K[1]=k1, K[2]=k2, K[3]=k3, K[4]=f1, K[5]=f2. */
@@ -928,7 +949,7 @@ static void solve_one(const ctx_t* c, const double* u0, int n_save_use, save_sin
               TMP[qq] = U[qq] + dt * acc;
             }
           } else if (trb) { /* Hermite on (u_n, fsalfirst) .. (u_{n+1}, fsallast = z3/dt) */
-            for (int i = 0; i < n; ++i)
+            for (int i = 0; i < tot; ++i)
               TMP[i] = (1.0 - th) * U[i] + th * Un[i] +
                        th * (th - 1.0) * ((1.0 - 2.0 * th) * (Un[i] - U[i]) + (th - 1.0) * dt * K[0][i] + th * dt * K[5][i]);
           } else {
@@ -1468,7 +1489,7 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
                                 int n_threads) {
   int rc = check_dims(m, o);
   if (rc) return rc;
-  if (o->alg == CRNN_ALG_KENCARP4 || o->alg == CRNN_ALG_TRBDF2 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) return CRNN_ERR_UNSUPPORTED; /* value path only */
+  if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
   if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;

@@ -152,3 +152,72 @@ def test_autotsit5_fast_path_mixed_batch(engine, golden):
     ref = oracle.loss_grad_batch(*args, n_save_used=nsu, want_pred=True, n_threads=8)
     _compare(got, ref, rtol_state=1e-7, rtol_loss=1e-7, rtol_grad=1e-6)
     assert np.array_equal(got["n_saved"], nsu)
+
+
+@pytest.mark.parametrize("alg", [_abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2])
+def test_gradients_through_trbdf2_and_its_composite(engine, golden, alg):
+    """ForwardDiff through AutoTsit5(TRBDF2) (the Cathode scripts' training path, Cathode/src/network.jl:102 +
+    Cathode_NCM333_UQ/src_333/network.jl:232): dual columns through the simplified-Newton iterations, against the oracle"""
+    for name, N in (("robertson", 64), ("case2", 48)):
+        pb = make_problem(name, golden, N)
+        c = pb["case"]
+        o = c.opts(obs_idx=np.arange(c.ns), alg=alg)
+        args = (pb["model"], o, pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+        got = engine.loss_grad_batch(*args, want_pred=True)
+        ref = oracle.loss_grad_batch(*args, want_pred=True, n_threads=8)
+        assert (got["retcode"] == _abi.RET_SUCCESS).all()
+        if name == "case2" and alg == _abi.ALG_AUTO_TSIT5_TRBDF2:
+            _compare(got, ref)                                    # never stiff: Tsit5, exact counts
+            assert (got["stats"]["n_jac"] == 0).all()
+            continue
+        # Newton iteration counts can flip on summation order for a few trajectories; the rest agree to rounding
+        same = np.ones(N, dtype=bool)
+        for k in ("n_accept", "n_reject", "n_rhs", "n_jac"):
+            same &= got["stats"][k] == ref["stats"][k]
+        assert same.mean() >= 0.9, f"{(~same).sum()} of {N} trajectories differ in counts"
+        np.testing.assert_allclose(got["loss"][same], ref["loss"][same], rtol=1e-6)
+        scale = np.abs(ref["pred"]).max(axis=(0, 1))
+        assert (np.abs(got["pred"] - ref["pred"])[same] / scale).max() < 1e-6
+        assert np.linalg.norm(got["grad_sum"] - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]) < (1e-6 if same.all() else 2e-3)
+        if alg == _abi.ALG_AUTO_TSIT5_TRBDF2 and name == "robertson":
+            assert (got["stats"]["n_jac"] > 0).any()
+    # and against Rosenbrock23's gradient at tight tolerances (two different discretisations of the same sensitivities)
+    pb = make_problem("robertson", golden, 8)
+    c = pb["case"]
+    tight = dict(abstol=np.array([1e-11, 1e-13, 1e-11]), reltol=np.full(3, 1e-8), maxiters=10 ** 7)
+    args = (pb["seed"], pb["u0"], pb["data"], pb["yscale"], pb["loss_kind"])
+    g_t = engine.loss_grad_batch(pb["model"], c.opts(alg=alg, **tight), *args)
+    g_r = engine.loss_grad_batch(pb["model"], c.opts(alg=_abi.ALG_ROSENBROCK23, **tight), *args)
+    assert np.linalg.norm(g_t["grad_sum"] - g_r["grad_sum"]) / np.linalg.norm(g_r["grad_sum"]) < 1e-5
+
+
+def test_cathode_training_path_as_written_trbdf2_gradients(engine):
+    """loss + gradient of the heat-release MSE through AutoTsit5(TRBDF2) on the F5 model, batched and particle-batched
+    (src_333/network.jl:222-260 with the script's own algorithm)"""
+    import cathode_problem as cp
+    pb = cp.make(4, seed=1, alg=_abi.ALG_AUTO_TSIT5_TRBDF2)
+    assert pb["opts"].alg == _abi.ALG_AUTO_TSIT5_TRBDF2
+    for alg in (_abi.ALG_TRBDF2, _abi.ALG_AUTO_TSIT5_TRBDF2):
+        o = cases.cathode_opts(pb["opts"].saveat, alg=alg, pred_clamp=(-np.inf, np.inf))
+        e = 1                                         # 5 K/min: TRBDF2 alone equals the oracle count for count
+        m, sd = cp.model_for(pb["particles"][0], cp.BETAS[e], pb["t_hi"])
+        u0 = np.tile(pb["u0"][e], (8, 1)) * (1.0 - 0.01 * np.arange(8))[:, None]
+        data = np.tile(pb["data"][e], (8, 1, 1))
+        got = engine.loss_grad_batch(m, o, sd, u0, data, pb["yscale"], _abi.LOSS_MSE, want_pred=True)
+        ref = oracle.loss_grad_batch(m, o, sd, u0, data, pb["yscale"], _abi.LOSS_MSE, want_pred=True, n_threads=8)
+        assert (got["retcode"] == _abi.RET_SUCCESS).all()
+        np.testing.assert_allclose(got["pred"], ref["pred"], rtol=2e-2, atol=1e-3 * np.abs(ref["pred"]).max())
+        assert np.linalg.norm(got["grad_sum"] - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]) < 2e-2
+        if alg == _abi.ALG_TRBDF2:
+            same = (got["stats"]["n_rhs"] == ref["stats"]["n_rhs"]) & (got["stats"]["n_accept"] == ref["stats"]["n_accept"])
+            assert same.mean() >= 0.75
+            np.testing.assert_allclose(got["loss"][same], ref["loss"][same], rtol=1e-5)
+    # the SVGD form with the script's algorithm: one launch of particles x experiments
+    o5 = cases.cathode_opts(pb["opts"].saveat, alg=_abi.ALG_TRBDF2, pred_clamp=(-np.inf, np.inf))
+    got = engine.loss_grad_particles(pb["model"], o5, pb["weights"], pb["seeds"], pb["u0"], pb["data"], pb["yscale"],
+                                     _abi.LOSS_MSE, tab_T=pb["tab_T"], want_stats=True)
+    pb5 = dict(pb, opts=o5)
+    loss, grad, nacc = cp.oracle_particles(pb5, _abi.LOSS_MSE)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    np.testing.assert_allclose(got["loss"], loss, rtol=2e-2)
+    assert np.abs(got["grad"] - grad).max() < 2e-2 * np.abs(grad).max()

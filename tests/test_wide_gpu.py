@@ -255,10 +255,11 @@ def test_trbdf2_and_its_composite_match_the_oracle(engine, golden, alg):
     b = oracle.solve_batch(p2["model"], p2["case"].opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2), p2["u0"], n_threads=8)
     _counts_equal(a, b)
     assert (a["stats"]["n_jac"] == 0).all() and _rel_err(a["pred"], b["pred"]) < 1e-9
-    # value path only: a gradient through TRBDF2 is refused loudly
+    # (gradients through TRBDF2: tests/test_gen_sens_gpu.py; the HyChem flavour keeps Rosenbrock23 and is refused loudly)
     from crnn_b200.engine import EngineError
+    _, sh = cases.hychem_model(cases.hychem_p(0), YS_HYCHEM)
     with pytest.raises(EngineError):
-        engine.loss_grad_batch(pb["model"], c.opts(alg=alg), pb["seed"], pb["u0"], pb["data"], pb["yscale"])
+        engine.loss_grad_batch(m, oh, sh, u0[:4], ref["pred"][:4], YS_HYCHEM)
 
 
 def test_cathode_predict_as_written_autotsit5_trbdf2_with_heat_release(engine):
