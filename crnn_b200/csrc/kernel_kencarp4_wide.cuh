@@ -175,9 +175,10 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
       dt_last = dt;
       if (!ok) { ++n_rej; dt = dt / 2.0; continue; }
       const double un = fma(kc::g, z[5], tmp);
-      double e = (kc::g - kc::BHAT[5]) * z[5];
+      double e = (kc::A[5][0] - kc::BHAT[0]) * z[0];   // the oracle's order: stages 1..5 ascending, the diagonal term last
 #pragma unroll
-      for (int j = 4; j >= 0; --j) e = fma(kc::A[5][j] - kc::BHAT[j], z[j], e);
+      for (int j = 1; j < 5; ++j) e = fma(kc::A[5][j] - kc::BHAT[j], z[j], e);
+      e = fma(kc::g - kc::BHAT[5], z[5], e);
       e = lusolve(isp ? e : 0.0);
       const double EEst = wrms(e, u, un);
       double q11, q;
