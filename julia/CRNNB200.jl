@@ -76,7 +76,7 @@ check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:crnn_last_error, L
 
 "Problem constants a script defines once (tsteps, tolerances, lb/ub, i_obs, dydt_scale ...)."
 Base.@kwdef struct Setup
-    rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state),
+    rhs_kind::Int32 = 0            # 0: F0 (case1/3/robertson), 1: F1 (case2: Arrhenius row, T as last state), 4: F4 (MLP-augmented inputs, predict),
                                    # 2: F2 (HyChem/crnn_pyrolysis_mass.jl: mass fractions, tabulated T(t), P(t)),
                                    # 3: F5 (Cathode/src/network.jl:68-80: temperature programme T(t), no density map)
     alg::Int32 = 0                 # 0 Tsit5, 1 Rosenbrock23, 2 KenCarp4, 3 AutoTsit5(Rosenbrock23()), 4 TRBDF2, 5 AutoTsit5(TRBDF2())
@@ -87,6 +87,13 @@ Base.@kwdef struct Setup
     tab_T::Vector{Float64} = Float64[]
     tab_P::Vector{Float64} = Float64[]
     w_obs::Vector{Float64} = Float64[]     # heat-release weights w_delH (Cathode/src/network.jl:121); empty: observe rows of u
+    # F4 (rhs_kind = 4; yeast_glycolysis.jl:128-142, rober_crnn_qssa.jl:111-126): the Flux chain that supplies the hidden input rows
+    mlp_dims::Vector{Int32} = Int32[]      # layer widths, e.g. [7, 5, 5, 5, 5]
+    mlp_params::Vector{Float64} = Float64[]   # Float64.(Flux.destructure(dudt2)[1])
+    mlp_in_idx::Vector{Int32} = Int32[]    # 0-based state rows fed to the MLP
+    mlp_act_out::Int32 = 0                 # 0 softplus, 1 exp
+    aug_src::Vector{Int32} = Int32[]       # per input row of the CRNN: >= 0 state row, < 0: MLP output -1 - value
+    w_J::Vector{Float64} = Float64[]       # additive source term (yeast)
     lb::Float64; ub::Float64
     abstol::Vector{Float64} = [1e-6]; reltol::Vector{Float64} = [1e-3]
     tspan::Tuple{Float64,Float64}; saveat::Vector{Float64}
@@ -104,12 +111,14 @@ function with_structs(f, s::Setup, w_in, w_b, w_out)
     ns, nr = size(w_out); n_in = size(w_in, 1)
     osc = s.out_scale === nothing ? Float64[] : s.out_scale
     GC.@preserve w_in w_b w_out osc s begin
-        n_state = s.rhs_kind >= 2 ? ns : n_in      # F0/F1: n_in == n_state; F2/F5: n_in = n_species + 2
+        n_state = s.rhs_kind >= 2 ? ns : n_in      # F0/F1: n_in == n_state; F2/F5: n_in = n_species + 2; F4: n_state = n_species
+        i2p(v) = isempty(v) ? Ptr{Int32}(C_NULL) : pointer(v)
         f2p(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
         m = CModel(n_state, ns, n_in, nr, s.rhs_kind, length(s.tab_t), s.lb, s.ub, s.gas_R,
                    isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out),
                    f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P), f2p(s.w_obs),
-                   0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
+                   max(length(s.mlp_dims) - 1, 0), s.mlp_act_out, i2p(s.mlp_dims), i2p(s.mlp_in_idx), f2p(s.mlp_params),
+                   i2p(s.aug_src), f2p(s.w_J))
         o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
