@@ -684,15 +684,17 @@ template <class C>
 int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const crnn_train_opts* t, const crnn_dataset* ds,
                const int64_t* order, int64_t n_steps, const double* yscale, int32_t loss_kind, double* p, double* opt_state,
                double* step_loss, double* step_gnorm) {
-  if constexpr (!(C::NS == 6 && C::NR == 3 && C::KIND == 1)) {
-    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has a device p2vec for case2 (6 species, 3 reactions, F1) only");
+  // device p2vec kernels: 2 = case2/case2.jl:91-99 (6 species, 3 reactions, F1), 1 = case1/case1.jl:70-78 (5 species, 4 reactions, F0)
+  constexpr int PK = (C::NS == 6 && C::NR == 3 && C::KIND == 1) ? 2 : ((C::NS == 5 && C::NR == 4 && C::KIND == 0) ? 1 : 0);
+  if constexpr (PK == 0) {
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has device p2vec kernels for case1 (5 x 4, F0) and case2 (6 x 3, F1)");
   } else {
-    constexpr int NP = C::NR * (C::NS + 2) + 1;   // 25
-    if (t->p2vec_kind != 2) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind: 2 (case2/case2.jl:91-99) is the one built");
+    constexpr int NP = PK == 2 ? C::NR * (C::NS + 2) + 1 : C::NR * (C::NS + 1);   // 25 / 24
+    if (t->p2vec_kind != PK) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind does not match the model: 1 = case1.jl:70-78, 2 = case2.jl:91-99");
     if (o->alg != CRNN_ALG_TSIT5 || o->sens_mode != CRNN_SENS_FORWARD)
       return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop runs Tsit5 with forward sensitivities");
     if (t->batch < 1 || n_steps < 0) return fail(h, CRNN_ERR_BAD_ARG, "bad batch / n_steps");
-    if (m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case2 has no out_scale");
+    if (m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case1 / case2 have no out_scale");
     const int batch = t->batch;
     for (int64_t q = 0; q < n_steps * batch; ++q)
       if (order[q] < 0 || order[q] >= ds->N) return fail(h, CRNN_ERR_BAD_ARG, "order: dataset row index out of range");
@@ -741,7 +743,8 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     const int nb_red = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (batch + 63) / 64));
     CK(h->partial.reserve((size_t)nb_red * NP * sizeof(double)));
     for (int64_t s = 0; s < n_steps; ++s) {
-      k_p2vec_case2<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->gas_R, d_mp, d_rows, d_desc);
+      if constexpr (PK == 2) k_p2vec_case2<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->gas_R, d_mp, d_rows, d_desc);
+      else k_p2vec_case1<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, t->p2vec_b0, d_mp, d_rows, d_desc);
       CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
       kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nullptr, batch,
                                           ds->data[0].as<double>(), h->d_loss.as<double>(), h->d_grad_each.as<double>(), nullptr,

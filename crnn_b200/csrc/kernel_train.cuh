@@ -66,6 +66,34 @@ __global__ void k_p2vec_case2(const double* __restrict__ p, double lb, double ub
   }
 }
 
+// p2vec of case1/case1.jl:70-78: w_b = p[1:nr] .+ b0 (b0 = -10, :70), w_out = reshape(p[nr+1:end], ns, nr), w_in = clamp(-w_out, 0, 2.5)
+template <class C>
+__global__ void k_p2vec_case1(const double* __restrict__ p, double lb, double ub, double b0, ModelP<C>* __restrict__ mp,
+                              double* __restrict__ rows /* [2*NR][32] */, R1Desc* __restrict__ desc /* [32] */) {
+  constexpr int NS = C::NS, NR = C::NR, NIN = C::NIN;
+  static_assert(C::KIND == 0 && NIN == NS, "an F0 model");
+  const int t = threadIdx.x;
+  for (int q = t; q < 2 * NR * 32; q += blockDim.x) rows[q] = 0.0;
+  if (t < 32) { R1Desc d{}; d.o = 0.0; d.i_in = 0; d.i_out = 0; d.j_out = 0; d.pad = 0; desc[t] = d; }
+  __syncthreads();
+  if (t == 0) { mp->lb = lb; mp->ub = ub; mp->gas_R = 0.0; }
+  if (t < NR) {
+    mp->w_b[t] = p[t] + b0;
+    rows[(NR + t) * 32 + (1 + t)] = 1.0;
+  }
+  if (t < NS * NR) {
+    const int i = t % NS, j = t / NS;
+    const double wo = p[NR + i + NS * j];
+    mp->w_out[i + NS * j] = wo;
+    const double wi = -wo;
+    mp->w_in[i + NIN * j] = wi > 2.5 ? 2.5 : (wi < 0.0 ? 0.0 : wi);
+    const int c = 1 + NR + i + NS * j;
+    R1Desc d{}; d.o = 1.0; d.i_in = i; d.i_out = i; d.j_out = j; d.pad = 0;
+    desc[c] = d;
+    rows[j * 32 + c] = (wi >= 0.0 && wi <= 2.5) ? -1.0 : 0.0;
+  }
+}
+
 // [sum of the finite losses, number of them] of one step's experiments (fixed order: deterministic)
 static __global__ void __launch_bounds__(256) k_train_loss_sum(const double* __restrict__ loss, int n, double* __restrict__ out) {
   __shared__ double s_sum[256], s_cnt[256];

@@ -301,7 +301,7 @@ Engine.loss_grad_particles = _particles
 
 def _train_steps(self, model: CRNNModel, opts: SolveOpts, ds: Dataset, order, yscale, p, opt_state=None,
                  loss_kind=_abi.LOSS_MAE_SCALED, p2vec_kind=2, optimiser="adam", batch=1, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, expdecay=None, grad_max=None):
+                 weight_decay=0.0, expdecay=None, grad_max=None, p2vec_b0=-10.0):
     """`crnn_train_steps`: the scripts' epoch loop (case2/case2.jl:192-198) entirely on the device - p2vec, solve +
     forward sensitivities, gradient reduction and the Flux optimiser chain enqueued back to back, nothing returning to the
     host between optimiser steps.  `order` [n_steps * batch] dataset rows (the host's randperm), `expdecay` =
@@ -322,7 +322,7 @@ def _train_steps(self, model: CRNNModel, opts: SolveOpts, ds: Dataset, order, ys
     if opt_state.size != 2 * n_p + 4:
         raise ValueError("opt_state must be [2*np + 4]")
     t = _abi.CTrainOpts(int(p2vec_kind), {"adam": 0, "nadam": 1}[optimiser], int(batch), 0, eta, beta[0], beta[1], eps, weight_decay,
-                        ed[0], ed[1], ed[3], int(ed[2]), 0.0 if grad_max is None else float(grad_max))
+                        ed[0], ed[1], ed[3], int(ed[2]), 0.0 if grad_max is None else float(grad_max), float(p2vec_b0))
     ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (opts.n_obs(model.n_state),), "yscale")
     sl, sg = np.empty(n_steps), np.empty(n_steps)
     hp = lambda a: a.ctypes.data_as(C.c_void_p)

@@ -290,7 +290,7 @@ int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts*
  * (rober_crnn.jl:220-223) are enqueued back to back.  The host supplies the visiting order (its own randperm).
  * --------------------------------------------------------------------------------------------- */
 typedef struct crnn_train_opts {
-  int32_t p2vec_kind;   /* which script's p2vec runs on the device: 2 = case2/case2.jl:91-99 (the one built) */
+  int32_t p2vec_kind;   /* which script's p2vec runs on the device: 1 = case1/case1.jl:70-78, 2 = case2/case2.jl:91-99 */
   int32_t optimiser;    /* 0 ADAM (+ weight_decay = ADAMW), 1 NADAM */
   int32_t batch;        /* experiments per optimiser step (the scripts: 1) */
   int32_t reserved;
@@ -299,6 +299,7 @@ typedef struct crnn_train_opts {
   double expdecay_decay, expdecay_clip;
   int64_t expdecay_step;
   double grad_max;      /* > 0: clip the gradient's 2-norm (rober_crnn.jl:29,221) */
+  double p2vec_b0;      /* p2vec_kind 1: the bias offset b0 of case1/case1.jl:70 (-10) */
 } crnn_train_opts;
 
 /* n_steps optimiser steps; step s uses dataset rows order[s*batch .. (s+1)*batch).  Single-device handle, Tsit5 +

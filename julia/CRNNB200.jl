@@ -42,6 +42,7 @@ struct CTrainOpts
     expdecay_eta::Float64; expdecay_decay::Float64; expdecay_clip::Float64
     expdecay_step::Int64
     grad_max::Float64
+    p2vec_b0::Float64
 end
 
 mutable struct Engine
@@ -227,15 +228,15 @@ end
 The epoch loop `for i_exp in randperm(n_exp_train); grad = ForwardDiff.gradient(...); update!(opt, p, grad); end`
 (case2/case2.jl:192-198) with every optimiser step ON the device: `order` is the 1-based visiting order (the script's own
 `randperm`), `p` and `opt_state` (2np + 4: ADAM m, v, beta powers, ExpDecay eta and count) are updated in place.  The
-device runs case2's p2vec itself (`p2vec_kind = 2`), so no weights are passed.
+device runs the script's p2vec itself (`p2vec_kind` 2: case2.jl:91-99, 1: case1.jl:70-78), so no weights are passed.
 """
 function train_steps!(e::Engine, s::Setup, ds::Dataset, order, p::Vector{Float64}, opt_state::Vector{Float64};
                       ns::Integer, nr::Integer, batch::Integer=1, optimiser::Integer=0, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,
-                      weight_decay=0.0, expdecay=(0.0, 1.0, 0, 0.0), grad_max=0.0)
+                      weight_decay=0.0, expdecay=(0.0, 1.0, 0, 0.0), grad_max=0.0, p2vec_kind::Integer=2, p2vec_b0=-10.0)
     ord = Vector{Int64}(order .- 1); n_steps = div(length(ord), batch)
     step_loss = zeros(n_steps); step_gnorm = zeros(n_steps)
-    t = CTrainOpts(2, optimiser, batch, 0, eta, beta[1], beta[2], eps, weight_decay, expdecay[1], expdecay[2], expdecay[4],
-                   expdecay[3], grad_max)
+    t = CTrainOpts(p2vec_kind, optimiser, batch, 0, eta, beta[1], beta[2], eps, weight_decay, expdecay[1], expdecay[2], expdecay[4],
+                   expdecay[3], grad_max, p2vec_b0)
     n_in = s.rhs_kind == 1 ? ns + 1 : ns
     with_structs(s, zeros(n_in, nr), zeros(nr), zeros(ns, nr)) do m, o
         check(e, ccall((:crnn_train_steps, LIB), Cint,

@@ -115,6 +115,41 @@ def test_on_device_training_loop_equals_the_host_loop(engine, variant):
     assert np.array_equal(np.concatenate([r1["step_loss"], r2["step_loss"]]), r_all["step_loss"])
 
 
+def test_on_device_loop_case1_p2vec(engine, golden):
+    """p2vec_kind = 1: case1/case1.jl:70-78 on the device (w_b = p + b0, w_in = clamp(-w_out, 0, 2.5)); every step against the host
+    mirror from the same (p, state), ADAMW(0.001, (0.9, 0.999), 1e-8) as in case1.jl:18"""
+    from problems import make_problem
+    pb = make_problem("case1", golden, 12)
+    prob = CRNNProblem("case1", pb["u0"], pb["data"], pb["yscale"], engine=engine)
+    g = np.random.default_rng(3)
+    p = 0.1 * g.standard_normal(24)                                        # case1.jl:86
+    opt = optim.ADAMW(0.001, (0.9, 0.999), 1e-8)
+    kw = dict(p2vec_kind=1, optimiser="adam", eta=0.001, beta=(0.9, 0.999), weight_decay=1e-8)
+    model, _ = prob.case.model(p)
+    st = None
+    order = np.concatenate([g.permutation(12) for _ in range(3)])
+    for s in range(30):
+        idx = order[s:s + 1]
+        loss, grad = prob.loss_grad(p, idx)
+        p_host = p.copy(); opt.update(p_host, grad)
+        r = engine.train_steps(model, prob.opts, prob.dataset, idx, prob.yscale, p, st, prob.case.loss_kind, **kw)
+        np.testing.assert_allclose(r["step_loss"][0], loss, rtol=1e-13)
+        np.testing.assert_allclose(r["p"], p_host, rtol=1e-12, atol=1e-15, err_msg=f"step {s}")
+        p, st = r["p"], r["opt_state"]
+        adam = opt.chain[0]
+        adam.m, adam.v = st[:24].copy(), st[24:48].copy()
+    # a model the device has no p2vec for is refused, as is a mismatching kind
+    from crnn_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        engine.train_steps(model, prob.opts, prob.dataset, order[:2], prob.yscale, p, None, prob.case.loss_kind, p2vec_kind=2)
+    pb3 = make_problem("case3", golden, 4)
+    prob3 = CRNNProblem("case3", pb3["u0"], np.abs(pb3["data"]) + 1e-6, pb3["yscale"], engine=engine)
+    with pytest.raises(EngineError):
+        engine.train_steps(pb3["model"], prob3.opts, prob3.dataset, np.arange(2), prob3.yscale, np.zeros(153), None, prob3.case.loss_kind)
+    with pytest.raises(EngineError):                                           # dataset row out of range
+        engine.train_steps(model, prob.opts, prob.dataset, np.array([99]), prob.yscale, p, None, prob.case.loss_kind, **kw)
+
+
 def test_on_device_epochs_descend(engine):
     prob, p0, g = _case2_problem(engine)
     p_end, hist = prob.train_on_device(p0, n_epoch=30, n_exp_train=20, rng=g, optimiser="adam", eta=0.005, weight_decay=1e-6,
