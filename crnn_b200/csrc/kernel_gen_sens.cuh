@@ -96,8 +96,11 @@ __device__ __forceinline__ double gen_rhs(const WideP& P, const WideBlock& sb, G
       const double C = dens ? rho * ymw * 1e3 : Y;
       chiC = (C >= P.lb && C <= P.ub) ? 1.0 : 0.0;
       xi = lean_log(clampd(C, P.lb, P.ub));
-      dxi = chi / Y; d2i = chi / (Y * Y); chimw = dens ? chi / mw : 0.0;
-      a.chiC = chiC; a.dx = chiC * chi / Y; a.rr = dens ? -chi / (mw * S) : 0.0;
+      // chi, chiC are 0 or 1: x * (1 / Y) has the bits of x / Y, and a zero numerator no longer takes the division's slow path
+      // (a consumed species sits on the clamp: chi = 0 on every evaluation of the Cathode model)
+      const double rY = 1.0 / Y;
+      dxi = chi * rY; d2i = chi * (1.0 / (Y * Y)); chimw = dens ? chi * (1.0 / mw) : 0.0;
+      a.chiC = chiC; a.dx = (chiC * chi) * rY; a.rr = dens ? -chi * (1.0 / (mw * S)) : 0.0;
     } else if (lane == ns) {
       xi = -1.0 / P.gas_R / tv.T;
     } else if (lane == ns + 1) {
@@ -186,9 +189,11 @@ __device__ __forceinline__ void col_apply(const WideP& P, const WideBlock& sb, c
   double lr1 = 0.0, lr2 = 0.0, lr12 = 0.0;
   if (F2) {
     double s1 = 0.0;
-    for (int l = 0; l < ns; ++l) s1 = fma(pc.chimw[l], a[l * cs], s1);
-    lr1 = -s1 / pc.Ssum;
-    if (D2) { lr2 = d.lr2; lr12 = s1 * d.s2 / (pc.Ssum * pc.Ssum); }
+    if (P.kind == CRNN_RHS_F2_MASSFRAC_TP) {   // F5 has no density map: chimw = 0, every term below is zero
+      for (int l = 0; l < ns; ++l) s1 = fma(pc.chimw[l], a[l * cs], s1);
+      lr1 = -s1 / pc.Ssum;
+      if (D2) { lr2 = d.lr2; lr12 = s1 * d.s2 / (pc.Ssum * pc.Ssum); }
+    }
   }
   for (int i = 0; i < ns; ++i) dst[i * cs] = 0.0;
   const double xin = pc.x[ds.i_in], x2in = D2 ? d.x2[ds.i_in] : 0.0;
