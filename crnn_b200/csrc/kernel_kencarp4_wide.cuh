@@ -58,7 +58,7 @@ k_kencarp4_wide(const __grid_constant__ WideP P, const double* __restrict__ u0,
   auto rhs = [&](double tt, double y, WideAux& ax) -> double { return wide_rhs<F2, SPARSE>(P, sb, ww, lane, my_mw, tt, y, ax, tab_seg); };
   // W^{-1} explicitly (Gauss-Jordan, in place) and mat-vec "solves": ~20 Newton solves share one factorisation
   auto lusolve = [&](double b) -> double { return wide_invmul(ww, lane, ns, b); };
-  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { wide_build_inv<F2>(P, sb, ww, lane, rsrc, ax, gdt); };
+  auto build_lu = [&](const double* rsrc, const WideAux& ax, double gdt) { wide_build_inv<F2, SPARSE>(P, sb, ww, lane, rsrc, ax, gdt); };
   // rms over the n state components of v_i / (atol_i + max(|a_i|,|b_i|) rtol_i)
   auto wrms = [&](double v, double a, double b) -> double {
     double q = 0.0;
