@@ -72,3 +72,34 @@ def test_f4_gradients_and_kencarp4_are_refused_loudly(engine, golden):
         engine.loss_grad_batch(m, cases.yeast_opts(alg=0), np.zeros((m.n_w, 2)), u0, np.zeros((4, 300, 7)), np.ones(7))
     with pytest.raises(EngineError):
         engine.solve_batch(m, cases.yeast_opts(alg=_abi.ALG_KENCARP4), u0)
+
+
+def test_edge_cases_of_the_new_steppers_and_flavours(engine, golden):
+    """empty and single-trajectory calls, per-trajectory truncation (`n_save_used`, rober_crnn.jl:218), `maxiters` and device buffers
+    for TRBDF2 / AutoTsit5(TRBDF2) and the F4 flavour: retcodes, n_saved and counts as the oracle's"""
+    import torch
+    from dataclasses import replace
+    from problems import make_problem
+    m4 = cases.yeast_model(np.array(golden["yeast"]["p"]))
+    pb = make_problem("robertson", golden, 24)
+    jobs = [(m4, cases.yeast_opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2, n_save=40), yeast_u0(24, seed=9)),
+            (pb["true_model"], pb["case"].opts(alg=_abi.ALG_TRBDF2, pred_clamp=(-np.inf, np.inf)), pb["u0"]),
+            (pb["true_model"], pb["case"].opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2, pred_clamp=(-np.inf, np.inf)), pb["u0"])]
+    for model, o, u0 in jobs:
+        r0 = engine.solve_batch(model, o, u0[:0])
+        assert r0["pred"].shape == (0, o.n_save, o.n_obs(model.n_state)) and r0["retcode"].shape == (0,)
+        g1 = engine.solve_batch(model, o, u0[:1]); r1 = oracle.solve_batch(model, o, u0[:1])
+        assert g1["retcode"][0] == r1["retcode"][0] == _abi.RET_SUCCESS and g1["stats"]["n_rhs"][0] == r1["stats"]["n_rhs"][0]
+        nsu = np.random.default_rng(1).integers(1, o.n_save + 1, size=len(u0)).astype(np.int32)
+        g = engine.solve_batch(model, o, u0, n_save_used=nsu); r = oracle.solve_batch(model, o, u0, n_save_used=nsu, n_threads=8)
+        assert np.array_equal(g["n_saved"], nsu) and np.array_equal(g["retcode"], r["retcode"])
+        assert (g["stats"]["n_accept"] == r["stats"]["n_accept"]).mean() > 0.9
+        assert (g["pred"][np.arange(len(u0))[:, None] * 0 + np.arange(o.n_save)[None, :] >= nsu[:, None]] == 0.0).all()   # rows beyond n_saved are zero
+        om = replace(o, maxiters=7)
+        g = engine.solve_batch(model, om, u0); r = oracle.solve_batch(model, om, u0, n_threads=8)
+        assert (g["retcode"] == _abi.RET_MAXITERS).all() and np.array_equal(g["retcode"], r["retcode"])
+        assert np.array_equal(g["n_saved"], r["n_saved"]) and np.array_equal(g["stats"]["n_rhs"], r["stats"]["n_rhs"])
+        # device buffers: same bits as the host-buffer call
+        gh = engine.solve_batch(model, o, u0)
+        gd = engine.solve_batch(model, o, torch.from_numpy(u0).cuda())
+        assert np.array_equal(gd["pred"].cpu().numpy(), gh["pred"]) and np.array_equal(gd["retcode"].cpu().numpy(), gh["retcode"])
