@@ -44,8 +44,8 @@ N_PER_GPU = 65536
 BYTES_PER_TRAJ = 8 * (7 + 2 * 6 * 50 + 1)   # u0 + targets read + saved states written + loss
 FP64_PEAK_TFLOPS = 37.106   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak.json)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_tsit5_sens launch of this exact workload, from the committed
-# `ncu --set full` capture of the round-2 kernel (profiles/r2_sens_v14_base.txt): 162.2 MB + 126.2 MB; algorithmic bytes are 318.8 MB
-NCU_DRAM_BYTES_PER_LAUNCH = 288.46e6
+# `ncu --set full` capture of the round's final kernel (profiles/r2_sens_final.txt): 161.4 MB + 128.2 MB; algorithmic bytes are 318.8 MB
+NCU_DRAM_BYTES_PER_LAUNCH = 289.57e6
 METRIC = "trajectories/sec (case2: Tsit5 + 25 forward sensitivities + fused loss, 65 536 ICs per B200)"
 
 
