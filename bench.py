@@ -402,6 +402,42 @@ def train_loop_rates(eng, c, opts, u0_h, data_h, yscale, n_exp=20, n_steps=400):
             "final_step_loss_device": float(r["step_loss"][-1])}
 
 
+def svgd_rates(eng, n_particles=100, n_save=48):
+    """The SVGD gradient call of Cathode_NCM333_UQ/src_333/network.jl:222-260 - 100 particles x 5 heating rates (17 parameters, RHS F5,
+    heat-release MSE), sequential in the reference - as ONE crnn_loss_grad_particles launch, with the script's own AutoTsit5(TRBDF2)
+    and with its Rosenbrock23 sibling.  Targets come from an engine solve of a 'true' parameter set (2 % noise)."""
+    from crnn_b200 import _abi, cases
+    betas = np.array([2.0, 5.0, 10.0, 15.0, 20.0])
+    scales = np.array([30.0, 30.0, 30.0, 1.5, 1.5, 1.5, 1.0, 1.0, 1.0, 100.0, 100.0, 100.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    t_hi = 330.0 / (betas.max() / 60.0)
+    ts = np.linspace(0.0, t_hi, n_save)
+    g = np.random.default_rng(2)
+    p_true = cases.cathode_p_true() / scales
+    E = betas.size
+    u0 = np.tile(np.array([1.0, 0.0, 0.0]), (E, 1))
+    tab_T = np.stack([cases.cathode_ramp(b, t_hi)[1] for b in betas])
+
+    def model_for(p, beta):
+        w_in, w_b, w_out, w_obs, seed = cases.p2vec_cathode_uq(p, scales)
+        return cases.cathode_model(w_in, w_b, w_out, w_obs, beta, t_hi), seed
+    o_gen = cases.cathode_opts(ts, alg=_abi.ALG_ROSENBROCK23, pred_clamp=(-np.inf, np.inf))
+    data = np.stack([eng.solve_batch(model_for(p_true, b)[0], o_gen, u0[e:e + 1])["pred"][0] for e, b in enumerate(betas)])
+    data *= 1.0 + 0.02 * g.standard_normal(data.shape)
+    parts = p_true[None, :] * (1.0 + 0.03 * g.standard_normal((n_particles, 17)))
+    ws, sds = zip(*[(lambda ms: (ms[0].flat_weights(), ms[1]))(model_for(q, betas[0])) for q in parts])
+    m0 = model_for(parts[0], betas[0])[0]
+    out = {"workload": f"{n_particles} particles x {E} heating rates, 17 parameters, {n_save} saves, heat-release MSE (one launch of {n_particles * E} trajectories)"}
+    for name, alg in (("AutoTsit5(TRBDF2)", _abi.ALG_AUTO_TSIT5_TRBDF2), ("AutoTsit5(Rosenbrock23)", _abi.ALG_AUTO_TSIT5_ROS23)):
+        o = cases.cathode_opts(ts, alg=alg, pred_clamp=(-np.inf, np.inf))
+        call = lambda: eng.loss_grad_particles(m0, o, np.array(ws), np.array(sds), u0, data, np.array([1.0]), _abi.LOSS_MSE, tab_T=tab_T)
+        r = call(); call()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            r = call()
+        out[name] = {"ms_per_gradient_call": (time.perf_counter() - t0) / 5 * 1e3, "all_success": bool((r["retcode"] == 1).all())}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -613,6 +649,7 @@ def main():
                                  "grad_rel_l2": float(np.linalg.norm(gpu_grad - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"]))}
         if a.gpus == 1 and not a.no_extra:
             out["train_loop"] = train_loop_rates(eng, c, opts, u0_h, data_h, yscale)
+            out["svgd_particles"] = svgd_rates(eng)
         if extra is not None:
             out["configs"] = extra
         print(json.dumps(out))

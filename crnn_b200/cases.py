@@ -533,8 +533,8 @@ def cathode_model(w_in, w_b, w_out, w_obs, beta, t_end, lb=1e-8):
 
 
 def cathode_opts(ts, alg=_abi.ALG_AUTO_TSIT5_ROS23, lb=1e-8, **kw) -> SolveOpts:
-    """`ODEProblem(crnn!, u0, tspan, p, abstol = lb)`, `saveat = ts` (network.jl:96,103-116); the stiff half of the
-    script's composite is TRBDF2, here Rosenbrock23 (DESIGN.md "Named deviations")."""
+    """`ODEProblem(crnn!, u0, tspan, p, abstol = lb)`, `saveat = ts` (network.jl:96,103-116); `alg = ALG_AUTO_TSIT5_TRBDF2` is the
+    script's own `AutoTsit5(TRBDF2(autodiff = true))` (:102), the default its Rosenbrock23 sibling."""
     ts = np.asarray(ts, dtype=np.float64)
     base = dict(saveat=ts, t0=float(ts[0]), t1=float(ts[-1]), alg=alg, abstol=lb, reltol=1e-3, maxiters=100000,
                 obs_idx=np.array([0]))
