@@ -585,6 +585,24 @@ def p2vec_yeast(p):
     return w_in, w_b, w_out, w_J, pnn
 
 
+def yeast_seed(p):
+    """dW/dp of the yeast script's parameter vector in the adjoint's weight space [vec(w_in) 12x12; w_b; vec(w_out[1:ns, :]); w_J;
+    pnn]: p2vec (:112-123) differentiated with ForwardDiff's clamp convention, the MLP parameters map to themselves."""
+    ns, ns_, nr = YEAST_NS, YEAST_NS_, YEAST_NR
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    n_crnn = nr * (ns_ + 1) + ns + 1
+    d = _D.seed(p)
+    slope = d[n_crnn - 1] * 100.0
+    w_b = d[0:nr] * slope.broadcast_scalar((nr,))
+    w_out = d[nr:nr * (ns_ + 1)].reshape_f(ns_, nr)
+    w_in = (-w_out).clamp(0.0, 4.0)
+    w_J = d[nr * (ns_ + 1):n_crnn - 1]
+    pnn = d[n_crnn:]
+    n_p = p.size
+    return np.concatenate([w_in.j.reshape(-1, n_p, order="F"), w_b.j.reshape(-1, n_p), w_out.j[:ns].reshape(-1, n_p, order="F"),
+                           w_J.j.reshape(-1, n_p), pnn.j.reshape(-1, n_p)], axis=0)
+
+
 def yeast_model(p, lb=1e-5, ub=100.0) -> CRNNModel:
     """`crnn` of yeast_glycolysis.jl:128-132 as an F4 model: u_ = vcat(u, rep(u)), du = (w_out * exp(w_in' log clamp(u_) + w_b))[1:ns]
     .+ w_J — only the first ns rows of w_out enter (lb = atol = 1e-5, ub = 100, :34-37)."""
@@ -601,6 +619,21 @@ def yeast_opts(alg=_abi.ALG_AUTO_TSIT5_TRBDF2, n_save=300, t1=5.0, abstol=1e-6, 
     kw.setdefault("pred_clamp", (1e-5, 100.0))
     return SolveOpts(saveat=np.linspace(0.0, t1, n_save), t0=0.0, t1=t1, alg=alg, abstol=abstol, reltol=reltol,
                      maxiters=100000, obs_idx=np.arange(YEAST_NS), **kw)
+
+
+@dataclass
+class _YeastCase(Case):
+    """yeast_glycolysis.jl as a Case: F4 model, gradient of all 294 parameters (164 CRNN + 130 MLP) by the adjoint kernels over the
+    extended weight space; `alg` is Tsit5 — the non-stiff half of the script's AutoTsit5(TRBDF2), which the gradient path serves
+    (predictions with the composite: `opts(alg=ALG_AUTO_TSIT5_TRBDF2)`)."""
+
+    def model(self, p, out_scale=None):
+        return yeast_model(p, self.lb, self.ub), yeast_seed(p)
+
+
+CASES["yeast"] = _YeastCase("yeast", YEAST_NS, YEAST_NR, 294, _abi.RHS_F4, 1e-5, 100.0, _abi.ALG_TSIT5, 1e-6, 1e-3, (0.0, 5.0), 300,
+                            p2vec=lambda p: (*p2vec_yeast(p)[:3], None), pred_clamp=(1e-5, 100.0), loss_kind=_abi.LOSS_MAE_SCALED,
+                            sens_mode=_abi.SENS_DISCRETE_ADJOINT)
 
 
 def mlp_reference(dims, params, x, act_out=0):

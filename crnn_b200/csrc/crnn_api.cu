@@ -207,7 +207,13 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   if (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs || loss_kind == CRNN_LOSS_MSE)
     return fail(h, CRNN_ERR_UNSUPPORTED, "the adjoint kernels serve F0 / F1 / F2 with the MAE losses on the states (use sens_mode FORWARD)");
   const int n = m->n_state, ns = m->n_species, nr = m->n_reac;
-  const int nw = nr * (m->n_in + 1 + ns);
+  // F4: the quadrature runs in the extended weight space [vec(w_in); w_b; vec(w_out); w_J; mlp_params]
+  const bool f4 = (m->rhs_kind == CRNN_RHS_F4_MLP_AUG);
+  int nw = nr * (m->n_in + 1 + ns);
+  if (f4) {
+    nw += ns;
+    for (int l = 0; l < m->mlp_n_layers; ++l) nw += m->mlp_dims[l] * m->mlp_dims[l + 1] + m->mlp_dims[l + 1];
+  }
   if (nw > 32 * ADJ_MAX_ENT) return fail(h, CRNN_ERR_UNSUPPORTED, "adjoint kernel supports n_w <= 512");
   // extra device doubles: scale[ns] | inv_ys[n] | seed [nw*np]
   std::vector<double> extra((size_t)ns + n + (size_t)nw * np, 1.0);
@@ -228,12 +234,13 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   const double* seed_dev = extra_dev + ns + n;
   P.nw = nw; P.loss_kind = loss_kind;
   P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
+  P.mlp_extra = f4 ? (3 * m->mlp_n_layers + 2) * 32 : 0;
   constexpr int WARPS = 4;
   // blocks per SM: four (16 warps, 128 registers with 116 B spilled) unless CRNN_B200_ADJ_BLOCKS=2 asks for the two-block build
   static const bool want_four = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return !e || std::atoi(e) != 2; }();
   const bool f2 = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP;
   const int stride = 8 * n + 2;
-  const size_t fixed_pw = (6 * 32 + 2 + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);   // kernel_tsit5_adjoint.cuh: ADJ_FIXED
+  const size_t fixed_pw = (6 * 32 + 2 + (size_t)P.mlp_extra + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);   // kernel_tsit5_adjoint.cuh: ADJ_FIXED
   // forward-record capacity in shared memory for `nb` blocks of 4 warps per SM (steps per warp; < 0: does not fit)
   auto cap_for = [&](int nb) -> long long {
     const size_t budget = (size_t)(227 * 1024 / nb) - 2048 - sizeof(WideBlockLite);
@@ -244,8 +251,9 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   const bool four_blocks = want_four && cap_for(4) >= 4;
   const long long cap = cap_for(four_blocks ? 4 : 2);
   if (cap < 1) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
-  auto kern = four_blocks ? (f2 ? k_tsit5_adjoint<WARPS, true, 4> : k_tsit5_adjoint<WARPS, false, 4>)
-                          : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
+  auto kern = f4 ? (four_blocks ? k_tsit5_adjoint<WARPS, false, 4, true> : k_tsit5_adjoint<WARPS, false, 2, true>)
+              : four_blocks ? (f2 ? k_tsit5_adjoint<WARPS, true, 4> : k_tsit5_adjoint<WARPS, false, 4>)
+                            : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
   P.cap_s = (int)cap;
   P.cap_g = 512;
   const size_t smem = sizeof(WideBlockLite) + WARPS * (fixed_pw + (size_t)P.cap_s * stride * sizeof(double));
@@ -449,8 +457,8 @@ int loss_grad_core(crnn_handle* h, const crnn_model* m, const crnn_opts* o, cons
                    const double* yscale, int32_t loss_kind, const HostIO& io, int64_t N, double* grad_sum) {
   int rc = validate(h, m, o, N);
   if (rc) return rc;
-  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG)
-    return fail(h, CRNN_ERR_UNSUPPORTED, "the MLP-augmented RHS (F4) is served on the predict path (crnn_solve_batch) only");
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG && o->sens_mode != CRNN_SENS_INTERP_ADJOINT && o->sens_mode != CRNN_SENS_DISCRETE_ADJOINT)
+    return fail(h, CRNN_ERR_UNSUPPORTED, "gradients of the MLP-augmented RHS (F4) come from the adjoint sens_modes (Tsit5): forward mode is not built");
   if (N > 0 && (!io.u0 || !io.data || !io.loss)) return fail(h, CRNN_ERR_BAD_ARG, "null u0/data/loss");
   if (np < 0 || (np > 0 && !dW_dp)) return fail(h, CRNN_ERR_BAD_ARG, "bad seed matrix");
   if (loss_kind != CRNN_LOSS_MAE_SCALED && loss_kind != CRNN_LOSS_MAE_LOG && loss_kind != CRNN_LOSS_MSE)

@@ -45,12 +45,16 @@ struct AdjP {
   double* scratch;         // global overflow record, per warp slot
   int cap_s, cap_g;        // record capacity (steps) in shared / global memory
   int nw, loss_kind;
-  int discrete, pad;       // 1: discrete adjoint (reverse-mode through the recorded steps), 0: interpolating adjoint
+  int discrete;            // 1: discrete adjoint (reverse-mode through the recorded steps), 0: interpolating adjoint
+  int mlp_extra;           // F4: doubles per warp for the MLP's activations / pre-activations / deltas ((3L + 2) * 32), else 0
 };
 
 constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
 
-template <int WARPS, bool F2, int MINB = 2>
+// MLP: the F4 flavour (MLP-augmented inputs, yeast_glycolysis.jl:128-142): the forward pass evaluates the Flux chain lane-per-neuron,
+// the adjoint RHS goes back through it (oracle adj_rhs_f4) and the quadrature runs in the extended weight space
+// [vec(w_in); w_b; vec(w_out); w_J; mlp_params] - its own instantiation.
+template <int WARPS, bool F2, int MINB = 2, bool MLP = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, const int* __restrict__ n_save_used,
                 long long ntraj, const double* __restrict__ data, double* __restrict__ loss,
@@ -66,12 +70,18 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] | GW[nw] GS[nw] | record[cap_s][stride]
   // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] sl[32] one[2] | GW[nw] GS[nw] | record[cap_s][stride]
   constexpr int ADJ_FIXED = 6 * 32 + 2;   // crnn_api.cu::loss_grad_adjoint sizes the launch with the same number
-  const size_t per_warp = ADJ_FIXED + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
+  const size_t per_warp = ADJ_FIXED + (MLP ? P.mlp_extra : 0) + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
   double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlockLite)) + per_warp * warp;
   double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
   double* s_chi = wbase + 128;
   double* s_sl = wbase + 160;   // scale_i * lambda_i / rho: the left factor of the G_out outer product
-  double* GW = wbase + ADJ_FIXED; double* GS = GW + ((nw + 1) & ~1);
+  // F4: v[32] (cotangents of the augmented input rows; also the state broadcast) | a_l[32], l = 0..L | s_l[32], l < L | delta_l[32], l < L
+  const int ML = MLP ? W.mlp_layers : 0;
+  double* s_v = wbase + ADJ_FIXED;
+  auto A_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * l; };
+  auto SP_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * (ML + 1 + l); };
+  auto DL_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * (2 * ML + 1 + l); };
+  double* GW = wbase + ADJ_FIXED + (MLP ? P.mlp_extra : 0); double* GS = GW + ((nw + 1) & ~1);
   if (lane == 0) wbase[192] = 1.0;   // the unit left factor of the G_b entries
   double* rec_s = GS + ((nw + 1) & ~1);
   double* rec_g = P.scratch + ((size_t)blockIdx.x * WARPS + warp) * (size_t)P.cap_g * stride;
@@ -98,7 +108,19 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     int code = 0;
     if (e < nin * nr) code = ((0 + e % nin) << 16) | (96 + e / nin);
     else if (e < nin * nr + nr) code = (192 << 16) | (96 + e - nin * nr);
-    else if (e < nw) { const int f = e - nin * nr - nr; code = ((160 + f % ns) << 16) | (32 + f / ns); }
+    else if (e < nin * nr + nr + ns * nr) { const int f = e - nin * nr - nr; code = ((160 + f % ns) << 16) | (32 + f / ns); }
+    else if (MLP && e < nin * nr + nr + ns * nr + ns) code = ((160 + (e - nin * nr - nr - ns * nr)) << 16) | 192;   // w_J[i]: (scale_i lambda_i) * 1
+    else if (MLP && e < nw) {   // W_l[k, i]: delta_l[k] * a_l[i];  b_l[k]: delta_l[k] * 1
+      int f = e - (nin * nr + nr + ns * nr + ns);
+      for (int l = 0; l < ML; ++l) {
+        const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
+        const int dl_off = ADJ_FIXED + 32 + 32 * (2 * ML + 1 + l), a_off = ADJ_FIXED + 32 + 32 * l;
+        if (f < din * dout) { code = ((dl_off + f % dout) << 16) | (a_off + f / dout); break; }
+        f -= din * dout;
+        if (f < dout) { code = ((dl_off + f) << 16) | 192; break; }
+        f -= dout;
+      }
+    }
     sb.ent[e] = code;
   }
   __syncthreads();
@@ -106,9 +128,63 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   auto rec_ptr = [&](int step) -> double* {
     return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
   };
+  // F4: the Flux chain of the state y (lane i holds y_i), lane k = neuron k, activations a_l and pre-activations s_l kept in the
+  // per-warp arrays for the way back; returns the value of augmented input row `lane` (state row or MLP output).  Same
+  // arithmetic as wide_mlp_aug / the oracle's mlp_eval.
+  auto mlp_aug = [&](double y) -> double {
+    __syncwarp();
+    s_v[lane] = y;
+    __syncwarp();
+    double a = lane < W.mlp_dims[0] ? s_v[__ldg(W.mlp_in_idx + lane)] : 0.0;
+    const double* w = W.mlp_params;
+#pragma unroll 1
+    for (int l = 0; l < ML; ++l) {
+      const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
+      A_(l)[lane] = a;
+      __syncwarp();
+      double sacc = 0.0;
+      if (lane < dout) {
+        for (int i = 0; i < din; ++i) sacc = fma(__ldg(w + lane + dout * i), A_(l)[i], sacc);
+        sacc += __ldg(w + din * dout + lane);
+        SP_(l)[lane] = sacc;
+        if (l + 1 < ML) {
+          const double th = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (sacc + 0.044715 * (sacc * sacc * sacc)))) + 1.0);
+          sacc = 0.5 * sacc * (1.0 + th);
+        } else {
+          sacc = W.mlp_act_out == 0 ? lean_log(1.0 + lean_exp(-fabs(sacc))) + (sacc > 0.0 ? sacc : 0.0) : lean_exp(sacc);
+        }
+      }
+      a = sacc;
+      w += din * dout + dout;
+    }
+    A_(ML)[lane] = a;
+    __syncwarp();
+    if (lane >= nin) return 0.0;
+    const int src = __ldg(W.aug_src + lane);
+    return src >= 0 ? s_v[src] : A_(ML)[-1 - src];
+  };
   // forward RHS: lane i holds y_i -> f_i (x, r left in shared memory)
   int tab_seg = 0;  // F2: segment hint of the T(t), P(t) lookup
   auto rhs = [&](double tt, double y) -> double {
+    if (MLP) {
+      const double v = mlp_aug(y);
+      s_x[lane] = lane < nin ? lean_log(clampd(v, W.lb, W.ub)) : 0.0;
+      __syncwarp();
+      if (lane < nr) {
+        double z = sb.w_b[lane];
+#pragma unroll 2
+        for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+        s_r[lane] = lean_exp(z);
+      }
+      __syncwarp();
+      double f = 0.0;
+      if (isp) {
+#pragma unroll 2
+        for (int j = 0; j < nr; ++j) f = fma(sb.w_out[j][lane], s_r[j], f);
+        if (W.w_J) f += __ldg(W.w_J + lane);
+      }
+      return f;
+    }
     __syncwarp();
     double xi = 0.0, rho = 1.0;
     if (f2) {  // HyChem mass fractions (kernel_wide_solve.cuh::wide_rhs)
@@ -276,6 +352,87 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     // x, r, chiC are still in shared memory, dx / rr / 1/rho / WS in the registers below.  Same bits: they are functions of (t, u).
     double c_dxi = 0.0, c_rrl = 0.0, c_inv_rho = 1.0, c_ws = 0.0;
     auto adj_rhs = [&](double tt, double ui, double li, bool reuse) -> double {
+      if (MLP) {   // F4 (oracle adj_rhs_f4)
+        if (!reuse) {
+          const double v = mlp_aug(ui);
+          double xi = 0.0, dxi = 0.0;
+          if (lane < nin) {
+            const double vc = clampd(v, W.lb, W.ub);
+            xi = lean_log(vc);
+            dxi = (v >= W.lb && v <= W.ub) ? 1.0 / vc : 0.0;
+          }
+          s_x[lane] = xi;
+          c_dxi = dxi;
+        }
+        __syncwarp();
+        s_lam[lane] = isp ? li : 0.0;
+        s_sl[lane] = my_scale * (isp ? li : 0.0);
+        __syncwarp();
+        if (lane < nr) {
+          double gs = 0.0, r;
+#pragma unroll 2
+          for (int i = 0; i < ns; ++i) gs = fma(sb.w_out[lane][i], s_lam[i], gs);
+          if (!reuse) {
+            double z = sb.w_b[lane];
+#pragma unroll 2
+            for (int i = 0; i < nin; ++i) z = fma(sb.w_inT[i][lane], s_x[i], z);
+            r = lean_exp(z);
+            s_r[lane] = r;
+          } else r = s_r[lane];
+          s_gr[lane] = gs * r;
+        }
+        __syncwarp();
+        {   // cotangent of every augmented input row
+          double sacc = 0.0;
+          if (lane < nin)
+#pragma unroll 2
+            for (int j = 0; j < nr; ++j) sacc = fma(sb.w_inT[lane][j], s_gr[j], sacc);
+          s_v[lane] = c_dxi * sacc;
+        }
+        __syncwarp();
+        double dl = 0.0, dh = 0.0;
+        for (int q = 0; q < nin; ++q) {   // state rows collect directly, hidden rows through the chain (ascending q, like the oracle)
+          const int src = __ldg(W.aug_src + q);
+          if (src == lane) dl += s_v[q];
+          if (-1 - src == lane) dh += s_v[q];
+        }
+        if (lane < W.mlp_dims[ML]) {
+          const double sl = SP_(ML - 1)[lane];
+          const double da = W.mlp_act_out == 0 ? 1.0 / (1.0 + lean_exp(-sl)) : A_(ML)[lane];
+          DL_(ML - 1)[lane] = dh * da;
+        }
+        const double* wl = W.mlp_params;
+        int woff[8];
+        {
+          int off = 0;
+#pragma unroll 1
+          for (int l = 0; l < ML; ++l) { woff[l] = off; off += W.mlp_dims[l] * W.mlp_dims[l + 1] + W.mlp_dims[l + 1]; }
+        }
+#pragma unroll 1
+        for (int l = ML - 1; l >= 0; --l) {
+          const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
+          __syncwarp();
+          double sacc = 0.0;
+          if (lane < din)
+            for (int k = 0; k < dout; ++k) sacc = fma(__ldg(wl + woff[l] + k + dout * lane), DL_(l)[k], sacc);
+          if (l > 0) {
+            if (lane < din) {
+              const double x = SP_(l - 1)[lane];
+              const double T = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (x + 0.044715 * (x * x * x)))) + 1.0);
+              const double gd = 0.5 * (1.0 + T) + 0.5 * x * (1.0 - T * T) * (0.7978845608028654 * (1.0 + 3.0 * 0.044715 * (x * x)));
+              DL_(l - 1)[lane] = sacc * gd;
+            }
+          } else {
+            __syncwarp();
+            s_v[lane] = lane < din ? sacc : 0.0;   // d / d (MLP input i); s_v's cotangents have been consumed
+            __syncwarp();
+            for (int i = 0; i < din; ++i)
+              if (__ldg(W.mlp_in_idx + i) == lane) dl += s_v[i];
+          }
+        }
+        __syncwarp();
+        return isp ? dl : 0.0;
+      }
       __syncwarp();
       if (!reuse) {
         double xi = 0.0, dxi = 0.0, rrl = 0.0, chiC = 0.0, inv_rho = 1.0;

@@ -118,13 +118,18 @@ class CRNNModel:
 
     @property
     def n_w(self) -> int:
-        return self.n_reac * (self.n_in + 1 + self.n_species) + (self.n_reac if self.w_obs is not None else 0)
+        n = self.n_reac * (self.n_in + 1 + self.n_species) + (self.n_reac if self.w_obs is not None else 0)
+        if self.rhs_kind == _abi.RHS_F4:   # the adjoint's extended weight space: + w_J + the MLP parameters
+            n += self.n_species + self.mlp_params.size
+        return n
 
     def flat_weights(self) -> np.ndarray:
-        """[vec(w_in); w_b; vec(w_out); (w_obs)] column-major: the row order of dW_dp."""
+        """[vec(w_in); w_b; vec(w_out); (w_obs) | (F4: w_J; mlp_params)] column-major: the row order of dW_dp."""
         parts = [self.w_in.reshape(-1, order="F"), self.w_b, self.w_out.reshape(-1, order="F")]
         if self.w_obs is not None:
             parts.append(self.w_obs)
+        if self.rhs_kind == _abi.RHS_F4:
+            parts += [np.zeros(self.n_species) if self.w_J is None else self.w_J, self.mlp_params]
         return np.concatenate(parts)
 
     def to_c(self):

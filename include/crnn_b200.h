@@ -70,8 +70,9 @@ enum crnn_rhs_kind {
                                   u_ = [u ; mlp(u)] (yeast-glycolysis/yeast_glycolysis.jl:128-142: 7 observed + 5 hidden species, du =
                                   (W_out*exp(W_in'*log(clamp(u_,lb,ub)) + b))[1:ns] .+ w_J) or u_ = [u1 ; mlp(u[1,3]) ; u3]
                                   (robertson/rober_crnn_qssa.jl:111-126); see the mlp_* / aug_src / w_J fields.  Predict path
-                                  (crnn_solve_batch); the stiff steppers use the scripts' own FINITE-DIFFERENCE Jacobian
-                                  (TRBDF2 / Rosenbrock23(autodiff=false)) */
+                                  (crnn_solve_batch): the stiff steppers use the scripts' own FINITE-DIFFERENCE Jacobian
+                                  (TRBDF2 / Rosenbrock23(autodiff=false)).  Loss + gradient (crnn_loss_grad_batch): the adjoint
+                                  sens_modes with Tsit5, in the extended weight space [.. ; w_J ; mlp_params] */
   CRNN_RHS_F5_TRAMP = 3        /* species under a tabulated temperature programme T(t), no density map:
                                   x=[log clamp(u,lb,ub); -1/(gas_R T(t)); log T(t)], du = W_out*exp(W_in'x+b) .* out_scale:
                                   Cathode/src/network.jl:68-80 and Cathode_NCM333_UQ/src_333/network.jl:153-168 (there
@@ -224,10 +225,12 @@ int crnn_solve_batch(crnn_handle* h, const crnn_model* m, const crnn_opts* o,
  *   Tsit5 (np <= 255) and Rosenbrock23 (np <= 63, n_species <= 6) for the reference scripts' dimensions, F0 / F1;
  *   with err_norm_includes_sens = 0 and Tsit5 every other model (<= 32, F2) is served by the discrete adjoint, which
  *   computes exactly that derivative.
- * sens_mode INTERP_ADJOINT / DISCRETE_ADJOINT: Tsit5, any dimensions <= 32, any np, n_w <= 512, F0 / F1 / F2.
+ * sens_mode INTERP_ADJOINT / DISCRETE_ADJOINT: Tsit5, any dimensions <= 32, any np, n_w <= 512, F0 / F1 / F2 / F4, MAE losses.
  *   dW_dp   [n_w, np] col-major HOST seed matrix = Jacobian of p2vec, with the
  *           n_w = n_reac*(n_in + 1 + n_species) rows ordered
  *           [vec(w_in); w_b; vec(w_out)]
+ *           (F4, adjoint modes: n_w += n_species + #mlp_params, rows [...; w_J; mlp_params] — the gradient covers the
+ *           CRNN weights AND the Flux chain, yeast_glycolysis.jl:136-145,246)
  *   data    [n_obs, n_save, N], yscale [n_obs] (host; ignored for MAE_LOG)
  *   loss    [N] per-trajectory loss (NaN when a trajectory saved nothing)
  *   grad_sum[np] sum over trajectories of d loss_i / d p, accumulated in a fixed

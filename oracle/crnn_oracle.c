@@ -1150,8 +1150,101 @@ static void solve_one_kencarp4(const ctx_t* c, const double* u0, int n_save_use,
  *  forward-mode one by O(tolerance). */
 typedef struct { double t, dt; } rec_hdr;
 
+/* F4 (MLP-augmented inputs): lambda^T df/du and the integrand of the parameter quadrature in the extended weight space
+ * [vec(w_in); w_b; vec(w_out); w_J; mlp_params]: the CRNN part as below with the nin augmented inputs, then reverse mode through
+ * u_ = A(u) (state rows pass through, hidden rows go back through the Flux chain: delta_L = v_hidden .* act_out'(s_L),
+ * delta_{l-1} = (W_l^T delta_l) .* gelu'(s_{l-1}), dW_l = delta_l a_{l-1}^T, db_l = delta_l). */
+static double act_gelu_d(double x) {
+  const double c0 = 0.7978845608028654, c1 = 0.044715;
+  const double T = m_tanh(c0 * (x + c1 * (x * x * x)));
+  return 0.5 * (1.0 + T) + 0.5 * x * (1.0 - T * T) * (c0 * (1.0 + 3.0 * c1 * (x * x)));
+}
+static void adj_rhs_f4(const ctx_t* c, double t, const double* u, const double* lam, double* dlam, double* gw) {
+  const crnn_model* m = c->m;
+  const int ns = c->ns, nin = c->nin, nr = c->nr, L = m->mlp_n_layers;
+  double a[9][MAXN], sp[8][MAXN], delta[8][MAXN];
+  (void)t;
+  for (int i = 0; i < m->mlp_dims[0]; ++i) a[0][i] = u[m->mlp_in_idx[i]];
+  const double* w = m->mlp_params;
+  const double* wl[8];
+  for (int l = 0; l < L; ++l) {
+    const int din = m->mlp_dims[l], dout = m->mlp_dims[l + 1];
+    wl[l] = w;
+    for (int k = 0; k < dout; ++k) {
+      double sacc = 0.0;
+      for (int i = 0; i < din; ++i) sacc += w[k + dout * i] * a[l][i];
+      sacc += w[din * dout + k];
+      sp[l][k] = sacc;
+      a[l + 1][k] = (l + 1 < L) ? act_gelu(sacc) : (m->mlp_act_out == 0 ? act_softplus(sacc) : m_exp(sacc));
+    }
+    w += din * dout + dout;
+  }
+  double x[MAXN], dxq[MAXN], r[MAXR], g[MAXR], mu[MAXN], vq[MAXN], dh[MAXN];
+  for (int q = 0; q < nin; ++q) {
+    const int src = m->aug_src[q];
+    const double v = src >= 0 ? u[src] : a[L][-1 - src];
+    const double vc = clampd(v, m->lb, m->ub);
+    x[q] = m_log(vc);
+    dxq[q] = (v >= m->lb && v <= m->ub) ? 1.0 / vc : 0.0;
+  }
+  for (int j = 0; j < nr; ++j) {
+    double z = m->w_b[j];
+    for (int q = 0; q < nin; ++q) z += m->w_in[q + nin * j] * x[q];
+    r[j] = m_exp(z);
+  }
+  for (int i = 0; i < ns; ++i) mu[i] = (m->out_scale ? m->out_scale[i] : 1.0) * lam[i];
+  for (int j = 0; j < nr; ++j) {
+    double sacc = 0.0;
+    for (int i = 0; i < ns; ++i) sacc += m->w_out[i + ns * j] * mu[i];
+    g[j] = sacc * r[j];
+  }
+  for (int q = 0; q < nin; ++q) {
+    double sacc = 0.0;
+    for (int j = 0; j < nr; ++j) sacc += m->w_in[q + nin * j] * g[j];
+    vq[q] = dxq[q] * sacc;
+  }
+  for (int l = 0; l < c->n; ++l) dlam[l] = 0.0;
+  for (int k = 0; k < m->mlp_dims[L]; ++k) dh[k] = 0.0;
+  for (int q = 0; q < nin; ++q) {
+    const int src = m->aug_src[q];
+    if (src >= 0) dlam[src] += vq[q]; else dh[-1 - src] += vq[q];
+  }
+  for (int k = 0; k < m->mlp_dims[L]; ++k) {
+    const double sl = sp[L - 1][k];
+    const double da = m->mlp_act_out == 0 ? 1.0 / (1.0 + m_exp(-sl)) : a[L][k];   /* softplus' = sigmoid, exp' = exp */
+    delta[L - 1][k] = dh[k] * da;
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const int din = m->mlp_dims[l], dout = m->mlp_dims[l + 1];
+    for (int i = 0; i < din; ++i) {
+      double sacc = 0.0;
+      for (int k = 0; k < dout; ++k) sacc += wl[l][k + dout * i] * delta[l][k];
+      if (l > 0) delta[l - 1][i] = sacc * act_gelu_d(sp[l - 1][i]);
+      else dlam[m->mlp_in_idx[i]] += sacc;
+    }
+  }
+  if (gw) {
+    const int off_b = nin * nr, off_out = off_b + nr, off_wJ = off_out + ns * nr, off_mlp = off_wJ + ns;
+    for (int j = 0; j < nr; ++j) {
+      for (int q = 0; q < nin; ++q) gw[q + nin * j] = x[q] * g[j];
+      gw[off_b + j] = g[j];
+      for (int i = 0; i < ns; ++i) gw[off_out + i + ns * j] = mu[i] * r[j];
+    }
+    for (int i = 0; i < ns; ++i) gw[off_wJ + i] = mu[i];
+    int off = off_mlp;
+    for (int l = 0; l < L; ++l) {
+      const int din = m->mlp_dims[l], dout = m->mlp_dims[l + 1];
+      for (int i = 0; i < din; ++i)
+        for (int k = 0; k < dout; ++k) gw[off + k + dout * i] = delta[l][k] * a[l][i];
+      for (int k = 0; k < dout; ++k) gw[off + din * dout + k] = delta[l][k];
+      off += din * dout + dout;
+    }
+  }
+}
+
 static void adj_rhs(const ctx_t* c, double t, const double* u, const double* lam, double* dlam, double* gw /* nw integrand or NULL */) {
   const crnn_model* m = c->m;
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) { adj_rhs_f4(c, t, u, lam, dlam, gw); return; }
   int ns = c->ns, nin = c->nin, nr = c->nr;
   const int f2 = (m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP);
   rhs_cache k; double du[MAXN], g[MAXR], mu[MAXN];
@@ -1418,6 +1511,10 @@ static void make_ctx(ctx_t* c, const crnn_model* m, const crnn_opts* o, const do
   c->m = m; c->o = o;
   c->n = m->n_state; c->ns = m->n_species; c->nin = m->n_in; c->nr = m->n_reac;
   c->nw = m->n_reac * (m->n_in + 1 + m->n_species) + (m->w_obs ? m->n_reac : 0);
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) { /* extended weight space of the adjoint: + w_J + the MLP parameters */
+    c->nw += m->n_species;
+    for (int l = 0; l < m->mlp_n_layers; ++l) c->nw += m->mlp_dims[l] * m->mlp_dims[l + 1] + m->mlp_dims[l + 1];
+  }
   c->seed = seed; c->ncol = 1 + np;
   c->order = (o->alg == CRNN_ALG_TSIT5 || o->alg == CRNN_ALG_AUTO_TSIT5_ROS23 || o->alg == CRNN_ALG_AUTO_TSIT5_TRBDF2) ? 5
              : ((o->alg == CRNN_ALG_ROSENBROCK23 || o->alg == CRNN_ALG_TRBDF2) ? 2 : 4);
@@ -1490,10 +1587,10 @@ int crnn_oracle_loss_grad_batch(const crnn_model* m, const crnn_opts* o, const d
   int rc = check_dims(m, o);
   if (rc) return rc;
   if (o->alg == CRNN_ALG_KENCARP4) return CRNN_ERR_UNSUPPORTED; /* value path only */
-  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG) return CRNN_ERR_UNSUPPORTED; /* value path only */
   const int adjoint = (o->sens_mode == CRNN_SENS_INTERP_ADJOINT || o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT);
+  if (m->rhs_kind == CRNN_RHS_F4_MLP_AUG && !adjoint) return CRNN_ERR_UNSUPPORTED; /* gradients of F4 models: the adjoint modes */
   if (adjoint && o->alg != CRNN_ALG_TSIT5) return CRNN_ERR_UNSUPPORTED;
-  if (adjoint && (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs)) return CRNN_ERR_UNSUPPORTED; /* forward mode only */
+  if (adjoint && (m->rhs_kind == CRNN_RHS_F5_TRAMP || m->w_obs || loss_kind == CRNN_LOSS_MSE)) return CRNN_ERR_UNSUPPORTED; /* forward mode only */
   ctx_t c; make_ctx(&c, m, o, dW_dp, o->sens_mode == CRNN_SENS_FORWARD ? np : 0);
   size_t pstride = (size_t)o->n_obs * o->n_save;
   double* gall = (double*)calloc((size_t)(np > 0 ? np : 1) * (size_t)N, sizeof(double));

@@ -7,7 +7,7 @@ import pytest
 from scipy.integrate import solve_ivp
 
 from crnn_b200 import _abi, cases
-from crnn_b200.model import CRNNModel
+from crnn_b200.model import CRNNModel, SolveOpts
 from oracle import oracle
 
 
@@ -84,5 +84,65 @@ def test_committed_yeast_checkpoint_follows_the_glycolysis_oscillator(golden):
     sol = solve_ivp(lambda t, y: lit(y), (0, 5), u0[0], method="DOP853", rtol=1e-10, atol=1e-12, t_eval=ts)
     tight = oracle.solve_batch(m, cases.yeast_opts(alg=_abi.ALG_TSIT5, abstol=1e-11, reltol=1e-9, pred_clamp=(-np.inf, np.inf)), u0[:1])
     assert np.abs(tight["pred"][0] - sol.y.T).max() < 1e-6
-    with pytest.raises(RuntimeError):      # predict path only
+    with pytest.raises(RuntimeError):      # gradients of F4: the adjoint sens_modes only
         oracle.loss_grad_batch(m, cases.yeast_opts(alg=0), np.zeros((m.n_w, 1)), u0, data, yscale)
+
+
+def model_from_flat(m, w):
+    """inverse of CRNNModel.flat_weights for an F4 model without an observable row"""
+    import dataclasses
+    nin, nr, ns = m.n_in, m.n_reac, m.n_species
+    o = np.cumsum([0, nin * nr, nr, ns * nr, ns, m.mlp_params.size])
+    return dataclasses.replace(m, w_in=w[o[0]:o[1]].reshape(nin, nr, order="F"), w_b=w[o[1]:o[2]], w_out=w[o[2]:o[3]].reshape(ns, nr, order="F"),
+                               w_J=w[o[3]:o[4]], mlp_params=w[o[4]:o[5]])
+
+
+def test_f4_adjoint_gradients_in_the_oracle(golden):
+    """the oracle's adjoint RHS for F4 goes back through the Flux chain (reverse mode: gelu' / softplus' / exp') and integrates the
+    gradient in the extended weight space [vec(w_in); w_b; vec(w_out); w_J; mlp]: (a) cases.yeast_seed = d flat_weights / dp,
+    (b) discrete and interpolating adjoint agree at tight tolerance, (c) both are the central differences of the loss,
+    for the yeast checkpoint (softplus output, all states into the MLP, w_J) and for the QSSA shape (exp output, a state subset
+    into the MLP, an augmented row BETWEEN state rows, no w_J) with an identity seed"""
+    p = np.array(golden["yeast"]["p"])
+    m, seed = cases.yeast_model(p), cases.yeast_seed(p)
+    assert m.n_w == 377 and seed.shape == (377, 294)
+    for k in (0, 5, 20, 100, 157, 163, 170, 293):
+        e = 1e-6 * np.eye(294)[k]
+        fd = (cases.yeast_model(p + e).flat_weights() - cases.yeast_model(p - e).flat_weights()) / 2e-6
+        assert np.abs(seed[:, k] - fd).max() < 1e-8 * max(1.0, np.abs(fd).max())
+    tight = dict(n_save=40, abstol=1e-12, reltol=1e-10, pred_clamp=(-np.inf, np.inf))
+    u0 = yeast_u0(2)
+    ts = np.linspace(0.0, 5.0, 40)
+    data = np.array([solve_ivp(cases.yeast_true_rhs, (0, 5), u, method="Radau", rtol=1e-9, atol=1e-12, t_eval=ts).y.T for u in u0])
+    ys = data.std(axis=1).max(axis=0) + 1e-5
+    g = {mode: oracle.loss_grad_batch(m, cases.yeast_opts(alg=0, sens_mode=mode, **tight), seed, u0, data, ys, _abi.LOSS_MAE_SCALED, n_threads=2)
+         for mode in (_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT)}
+    gd, gi = g[_abi.SENS_DISCRETE_ADJOINT]["grad_sum"], g[_abi.SENS_INTERP_ADJOINT]["grad_sum"]
+    assert np.linalg.norm(gd - gi) < 1e-7 * np.linalg.norm(gd)
+    ov = cases.yeast_opts(alg=0, **tight)
+    def L(q):
+        pr = oracle.solve_batch(cases.yeast_model(q), ov, u0, n_threads=2)["pred"]
+        return np.sum(np.mean(np.abs(data / ys - pr / ys), axis=(1, 2)))
+    ks = [0, 15, 60, 130, 157, 160, 163, 165, 200, 293]
+    fd = np.array([(L(p + 1e-6 * np.eye(294)[k]) - L(p - 1e-6 * np.eye(294)[k])) / 2e-6 for k in ks])
+    assert np.abs(gd[ks] - fd).max() < 1e-5 * np.abs(fd).max(), (gd[ks], fd)
+
+    q = qssa_like_model()
+    w = q.flat_weights()
+    assert w.size == q.n_w == 6 * 7 + 3 + 57
+    u0 = 0.2 + np.random.default_rng(3).random((2, 3))
+    so = lambda **kw: SolveOpts(saveat=np.linspace(0.0, 2.0, 21), t0=0.0, t1=2.0, alg=0, abstol=1e-12, reltol=1e-10, maxiters=100000, **kw)
+    data = oracle.solve_batch(model_from_flat(q, w * (1.0 + 0.05 * np.random.default_rng(5).normal(size=w.size))), so(), u0)["pred"]
+    gq = {mode: oracle.loss_grad_batch(q, so(sens_mode=mode), np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MAE_SCALED)["grad_sum"]
+          for mode in (_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT)}
+    assert np.linalg.norm(gq[_abi.SENS_DISCRETE_ADJOINT] - gq[_abi.SENS_INTERP_ADJOINT]) < 1e-4 * np.linalg.norm(gq[_abi.SENS_DISCRETE_ADJOINT])
+    def Lq(v):
+        pr = oracle.solve_batch(model_from_flat(q, v), so(), u0)["pred"]
+        return np.sum(np.mean(np.abs(data - pr), axis=(1, 2)))
+    ks = [0, 4, 17, 20, 30, 41, 43, 46, 60, 80, 101]    # w_in (incl. the MLP-fed row 1), w_b, w_out, w_J, MLP weights and biases
+    fd = np.array([(Lq(w + 1e-6 * np.eye(w.size)[k]) - Lq(w - 1e-6 * np.eye(w.size)[k])) / 2e-6 for k in ks])
+    gd = gq[_abi.SENS_INTERP_ADJOINT]
+    assert np.abs(gd[ks] - fd).max() < 1e-5 * np.abs(fd).max(), (gd[ks], fd)
+    with pytest.raises(RuntimeError):      # the adjoints carry the MAE losses
+        oracle.loss_grad_batch(q, so(sens_mode=_abi.SENS_INTERP_ADJOINT), np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MSE)
+    assert np.abs(gd[42:45]).max() > 0 and np.abs(gd[45:]).max() > 0

@@ -1,13 +1,15 @@
-"""GPU parity of the MLP-augmented RHS (F4: yeast_glycolysis.jl:128-142, rober_crnn_qssa.jl:111-126) on the predict path
-(k_wide_solve<..., MLP = true>: the MLP evaluated lane-per-neuron, finite-difference Jacobian for the stiff steppers as the scripts'
-autodiff=false) against the CPU oracle, through the C-ABI."""
+"""GPU parity of the MLP-augmented RHS (F4: yeast_glycolysis.jl:128-142, rober_crnn_qssa.jl:111-126) against the CPU oracle, through
+the C-ABI: the predict path (k_wide_solve<..., MLP = true>: the MLP evaluated lane-per-neuron, finite-difference Jacobian for the stiff
+steppers as the scripts' autodiff=false) and the gradient path (k_tsit5_adjoint<..., MLP = true>: the adjoint RHS goes back through
+the chain, all CRNN + MLP parameters in one backward pass)."""
 import numpy as np
 import pytest
 
 from crnn_b200 import _abi, cases
 from crnn_b200.engine import EngineError
 from oracle import oracle
-from test_f4_mlp_cpu import qssa_like_model, yeast_u0
+from crnn_b200.model import SolveOpts
+from test_f4_mlp_cpu import model_from_flat, qssa_like_model, yeast_u0
 
 pytestmark = pytest.mark.gpu
 
@@ -65,10 +67,85 @@ def test_qssa_shaped_model(engine, alg):
     assert (np.abs(got["pred"] - ref["pred"])[ok & same] / scale).max() < 1e-6
 
 
-def test_f4_gradients_and_kencarp4_are_refused_loudly(engine, golden):
+def _yeast_training_problem(golden, N, n_save=60, seed=4):
+    from scipy.integrate import solve_ivp
+    p = np.array(golden["yeast"]["p"])
+    u0 = yeast_u0(N, seed=seed)
+    ts = np.linspace(0.0, 5.0, n_save)
+    data = np.array([solve_ivp(cases.yeast_true_rhs, (0, 5), u, method="Radau", rtol=1e-9, atol=1e-12, t_eval=ts).y.T for u in u0])
+    return p, u0, data, data.std(axis=1).max(axis=0) + 1e-5
+
+
+@pytest.mark.parametrize("mode", [_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT])
+def test_f4_gradient_by_the_adjoints(engine, golden, mode):
+    """loss + gradient of all 294 parameters of the yeast model (164 CRNN + 130 MLP) from the adjoint kernels: the adjoint RHS goes back
+    through the Flux chain, the quadrature runs in the extended weight space [w_in; w_b; w_out; w_J; mlp]; against the oracle
+    (whose gradient tests/test_f4_mlp_cpu.py checks against finite differences)"""
+    p, u0, data, ys = _yeast_training_problem(golden, 48)
+    m, seed = cases.yeast_model(p), cases.yeast_seed(p)
+    assert seed.shape == (m.n_w, 294) and m.n_w == 377
+    o = cases.yeast_opts(alg=_abi.ALG_TSIT5, n_save=60, sens_mode=mode)
+    got = engine.loss_grad_batch(m, o, seed, u0, data, ys, _abi.LOSS_MAE_SCALED, want_pred=True)
+    ref = oracle.loss_grad_batch(m, o, seed, u0, data, ys, _abi.LOSS_MAE_SCALED, want_pred=True, n_threads=8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    for k in ("n_accept", "n_reject"):                     # the forward pass: the oracle's steps
+        assert np.array_equal(got["stats"][k], ref["stats"][k])
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-6)
+    rel = np.linalg.norm(got["grad_sum"] - ref["grad_sum"]) / np.linalg.norm(ref["grad_sum"])
+    assert rel < (1e-6 if mode == _abi.SENS_DISCRETE_ADJOINT else 1e-3), rel
+    assert np.abs(got["grad_sum"][164:]).max() > 0 and np.abs(got["grad_sum"][156:163]).max() > 0   # MLP and w_J entries are live
+    if mode == _abi.SENS_DISCRETE_ADJOINT:
+        # an oracle-free check: central differences of the GPU's own loss at reltol 1e-6 (~400 steps, inside the kernel's record
+        # capacity).  The discrete adjoint holds the step sizes fixed, the differences do not: agreement to ~tol/h, bar 1e-2
+        tol = dict(n_save=60, abstol=1e-9, reltol=1e-6, pred_clamp=(-np.inf, np.inf))
+        ov, og = cases.yeast_opts(alg=_abi.ALG_TSIT5, **tol), cases.yeast_opts(alg=_abi.ALG_TSIT5, sens_mode=mode, **tol)
+        def L(q):
+            pr = engine.solve_batch(cases.yeast_model(q), ov, u0[:4])["pred"]
+            return float(np.sum(np.mean(np.abs(data[:4] / ys - pr / ys), axis=(1, 2))))
+        r4 = engine.loss_grad_batch(m, og, seed, u0[:4], data[:4], ys, _abi.LOSS_MAE_SCALED)
+        assert (r4["retcode"] == _abi.RET_SUCCESS).all()
+        ks = [1, 40, 100, 158, 162, 163, 170, 260]
+        fd = np.array([(L(p + 1e-6 * np.eye(294)[k]) - L(p - 1e-6 * np.eye(294)[k])) / 2e-6 for k in ks])
+        assert np.abs(r4["grad_sum"][ks] - fd).max() < 1e-2 * np.abs(fd).max(), (r4["grad_sum"][ks], fd)
+
+
+@pytest.mark.parametrize("mode", [_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT])
+def test_f4_gradient_of_the_qssa_shape(engine, mode):
+    """rober_crnn_qssa.jl's shape: exp output, two of the three states into the MLP, the MLP-fed input row BETWEEN state rows, no w_J;
+    identity seed = the gradient with respect to every weight of the extended space"""
+    q = qssa_like_model()
+    w = q.flat_weights()
+    u0 = 0.2 + np.random.default_rng(3).random((64, 3))
+    o = SolveOpts(saveat=np.linspace(0.0, 2.0, 21), t0=0.0, t1=2.0, alg=_abi.ALG_TSIT5, abstol=1e-8, reltol=1e-6, maxiters=100000, sens_mode=mode)
+    data = oracle.solve_batch(model_from_flat(q, w * (1.0 + 0.05 * np.random.default_rng(5).normal(size=w.size))), o, u0, n_threads=8)["pred"]
+    got = engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MAE_SCALED)
+    ref = oracle.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MAE_SCALED, n_threads=8)
+    assert (got["retcode"] == _abi.RET_SUCCESS).all()
+    for k in ("n_accept", "n_reject"):
+        assert np.array_equal(got["stats"][k], ref["stats"][k])
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-9)
+    tol = 1e-7 if mode == _abi.SENS_DISCRETE_ADJOINT else 1e-3
+    assert np.linalg.norm(got["grad_sum"] - ref["grad_sum"]) < tol * np.linalg.norm(ref["grad_sum"])
+    assert np.abs(got["grad_sum"] - ref["grad_sum"]).max() < tol * np.abs(ref["grad_sum"]).max()
+    assert np.abs(got["grad_sum"][42:45]).max() > 0 and np.abs(got["grad_sum"][45:]).max() > 0    # w_J and MLP entries are live
+    with pytest.raises(EngineError):        # the adjoints carry the MAE losses
+        engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MSE)
+
+
+def test_f4_adjoint_record_capacity_is_reported(engine, golden):
+    """the adjoint kernels keep the forward steps of a trajectory in shared memory plus 512 overflow slots: a solve that needs more
+    (here: tolerances of 1e-10) comes back MaxIters for that trajectory — never a silently truncated gradient"""
+    p, u0, data, ys = _yeast_training_problem(golden, 4)
+    m, seed = cases.yeast_model(p), cases.yeast_seed(p)
+    o = cases.yeast_opts(alg=_abi.ALG_TSIT5, n_save=60, sens_mode=_abi.SENS_DISCRETE_ADJOINT, abstol=1e-12, reltol=1e-10)
+    got = engine.loss_grad_batch(m, o, seed, u0, data, ys, _abi.LOSS_MAE_SCALED)
+    assert (got["retcode"] == _abi.RET_MAXITERS).all()
+
+
+def test_f4_forward_mode_and_kencarp4_are_refused_loudly(engine, golden):
     m = cases.yeast_model(np.array(golden["yeast"]["p"]))
     u0 = yeast_u0(4)
-    with pytest.raises(EngineError):
+    with pytest.raises(EngineError):     # forward sensitivities of F4 are not built: the adjoint sens_modes serve its gradients
         engine.loss_grad_batch(m, cases.yeast_opts(alg=0), np.zeros((m.n_w, 2)), u0, np.zeros((4, 300, 7)), np.ones(7))
     with pytest.raises(EngineError):
         engine.solve_batch(m, cases.yeast_opts(alg=_abi.ALG_KENCARP4), u0)
