@@ -107,19 +107,20 @@ Base.@kwdef struct Setup
 end
 yscale_of(s::Setup) = isempty(s.yscale) ? ones(length(s.obs_idx)) : s.yscale
 
-function with_structs(f, s::Setup, w_in, w_b, w_out)
+function with_structs(f, s::Setup, w_in, w_b, w_out, w_J=s.w_J, mlp_params=s.mlp_params)
     w_in = Matrix{Float64}(w_in); w_b = Vector{Float64}(w_b); w_out = Matrix{Float64}(w_out)
+    w_J = Vector{Float64}(w_J); mlp_params = Vector{Float64}(mlp_params)   # F4: the current values when p2vec returns them
     ns, nr = size(w_out); n_in = size(w_in, 1)
     osc = s.out_scale === nothing ? Float64[] : s.out_scale
-    GC.@preserve w_in w_b w_out osc s begin
+    GC.@preserve w_in w_b w_out w_J mlp_params osc s begin
         n_state = s.rhs_kind >= 2 ? ns : n_in      # F0/F1: n_in == n_state; F2/F5: n_in = n_species + 2; F4: n_state = n_species
         i2p(v) = isempty(v) ? Ptr{Int32}(C_NULL) : pointer(v)
         f2p(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
         m = CModel(n_state, ns, n_in, nr, s.rhs_kind, length(s.tab_t), s.lb, s.ub, s.gas_R,
                    isempty(osc) ? C_NULL : pointer(osc), pointer(w_in), pointer(w_b), pointer(w_out),
                    f2p(s.mw), f2p(s.tab_t), f2p(s.tab_T), f2p(s.tab_P), f2p(s.w_obs),
-                   max(length(s.mlp_dims) - 1, 0), s.mlp_act_out, i2p(s.mlp_dims), i2p(s.mlp_in_idx), f2p(s.mlp_params),
-                   i2p(s.aug_src), f2p(s.w_J))
+                   max(length(s.mlp_dims) - 1, 0), s.mlp_act_out, i2p(s.mlp_dims), i2p(s.mlp_in_idx), f2p(mlp_params),
+                   i2p(s.aug_src), f2p(w_J))
         o = COpts(s.alg, s.sens_mode, 1, length(s.saveat), length(s.obs_idx), length(s.abstol), length(s.reltol), 0,
                   s.maxiters, s.tspan[1], s.tspan[2], s.pred_clamp[1], s.pred_clamp[2],
                   pointer(s.abstol), pointer(s.reltol), pointer(s.saveat), pointer(s.obs_idx),
@@ -134,12 +135,12 @@ end
 Drop-in for the scripts' `predict_neuralode(u0, p)`, batched: `u0s` is n_state × N.
 """
 function predict_neuralode(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, p; sample=nothing)
-    w_in, w_b, w_out = p2vec(p)
+    W = p2vec(p)                   # (w_in, w_b, w_out); an F4 p2vec may append (w_J, pnn), else Setup's w_J / mlp_params are used
     N = size(u0s, 2)
     nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)   # n_save_used: tspan = [0, tsteps[sample]] (rober_crnn.jl:125)
     pred = zeros(length(s.obs_idx), length(s.saveat), N)
     n_saved = zeros(Int32, N); ret = zeros(Int32, N)
-    with_structs(s, w_in, w_b, w_out) do m, o
+    with_structs(s, W...) do m, o
         check(e, ccall((:crnn_solve_batch, LIB), Cint,
               (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
               e.h, m, o, u0s, N, sample === nothing ? C_NULL : nsu, pred, n_saved, ret, C_NULL))
@@ -154,14 +155,17 @@ Replaces `ForwardDiff.gradient(x -> loss_neuralode(x, i_exp), p)` for a batch of
 `data` is n_obs × n_save × N (a `permutedims` of the scripts' `ode_data_list[i, :, :]`).
 The result feeds the unchanged `update!(opt, p, grad)` line.
 """
+# rows of the seed matrix: [vec(w_in); w_b; vec(w_out)] and, for an F4 model whose p2vec also returns (w_J, pnn), [...; w_J; pnn] — the
+# adjoint sens_modes (2, 3) then return the gradient of the CRNN weights AND the Flux chain (yeast_glycolysis.jl:136-145,246)
+flat_weights(p2vec) = q -> vcat(map(vec, p2vec(q))...)
+
 function loss_grad(e::Engine, s::Setup, p2vec, u0s::Matrix{Float64}, data::Array{Float64,3}, yscale::Vector{Float64}, p; sample=nothing)
     nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)   # per-experiment n_save_used (rober_crnn.jl:218)
-    flat(q) = (w = p2vec(q); vcat(vec(w[1]), vec(w[2]), vec(w[3])))
-    w_in, w_b, w_out = p2vec(p)
-    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat, p))      # n_w × np seed matrix
+    W = p2vec(p)                                               # (w_in, w_b, w_out) or, F4, (w_in, w_b, w_out[1:ns, :], w_J, pnn)
+    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat_weights(p2vec), p))      # n_w × np seed matrix
     N = size(u0s, 2); np_ = length(p)
     loss = zeros(N); grad = zeros(np_); n_saved = zeros(Int32, N); ret = zeros(Int32, N)
-    with_structs(s, w_in, w_b, w_out) do m, o
+    with_structs(s, W...) do m, o
         check(e, ccall((:crnn_loss_grad_batch, LIB), Cint,
               (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int32},
                Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
@@ -181,13 +185,12 @@ time truncation of robertson/rober_crnn.jl:218 (`n_save_used`).  Per step only t
 travel to the GPU(s) and np + 2 doubles come back.
 """
 function loss_grad(e::Engine, s::Setup, p2vec, ds::Dataset, idx, p; sample=nothing)
-    flat(q) = (w = p2vec(q); vcat(vec(w[1]), vec(w[2]), vec(w[3])))
-    w_in, w_b, w_out = p2vec(p)
-    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat, p))
+    W = p2vec(p)
+    dWdp = Matrix{Float64}(ForwardDiff.jacobian(flat_weights(p2vec), p))
     np_ = length(p); lsum = zeros(2); grad = zeros(np_)
     ix = idx === nothing ? Int64[] : Vector{Int64}(idx .- 1)
     nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)
-    with_structs(s, w_in, w_b, w_out) do m, o
+    with_structs(s, W...) do m, o
         check(e, ccall((:crnn_loss_grad_indexed, LIB), Cint,
               (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ptr{Float64}, Int32, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int32},
                Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),

@@ -73,6 +73,11 @@ uy = cases.YEAST_IC_LB + np.random.default_rng(0).random((min(N, 16), 7)) * (cas
 for alg in (_abi.ALG_TSIT5, _abi.ALG_ROSENBROCK23, _abi.ALG_AUTO_TSIT5_TRBDF2, _abi.ALG_TRBDF2):
     eng.solve_batch(my, cases.yeast_opts(alg=alg, n_save=40), uy)
 done.append("F4 yeast")
+dy = eng.solve_batch(my, cases.yeast_opts(alg=_abi.ALG_TSIT5, n_save=40), uy * 1.02)["pred"]
+for smode in (_abi.SENS_DISCRETE_ADJOINT, _abi.SENS_INTERP_ADJOINT):   # incl. forward steps beyond the shared-memory record
+    eng.loss_grad_batch(my, cases.yeast_opts(alg=_abi.ALG_TSIT5, n_save=40, sens_mode=smode), cases.yeast_seed(np.array(golden["yeast"]["p"])),
+                        uy, dy, np.ones(7))
+done.append("F4 yeast adjoint gradients")
 pb = make_problem("case2", golden, 20)
 ds = eng.dataset(pb["u0"], pb["data"])
 eng.train_steps(pb["model"], pb["opts"], ds, np.arange(20)[::-1].copy(), pb["yscale"], np.array(golden["case2"]["p"]), None, pb["loss_kind"],
