@@ -234,29 +234,43 @@ int loss_grad_adjoint(crnn_handle* h, const crnn_model* m, const crnn_opts* o, c
   const double* seed_dev = extra_dev + ns + n;
   P.nw = nw; P.loss_kind = loss_kind;
   P.discrete = (o->sens_mode == CRNN_SENS_DISCRETE_ADJOINT) ? 1 : 0;
-  P.mlp_extra = f4 ? (3 * m->mlp_n_layers + 2) * 32 : 0;
+  if (f4) {   // per-warp MLP arrays packed to the widest layer; a per-block copy of the parameters
+    int widest = 2, npar = 0;
+    for (int l = 0; l <= m->mlp_n_layers; ++l) widest = std::max(widest, (int)m->mlp_dims[l]);
+    for (int l = 0; l < m->mlp_n_layers; ++l) npar += m->mlp_dims[l] * m->mlp_dims[l + 1] + m->mlp_dims[l + 1];
+    P.mlp_stride = (widest + 1) & ~1;
+    P.mlp_extra = 32 + (3 * m->mlp_n_layers + 1) * P.mlp_stride;
+    P.mlp_np_raw = npar;
+    P.mlp_np = (npar + 1) & ~1;
+  }
+  P.gs_len = P.discrete ? 0 : ((nw + 1) & ~1);   // the stage accumulator of the interpolating adjoint's quadrature
   constexpr int WARPS = 4;
   // blocks per SM: four (16 warps, 128 registers with 116 B spilled) unless CRNN_B200_ADJ_BLOCKS=2 asks for the two-block build
   static const bool want_four = [] { const char* e = std::getenv("CRNN_B200_ADJ_BLOCKS"); return !e || std::atoi(e) != 2; }();
   const bool f2 = m->rhs_kind == CRNN_RHS_F2_MASSFRAC_TP;
   const int stride = 8 * n + 2;
-  const size_t fixed_pw = (6 * 32 + 2 + (size_t)P.mlp_extra + 2 * (size_t)((nw + 1) & ~1)) * sizeof(double);   // kernel_tsit5_adjoint.cuh: ADJ_FIXED
+  const size_t fixed_pw = (6 * 32 + 2 + (size_t)P.mlp_extra + (size_t)((nw + 1) & ~1) + (size_t)P.gs_len) * sizeof(double);   // kernel_tsit5_adjoint.cuh: ADJ_FIXED
+  const size_t block_fixed = sizeof(WideBlockLite) + (size_t)P.mlp_np * sizeof(double);
   // forward-record capacity in shared memory for `nb` blocks of 4 warps per SM (steps per warp; < 0: does not fit)
   auto cap_for = [&](int nb) -> long long {
-    const size_t budget = (size_t)(227 * 1024 / nb) - 2048 - sizeof(WideBlockLite);
+    const size_t budget = (size_t)(227 * 1024 / nb) - 2048 - block_fixed;
     if (fixed_pw * WARPS > budget) return -1;
     return (long long)std::min<size_t>(256, (budget / WARPS - fixed_pw) / (stride * sizeof(double)));
   };
   // large models (n_w towards 512) leave a four-block build no room for the record: they keep two blocks per SM
   const bool four_blocks = want_four && cap_for(4) >= 4;
-  const long long cap = cap_for(four_blocks ? 4 : 2);
+  // F4: the MLP state adds (3L + 2)*32 doubles per warp; three blocks (12 warps per SM) with a short record beat two with a long one
+  static const int f4_blocks_env = [] { const char* e = std::getenv("CRNN_B200_ADJ_F4_BLOCKS"); return e ? std::atoi(e) : 0; }();
+  const bool three_blocks = f4 && !four_blocks && f4_blocks_env != 2 && cap_for(3) >= 2;
+  const long long cap = cap_for(four_blocks ? 4 : three_blocks ? 3 : 2);
   if (cap < 1) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the adjoint kernel's shared memory");
-  auto kern = f4 ? (four_blocks ? k_tsit5_adjoint<WARPS, false, 4, true> : k_tsit5_adjoint<WARPS, false, 2, true>)
+  auto kern = f4 ? (four_blocks ? k_tsit5_adjoint<WARPS, false, 4, true> : three_blocks ? k_tsit5_adjoint<WARPS, false, 3, true>
+                                                                                        : k_tsit5_adjoint<WARPS, false, 2, true>)
               : four_blocks ? (f2 ? k_tsit5_adjoint<WARPS, true, 4> : k_tsit5_adjoint<WARPS, false, 4>)
                             : (f2 ? k_tsit5_adjoint<WARPS, true, 2> : k_tsit5_adjoint<WARPS, false, 2>);
   P.cap_s = (int)cap;
   P.cap_g = 512;
-  const size_t smem = sizeof(WideBlockLite) + WARPS * (fixed_pw + (size_t)P.cap_s * stride * sizeof(double));
+  const size_t smem = block_fixed + WARPS * (fixed_pw + (size_t)P.cap_s * stride * sizeof(double));
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));

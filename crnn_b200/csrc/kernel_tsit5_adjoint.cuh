@@ -46,7 +46,10 @@ struct AdjP {
   int cap_s, cap_g;        // record capacity (steps) in shared / global memory
   int nw, loss_kind;
   int discrete;            // 1: discrete adjoint (reverse-mode through the recorded steps), 0: interpolating adjoint
-  int mlp_extra;           // F4: doubles per warp for the MLP's activations / pre-activations / deltas ((3L + 2) * 32), else 0
+  int mlp_extra;           // F4: doubles per warp for the MLP's activations / activation derivatives / deltas (32 + (3L + 1) * mlp_stride), else 0
+  int mlp_stride;          // F4: slots per layer in those arrays (the widest layer, rounded up to even)
+  int mlp_np, mlp_np_raw;  // F4: number of MLP parameters, rounded up to even (a per-block shared-memory copy) and as is; else 0
+  int gs_len;              // length of the stage accumulator GS: (nw rounded up to even) for the interpolating adjoint, 0 for the discrete one
 };
 
 constexpr int ADJ_MAX_ENT = 16;  // quadrature entries per lane: n_w <= 512
@@ -67,23 +70,28 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   const int stride = 8 * n + 2;  // doubles per recorded step: t, dt, u, k1..k7
   WideBlockLite& sb = *reinterpret_cast<WideBlockLite*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] | GW[nw] GS[nw] | record[cap_s][stride]
-  // per-warp region: x[32] r[32] lam[32] gr[32] chi[32] sl[32] one[2] | GW[nw] GS[nw] | record[cap_s][stride]
+  // block: WideBlockLite | (F4: MLP parameters)    per warp: x[32] r[32] lam[32] gr[32] chi[32] sl[32] one[2] | (F4: MLP arrays) |
+  // GW[nw] | (interpolating: GS[nw]) | record[cap_s][stride]
   constexpr int ADJ_FIXED = 6 * 32 + 2;   // crnn_api.cu::loss_grad_adjoint sizes the launch with the same number
-  const size_t per_warp = ADJ_FIXED + (MLP ? P.mlp_extra : 0) + 2 * (size_t)((nw + 1) & ~1) + (size_t)P.cap_s * stride;
-  double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(WideBlockLite)) + per_warp * warp;
+  const size_t per_warp = ADJ_FIXED + (MLP ? P.mlp_extra : 0) + (size_t)((nw + 1) & ~1) + (size_t)P.gs_len + (size_t)P.cap_s * stride;
+  double* s_mw = reinterpret_cast<double*>(smem_raw + sizeof(WideBlockLite));   // F4: the block's copy of the MLP parameters
+  double* wbase = s_mw + (MLP ? P.mlp_np : 0) + per_warp * warp;
   double* s_x = wbase; double* s_r = wbase + 32; double* s_lam = wbase + 64; double* s_gr = wbase + 96;
   double* s_chi = wbase + 128;
   double* s_sl = wbase + 160;   // scale_i * lambda_i / rho: the left factor of the G_out outer product
-  // F4: v[32] (cotangents of the augmented input rows; also the state broadcast) | a_l[32], l = 0..L | s_l[32], l < L | delta_l[32], l < L
+  // F4: v[32] (cotangents of the augmented input rows; also the state broadcast) | a_l[ms], l = 0..L | act'_l[ms], l < L | delta_l[ms], l < L
+  // (ms = P.mlp_stride slots per layer)
   const int ML = MLP ? W.mlp_layers : 0;
+  const int ms = MLP ? P.mlp_stride : 0;
   double* s_v = wbase + ADJ_FIXED;
-  auto A_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * l; };
-  auto SP_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * (ML + 1 + l); };
-  auto DL_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + 32 * (2 * ML + 1 + l); };
+  auto A_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + ms * l; };
+  auto SP_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + ms * (ML + 1 + l); };
+  auto DL_ = [&](int l) -> double* { return wbase + ADJ_FIXED + 32 + ms * (2 * ML + 1 + l); };
   double* GW = wbase + ADJ_FIXED + (MLP ? P.mlp_extra : 0); double* GS = GW + ((nw + 1) & ~1);
   if (lane == 0) wbase[192] = 1.0;   // the unit left factor of the G_b entries
-  double* rec_s = GS + ((nw + 1) & ~1);
+  double* rec_s = GS + P.gs_len;
+  if (MLP)
+    for (int q = threadIdx.x; q < P.mlp_np; q += blockDim.x) s_mw[q] = q < P.mlp_np_raw ? W.mlp_params[q] : 0.0;
   double* rec_g = P.scratch + ((size_t)blockIdx.x * WARPS + warp) * (size_t)P.cap_g * stride;
 
   for (int q = threadIdx.x; q < KW_MAXN * KW_MAXN; q += blockDim.x) {
@@ -114,7 +122,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       int f = e - (nin * nr + nr + ns * nr + ns);
       for (int l = 0; l < ML; ++l) {
         const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
-        const int dl_off = ADJ_FIXED + 32 + 32 * (2 * ML + 1 + l), a_off = ADJ_FIXED + 32 + 32 * l;
+        const int dl_off = ADJ_FIXED + 32 + ms * (2 * ML + 1 + l), a_off = ADJ_FIXED + 32 + ms * l;
         if (f < din * dout) { code = ((dl_off + f % dout) << 16) | (a_off + f / dout); break; }
         f -= din * dout;
         if (f < dout) { code = ((dl_off + f) << 16) | 192; break; }
@@ -136,28 +144,35 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
     s_v[lane] = y;
     __syncwarp();
     double a = lane < W.mlp_dims[0] ? s_v[__ldg(W.mlp_in_idx + lane)] : 0.0;
-    const double* w = W.mlp_params;
+    const double* w = s_mw;
 #pragma unroll 1
     for (int l = 0; l < ML; ++l) {
       const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
-      A_(l)[lane] = a;
+      if (lane < din) A_(l)[lane] = a;
       __syncwarp();
       double sacc = 0.0;
       if (lane < dout) {
-        for (int i = 0; i < din; ++i) sacc = fma(__ldg(w + lane + dout * i), A_(l)[i], sacc);
-        sacc += __ldg(w + din * dout + lane);
-        SP_(l)[lane] = sacc;
+        const double* al = A_(l);
+        for (int i = 0; i < din; ++i) sacc = fma(w[lane + dout * i], al[i], sacc);
+        sacc += w[din * dout + lane];
+        // the activation and, for the way back, its derivative at the pre-activation (gelu' in NNlib's tanh form, softplus' = sigma, exp' = exp)
         if (l + 1 < ML) {
-          const double th = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (sacc + 0.044715 * (sacc * sacc * sacc)))) + 1.0);
-          sacc = 0.5 * sacc * (1.0 + th);
+          const double x = sacc;
+          const double th = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (x + 0.044715 * (x * x * x)))) + 1.0);
+          SP_(l)[lane] = 0.5 * (1.0 + th) + 0.5 * x * (1.0 - th * th) * (0.7978845608028654 * (1.0 + 3.0 * 0.044715 * (x * x)));
+          sacc = 0.5 * x * (1.0 + th);
+        } else if (W.mlp_act_out == 0) {
+          SP_(l)[lane] = 1.0 / (1.0 + lean_exp(-sacc));
+          sacc = lean_log(1.0 + lean_exp(-fabs(sacc))) + (sacc > 0.0 ? sacc : 0.0);
         } else {
-          sacc = W.mlp_act_out == 0 ? lean_log(1.0 + lean_exp(-fabs(sacc))) + (sacc > 0.0 ? sacc : 0.0) : lean_exp(sacc);
+          sacc = lean_exp(sacc);
+          SP_(l)[lane] = sacc;
         }
       }
       a = sacc;
       w += din * dout + dout;
     }
-    A_(ML)[lane] = a;
+    if (lane < W.mlp_dims[ML]) A_(ML)[lane] = a;
     __syncwarp();
     if (lane >= nin) return 0.0;
     const int src = __ldg(W.aug_src + lane);
@@ -396,32 +411,21 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
           if (src == lane) dl += s_v[q];
           if (-1 - src == lane) dh += s_v[q];
         }
-        if (lane < W.mlp_dims[ML]) {
-          const double sl = SP_(ML - 1)[lane];
-          const double da = W.mlp_act_out == 0 ? 1.0 / (1.0 + lean_exp(-sl)) : A_(ML)[lane];
-          DL_(ML - 1)[lane] = dh * da;
-        }
-        const double* wl = W.mlp_params;
-        int woff[8];
-        {
-          int off = 0;
-#pragma unroll 1
-          for (int l = 0; l < ML; ++l) { woff[l] = off; off += W.mlp_dims[l] * W.mlp_dims[l + 1] + W.mlp_dims[l + 1]; }
-        }
+        if (lane < W.mlp_dims[ML]) DL_(ML - 1)[lane] = dh * SP_(ML - 1)[lane];
+        int woff = P.mlp_np_raw;   // walks down the layers of the block's parameter copy
 #pragma unroll 1
         for (int l = ML - 1; l >= 0; --l) {
           const int din = W.mlp_dims[l], dout = W.mlp_dims[l + 1];
+          woff -= din * dout + dout;
           __syncwarp();
           double sacc = 0.0;
-          if (lane < din)
-            for (int k = 0; k < dout; ++k) sacc = fma(__ldg(wl + woff[l] + k + dout * lane), DL_(l)[k], sacc);
+          if (lane < din) {
+            const double* wl = s_mw + woff + dout * lane;
+            const double* dl_l = DL_(l);
+            for (int k = 0; k < dout; ++k) sacc = fma(wl[k], dl_l[k], sacc);
+          }
           if (l > 0) {
-            if (lane < din) {
-              const double x = SP_(l - 1)[lane];
-              const double T = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (x + 0.044715 * (x * x * x)))) + 1.0);
-              const double gd = 0.5 * (1.0 + T) + 0.5 * x * (1.0 - T * T) * (0.7978845608028654 * (1.0 + 3.0 * 0.044715 * (x * x)));
-              DL_(l - 1)[lane] = sacc * gd;
-            }
+            if (lane < din) DL_(l - 1)[lane] = sacc * SP_(l - 1)[lane];
           } else {
             __syncwarp();
             s_v[lane] = lane < din ? sacc : 0.0;   // d / d (MLP input i); s_v's cotangents have been consumed

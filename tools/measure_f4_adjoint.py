@@ -41,6 +41,8 @@ for mode, nm in ((_abi.SENS_DISCRETE_ADJOINT, "discrete"), (_abi.SENS_INTERP_ADJ
     o = cases.yeast_opts(alg=_abi.ALG_TSIT5, sens_mode=mode)
     ms, r = timed(lambda: eng.loss_grad_batch(m, o, seed, u0, data, ys, want_stats=False))
     out[f"yeast_grad_np294_{nm}_adjoint"] = {"N": N, "ms": ms, "traj_per_s": N / ms * 1e3, "loss": float(np.nanmean(r["loss"].cpu().numpy() if hasattr(r["loss"], "cpu") else r["loss"]))}
+    if "--no-oracle" in sys.argv:
+        continue
     n = 64
     t0 = time.perf_counter()
     oracle.loss_grad_batch(m, o, seed, u0h[:n], (data[:n].cpu().numpy() if hasattr(data, "cpu") else data[:n]), ys, n_threads=os.cpu_count())
