@@ -173,3 +173,33 @@ def test_config5_hychem_sized_kencarp4_share(engine):
     # (row ranges floored at 1e-4: most of the 29 species are traces; equal TOTAL counts do not imply the same path)
     assert r["state_max_err_same_counts"] < 5e-3 and r["state_max_err_rel_to_row_range"] < 0.5
     assert np.abs(got["pred"].sum(axis=2) - u0[:, :29].sum(axis=1)[:, None]).max() < 1e-6
+
+
+def test_f4_yeast_predict_and_gradient(engine, golden):
+    """Row f4 of the scope table at batch size: the reference's committed yeast model (MLP-augmented RHS) — 8 192 trajectories
+    through AutoTsit5(TRBDF2(autodiff=false)) as the script writes it, and loss + gradient of all 294 parameters for 4 096 of them by
+    the discrete adjoint, every trajectory against the oracle."""
+    p = np.array(golden["yeast"]["p"])
+    m, seed = cases.yeast_model(p), cases.yeast_seed(p)
+    N, M = 8192, 4096
+    g = np.random.default_rng(11)
+    u0 = cases.YEAST_IC_LB + g.random((N, 7)) * (cases.YEAST_IC_UB - cases.YEAST_IC_LB)
+    o = cases.yeast_opts()
+    got = engine.solve_batch(m, o, u0)
+    ref = oracle.solve_batch(m, o, u0, n_threads=CORES)
+    r = compare("f4_yeast_predict_auto_tsit5_trbdf2", got, ref)
+    # targets for the gradient: the model's own predictions from initial conditions 2 % off
+    data = engine.solve_batch(m, cases.yeast_opts(alg=_abi.ALG_TSIT5), u0[:M] * (1.0 + 0.02 * g.normal(size=(M, 7))))["pred"]
+    og = cases.yeast_opts(alg=_abi.ALG_TSIT5, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    gg = engine.loss_grad_batch(m, og, seed, u0[:M], data, np.ones(7), want_pred=True)
+    rg = oracle.loss_grad_batch(m, og, seed, u0[:M], data, np.ones(7), want_pred=True, n_threads=CORES)
+    r2 = compare("f4_yeast_gradient_np294_discrete_adjoint", gg, rg, keys=("n_accept", "n_reject"))
+    if REPORT_ONLY:
+        return
+    # the composite's stiff half takes a finite-difference Jacobian (the script's autodiff=false): its rounding noise reaches the
+    # accept tests of the few trajectories that switch; everything that stays on Tsit5 is count-exact
+    assert r["count_mismatches"] <= N // 100
+    assert r2["count_mismatches"] == 0
+    # a trained oscillator: a few trajectories amplify last-bit differences of the RHS to 5e-5 of the row range by t = 5
+    # (measured: worst loss 2.6e-5, gradient sum 2.0e-6); on most trajectories the agreement is 1e-10 (tests/test_f4_mlp_gpu.py)
+    assert r2["loss_max_rel"] < 1e-3 and r2["grad_rel_l2"] < 1e-4
