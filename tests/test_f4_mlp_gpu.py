@@ -116,10 +116,13 @@ def test_f4_gradient_of_the_qssa_shape(engine, mode):
     q = qssa_like_model()
     w = q.flat_weights()
     u0 = 0.2 + np.random.default_rng(3).random((64, 3))
-    o = SolveOpts(saveat=np.linspace(0.0, 2.0, 21), t0=0.0, t1=2.0, alg=_abi.ALG_TSIT5, abstol=1e-8, reltol=1e-6, maxiters=100000, sens_mode=mode)
+    # the script's loss looks at rows [1, 3] only (`loss_neuralode`, :150-155: mae over pred[[1, 3], :]): obs_idx = [0, 2]
+    o = SolveOpts(saveat=np.linspace(0.0, 2.0, 21), t0=0.0, t1=2.0, alg=_abi.ALG_TSIT5, abstol=1e-8, reltol=1e-6, maxiters=100000, sens_mode=mode,
+                  obs_idx=np.array([0, 2]))
     data = oracle.solve_batch(model_from_flat(q, w * (1.0 + 0.05 * np.random.default_rng(5).normal(size=w.size))), o, u0, n_threads=8)["pred"]
-    got = engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MAE_SCALED)
-    ref = oracle.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MAE_SCALED, n_threads=8)
+    assert data.shape == (64, 21, 2)
+    got = engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(2), _abi.LOSS_MAE_SCALED)
+    ref = oracle.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(2), _abi.LOSS_MAE_SCALED, n_threads=8)
     assert (got["retcode"] == _abi.RET_SUCCESS).all()
     for k in ("n_accept", "n_reject"):
         assert np.array_equal(got["stats"][k], ref["stats"][k])
@@ -129,7 +132,7 @@ def test_f4_gradient_of_the_qssa_shape(engine, mode):
     assert np.abs(got["grad_sum"] - ref["grad_sum"]).max() < tol * np.abs(ref["grad_sum"]).max()
     assert np.abs(got["grad_sum"][42:45]).max() > 0 and np.abs(got["grad_sum"][45:]).max() > 0    # w_J and MLP entries are live
     with pytest.raises(EngineError):        # the adjoints carry the MAE losses
-        engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MSE)
+        engine.loss_grad_batch(q, o, np.eye(w.size), u0, data, np.ones(2), _abi.LOSS_MSE)
 
 
 def test_f4_adjoint_record_capacity_is_reported(engine, golden):
@@ -180,3 +183,31 @@ def test_edge_cases_of_the_new_steppers_and_flavours(engine, golden):
         gh = engine.solve_batch(model, o, u0)
         gd = engine.solve_batch(model, o, torch.from_numpy(u0).cuda())
         assert np.array_equal(gd["pred"].cpu().numpy(), gh["pred"]) and np.array_equal(gd["retcode"].cpu().numpy(), gh["retcode"])
+
+
+def test_f4_gradient_edge_cases(engine, golden):
+    """the F4 gradient path with an empty batch, one trajectory, the script's random truncation (`batch = rand(batch_min:ntotal)`,
+    yeast_glycolysis.jl:245 -> n_save_used), device-resident buffers (same bits) and the dataset-indexed call of the training loop"""
+    import torch
+    p, u0, data, ys = _yeast_training_problem(golden, 24, seed=12)
+    m, seed = cases.yeast_model(p), cases.yeast_seed(p)
+    o = cases.yeast_opts(alg=_abi.ALG_TSIT5, n_save=60, sens_mode=_abi.SENS_DISCRETE_ADJOINT)
+    r0 = engine.loss_grad_batch(m, o, seed, u0[:0], data[:0], ys)
+    assert r0["loss"].shape == (0,) and r0["grad_sum"].shape == (294,) and not r0["grad_sum"].any()
+    g1 = engine.loss_grad_batch(m, o, seed, u0[:1], data[:1], ys); r1 = oracle.loss_grad_batch(m, o, seed, u0[:1], data[:1], ys)
+    assert np.linalg.norm(g1["grad_sum"] - r1["grad_sum"]) < 1e-6 * np.linalg.norm(r1["grad_sum"])
+    nsu = np.random.default_rng(2).integers(32, 61, size=24).astype(np.int32)
+    g = engine.loss_grad_batch(m, o, seed, u0, data, ys, n_save_used=nsu)
+    r = oracle.loss_grad_batch(m, o, seed, u0, data, ys, n_save_used=nsu, n_threads=8)
+    assert np.array_equal(g["n_saved"], nsu) and np.array_equal(g["stats"]["n_accept"], r["stats"]["n_accept"])
+    np.testing.assert_allclose(g["loss"], r["loss"], rtol=1e-6)
+    assert np.linalg.norm(g["grad_sum"] - r["grad_sum"]) < 1e-6 * np.linalg.norm(r["grad_sum"])
+    gd = engine.loss_grad_batch(m, o, seed, torch.from_numpy(u0).cuda(), torch.from_numpy(data).cuda(), ys, n_save_used=torch.from_numpy(nsu).cuda())
+    assert np.array_equal(gd["grad_sum"].cpu().numpy(), g["grad_sum"]) and np.array_equal(gd["loss"].cpu().numpy(), g["loss"])
+    ds = engine.dataset(u0, data)
+    idx = np.array([5, 3, 3, 17, 0])
+    gi = engine.loss_grad_indexed(m, o, seed, ds, ys, _abi.LOSS_MAE_SCALED, idx=idx, n_save_used=nsu[idx], want_loss=True)
+    gb = engine.loss_grad_batch(m, o, seed, u0[idx], data[idx], ys, n_save_used=nsu[idx])
+    np.testing.assert_allclose(gi["grad_sum"], gb["grad_sum"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gi["loss"], gb["loss"], rtol=1e-13)
+    ds.close()
