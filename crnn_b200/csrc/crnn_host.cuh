@@ -684,17 +684,21 @@ template <class C>
 int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const crnn_train_opts* t, const crnn_dataset* ds,
                const int64_t* order, int64_t n_steps, const double* yscale, int32_t loss_kind, double* p, double* opt_state,
                double* step_loss, double* step_gnorm) {
-  // device p2vec kernels: 2 = case2/case2.jl:91-99 (6 species, 3 reactions, F1), 1 = case1/case1.jl:70-78 (5 species, 4 reactions, F0)
-  constexpr int PK = (C::NS == 6 && C::NR == 3 && C::KIND == 1) ? 2 : ((C::NS == 5 && C::NR == 4 && C::KIND == 0) ? 1 : 0);
+  // device p2vec kernels: 2 = case2/case2.jl:91-99 (6 species, 3 reactions, F1), 1 = case1/case1.jl:70-78 (5 species, 4 reactions, F0),
+  // 3 = case3/case3.jl:42-53 (9 species, 8 reactions, F0 with out_scale; 153 parameters: five warps per trajectory)
+  constexpr int PK = (C::NS == 6 && C::NR == 3 && C::KIND == 1) ? 2 : ((C::NS == 5 && C::NR == 4 && C::KIND == 0) ? 1 :
+                     ((C::NS == 9 && C::NR == 8 && C::KIND == 0) ? 3 : 0));
   if constexpr (PK == 0) {
-    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has device p2vec kernels for case1 (5 x 4, F0) and case2 (6 x 3, F1)");
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has device p2vec kernels for case1 (5 x 4, F0), case2 (6 x 3, F1) and case3 (9 x 8, F0)");
   } else {
-    constexpr int NP = PK == 2 ? C::NR * (C::NS + 2) + 1 : C::NR * (C::NS + 1);   // 25 / 24
-    if (t->p2vec_kind != PK) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind does not match the model: 1 = case1.jl:70-78, 2 = case2.jl:91-99");
+    constexpr int NP = PK == 2 ? C::NR * (C::NS + 2) + 1 : (PK == 3 ? C::NR * (2 * C::NS + 1) + 1 : C::NR * (C::NS + 1));   // 25 / 153 / 24
+    constexpr int WPT = PK == 3 ? 5 : 1;                 // warps sharing a trajectory (np + 1 columns over 32-lane tiles)
+    constexpr int COLS = 32 * WPT;
+    if (t->p2vec_kind != PK) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind does not match the model: 1 = case1.jl:70-78, 2 = case2.jl:91-99, 3 = case3.jl:42-53");
     if (o->alg != CRNN_ALG_TSIT5 || o->sens_mode != CRNN_SENS_FORWARD)
       return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop runs Tsit5 with forward sensitivities");
     if (t->batch < 1 || n_steps < 0) return fail(h, CRNN_ERR_BAD_ARG, "bad batch / n_steps");
-    if (m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case1 / case2 have no out_scale");
+    if (PK != 3 && m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case1 / case2 have no out_scale");
     const int batch = t->batch;
     for (int64_t q = 0; q < n_steps * batch; ++q)
       if (order[q] < 0 || order[q] >= ds->N) return fail(h, CRNN_ERR_BAD_ARG, "order: dataset row index out of range");
@@ -711,10 +715,10 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     CK(cudaSetDevice(h->device));
     rc = upload_cfg<C>(h, o, pk, sp, st);
     if (rc) return rc;
-    // device block: p[NP] | state[2NP+4] | ModelP | rows[2*NR*32] | desc[32] | loss_sum[2] | grad_sum[NP] | order | step_loss | step_gnorm
-    const size_t n_mp = (sizeof(ModelP<C>) + 7) / 8, n_rows = 2 * C::NR * 32, n_desc = 3 * 32;
+    // device block: p[NP] | state[2NP+4] | ModelP | rows[2*NR*COLS] | desc[COLS] | loss_sum[2] | grad_sum[NP] | order | step_loss | step_gnorm | out_scale[NS]
+    const size_t n_mp = (sizeof(ModelP<C>) + 7) / 8, n_rows = 2 * C::NR * COLS, n_desc = 3 * COLS;
     const size_t n_order = (size_t)n_steps * batch;
-    const size_t total = NP + (2 * NP + 4) + n_mp + n_rows + n_desc + 2 + NP + n_order + 2 * (size_t)n_steps + 8;
+    const size_t total = NP + (2 * NP + 4) + n_mp + n_rows + n_desc + 2 + NP + n_order + 2 * (size_t)n_steps + 8 + C::NS;
     CK(h->train.reserve(total * sizeof(double)));
     double* d_p = h->train.as<double>(); double* d_st = d_p + NP;
     ModelP<C>* d_mp = reinterpret_cast<ModelP<C>*>(d_st + 2 * NP + 4);
@@ -722,6 +726,8 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     double* d_lsum = d_rows + n_rows + n_desc; double* d_gsum = d_lsum + 2;
     long long* d_order = reinterpret_cast<long long*>(d_gsum + NP);
     double* d_sloss = reinterpret_cast<double*>(d_order + n_order); double* d_sgn = d_sloss + n_steps;
+    double* d_oscale = d_sgn + n_steps;
+    if (m->out_scale) CK(cudaMemcpyAsync(d_oscale, m->out_scale, C::NS * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_p, p, NP * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_st, opt_state, (2 * NP + 4) * sizeof(double), cudaMemcpyHostToDevice, st));
     if (n_order) CK(cudaMemcpyAsync(d_order, order, n_order * sizeof(long long), cudaMemcpyHostToDevice, st));
@@ -734,16 +740,20 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     T.optimiser = t->optimiser; T.np = NP; T.eta = t->eta; T.beta1 = t->beta1; T.beta2 = t->beta2; T.eps = t->eps;
     T.weight_decay = t->weight_decay; T.expdecay_decay = t->expdecay_decay; T.expdecay_clip = t->expdecay_clip;
     T.expdecay_step = t->expdecay_eta > 0 ? t->expdecay_step : 0; T.grad_max = t->grad_max;
-    constexpr int WARPS = 8;
-    auto kern = k_tsit5_sens<C, 1, WARPS, 2, true, 1, false, true>;
-    const size_t smem = sizeof(SensSmem<C, 1, true, 1>) + WARPS * sizeof(WarpBuf<C, 1>);
+    // one warp per trajectory, eight per block - or, for case3, two groups of five warps per block (launch_sens' shapes)
+    constexpr int WARPS = WPT == 1 ? 8 : 2 * WPT;
+    constexpr int GROUPS = WARPS / WPT;
+    auto kern = k_tsit5_sens<C, 1, WARPS, (WPT == 1 ? 2 : 1), true, WPT, false, true>;
+    const size_t smem = sizeof(SensSmem<C, 1, true, WPT>) + WARPS * sizeof(WarpBuf<C, 1>);
+    if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)std::min<long long>(2LL * h->num_sms, (batch + WARPS - 1) / WARPS);
+    const unsigned blocks = (unsigned)std::min<long long>((WPT == 1 ? 2LL : 1LL) * h->num_sms, (batch + GROUPS - 1) / GROUPS);
     unsigned long long* queue = h->ctr.as<unsigned long long>();
     const int nb_red = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (batch + 63) / 64));
     CK(h->partial.reserve((size_t)nb_red * NP * sizeof(double)));
     for (int64_t s = 0; s < n_steps; ++s) {
       if constexpr (PK == 2) k_p2vec_case2<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->gas_R, d_mp, d_rows, d_desc);
+      else if constexpr (PK == 3) k_p2vec_case3<C, COLS><<<1, 128, 0, st>>>(d_p, m->lb, m->ub, m->out_scale ? d_oscale : nullptr, d_mp, d_rows, d_desc);
       else k_p2vec_case1<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, t->p2vec_b0, d_mp, d_rows, d_desc);
       CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
       kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nullptr, batch,

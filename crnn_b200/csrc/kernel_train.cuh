@@ -94,6 +94,39 @@ __global__ void k_p2vec_case1(const double* __restrict__ p, double lb, double ub
   }
 }
 
+// p2vec of case3/case3.jl:42-53 (9 species, 8 reactions, np = 153; five warps share a trajectory: COLS = 160 seed columns):
+//   w_b = p[1:nr];  w_in_raw = reshape(p[nr(ns+1)+1 : nr(2ns+1)], ns, nr);  w_out = -w_in_raw .* abs(reshape(p[nr+1 : nr(ns+1)], ns, nr));
+//   w_in = clamp(w_in_raw, 0, 4);  p[end] is not used by the weights.  out_scale (dy_std of the RHS, case3.jl:165) is folded into
+//   w_out and into the seed entries as pack<C>() / plan_r1 do on the host path.
+template <class C, int COLS>
+__global__ void k_p2vec_case3(const double* __restrict__ p, double lb, double ub, const double* __restrict__ oscale,
+                              ModelP<C>* __restrict__ mp, double* __restrict__ rows /* [2*NR][COLS] */, R1Desc* __restrict__ desc /* [COLS] */) {
+  constexpr int NS = C::NS, NR = C::NR, NIN = C::NIN;
+  static_assert(C::KIND == 0 && NIN == NS && 2 + NR * (2 * NS + 1) <= COLS, "an F0 model whose columns fit");
+  const int t = threadIdx.x;
+  for (int q = t; q < 2 * NR * COLS; q += blockDim.x) rows[q] = 0.0;
+  for (int q = t; q < COLS; q += blockDim.x) { R1Desc d{}; d.o = 0.0; d.i_in = 0; d.i_out = 0; d.j_out = 0; d.pad = 0; desc[q] = d; }
+  __syncthreads();
+  if (t == 0) { mp->lb = lb; mp->ub = ub; mp->gas_R = 0.0; }
+  if (t < NR) {
+    mp->w_b[t] = p[t];
+    rows[(NR + t) * COLS + (1 + t)] = 1.0;
+  }
+  if (t < NS * NR) {
+    const int i = t % NS, j = t / NS;
+    const double os = oscale ? oscale[i] : 1.0;
+    const double a = p[NR * (NS + 1) + i + NS * j], b = p[NR + i + NS * j];   // w_in_raw, w_out_raw
+    const double sg = signbit(b) ? -1.0 : 1.0, ab = b * sg;                    // abs(dual): sign from signbit
+    mp->w_out[i + NS * j] = ((-a) * ab) * os;
+    mp->w_in[i + NIN * j] = a > 4.0 ? 4.0 : (a < 0.0 ? 0.0 : a);
+    const int c_out = 1 + NR + i + NS * j, c_in = 1 + NR * (NS + 1) + i + NS * j;
+    R1Desc d{}; d.pad = 0; d.i_in = i; d.i_out = i; d.j_out = j;
+    d.o = ((-a) * sg) * os;  desc[c_out] = d;                                  // d w_out[i,j] / d w_out_raw[i,j]; no w_in row
+    d.o = (-ab) * os;        desc[c_in] = d;                                   // d w_out[i,j] / d w_in_raw[i,j]
+    rows[j * COLS + c_in] = (a >= 0.0 && a <= 4.0) ? 1.0 : 0.0;                // clamp(dual): derivative 1 on the closed interval
+  }
+}
+
 // [sum of the finite losses, number of them] of one step's experiments (fixed order: deterministic)
 static __global__ void __launch_bounds__(256) k_train_loss_sum(const double* __restrict__ loss, int n, double* __restrict__ out) {
   __shared__ double s_sum[256], s_cnt[256];

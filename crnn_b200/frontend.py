@@ -112,7 +112,7 @@ class CRNNProblem:
         model, _ = self.case.model(p, self.out_scale)
         state, history = None, []
         n_steps = n_exp_train // batch
-        optimiser.setdefault("p2vec_kind", {"case1": 1, "case2": 2}.get(self.case.name, 0))   # the device p2vec kernels built
+        optimiser.setdefault("p2vec_kind", {"case1": 1, "case2": 2, "case3": 3}.get(self.case.name, 0))   # the device p2vec kernels built
         for epoch in range(n_epoch):
             order = rng.permutation(n_exp_train)[:n_steps * batch]
             r = self.engine.train_steps(model, self.opts, self.dataset, order, self.yscale, p, state, self.case.loss_kind,

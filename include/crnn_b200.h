@@ -293,7 +293,8 @@ int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts*
  * (rober_crnn.jl:220-223) are enqueued back to back.  The host supplies the visiting order (its own randperm).
  * --------------------------------------------------------------------------------------------- */
 typedef struct crnn_train_opts {
-  int32_t p2vec_kind;   /* which script's p2vec runs on the device: 1 = case1/case1.jl:70-78, 2 = case2/case2.jl:91-99 */
+  int32_t p2vec_kind;   /* which script's p2vec runs on the device: 1 = case1/case1.jl:70-78, 2 = case2/case2.jl:91-99,
+                           3 = case3/case3.jl:42-53 (model.out_scale = dy_std is folded in on the device) */
   int32_t optimiser;    /* 0 ADAM (+ weight_decay = ADAMW), 1 NADAM */
   int32_t batch;        /* experiments per optimiser step (the scripts: 1) */
   int32_t reserved;

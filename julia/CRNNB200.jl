@@ -231,7 +231,7 @@ end
 The epoch loop `for i_exp in randperm(n_exp_train); grad = ForwardDiff.gradient(...); update!(opt, p, grad); end`
 (case2/case2.jl:192-198) with every optimiser step ON the device: `order` is the 1-based visiting order (the script's own
 `randperm`), `p` and `opt_state` (2np + 4: ADAM m, v, beta powers, ExpDecay eta and count) are updated in place.  The
-device runs the script's p2vec itself (`p2vec_kind` 2: case2.jl:91-99, 1: case1.jl:70-78), so no weights are passed.
+device runs the script's p2vec itself (`p2vec_kind` 2: case2.jl:91-99, 1: case1.jl:70-78, 3: case3.jl:42-53 with `s.out_scale = dy_std`), so no weights are passed.
 """
 function train_steps!(e::Engine, s::Setup, ds::Dataset, order, p::Vector{Float64}, opt_state::Vector{Float64};
                       ns::Integer, nr::Integer, batch::Integer=1, optimiser::Integer=0, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,

@@ -6,7 +6,7 @@ show the same descent and move the Arrhenius parameters towards the generating m
 import numpy as np
 import pytest
 
-from crnn_b200 import cases, optim, synth
+from crnn_b200 import _abi, cases, optim, synth
 from crnn_b200.frontend import CRNNProblem
 
 pytestmark = pytest.mark.gpu
@@ -142,12 +142,50 @@ def test_on_device_loop_case1_p2vec(engine, golden):
     from crnn_b200.engine import EngineError
     with pytest.raises(EngineError):
         engine.train_steps(model, prob.opts, prob.dataset, order[:2], prob.yscale, p, None, prob.case.loss_kind, p2vec_kind=2)
-    pb3 = make_problem("case3", golden, 4)
-    prob3 = CRNNProblem("case3", pb3["u0"], np.abs(pb3["data"]) + 1e-6, pb3["yscale"], engine=engine)
+    pbr = make_problem("robertson", golden, 4)                                 # no device p2vec for the robertson script
+    probr = CRNNProblem("robertson", pbr["u0"], pbr["data"], pbr["yscale"], engine=engine, alg=_abi.ALG_TSIT5)
     with pytest.raises(EngineError):
-        engine.train_steps(pb3["model"], prob3.opts, prob3.dataset, np.arange(2), prob3.yscale, np.zeros(153), None, prob3.case.loss_kind)
+        engine.train_steps(pbr["model"], probr.opts, probr.dataset, np.arange(2), probr.yscale, np.zeros(43), None, probr.case.loss_kind)
     with pytest.raises(EngineError):                                           # dataset row out of range
         engine.train_steps(model, prob.opts, prob.dataset, np.array([99]), prob.yscale, p, None, prob.case.loss_kind, **kw)
+
+
+def test_on_device_loop_case3_p2vec(engine, golden):
+    """p2vec_kind = 3: case3/case3.jl:42-53 on the device (w_out = -w_in .* |w_out_raw|, w_in = clamp(w_in, 0, 4), dy_std folded in),
+    153 parameters = five warps per trajectory in the forward-sensitivity kernel reading its weights and seed columns from device
+    memory, log-MAE loss, NADAM(0.001) as in case3.jl:20; every step against the host mirror from the same (p, state)"""
+    from problems import make_problem, trained_p
+    pb = make_problem("case3", golden, 10)
+    prob = CRNNProblem("case3", pb["u0"], np.abs(pb["data"]) + 1e-6, pb["yscale"], out_scale=pb["model"].out_scale, engine=engine)
+    g = np.random.default_rng(5)
+    p = trained_p("case3", golden)                                         # the script's Xavier initialisation (case3.jl:35-36)
+    assert p.size == 153 and prob.opts.sens_mode == _abi.SENS_FORWARD
+    opt = optim.Optimiser(optim.NADAM(0.001, (0.9, 0.999)))
+    kw = dict(p2vec_kind=3, optimiser="nadam", eta=0.001, beta=(0.9, 0.999))
+    model, _ = prob.case.model(p, prob.out_scale)
+    st = None
+    order = np.concatenate([g.permutation(10) for _ in range(2)])
+    for s in range(16):
+        idx = order[s:s + 1]
+        loss, grad = prob.loss_grad(p, idx)
+        p_host = p.copy(); opt.update(p_host, grad)
+        r = engine.train_steps(model, prob.opts, prob.dataset, idx, prob.yscale, p, st, prob.case.loss_kind, **kw)
+        np.testing.assert_allclose(r["step_loss"][0], loss, rtol=1e-13)
+        np.testing.assert_allclose(r["step_gnorm"][0], np.linalg.norm(grad), rtol=1e-11)
+        np.testing.assert_allclose(r["p"], p_host, rtol=1e-11, atol=1e-14, err_msg=f"step {s}")
+        p, st = r["p"], r["opt_state"]
+        nadam = opt.chain[0]
+        nadam.m, nadam.v = st[:153].copy(), st[153:306].copy()
+    # a mini-batch of four, two optimiser steps in one call = the same steps taken one call at a time
+    r_a = engine.train_steps(model, prob.opts, prob.dataset, order[:8], prob.yscale, p, st, prob.case.loss_kind, batch=4, **kw)
+    r_1 = engine.train_steps(model, prob.opts, prob.dataset, order[:4], prob.yscale, p, st, prob.case.loss_kind, batch=4, **kw)
+    r_2 = engine.train_steps(model, prob.opts, prob.dataset, order[4:8], prob.yscale, r_1["p"], r_1["opt_state"], prob.case.loss_kind, batch=4, **kw)
+    assert np.array_equal(r_a["p"], r_2["p"]) and np.array_equal(r_a["opt_state"], r_2["opt_state"])
+    l4, g4 = prob.loss_grad(p, order[:4])
+    np.testing.assert_allclose(r_1["step_loss"][0], l4, rtol=1e-12)
+    # and the frontend's epoch loop picks the kernel by the case name
+    p_end, hist = prob.train_on_device(p, n_epoch=2, n_exp_train=8, rng=g, optimiser="nadam", eta=0.001)
+    assert np.isfinite([h[0] for h in hist]).all() and p_end.shape == (153,)
 
 
 def test_on_device_epochs_descend(engine):

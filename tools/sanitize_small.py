@@ -83,5 +83,11 @@ ds = eng.dataset(pb["u0"], pb["data"])
 eng.train_steps(pb["model"], pb["opts"], ds, np.arange(20)[::-1].copy(), pb["yscale"], np.array(golden["case2"]["p"]), None, pb["loss_kind"],
                 batch=2, eta=5e-3, weight_decay=1e-6, expdecay=(5e-3, 0.5, 3, 1e-4), grad_max=0.5)
 ds.close(); done.append("train_steps")
+pb3 = make_problem("case3", golden, 6)
+ds3 = eng.dataset(pb3["u0"], np.abs(pb3["data"]) + 1e-6)
+from problems import trained_p
+eng.train_steps(pb3["model"], pb3["opts"], ds3, np.arange(6), pb3["yscale"], trained_p("case3", golden), None, pb3["loss_kind"],
+                p2vec_kind=3, optimiser="nadam", batch=2)
+ds3.close(); done.append("train_steps case3 (five warps per trajectory)")
 eng.close()
 print("sanitize_small ok:", "; ".join(done))
