@@ -308,7 +308,7 @@ typedef struct crnn_train_opts {
 
 /* n_steps optimiser steps; step s uses dataset rows order[s*batch .. (s+1)*batch).  Single-device handle, Tsit5 +
  * forward sensitivities.
- *   m          dimensions, clamps and gas_R of the model (weight pointers ignored: the device p2vec produces them)
+ *   m          dimensions, clamps, gas_R and out_scale of the model (weight pointers ignored: the device p2vec produces them)
  *   p          [np] in/out
  *   opt_state  [2*np + 4] in/out: ADAM m, v, beta1^t, beta2^t, ExpDecay's current eta and count
  *              (a fresh run: zeros, beta1, beta2, expdecay_eta, 0)
