@@ -651,3 +651,24 @@ def mlp_reference(dims, params, x, act_out=0):
         else:
             a = np.log1p(np.exp(-np.abs(s))) + np.maximum(s, 0.0) if act_out == 0 else np.exp(s)
     return a
+
+
+def mlp_rows_postmap(model, pred, obs_idx=None):
+    """`pred[2:2, :] .= rep(pred[[1, 3], :])` of rober_crnn_qssa.jl:139 (and the hidden-species read-out `rep(pred)` of
+    yeast_glycolysis.jl:170-171): the Flux chain evaluated on the saved states of an F4 model, host side.
+    pred [N, n_save, n_obs] with all state rows observed (or `obs_idx` naming them) -> (mlp_out [N, n_save, n_mlp_out], pred with
+    every state row that `aug_src` feeds from the MLP at the SAME position replaced by that output — the QSSA convention)."""
+    pred = np.asarray(pred, dtype=np.float64)
+    obs = np.arange(model.n_state) if obs_idx is None else np.asarray(obs_idx)
+    col = {int(r): k for k, r in enumerate(obs)}
+    if any(int(r) not in col for r in model.mlp_in_idx):
+        raise ValueError("the MLP's input rows must be among the observed rows")
+    x = pred[..., [col[int(r)] for r in model.mlp_in_idx]]
+    flat = x.reshape(-1, x.shape[-1])
+    out = np.array([mlp_reference(tuple(int(d) for d in model.mlp_dims), model.mlp_params, v, model.mlp_act_out) for v in flat])
+    out = out.reshape(pred.shape[:-1] + (out.shape[-1],))
+    mapped = pred.copy()
+    for q, src in enumerate(model.aug_src):      # input row q of the CRNN sits at state position q when n_in == n_state (QSSA)
+        if src < 0 and model.n_in == model.n_state and q in col:
+            mapped[..., col[q]] = out[..., -1 - int(src)]
+    return out, mapped

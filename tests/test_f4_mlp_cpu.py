@@ -146,3 +146,21 @@ def test_f4_adjoint_gradients_in_the_oracle(golden):
     with pytest.raises(RuntimeError):      # the adjoints carry the MAE losses
         oracle.loss_grad_batch(q, so(sens_mode=_abi.SENS_INTERP_ADJOINT), np.eye(w.size), u0, data, np.ones(3), _abi.LOSS_MSE)
     assert np.abs(gd[42:45]).max() > 0 and np.abs(gd[45:]).max() > 0
+
+
+def test_mlp_rows_postmap_is_the_qssa_scripts_line(golden):
+    """rober_crnn_qssa.jl:139 `pred[2:2, :] .= rep(pred[[1, 3], :])` and the yeast script's hidden-species read-out, host side"""
+    q = qssa_like_model()
+    pred = 0.2 + np.random.default_rng(0).random((3, 5, 3))
+    out, mapped = cases.mlp_rows_postmap(q, pred)
+    assert out.shape == (3, 5, 1) and np.array_equal(mapped[..., [0, 2]], pred[..., [0, 2]])
+    for n in range(3):
+        for k in range(5):
+            want = cases.mlp_reference((2, 4, 4, 4, 1), q.mlp_params, pred[n, k, [0, 2]], act_out=1)
+            assert mapped[n, k, 1] == want[0] == out[n, k, 0]
+    m = cases.yeast_model(np.array(golden["yeast"]["p"]))
+    pr = 0.5 + np.random.default_rng(1).random((2, 4, 7))
+    hidden, same = cases.mlp_rows_postmap(m, pr)
+    assert hidden.shape == (2, 4, 5) and np.array_equal(same, pr)       # yeast: the MLP rows are extra inputs, no state row is replaced
+    with pytest.raises(ValueError):
+        cases.mlp_rows_postmap(q, pred[..., :2], obs_idx=[0, 1])          # the chain reads rows 0 and 2
