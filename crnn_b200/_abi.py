@@ -62,6 +62,7 @@ class CTrainOpts(C.Structure):
         ("eta", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
         ("expdecay_eta", C.c_double), ("expdecay_decay", C.c_double), ("expdecay_clip", C.c_double),
         ("expdecay_step", C.c_int64), ("grad_max", C.c_double), ("p2vec_b0", C.c_double),
+        ("n_save_used", C.c_void_p),
     ]
 
 

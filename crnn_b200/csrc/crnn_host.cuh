@@ -399,7 +399,8 @@ int launch_ros_sens(crnn_handle* h, const ModelP<C>& mp, const SolveP<C>& sp, in
     CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     ProfScope prof(h, st);
     kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, h->seed.as<double>(), h->desc.as<R1Desc>(), ncol, b.u0, b.nsu, b.n,
-                                        b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx);
+                                        b.data, b.loss, b.grad_each, b.pred, b.n_saved, b.retcode, b.stats, queue, b.in_idx,
+                                        nullptr);
     CK(cudaGetLastError());
     h->launches++;
     return CRNN_OK;
@@ -685,20 +686,26 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
                const int64_t* order, int64_t n_steps, const double* yscale, int32_t loss_kind, double* p, double* opt_state,
                double* step_loss, double* step_gnorm) {
   // device p2vec kernels: 2 = case2/case2.jl:91-99 (6 species, 3 reactions, F1), 1 = case1/case1.jl:70-78 (5 species, 4 reactions, F0),
-  // 3 = case3/case3.jl:42-53 (9 species, 8 reactions, F0 with out_scale; 153 parameters: five warps per trajectory)
+  // 3 = case3/case3.jl:42-53 (9 species, 8 reactions, F0 with out_scale; 153 parameters: five warps per trajectory),
+  // 4 = robertson/rober_crnn.jl:85-96 (3 species, 6 reactions, F0 with out_scale; 43 parameters: Rosenbrock23 sensitivities, two column tiles)
   constexpr int PK = (C::NS == 6 && C::NR == 3 && C::KIND == 1) ? 2 : ((C::NS == 5 && C::NR == 4 && C::KIND == 0) ? 1 :
-                     ((C::NS == 9 && C::NR == 8 && C::KIND == 0) ? 3 : 0));
+                     ((C::NS == 9 && C::NR == 8 && C::KIND == 0) ? 3 : ((C::NS == 3 && C::NR == 6 && C::KIND == 0) ? 4 : 0)));
   if constexpr (PK == 0) {
-    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has device p2vec kernels for case1 (5 x 4, F0), case2 (6 x 3, F1) and case3 (9 x 8, F0)");
+    return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop has device p2vec kernels for case1 (5 x 4, F0), case2 (6 x 3, F1), case3 (9 x 8, F0) and robertson (3 x 6, F0)");
   } else {
-    constexpr int NP = PK == 2 ? C::NR * (C::NS + 2) + 1 : (PK == 3 ? C::NR * (2 * C::NS + 1) + 1 : C::NR * (C::NS + 1));   // 25 / 153 / 24
+    constexpr int NP = PK == 2 ? C::NR * (C::NS + 2) + 1 : (PK >= 3 ? C::NR * (2 * C::NS + 1) + 1 : C::NR * (C::NS + 1));   // 25 / 153, 43 / 24
+    constexpr bool ROS = (PK == 4);                      // the robertson script integrates with Rosenbrock23 (rober_crnn.jl:33)
     constexpr int WPT = PK == 3 ? 5 : 1;                 // warps sharing a trajectory (np + 1 columns over 32-lane tiles)
-    constexpr int COLS = 32 * WPT;
-    if (t->p2vec_kind != PK) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind does not match the model: 1 = case1.jl:70-78, 2 = case2.jl:91-99, 3 = case3.jl:42-53");
-    if (o->alg != CRNN_ALG_TSIT5 || o->sens_mode != CRNN_SENS_FORWARD)
-      return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop runs Tsit5 with forward sensitivities");
+    constexpr int CT = ROS ? 2 : 1;                      // column tiles per lane
+    constexpr int COLS = 32 * WPT * CT;
+    if (t->p2vec_kind != PK) return fail(h, CRNN_ERR_UNSUPPORTED, "p2vec_kind does not match the model: 1 = case1.jl:70-78, 2 = case2.jl:91-99, 3 = case3.jl:42-53, 4 = rober_crnn.jl:85-96");
+    if (o->alg != (ROS ? CRNN_ALG_ROSENBROCK23 : CRNN_ALG_TSIT5) || o->sens_mode != CRNN_SENS_FORWARD)
+      return fail(h, CRNN_ERR_UNSUPPORTED, "the on-device training loop runs forward sensitivities through Tsit5 (case1 / case2 / case3) or Rosenbrock23 (robertson)");
     if (t->batch < 1 || n_steps < 0) return fail(h, CRNN_ERR_BAD_ARG, "bad batch / n_steps");
-    if (PK != 3 && m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case1 / case2 have no out_scale");
+    if (PK < 3 && m->out_scale) return fail(h, CRNN_ERR_UNSUPPORTED, "case1 / case2 have no out_scale");
+    if (t->n_save_used)
+      for (int64_t q = 0; q < n_steps * t->batch; ++q)
+        if (t->n_save_used[q] < 1 || t->n_save_used[q] > o->n_save) return fail(h, CRNN_ERR_BAD_ARG, "n_save_used: 1 .. n_save");
     const int batch = t->batch;
     for (int64_t q = 0; q < n_steps * batch; ++q)
       if (order[q] < 0 || order[q] >= ds->N) return fail(h, CRNN_ERR_BAD_ARG, "order: dataset row index out of range");
@@ -718,7 +725,7 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     // device block: p[NP] | state[2NP+4] | ModelP | rows[2*NR*COLS] | desc[COLS] | loss_sum[2] | grad_sum[NP] | order | step_loss | step_gnorm | out_scale[NS]
     const size_t n_mp = (sizeof(ModelP<C>) + 7) / 8, n_rows = 2 * C::NR * COLS, n_desc = 3 * COLS;
     const size_t n_order = (size_t)n_steps * batch;
-    const size_t total = NP + (2 * NP + 4) + n_mp + n_rows + n_desc + 2 + NP + n_order + 2 * (size_t)n_steps + 8 + C::NS;
+    const size_t total = NP + (2 * NP + 4) + n_mp + n_rows + n_desc + 2 + NP + n_order + 2 * (size_t)n_steps + 8 + C::NS + (n_order + 1) / 2;
     CK(h->train.reserve(total * sizeof(double)));
     double* d_p = h->train.as<double>(); double* d_st = d_p + NP;
     ModelP<C>* d_mp = reinterpret_cast<ModelP<C>*>(d_st + 2 * NP + 4);
@@ -728,6 +735,8 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     double* d_sloss = reinterpret_cast<double*>(d_order + n_order); double* d_sgn = d_sloss + n_steps;
     double* d_oscale = d_sgn + n_steps;
     if (m->out_scale) CK(cudaMemcpyAsync(d_oscale, m->out_scale, C::NS * sizeof(double), cudaMemcpyHostToDevice, st));
+    int* d_nsu = reinterpret_cast<int*>(d_oscale + C::NS);    // per visited experiment: save points used (or none)
+    if (t->n_save_used && n_order) CK(cudaMemcpyAsync(d_nsu, t->n_save_used, n_order * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_p, p, NP * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_st, opt_state, (2 * NP + 4) * sizeof(double), cudaMemcpyHostToDevice, st));
     if (n_order) CK(cudaMemcpyAsync(d_order, order, n_order * sizeof(long long), cudaMemcpyHostToDevice, st));
@@ -740,13 +749,19 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     T.optimiser = t->optimiser; T.np = NP; T.eta = t->eta; T.beta1 = t->beta1; T.beta2 = t->beta2; T.eps = t->eps;
     T.weight_decay = t->weight_decay; T.expdecay_decay = t->expdecay_decay; T.expdecay_clip = t->expdecay_clip;
     T.expdecay_step = t->expdecay_eta > 0 ? t->expdecay_step : 0; T.grad_max = t->grad_max;
-    // one warp per trajectory, eight per block - or, for case3, two groups of five warps per block (launch_sens' shapes)
-    constexpr int WARPS = WPT == 1 ? 8 : 2 * WPT;
+    // one warp per trajectory, eight per block - or, for case3, two groups of five warps per block; robertson: the
+    // Rosenbrock23 kernel's four warps (launch_sens' / launch_ros_sens' shapes)
+    constexpr int WARPS = ROS ? 4 : (WPT == 1 ? 8 : 2 * WPT);
     constexpr int GROUPS = WARPS / WPT;
-    auto kern = k_tsit5_sens<C, 1, WARPS, (WPT == 1 ? 2 : 1), true, WPT, false, true>;
-    const size_t smem = sizeof(SensSmem<C, 1, true, WPT>) + WARPS * sizeof(WarpBuf<C, 1>);
-    if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = 0;
+    if constexpr (ROS) {
+      smem = sizeof(SensSmem<C, CT, true>) + WARPS * sizeof(RosWarpBuf<C, CT>);
+      CK(cudaFuncSetAttribute(k_rosenbrock23_sens<C, CT, WARPS, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      smem = sizeof(SensSmem<C, 1, true, WPT>) + WARPS * sizeof(WarpBuf<C, 1>);
+      if (smem > 227 * 1024) return fail(h, CRNN_ERR_UNSUPPORTED, "model too large for the forward-sensitivity kernel's shared memory");
+      CK(cudaFuncSetAttribute(k_tsit5_sens<C, 1, WARPS, (WPT == 1 ? 2 : 1), true, WPT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const unsigned blocks = (unsigned)std::min<long long>((WPT == 1 ? 2LL : 1LL) * h->num_sms, (batch + GROUPS - 1) / GROUPS);
     unsigned long long* queue = h->ctr.as<unsigned long long>();
     const int nb_red = (int)std::max<long long>(1, std::min<long long>(4LL * h->num_sms, (batch + 63) / 64));
@@ -754,12 +769,19 @@ int train_impl(crnn_handle* h, const crnn_model* m, const crnn_opts* o, const cr
     for (int64_t s = 0; s < n_steps; ++s) {
       if constexpr (PK == 2) k_p2vec_case2<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->gas_R, d_mp, d_rows, d_desc);
       else if constexpr (PK == 3) k_p2vec_case3<C, COLS><<<1, 128, 0, st>>>(d_p, m->lb, m->ub, m->out_scale ? d_oscale : nullptr, d_mp, d_rows, d_desc);
+      else if constexpr (PK == 4) k_p2vec_robertson<C, COLS><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, m->out_scale ? d_oscale : nullptr, d_mp, d_rows, d_desc);
       else k_p2vec_case1<C><<<1, 64, 0, st>>>(d_p, m->lb, m->ub, t->p2vec_b0, d_mp, d_rows, d_desc);
       CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
-      kern<<<blocks, WARPS * 32, smem, st>>>(mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nullptr, batch,
-                                          ds->data[0].as<double>(), h->d_loss.as<double>(), h->d_grad_each.as<double>(), nullptr,
-                                          h->d_nsaved.as<int>(), h->d_ret.as<int>(), nullptr, queue, d_order + s * batch,
-                                          nullptr, nullptr, d_mp);
+      const int* nsu = t->n_save_used ? d_nsu + s * batch : nullptr;
+      if constexpr (ROS)
+        k_rosenbrock23_sens<C, CT, WARPS, 3, true><<<blocks, WARPS * 32, smem, st>>>(
+            mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nsu, batch, ds->data[0].as<double>(), h->d_loss.as<double>(),
+            h->d_grad_each.as<double>(), nullptr, h->d_nsaved.as<int>(), h->d_ret.as<int>(), nullptr, queue, d_order + s * batch, d_mp);
+      else
+        k_tsit5_sens<C, 1, WARPS, (WPT == 1 ? 2 : 1), true, WPT, false, true><<<blocks, WARPS * 32, smem, st>>>(
+            mp, sp, d_rows, d_desc, ncol, ds->u0[0].as<double>(), nsu, batch, ds->data[0].as<double>(), h->d_loss.as<double>(),
+            h->d_grad_each.as<double>(), nullptr, h->d_nsaved.as<int>(), h->d_ret.as<int>(), nullptr, queue, d_order + s * batch,
+            nullptr, nullptr, d_mp);
       k_grad_reduce<<<nb_red, 256, 0, st>>>(h->d_grad_each.as<double>(), batch, NP, h->partial.as<double>(), d_gsum,
                                             reinterpret_cast<unsigned int*>(h->ctr.as<unsigned long long>() + 1));
       k_train_loss_sum<<<1, 256, 0, st>>>(h->d_loss.as<double>(), batch, d_lsum);

@@ -32,7 +32,8 @@ struct alignas(16) RosWarpBuf {
   double rp[C::NS][8];                    // partial row sums of the norm reduction (RP lanes share one row of `red`)
 };
 
-template <class C, int CT, int WARPS, int MINB>
+// DEVW = true: weights come from device memory (mp_dev, written by a p2vec kernel of the on-device training loop, kernel_train.cuh)
+template <class C, int CT, int WARPS, int MINB, bool DEVW = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant__ SolveP<C> sp,
                     const double* __restrict__ seed_dev, const R1Desc* __restrict__ desc_dev, int ncol,
@@ -40,7 +41,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
                     const double* __restrict__ data, double* __restrict__ loss, double* __restrict__ grad_each,
                     double* __restrict__ pred, int* __restrict__ n_saved, int* __restrict__ retcode,
                     crnn_stats* __restrict__ stats, unsigned long long* __restrict__ queue,
-                    const long long* __restrict__ in_idx) {
+                    const long long* __restrict__ in_idx, const ModelP<C>* __restrict__ mp_dev = nullptr) {
   constexpr int NS = C::NS, NR = C::NR, N = C::N, NIN = C::NIN;
   static_assert(NS <= 6, "per-lane register LU");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -50,8 +51,14 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
   RosWarpBuf<C, CT>& wb = wbs[warp];
 
   for (int q = threadIdx.x; q < 2 * NR * 32 * CT; q += blockDim.x) (&sm.seed[0][0])[q] = seed_dev[q];
-  for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = mp.w_in[q];
-  for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = mp.w_b[q];
+  if (DEVW) {
+    for (int q = threadIdx.x; q < (int)(sizeof(ModelP<C>) / sizeof(double)); q += blockDim.x)
+      reinterpret_cast<double*>(&sm.mpw)[q] = reinterpret_cast<const double*>(mp_dev)[q];
+    __syncthreads();
+  }
+  const ModelP<C>& M = DEVW ? sm.mpw : mp;   // compile-time choice: shared-memory loads or constant-bank operands
+  for (int q = threadIdx.x; q < NIN * NR; q += blockDim.x) sm.w_in[q] = M.w_in[q];
+  for (int q = threadIdx.x; q < NR; q += blockDim.x) sm.w_b[q] = M.w_b[q];
   for (int q = threadIdx.x; q < N; q += blockDim.x) {
     sm.inv_ys[q] = sp.inv_yscale[q];
     sm.row2obs[q] = sp.row2obs[q];
@@ -88,7 +95,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
 
     double U[CT][NS], Y[CT][NS], KO[CT][NS];
     double Tval = 0.0, xT = 0.0, mybT = 0.0, my_sk = 1.0, my_u0 = 0.0;
-    if (C::KIND == 1) { Tval = __ldg(u0t + NS); xT = -1.0 / (mp.gas_R * Tval); }
+    if (C::KIND == 1) { Tval = __ldg(u0t + NS); xT = -1.0 / (M.gas_R * Tval); }
     if (lane < NR) {
       mybT = sm.w_b[lane];
       if (C::KIND == 1) mybT = fma(sm.w_in[NS + NIN * lane], xT, mybT);
@@ -142,8 +149,8 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
         __syncwarp();
         if (lane < NS) {
           const double yi = wb.y[lane];
-          const double uc = clampd(yi, mp.lb, mp.ub);
-          const bool inside = (yi >= mp.lb) && (yi <= mp.ub);
+          const double uc = clampd(yi, M.lb, M.ub);
+          const bool inside = (yi >= M.lb) && (yi <= M.ub);
           wb.x[lane] = lean_log(uc);
           wb.dx[lane] = inside ? __drcp_rn(uc) : 0.0;
         }
@@ -170,7 +177,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             for (int j = 0; j < NR; ++j) {
               double zd = fma(sm.seed[j][lc], xin, sm.seed[NR + j][lc]);
 #pragma unroll
-              for (int i = 0; i < NS; ++i) zd = fma(mp.w_in[i + NIN * j], Y[tt][i] * dx[i], zd);
+              for (int i = 0; i < NS; ++i) zd = fma(M.w_in[i + NIN * j], Y[tt][i] * dx[i], zd);
               if (isval[tt]) zd = 1.0;
               q[j] = r[j] * zd;
             }
@@ -179,7 +186,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             for (int i = 0; i < NS; ++i) {
               double s = 0.0;
 #pragma unroll
-              for (int j = 0; j < NR; ++j) s = fma(mp.w_out[i + NS * j], q[j], s);
+              for (int j = 0; j < NR; ++j) s = fma(M.w_out[i + NS * j], q[j], s);
               if (d_iout[tt] == i) s += ro;
               KO[tt][i] = s;
             }
@@ -217,7 +224,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             for (int l = 0; l < NS; ++l) {
               double s = 0.0;
 #pragma unroll
-              for (int j = 0; j < NR; ++j) s = fma(mp.w_out[i + NS * j] * r0[j], mp.w_in[l + NIN * j], s);
+              for (int j = 0; j < NR; ++j) s = fma(M.w_out[i + NS * j] * r0[j], M.w_in[l + NIN * j], s);
               W[i][l] = (i == l ? 1.0 : 0.0) - gam * (s * dx0[l]);
             }
           ++n_jac;
@@ -257,7 +264,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
             r0[j] = wb.r0[j];
             double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) a = fma(mp.w_in[i + NIN * j], v[i] * dx0[i], a);
+            for (int i = 0; i < NS; ++i) a = fma(M.w_in[i + NIN * j], v[i] * dx0[i], a);
             aj[j] = a;
           }
 #pragma unroll
@@ -276,7 +283,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
                 double ad = sa * vdx_in;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
-                  const double w = mp.w_in[i + NIN * j];
+                  const double w = M.w_in[i + NIN * j];
                   const double sdx = U[tt][i] * dx0[i];
                   zd = fma(w, sdx, zd);
                   ad = fma(w, -(v[i] * dx0[i]) * sdx, ad);  // v_i * d2x_i * S_i
@@ -296,7 +303,7 @@ k_rosenbrock23_sens(const __grid_constant__ ModelP<C> mp, const __grid_constant_
               for (int i = 0; i < NS; ++i) {
                 double s = 0.0;
 #pragma unroll
-                for (int j = 0; j < NR; ++j) s = fma(mp.w_out[i + NS * j], q2[j], s);
+                for (int j = 0; j < NR; ++j) s = fma(M.w_out[i + NS * j], q2[j], s);
                 if (d_iout[tt] == i) s += djo;
                 KO[tt][i] = fma(gam, s, KO[tt][i]);
               }

@@ -10,6 +10,7 @@
 #pragma once
 #include "crnn_dev.cuh"
 #include "kernel_tsit5_sens.cuh"
+#include "kernel_rosenbrock23_sens.cuh"
 
 namespace crnn {
 
@@ -124,6 +125,41 @@ __global__ void k_p2vec_case3(const double* __restrict__ p, double lb, double ub
     d.o = ((-a) * sg) * os;  desc[c_out] = d;                                  // d w_out[i,j] / d w_out_raw[i,j]; no w_in row
     d.o = (-ab) * os;        desc[c_in] = d;                                   // d w_out[i,j] / d w_in_raw[i,j]
     rows[j * COLS + c_in] = (a >= 0.0 && a <= 4.0) ? 1.0 : 0.0;                // clamp(dual): derivative 1 on the closed interval
+  }
+}
+
+// p2vec of robertson/rober_crnn.jl:85-96 (3 species, 6 reactions, np = 43: two column tiles, COLS = 64):
+//   slope = abs(p[end]);  w_b = p[1:nr] .* (10 slope);  w_in_raw = reshape(p[nr(ns+1)+1 : nr(2ns+1)], ns, nr);
+//   w_out = -w_in_raw .* 10 .^ reshape(p[nr+1 : nr(ns+1)], ns, nr);  w_in = clamp(w_in_raw, 0, 2.5);  out_scale = dydt_scale (:81-82,115)
+template <class C, int COLS>
+__global__ void k_p2vec_robertson(const double* __restrict__ p, double lb, double ub, const double* __restrict__ oscale,
+                                  ModelP<C>* __restrict__ mp, double* __restrict__ rows /* [2*NR][COLS] */, R1Desc* __restrict__ desc /* [COLS] */) {
+  constexpr int NS = C::NS, NR = C::NR, NIN = C::NIN;
+  static_assert(C::KIND == 0 && NIN == NS && 2 + NR * (2 * NS + 1) <= COLS, "an F0 model whose columns fit");
+  constexpr int K_SLOPE = NR * (2 * NS + 1);
+  const int t = threadIdx.x;
+  for (int q = t; q < 2 * NR * COLS; q += blockDim.x) rows[q] = 0.0;
+  for (int q = t; q < COLS; q += blockDim.x) { R1Desc d{}; d.o = 0.0; d.i_in = 0; d.i_out = 0; d.j_out = 0; d.pad = 0; desc[q] = d; }
+  __syncthreads();
+  if (t == 0) { mp->lb = lb; mp->ub = ub; mp->gas_R = 0.0; }
+  const double sgs = signbit(p[K_SLOPE]) ? -1.0 : 1.0, slope = p[K_SLOPE] * sgs;   // abs(dual): sign from signbit
+  if (t < NR) {
+    mp->w_b[t] = p[t] * (slope * 10.0);
+    rows[(NR + t) * COLS + (1 + t)] = slope * 10.0;
+    rows[(NR + t) * COLS + (1 + K_SLOPE)] = p[t] * (sgs * 10.0);
+  }
+  if (t < NS * NR) {
+    const int i = t % NS, j = t / NS;
+    const double os = oscale ? oscale[i] : 1.0;
+    const double a = p[NR * (NS + 1) + i + NS * j], b = p[NR + i + NS * j];   // w_in_raw, w_out_raw
+    const double v = pow(10.0, b);
+    mp->w_out[i + NS * j] = ((-a) * v) * os;
+    mp->w_in[i + NIN * j] = a > 2.5 ? 2.5 : (a < 0.0 ? 0.0 : a);
+    const int c_out = 1 + NR + i + NS * j, c_in = 1 + NR * (NS + 1) + i + NS * j;
+    R1Desc d{}; d.pad = 0; d.i_in = i; d.i_out = i; d.j_out = j;
+    d.o = ((-a) * (v * 2.302585092994046)) * os;  desc[c_out] = d;           // d w_out / d w_out_raw = -a 10^b ln 10; no w_in row
+    d.o = (-v) * os;                              desc[c_in] = d;            // d w_out / d w_in_raw
+    rows[j * COLS + c_in] = (a >= 0.0 && a <= 2.5) ? 1.0 : 0.0;               // clamp(dual): derivative 1 on the closed interval
   }
 }
 

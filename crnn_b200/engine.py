@@ -301,11 +301,12 @@ Engine.loss_grad_particles = _particles
 
 def _train_steps(self, model: CRNNModel, opts: SolveOpts, ds: Dataset, order, yscale, p, opt_state=None,
                  loss_kind=_abi.LOSS_MAE_SCALED, p2vec_kind=2, optimiser="adam", batch=1, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, expdecay=None, grad_max=None, p2vec_b0=-10.0):
+                 weight_decay=0.0, expdecay=None, grad_max=None, p2vec_b0=-10.0, n_save_used=None):
     """`crnn_train_steps`: the scripts' epoch loop (case2/case2.jl:192-198) entirely on the device - p2vec, solve +
     forward sensitivities, gradient reduction and the Flux optimiser chain enqueued back to back, nothing returning to the
     host between optimiser steps.  `order` [n_steps * batch] dataset rows (the host's randperm), `expdecay` =
-    (eta, decay, step, clip) or None, `opt_state` [2 np + 4] from a previous call (None: fresh).
+    (eta, decay, step, clip) or None, `opt_state` [2 np + 4] from a previous call (None: fresh), `n_save_used` [n_steps * batch]
+    the per-visit random truncation `sample = rand(batchsize:datasize)` of rober_crnn.jl:218 (None: all save points).
     -> dict(p, opt_state, step_loss [n_steps], step_gnorm [n_steps])."""
     cm, k1 = model.to_c()
     co, k2 = opts.to_c(model.n_state, False)
@@ -321,8 +322,14 @@ def _train_steps(self, model: CRNNModel, opts: SolveOpts, ds: Dataset, order, ys
     opt_state = np.array(opt_state, dtype=np.float64).reshape(-1)
     if opt_state.size != 2 * n_p + 4:
         raise ValueError("opt_state must be [2*np + 4]")
+    nsu = None
+    if n_save_used is not None:
+        nsu = np.ascontiguousarray(n_save_used, dtype=np.int32).reshape(-1)
+        if nsu.size != order.size:
+            raise ValueError("n_save_used must hold one entry per visited experiment (n_steps * batch)")
     t = _abi.CTrainOpts(int(p2vec_kind), {"adam": 0, "nadam": 1}[optimiser], int(batch), 0, eta, beta[0], beta[1], eps, weight_decay,
-                        ed[0], ed[1], ed[3], int(ed[2]), 0.0 if grad_max is None else float(grad_max), float(p2vec_b0))
+                        ed[0], ed[1], ed[3], int(ed[2]), 0.0 if grad_max is None else float(grad_max), float(p2vec_b0),
+                        None if nsu is None else nsu.ctypes.data)
     ys = self._host(np.asarray(yscale).reshape(-1), np.float64, (opts.n_obs(model.n_state),), "yscale")
     sl, sg = np.empty(n_steps), np.empty(n_steps)
     hp = lambda a: a.ctypes.data_as(C.c_void_p)

@@ -103,7 +103,7 @@ class CRNNProblem:
         return p, history
 
 
-    def train_on_device(self, p, n_epoch, n_exp_train, rng=None, batch=1, **optimiser):
+    def train_on_device(self, p, n_epoch, n_exp_train, rng=None, batch=1, sample_range=None, **optimiser):
         """The same epoch loop with every optimiser step ON the device (`crnn_train_steps`): one C call per epoch, the
         visiting order `randperm(n_exp_train)` (case2/case2.jl:194) drawn here.  `optimiser`: Engine.train_steps keywords
         (optimiser, eta, beta, weight_decay, expdecay, grad_max).  -> (p, history) like `train`."""
@@ -112,11 +112,12 @@ class CRNNProblem:
         model, _ = self.case.model(p, self.out_scale)
         state, history = None, []
         n_steps = n_exp_train // batch
-        optimiser.setdefault("p2vec_kind", {"case1": 1, "case2": 2, "case3": 3}.get(self.case.name, 0))   # the device p2vec kernels built
+        optimiser.setdefault("p2vec_kind", {"case1": 1, "case2": 2, "case3": 3, "robertson": 4}.get(self.case.name, 0))   # the device p2vec kernels built
         for epoch in range(n_epoch):
             order = rng.permutation(n_exp_train)[:n_steps * batch]
+            sample = None if sample_range is None else rng.integers(sample_range[0], sample_range[1] + 1, size=order.size)
             r = self.engine.train_steps(model, self.opts, self.dataset, order, self.yscale, p, state, self.case.loss_kind,
-                                        batch=batch, **optimiser)
+                                        batch=batch, n_save_used=sample, **optimiser)
             p, state = r["p"], r["opt_state"]
             model, seed = self.case.model(p, self.out_scale)
             losses = self.engine.loss_grad_indexed(model, self.opts, seed, self.dataset, self.yscale,

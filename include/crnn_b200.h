@@ -294,7 +294,8 @@ int crnn_loss_grad_indexed(crnn_handle* h, const crnn_model* m, const crnn_opts*
  * --------------------------------------------------------------------------------------------- */
 typedef struct crnn_train_opts {
   int32_t p2vec_kind;   /* which script's p2vec runs on the device: 1 = case1/case1.jl:70-78, 2 = case2/case2.jl:91-99,
-                           3 = case3/case3.jl:42-53 (model.out_scale = dy_std is folded in on the device) */
+                           3 = case3/case3.jl:42-53 (model.out_scale = dy_std is folded in on the device),
+                           4 = robertson/rober_crnn.jl:85-96 (opts.alg = Rosenbrock23, out_scale = dydt_scale) */
   int32_t optimiser;    /* 0 ADAM (+ weight_decay = ADAMW), 1 NADAM */
   int32_t batch;        /* experiments per optimiser step (the scripts: 1) */
   int32_t reserved;
@@ -304,10 +305,12 @@ typedef struct crnn_train_opts {
   int64_t expdecay_step;
   double grad_max;      /* > 0: clip the gradient's 2-norm (rober_crnn.jl:29,221) */
   double p2vec_b0;      /* p2vec_kind 1: the bias offset b0 of case1/case1.jl:70 (-10) */
+  const int32_t* n_save_used;  /* HOST [n_steps * batch] or NULL: per visited experiment, the number of save points its loss uses
+                                  (`sample = rand(batchsize:datasize)`, rober_crnn.jl:218; tspan ends at saveat[n - 1]) */
 } crnn_train_opts;
 
-/* n_steps optimiser steps; step s uses dataset rows order[s*batch .. (s+1)*batch).  Single-device handle, Tsit5 +
- * forward sensitivities.
+/* n_steps optimiser steps; step s uses dataset rows order[s*batch .. (s+1)*batch).  Single-device handle, forward
+ * sensitivities through Tsit5 (p2vec_kind 1-3) or Rosenbrock23 (p2vec_kind 4).
  *   m          dimensions, clamps, gas_R and out_scale of the model (weight pointers ignored: the device p2vec produces them)
  *   p          [np] in/out
  *   opt_state  [2*np + 4] in/out: ADAM m, v, beta1^t, beta2^t, ExpDecay's current eta and count

@@ -43,6 +43,7 @@ struct CTrainOpts
     expdecay_step::Int64
     grad_max::Float64
     p2vec_b0::Float64
+    n_save_used::Ptr{Int32}        # host [n_steps * batch] or C_NULL: `sample = rand(batchsize:datasize)` per visit (rober_crnn.jl:218)
 end
 
 mutable struct Engine
@@ -231,21 +232,25 @@ end
 The epoch loop `for i_exp in randperm(n_exp_train); grad = ForwardDiff.gradient(...); update!(opt, p, grad); end`
 (case2/case2.jl:192-198) with every optimiser step ON the device: `order` is the 1-based visiting order (the script's own
 `randperm`), `p` and `opt_state` (2np + 4: ADAM m, v, beta powers, ExpDecay eta and count) are updated in place.  The
-device runs the script's p2vec itself (`p2vec_kind` 2: case2.jl:91-99, 1: case1.jl:70-78, 3: case3.jl:42-53 with `s.out_scale = dy_std`), so no weights are passed.
+device runs the script's p2vec itself (`p2vec_kind` 2: case2.jl:91-99, 1: case1.jl:70-78, 3: case3.jl:42-53 with `s.out_scale = dy_std`, 4: rober_crnn.jl:85-96 with
+`s.alg = 1`, `s.out_scale = dydt_scale` and `sample` = the per-visit `rand(batchsize:datasize)`), so no weights are passed.
 """
 function train_steps!(e::Engine, s::Setup, ds::Dataset, order, p::Vector{Float64}, opt_state::Vector{Float64};
                       ns::Integer, nr::Integer, batch::Integer=1, optimiser::Integer=0, eta=1e-3, beta=(0.9, 0.999), eps=1e-8,
-                      weight_decay=0.0, expdecay=(0.0, 1.0, 0, 0.0), grad_max=0.0, p2vec_kind::Integer=2, p2vec_b0=-10.0)
+                      weight_decay=0.0, expdecay=(0.0, 1.0, 0, 0.0), grad_max=0.0, p2vec_kind::Integer=2, p2vec_b0=-10.0, sample=nothing)
     ord = Vector{Int64}(order .- 1); n_steps = div(length(ord), batch)
     step_loss = zeros(n_steps); step_gnorm = zeros(n_steps)
-    t = CTrainOpts(p2vec_kind, optimiser, batch, 0, eta, beta[1], beta[2], eps, weight_decay, expdecay[1], expdecay[2], expdecay[4],
-                   expdecay[3], grad_max, p2vec_b0)
+    nsu = sample === nothing ? Int32[] : Vector{Int32}(sample)     # one entry per visited experiment
     n_in = s.rhs_kind == 1 ? ns + 1 : ns
-    with_structs(s, zeros(n_in, nr), zeros(nr), zeros(ns, nr)) do m, o
-        check(e, ccall((:crnn_train_steps, LIB), Cint,
-              (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ref{CTrainOpts}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Int32,
-               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-              e.h, m, o, Ref(t), ds.d, ord, n_steps, yscale_of(s), s.loss_kind, p, opt_state, step_loss, step_gnorm))
+    GC.@preserve nsu begin
+        t = CTrainOpts(p2vec_kind, optimiser, batch, 0, eta, beta[1], beta[2], eps, weight_decay, expdecay[1], expdecay[2], expdecay[4],
+                       expdecay[3], grad_max, p2vec_b0, sample === nothing ? Ptr{Int32}(C_NULL) : pointer(nsu))
+        with_structs(s, zeros(n_in, nr), zeros(nr), zeros(ns, nr)) do m, o
+            check(e, ccall((:crnn_train_steps, LIB), Cint,
+                  (Ptr{Cvoid}, Ref{CModel}, Ref{COpts}, Ref{CTrainOpts}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Int32,
+                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                  e.h, m, o, Ref(t), ds.d, ord, n_steps, yscale_of(s), s.loss_kind, p, opt_state, step_loss, step_gnorm))
+        end
     end
     step_loss, step_gnorm
 end

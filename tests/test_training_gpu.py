@@ -142,10 +142,10 @@ def test_on_device_loop_case1_p2vec(engine, golden):
     from crnn_b200.engine import EngineError
     with pytest.raises(EngineError):
         engine.train_steps(model, prob.opts, prob.dataset, order[:2], prob.yscale, p, None, prob.case.loss_kind, p2vec_kind=2)
-    pbr = make_problem("robertson", golden, 4)                                 # no device p2vec for the robertson script
+    pbr = make_problem("robertson", golden, 4)                                 # the robertson loop integrates with Rosenbrock23
     probr = CRNNProblem("robertson", pbr["u0"], pbr["data"], pbr["yscale"], engine=engine, alg=_abi.ALG_TSIT5)
     with pytest.raises(EngineError):
-        engine.train_steps(pbr["model"], probr.opts, probr.dataset, np.arange(2), probr.yscale, np.zeros(43), None, probr.case.loss_kind)
+        engine.train_steps(pbr["model"], probr.opts, probr.dataset, np.arange(2), probr.yscale, np.zeros(43), None, probr.case.loss_kind, p2vec_kind=4)
     with pytest.raises(EngineError):                                           # dataset row out of range
         engine.train_steps(model, prob.opts, prob.dataset, np.array([99]), prob.yscale, p, None, prob.case.loss_kind, **kw)
 
@@ -186,6 +186,55 @@ def test_on_device_loop_case3_p2vec(engine, golden):
     # and the frontend's epoch loop picks the kernel by the case name
     p_end, hist = prob.train_on_device(p, n_epoch=2, n_exp_train=8, rng=g, optimiser="nadam", eta=0.001)
     assert np.isfinite([h[0] for h in hist]).all() and p_end.shape == (153,)
+
+
+def test_on_device_loop_robertson_p2vec(engine, golden):
+    """p2vec_kind = 4: robertson/rober_crnn.jl:85-96 on the device (slope = |p[end]|, w_b = p .* 10 slope, w_out = -w_in .* 10 .^ w_out,
+    w_in = clamp(w_in, 0, 2.5), dydt_scale folded in), the Rosenbrock23 sensitivity kernel reading weights and seed columns from
+    device memory, the per-visit truncation `sample = rand(batchsize:datasize)` (:218), the 2-norm clip (:220-223) and
+    ADAMW(0.005, (0.9, 0.999), 1e-6) (:19); every step against the host mirror from the same (p, state), from the reference's
+    committed checkpoint"""
+    from problems import make_problem
+    pb = make_problem("robertson", golden, 12)
+    prob = CRNNProblem("robertson", pb["u0"], pb["data"], pb["yscale"], out_scale=pb["model"].out_scale, engine=engine)
+    assert prob.opts.alg == _abi.ALG_ROSENBROCK23
+    g = np.random.default_rng(8)
+    p = np.array(golden["robertson"]["p"], dtype=np.float64)
+    opt = optim.ADAMW(0.005, (0.9, 0.999), 1e-6)
+    grad_max = 10.0                                                        # rober_crnn.jl:29
+    kw = dict(p2vec_kind=4, optimiser="adam", eta=0.005, beta=(0.9, 0.999), weight_decay=1e-6, grad_max=grad_max)
+    model, _ = prob.case.model(p, prob.out_scale)
+    st = None
+    order = np.concatenate([g.permutation(12) for _ in range(2)])
+    sample = g.integers(32, 41, size=order.size)                           # batchsize = 32, datasize = 40 (:21,218)
+    for s in range(20):
+        idx = order[s:s + 1]
+        loss, grad = prob.loss_grad(p, idx, sample=sample[s:s + 1])
+        gn = np.linalg.norm(grad)
+        gc, _ = optim.clip_by_norm(grad, grad_max)
+        p_host = p.copy(); opt.update(p_host, gc)
+        r = engine.train_steps(model, prob.opts, prob.dataset, idx, prob.yscale, p, st, prob.case.loss_kind, n_save_used=sample[s:s + 1], **kw)
+        np.testing.assert_allclose(r["step_loss"][0], loss, rtol=1e-10)
+        np.testing.assert_allclose(r["step_gnorm"][0], gn, rtol=1e-8)
+        np.testing.assert_allclose(r["p"], p_host, rtol=1e-9, atol=1e-12, err_msg=f"step {s}")
+        p, st = r["p"], r["opt_state"]
+        adam = opt.chain[0]
+        adam.m, adam.v = st[:43].copy(), st[43:86].copy()
+    # K steps in one call = K calls of one step; the frontend's epoch loop draws the truncation itself
+    kw["grad_max"] = 1e-3                                                  # every step clipped
+    r_a = engine.train_steps(model, prob.opts, prob.dataset, order[:6], prob.yscale, p, st, prob.case.loss_kind, batch=2, n_save_used=sample[:6], **kw)
+    assert (r_a["step_gnorm"] > 1e-3).all()
+    q, stq = p, st
+    for k in range(3):
+        r_k = engine.train_steps(model, prob.opts, prob.dataset, order[2 * k:2 * k + 2], prob.yscale, q, stq, prob.case.loss_kind, batch=2,
+                                 n_save_used=sample[2 * k:2 * k + 2], **kw)
+        q, stq = r_k["p"], r_k["opt_state"]
+    assert np.array_equal(r_a["p"], q) and np.array_equal(r_a["opt_state"], stq)
+    with pytest.raises(Exception):
+        engine.train_steps(model, prob.opts, prob.dataset, order[:2], prob.yscale, p, st, prob.case.loss_kind, n_save_used=np.array([0, 41]), **kw)
+    p_end, hist = prob.train_on_device(p, n_epoch=2, n_exp_train=10, rng=g, sample_range=(32, 40), optimiser="adam", eta=0.005,
+                                       weight_decay=1e-6, grad_max=grad_max)
+    assert np.isfinite([h[0] for h in hist]).all() and p_end.shape == (43,)
 
 
 def test_on_device_epochs_descend(engine):

@@ -89,5 +89,10 @@ from problems import trained_p
 eng.train_steps(pb3["model"], pb3["opts"], ds3, np.arange(6), pb3["yscale"], trained_p("case3", golden), None, pb3["loss_kind"],
                 p2vec_kind=3, optimiser="nadam", batch=2)
 ds3.close(); done.append("train_steps case3 (five warps per trajectory)")
+pbr = make_problem("robertson", golden, 6)
+dsr = eng.dataset(pbr["u0"], pbr["data"])
+eng.train_steps(pbr["model"], pbr["opts"], dsr, np.arange(6), pbr["yscale"], np.array(golden["robertson"]["p"]), None, pbr["loss_kind"],
+                p2vec_kind=4, batch=2, grad_max=10.0, n_save_used=np.array([35, 40, 32, 33, 36, 38]))
+dsr.close(); done.append("train_steps robertson (Rosenbrock23 sensitivities)")
 eng.close()
 print("sanitize_small ok:", "; ".join(done))
