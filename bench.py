@@ -236,8 +236,10 @@ def _timed(fn, steps, world, dev):
     for _ in range(3):          # W >= 3 warm-up calls
         fn()
     ms, r = once(steps)
-    if ms < 50.0:               # a short step: a single allocator / page-in hiccup would dominate two steps - time twenty
-        ms, r = once(max(steps, 20))
+    if ms < 50.0:               # a short step: a single allocator / page-in hiccup would dominate two steps - time twenty,
+        ms, r = once(max(steps, 20))          # twice, and keep the quieter block (these are the `configs` extras, not the headline)
+        ms2, r = once(max(steps, 20))
+        ms = min(ms, ms2)
     return ms, r
 
 
