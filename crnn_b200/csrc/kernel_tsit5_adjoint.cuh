@@ -153,8 +153,10 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
       double sacc = 0.0;
       if (lane < dout) {
         const double* al = A_(l);
-        for (int i = 0; i < din; ++i) sacc = fma(w[lane + dout * i], al[i], sacc);
-        sacc += w[din * dout + lane];
+        const double* wp = w + lane;
+#pragma unroll 4
+        for (int i = 0; i < din; ++i, wp += dout) sacc = fma(*wp, al[i], sacc);
+        sacc += *wp;
         // the activation and, for the way back, its derivative at the pre-activation (gelu' in NNlib's tanh form, softplus' = sigma, exp' = exp)
         if (l + 1 < ML) {
           const double x = sacc;
@@ -422,6 +424,7 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
           if (lane < din) {
             const double* wl = s_mw + woff + dout * lane;
             const double* dl_l = DL_(l);
+#pragma unroll 4
             for (int k = 0; k < dout; ++k) sacc = fma(wl[k], dl_l[k], sacc);
           }
           if (l > 0) {
