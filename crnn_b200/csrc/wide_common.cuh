@@ -204,8 +204,10 @@ __device__ __forceinline__ double wide_mlp_aug(const WideP& P, WW& ww, int lane,
     __syncwarp();
     double s = 0.0;
     if (lane < dout) {
-      for (int i = 0; i < din; ++i) s = fma(__ldg(w + lane + dout * i), ww.bchi[i], s);
-      s += __ldg(w + din * dout + lane);
+      const double* wp = w + lane;
+#pragma unroll 4
+      for (int i = 0; i < din; ++i, wp += dout) s = fma(__ldg(wp), ww.bchi[i], s);
+      s += __ldg(wp);
       if (l + 1 < P.mlp_layers) {
         const double th = 1.0 - 2.0 / (lean_exp(2.0 * (0.7978845608028654 * (s + 0.044715 * (s * s * s)))) + 1.0);
         s = 0.5 * s * (1.0 + th);
