@@ -1,5 +1,5 @@
 """The CPU oracle under AddressSanitizer + UBSan: every algorithm, RHS flavour and sensitivity mode on small batches.
-  gcc -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fopenmp -fPIC -std=gnu11 -shared -o /tmp/liboracle_asan.so oracle/crnn_oracle.c -lm
+  gcc -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fopenmp -fPIC -std=gnu11 -ffp-contract=off -shared -o /tmp/liboracle_asan.so oracle/crnn_oracle.c oracle/lean_math_host.c -lm
   LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 python tools/asan_oracle.py
 (rounds 1 and 2, incl. TRBDF2, F4 and the F4 adjoint: clean)"""
 import sys, json
