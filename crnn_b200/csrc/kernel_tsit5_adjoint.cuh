@@ -136,8 +136,8 @@ k_tsit5_adjoint(const __grid_constant__ AdjP P, const double* __restrict__ u0, c
   auto rec_ptr = [&](int step) -> double* {
     return step < P.cap_s ? rec_s + (size_t)step * stride : rec_g + (size_t)(step - P.cap_s) * stride;
   };
-  // F4: the Flux chain of the state y (lane i holds y_i), lane k = neuron k, activations a_l and pre-activations s_l kept in the
-  // per-warp arrays for the way back; returns the value of augmented input row `lane` (state row or MLP output).  Same
+  // F4: the Flux chain of the state y (lane i holds y_i), lane k = neuron k, activations a_l and activation derivatives act'_l kept in
+  // the per-warp arrays for the way back; returns the value of augmented input row `lane` (state row or MLP output).  Same
   // arithmetic as wide_mlp_aug / the oracle's mlp_eval.
   auto mlp_aug = [&](double y) -> double {
     __syncwarp();
